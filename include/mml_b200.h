@@ -1,0 +1,156 @@
+/* mml_b200.h -- C ABI of libmml_b200.so: the B200 (sm_100a) kernels behind MML_Suite's late-fusion training step.
+ *
+ * The reference (TArsenii/task-specific-pretraining-multimodal, directory MML_Suite/) is pure PyTorch: it has no
+ * native code and therefore no FFI of its own.  The boundary below is what a binding for the hot path replaces, op by
+ * op; every entry point cites the reference call it stands in for (paths relative to MML_Suite/).  The Python host
+ * side (task-specific-pretraining-multimodal_b200/*.py) binds these with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.  All tensor memory is caller-owned DEVICE memory.
+ *   - activations: NHWC bf16 (uint16_t storage).  conv weights: K,R,S,C ("KRSC", == torch channels_last of OIHW).
+ *   - every kernel is enqueued on `stream` (a cudaStream_t passed as void*) and never synchronises, so a whole
+ *     training step can be captured into a CUDA graph.
+ *   - return value: 0 on success, negative mml_status on failure; text via mml_last_error().  Never throws/aborts.
+ *   - one ctx per (process, device); not re-entrant.
+ */
+#ifndef MML_B200_H
+#define MML_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mml_ctx mml_ctx;
+
+enum mml_status {
+  MML_OK = 0,
+  MML_ERR_INVALID = -1,     /* bad argument / unsupported geometry */
+  MML_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed */
+  MML_ERR_UNSUPPORTED = -3, /* not an sm_100 device, missing driver entry point, ... */
+};
+
+/* conv geometry: x [N,H,W,C] -> y [N,P,Q,K], filter K x R x S x C, P = (H + 2*pad - R)/stride + 1 (nn.Conv2d, bias=False) */
+typedef struct mml_conv_geom {
+  int32_t N, H, W, C; /* input */
+  int32_t K, R, S;    /* filter */
+  int32_t stride, pad;
+} mml_conv_geom;
+
+/* ---- context ------------------------------------------------------------------------------------------------- */
+int mml_version(void);
+int mml_ctx_create(int device, mml_ctx** out);
+void mml_ctx_destroy(mml_ctx* ctx);
+const char* mml_last_error(const mml_ctx* ctx); /* ctx may be NULL: error of a failed mml_ctx_create */
+int mml_ctx_sm_count(const mml_ctx* ctx);
+/* number of kernels this library has launched since the ctx was created (bench.py's gpu_launches) */
+int64_t mml_ctx_launch_count(const mml_ctx* ctx);
+
+/* ---- a1: missing-modality mask -- data/base_dataset.py:70-72  sample[mod] = original * mask -------------------- */
+/* y[b, :] = x[b, :] * mask[b]   (true IEEE multiply, bit-exact with torch CPU); reverse: x * -1 * (mask - 1) */
+int mml_mask_apply_f32(mml_ctx*, const float* x, const float* mask, float* y, float* y_reverse, int64_t batch,
+                       int64_t per_sample, void* stream);
+
+/* ---- a2/a3: ResNetEncoder stem -- models/msa/networks/resnet.py:137 conv1 (7x7, stride 2, pad 3, C_in = 1) ----- */
+/* x fp32 [B,H,W] (optionally multiplied by mask[b], same multiply as above), w fp32 [64][7][7] ->
+ * y bf16 [B,P,Q,64]; stats_partial [mml_stem_stat_tiles][64][2] = per-tile (sum, sum of squares) of the stored y */
+int mml_stem_stat_tiles(int B, int H, int W);
+int mml_stem_fprop(mml_ctx*, const float* x, const float* mask, const float* w, uint16_t* y, float* stats_partial, int B,
+                   int H, int W, void* stream);
+/* dw fp32 [64][49] = sum_{b,p,q} dy[b,p,q,k] * (x*mask)[b, 2p+r-3, 2q+s-3]  (overwrites dw) */
+int mml_stem_wgrad(mml_ctx*, const float* x, const float* mask, const uint16_t* dy, float* dw, float* workspace,
+                   int64_t workspace_bytes, int B, int H, int W, void* stream);
+int64_t mml_stem_wgrad_workspace(const mml_ctx*, int B, int H, int W);
+
+/* ---- a2-a4: 3x3 / 1x1 convolutions -- resnet.py:25,30,176 (nn.Conv2d fwd) and their autograd -------------------- */
+/* tcgen05 implicit GEMM.  fprop: y = conv(x, w); optional stats_partial [mml_conv_stat_tiles][K][2] */
+int mml_conv_stat_tiles(const mml_conv_geom* g);
+int mml_conv_fprop(mml_ctx*, const mml_conv_geom* g, const uint16_t* x, const uint16_t* w_krsc, uint16_t* y,
+                   float* stats_partial, void* stream);
+/* dgrad: dx [N,H,W,C] = conv_transpose(dy [N,P,Q,K], w); w_crsk is the transposed copy W_t[c][r][s][k] = W[k][r][s][c] */
+int mml_conv_dgrad(mml_ctx*, const mml_conv_geom* g, const uint16_t* dy, const uint16_t* w_crsk, uint16_t* dx, void* stream);
+/* wgrad: dw_krsc fp32 [K][R][S][C] += sum_{n,p,q} dy * x   (ACCUMULATES: caller zeroes the gradient buffer) */
+int mml_conv_wgrad(mml_ctx*, const mml_conv_geom* g, const uint16_t* x, const uint16_t* dy, float* dw_krsc, void* stream);
+
+/* ---- a5: BatchNorm2d (train / eval) + ReLU + residual -- resnet.py:26,31,138,177 and BasicBlock.forward :37-54 --- */
+/* reduce per-tile partials -> batch mean / biased var; scale = gamma*invstd, shift = beta - mean*scale;
+ * running = (1-m)*running + m*batch (unbiased var); saves mean / invstd for backward */
+int mml_bn_finalize(mml_ctx*, const float* stats_partial, int tiles, int C, int64_t count, const float* gamma,
+                    const float* beta, float* running_mean, float* running_var, float momentum, float eps, float* scale,
+                    float* shift, float* save_mean, float* save_invstd, void* stream);
+/* eval mode: scale/shift from running statistics */
+int mml_bn_eval_coeffs(mml_ctx*, int C, const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, float* scale, float* shift, void* stream);
+/* y = act(x*scale + shift [+ res*rscale + rshift]); res may be NULL; rscale NULL => identity residual */
+int mml_bn_act_fwd(mml_ctx*, const uint16_t* x, const float* scale, const float* shift, const uint16_t* res,
+                   const float* rscale, const float* rshift, uint16_t* y, int64_t rows, int C, int relu, void* stream);
+/* backward of y = relu?(bn(x) [+ r]):  g = (dy1 [+ dy2]) * (y > 0 if relu);
+ * reduce: partial [blocks][C][2] = (sum g, sum g*xhat);   blocks = mml_bn_bwd_blocks() */
+int mml_bn_bwd_blocks(const mml_ctx*, int64_t rows, int C);
+int mml_bn_bwd_reduce(mml_ctx*, const uint16_t* dy1, const uint16_t* dy2, const uint16_t* y, const uint16_t* x,
+                      const float* mean, const float* invstd, float* partial, int64_t rows, int C, int relu, void* stream);
+/* dgamma = sum g*xhat, dbeta = sum g (written, not accumulated); coef [3][C] for the apply pass */
+int mml_bn_bwd_finalize(mml_ctx*, const float* partial, int blocks, int C, int64_t count, const float* gamma,
+                        const float* invstd, float* dgamma, float* dbeta, float* coef, void* stream);
+/* dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) as bf16; g_out (optional) = g as bf16 (gradient of the skip path) */
+int mml_bn_bwd_apply(mml_ctx*, const uint16_t* dy1, const uint16_t* dy2, const uint16_t* y, const uint16_t* x,
+                     const float* mean, const float* invstd, const float* coef, uint16_t* dx, uint16_t* g_out, int64_t rows,
+                     int C, int relu, void* stream);
+
+/* ---- pooling -- resnet.py:140 MaxPool2d(3,2,1), :149 AdaptiveAvgPool2d((1,1)) ---------------------------------- */
+int mml_maxpool3x3s2_fwd(mml_ctx*, const uint16_t* x, uint16_t* y, uint8_t* argmax, int N, int H, int W, int C, void* stream);
+int mml_maxpool3x3s2_bwd(mml_ctx*, const uint16_t* dy, const uint8_t* argmax, uint16_t* dx, int N, int H, int W, int C,
+                         void* stream);
+int mml_avgpool_fwd(mml_ctx*, const uint16_t* x, float* y, int N, int HW, int C, void* stream);
+int mml_avgpool_bwd(mml_ctx*, const float* dy, uint16_t* dx, int N, int HW, int C, void* stream);
+
+/* ---- a6/a7: encoder fc x2 + concat + fusion MLP + dropout + softmax-CE -- avmnist.py:219-267, loss.py:98-148 ----- */
+typedef struct mml_head_params {
+  /* fp32 device pointers, torch nn.Linear layout [out][in] */
+  const float *fcA_w, *fcA_b; /* [EA][FA] */
+  const float *fcI_w, *fcI_b; /* [EI][FI] */
+  const float *w0, *b0;       /* [H1][EA+EI]  net.0 */
+  const float *w3, *b3;       /* [H2][H1]     net.3 */
+  const float *w5, *b5;       /* [NC][H2]     net.5 */
+  int32_t FA, FI, EA, EI, H1, H2, NC;
+} mml_head_params;
+typedef struct mml_head_grads {
+  float *fcA_w, *fcA_b, *fcI_w, *fcI_b, *w0, *b0, *w3, *b3, *w5, *b5; /* written (not accumulated) */
+} mml_head_grads;
+/* scratch: fp32 [B][mml_head_scratch_per_sample()] kept between fwd and bwd */
+int mml_head_scratch_per_sample(const mml_head_params* p);
+/* pooledA [B][FA], pooledI [B][FI] fp32; labels int64 [B] (may be NULL: no loss); dropout_mask uint8 [B][H1] or NULL;
+ * dropout_scale = 1/(1-p).  Outputs: logits [B][NC], loss_out[0] = mean CE, pred int32 [B] (argmax of softmax) */
+int mml_head_fwd(mml_ctx*, const mml_head_params* p, const float* pooledA, const float* pooledI, const int64_t* labels,
+                 const uint8_t* dropout_mask, float dropout_scale, float* scratch, float* logits, float* loss_out,
+                 int32_t* pred, int B, void* stream);
+/* backward of mean CE: fills weight grads, dpooledA [B][FA], dpooledI [B][FI].  loss_scale multiplies dlogits. */
+int mml_head_bwd(mml_ctx*, const mml_head_params* p, const mml_head_grads* g, const float* pooledA, const float* pooledI,
+                 const int64_t* labels, const uint8_t* dropout_mask, float dropout_scale, float* scratch,
+                 float loss_scale, float* dpooledA, float* dpooledI, int B, void* stream);
+/* Philox-free counter RNG for the throughput path: mask[i] = hash(seed, *step_counter, i) >= p ? 1 : 0 */
+int mml_dropout_mask(mml_ctx*, uint8_t* mask, int64_t n, float p, uint64_t seed, const int64_t* step_counter, void* stream);
+
+/* ---- a9: torch.optim.Adam (coupled weight decay) over the flat parameter buffer -- avmnist.py:303 ---------------- */
+/* hyper (device, fp32[8]): lr, beta1, beta2, eps, weight_decay, grad_scale, -, -;  step (device int64[1]) is
+ * incremented by the kernel (so a captured graph advances it).  p/g/m/v fp32 [n]; p_bf16 (optional) gets bf16(p). */
+int mml_adam_step(mml_ctx*, float* p, const float* g, float* m, float* v, uint16_t* p_bf16, int64_t n, const float* hyper,
+                  int64_t* step, void* stream);
+/* fp32 -> bf16 copy (shadow refresh after load_state_dict) */
+int mml_cast_f32_bf16(mml_ctx*, const float* src, uint16_t* dst, int64_t n, void* stream);
+/* batched KRSC -> CRSK transposes of the bf16 shadow weights (dgrad operand).  table (device int64[n_convs][6]):
+ * src_off, dst_off (elements), K, RS, C, first_block;  total_blocks = sum of per-conv blocks (see binding) */
+int mml_weights_transpose(mml_ctx*, const uint16_t* src, uint16_t* dst, const int64_t* table, int n_convs, int total_blocks,
+                          void* stream);
+
+/* ---- a13: FedAvg weighted aggregation (no reference implementation exists; McMahan et al.) ---------------------- */
+/* out[i] = sum_k weights[k] * clients[k][i];  clients: DEVICE array of K device pointers; weights: device fp32[K] */
+int mml_fedavg(mml_ctx*, const float* const* clients, const float* weights, int K, float* out, int64_t n, void* stream);
+/* in-place scale (pre-scale for the allreduce variant): x *= weights[idx] */
+int mml_scale_inplace(mml_ctx*, float* x, const float* weights, int idx, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MML_B200_H */

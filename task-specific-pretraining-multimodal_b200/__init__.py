@@ -1,0 +1,14 @@
+"""mml_b200 -- B200 (sm_100a) native late-fusion multimodal training step behind MML_Suite's model surface.
+
+Sub-modules (imported lazily so that ``import mml_b200`` works on a CPU-only box for host-side logic and tests):
+  _lib      ctypes binding of libmml_b200.so (C ABI in include/mml_b200.h); raises if the library is missing
+  ops       torch-tensor wrappers over the C ABI
+  resnet    ResNetEncoder / ResNet18 / ResNet34 (same ctor, state_dict and forward contract as the reference)
+  avmnist   AVMNIST late-fusion model: forward / train_step / validation_step / get_embeddings
+  engine    the fused training / inference step (static buffers, kernel schedule, CUDA graph)
+  data      missing-modality patterns and on-device mask application
+  dist      one-process-per-GPU data parallelism (NCCL) with bucketed gradient allreduce
+  fedavg    FedAvg weighted aggregation
+  shim      registration under the reference's YAML tags / model resolver
+"""
+__version__ = "0.1.0"

@@ -1,0 +1,49 @@
+// mml_ctx.h -- per-device context of libmml_b200.so (internal).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mml_b200.h"
+
+typedef CUresult (*mml_tmap_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct mml_ctx {
+  int device;
+  int sm_count;
+  int64_t launches;
+  mml_tmap_encode_tiled_fn encode_tiled;
+  char err[512];
+};
+
+int mml_set_error(mml_ctx* ctx, int code, const char* fmt, ...);
+
+#define MML_CHECK_CUDA(ctx, expr)                                                                          \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess)                                                                                 \
+      return mml_set_error(ctx, MML_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define MML_REQUIRE(ctx, cond, ...)                                        \
+  do {                                                                     \
+    if (!(cond)) return mml_set_error(ctx, MML_ERR_INVALID, __VA_ARGS__);  \
+  } while (0)
+
+// after a <<< >>> launch: count it and surface launch-configuration errors
+#define MML_LAUNCHED(ctx)                                                                               \
+  do {                                                                                                  \
+    (ctx)->launches++;                                                                                  \
+    cudaError_t _e = cudaPeekAtLastError();                                                             \
+    if (_e != cudaSuccess) {                                                                            \
+      cudaGetLastError();                                                                               \
+      return mml_set_error(ctx, MML_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+    }                                                                                                   \
+  } while (0)
+
+static inline int64_t mml_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -1,0 +1,247 @@
+"""Thin torch-tensor wrappers over the C ABI (include/mml_b200.h).
+
+PyTorch is used here for device memory and streams only: every function checks dtype / device / contiguity, passes
+raw device pointers and the CURRENT torch stream to libmml_b200.so and returns.  No function here computes anything
+in PyTorch; if the library is missing the import of ``_lib`` raises -- there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import ConvGeom, Context, HeadGrads, HeadParams, MMLError
+
+BF16 = torch.bfloat16
+
+
+def _ctx(t: torch.Tensor) -> Context:
+    if not t.is_cuda:
+        raise MMLError("mml_b200 ops need CUDA tensors (no CPU path)")
+    return Context.get(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _stream(t: torch.Tensor) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor], dtype=None) -> C.c_void_p:
+    if t is None:
+        return C.c_void_p(0)
+    if dtype is not None and t.dtype != dtype:
+        raise MMLError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise MMLError("tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def conv_out_hw(H: int, W: int, R: int, S: int, stride: int, pad: int) -> Tuple[int, int]:
+    return (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+
+
+def make_geom(N, H, W, Cin, K, R, S, stride, pad) -> ConvGeom:
+    return ConvGeom(int(N), int(H), int(W), int(Cin), int(K), int(R), int(S), int(stride), int(pad))
+
+
+# ---- a1 ------------------------------------------------------------------------------------------------------
+def mask_apply(x: torch.Tensor, mask: torch.Tensor, want_reverse: bool = False):
+    """sample = original * mask  (data/base_dataset.py:71); x fp32 [B, ...], mask fp32 [B]."""
+    ctx = _ctx(x)
+    B = x.shape[0]
+    per = x.numel() // max(B, 1)
+    y = torch.empty_like(x)
+    yr = torch.empty_like(x) if want_reverse else None
+    ctx.check(ctx.lib.mml_mask_apply_f32(ctx.handle, _p(x, torch.float32), _p(mask, torch.float32), _p(y), _p(yr), B, per, _stream(x)), "mask_apply")
+    return (y, yr) if want_reverse else y
+
+
+# ---- stem ----------------------------------------------------------------------------------------------------
+def stem_stat_tiles(B, H, W) -> int:
+    from ._lib import load_library
+
+    return load_library().mml_stem_stat_tiles(B, H, W)
+
+
+def stem_fprop(x, mask, w, y, stats_partial) -> None:
+    ctx = _ctx(x)
+    B, H, W = x.shape
+    ctx.check(ctx.lib.mml_stem_fprop(ctx.handle, _p(x, torch.float32), _p(mask, torch.float32), _p(w, torch.float32), _p(y, BF16),
+                                     _p(stats_partial, torch.float32), B, H, W, _stream(x)), "stem_fprop")
+
+
+def stem_wgrad_workspace(x) -> int:
+    ctx = _ctx(x)
+    B, H, W = x.shape
+    return int(ctx.lib.mml_stem_wgrad_workspace(ctx.handle, B, H, W))
+
+
+def stem_wgrad(x, mask, dy, dw, workspace) -> None:
+    ctx = _ctx(x)
+    B, H, W = x.shape
+    ctx.check(ctx.lib.mml_stem_wgrad(ctx.handle, _p(x, torch.float32), _p(mask, torch.float32), _p(dy, BF16), _p(dw, torch.float32),
+                                     _p(workspace, torch.float32), workspace.numel() * 4, B, H, W, _stream(x)), "stem_wgrad")
+
+
+# ---- conv ----------------------------------------------------------------------------------------------------
+def conv_stat_tiles(g: ConvGeom) -> int:
+    from ._lib import load_library
+
+    return load_library().mml_conv_stat_tiles(C.byref(g))
+
+
+def conv_fprop(g: ConvGeom, x, w_krsc, y, stats_partial=None) -> None:
+    ctx = _ctx(x)
+    ctx.check(ctx.lib.mml_conv_fprop(ctx.handle, C.byref(g), _p(x, BF16), _p(w_krsc, BF16), _p(y, BF16), _p(stats_partial, torch.float32),
+                                     _stream(x)), "conv_fprop")
+
+
+def conv_dgrad(g: ConvGeom, dy, w_crsk, dx) -> None:
+    ctx = _ctx(dy)
+    ctx.check(ctx.lib.mml_conv_dgrad(ctx.handle, C.byref(g), _p(dy, BF16), _p(w_crsk, BF16), _p(dx, BF16), _stream(dy)), "conv_dgrad")
+
+
+def conv_wgrad(g: ConvGeom, x, dy, dw_krsc) -> None:
+    ctx = _ctx(x)
+    ctx.check(ctx.lib.mml_conv_wgrad(ctx.handle, C.byref(g), _p(x, BF16), _p(dy, BF16), _p(dw_krsc, torch.float32), _stream(x)), "conv_wgrad")
+
+
+# ---- batch norm / activations / pooling ---------------------------------------------------------------------------
+def bn_finalize(partial, tiles, Cn, count, gamma, beta, rmean, rvar, momentum, eps, scale, shift, save_mean, save_invstd) -> None:
+    ctx = _ctx(partial)
+    ctx.check(ctx.lib.mml_bn_finalize(ctx.handle, _p(partial, torch.float32), tiles, Cn, count, _p(gamma), _p(beta), _p(rmean), _p(rvar),
+                                      momentum, eps, _p(scale), _p(shift), _p(save_mean), _p(save_invstd), _stream(partial)), "bn_finalize")
+
+
+def bn_eval_coeffs(Cn, gamma, beta, rmean, rvar, eps, scale, shift) -> None:
+    ctx = _ctx(gamma)
+    ctx.check(ctx.lib.mml_bn_eval_coeffs(ctx.handle, Cn, _p(gamma), _p(beta), _p(rmean), _p(rvar), eps, _p(scale), _p(shift), _stream(gamma)),
+              "bn_eval_coeffs")
+
+
+def bn_act_fwd(x, scale, shift, res, rscale, rshift, y, rows, Cn, relu) -> None:
+    ctx = _ctx(x)
+    ctx.check(ctx.lib.mml_bn_act_fwd(ctx.handle, _p(x, BF16), _p(scale), _p(shift), _p(res), _p(rscale), _p(rshift), _p(y, BF16), rows, Cn,
+                                     int(relu), _stream(x)), "bn_act_fwd")
+
+
+def bn_bwd_blocks(t, rows, Cn) -> int:
+    ctx = _ctx(t)
+    return ctx.lib.mml_bn_bwd_blocks(ctx.handle, rows, Cn)
+
+
+def bn_bwd_reduce(dy1, dy2, y, x, mean, invstd, partial, rows, Cn, relu) -> None:
+    ctx = _ctx(dy1)
+    ctx.check(ctx.lib.mml_bn_bwd_reduce(ctx.handle, _p(dy1, BF16), _p(dy2), _p(y), _p(x, BF16), _p(mean), _p(invstd), _p(partial), rows, Cn,
+                                        int(relu), _stream(dy1)), "bn_bwd_reduce")
+
+
+def bn_bwd_finalize(partial, blocks, Cn, count, gamma, invstd, dgamma, dbeta, coef) -> None:
+    ctx = _ctx(partial)
+    ctx.check(ctx.lib.mml_bn_bwd_finalize(ctx.handle, _p(partial), blocks, Cn, count, _p(gamma), _p(invstd), _p(dgamma), _p(dbeta), _p(coef),
+                                          _stream(partial)), "bn_bwd_finalize")
+
+
+def bn_bwd_apply(dy1, dy2, y, x, mean, invstd, coef, dx, g_out, rows, Cn, relu) -> None:
+    ctx = _ctx(dy1)
+    ctx.check(ctx.lib.mml_bn_bwd_apply(ctx.handle, _p(dy1, BF16), _p(dy2), _p(y), _p(x, BF16), _p(mean), _p(invstd), _p(coef), _p(dx, BF16),
+                                       _p(g_out), rows, Cn, int(relu), _stream(dy1)), "bn_bwd_apply")
+
+
+def maxpool_fwd(x, y, argmax, N, H, W, Cn) -> None:
+    ctx = _ctx(x)
+    ctx.check(ctx.lib.mml_maxpool3x3s2_fwd(ctx.handle, _p(x, BF16), _p(y, BF16), _p(argmax, torch.uint8), N, H, W, Cn, _stream(x)), "maxpool_fwd")
+
+
+def maxpool_bwd(dy, argmax, dx, N, H, W, Cn) -> None:
+    ctx = _ctx(dy)
+    ctx.check(ctx.lib.mml_maxpool3x3s2_bwd(ctx.handle, _p(dy, BF16), _p(argmax, torch.uint8), _p(dx, BF16), N, H, W, Cn, _stream(dy)), "maxpool_bwd")
+
+
+def avgpool_fwd(x, y, N, HW, Cn) -> None:
+    ctx = _ctx(x)
+    ctx.check(ctx.lib.mml_avgpool_fwd(ctx.handle, _p(x, BF16), _p(y, torch.float32), N, HW, Cn, _stream(x)), "avgpool_fwd")
+
+
+def avgpool_bwd(dy, dx, N, HW, Cn) -> None:
+    ctx = _ctx(dy)
+    ctx.check(ctx.lib.mml_avgpool_bwd(ctx.handle, _p(dy, torch.float32), _p(dx, BF16), N, HW, Cn, _stream(dy)), "avgpool_bwd")
+
+
+# ---- head ----------------------------------------------------------------------------------------------------
+def head_params(fcA_w, fcA_b, fcI_w, fcI_b, w0, b0, w3, b3, w5, b5) -> HeadParams:
+    ts = (fcA_w, fcA_b, fcI_w, fcI_b, w0, b0, w3, b3, w5, b5)
+    for t in ts:
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise MMLError("head parameters must be contiguous fp32")
+    hp = HeadParams(*[t.data_ptr() for t in ts], fcA_w.shape[1], fcI_w.shape[1], fcA_w.shape[0], fcI_w.shape[0], w0.shape[0], w3.shape[0], w5.shape[0])
+    if w0.shape[1] != hp.EA + hp.EI or w3.shape[1] != hp.H1 or w5.shape[1] != hp.H2:
+        raise MMLError("head parameter shapes are inconsistent")
+    return hp
+
+
+def head_grads(*ts) -> HeadGrads:
+    for t in ts:
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise MMLError("head gradients must be contiguous fp32")
+    return HeadGrads(*[t.data_ptr() for t in ts])
+
+
+def head_scratch_per_sample(hp: HeadParams) -> int:
+    from ._lib import load_library
+
+    return load_library().mml_head_scratch_per_sample(C.byref(hp))
+
+
+def head_fwd(hp, pooledA, pooledI, labels, drop_mask, drop_scale, scratch, logits, loss_out, pred) -> None:
+    ctx = _ctx(pooledA)
+    B = pooledA.shape[0]
+    ctx.check(ctx.lib.mml_head_fwd(ctx.handle, C.byref(hp), _p(pooledA, torch.float32), _p(pooledI, torch.float32), _p(labels), _p(drop_mask),
+                                   float(drop_scale), _p(scratch), _p(logits), _p(loss_out), _p(pred, torch.int32), B, _stream(pooledA)), "head_fwd")
+
+
+def head_bwd(hp, hg, pooledA, pooledI, labels, drop_mask, drop_scale, scratch, loss_scale, dpooledA, dpooledI) -> None:
+    ctx = _ctx(pooledA)
+    B = pooledA.shape[0]
+    ctx.check(ctx.lib.mml_head_bwd(ctx.handle, C.byref(hp), C.byref(hg), _p(pooledA), _p(pooledI), _p(labels, torch.int64), _p(drop_mask),
+                                   float(drop_scale), _p(scratch), float(loss_scale), _p(dpooledA), _p(dpooledI), B, _stream(pooledA)), "head_bwd")
+
+
+def dropout_mask(mask, p, seed, step_counter) -> None:
+    ctx = _ctx(mask)
+    ctx.check(ctx.lib.mml_dropout_mask(ctx.handle, _p(mask, torch.uint8), mask.numel(), float(p), int(seed), _p(step_counter), _stream(mask)),
+              "dropout_mask")
+
+
+# ---- optimizer / aggregation ----------------------------------------------------------------------------------------
+def adam_step(p, g, m, v, p_bf16, hyper, step) -> None:
+    ctx = _ctx(p)
+    ctx.check(ctx.lib.mml_adam_step(ctx.handle, _p(p, torch.float32), _p(g, torch.float32), _p(m, torch.float32), _p(v, torch.float32), _p(p_bf16),
+                                    p.numel(), _p(hyper, torch.float32), _p(step, torch.int64), _stream(p)), "adam_step")
+
+
+def cast_f32_bf16(src, dst) -> None:
+    ctx = _ctx(src)
+    ctx.check(ctx.lib.mml_cast_f32_bf16(ctx.handle, _p(src, torch.float32), _p(dst, BF16), src.numel(), _stream(src)), "cast_f32_bf16")
+
+
+def weights_transpose(src, dst, table, n_convs, total_blocks) -> None:
+    ctx = _ctx(src)
+    ctx.check(ctx.lib.mml_weights_transpose(ctx.handle, _p(src, BF16), _p(dst, BF16), _p(table, torch.int64), n_convs, total_blocks, _stream(src)),
+              "weights_transpose")
+
+
+def fedavg(client_ptrs, weights, K, out) -> None:
+    """client_ptrs: device int64 tensor [K] of device pointers to fp32 buffers of out.numel() elements."""
+    ctx = _ctx(out)
+    ctx.check(ctx.lib.mml_fedavg(ctx.handle, _p(client_ptrs, torch.int64), _p(weights, torch.float32), K, _p(out, torch.float32), out.numel(),
+                                 _stream(out)), "fedavg")
+
+
+def scale_inplace(x, weights, idx) -> None:
+    ctx = _ctx(x)
+    ctx.check(ctx.lib.mml_scale_inplace(ctx.handle, _p(x, torch.float32), _p(weights, torch.float32), idx, x.numel(), _stream(x)), "scale_inplace")
+
+
+def launch_count(device_index: int = 0) -> int:
+    return Context.get(device_index).launches

@@ -1,0 +1,120 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolutions (through the C ABI) against torch on the same bf16 operands.
+
+Every (C, K, H, W, stride) below is a layer shape of the reference's ResNet18 @112x112 / ResNet34 @28x28 encoders
+(MML_Suite/models/msa/networks/resnet.py:25,30,176) plus the real 32x94 spectrogram shapes and
+ragged batch sizes.  Tolerance: operands are identical bf16 values, accumulation is fp32 in both, the result is stored
+as bf16 => |err| <= 2^-8 relative to the output magnitude plus fp32 reordering noise.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# (N, H, W, C, K, R, stride, pad)
+SHAPES = [
+    (8, 28, 28, 64, 64, 3, 1, 1),     # R18 layer1
+    (8, 28, 28, 64, 128, 3, 2, 1),    # R18 layer2.0.conv1
+    (8, 28, 28, 64, 128, 1, 2, 0),    # R18 layer2.0.downsample
+    (8, 14, 14, 128, 128, 3, 1, 1),   # R18 layer2
+    (8, 14, 14, 128, 256, 3, 2, 1),   # R18 layer3.0.conv1
+    (8, 14, 14, 128, 256, 1, 2, 0),
+    (8, 7, 7, 256, 256, 3, 1, 1),     # R18 layer3 / R34 layer1 spatial
+    (8, 7, 7, 256, 512, 3, 2, 1),     # R18 layer4.0.conv1 (7 -> 4, odd input)
+    (8, 7, 7, 256, 512, 1, 2, 0),
+    (16, 4, 4, 512, 512, 3, 1, 1),    # R18 layer4
+    (6, 7, 7, 64, 64, 3, 1, 1),       # R34 layer1
+    (6, 7, 7, 64, 128, 3, 2, 1),      # R34 layer2.0 (7 -> 4)
+    (6, 4, 4, 128, 128, 3, 1, 1),
+    (6, 4, 4, 128, 256, 3, 2, 1),     # 4 -> 2
+    (40, 2, 2, 256, 256, 3, 1, 1),    # R34 layer3
+    (40, 2, 2, 256, 512, 3, 2, 1),    # 2 -> 1
+    (40, 2, 2, 256, 512, 1, 2, 0),
+    (130, 1, 1, 512, 512, 3, 1, 1),   # R34 layer4 (only the centre tap reaches the input), ragged N
+    (3, 8, 24, 64, 64, 3, 1, 1),      # real 32x94 audio: layer1 is 8x24
+    (3, 8, 24, 64, 128, 3, 2, 1),
+    (5, 2, 6, 256, 512, 3, 2, 1),     # -> 1x3
+    (5, 1, 3, 512, 512, 3, 1, 1),
+]
+
+
+def _mk(shape, seed):
+    N, H, W, C, K, R, st, pad = shape
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(N, H, W, C, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(K, R, R, C, device="cuda", generator=g) * (2.0 / (C * R * R)) ** 0.5).to(torch.bfloat16)
+    return x, w
+
+
+def _ref_conv(x, w, st, pad):
+    return torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), stride=st, padding=pad)
+
+
+def _report(name, got, ref, tol):
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err <= tol * scale, f"{name}: max|err|={err:.4g} vs max|ref|={scale:.4g} (tol {tol})"
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_fprop_and_stats(shape):
+    from mml_b200 import ops
+
+    N, H, W, C, K, R, st, pad = shape
+    x, w = _mk(shape, 1)
+    geom = ops.make_geom(N, H, W, C, K, R, R, st, pad)
+    P, Q = ops.conv_out_hw(H, W, R, R, st, pad)
+    y = torch.full((N, P, Q, K), float("nan"), device="cuda", dtype=torch.bfloat16)
+    tiles = ops.conv_stat_tiles(geom)
+    part = torch.zeros(tiles, K, 2, device="cuda")
+    ops.conv_fprop(geom, x, w, y, part)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, w, st, pad).permute(0, 2, 3, 1)
+    _report("fprop", y.float(), ref, 2.0 ** -7)
+    yf = y.float().reshape(-1, K)
+    s = part.sum(0)
+    assert torch.allclose(s[:, 0], yf.sum(0), rtol=1e-3, atol=1e-2 * yf.abs().max().item()), "BN partial sum"
+    assert torch.allclose(s[:, 1], (yf * yf).sum(0), rtol=1e-3, atol=1e-3), "BN partial sum of squares"
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_dgrad(shape):
+    from mml_b200 import ops
+
+    N, H, W, C, K, R, st, pad = shape
+    x, w = _mk(shape, 2)
+    geom = ops.make_geom(N, H, W, C, K, R, R, st, pad)
+    P, Q = ops.conv_out_hw(H, W, R, R, st, pad)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    dy = torch.randn(N, P, Q, K, device="cuda", generator=g).to(torch.bfloat16)
+    w_t = w.permute(3, 1, 2, 0).contiguous()  # [C][R][S][K]
+    dx = torch.full((N, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv_dgrad(geom, dy, w_t, dx)
+    torch.cuda.synchronize()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    out = torch.nn.functional.conv2d(xr, w.float().permute(0, 3, 1, 2), stride=st, padding=pad)
+    out.backward(dy.float().permute(0, 3, 1, 2))
+    _report("dgrad", dx.float(), xr.grad.permute(0, 2, 3, 1), 2.0 ** -7)
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_wgrad(shape):
+    from mml_b200 import ops
+
+    N, H, W, C, K, R, st, pad = shape
+    x, w = _mk(shape, 4)
+    geom = ops.make_geom(N, H, W, C, K, R, R, st, pad)
+    P, Q = ops.conv_out_hw(H, W, R, R, st, pad)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dy = torch.randn(N, P, Q, K, device="cuda", generator=g).to(torch.bfloat16)
+    dw = torch.zeros(K, R, R, C, device="cuda")
+    ops.conv_wgrad(geom, x, dy, dw)
+    torch.cuda.synchronize()
+    wr = w.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    out = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wr, stride=st, padding=pad)
+    out.backward(dy.float().permute(0, 3, 1, 2))
+    ref = wr.grad.permute(0, 2, 3, 1)
+    _report("wgrad", dw, ref, 1e-3)
+    # accumulation semantics: a second call doubles the result
+    ops.conv_wgrad(geom, x, dy, dw)
+    torch.cuda.synchronize()
+    _report("wgrad x2", dw, 2 * ref, 1e-3)

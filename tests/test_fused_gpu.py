@@ -1,0 +1,294 @@
+"""GPU parity of the HBM-bound fused kernels (through the C ABI) against plain torch fp32 references of the same op.
+
+mask: bit-exact (data/base_dataset.py:71).  BN / pooling / head / Adam / FedAvg: fp32 tolerances stated per test; bf16
+storage where the kernel stores bf16.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def gen(seed):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+def test_mask_apply_bit_exact():
+    from mml_b200 import ops
+
+    x = torch.randn(7, 33, 5, device="cuda", generator=gen(0))
+    x[0, 0, 0], x[1, 0, 0], x[2, 0, 0], x[3, 0, 0] = float("inf"), float("nan"), -0.0, 1e-42
+    m = torch.tensor([0.0, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0], device="cuda")
+    y, yr = ops.mask_apply(x, m, want_reverse=True)
+    ref = x.cpu() * m.cpu().view(-1, 1, 1)
+    refr = x.cpu() * -1 * (m.cpu().view(-1, 1, 1) - 1)
+    assert torch.equal(y.cpu().view(torch.int32), ref.view(torch.int32))
+    assert torch.equal(yr.cpu().view(torch.int32), refr.view(torch.int32))
+    # committed golden bit patterns produced by torch CPU in the build container
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "mask_bits.npz"))
+    xg = torch.from_numpy(gold["x"]).view(torch.float32).cuda().view(1, -1)
+    for i, mval in enumerate((0.0, 1.0)):
+        yy, rr = ops.mask_apply(xg, torch.tensor([mval], device="cuda"), want_reverse=True)
+        assert np.array_equal(yy.cpu().view(torch.int32).numpy()[0], gold["out"][2 * i])
+        assert np.array_equal(rr.cpu().view(torch.int32).numpy()[0], gold["out"][2 * i + 1])
+
+
+@pytest.mark.parametrize("B,H,W", [(4, 112, 112), (5, 28, 28), (3, 32, 94), (2, 9, 13)])
+def test_stem_fprop_wgrad(B, H, W):
+    from mml_b200 import ops
+
+    x = torch.rand(B, H, W, device="cuda", generator=gen(1))
+    m = (torch.rand(B, device="cuda", generator=gen(2)) > 0.3).float()
+    w = torch.randn(64, 1, 7, 7, device="cuda", generator=gen(3)) * 0.2
+    P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty(B, P, Q, 64, device="cuda", dtype=BF)
+    tiles = ops.stem_stat_tiles(B, H, W)
+    part = torch.zeros(tiles, 64, 2, device="cuda")
+    ops.stem_fprop(x, m, w.view(64, 49).contiguous(), y, part)
+    xm = x * m.view(-1, 1, 1)
+    ref = F.conv2d(xm.unsqueeze(1), w, stride=2, padding=3).permute(0, 2, 3, 1)
+    assert ref.shape == y.shape
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 2.0 ** -8 * ref.abs().max().item() + 1e-5, err
+    yf = y.float().reshape(-1, 64)
+    s = part.sum(0)
+    assert torch.allclose(s[:, 0], yf.sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[:, 1], (yf * yf).sum(0), rtol=1e-4, atol=1e-2)
+    # wgrad
+    dy = torch.randn(B, P, Q, 64, device="cuda", generator=gen(4)).to(BF)
+    ws = torch.empty(ops.stem_wgrad_workspace(x) // 4, device="cuda")
+    dw = torch.empty(64, 49, device="cuda")
+    ops.stem_wgrad(x, m, dy, dw, ws)
+    wr = w.clone().requires_grad_(True)
+    F.conv2d(xm.unsqueeze(1), wr, stride=2, padding=3).backward(dy.float().permute(0, 3, 1, 2))
+    refw = wr.grad.view(64, 49)
+    assert (dw - refw).abs().max().item() <= 1e-4 * refw.abs().max().item() + 1e-4
+
+
+@pytest.mark.parametrize("rows,C", [(256 * 49, 64), (1000, 128), (98, 256), (4096, 512), (7, 512)])
+def test_bn_forward_backward(rows, C):
+    from mml_b200 import ops
+
+    x = (torch.randn(rows, C, device="cuda", generator=gen(5)) * 2 + 0.5).to(BF)
+    res = torch.randn(rows, C, device="cuda", generator=gen(6)).to(BF)
+    gamma = torch.rand(C, device="cuda", generator=gen(7)) + 0.5
+    beta = torch.randn(C, device="cuda", generator=gen(8)) * 0.1
+    # partials as a conv epilogue would emit them (two "tiles")
+    xf = x.float()
+    h = rows // 2
+    part = torch.stack([torch.stack([xf[:h].sum(0), (xf[:h] ** 2).sum(0)], 1), torch.stack([xf[h:].sum(0), (xf[h:] ** 2).sum(0)], 1)]).contiguous()
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    scale, shift, mean, invstd = (torch.empty(C, device="cuda") for _ in range(4))
+    ops.bn_finalize(part, 2, C, rows, gamma, beta, rm, rv, 0.1, 1e-5, scale, shift, mean, invstd)
+    rm_ref, rv_ref = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    xr = xf.clone().requires_grad_(True)
+    gr = gamma.clone().requires_grad_(True)
+    br = beta.clone().requires_grad_(True)
+    resr = res.float().clone().requires_grad_(True)
+    bn = F.batch_norm(xr.t().reshape(1, C, rows), rm_ref, rv_ref, gr, br, True, 0.1, 1e-5).reshape(C, rows).t()
+    out_ref = F.relu(bn + resr)
+    assert torch.allclose(mean, xf.mean(0), rtol=1e-4, atol=1e-4)
+    assert torch.allclose(rm, rm_ref, rtol=1e-4, atol=1e-5) and torch.allclose(rv, rv_ref, rtol=1e-4, atol=1e-5)
+    y = torch.empty(rows, C, device="cuda", dtype=BF)
+    ops.bn_act_fwd(x, scale, shift, res, None, None, y, rows, C, True)
+    assert (y.float() - out_ref).abs().max().item() <= 2.0 ** -7 * out_ref.abs().max().item() + 1e-3
+    # affine residual variant and no-residual / no-relu variants
+    y2 = torch.empty_like(y)
+    ops.bn_act_fwd(x, scale, shift, res, gamma, beta, y2, rows, C, True)
+    ref2 = F.relu(xf * scale + shift + res.float() * gamma + beta)
+    assert (y2.float() - ref2).abs().max().item() <= 2.0 ** -7 * ref2.abs().max().item() + 1e-3
+    y3 = torch.empty_like(y)
+    ops.bn_act_fwd(x, scale, shift, None, None, None, y3, rows, C, False)
+    ref3 = xf * scale + shift
+    assert (y3.float() - ref3).abs().max().item() <= 2.0 ** -7 * ref3.abs().max().item() + 1e-3
+    # backward (two incoming gradients, relu mask from the stored output)
+    dy1 = torch.randn(rows, C, device="cuda", generator=gen(9)).to(BF)
+    dy2 = torch.randn(rows, C, device="cuda", generator=gen(10)).to(BF)
+    out_from_y = F.relu(bn + resr)  # same graph; use mask of the kernel's stored y for consistency
+    gmask = (y.float() > 0).float()
+    gin = (dy1.float() + dy2.float()) * gmask
+    (bn * gin).sum().backward()  # d/dx of bn with upstream gradient gin (relu mask applied explicitly)
+    blocks = ops.bn_bwd_blocks(x, rows, C)
+    bpart = torch.zeros(blocks, C, 2, device="cuda")
+    ops.bn_bwd_reduce(dy1, dy2, y, x, mean, invstd, bpart, rows, C, True)
+    dgamma, dbeta, coef = torch.empty(C, device="cuda"), torch.empty(C, device="cuda"), torch.empty(3, C, device="cuda")
+    ops.bn_bwd_finalize(bpart, blocks, C, rows, gamma, invstd, dgamma, dbeta, coef)
+    dx, gout = torch.empty(rows, C, device="cuda", dtype=BF), torch.empty(rows, C, device="cuda", dtype=BF)
+    ops.bn_bwd_apply(dy1, dy2, y, x, mean, invstd, coef, dx, gout, rows, C, True)
+    tol = 2e-2
+    assert (dgamma - gr.grad).abs().max().item() <= tol * gr.grad.abs().max().item() + 1e-2
+    assert (dbeta - br.grad).abs().max().item() <= tol * br.grad.abs().max().item() + 1e-2
+    assert (dx.float() - xr.grad).abs().max().item() <= tol * xr.grad.abs().max().item() + 1e-3
+    assert (gout.float() - gin).abs().max().item() <= 2.0 ** -7 * gin.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("N,H,W,C", [(3, 56, 56, 64), (2, 14, 14, 64), (2, 16, 47, 64), (1, 5, 7, 64)])
+def test_maxpool(N, H, W, C):
+    from mml_b200 import ops
+
+    x = F.relu(torch.randn(N, H, W, C, device="cuda", generator=gen(11))).to(BF)  # many exact ties at 0
+    P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty(N, P, Q, C, device="cuda", dtype=BF)
+    am = torch.empty(N, P, Q, C, device="cuda", dtype=torch.uint8)
+    ops.maxpool_fwd(x, y, am, N, H, W, C)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.max_pool2d(xr, 3, 2, 1)
+    assert torch.equal(y.float(), ref.permute(0, 2, 3, 1))
+    dy = torch.randn(N, P, Q, C, device="cuda", generator=gen(12)).to(BF)
+    dx = torch.empty(N, H, W, C, device="cuda", dtype=BF)
+    ops.maxpool_bwd(dy, am, dx, N, H, W, C)
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    refdx = xr.grad.permute(0, 2, 3, 1)
+    # where the input is positive the argmax is unique almost surely; ties at zero are masked by the following ReLU
+    pos = x.float() > 0
+    assert (dx.float() - refdx)[pos].abs().max().item() <= 2.0 ** -6 * refdx.abs().max().item()
+
+
+@pytest.mark.parametrize("N,HW,C", [(256, 16, 512), (5, 1, 512), (3, 3, 512)])
+def test_avgpool(N, HW, C):
+    from mml_b200 import ops
+
+    x = torch.randn(N, HW, C, device="cuda", generator=gen(13)).to(BF)
+    y = torch.empty(N, C, device="cuda")
+    ops.avgpool_fwd(x, y, N, HW, C)
+    assert torch.allclose(y, x.float().mean(1), rtol=1e-5, atol=1e-6)
+    dy = torch.randn(N, C, device="cuda", generator=gen(14))
+    dx = torch.empty(N, HW, C, device="cuda", dtype=BF)
+    ops.avgpool_bwd(dy, dx, N, HW, C)
+    ref = (dy / HW).unsqueeze(1).expand(N, HW, C)
+    assert (dx.float() - ref).abs().max().item() <= 2.0 ** -8 * ref.abs().max().item() + 1e-7
+
+
+@pytest.mark.parametrize("B,use_drop", [(256, True), (5, False), (13, True)])
+def test_head_fwd_bwd(B, use_drop):
+    from mml_b200 import ops
+
+    FA = FI = 512
+    EA, EI, H1, H2, NC = 64, 128, 128, 64, 10
+    g = gen(15)
+
+    def lin(o, i):
+        return (torch.randn(o, i, device="cuda", generator=g) / math.sqrt(i)).requires_grad_(True), (torch.randn(o, device="cuda", generator=g) * 0.1).requires_grad_(True)
+
+    fcA_w, fcA_b = lin(EA, FA)
+    fcI_w, fcI_b = lin(EI, FI)
+    w0, b0 = lin(H1, EA + EI)
+    w3, b3 = lin(H2, H1)
+    w5, b5 = lin(NC, H2)
+    pa = torch.randn(B, FA, device="cuda", generator=g).requires_grad_(True)
+    pi = torch.randn(B, FI, device="cuda", generator=g).requires_grad_(True)
+    labels = torch.randint(0, NC, (B,), device="cuda", generator=g)
+    drop = (torch.rand(B, H1, device="cuda", generator=g) > 0.5).to(torch.uint8) if use_drop else None
+    params = [fcA_w, fcA_b, fcI_w, fcI_b, w0, b0, w3, b3, w5, b5]
+    hp = ops.head_params(*[p.detach() for p in params])
+    PS = ops.head_scratch_per_sample(hp)
+    scratch = torch.zeros(B, PS, device="cuda")
+    logits = torch.empty(B, NC, device="cuda")
+    loss = torch.zeros(1, device="cuda")
+    pred = torch.empty(B, device="cuda", dtype=torch.int32)
+    ops.head_fwd(hp, pa.detach(), pi.detach(), labels, drop, 2.0, scratch, logits, loss, pred)
+    emb = torch.cat((F.linear(pa, fcA_w, fcA_b), F.linear(pi, fcI_w, fcI_b)), 1)
+    h = F.relu(F.linear(emb, w0, b0))
+    if use_drop:
+        h = h * drop.float() * 2.0
+    h = F.relu(F.linear(h, w3, b3))
+    ref_logits = F.linear(h, w5, b5)
+    ref_loss = F.cross_entropy(ref_logits, labels)
+    assert torch.allclose(logits, ref_logits, rtol=1e-4, atol=1e-4)
+    assert abs(loss.item() - ref_loss.item()) < 1e-5 * max(1, abs(ref_loss.item())) + 1e-5
+    assert torch.equal(pred.long(), torch.softmax(ref_logits, 1).argmax(1))
+    grads = [torch.full_like(p, float("nan")) for p in params]
+    hg = ops.head_grads(*grads)
+    dpa, dpi = torch.empty_like(pa), torch.empty_like(pi)
+    ops.head_bwd(hp, hg, pa.detach(), pi.detach(), labels, drop, 2.0, scratch, 1.0, dpa, dpi)
+    ref_loss.backward()
+    for got, p in zip(grads, params):
+        assert torch.allclose(got, p.grad, rtol=1e-3, atol=1e-5), (got - p.grad).abs().max()
+    assert torch.allclose(dpa, pa.grad, rtol=1e-3, atol=1e-6) and torch.allclose(dpi, pi.grad, rtol=1e-3, atol=1e-6)
+
+
+def test_adam_matches_torch():
+    from mml_b200 import ops
+
+    n = 100003
+    p = torch.randn(n, device="cuda", generator=gen(16))
+    pt = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pt], lr=5e-4, weight_decay=1e-4)
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    pb = torch.empty(n, device="cuda", dtype=BF)
+    hyper = torch.tensor([5e-4, 0.9, 0.999, 1e-8, 1e-4, 1.0, 0, 0], device="cuda")
+    step = torch.zeros(1, device="cuda", dtype=torch.int64)
+    for it in range(5):
+        g = torch.randn(n, device="cuda", generator=gen(17 + it)) * 0.01
+        pt.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g, m, v, pb, hyper, step)
+    assert int(step.item()) == 5
+    assert torch.allclose(p, pt.detach(), rtol=1e-5, atol=1e-7), (p - pt.detach()).abs().max()
+    assert torch.allclose(m, opt.state[pt]["exp_avg"], rtol=1e-5, atol=1e-9)
+    assert torch.allclose(v, opt.state[pt]["exp_avg_sq"], rtol=1e-5, atol=1e-12)
+    assert torch.equal(pb, p.to(BF))
+
+
+def test_cast_and_weight_transpose():
+    from mml_b200 import ops
+
+    convs = [(64, 9, 64), (128, 1, 64), (512, 9, 256)]
+    total = sum(k * rs * c for k, rs, c in convs)
+    src32 = torch.randn(total, device="cuda", generator=gen(30))
+    src = torch.empty(total, device="cuda", dtype=BF)
+    ops.cast_f32_bf16(src32, src)
+    assert torch.equal(src, src32.to(BF))
+    dst = torch.empty_like(src)
+    rows, off, blk = [], 0, 0
+    for k, rs, c in convs:
+        rows.append([off, off, k, rs, c, blk])
+        off += k * rs * c
+        blk += rs * (k // 32) * (c // 32)
+    table = torch.tensor(rows, device="cuda", dtype=torch.int64)
+    ops.weights_transpose(src, dst, table, len(convs), blk)
+    off = 0
+    for k, rs, c in convs:
+        a = src[off:off + k * rs * c].view(k, rs, c)
+        b = dst[off:off + k * rs * c].view(c, rs, k)
+        assert torch.equal(b, a.permute(2, 1, 0).contiguous())
+        off += k * rs * c
+
+
+def test_fedavg():
+    from mml_b200 import ops
+
+    K, n = 8, 1_000_003
+    clients = [torch.randn(n, device="cuda", generator=gen(40 + k)) * 0.02 for k in range(K)]
+    nk = torch.arange(1, K + 1, dtype=torch.float32) * 1000
+    w = (nk / nk.sum()).cuda()
+    ptrs = torch.tensor([c.data_ptr() for c in clients], device="cuda", dtype=torch.int64)
+    out = torch.empty(n, device="cuda")
+    ops.fedavg(ptrs, w, K, out)
+    ref = sum(c.double() * float(wk) for c, wk in zip(clients, w.cpu()))
+    assert torch.allclose(out.double(), ref, rtol=1e-5, atol=1e-8)
+    x = clients[0].clone()
+    ops.scale_inplace(x, w, 3)
+    assert torch.allclose(x, clients[0] * w[3])
+
+
+def test_dropout_mask_rate_and_determinism():
+    from mml_b200 import ops
+
+    n = 256 * 128
+    m1 = torch.empty(n, device="cuda", dtype=torch.uint8)
+    m2 = torch.empty_like(m1)
+    step = torch.zeros(1, device="cuda", dtype=torch.int64)
+    ops.dropout_mask(m1, 0.5, 1234, step)
+    ops.dropout_mask(m2, 0.5, 1234, step)
+    assert torch.equal(m1, m2)
+    assert abs(m1.float().mean().item() - 0.5) < 0.02
+    step += 1
+    ops.dropout_mask(m2, 0.5, 1234, step)
+    assert not torch.equal(m1, m2)
