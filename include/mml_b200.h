@@ -100,8 +100,9 @@ int mml_bn_bwd_apply(mml_ctx*, const uint16_t* dy1, const uint16_t* dy2, const u
 
 /* ---- pooling -- resnet.py:140 MaxPool2d(3,2,1), :149 AdaptiveAvgPool2d((1,1)) ---------------------------------- */
 int mml_maxpool3x3s2_fwd(mml_ctx*, const uint16_t* x, uint16_t* y, uint8_t* argmax, int N, int H, int W, int C, void* stream);
-int mml_maxpool3x3s2_bwd(mml_ctx*, const uint16_t* dy, const uint8_t* argmax, uint16_t* dx, int N, int H, int W, int C,
-                         void* stream);
+/* dx = scatter of (dy [+ dy2]) to the argmax positions; dy2 may be NULL */
+int mml_maxpool3x3s2_bwd(mml_ctx*, const uint16_t* dy, const uint16_t* dy2, const uint8_t* argmax, uint16_t* dx, int N, int H,
+                         int W, int C, void* stream);
 int mml_avgpool_fwd(mml_ctx*, const uint16_t* x, float* y, int N, int HW, int C, void* stream);
 int mml_avgpool_bwd(mml_ctx*, const float* dy, uint16_t* dx, int N, int HW, int C, void* stream);
 
@@ -129,6 +130,8 @@ int mml_head_fwd(mml_ctx*, const mml_head_params* p, const float* pooledA, const
 int mml_head_bwd(mml_ctx*, const mml_head_params* p, const mml_head_grads* g, const float* pooledA, const float* pooledI,
                  const int64_t* labels, const uint8_t* dropout_mask, float dropout_scale, float* scratch,
                  float loss_scale, float* dpooledA, float* dpooledI, int B, void* stream);
+/* stand-alone nn.Linear forward (encoder fc outside the fused head, resnet.py:218): y [B][n_out] = x [B][n_in] W^T + b */
+int mml_linear_fwd(mml_ctx*, const float* x, const float* w, const float* bias, float* y, int B, int n_in, int n_out, void* stream);
 /* Philox-free counter RNG for the throughput path: mask[i] = hash(seed, *step_counter, i) >= p ? 1 : 0 */
 int mml_dropout_mask(mml_ctx*, uint8_t* mask, int64_t n, float p, uint64_t seed, const int64_t* step_counter, void* stream);
 

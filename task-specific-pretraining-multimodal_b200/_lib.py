@@ -58,12 +58,13 @@ SIGNATURES = {
     "mml_bn_bwd_finalize": (I32, [P, P, I32, I32, I64, P, P, P, P, P, P]),
     "mml_bn_bwd_apply": (I32, [P, P, P, P, P, P, P, P, P, P, I64, I32, I32, P]),
     "mml_maxpool3x3s2_fwd": (I32, [P, P, P, P, I32, I32, I32, I32, P]),
-    "mml_maxpool3x3s2_bwd": (I32, [P, P, P, P, I32, I32, I32, I32, P]),
+    "mml_maxpool3x3s2_bwd": (I32, [P, P, P, P, P, I32, I32, I32, I32, P]),
     "mml_avgpool_fwd": (I32, [P, P, P, I32, I32, I32, P]),
     "mml_avgpool_bwd": (I32, [P, P, P, I32, I32, I32, P]),
     "mml_head_scratch_per_sample": (I32, [C.POINTER(HeadParams)]),
     "mml_head_fwd": (I32, [P, C.POINTER(HeadParams), P, P, P, P, F32, P, P, P, P, I32, P]),
     "mml_head_bwd": (I32, [P, C.POINTER(HeadParams), C.POINTER(HeadGrads), P, P, P, P, F32, P, F32, P, P, I32, P]),
+    "mml_linear_fwd": (I32, [P, P, P, P, P, I32, I32, I32, P]),
     "mml_dropout_mask": (I32, [P, P, I64, F32, U64, P, P]),
     "mml_adam_step": (I32, [P, P, P, P, P, P, I64, P, P, P]),
     "mml_cast_f32_bf16": (I32, [P, P, P, I64, P]),

@@ -54,8 +54,8 @@ __global__ void mask_apply_kernel(const float* __restrict__ x, const float* __re
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const float m = mask[i / per_sample];
     const float v = x[i];
-    if (y) y[i] = __fmul_rn(v, m);
-    if (yrev) yrev[i] = __fmul_rn(__fmul_rn(v, -1.0f), __fsub_rn(m, 1.0f));
+    if (y) y[i] = mask_mul(v, m);
+    if (yrev) yrev[i] = mask_mul(mask_mul(v, -1.0f), __fsub_rn(m, 1.0f));  // original * -1 * (mask - 1), :72
   }
 }
 
@@ -311,8 +311,8 @@ maxpool_fwd_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, uin
 }
 
 __global__ void __launch_bounds__(kThreads)
-maxpool_bwd_kernel(const uint16_t* __restrict__ dy, const uint8_t* __restrict__ amax, uint16_t* __restrict__ dx, int N, int H, int W,
-                   int C, int P, int Q) {
+maxpool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__ dy2, const uint8_t* __restrict__ amax,
+                   uint16_t* __restrict__ dx, int N, int H, int W, int C, int P, int Q) {
   const int c8 = C >> 3;
   const long long total = (long long)N * H * W * c8;
   for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
@@ -336,7 +336,12 @@ maxpool_bwd_kernel(const uint16_t* __restrict__ dy, const uint8_t* __restrict__ 
         if (s < 0 || s > 2) continue;
         const long long o = ((((long long)n * P + p) * Q + q) * c8 + cg) * 8;
         const uint2 a = __ldg(reinterpret_cast<const uint2*>(amax + o));
-        const F8 g = unpack8(ldg16(dy + o));
+        F8 g = unpack8(ldg16(dy + o));
+        if (dy2 != nullptr) {  // gradient arriving over two paths (conv branch + identity skip)
+          const F8 g2 = unpack8(ldg16(dy2 + o));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g.v[j] += g2.v[j];
+        }
         const uint32_t want = (uint32_t)(r * 3 + s);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -529,11 +534,11 @@ int mml_maxpool3x3s2_fwd(mml_ctx* ctx, const uint16_t* x, uint16_t* y, uint8_t* 
   return MML_OK;
 }
 
-int mml_maxpool3x3s2_bwd(mml_ctx* ctx, const uint16_t* dy, const uint8_t* argmax, uint16_t* dx, int N, int H, int W, int C,
-                         void* stream) {
+int mml_maxpool3x3s2_bwd(mml_ctx* ctx, const uint16_t* dy, const uint16_t* dy2, const uint8_t* argmax, uint16_t* dx, int N, int H,
+                         int W, int C, void* stream) {
   MML_REQUIRE(ctx, ctx && dy && dx && argmax && N >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "maxpool_bwd: bad arguments");
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
-  maxpool_bwd_kernel<<<ew_grid(ctx, (long long)N * H * W * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(dy, argmax, dx, N, H, W, C, P, Q);
+  maxpool_bwd_kernel<<<ew_grid(ctx, (long long)N * H * W * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(dy, dy2, argmax, dx, N, H, W, C, P, Q);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }

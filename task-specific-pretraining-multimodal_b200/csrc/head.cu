@@ -304,6 +304,18 @@ __global__ void __launch_bounds__(256) head_bwd_weights_kernel(WgradJobs jobs, i
   if (threadIdx.x == 0) J.db[o] = bsum;
 }
 
+// y[b][o] = bias[o] + sum_k x[b][k] * W[o][k]: the encoder fc used stand-alone (resnet.py:150,218); one warp per output
+__global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                                                         float* __restrict__ y, int B, int n_in, int n_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * n_out) return;
+  const int b = warp / n_out, o = warp - b * n_out;
+  float acc = 0.f;
+  for (int k = lane; k < n_in; k += 32) acc = fmaf(__ldg(x + (size_t)b * n_in + k), __ldg(W + (size_t)o * n_in + k), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) y[(size_t)b * n_out + o] = acc + (bias ? bias[o] : 0.f);
+}
+
 __global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, long long n, float p, unsigned long long seed,
                                     const long long* __restrict__ step) {
   const unsigned long long st = step ? (unsigned long long)step[0] : 0ull;
@@ -392,6 +404,14 @@ int mml_head_bwd(mml_ctx* ctx, const mml_head_params* p, const mml_head_grads* g
   set(3, scratch + d.off_dh2(), PS, scratch + d.off_h1(), PS, g->w3, g->b3, d.H2, d.H1);
   set(4, scratch + d.off_dlog(), PS, scratch + d.off_h2(), PS, g->w5, g->b5, d.NC, d.H2);
   head_bwd_weights_kernel<<<fb, 256, 0, st>>>(jobs, B);
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
+int mml_linear_fwd(mml_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int n_in, int n_out, void* stream) {
+  MML_REQUIRE(ctx, ctx && x && w && y && B >= 1 && n_in >= 1 && n_out >= 1, "linear_fwd: bad arguments");
+  const long long warps = (long long)B * n_out;
+  linear_fwd_kernel<<<(unsigned)mml_ceil_div(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, n_in, n_out);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }

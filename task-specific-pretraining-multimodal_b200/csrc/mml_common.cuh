@@ -199,6 +199,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
+// sample = original * mask (MML_Suite/data/base_dataset.py:71), bit-identical to torch on the reference's x86 host:
+// a true IEEE multiply (x*1 == x, x*0 == +-0 with the sign of x, denormals kept); IEEE leaves NaN payloads to the
+// implementation, so the two NaN cases follow SSE: a NaN operand comes back quieted with its payload, and an invalid
+// operation (inf * 0) gives the x86 default NaN 0xFFC00000.
+__device__ __forceinline__ float mask_mul(float x, float m) {
+  float r = __fmul_rn(x, m);
+  if (r != r) {
+    if (x != x) r = __uint_as_float(__float_as_uint(x) | 0x00400000u);
+    else if (m != m) r = __uint_as_float(__float_as_uint(m) | 0x00400000u);
+    else r = __uint_as_float(0xFFC00000u);
+  }
+  return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -46,7 +46,7 @@ __device__ __forceinline__ void load_patch(float* patch, const float* __restrict
     float v = 0.f;
     if (c < PATCH_W && h >= 0 && h < g.H && w >= 0 && w < g.W) {
       v = img[(size_t)h * g.W + w];
-      if (mask) v = __fmul_rn(v, m);  // base_dataset.py:71
+      if (mask) v = mask_mul(v, m);  // base_dataset.py:71
     }
     patch[i] = v;
   }

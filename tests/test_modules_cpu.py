@@ -1,0 +1,90 @@
+"""CPU tests of the host-side mirror: constructors, state_dict surface, RNG-order parity with the oracle."""
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+import late_fusion_oracle as O
+
+
+def _build(seed=0, dropout=0.5):
+    from mml_b200.avmnist import AVMNIST
+    from mml_b200.resnet import ResNet18, ResNet34
+
+    torch.manual_seed(seed)
+    return AVMNIST(ResNet18(in_channels=1, hidden_dim=64), ResNet34(in_channels=1, hidden_dim=128), hidden_dim=128, dropout=dropout, fusion_fn="concat")
+
+
+def test_state_dict_matches_reference_surface_and_init():
+    model = _build(0)
+    sd = model.state_dict()
+    torch.manual_seed(0)
+    ref = O.init_avmnist_state()
+    assert list(sd.keys()) == list(ref.keys())
+    assert len(sd) == 346
+    assert sum(p.numel() for p in model.parameters()) == 32_580_746
+    for k in ref:
+        assert sd[k].shape == ref[k].shape and sd[k].dtype == ref[k].dtype, k
+        assert torch.equal(sd[k], ref[k]), f"init differs at {k}"
+
+
+def test_constructor_contract():
+    from mml_b200.avmnist import AVMNIST
+    from mml_b200.resnet import ResNet18, ResNet34, ResNetEncoder
+
+    enc = ResNet18(1, 64)
+    assert isinstance(enc, ResNetEncoder) and enc.get_embedding_size() == 64
+    assert ResNet34(hidden_dim=128).get_embedding_size() == 128
+    with pytest.raises(ValueError):
+        AVMNIST(enc, ResNet34(), 128, fusion_fn="sum")
+    m = AVMNIST(enc, ResNet34(), 128, dropout=0.0)
+    assert isinstance(m.net[2], torch.nn.Identity)
+    assert m.get_encoder("audio") is enc
+    with pytest.raises(ValueError):
+        m.get_encoder("text")
+
+
+def test_no_cpu_fallback():
+    model = _build(0)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        model.forward(A=torch.zeros(2, 112, 112), I=torch.zeros(2, 1, 28, 28))
+    with pytest.raises(RuntimeError, match="GPU only"):
+        model.audio_encoder(torch.zeros(2, 112, 112))
+
+
+def test_loss_and_optimizer_guards():
+    from mml_b200.avmnist import AVMNIST
+
+    class Term:
+        def __init__(self, fn, w=1.0):
+            self.loss_fn, self.weight = fn, w
+
+    AVMNIST._check_loss({"ce": Term(torch.nn.CrossEntropyLoss())})
+    for bad in ({"ce": Term(torch.nn.CrossEntropyLoss(label_smoothing=0.1))}, {"ce": Term(torch.nn.CrossEntropyLoss(), 0.5)},
+                {"mse": Term(torch.nn.MSELoss())}, {"a": Term(torch.nn.CrossEntropyLoss()), "b": Term(torch.nn.CrossEntropyLoss())}):
+        with pytest.raises(NotImplementedError):
+            AVMNIST._check_loss(bad)
+
+
+def test_c_abi_library_loads_and_exports_every_header_symbol():
+    from mml_b200 import _lib
+
+    lib = _lib.load_library()
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "mml_b200.h")).read()
+    declared = set(re.findall(r"\b(mml_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mml_version() >= 100
+
+
+def test_product_package_never_imports_the_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "task-specific-pretraining-multimodal_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "late_fusion_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f

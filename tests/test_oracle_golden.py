@@ -1,0 +1,83 @@
+"""The oracle restatement against the golden vectors produced from the UNMODIFIED reference (oracle/make_golden.py)."""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+import late_fusion_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", ["avmnist_b4_112", "avmnist_b6_32x94"])
+def test_train_steps_match_reference(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    batch, aH, aW, seed, steps = (int(v) for v in g["meta"])
+    torch.manual_seed(0)
+    state = O.init_avmnist_state()
+    data = O.synthetic_batch(batch, seed, (aH, aW))
+    A = O.apply_missing_mask(data["audio"], data["audio_mask"])
+    I = O.apply_missing_mask(data["image"], data["image_mask"])
+    y = data["labels"]
+    assert np.allclose(g["input_checksum"], [float(A.double().sum()), float(I.double().sum()), float(y.sum())])
+    opt_state = {}
+    for step in range(steps):
+        out = O.train_step(state, opt_state, A, I, y, data["dropout_mask"], 0.5)
+        assert abs(out["loss"] - float(g["losses"][step])) < (1e-5 if step == 0 else 5e-3)
+        if step == 0:
+            assert np.allclose(out["logits"].numpy(), g["logits"], rtol=1e-4, atol=1e-5)
+            assert np.array_equal(out["predictions"].numpy(), g["predictions"])
+            keys = list(g["grad_keys"])
+            l2 = np.array([float(out["grads"][k].double().norm()) for k in keys])
+            assert np.allclose(l2, g["grad_l2"], rtol=1e-3, atol=1e-7)
+            for k in g.files:
+                if k.startswith("grad::"):
+                    ref = g[k]
+                    got = out["grads"][k[6:]].numpy()
+                    assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-7, k
+    for k in g.files:
+        if k.startswith("state::"):
+            ref = g[k]
+            got = state[k[7:]].numpy()
+            assert np.abs(got - ref).max() <= 5e-3 * np.abs(ref).max() + 1e-6, k
+    ev = O.validation_step(state, A, I, y)
+    assert np.abs(ev["logits"].numpy() - g["eval_logits"]).max() < 5e-2
+
+
+def test_patterns_match_reference():
+    lines = open(os.path.join(GOLD, "patterns.txt")).read().split()
+    cases = {
+        "avmnist_audio02": (OrderedDict([("audio", (0.2, None)), ("image", (0.0, None))]), ["ai"]),
+        "avmnist_all": (OrderedDict([("audio", (0.2, None)), ("image", (0.3, None))]), None),
+        "avmnist_apply": (OrderedDict([("audio", (0.25, ["a"])), ("image", (0.5, ["ai", "i"]))]), None),
+        "mosi_3": (OrderedDict([("audio", (0.2, None)), ("video", (0.0, None)), ("text", (0.9, None))]), None),
+    }
+    want = {}
+    for ln in lines:
+        c, pat, mod, v = ln.split("|")
+        want.setdefault(c, {}).setdefault(pat, {})[mod] = float(v)
+    for cname, (mods, sel) in cases.items():
+        assert O.generate_patterns(mods, sel) == want[cname]
+
+
+def test_mask_semantics_bits():
+    g = np.load(os.path.join(GOLD, "mask_bits.npz"))
+    x = torch.from_numpy(g["x"]).view(torch.float32)
+    for i, m in enumerate((0.0, 1.0)):
+        assert np.array_equal(O.apply_missing_mask(x, m).view(torch.int32).numpy(), g["out"][2 * i])
+        assert np.array_equal(O.reverse_missing_mask(x, m).view(torch.int32).numpy(), g["out"][2 * i + 1])
+
+
+def test_data_parallel_semantics_and_fedavg():
+    torch.manual_seed(0)
+    state = O.init_avmnist_state()
+    d = O.synthetic_batch(4, 11, (32, 32))
+    shards = [(d["audio"][:2], d["image"][:2], d["labels"][:2], d["dropout_mask"][:2]), (d["audio"][2:], d["image"][2:], d["labels"][2:], d["dropout_mask"][2:])]
+    g = O.data_parallel_grads(state, shards)
+    assert set(g) == {k for k in state if O.is_parameter(k)}
+    s2 = OrderedDict((k, v * 3 if v.dtype.is_floating_point else v) for k, v in state.items())
+    avg = O.fedavg([state, s2], [1000, 3000])
+    k = "net.5.bias"
+    assert torch.allclose(avg[k], state[k] * 0.25 + s2[k] * 0.75)
