@@ -212,6 +212,45 @@ def arch_of(state: Dict[str, Tensor], prefix: str) -> str:
 
 
 # ----------------------------------------------------------------------------------------------
+# optional bf16 storage emulation (a DEBUGGING AID for the CUDA path, not part of the reference):
+# the B200 path stores activations and activation-gradients as bf16 and keeps fp32 accumulation.
+# With emulate_bf16=True the oracle rounds at the same points, so that schedule / wiring bugs can
+# be told apart from precision noise.
+# ----------------------------------------------------------------------------------------------
+class _RoundBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).float()
+
+
+class _RoundGradBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).float()
+
+
+def _q(x: Tensor, on: bool) -> Tensor:
+    return _RoundBF16.apply(x) if on else x
+
+
+def _qg(x: Tensor, on: bool) -> Tensor:
+    return _RoundGradBF16.apply(x) if on else x
+
+
+def _qw(w: Tensor, on: bool) -> Tensor:
+    """bf16 operand copy of an fp32 master weight (gradient stays fp32)."""
+    return w + (w.detach().to(torch.bfloat16).float() - w.detach()) if on else w
+
+
+# ----------------------------------------------------------------------------------------------
 # a2-a5 -- encoders (resnet.py:37-54, 199-219)
 # ----------------------------------------------------------------------------------------------
 def _batch_norm(state: Dict[str, Tensor], prefix: str, x: Tensor, training: bool, update_running: bool) -> Tensor:
@@ -231,39 +270,44 @@ def resnet_forward(
     training: bool,
     update_running: bool = True,
     taps: Optional[Dict[str, Tensor]] = None,
+    emulate_bf16: bool = False,
+    forced: Optional[Dict[str, Tensor]] = None,
 ) -> Tensor:
-    """ResNetEncoder.forward (resnet.py:199-219).  ``taps`` collects intermediates for tests."""
+    """ResNetEncoder.forward (resnet.py:199-219).
+
+    ``taps`` collects every stored intermediate (NCHW fp32) under ``prefix + name``.
+    ``forced`` (testing aid) substitutes the VALUE of those intermediates by the given tensors while
+    keeping the autograd graph (x + (forced - x).detach()): the backward pass then runs over exactly the
+    activations another implementation stored, which makes a gradient comparison well conditioned.
+    """
+    eb = emulate_bf16
     if x.dim() == 3:
         x = x.unsqueeze(1)  # resnet.py:201-203
 
     def bn(p: str, t: Tensor) -> Tensor:
         return _batch_norm(state, prefix + p, t, training, update_running)
 
-    def tap(name: str, t: Tensor) -> None:
+    def pt(name: str, t: Tensor) -> Tensor:
+        if forced is not None and (prefix + name) in forced:
+            t = t + (forced[prefix + name].to(t.dtype) - t).detach()
         if taps is not None:
             taps[prefix + name] = t
+        return t
 
-    x = F.conv2d(x, state[prefix + "conv1.weight"], None, stride=2, padding=3)
-    tap("conv1", x)
-    x = F.relu(bn("bn1", x))
-    tap("relu1", x)
-    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
-    tap("maxpool", x)
+    x = pt("conv1", _q(F.conv2d(x, state[prefix + "conv1.weight"], None, stride=2, padding=3), eb))
+    x = pt("relu1", _q(F.relu(bn("bn1", x)), eb))
+    x = pt("maxpool", F.max_pool2d(x, kernel_size=3, stride=2, padding=1))
     for bp, _inpl, _planes, stride, ds in block_plan(arch_of(state, prefix)):
-        identity = x
-        out = F.conv2d(x, state[f"{prefix}{bp}.conv1.weight"], None, stride=stride, padding=1)
-        tap(f"{bp}.conv1", out)
-        out = F.relu(bn(f"{bp}.bn1", out))
-        out = F.conv2d(out, state[f"{prefix}{bp}.conv2.weight"], None, stride=1, padding=1)
-        tap(f"{bp}.conv2", out)
+        identity = _qg(x, eb)
+        out = pt(f"{bp}.conv1", _q(F.conv2d(_qg(x, eb), _qw(state[f"{prefix}{bp}.conv1.weight"], eb), None, stride=stride, padding=1), eb))
+        out = pt(f"{bp}.relu1", _q(F.relu(bn(f"{bp}.bn1", out)), eb))
+        out = pt(f"{bp}.conv2", _q(F.conv2d(out, _qw(state[f"{prefix}{bp}.conv2.weight"], eb), None, stride=1, padding=1), eb))
         out = bn(f"{bp}.bn2", out)
         if ds:
-            identity = F.conv2d(x, state[f"{prefix}{bp}.downsample.0.weight"], None, stride=stride)
+            identity = pt(f"{bp}.downsample", _q(F.conv2d(_qg(x, eb), _qw(state[f"{prefix}{bp}.downsample.0.weight"], eb), None, stride=stride), eb))
             identity = bn(f"{bp}.downsample.1", identity)
-        x = F.relu(out + identity)
-        tap(bp, x)
-    x = torch.flatten(F.adaptive_avg_pool2d(x, (1, 1)), 1)
-    tap("avgpool", x)
+        x = pt(bp, _q(F.relu(out + identity), eb))
+    x = pt("avgpool", torch.flatten(F.adaptive_avg_pool2d(x, (1, 1)), 1))
     return F.linear(x, state[prefix + "fc.weight"], state[prefix + "fc.bias"])
 
 
@@ -290,10 +334,12 @@ def late_fusion_forward(
     dropout_p: float = 0.5,
     update_running: bool = True,
     taps: Optional[Dict[str, Tensor]] = None,
+    emulate_bf16: bool = False,
+    forced: Optional[Dict[str, Tensor]] = None,
 ) -> Tensor:
     """AVMNIST.forward(A=A, I=I) (avmnist.py:238-267); inputs are already masked (x * m)."""
-    audio = resnet_forward(state, "audio_encoder.", A.float(), training, update_running, taps)
-    image = resnet_forward(state, "image_encoder.", I.float(), training, update_running, taps)
+    audio = resnet_forward(state, "audio_encoder.", A.float(), training, update_running, taps, emulate_bf16, forced)
+    image = resnet_forward(state, "image_encoder.", I.float(), training, update_running, taps, emulate_bf16, forced)
     if taps is not None:
         taps["audio_emb"], taps["image_emb"] = audio, image
     return head_forward(state, audio, image, dropout_mask if training else None, dropout_p)
@@ -350,13 +396,15 @@ def train_step(
     weight_decay: float = 1e-4,
     apply_update: bool = True,
     grad_scale: float = 1.0,
+    emulate_bf16: bool = False,
+    forced: Optional[Dict[str, Tensor]] = None,
 ) -> Dict[str, object]:
     """Returns {"loss", "logits", "predictions", "grads"}; mutates ``state`` / ``opt_state`` in place."""
     params = {k: v for k, v in state.items() if is_parameter(k)}
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
     work = dict(state)
     work.update(leaves)
-    logits = late_fusion_forward(work, A, I, True, dropout_mask, dropout_p)
+    logits = late_fusion_forward(work, A, I, True, dropout_mask, dropout_p, emulate_bf16=emulate_bf16, forced=forced)
     loss = total_loss(logits, labels)
     gl = torch.autograd.grad(loss, list(leaves.values()))
     grads = {k: g * grad_scale for k, g in zip(leaves.keys(), gl)}

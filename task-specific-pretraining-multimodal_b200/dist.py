@@ -1,0 +1,90 @@
+"""One-process-per-GPU data parallelism for the fused step (the reference has no distributed code at all).
+
+Semantics: every rank holds the full fp32 weights + Adam state, takes its own shard of the global
+batch, keeps PER-REPLICA BatchNorm statistics (the reference is single-device; there is no SyncBN to match), and the
+gradients are summed over ranks and divided by the world size inside the Adam kernel (``hyper[5] = 1/world``).
+
+The flat gradient buffer ``G`` is reduced in two contiguous buckets, ordered so that communication hides under compute:
+the image encoder has 2/3 of the parameters but few FLOPs, so its backward runs FIRST and bucket 0 (image encoder +
+head, ~85 MB) is all-reduced on a side stream while the audio encoder's backward (87 % of the FLOPs) is still running;
+bucket 1 (audio encoder, ~45 MB) follows.  The wgrad kernels write straight into ``G``, so there is no pack/copy step.
+``torch.distributed`` (NCCL over NVLink/NVSwitch) is the plumbing; both the collectives and the cross-stream
+dependencies are captured into the step's CUDA graph.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def bucket_ranges(offsets: dict, total: int) -> List[Tuple[int, int]]:
+    """[(begin, end)] element ranges of G: bucket 0 = image encoder + head (ready first), bucket 1 = audio encoder."""
+    img = [o for n, o in offsets.items() if n.startswith("image_encoder.")]
+    if not img:
+        return [(0, total)]
+    split = min(img)
+    return [(split, total), (0, split)]
+
+
+class DataParallel:
+    def __init__(self, process_group: Optional[dist.ProcessGroup] = None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised (use mml_b200.dist.init_from_env())")
+        self.group = process_group
+        self.world_size = dist.get_world_size(process_group)
+        self.rank = dist.get_rank(process_group)
+        self.comm_stream: Optional[torch.cuda.Stream] = None
+        self.buckets: List[Tuple[int, int]] = []
+        self.engine = None
+
+    def attach(self, engine) -> None:
+        self.engine = engine
+        self.buckets = bucket_ranges(engine.fs.offsets, engine.fs.total)
+        self.comm_stream = torch.cuda.Stream(device=engine.device)
+        engine.world = self.world_size
+        engine.allreduce = self._allreduce if self.world_size > 1 else None
+
+    def _allreduce(self, plan, idx: int) -> None:
+        eng = self.engine
+        if idx >= len(self.buckets):
+            return
+        a, b = self.buckets[idx]
+        main = torch.cuda.current_stream(eng.device)
+        self.comm_stream.wait_stream(main)  # gradients of this bucket are complete in stream order
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(eng.fs.G[a:b], op=dist.ReduceOp.SUM, group=self.group)
+        if idx == len(self.buckets) - 1:
+            main.wait_stream(self.comm_stream)  # Adam consumes the reduced gradients
+
+    def broadcast_state(self, engine) -> None:
+        """Make every rank start from rank 0's weights / Adam state / running statistics."""
+        fs = engine.fs
+        for t in (fs.P, fs.M, fs.V, fs.S, fs.NBT, fs.step):
+            dist.broadcast(t, src=0, group=self.group)
+        fs.refresh_shadows()
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """(rank, local_rank, world) from torchrun's environment; initialises the default process group if world > 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local_rank, world
+
+
+def shard_batch(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Rows [begin, end) of the global batch owned by ``rank`` (contiguous, equal shards)."""
+    if global_batch % world != 0:
+        raise ValueError(f"global batch {global_batch} is not divisible by the world size {world}")
+    per = global_batch // world
+    return rank * per, (rank + 1) * per

@@ -213,7 +213,7 @@ class EncoderPlan:
         self.mask = torch.ones(B, device=dev)            # per-sample missing-modality mask
         self.pooled = torch.zeros(B, 512, device=dev)
         self.dpooled = torch.zeros(B, 512, device=dev)
-        self._scratch_floats = 0
+        self.taps: Dict[str, torch.Tensor] = {}  # stored intermediates by name (NHWC bf16), for tests / inspection
         self._build(train)
 
     # -- helpers -----------------------------------------------------------------------------------------------
@@ -247,6 +247,7 @@ class EncoderPlan:
         dw_stem = fs.flat_slice(fs.G, pre + "conv1.weight")
         raw0, act0 = self._act(B, P0, Q0, 64), self._act(B, P0, Q0, 64)
         pool, amax = self._act(B, P1, Q1, 64), torch.zeros(B, P1, Q1, 64, device=dev, dtype=torch.uint8)
+        self.taps.update({"conv1": raw0, "relu1": act0, "maxpool": pool})
         tiles0 = ops.stem_stat_tiles(B, self.H, self.W)
         part0 = torch.zeros(tiles0, 64, 2, device=dev)
         bn0 = self._bn("bn1", 64)
@@ -276,6 +277,7 @@ class EncoderPlan:
             w1t, w2t = fs.flat_slice(fs.Wt, n1), fs.flat_slice(fs.Wt, n2)
             dw1, dw2 = fs.flat_slice(fs.G, n1), fs.flat_slice(fs.G, n2)
             raw1, a1, raw2, out = (self._act(B, oH, oW, outC) for _ in range(4))
+            self.taps.update({f"{bname}.conv1": raw1, f"{bname}.relu1": a1, f"{bname}.conv2": raw2, bname: out})
             t1, t2 = ops.conv_stat_tiles(g1), ops.conv_stat_tiles(g2)
             part1, part2 = torch.zeros(t1, outC, 2, device=dev), torch.zeros(t2, outC, 2, device=dev)
             bn1, bn2 = self._bn(f"{bname}.bn1", outC), self._bn(f"{bname}.bn2", outC)
@@ -285,6 +287,7 @@ class EncoderPlan:
                 nd = f"{pre}{bname}.downsample.0.weight"
                 wd, wdt, dwd = fs.flat_slice(fs.Wb, nd), fs.flat_slice(fs.Wt, nd), fs.flat_slice(fs.G, nd)
                 rawd = self._act(B, oH, oW, outC)
+                self.taps[f"{bname}.downsample"] = rawd
                 td = ops.conv_stat_tiles(gd)
                 partd = torch.zeros(td, outC, 2, device=dev)
                 bnd = self._bn(f"{bname}.downsample.1", outC)

@@ -1,0 +1,73 @@
+"""FedAvg weighted parameter aggregation on the GPU (BASELINE.json config 5).
+
+The reference has NO federated implementation: ``MML_Suite/train_congruent_federated.py`` and friends are empty files,
+only ``federated/federated_utils.py:7-41`` (base64 of ``torch.save``) exists.  This module provides what that script
+would need on the aggregation path: theta <- sum_k (n_k / sum_j n_j) * theta_k over the clients' flat parameter buffers
+(float parameters and BatchNorm running statistics; ``num_batches_tracked`` is taken from client 0), as ONE HBM-bound
+kernel over K flat buffers (mml_fedavg), or -- when every client lives on its own GPU -- as an in-place pre-scale
+followed by a sum all-reduce over NCCL.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+
+
+def weights_from_counts(num_samples: Sequence[float], device) -> torch.Tensor:
+    n = torch.tensor([float(v) for v in num_samples], dtype=torch.float64)
+    if (n < 0).any() or float(n.sum()) <= 0:
+        raise ValueError("client sample counts must be non-negative with a positive sum")
+    return (n / n.sum()).to(torch.float32).to(device)
+
+
+def aggregate_flat(buffers: List[torch.Tensor], num_samples: Sequence[float], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[i] = sum_k w_k * buffers[k][i]; buffers: K contiguous fp32 CUDA tensors of equal length."""
+    K = len(buffers)
+    if K == 0 or K != len(num_samples):
+        raise ValueError("need one sample count per client")
+    n = buffers[0].numel()
+    for b in buffers:
+        if b.numel() != n or b.dtype != torch.float32 or not b.is_cuda or not b.is_contiguous():
+            raise ValueError("client buffers must be contiguous fp32 CUDA tensors of equal length")
+    dev = buffers[0].device
+    w = weights_from_counts(num_samples, dev)
+    ptrs = torch.tensor([b.data_ptr() for b in buffers], dtype=torch.int64, device=dev)
+    if out is None:
+        out = torch.empty(n, device=dev)
+    ops.fedavg(ptrs, w, K, out)
+    return out
+
+
+def federated_round(models: Sequence[torch.nn.Module], num_samples: Sequence[float]) -> None:
+    """Aggregate K client models that live on ONE GPU and push the average back into every client (in place)."""
+    engines = []
+    for m in models:
+        p = next(m.parameters())
+        engines.append(m._get_engine(p.device))
+    for attr in ("P", "S"):
+        bufs = [getattr(e.fs, attr) for e in engines]
+        avg = aggregate_flat(bufs, num_samples)
+        for b in bufs:
+            b.copy_(avg)
+    for e in engines[1:]:
+        e.fs.NBT.copy_(engines[0].fs.NBT)
+    for e in engines:
+        e.fs.refresh_shadows()
+
+
+def federated_allreduce(model: torch.nn.Module, my_num_samples: float, group=None) -> None:
+    """One client per rank/GPU: pre-scale by n_k / sum n, then sum all-reduce (NCCL) of parameters and running stats."""
+    import torch.distributed as dist
+
+    eng = model._get_engine(next(model.parameters()).device)
+    n = torch.tensor([float(my_num_samples)], device=eng.device, dtype=torch.float64)
+    dist.all_reduce(n, group=group)
+    w = torch.tensor([float(my_num_samples) / float(n.item())], device=eng.device, dtype=torch.float32)
+    for buf in (eng.fs.P, eng.fs.S):
+        ops.scale_inplace(buf, w, 0)
+        dist.all_reduce(buf, group=group)
+    dist.broadcast(eng.fs.NBT, src=0, group=group)
+    eng.fs.refresh_shadows()

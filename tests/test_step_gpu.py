@@ -1,0 +1,212 @@
+"""End-to-end GPU parity of the fused late-fusion step (mml_b200.AVMNIST.train_step) against the CPU oracle.
+
+Tolerances and why (DESIGN.md "Numerics"):
+  * The reference is fp32; the B200 path stores activations / activation-gradients as bf16 with fp32 accumulation (the
+    north star's precision).  At random initialisation the 34-layer BN/ReLU stack is ill-conditioned: perturbing the
+    reference's OWN weights by 1e-3 relative (less than one bf16 rounding) in fp64 already moves its gradients by
+    30-45 % (cosine 0.90-0.95) because ReLU masks flip.  An un-forced gradient comparison therefore measures the
+    reference's conditioning, not the kernels.
+  * So gradients are checked "teacher forced": the oracle's backward runs over the activations the GPU stored
+    (same ReLU masks, same BN statistics), which is a linear, well-conditioned comparison -> tight tolerance.
+  * Un-forced: loss within 1e-2, logits within 10 % of the logit range, and a matched loss curve over 100 steps.
+"""
+import copy
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+import late_fusion_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class Term:
+    def __init__(self):
+        self.loss_fn, self.weight = torch.nn.CrossEntropyLoss(), 1.0
+
+
+LOSS = {"cross_entropy": Term()}
+
+
+def build(dropout=0.5, graphs=True):
+    from mml_b200.avmnist import AVMNIST
+    from mml_b200.resnet import ResNet18, ResNet34
+
+    torch.manual_seed(0)
+    model = AVMNIST(ResNet18(1, 64), ResNet34(1, 128), 128, dropout=dropout).to(DEV)
+    eng = model._get_engine(torch.device(DEV))
+    eng.use_graphs = graphs
+    return model
+
+
+def make_batch(d, B):
+    return {"audio_original": d["audio"], "audio_missing_index": d["audio_mask"], "image_original": d["image"],
+            "image_missing_index": d["image_mask"], "labels": d["labels"], "pattern_name": ["ai"] * B}
+
+
+def nchw(t):
+    return t.detach().float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def forced_from_plan(plan):
+    forced = {}
+    for pre, ep in (("audio_encoder.", plan.audio), ("image_encoder.", plan.image)):
+        for name, t in ep.taps.items():
+            forced[pre + name] = nchw(t)
+        forced[pre + "avgpool"] = ep.pooled.detach().cpu().clone()
+    return forced
+
+
+@pytest.mark.parametrize("B,hw", [(16, (112, 112)), (6, (32, 94))])
+def test_forced_backward_parity(B, hw):
+    model = build(graphs=False)
+    torch.manual_seed(0)
+    state = O.init_avmnist_state()
+    d = O.synthetic_batch(B, 1234, hw)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
+    out = model.train_step(make_batch(d, B), opt, LOSS, torch.device(DEV), None, dropout_mask=d["dropout_mask"])
+    plan = next(iter(model._engine.plans.values()))
+    A = O.apply_missing_mask(d["audio"], d["audio_mask"])
+    I = O.apply_missing_mask(d["image"], d["image_mask"])
+    ref = O.train_step(copy.deepcopy(state), {}, A, I, d["labels"], d["dropout_mask"], 0.5, apply_update=False, forced=forced_from_plan(plan))
+    assert abs(out["loss"] - ref["loss"]) < 1e-4
+    assert (plan.logits.cpu() - ref["logits"]).abs().max().item() < 1e-4
+    assert torch.equal(plan.pred.cpu().long(), ref["predictions"])
+    worst = []
+    for name, p in model.named_parameters():
+        g, r = p.grad.detach().cpu().float(), ref["grads"][name]
+        worst.append((float((g - r).norm() / (r.norm() + 1e-12)), name))
+    worst.sort(reverse=True)
+    print("worst forced-gradient errors:", worst[:8])
+    gall = torch.cat([p.grad.detach().cpu().float().reshape(-1) for _, p in model.named_parameters()])
+    rall = torch.cat([ref["grads"][n].reshape(-1) for n, _ in model.named_parameters()])
+    glob = float((gall - rall).norm() / rall.norm())
+    print("global forced-gradient rel L2:", glob)
+    assert glob < 3e-2, glob
+    assert worst[0][0] < 1.5e-1, worst[:5]
+    # BatchNorm running statistics follow the reference update rule on the GPU's own batch statistics
+    sd = model.state_dict()
+    assert int(sd["audio_encoder.bn1.num_batches_tracked"]) == 1 and int(sd["image_encoder.layer4.2.bn2.num_batches_tracked"]) == 1
+    assert sd["audio_encoder.conv1.weight"].shape == (64, 1, 7, 7) and sd["image_encoder.layer3.5.conv2.weight"].shape == (256, 256, 3, 3)
+
+
+def test_unforced_loss_logits_and_adam_update():
+    B = 32
+    model = build(graphs=False)
+    torch.manual_seed(0)
+    state = O.init_avmnist_state()
+    d = O.synthetic_batch(B, 77, (112, 112))
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    out = model.train_step(make_batch(d, B), opt, LOSS, torch.device(DEV), None, dropout_mask=d["dropout_mask"])
+    plan = next(iter(model._engine.plans.values()))
+    A = O.apply_missing_mask(d["audio"], d["audio_mask"])
+    ref = O.train_step(copy.deepcopy(state), {}, A, d["image"], d["labels"], d["dropout_mask"], 0.5, apply_update=False)
+    assert abs(out["loss"] - ref["loss"]) < 1e-2
+    rng = float(ref["logits"].max() - ref["logits"].min())
+    assert (plan.logits.cpu() - ref["logits"]).abs().max().item() < 0.10 * rng
+    # Adam: the fused update applied exactly torch's rule to the GPU's own gradients
+    for n, p in model.named_parameters():
+        g = p.grad.detach()
+        gr = g + 1e-4 * before[n]
+        m = 0.1 * gr
+        v = 0.001 * gr * gr
+        upd = before[n] - (5e-4 / 0.1) * m / (v.sqrt() / (0.001 ** 0.5) + 1e-8)
+        assert torch.allclose(p.detach(), upd, rtol=1e-5, atol=1e-7), n
+        st = opt.state[p]
+        assert st["exp_avg"].data_ptr() == model._engine.fs.M.data_ptr() + 4 * model._engine.fs.offsets[n]
+        assert float(st["step"]) == 1.0
+
+
+def test_loss_curve_100_steps_matches_reference():
+    B, steps = 32, 100
+    model = build()
+    torch.manual_seed(0)
+    state = O.init_avmnist_state()
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
+    opt_state = {}
+    # a small fixed pool of batches, cycled: the loss must go down the same way in both implementations
+    pool = [O.synthetic_batch(B, 500 + i, (112, 112)) for i in range(4)]
+    gpu, ref = [], []
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    for s in range(steps):
+        d = pool[s % len(pool)]
+        gpu.append(model.train_step(make_batch(d, B), opt, LOSS, torch.device(DEV), None, dropout_mask=d["dropout_mask"])["loss"])
+        A = O.apply_missing_mask(d["audio"], d["audio_mask"])
+        ref.append(O.train_step(state, opt_state, A, d["image"], d["labels"], d["dropout_mask"], 0.5)["loss"])
+    gpu, ref = np.array(gpu), np.array(ref)
+    print("loss curve gpu:", np.round(gpu[::10], 4), "\nloss curve ref:", np.round(ref[::10], 4))
+    assert np.all(np.isfinite(gpu))
+    assert np.abs(gpu[:5] - ref[:5]).max() < 2e-2
+    k = 10
+    sm_g, sm_r = np.convolve(gpu, np.ones(k) / k, "valid"), np.convolve(ref, np.ones(k) / k, "valid")
+    assert np.abs(sm_g - sm_r).max() < 0.15 * max(ref[0], 1.0), np.abs(sm_g - sm_r).max()
+    assert gpu[-10:].mean() < 0.5 * gpu[0] and ref[-10:].mean() < 0.5 * ref[0]
+
+
+def test_graph_replay_equals_eager_and_eval_roundtrip():
+    B = 16
+    d = O.synthetic_batch(B, 9, (112, 112))
+    losses = {}
+    for graphs in (False, True):
+        model = build(graphs=graphs)
+        opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
+        ls = [model.train_step(make_batch(d, B), opt, LOSS, torch.device(DEV), None, dropout_mask=d["dropout_mask"])["loss"] for _ in range(5)]
+        losses[graphs] = ls
+    # steps 3-4 of the graph run are replays; split-K wgrad uses fp32 atomics => tiny run-to-run differences allowed
+    assert np.allclose(losses[False], losses[True], rtol=0, atol=3e-2), losses  # chaotic amplification of atomic-order noise, see module docstring
+    # eval forward == validation_step, and a state_dict round trip reproduces it bit for bit
+    A = O.apply_missing_mask(d["audio"], d["audio_mask"]).to(DEV)
+    I = d["image"].to(DEV)
+    model.eval()
+    ev = model.forward(A=A, I=I)
+    vs = model.validation_step({"audio": A, "image": I, "labels": d["labels"], "pattern_name": ["ai"] * B}, LOSS, torch.device(DEV), None, return_test_info=True)
+    assert np.array_equal(vs["predictions"], ev.argmax(1).cpu().numpy())
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    # fp32 oracle in eval mode on the trained weights: running-stat BN, no dropout
+    ref = O.validation_step(OrderedDict((k, v.contiguous()) for k, v in sd.items()), A.cpu(), I.cpu(), d["labels"])
+    rng = float(ref["logits"].max() - ref["logits"].min())
+    assert (ev.cpu() - ref["logits"]).abs().max().item() < 0.05 * rng + 1e-2
+    assert abs(vs["loss"] - ref["loss"]) < 2e-2
+    model2 = build()
+    model2.load_state_dict(sd, strict=True)
+    model2.eval()
+    ev2 = model2.forward(A=A, I=I)
+    assert torch.equal(ev, ev2)
+
+
+def test_premasked_batch_equals_device_mask():
+    """Reference batch contract (already masked tensors under Modality keys) == *_original + *_missing_index on device."""
+    B = 8
+    d = O.synthetic_batch(B, 3, (112, 112))
+    A = O.apply_missing_mask(d["audio"], d["audio_mask"])
+
+    class Modality:  # stand-in for the un-vendored enum: str() gives the lower-case name
+        def __init__(self, n):
+            self.n = n
+
+        def __str__(self):
+            return self.n
+
+    res = []
+    for batch in (make_batch(d, B), {Modality("audio"): A, Modality("image"): d["image"], "labels": d["labels"], "pattern_name": ["ai"] * B}):
+        model = build(graphs=False)
+        opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
+        model.train_step(batch, opt, LOSS, torch.device(DEV), None, dropout_mask=d["dropout_mask"])
+        plan = next(iter(model._engine.plans.values()))
+        res.append((plan.audio.taps["conv1"].clone(), plan.logits.clone()))
+    assert torch.equal(res[0][0], res[1][0])  # stem output identical bit for bit => mask applied identically
+
+
+def test_unsupported_requests_fail_loudly():
+    model = build()
+    d = O.synthetic_batch(4, 1, (112, 112))
+    sgd = torch.optim.SGD(model.parameters(), lr=0.1)
+    with pytest.raises(NotImplementedError):
+        model.train_step(make_batch(d, 4), sgd, LOSS, torch.device(DEV), None)
+    with pytest.raises(NotImplementedError):
+        model.forward(A=d["audio"].to(DEV), I=None)

@@ -36,12 +36,13 @@ def main():
     A = O.apply_missing_mask(d["audio"], d["audio_mask"])
     I = O.apply_missing_mask(d["image"], d["image_mask"])
     opt_state = {}
+    emu = os.environ.get("EMU", "0") == "1"
     for step in range(steps):
         t0 = time.time()
         out = model.train_step(batch, opt, {"cross_entropy": Term()}, dev, None, dropout_mask=d["dropout_mask"])
         torch.cuda.synchronize()
         t1 = time.time()
-        ref = O.train_step(state, opt_state, A, I, d["labels"], d["dropout_mask"], 0.5)
+        ref = O.train_step(state, opt_state, A, I, d["labels"], d["dropout_mask"], 0.5, emulate_bf16=emu)
         plan = next(iter(model._engine.plans.values()))
         lg = plan.logits.cpu()
         print(f"step {step}: loss gpu {out['loss']:.6f} ref {ref['loss']:.6f} | max|dlogit| {(lg - ref['logits']).abs().max():.4e} (max|logit| {ref['logits'].abs().max():.3f}) "
@@ -55,6 +56,10 @@ def main():
                 cos = float((g * r).sum() / (g.norm() * r.norm() + 1e-20))
                 worst.append((rel, cos, name, float(r.norm())))
             worst.sort(reverse=True)
+            for enc in ("audio_encoder.", "image_encoder.", "net."):
+                ga = torch.cat([p.grad.detach().cpu().float().reshape(-1) for n, p in model.named_parameters() if n.startswith(enc)])
+                ra = torch.cat([ref["grads"][n].reshape(-1) for n, _ in model.named_parameters() if n.startswith(enc)])
+                print(f"  {enc:16s} rel L2 {float((ga - ra).norm() / ra.norm()):.4f} cosine {float((ga * ra).sum() / (ga.norm() * ra.norm())):.5f}")
             print("worst gradient tensors (rel L2 err, cosine, name, |ref|):")
             for w in worst[:25]:
                 print("   %.4f  %.5f  %-50s %.3e" % w)
