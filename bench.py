@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- AVMNIST late-fusion training throughput on B200 (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch 256]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one synthetic batch: mask -> ResNet18(audio 112x112) + ResNet34(image 28x28)
+forward -> concat head -> softmax-CE -> backward -> [NCCL allreduce] -> Adam  (BASELINE.json configs[1]: batch 256 per
+GPU, audio missing_rate 0.2, bf16 operands / fp32 accumulation).  One JSON line is printed by rank 0:
+  value   samples/s, whole job, inputs already resident in HBM (CUDA-graph replays, CUDA events, max over ranks)
+  e2e     the same metric through the public API  AVMNIST.train_step(batch, optimizer, loss_functions, device,
+          metric_recorder)  with pinned HOST buffers: H2D of the batch and D2H of loss + predictions inside the timed region
+  roofline  the dominant kernel (tcgen05 implicit-GEMM conv) timed alone with CUDA events vs the measured bf16 peak
+  cpu_baseline  the reference's CPU path (oracle port of MML_Suite, fp32, all host cores) on a bounded sample
+--impl reference times that CPU path as its own arm (the reference is Python and cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "avmnist_late_fusion_train_samples_per_s"
+UNIT = "samples/s"
+TRAIN_GFLOP_PER_SAMPLE = 3.1889  # dense nominal fwd+dgrad+wgrad, SURVEY.md section 8d / BASELINE.md section 3
+CPU_SAMPLE_BATCH = 32            # BASELINE.json configs[0]: the reference's own CPU-runnable case
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "tf_burst": float(p["bf16_tflops"]), "tf_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's path restated (oracle/late_fusion_oracle.py, pinned against the imported reference)
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int, budget_s: float = 25.0):
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import late_fusion_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    state = O.init_avmnist_state()
+    d = O.synthetic_batch(CPU_SAMPLE_BATCH, 0)
+    A = O.apply_missing_mask(d["audio"], d["audio_mask"])
+    I = O.apply_missing_mask(d["image"], d["image_mask"])
+    opt_state = {}
+    for _ in range(max(1, warmup)):
+        O.train_step(state, opt_state, A, I, d["labels"], d["dropout_mask"], 0.5)
+    times = []
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.train_step(state, opt_state, A, I, d["labels"], d["dropout_mask"], 0.5)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s and len(times) >= 3:
+            break
+    per = statistics.median(times)
+    return {"value": CPU_SAMPLE_BATCH / per, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(times)} train steps (zero_grad/forward/CE/backward/Adam) of the oracle port at batch {CPU_SAMPLE_BATCH}, fp32, torch CPU, median step {per * 1e3:.0f} ms",
+            "steps_timed": len(times), "ms_per_step": per * 1e3}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps_timed"], "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {"workload": "AVMNIST late-fusion train step: ResNet18 audio 112x112 + ResNet34 image 28x28, concat head, CE, Adam; audio missing_rate 0.2",
+            "batch_per_gpu": args.batch, "global_batch": args.batch * world, "parallelism": f"dp{world}",
+            "l2_policy": "per-step working set (~2.5 GB of bf16 activations + 0.9 GB optimizer state) exceeds the 126 MB L2; no explicit flush",
+            "timing": "CUDA events around K CUDA-graph replays, barrier + synchronize on both sides, max over ranks"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------------------
+class _Term:
+    def __init__(self, fn):
+        self.loss_fn, self.weight = fn, 1.0
+
+
+def dominant_kernel_roofline(torch, ops, B, pk):
+    """Times the dominant kernel type alone: the tcgen05 implicit-GEMM fprop of ResNet18 layer1 (C=K=64, 28x28), the
+    shape with the largest share of the step (8 fprop/dgrad launches of it per step)."""
+    N, H, W, C, K = B, 28, 28, 64, 64
+    g = ops.make_geom(N, H, W, C, K, 3, 3, 1, 1)
+    x = torch.randn(N, H, W, C, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(K, 3, 3, C, device="cuda") * 0.05).to(torch.bfloat16)
+    y = torch.empty(N, H, W, K, device="cuda", dtype=torch.bfloat16)
+    part = torch.zeros(ops.conv_stat_tiles(g), K, 2, device="cuda")
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > L2
+    for _ in range(3):
+        ops.conv_fprop(g, x, w, y, part)
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.conv_fprop(g, x, w, y, part)
+        e1.record()
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1) * 1e-3)
+    t = statistics.median(times)
+    flops = 2.0 * N * H * W * K * C * 9
+    ach = flops / t / 1e12
+    return {"bound": "tensor", "kernel": "conv_igemm_kernel<64,3,2> fprop C=K=64 28x28 (ResNet18 layer1)", "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+            "frac": ach / pk["tf_burst"], "traffic": None, "peak_source": f"{pk['src']} bf16 burst (kernel timed alone, L2 flushed between launches)",
+            "flops_per_launch": flops, "us_per_launch": t * 1e6}
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from mml_b200 import dist as mdist
+    from mml_b200 import ops
+    from mml_b200.avmnist import AVMNIST
+    from mml_b200.resnet import ResNet18, ResNet34
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import late_fusion_oracle as O  # synthetic input generator + cpu_baseline leg only
+
+    rank, local_rank, world = mdist.init_from_env("nccl")
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pk = peaks()
+    B = args.batch
+
+    torch.manual_seed(0)  # identical weights on all ranks
+    model = AVMNIST(ResNet18(1, 64), ResNet34(1, 128), 128, dropout=0.5).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
+    loss_fns = {"cross_entropy": _Term(torch.nn.CrossEntropyLoss())}
+    if world > 1:
+        dp = mdist.DataParallel()
+        model.enable_data_parallel(dp)
+    eng = model._get_engine(dev)
+    if world > 1:
+        dp.broadcast_state(eng)
+
+    d = O.synthetic_batch(B, 1234 + rank)  # per-rank data, Bernoulli(0.8) audio mask
+    host = {"audio_original": d["audio"].pin_memory(), "audio_missing_index": d["audio_mask"].pin_memory(), "image_original": d["image"].pin_memory(),
+            "image_missing_index": d["image_mask"].pin_memory(), "labels": d["labels"].pin_memory(), "pattern_name": ["ai"] * B}
+    h2d = sum(host[k].numel() * host[k].element_size() for k in host if k != "pattern_name")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up through the public API (also builds the plan and captures the CUDA graph) --------------------------
+    for _ in range(max(args.warmup, 3)):
+        model.train_step(host, opt, loss_fns, dev, None)
+    plan = next(iter(eng.plans.values()))
+    launches_per_step = plan.launches_per_step
+
+    # ---- (1) device-resident throughput ------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        plan.train_step(given_dropout=False)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    t_dev = float(dt.item())
+    eng.fs._host_step += args.steps
+
+    # ---- (2) end to end through AVMNIST.train_step with host buffers ----------------------------------------------------
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = model.train_step(host, opt, loss_fns, dev, None)
+    e1.record()
+    barrier()
+    dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    t_e2e = float(dt.item())
+    d2h = 4 + 4 * B
+
+    if rank != 0:
+        return
+    value = B * world * args.steps / t_dev
+    e2e_value = B * world * args.steps / t_e2e
+    roof = dominant_kernel_roofline(torch, ops, B, pk)
+    step_tf = TRAIN_GFLOP_PER_SAMPLE * B * args.steps / t_dev / 1e3
+    cpu = cpu_reference_run(12, 2)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / args.steps * 1e3},
+        "gpu_launches": launches_per_step * args.steps,
+        "launches_per_step": launches_per_step,
+        "clocks": clocks,
+        "roofline": roof,
+        "step_tensor_roofline": {"achieved": step_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": step_tf / pk["tf_sustained"],
+                                 "note": f"{TRAIN_GFLOP_PER_SAMPLE} dense-nominal GFLOP/sample x samples/s per GPU vs {pk['src']} sustained bf16"},
+        "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "last_loss": out["loss"],
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="samples per GPU (BASELINE.json configs[1])")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+    try:
+        import torch.distributed as dist
+
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()
