@@ -1,0 +1,52 @@
+"""Registration shim: make the reference's own entry points build the B200 classes, with zero YAML / script changes.
+
+    import mml_b200.shim as shim; shim.install()      # before StandardMultimodalConfig.load(...)
+
+What it re-binds (reference file:line):
+  * YAML tags ``!ResNet18`` / ``!ResNet34`` / ``!ResNetEncoder`` (MML_Suite/config/yaml_constructors.py:159-178) ->
+    ``mml_b200.resnet`` factories (``yaml.SafeLoader.add_constructor`` replaces the earlier registration);
+  * ``resolve_model_name("avmnist")`` (MML_Suite/config/resolvers.py:18-22 does ``from models.avmnist import AVMNIST``
+    at call time) -> the attribute ``models.avmnist.AVMNIST`` is replaced by ``mml_b200.avmnist.AVMNIST``;
+  * ``models.msa.networks.resnet.ResNet18/ResNet34/ResNetEncoder`` for scripts that import them directly
+    (MML_Suite/train_monomodal.py).
+Works without the reference on the path too (then only the YAML tags are registered).
+"""
+from __future__ import annotations
+
+import sys
+from typing import Dict
+
+_installed: Dict[str, object] = {}
+
+
+def install(patch_reference_modules: bool = True) -> Dict[str, object]:
+    import yaml
+
+    from .avmnist import AVMNIST
+    from .resnet import ResNet18, ResNet34, ResNetEncoder
+
+    def register(tag, factory):
+        def construct(loader, node):
+            return factory(**loader.construct_mapping(node, deep=True))
+
+        yaml.SafeLoader.add_constructor(tag, construct)
+        _installed[tag] = factory
+
+    register("!ResNet18", ResNet18)
+    register("!ResNet34", ResNet34)
+    register("!ResNetEncoder", ResNetEncoder)
+    if patch_reference_modules:
+        ref_av = sys.modules.get("models.avmnist")
+        if ref_av is None:
+            try:
+                import models.avmnist as ref_av  # noqa: F401  (only importable when MML_Suite is on sys.path)
+            except Exception:
+                ref_av = None
+        if ref_av is not None:
+            _installed["reference.AVMNIST"] = getattr(ref_av, "AVMNIST", None)
+            ref_av.AVMNIST = AVMNIST
+        ref_rn = sys.modules.get("models.msa.networks.resnet")
+        if ref_rn is not None:
+            ref_rn.ResNet18, ref_rn.ResNet34, ref_rn.ResNetEncoder = ResNet18, ResNet34, ResNetEncoder
+    _installed["AVMNIST"] = AVMNIST
+    return dict(_installed)

@@ -88,3 +88,30 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "late_fusion_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_shim_registers_yaml_tags_and_swaps_reference_model():
+    import yaml
+
+    from mml_b200 import shim
+    from mml_b200.avmnist import AVMNIST
+    from mml_b200.resnet import ResNetEncoder
+
+    got = shim.install()
+    enc = yaml.safe_load("enc: !ResNet18\n  in_channels: 1\n  hidden_dim: 64\n")["enc"]
+    assert isinstance(enc, ResNetEncoder) and enc.get_embedding_size() == 64
+    enc34 = yaml.safe_load("enc: !ResNet34\n  hidden_dim: 128\n")["enc"]
+    assert len(enc34.blocks()) == 16
+    assert got["AVMNIST"] is AVMNIST
+    # with the reference importable (build container only) the resolver must hand out the B200 class
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import ref_import
+
+    if ref_import.reference_available():
+        ref_import.import_reference()
+        shim.install()
+        from config.resolvers import resolve_model_name
+
+        assert resolve_model_name("avmnist") is AVMNIST
+        cfg = yaml.safe_load("a: !ResNet18\n  in_channels: 1\n  hidden_dim: 64\n")
+        assert isinstance(cfg["a"], ResNetEncoder)
