@@ -68,8 +68,8 @@ int64_t mml_stem_wgrad_workspace(const mml_ctx*, int B, int H, int W);
 int mml_conv_stat_tiles(const mml_conv_geom* g);
 int mml_conv_fprop(mml_ctx*, const mml_conv_geom* g, const uint16_t* x, const uint16_t* w_krsc, uint16_t* y,
                    float* stats_partial, void* stream);
-/* dgrad: dx [N,H,W,C] = conv_transpose(dy [N,P,Q,K], w); w_crsk is the transposed copy W_t[c][r][s][k] = W[k][r][s][c] */
-int mml_conv_dgrad(mml_ctx*, const mml_conv_geom* g, const uint16_t* dy, const uint16_t* w_crsk, uint16_t* dx, void* stream);
+/* dgrad: dx [N,H,W,C] = conv_transpose(dy [N,P,Q,K], w); reads the SAME K,R,S,C weights as fprop (MN-major B operand) */
+int mml_conv_dgrad(mml_ctx*, const mml_conv_geom* g, const uint16_t* dy, const uint16_t* w_krsc, uint16_t* dx, void* stream);
 /* wgrad: dw_krsc fp32 [K][R][S][C] += sum_{n,p,q} dy * x   (ACCUMULATES: caller zeroes the gradient buffer) */
 int mml_conv_wgrad(mml_ctx*, const mml_conv_geom* g, const uint16_t* x, const uint16_t* dy, float* dw_krsc, void* stream);
 

@@ -11,7 +11,8 @@
 // rows land in shared memory as 128-byte rows with SWIZZLE_128B, which is exactly the canonical K-major UMMA operand
 // layout.  The same box of the output tensor is written back by a TMA store from a swizzled staging buffer.
 //   fprop           : in = x, W = w[K][R][S][C],            out = y      (+ per-tile BatchNorm partial sums)
-//   dgrad           : in = dy, W = w_t[C][R][S][K],          out = dx     (stride 2: one launch per output phase)
+//   dgrad           : in = dy, W = the same w[K][R][S][C] read as an MN-major B operand, out = dx (stride 2: one launch per
+//                     output phase)
 //   wgrad           : dW[k][t][c] += sum_pixels dy[pix][k] * in_view[t][pix][c]   (both operands MN-major)
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma issuer,
 // warps 2-5 = epilogue (TMEM -> registers -> bf16 -> swizzled smem -> TMA store, BatchNorm partials from smem).
@@ -41,7 +42,8 @@ struct alignas(64) IgemmMaps {
 
 struct IgemmParams {
   int num_taps;
-  int c_chunks;  // Cin / 64
+  int c_chunks;  // Cin / 64  (GEMM-K chunks per tap)
+  int w_tap_stride;  // elements between taps along the weight map's inner dimension
   int cin;
   int tiles_h;     // OutH / Hb
   int Hb, Nb;      // tile = {OutW, Hb, Nb}
@@ -65,7 +67,10 @@ struct IgemmSmem {
 // ------------------------------------------------------------------------------------------------------------------
 // fprop / dgrad kernel
 // ------------------------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int STAGES, int MIN_BLOCKS>
+// B_MN = false: weights are [N rows][taps*K inner] (fprop: W[k][r][s][c]), B operand K-major.
+// B_MN = true : weights are [K rows][taps*N inner] (dgrad reads the SAME K,R,S,C tensor: GEMM-K = k, GEMM-N = c), B operand
+//               MN-major: 64-row x 64-element boxes, 8 KB each, one per 64 output channels.
+template <int BLOCK_N, int STAGES, int MIN_BLOCKS, bool B_MN>
 __global__ void __launch_bounds__(192, MIN_BLOCKS)
 conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
   using L = IgemmSmem<BLOCK_N, STAGES>;
@@ -124,14 +129,20 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
           mbar_arrive_expect_tx(full_bar(s), tx_bytes);
           const uint32_t a_dst = smem_base + s * L::kStage;
           tma_load_4d(in_map, full_bar(s), a_dst, cc * 64, tap.dw, a0 + tap.dh, n0);
-          tma_load_2d(&maps.w, full_bar(s), a_dst + L::kA, tap.widx * p.cin + cc * 64, n_tile * BLOCK_N);
+          if (!B_MN) {
+            tma_load_2d(&maps.w, full_bar(s), a_dst + L::kA, tap.widx * p.w_tap_stride + cc * 64, n_tile * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(&maps.w, full_bar(s), a_dst + L::kA + j * 8192, tap.widx * p.w_tap_stride + n_tile * BLOCK_N + j * 64, cc * 64);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, B_MN ? 1 : 0);
       for (int it = 0; it < iters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -142,7 +153,9 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-          const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+          // K-major: +32 B per 16 K-elements inside the swizzle atom.  MN-major: 16 K-rows = 2 KB further down; the next
+          // 64 N-elements are one 8 KB box away (LBO).
+          const uint64_t db = B_MN ? umma_desc_sw128(b_addr + k * 2048, 8192, 1024) : umma_desc_sw128(b_addr + k * 32, 16, 1024);
           umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
         }
         umma_commit(empty_bar(s));  // frees the smem slot once these MMAs have read it
@@ -475,24 +488,24 @@ int set_smem_limit(mml_ctx* ctx, K kernel, int bytes) {
   return MML_OK;
 }
 
-template <int BLOCK_N, int STAGES, int MIN_BLOCKS>
+template <int BLOCK_N, int STAGES, int MIN_BLOCKS, bool B_MN>
 int launch_igemm_t(mml_ctx* ctx, const IgemmMaps& maps, const IgemmParams& p, dim3 grid, cudaStream_t st) {
   using L = IgemmSmem<BLOCK_N, STAGES>;
   static bool configured = false;
   if (!configured) {
-    int rc = set_smem_limit(ctx, conv_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS>, L::kBytes);
+    int rc = set_smem_limit(ctx, conv_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS, B_MN>, L::kBytes);
     if (rc) return rc;
     configured = true;
   }
-  conv_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS><<<grid, 192, L::kBytes, st>>>(maps, p);
+  conv_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS, B_MN><<<grid, 192, L::kBytes, st>>>(maps, p);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }
 
 // One "shifted GEMM" launch: out view <- sum over taps of in views @ weights.
-//   w: [cout rows][w_inner = n_wtaps*cin] bf16
+//   b_mn = false: w is [cout rows][n_wtaps*cin inner] bf16;   b_mn = true: w is [cin rows][n_wtaps*cout inner] bf16
 int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, int n_wtaps, int cin, int cout, const View& out,
-              const Tap* taps, int num_taps, float* stats_partial, cudaStream_t st) {
+              const Tap* taps, int num_taps, float* stats_partial, bool b_mn, cudaStream_t st) {
   MML_REQUIRE(ctx, cin % 64 == 0 && cout % 64 == 0, "conv: channel counts must be multiples of 64 (got C=%d K=%d)", cin, cout);
   MML_REQUIRE(ctx, num_taps >= 1 && num_taps <= kMaxTaps && n_views <= kMaxViews, "conv: bad tap table");
   TileGeom tg;
@@ -503,12 +516,17 @@ int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, in
   for (int i = 0; i < n_views; ++i)
     if ((rc = encode_view(ctx, &maps.in[i], in_views[i], tg.Wb, tg.Hb, tg.Nb))) return rc;
   const int block_n = cout >= 256 ? 256 : cout;
-  if ((rc = encode_weights(ctx, &maps.w, w, (long long)n_wtaps * cin, cout, block_n))) return rc;
+  if (!b_mn) {
+    if ((rc = encode_weights(ctx, &maps.w, w, (long long)n_wtaps * cin, cout, block_n))) return rc;
+  } else {
+    if ((rc = encode_weights(ctx, &maps.w, w, (long long)n_wtaps * cout, cin, 64))) return rc;
+  }
   if ((rc = encode_view(ctx, &maps.out, out, tg.Wb, tg.Hb, tg.Nb))) return rc;
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   p.num_taps = num_taps;
   p.c_chunks = cin / 64;
+  p.w_tap_stride = b_mn ? cout : cin;
   p.cin = cin;
   p.tiles_h = tg.tiles_h;
   p.Hb = tg.Hb;
@@ -518,10 +536,18 @@ int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, in
   p.stats_partial = stats_partial;
   for (int i = 0; i < num_taps; ++i) p.taps[i] = taps[i];
   dim3 grid(tg.tiles_h * tg.tiles_n, cout / block_n);
-  switch (block_n) {
-    case 64: return launch_igemm_t<64, 3, 2>(ctx, maps, p, grid, st);
-    case 128: return launch_igemm_t<128, 4, 1>(ctx, maps, p, grid, st);
-    case 256: return launch_igemm_t<256, 3, 1>(ctx, maps, p, grid, st);
+  if (!b_mn) {
+    switch (block_n) {
+      case 64: return launch_igemm_t<64, 3, 2, false>(ctx, maps, p, grid, st);
+      case 128: return launch_igemm_t<128, 4, 1, false>(ctx, maps, p, grid, st);
+      case 256: return launch_igemm_t<256, 3, 1, false>(ctx, maps, p, grid, st);
+    }
+  } else {
+    switch (block_n) {
+      case 64: return launch_igemm_t<64, 3, 2, true>(ctx, maps, p, grid, st);
+      case 128: return launch_igemm_t<128, 4, 1, true>(ctx, maps, p, grid, st);
+      case 256: return launch_igemm_t<256, 3, 1, true>(ctx, maps, p, grid, st);
+    }
   }
   return mml_set_error(ctx, MML_ERR_INVALID, "conv: unsupported K=%d", cout);
 }
@@ -613,10 +639,10 @@ int mml_conv_fprop(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, cons
   }
   for (int i = 0; i < n_taps; ++i) taps[i].map = (int8_t)remap[taps[i].map];
   View out = make_phase_view(y, g->N, P, Q, g->K, 1, 0, 0);
-  return run_igemm(ctx, used, n_used, w_krsc, g->R * g->S, g->C, g->K, out, taps, n_taps, stats_partial, (cudaStream_t)stream);
+  return run_igemm(ctx, used, n_used, w_krsc, g->R * g->S, g->C, g->K, out, taps, n_taps, stats_partial, false, (cudaStream_t)stream);
 }
 
-int mml_conv_dgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* dy, const uint16_t* w_crsk, uint16_t* dx, void* stream) {
+int mml_conv_dgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* dy, const uint16_t* w_krsc, uint16_t* dx, void* stream) {
   int P, Q, rc;
   if ((rc = check_geom(ctx, g, &P, &Q))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -657,7 +683,8 @@ int mml_conv_dgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* dy, con
     }
   if (need_zero) MML_CHECK_CUDA(ctx, cudaMemsetAsync(dx, 0, (size_t)g->N * g->H * g->W * g->C * 2, st));
   for (int i = 0; i < n_launch; ++i) {
-    rc = run_igemm(ctx, &in, 1, w_crsk, g->R * g->S, g->K, g->C, launches[i].out, launches[i].taps, launches[i].n, nullptr, st);
+    // GEMM-K = k (rows of the K,R,S,C weight matrix), GEMM-N = c: the fprop weights are read as an MN-major B operand
+    rc = run_igemm(ctx, &in, 1, w_krsc, g->R * g->S, g->K, g->C, launches[i].out, launches[i].taps, launches[i].n, nullptr, true, st);
     if (rc) return rc;
   }
   return MML_OK;

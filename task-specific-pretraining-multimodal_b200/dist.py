@@ -52,12 +52,12 @@ class DataParallel:
         if idx >= len(self.buckets):
             return
         a, b = self.buckets[idx]
-        main = torch.cuda.current_stream(eng.device)
-        self.comm_stream.wait_stream(main)  # gradients of this bucket are complete in stream order
+        producer = torch.cuda.current_stream(eng.device)  # the stream whose backward just finished this bucket
+        self.comm_stream.wait_stream(producer)
         with torch.cuda.stream(self.comm_stream):
             dist.all_reduce(eng.fs.G[a:b], op=dist.ReduceOp.SUM, group=self.group)
         if idx == len(self.buckets) - 1:
-            main.wait_stream(self.comm_stream)  # Adam consumes the reduced gradients
+            producer.wait_stream(self.comm_stream)  # Adam (on the main stream) consumes the reduced gradients
 
     def broadcast_state(self, engine) -> None:
         """Make every rank start from rank 0's weights / Adam state / running statistics."""

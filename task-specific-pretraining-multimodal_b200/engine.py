@@ -9,7 +9,8 @@ Layout in HBM
   * ``FlatState``: every parameter lives in ONE fp32 buffer ``P`` (conv weights physically K,R,S,C == torch
     channels_last, exposed to PyTorch as OIHW views so ``state_dict()`` keeps the reference's 346 names/shapes/dtypes);
     gradients ``G``, Adam moments ``M``/``V`` mirror it element for element; ``Wb`` is the bf16 shadow the tensor-core
-    kernels read, ``Wt`` the per-conv C,R,S,K transpose used by dgrad.  BatchNorm running statistics live in ``S``.
+    kernels read (fprop as a K-major, dgrad as an MN-major B operand -- no transposed copy).  BatchNorm running
+    statistics live in ``S``.
   * activations: NHWC bf16, one static buffer per conv output ("raw") and per block activation, kept for backward.
   * one schedule of closures per (batch, input size); after two eager steps it is captured into a CUDA graph.
 """
@@ -60,7 +61,6 @@ class FlatState:
         self.M = torch.zeros(off, device=device)
         self.V = torch.zeros(off, device=device)
         self.Wb = torch.zeros(off, device=device, dtype=BF16)
-        self.Wt = torch.zeros(off, device=device, dtype=BF16)
         # running statistics
         self.buf_offsets: Dict[str, int] = {}
         soff, nbt = 0, []
@@ -73,13 +73,6 @@ class FlatState:
         self.S = torch.zeros(max(soff, 4), device=device)
         self.nbt_names = nbt
         self.NBT = torch.zeros(max(len(nbt), 1), device=device, dtype=torch.int64)
-        # transpose table for the dgrad weight copies
-        rows, blk = [], 0
-        for _name, o, K, RS, Cc in self.tc_convs:
-            rows.append([o, o, K, RS, Cc, blk])
-            blk += RS * (K // 32) * (Cc // 32)
-        self.tr_table = torch.tensor(rows, device=device, dtype=torch.int64) if rows else None
-        self.tr_blocks = blk
         self.hyper = torch.zeros(8, device=device)
         self.hyper_host: Optional[Tuple[float, ...]] = None
         self.step = torch.zeros(1, device=device, dtype=torch.int64)
@@ -140,8 +133,6 @@ class FlatState:
     def refresh_shadows(self) -> None:
         """fp32 master -> bf16 operand copies (after load_state_dict / external optimizer steps)."""
         ops.cast_f32_bf16(self.P, self.Wb)
-        if self.tr_table is not None:
-            ops.weights_transpose(self.Wb, self.Wt, self.tr_table, len(self.tc_convs), self.tr_blocks)
         self._versions = self.param_versions()
 
     def ensure_fresh(self) -> None:
@@ -274,7 +265,7 @@ class EncoderPlan:
             rows = B * oH * oW
             n1, n2 = f"{pre}{bname}.conv1.weight", f"{pre}{bname}.conv2.weight"
             w1, w2 = fs.flat_slice(fs.Wb, n1), fs.flat_slice(fs.Wb, n2)
-            w1t, w2t = fs.flat_slice(fs.Wt, n1), fs.flat_slice(fs.Wt, n2)
+            w1t, w2t = w1, w2  # dgrad reads the same K,R,S,C bf16 weights (MN-major B operand)
             dw1, dw2 = fs.flat_slice(fs.G, n1), fs.flat_slice(fs.G, n2)
             raw1, a1, raw2, out = (self._act(B, oH, oW, outC) for _ in range(4))
             self.taps.update({f"{bname}.conv1": raw1, f"{bname}.relu1": a1, f"{bname}.conv2": raw2, bname: out})
@@ -285,7 +276,8 @@ class EncoderPlan:
             if has_ds:
                 gd = ops.make_geom(B, curH, curW, inC, outC, 1, 1, stride, 0)
                 nd = f"{pre}{bname}.downsample.0.weight"
-                wd, wdt, dwd = fs.flat_slice(fs.Wb, nd), fs.flat_slice(fs.Wt, nd), fs.flat_slice(fs.G, nd)
+                wd, dwd = fs.flat_slice(fs.Wb, nd), fs.flat_slice(fs.G, nd)
+                wdt = wd
                 rawd = self._act(B, oH, oW, outC)
                 self.taps[f"{bname}.downsample"] = rawd
                 td = ops.conv_stat_tiles(gd)
@@ -498,11 +490,34 @@ class _StepPlan:
         self.graph_eval: Optional[torch.cuda.CUDAGraph] = None
         self.eager_steps = 0
         self.launches_per_step = 0
-        self.comm_stream: Optional[torch.cuda.Stream] = None
+        self.side_stream: Optional[torch.cuda.Stream] = None
 
     # -- schedules -----------------------------------------------------------------------------------------------
     def _use_dropout(self) -> bool:
         return self.eng.dropout_p > 0.0
+
+    def _side(self) -> torch.cuda.Stream:
+        if self.side_stream is None:
+            self.side_stream = torch.cuda.Stream(device=self.eng.device)
+        return self.side_stream
+
+    def _both_encoders(self, audio_ops, image_ops, after_image=None) -> None:
+        """Audio encoder on the current stream, image encoder concurrently on a side stream (fork / join).
+
+        ResNet34 on 28x28 images is ~360 tiny latency-bound launches (1..128 CTAs each); run alone they cost more
+        wall time than the 7x bigger audio encoder.  Forked onto a second stream they fill SMs the audio kernels leave idle.
+        """
+        main = torch.cuda.current_stream(self.eng.device)
+        side = self._side()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for op in image_ops:
+                op()
+            if after_image is not None:
+                after_image()
+        for op in audio_ops:
+            op()
+        main.wait_stream(side)
 
     def run_train(self, own_dropout: bool) -> None:
         eng, fs = self.eng, self.eng.fs
@@ -510,22 +525,16 @@ class _StepPlan:
         fs.G.zero_()
         if self._use_dropout() and own_dropout:
             ops.dropout_mask(self.drop_mask, p, eng.seed, fs.step)
-        for op in self.audio.fwd_train:
-            op()
-        for op in self.image.fwd_train:
-            op()
+        self._both_encoders(self.audio.fwd_train, self.image.fwd_train)
         dm = self.drop_mask if self._use_dropout() else None
         scale = 1.0 / (1.0 - p) if self._use_dropout() else 1.0
         ops.head_fwd(self.hp, self.audio.pooled, self.image.pooled, self.labels, dm, scale, self.scratch, self.logits, self.loss, self.pred)
         ops.head_bwd(self.hp, self.hg, self.audio.pooled, self.image.pooled, self.labels, dm, scale, self.scratch, 1.0,
                      self.audio.dpooled, self.image.dpooled)
-        # image encoder first: few FLOPs but 2/3 of the parameters -> its gradient bucket is reduced under the audio backward
-        for op in self.image.bwd:
-            op()
-        if eng.allreduce is not None:
-            eng.allreduce(self, 0)
-        for op in self.audio.bwd:
-            op()
+        # the image encoder holds 2/3 of the parameters but few FLOPs: its gradient bucket (+ the head's) is all-reduced
+        # as soon as its backward is done, under the audio encoder's backward
+        ar0 = (lambda: eng.allreduce(self, 0)) if eng.allreduce is not None else None
+        self._both_encoders(self.audio.bwd, self.image.bwd, after_image=ar0)
         if eng.allreduce is not None:
             eng.allreduce(self, 1)
         fs.NBT += 1
@@ -533,14 +542,9 @@ class _StepPlan:
     def run_update(self) -> None:
         fs = self.eng.fs
         ops.adam_step(fs.P, fs.G, fs.M, fs.V, fs.Wb, fs.hyper, fs.step)
-        if fs.tr_table is not None:
-            ops.weights_transpose(fs.Wb, fs.Wt, fs.tr_table, len(fs.tc_convs), fs.tr_blocks)
 
     def run_eval(self, with_loss: bool) -> None:
-        for op in self.audio.fwd_eval:
-            op()
-        for op in self.image.fwd_eval:
-            op()
+        self._both_encoders(self.audio.fwd_eval, self.image.fwd_eval)
         ops.head_fwd(self.hp, self.audio.pooled, self.image.pooled, self.labels if with_loss else None, None, 1.0, self.scratch, self.logits,
                      self.loss if with_loss else None, self.pred)
 
@@ -549,10 +553,7 @@ class _StepPlan:
         eng, fs = self.eng, self.eng.fs
         if self._use_dropout():
             ops.dropout_mask(self.drop_mask, eng.dropout_p, eng.seed, fs.step)
-        for op in self.audio.fwd_train:
-            op()
-        for op in self.image.fwd_train:
-            op()
+        self._both_encoders(self.audio.fwd_train, self.image.fwd_train)
         dm = self.drop_mask if self._use_dropout() else None
         scale = 1.0 / (1.0 - eng.dropout_p) if self._use_dropout() else 1.0
         ops.head_fwd(self.hp, self.audio.pooled, self.image.pooled, None, dm, scale, self.scratch, self.logits, None, self.pred)

@@ -96,9 +96,9 @@ def conv_fprop(g: ConvGeom, x, w_krsc, y, stats_partial=None) -> None:
                                      _stream(x)), "conv_fprop")
 
 
-def conv_dgrad(g: ConvGeom, dy, w_crsk, dx) -> None:
+def conv_dgrad(g: ConvGeom, dy, w_krsc, dx) -> None:
     ctx = _ctx(dy)
-    ctx.check(ctx.lib.mml_conv_dgrad(ctx.handle, C.byref(g), _p(dy, BF16), _p(w_crsk, BF16), _p(dx, BF16), _stream(dy)), "conv_dgrad")
+    ctx.check(ctx.lib.mml_conv_dgrad(ctx.handle, C.byref(g), _p(dy, BF16), _p(w_krsc, BF16), _p(dx, BF16), _stream(dy)), "conv_dgrad")
 
 
 def conv_wgrad(g: ConvGeom, x, dy, dw_krsc) -> None:

@@ -86,9 +86,8 @@ def test_dgrad(shape):
     P, Q = ops.conv_out_hw(H, W, R, R, st, pad)
     g = torch.Generator(device="cuda").manual_seed(3)
     dy = torch.randn(N, P, Q, K, device="cuda", generator=g).to(torch.bfloat16)
-    w_t = w.permute(3, 1, 2, 0).contiguous()  # [C][R][S][K]
     dx = torch.full((N, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
-    ops.conv_dgrad(geom, dy, w_t, dx)
+    ops.conv_dgrad(geom, dy, w, dx)  # same K,R,S,C weights as fprop
     torch.cuda.synchronize()
     xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
     out = torch.nn.functional.conv2d(xr, w.float().permute(0, 3, 1, 2), stride=st, padding=pad)
