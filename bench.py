@@ -160,7 +160,7 @@ def dominant_kernel_roofline(torch, ops, B, pk):
     x = torch.randn(N, H, W, C, device="cuda").to(torch.bfloat16)
     w = (torch.randn(K, 3, 3, C, device="cuda") * 0.05).to(torch.bfloat16)
     y = torch.empty(N, H, W, K, device="cuda", dtype=torch.bfloat16)
-    part = torch.zeros(ops.conv_stat_tiles(g), K, 2, device="cuda")
+    part = torch.zeros(16, K, 2, device="cuda", dtype=torch.float64)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > L2
     for _ in range(3):
         ops.conv_fprop(g, x, w, y, part)

@@ -24,6 +24,11 @@ extern "C" {
 
 typedef struct mml_ctx mml_ctx;
 
+/* BatchNorm statistics accumulators are fp64 arrays [MML_BN_STAT_SLOTS][C][2]: producers (conv / stem epilogues, the BN
+ * backward reduce) add their partial sums into one of 16 slots to spread atomic contention, consumers sum the slots.
+ * The caller zeroes them once per step. */
+#define MML_BN_STAT_SLOTS 16
+
 enum mml_status {
   MML_OK = 0,
   MML_ERR_INVALID = -1,     /* bad argument / unsupported geometry */
@@ -54,31 +59,32 @@ int mml_mask_apply_f32(mml_ctx*, const float* x, const float* mask, float* y, fl
 
 /* ---- a2/a3: ResNetEncoder stem -- models/msa/networks/resnet.py:137 conv1 (7x7, stride 2, pad 3, C_in = 1) ----- */
 /* x fp32 [B,H,W] (optionally multiplied by mask[b], same multiply as above), w fp32 [64][7][7] ->
- * y bf16 [B,P,Q,64]; stats_partial [mml_stem_stat_tiles][64][2] = per-tile (sum, sum of squares) of the stored y */
-int mml_stem_stat_tiles(int B, int H, int W);
-int mml_stem_fprop(mml_ctx*, const float* x, const float* mask, const float* w, uint16_t* y, float* stats_partial, int B,
-                   int H, int W, void* stream);
+ * y bf16 [B,P,Q,64]; stats (optional) fp64 [16][64][2] += (sum, sum of squares) of the stored y */
+int mml_stem_fprop(mml_ctx*, const float* x, const float* mask, const float* w, uint16_t* y, double* stats, int B, int H,
+                   int W, void* stream);
 /* dw fp32 [64][49] = sum_{b,p,q} dy[b,p,q,k] * (x*mask)[b, 2p+r-3, 2q+s-3]  (overwrites dw) */
 int mml_stem_wgrad(mml_ctx*, const float* x, const float* mask, const uint16_t* dy, float* dw, float* workspace,
                    int64_t workspace_bytes, int B, int H, int W, void* stream);
 int64_t mml_stem_wgrad_workspace(const mml_ctx*, int B, int H, int W);
 
 /* ---- a2-a4: 3x3 / 1x1 convolutions -- resnet.py:25,30,176 (nn.Conv2d fwd) and their autograd -------------------- */
-/* tcgen05 implicit GEMM.  fprop: y = conv(x, w); optional stats_partial [mml_conv_stat_tiles][K][2] */
-int mml_conv_stat_tiles(const mml_conv_geom* g);
-int mml_conv_fprop(mml_ctx*, const mml_conv_geom* g, const uint16_t* x, const uint16_t* w_krsc, uint16_t* y,
-                   float* stats_partial, void* stream);
+/* tcgen05 implicit GEMM.  fprop: y = conv(x, w); stats (optional) fp64 [16][K][2] += per-channel (sum, sum of squares) of y */
+int mml_conv_fprop(mml_ctx*, const mml_conv_geom* g, const uint16_t* x, const uint16_t* w_krsc, uint16_t* y, double* stats,
+                   void* stream);
 /* dgrad: dx [N,H,W,C] = conv_transpose(dy [N,P,Q,K], w); reads the SAME K,R,S,C weights as fprop (MN-major B operand) */
 int mml_conv_dgrad(mml_ctx*, const mml_conv_geom* g, const uint16_t* dy, const uint16_t* w_krsc, uint16_t* dx, void* stream);
 /* wgrad: dw_krsc fp32 [K][R][S][C] += sum_{n,p,q} dy * x   (ACCUMULATES: caller zeroes the gradient buffer) */
 int mml_conv_wgrad(mml_ctx*, const mml_conv_geom* g, const uint16_t* x, const uint16_t* dy, float* dw_krsc, void* stream);
 
 /* ---- a5: BatchNorm2d (train / eval) + ReLU + residual -- resnet.py:26,31,138,177 and BasicBlock.forward :37-54 --- */
-/* reduce per-tile partials -> batch mean / biased var; scale = gamma*invstd, shift = beta - mean*scale;
- * running = (1-m)*running + m*batch (unbiased var); saves mean / invstd for backward */
-int mml_bn_finalize(mml_ctx*, const float* stats_partial, int tiles, int C, int64_t count, const float* gamma,
-                    const float* beta, float* running_mean, float* running_var, float momentum, float eps, float* scale,
-                    float* shift, float* save_mean, float* save_invstd, void* stream);
+/* training mode, fused: y = relu?(bn(x) [+ res | + bn_r(res)]) with scale/shift derived in-kernel from the fp64 sums the
+ * conv epilogue accumulated (stats [16][C][2]); also saves mean / invstd for backward and updates the running statistics
+ * (running = (1-m)*running + m*batch, unbiased var).  res NULL: none; rstats NULL: identity residual; else the residual
+ * goes through its own training-mode BN (downsample path).  count == rows. */
+int mml_bn_train_fwd(mml_ctx*, const uint16_t* x, const double* stats, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float* save_mean, float* save_invstd, const uint16_t* res, const double* rstats,
+                     const float* rgamma, const float* rbeta, float* r_running_mean, float* r_running_var, float* r_save_mean,
+                     float* r_save_invstd, uint16_t* y, int64_t rows, int C, int relu, float momentum, float eps, void* stream);
 /* eval mode: scale/shift from running statistics */
 int mml_bn_eval_coeffs(mml_ctx*, int C, const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, float* scale, float* shift, void* stream);
@@ -86,17 +92,14 @@ int mml_bn_eval_coeffs(mml_ctx*, int C, const float* gamma, const float* beta, c
 int mml_bn_act_fwd(mml_ctx*, const uint16_t* x, const float* scale, const float* shift, const uint16_t* res,
                    const float* rscale, const float* rshift, uint16_t* y, int64_t rows, int C, int relu, void* stream);
 /* backward of y = relu?(bn(x) [+ r]):  g = (dy1 [+ dy2]) * (y > 0 if relu);
- * reduce: partial [blocks][C][2] = (sum g, sum g*xhat);   blocks = mml_bn_bwd_blocks() */
-int mml_bn_bwd_blocks(const mml_ctx*, int64_t rows, int C);
+ * pass 1: bstat fp64 [16][C][2] += (sum g, sum g*xhat)   (caller zeroes it per step) */
 int mml_bn_bwd_reduce(mml_ctx*, const uint16_t* dy1, const uint16_t* dy2, const uint16_t* y, const uint16_t* x,
-                      const float* mean, const float* invstd, float* partial, int64_t rows, int C, int relu, void* stream);
-/* dgamma = sum g*xhat, dbeta = sum g (written, not accumulated); coef [3][C] for the apply pass */
-int mml_bn_bwd_finalize(mml_ctx*, const float* partial, int blocks, int C, int64_t count, const float* gamma,
-                        const float* invstd, float* dgamma, float* dbeta, float* coef, void* stream);
-/* dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) as bf16; g_out (optional) = g as bf16 (gradient of the skip path) */
+                      const float* mean, const float* invstd, double* bstat, int64_t rows, int C, int relu, void* stream);
+/* pass 2: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) as bf16; dgamma = sum g*xhat, dbeta = sum g (written, may be
+ * NULL); g_out (optional) = g as bf16 (gradient of the skip path) */
 int mml_bn_bwd_apply(mml_ctx*, const uint16_t* dy1, const uint16_t* dy2, const uint16_t* y, const uint16_t* x,
-                     const float* mean, const float* invstd, const float* coef, uint16_t* dx, uint16_t* g_out, int64_t rows,
-                     int C, int relu, void* stream);
+                     const float* mean, const float* invstd, const float* gamma, const double* bstat, float* dgamma, float* dbeta,
+                     uint16_t* dx, uint16_t* g_out, int64_t rows, int C, int relu, void* stream);
 
 /* ---- pooling -- resnet.py:140 MaxPool2d(3,2,1), :149 AdaptiveAvgPool2d((1,1)) ---------------------------------- */
 int mml_maxpool3x3s2_fwd(mml_ctx*, const uint16_t* x, uint16_t* y, uint8_t* argmax, int N, int H, int W, int C, void* stream);

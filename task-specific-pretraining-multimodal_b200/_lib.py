@@ -42,21 +42,17 @@ SIGNATURES = {
     "mml_ctx_sm_count": (I32, [P]),
     "mml_ctx_launch_count": (I64, [P]),
     "mml_mask_apply_f32": (I32, [P, P, P, P, P, I64, I64, P]),
-    "mml_stem_stat_tiles": (I32, [I32, I32, I32]),
     "mml_stem_fprop": (I32, [P, P, P, P, P, P, I32, I32, I32, P]),
     "mml_stem_wgrad": (I32, [P, P, P, P, P, P, I64, I32, I32, I32, P]),
     "mml_stem_wgrad_workspace": (I64, [P, I32, I32, I32]),
-    "mml_conv_stat_tiles": (I32, [C.POINTER(ConvGeom)]),
     "mml_conv_fprop": (I32, [P, C.POINTER(ConvGeom), P, P, P, P, P]),
     "mml_conv_dgrad": (I32, [P, C.POINTER(ConvGeom), P, P, P, P]),
     "mml_conv_wgrad": (I32, [P, C.POINTER(ConvGeom), P, P, P, P]),
-    "mml_bn_finalize": (I32, [P, P, I32, I32, I64, P, P, P, P, F32, F32, P, P, P, P, P]),
+    "mml_bn_train_fwd": (I32, [P] + [P] * 17 + [I64, I32, I32, F32, F32, P]),
     "mml_bn_eval_coeffs": (I32, [P, I32, P, P, P, P, F32, P, P, P]),
     "mml_bn_act_fwd": (I32, [P, P, P, P, P, P, P, P, I64, I32, I32, P]),
-    "mml_bn_bwd_blocks": (I32, [P, I64, I32]),
     "mml_bn_bwd_reduce": (I32, [P, P, P, P, P, P, P, P, I64, I32, I32, P]),
-    "mml_bn_bwd_finalize": (I32, [P, P, I32, I32, I64, P, P, P, P, P, P]),
-    "mml_bn_bwd_apply": (I32, [P, P, P, P, P, P, P, P, P, P, I64, I32, I32, P]),
+    "mml_bn_bwd_apply": (I32, [P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I32, I32, P]),
     "mml_maxpool3x3s2_fwd": (I32, [P, P, P, P, I32, I32, I32, I32, P]),
     "mml_maxpool3x3s2_bwd": (I32, [P, P, P, P, P, I32, I32, I32, I32, P]),
     "mml_avgpool_fwd": (I32, [P, P, P, I32, I32, I32, P]),

@@ -60,43 +60,89 @@ __global__ void mask_apply_kernel(const float* __restrict__ x, const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// BN statistics finalize (training): per-tile (sum, sumsq) partials -> mean / var -> scale / shift, running stats
+// training-mode BatchNorm forward, fused: statistics -> scale/shift in the prologue (no finalize launch)
+//   stats[c] = (sum, sum of squares) of the conv output, accumulated in fp64 by the conv / stem epilogue.
+//   y = relu?(bn(x) [+ res | + bn_r(res)]);  block 0 also saves mean / invstd for backward and updates the running
+//   statistics: running = (1-m)*running + m*batch, unbiased variance (torch.nn.BatchNorm2d, momentum 0.1).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float2* __restrict__ partial, int tiles, int C, double inv_count, double unbias,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean,
-                                   float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
-                                   float* save_invstd) {
-  __shared__ double sh_s[32][33];
-  __shared__ double sh_q[32][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  double s = 0.0, q = 0.0;
-  if (c < C)
-    for (int t = threadIdx.y; t < tiles; t += 32) {
-      const float2 v = partial[(size_t)t * C + c];
-      s += (double)v.x;
-      q += (double)v.y;
+struct BnTrain {
+  const double* stats;   // [C][2]
+  const float* gamma;
+  const float* beta;
+  float* running_mean;   // may be null
+  float* running_var;
+  float* save_mean;
+  float* save_invstd;
+};
+
+__device__ __forceinline__ void bn_coeffs(const BnTrain& b, int C, int c, double inv_count, float eps, float& scale, float& shift,
+                                          float& mean_f, float& invstd, double& var_out) {
+  double sum, sq;
+  stat_load(b.stats, C, c, sum, sq);
+  const double mean = sum * inv_count;
+  double var = sq * inv_count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  invstd = (float)(1.0 / sqrt(var + (double)eps));
+  scale = b.gamma[c] * invstd;
+  mean_f = (float)mean;
+  shift = b.beta[c] - mean_f * scale;
+  var_out = var;
+}
+
+// Cooperative prologue: the CTA derives scale / shift for all C channels once into shared memory (each channel = 32 fp64
+// loads from L2); block 0 also writes the saved statistics and the running-statistics update.
+__device__ __forceinline__ void bn_prologue(const BnTrain& b, int C, double inv_count, double unbias, float momentum, float eps, float* s_scale,
+                                            float* s_shift) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float sc, sh, mu, is;
+    double var;
+    bn_coeffs(b, C, c, inv_count, eps, sc, sh, mu, is, var);
+    s_scale[c] = sc;
+    s_shift[c] = sh;
+    if (blockIdx.x == 0) {
+      b.save_mean[c] = mu;
+      b.save_invstd[c] = is;
+      if (b.running_mean) {
+        b.running_mean[c] = (1.f - momentum) * b.running_mean[c] + momentum * mu;
+        b.running_var[c] = (1.f - momentum) * b.running_var[c] + momentum * (float)(var * unbias);
+      }
     }
-  sh_s[threadIdx.y][threadIdx.x] = s;
-  sh_q[threadIdx.y][threadIdx.x] = q;
+  }
+}
+
+constexpr int kMaxC = 512;
+
+// RES: 0 = none, 1 = identity residual, 2 = residual through its own training-mode BN (downsample path)
+template <int RES, bool RELU>
+__global__ void __launch_bounds__(kThreads)
+bn_train_fwd_kernel(const uint16_t* __restrict__ x, BnTrain bn, const uint16_t* __restrict__ res, BnTrain rbn, uint16_t* __restrict__ y,
+                    long long n8, int c8, double inv_count, double unbias, float momentum, float eps) {
+  __shared__ __align__(16) float s_coef[(RES == 2 ? 4 : 2) * kMaxC];
+  const int C = c8 * 8;
+  bn_prologue(bn, C, inv_count, unbias, momentum, eps, s_coef, s_coef + kMaxC);
+  if (RES == 2) bn_prologue(rbn, C, inv_count, unbias, momentum, eps, s_coef + 2 * kMaxC, s_coef + 3 * kMaxC);
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    for (int j = 1; j < 32; ++j) {
-      s += sh_s[j][threadIdx.x];
-      q += sh_q[j][threadIdx.x];
+  const long long stride = (long long)gridDim.x * kThreads;
+  long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
+  const int cg = (int)(i % c8);
+  const F8 sc = load8f(s_coef + cg * 8), sh = load8f(s_coef + kMaxC + cg * 8);
+  F8 rsc, rsh;
+  if (RES == 2) {
+    rsc = load8f(s_coef + 2 * kMaxC + cg * 8);
+    rsh = load8f(s_coef + 3 * kMaxC + cg * 8);
+  }
+  for (; i < n8; i += stride) {
+    F8 v = unpack8(ldg16(x + i * 8));
+    F8 r;
+    if (RES != 0) r = unpack8(ldg16(res + i * 8));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float o = fmaf(v.v[j], sc.v[j], sh.v[j]);
+      if (RES == 1) o += r.v[j];
+      if (RES == 2) o += fmaf(r.v[j], rsc.v[j], rsh.v[j]);
+      v.v[j] = RELU ? fmaxf(o, 0.f) : o;
     }
-    const double mean = s * inv_count;
-    double var = q * inv_count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float sc = gamma[c] * invstd;
-    scale[c] = sc;
-    shift[c] = beta[c] - (float)mean * sc;
-    save_mean[c] = (float)mean;
-    save_invstd[c] = invstd;
-    if (running_mean) {
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * unbias);
-    }
+    *reinterpret_cast<uint4*>(y + i * 8) = pack8(v);
   }
 }
 
@@ -111,7 +157,7 @@ __global__ void bn_eval_coeffs_kernel(int C, const float* gamma, const float* be
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// forward: y = relu?(x*scale + shift [+ res*rscale + rshift])
+// coefficient form (eval mode): y = relu?(x*scale + shift [+ res*rscale + rshift])
 // ---------------------------------------------------------------------------------------------------------------
 template <bool HAS_RES, bool RES_AFFINE, bool RELU>
 __global__ void __launch_bounds__(kThreads)
@@ -148,7 +194,7 @@ template <bool TWO, bool RELU>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_reduce_kernel(const uint16_t* __restrict__ dy1, const uint16_t* __restrict__ dy2, const uint16_t* __restrict__ y,
                      const uint16_t* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
-                     float2* __restrict__ partial, long long n8, int c8) {
+                     double* __restrict__ bstat, long long n8, int c8) {
   __shared__ float sh[kThreads][17];
   const long long stride = (long long)gridDim.x * kThreads;
   long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
@@ -192,51 +238,39 @@ bn_bwd_reduce_kernel(const uint16_t* __restrict__ dy1, const uint16_t* __restric
       a += sh[t][j];
       b += sh[t][8 + j];
     }
-    partial[(size_t)blockIdx.x * C + o] = make_float2(a, b);
+    stat_add(bstat, C, blockIdx.x, o, a, b);
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(const float2* __restrict__ partial, int blocks, int C, float inv_count,
-                                       const float* __restrict__ gamma, const float* __restrict__ invstd, float* dgamma,
-                                       float* dbeta, float* coef) {
-  __shared__ float sh_a[8][33];
-  __shared__ float sh_b[8][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  float a = 0.f, b = 0.f;
-  if (c < C)
-    for (int t = threadIdx.y; t < blocks; t += 8) {
-      const float2 v = partial[(size_t)t * C + c];
-      a += v.x;
-      b += v.y;
-    }
-  sh_a[threadIdx.y][threadIdx.x] = a;
-  sh_b[threadIdx.y][threadIdx.x] = b;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    for (int j = 1; j < 8; ++j) {
-      a += sh_a[j][threadIdx.x];
-      b += sh_b[j][threadIdx.x];
-    }
-    if (dbeta) dbeta[c] = a;
-    if (dgamma) dgamma[c] = b;
-    coef[c] = gamma[c] * invstd[c];
-    coef[C + c] = a * inv_count;
-    coef[2 * C + c] = b * inv_count;
-  }
-}
-
-// backward pass 2: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat));  optional g_out = g (skip-path gradient)
+// backward pass 2: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat));  optional g_out = g (skip-path gradient);
+// coefficients come straight from the fp64 sums of pass 1 (no finalize launch); block 0 writes dgamma / dbeta
 template <bool TWO, bool RELU, bool GOUT>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_apply_kernel(const uint16_t* __restrict__ dy1, const uint16_t* __restrict__ dy2, const uint16_t* __restrict__ y,
                     const uint16_t* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const float* __restrict__ coef, uint16_t* __restrict__ dx, uint16_t* __restrict__ g_out, long long n8, int c8) {
+                    const float* __restrict__ gamma, const double* __restrict__ bstat, float inv_count, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, uint16_t* __restrict__ dx, uint16_t* __restrict__ g_out, long long n8, int c8) {
+  __shared__ __align__(16) float s_k[2 * kMaxC];
+  const int C = c8 * 8;
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    double sg, sgx;
+    stat_load(bstat, C, c, sg, sgx);
+    s_k[c] = (float)sg * inv_count;          // mean(g)
+    s_k[kMaxC + c] = (float)sgx * inv_count; // mean(g * xhat)
+    if (blockIdx.x == 0) {
+      if (dbeta) dbeta[c] = (float)sg;
+      if (dgamma) dgamma[c] = (float)sgx;
+    }
+  }
+  __syncthreads();
   const long long stride = (long long)gridDim.x * kThreads;
   long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
   const int cg = (int)(i % c8);
-  const int C = c8 * 8;
   const F8 mu = load8f(mean + cg * 8), is = load8f(invstd + cg * 8);
-  const F8 k0 = load8f(coef + cg * 8), k1 = load8f(coef + C + cg * 8), k2 = load8f(coef + 2 * C + cg * 8);
+  F8 k0 = load8f(gamma + cg * 8);
+  const F8 k1 = load8f(s_k + cg * 8), k2 = load8f(s_k + kMaxC + cg * 8);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) k0.v[j] *= is.v[j];  // gamma * invstd
   for (; i < n8; i += stride) {
     F8 g = unpack8(ldg16(dy1 + i * 8));
     if (TWO) {
@@ -400,8 +434,8 @@ int ew_grid(const mml_ctx* ctx, long long items) {
 
 int check_rows_c(mml_ctx* ctx, int64_t rows, int C) {
   MML_REQUIRE(ctx, rows >= 1, "rows must be >= 1");
-  MML_REQUIRE(ctx, C >= 8 && C <= 2048 && (C % 8) == 0 && (kThreads % (C / 8)) == 0,
-              "channel count %d unsupported by the fused BN kernels (need C/8 to divide 256)", C);
+  MML_REQUIRE(ctx, C >= 8 && C <= kMaxC && (C % 8) == 0 && (kThreads % (C / 8)) == 0,
+              "channel count %d unsupported by the fused BN kernels (need C <= 512 and C/8 to divide 256)", C);
   return MML_OK;
 }
 
@@ -418,15 +452,33 @@ int mml_mask_apply_f32(mml_ctx* ctx, const float* x, const float* mask, float* y
   return MML_OK;
 }
 
-int mml_bn_finalize(mml_ctx* ctx, const float* stats_partial, int tiles, int C, int64_t count, const float* gamma,
-                    const float* beta, float* running_mean, float* running_var, float momentum, float eps, float* scale,
-                    float* shift, float* save_mean, float* save_invstd, void* stream) {
-  MML_REQUIRE(ctx, ctx && stats_partial && gamma && beta && scale && shift && save_mean && save_invstd, "bn_finalize: null pointer");
-  MML_REQUIRE(ctx, tiles >= 1 && C >= 1 && count >= 1, "bn_finalize: bad sizes");
-  const double unbias = count > 1 ? (double)count / (double)(count - 1) : 1.0;
-  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float2*>(stats_partial), tiles, C, 1.0 / (double)count, unbias, gamma, beta, running_mean, running_var,
-      momentum, eps, scale, shift, save_mean, save_invstd);
+int mml_bn_train_fwd(mml_ctx* ctx, const uint16_t* x, const double* stats, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float* save_mean, float* save_invstd, const uint16_t* res, const double* rstats,
+                     const float* rgamma, const float* rbeta, float* r_running_mean, float* r_running_var, float* r_save_mean,
+                     float* r_save_invstd, uint16_t* y, int64_t rows, int C, int relu, float momentum, float eps, void* stream) {
+  MML_REQUIRE(ctx, ctx && x && stats && gamma && beta && save_mean && save_invstd && y, "bn_train_fwd: null pointer");
+  MML_REQUIRE(ctx, (running_mean == nullptr) == (running_var == nullptr), "bn_train_fwd: running_mean / running_var must be given together");
+  int rc = check_rows_c(ctx, rows, C);
+  if (rc) return rc;
+  const int mode = res == nullptr ? 0 : (rstats == nullptr ? 1 : 2);
+  if (mode == 2) MML_REQUIRE(ctx, rgamma && rbeta && r_save_mean && r_save_invstd, "bn_train_fwd: residual BN needs gamma/beta/save buffers");
+  BnTrain bn{stats, gamma, beta, running_mean, running_var, save_mean, save_invstd};
+  BnTrain rbn{rstats, rgamma, rbeta, r_running_mean, r_running_var, r_save_mean, r_save_invstd};
+  const long long n8 = rows * (C / 8);
+  const int grid = ew_grid(ctx, n8);
+  const double inv_count = 1.0 / (double)rows;
+  const double unbias = rows > 1 ? (double)rows / (double)(rows - 1) : 1.0;
+  cudaStream_t st = (cudaStream_t)stream;
+#define MML_TR(M, RL) bn_train_fwd_kernel<M, RL><<<grid, kThreads, 0, st>>>(x, bn, res, rbn, y, n8, C / 8, inv_count, unbias, momentum, eps)
+  switch (mode * 2 + (relu ? 1 : 0)) {
+    case 0: MML_TR(0, false); break;
+    case 1: MML_TR(0, true); break;
+    case 2: MML_TR(1, false); break;
+    case 3: MML_TR(1, true); break;
+    case 4: MML_TR(2, false); break;
+    default: MML_TR(2, true); break;
+  }
+#undef MML_TR
   MML_LAUNCHED(ctx);
   return MML_OK;
 }
@@ -461,8 +513,7 @@ int mml_bn_act_fwd(mml_ctx* ctx, const uint16_t* x, const float* scale, const fl
   return MML_OK;
 }
 
-int mml_bn_bwd_blocks(const mml_ctx* ctx, int64_t rows, int C) {
-  if (!ctx || rows < 1 || C < 8) return 0;
+static int bn_bwd_grid(const mml_ctx* ctx, int64_t rows, int C) {
   long long b = mml_ceil_div(rows * (C / 8), (long long)kThreads * 4);
   const long long cap = (long long)ctx->sm_count * 4;
   if (b > cap) b = cap;
@@ -471,15 +522,14 @@ int mml_bn_bwd_blocks(const mml_ctx* ctx, int64_t rows, int C) {
 }
 
 int mml_bn_bwd_reduce(mml_ctx* ctx, const uint16_t* dy1, const uint16_t* dy2, const uint16_t* y, const uint16_t* x,
-                      const float* mean, const float* invstd, float* partial, int64_t rows, int C, int relu, void* stream) {
-  MML_REQUIRE(ctx, ctx && dy1 && x && mean && invstd && partial && (!relu || y), "bn_bwd_reduce: null pointer");
+                      const float* mean, const float* invstd, double* bstat, int64_t rows, int C, int relu, void* stream) {
+  MML_REQUIRE(ctx, ctx && dy1 && x && mean && invstd && bstat && (!relu || y), "bn_bwd_reduce: null pointer");
   int rc = check_rows_c(ctx, rows, C);
   if (rc) return rc;
   const long long n8 = rows * (C / 8);
-  const int grid = mml_bn_bwd_blocks(ctx, rows, C);
+  const int grid = bn_bwd_grid(ctx, rows, C);
   cudaStream_t st = (cudaStream_t)stream;
-  float2* part = reinterpret_cast<float2*>(partial);
-#define MML_RED(TW, RL) bn_bwd_reduce_kernel<TW, RL><<<grid, kThreads, 0, st>>>(dy1, dy2, y, x, mean, invstd, part, n8, C / 8)
+#define MML_RED(TW, RL) bn_bwd_reduce_kernel<TW, RL><<<grid, kThreads, 0, st>>>(dy1, dy2, y, x, mean, invstd, bstat, n8, C / 8)
   if (dy2) {
     if (relu) MML_RED(true, true); else MML_RED(true, false);
   } else {
@@ -490,26 +540,18 @@ int mml_bn_bwd_reduce(mml_ctx* ctx, const uint16_t* dy1, const uint16_t* dy2, co
   return MML_OK;
 }
 
-int mml_bn_bwd_finalize(mml_ctx* ctx, const float* partial, int blocks, int C, int64_t count, const float* gamma,
-                        const float* invstd, float* dgamma, float* dbeta, float* coef, void* stream) {
-  MML_REQUIRE(ctx, ctx && partial && gamma && invstd && coef && blocks >= 1 && C >= 1 && count >= 1, "bn_bwd_finalize: bad arguments");
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(partial), blocks, C,
-                                                                                 1.0f / (float)count, gamma, invstd, dgamma, dbeta, coef);
-  MML_LAUNCHED(ctx);
-  return MML_OK;
-}
-
 int mml_bn_bwd_apply(mml_ctx* ctx, const uint16_t* dy1, const uint16_t* dy2, const uint16_t* y, const uint16_t* x,
-                     const float* mean, const float* invstd, const float* coef, uint16_t* dx, uint16_t* g_out, int64_t rows,
-                     int C, int relu, void* stream) {
-  MML_REQUIRE(ctx, ctx && dy1 && x && mean && invstd && coef && dx && (!relu || y), "bn_bwd_apply: null pointer");
+                     const float* mean, const float* invstd, const float* gamma, const double* bstat, float* dgamma, float* dbeta,
+                     uint16_t* dx, uint16_t* g_out, int64_t rows, int C, int relu, void* stream) {
+  MML_REQUIRE(ctx, ctx && dy1 && x && mean && invstd && gamma && bstat && dx && (!relu || y), "bn_bwd_apply: null pointer");
   int rc = check_rows_c(ctx, rows, C);
   if (rc) return rc;
   const long long n8 = rows * (C / 8);
   const int grid = ew_grid(ctx, n8);
+  const float inv_count = 1.0f / (float)rows;
   cudaStream_t st = (cudaStream_t)stream;
 #define MML_APP(TW, RL, GO) \
-  bn_bwd_apply_kernel<TW, RL, GO><<<grid, kThreads, 0, st>>>(dy1, dy2, y, x, mean, invstd, coef, dx, g_out, n8, C / 8)
+  bn_bwd_apply_kernel<TW, RL, GO><<<grid, kThreads, 0, st>>>(dy1, dy2, y, x, mean, invstd, gamma, bstat, inv_count, dgamma, dbeta, dx, g_out, n8, C / 8)
   const int key = (dy2 ? 4 : 0) | (relu ? 2 : 0) | (g_out ? 1 : 0);
   switch (key) {
     case 0: MML_APP(false, false, false); break;

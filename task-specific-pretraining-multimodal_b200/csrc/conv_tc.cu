@@ -10,7 +10,7 @@
 // zero padding is TMA out-of-bounds fill.  An output tile is a box {64 ch, Wb = OutW, Hb, Nb} of <= 128 pixels; its
 // rows land in shared memory as 128-byte rows with SWIZZLE_128B, which is exactly the canonical K-major UMMA operand
 // layout.  The same box of the output tensor is written back by a TMA store from a swizzled staging buffer.
-//   fprop           : in = x, W = w[K][R][S][C],            out = y      (+ per-tile BatchNorm partial sums)
+//   fprop           : in = x, W = w[K][R][S][C],            out = y      (+ BatchNorm sum / sum-of-squares, fp64 atomics)
 //   dgrad           : in = dy, W = the same w[K][R][S][C] read as an MN-major B operand, out = dx (stride 2: one launch per
 //                     output phase)
 //   wgrad           : dW[k][t][c] += sum_pixels dy[pix][k] * in_view[t][pix][c]   (both operands MN-major)
@@ -49,7 +49,7 @@ struct IgemmParams {
   int Hb, Nb;      // tile = {OutW, Hb, Nb}
   int valid_rows;  // OutW * Hb * Nb  (<= 128)
   int cout;
-  float* stats_partial;  // [m_tiles][cout][2] or nullptr
+  double* stats;  // [16 slots][cout][2] (sum, sum of squares) of the stored output, accumulated with fp64 atomics; or nullptr
   Tap taps[kMaxTaps];
 };
 
@@ -210,7 +210,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
         tma_store_4d(&maps.out, buf, n_tile * BLOCK_N + ch * 64, 0, a0, n0);
         tma_store_commit();
       }
-      if (p.stats_partial != nullptr) {
+      if (p.stats != nullptr) {
         // BatchNorm partials of the STORED (bf16-rounded) tile: thread = (channel, row half)
         const int c = et & 63;
         const int half = et >> 6;
@@ -228,8 +228,8 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
         named_bar_sync(1, 128);
         if (half == 0) {
           const float2 o = stat_scratch[c];
-          float2* dst = reinterpret_cast<float2*>(p.stats_partial) + ((size_t)m_tile * p.cout + n_tile * BLOCK_N + ch * 64 + c);
-          *dst = make_float2(s + o.x, ss + o.y);
+          // fp64 atomics: the summation order across CTAs then changes the result far below fp32 resolution
+          stat_add(p.stats, p.cout, m_tile, n_tile * BLOCK_N + ch * 64 + c, s + o.x, ss + o.y);
         }
       }
     }
@@ -505,7 +505,7 @@ int launch_igemm_t(mml_ctx* ctx, const IgemmMaps& maps, const IgemmParams& p, di
 // One "shifted GEMM" launch: out view <- sum over taps of in views @ weights.
 //   b_mn = false: w is [cout rows][n_wtaps*cin inner] bf16;   b_mn = true: w is [cin rows][n_wtaps*cout inner] bf16
 int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, int n_wtaps, int cin, int cout, const View& out,
-              const Tap* taps, int num_taps, float* stats_partial, bool b_mn, cudaStream_t st) {
+              const Tap* taps, int num_taps, double* stats, bool b_mn, cudaStream_t st) {
   MML_REQUIRE(ctx, cin % 64 == 0 && cout % 64 == 0, "conv: channel counts must be multiples of 64 (got C=%d K=%d)", cin, cout);
   MML_REQUIRE(ctx, num_taps >= 1 && num_taps <= kMaxTaps && n_views <= kMaxViews, "conv: bad tap table");
   TileGeom tg;
@@ -533,7 +533,7 @@ int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, in
   p.Nb = tg.Nb;
   p.valid_rows = tg.valid_rows;
   p.cout = cout;
-  p.stats_partial = stats_partial;
+  p.stats = stats;
   for (int i = 0; i < num_taps; ++i) p.taps[i] = taps[i];
   dim3 grid(tg.tiles_h * tg.tiles_n, cout / block_n);
   if (!b_mn) {
@@ -609,17 +609,8 @@ int launch_wgrad_t(mml_ctx* ctx, const WgradMaps& maps, const WgradParams& p, di
 
 extern "C" {
 
-int mml_conv_stat_tiles(const mml_conv_geom* g) {
-  if (!g) return 0;
-  const int P = (g->H + 2 * g->pad - g->R) / g->stride + 1;
-  const int Q = (g->W + 2 * g->pad - g->S) / g->stride + 1;
-  TileGeom tg;
-  if (!choose_tile(Q, P, g->N, &tg)) return 0;
-  return tg.tiles_h * tg.tiles_n;
-}
-
 int mml_conv_fprop(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, const uint16_t* w_krsc, uint16_t* y,
-                   float* stats_partial, void* stream) {
+                   double* stats, void* stream) {
   int P, Q, rc;
   if ((rc = check_geom(ctx, g, &P, &Q))) return rc;
   View views[kMaxViews];
@@ -639,7 +630,7 @@ int mml_conv_fprop(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, cons
   }
   for (int i = 0; i < n_taps; ++i) taps[i].map = (int8_t)remap[taps[i].map];
   View out = make_phase_view(y, g->N, P, Q, g->K, 1, 0, 0);
-  return run_igemm(ctx, used, n_used, w_krsc, g->R * g->S, g->C, g->K, out, taps, n_taps, stats_partial, false, (cudaStream_t)stream);
+  return run_igemm(ctx, used, n_used, w_krsc, g->R * g->S, g->C, g->K, out, taps, n_taps, stats, false, (cudaStream_t)stream);
 }
 
 int mml_conv_dgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* dy, const uint16_t* w_krsc, uint16_t* dx, void* stream) {

@@ -213,6 +213,23 @@ __device__ __forceinline__ float mask_mul(float x, float m) {
   return r;
 }
 
+// BatchNorm statistics accumulators: fp64 [MML_BN_STAT_SLOTS][C][2]; producers add into slot (block index & 15) so that at
+// most 1/16 of the CTAs of a launch contend for one address; consumers sum the slots.
+constexpr int kStatSlots = 16;
+__device__ __forceinline__ void stat_add(double* stats, int C, int slot, int c, float a, float b) {
+  double* dst = stats + 2 * ((size_t)(slot & (kStatSlots - 1)) * C + c);
+  atomicAdd(dst, (double)a);
+  atomicAdd(dst + 1, (double)b);
+}
+__device__ __forceinline__ void stat_load(const double* stats, int C, int c, double& a, double& b) {
+  a = 0.0, b = 0.0;
+#pragma unroll
+  for (int k = 0; k < kStatSlots; ++k) {
+    a += stats[2 * ((size_t)k * C + c)];
+    b += stats[2 * ((size_t)k * C + c) + 1];
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -6,7 +6,7 @@
 // K = 49 is too thin for tcgen05 tiles and the op is bandwidth/latency bound on its 64-channel bf16 output, so this is
 // a SIMT fp32 kernel: a CTA owns a 4 x 28 output-pixel tile and all 64 channels, the input patch and the 64x49 filter
 // live in shared memory, every thread accumulates 4 pixels x 8 channels in registers.  The epilogue stores bf16 NHWC
-// and emits the per-tile BatchNorm partial sums of the stored values.
+// and accumulates the BatchNorm sum / sum of squares of the stored values (fp64 atomics).
 #include "mml_common.cuh"
 #include "mml_ctx.h"
 
@@ -54,7 +54,7 @@ __device__ __forceinline__ void load_patch(float* patch, const float* __restrict
 
 __global__ void __launch_bounds__(kStemThreads)
 stem_fprop_kernel(const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ w, uint16_t* __restrict__ y,
-                  float2* __restrict__ stats_partial, StemGeom g) {
+                  double* __restrict__ stats, StemGeom g) {
   __shared__ __align__(16) float wsm[49][64];          // [tap][k]
   __shared__ __align__(16) float patch[PATCH_H * PATCH_LD];
   __shared__ float red[TP * TQ / 4][64][2];
@@ -123,7 +123,7 @@ stem_fprop_kernel(const float* __restrict__ x, const float* __restrict__ mask, c
       }
     }
   }
-  if (stats_partial) {
+  if (stats) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       red[pgrp][cgrp * 8 + j][0] = sum[j];
@@ -136,7 +136,7 @@ stem_fprop_kernel(const float* __restrict__ x, const float* __restrict__ mask, c
         a += red[t][threadIdx.x][0];
         c += red[t][threadIdx.x][1];
       }
-      stats_partial[(size_t)blockIdx.x * 64 + threadIdx.x] = make_float2(a, c);
+      stat_add(stats, 64, blockIdx.x, threadIdx.x, a, c);
     }
   }
 }
@@ -222,17 +222,12 @@ int stem_wgrad_ctas(const mml_ctx* ctx, int total_tiles) {
 
 extern "C" {
 
-int mml_stem_stat_tiles(int B, int H, int W) {
-  const StemGeom g = stem_geom(B, H, W);
-  return B * g.tiles_p * g.tiles_q;
-}
-
-int mml_stem_fprop(mml_ctx* ctx, const float* x, const float* mask, const float* w, uint16_t* y, float* stats_partial, int B,
+int mml_stem_fprop(mml_ctx* ctx, const float* x, const float* mask, const float* w, uint16_t* y, double* stats, int B,
                    int H, int W, void* stream) {
   MML_REQUIRE(ctx, ctx && x && w && y, "stem_fprop: null pointer");
   MML_REQUIRE(ctx, B >= 1 && H >= 1 && W >= 1, "stem_fprop: bad dims");
   const StemGeom g = stem_geom(B, H, W);
-  stem_fprop_kernel<<<B * g.tiles_p * g.tiles_q, kStemThreads, 0, (cudaStream_t)stream>>>(x, mask, w, y, reinterpret_cast<float2*>(stats_partial), g);
+  stem_fprop_kernel<<<B * g.tiles_p * g.tiles_q, kStemThreads, 0, (cudaStream_t)stream>>>(x, mask, w, y, stats, g);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }

@@ -28,6 +28,7 @@ from ._lib import MMLError
 BF16 = torch.bfloat16
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+STAT_SLOTS = 16  # MML_BN_STAT_SLOTS
 ALIGN = 64  # elements; 256 B for fp32, 128 B for bf16 (TMA base alignment)
 
 
@@ -187,8 +188,11 @@ class FlatState:
 # =====================================================================================================================
 # per-encoder plan
 # =====================================================================================================================
-class _BN:
-    __slots__ = ("C", "gamma", "beta", "rmean", "rvar", "scale", "shift", "mean", "invstd", "coef", "dgamma", "dbeta")
+class _BN(ops.BNBuffers):
+    __slots__ = ("C", "scale", "shift", "bstat", "dgamma", "dbeta")
+
+    def __init__(self):  # filled field by field in EncoderPlan._bn
+        pass
 
 
 class EncoderPlan:
@@ -205,6 +209,9 @@ class EncoderPlan:
         self.pooled = torch.zeros(B, 512, device=dev)
         self.dpooled = torch.zeros(B, 512, device=dev)
         self.taps: Dict[str, torch.Tensor] = {}  # stored intermediates by name (NHWC bf16), for tests / inspection
+        n_stat = STAT_SLOTS * 4 * sum(m.num_features for m in enc.modules() if isinstance(m, nn.BatchNorm2d))
+        self.stat_arena = torch.zeros(n_stat, device=dev, dtype=torch.float64)  # zeroed once per step
+        self._stat_off = 0
         self._build(train)
 
     # -- helpers -----------------------------------------------------------------------------------------------
@@ -221,7 +228,12 @@ class EncoderPlan:
         o = fs.buf_offsets[f"{self.prefix}{name}.running_var"]
         bn.rvar = fs.S[o:o + C]
         bn.scale, bn.shift, bn.mean, bn.invstd = (torch.zeros(C, device=dev) for _ in range(4))
-        bn.coef = torch.zeros(3, C, device=dev)
+        # fp64 accumulators: forward (sum x, sum x^2) filled by the conv epilogue, backward (sum g, sum g*xhat)
+        o = self._stat_off
+        n = STAT_SLOTS * 2 * C
+        self._stat_off += 2 * n
+        bn.stats = self.stat_arena[o:o + n]
+        bn.bstat = self.stat_arena[o + n:o + 2 * n]
         return bn
 
     def _act(self, *shape) -> torch.Tensor:
@@ -239,17 +251,15 @@ class EncoderPlan:
         raw0, act0 = self._act(B, P0, Q0, 64), self._act(B, P0, Q0, 64)
         pool, amax = self._act(B, P1, Q1, 64), torch.zeros(B, P1, Q1, 64, device=dev, dtype=torch.uint8)
         self.taps.update({"conv1": raw0, "relu1": act0, "maxpool": pool})
-        tiles0 = ops.stem_stat_tiles(B, self.H, self.W)
-        part0 = torch.zeros(tiles0, 64, 2, device=dev)
         bn0 = self._bn("bn1", 64)
         rows0 = B * P0 * Q0
         x, mask = self.x, self.mask
-        F.append(lambda: ops.stem_fprop(x, mask, w_stem, raw0, part0))
-        F.append(lambda: ops.bn_finalize(part0, tiles0, 64, rows0, bn0.gamma, bn0.beta, bn0.rmean, bn0.rvar, BN_MOMENTUM, BN_EPS, bn0.scale, bn0.shift, bn0.mean, bn0.invstd))
+        F.append(lambda: ops.stem_fprop(x, mask, w_stem, raw0, bn0.stats))
+        F.append(lambda: ops.bn_train_fwd(raw0, bn0, None, None, act0, rows0, 64, True, BN_MOMENTUM, BN_EPS))
         E.append(lambda: ops.stem_fprop(x, mask, w_stem, raw0, None))
         E.append(lambda: ops.bn_eval_coeffs(64, bn0.gamma, bn0.beta, bn0.rmean, bn0.rvar, BN_EPS, bn0.scale, bn0.shift))
+        E.append(lambda: ops.bn_act_fwd(raw0, bn0.scale, bn0.shift, None, None, None, act0, rows0, 64, True))
         for L in (F, E):
-            L.append(lambda: ops.bn_act_fwd(raw0, bn0.scale, bn0.shift, None, None, None, act0, rows0, 64, True))
             L.append(lambda: ops.maxpool_fwd(act0, pool, amax, B, P0, Q0, 64))
         # backward of the stem is emitted last (see end of _build); needs the two gradients of `pool`
         cur, curH, curW, curC = pool, P1, Q1, 64
@@ -269,8 +279,6 @@ class EncoderPlan:
             dw1, dw2 = fs.flat_slice(fs.G, n1), fs.flat_slice(fs.G, n2)
             raw1, a1, raw2, out = (self._act(B, oH, oW, outC) for _ in range(4))
             self.taps.update({f"{bname}.conv1": raw1, f"{bname}.relu1": a1, f"{bname}.conv2": raw2, bname: out})
-            t1, t2 = ops.conv_stat_tiles(g1), ops.conv_stat_tiles(g2)
-            part1, part2 = torch.zeros(t1, outC, 2, device=dev), torch.zeros(t2, outC, 2, device=dev)
             bn1, bn2 = self._bn(f"{bname}.bn1", outC), self._bn(f"{bname}.bn2", outC)
             xin = cur
             if has_ds:
@@ -280,76 +288,69 @@ class EncoderPlan:
                 wdt = wd
                 rawd = self._act(B, oH, oW, outC)
                 self.taps[f"{bname}.downsample"] = rawd
-                td = ops.conv_stat_tiles(gd)
-                partd = torch.zeros(td, outC, 2, device=dev)
                 bnd = self._bn(f"{bname}.downsample.1", outC)
 
-            def fwd_block(training, g1=g1, g2=g2, xin=xin, w1=w1, w2=w2, raw1=raw1, a1=a1, raw2=raw2, out=out, part1=part1, part2=part2,
-                          bn1=bn1, bn2=bn2, t1=t1, t2=t2, rows=rows, outC=outC, has_ds=has_ds, blk_i=blk_i):
-                steps = []
-                if training:
-                    steps.append(lambda: ops.conv_fprop(g1, xin, w1, raw1, part1))
-                    steps.append(lambda: ops.bn_finalize(part1, t1, outC, rows, bn1.gamma, bn1.beta, bn1.rmean, bn1.rvar, BN_MOMENTUM, BN_EPS, bn1.scale, bn1.shift, bn1.mean, bn1.invstd))
+            bnd_ = bnd if has_ds else None
+            rawd_ = rawd if has_ds else None
+
+            def fwd_train(g1=g1, g2=g2, xin=xin, w1=w1, w2=w2, raw1=raw1, a1=a1, raw2=raw2, out=out, bn1=bn1, bn2=bn2, rows=rows, outC=outC,
+                          has_ds=has_ds, gd=gd if has_ds else None, wd=wd if has_ds else None, rawd=rawd_, bnd=bnd_):
+                steps = [lambda: ops.conv_fprop(g1, xin, w1, raw1, bn1.stats),
+                         lambda: ops.bn_train_fwd(raw1, bn1, None, None, a1, rows, outC, True, BN_MOMENTUM, BN_EPS),
+                         lambda: ops.conv_fprop(g2, a1, w2, raw2, bn2.stats)]
+                if has_ds:
+                    steps.append(lambda: ops.conv_fprop(gd, xin, wd, rawd, bnd.stats))
+                    steps.append(lambda: ops.bn_train_fwd(raw2, bn2, rawd, bnd, out, rows, outC, True, BN_MOMENTUM, BN_EPS))
                 else:
-                    steps.append(lambda: ops.conv_fprop(g1, xin, w1, raw1, None))
-                    steps.append(lambda: ops.bn_eval_coeffs(outC, bn1.gamma, bn1.beta, bn1.rmean, bn1.rvar, BN_EPS, bn1.scale, bn1.shift))
-                steps.append(lambda: ops.bn_act_fwd(raw1, bn1.scale, bn1.shift, None, None, None, a1, rows, outC, True))
-                if training:
-                    steps.append(lambda: ops.conv_fprop(g2, a1, w2, raw2, part2))
-                    steps.append(lambda: ops.bn_finalize(part2, t2, outC, rows, bn2.gamma, bn2.beta, bn2.rmean, bn2.rvar, BN_MOMENTUM, BN_EPS, bn2.scale, bn2.shift, bn2.mean, bn2.invstd))
-                else:
-                    steps.append(lambda: ops.conv_fprop(g2, a1, w2, raw2, None))
-                    steps.append(lambda: ops.bn_eval_coeffs(outC, bn2.gamma, bn2.beta, bn2.rmean, bn2.rvar, BN_EPS, bn2.scale, bn2.shift))
+                    steps.append(lambda: ops.bn_train_fwd(raw2, bn2, xin, None, out, rows, outC, True, BN_MOMENTUM, BN_EPS))
                 return steps
 
-            F.extend(fwd_block(True))
-            E.extend(fwd_block(False))
-            if has_ds:
-                F.append(lambda gd=gd, xin=xin, wd=wd, rawd=rawd, partd=partd: ops.conv_fprop(gd, xin, wd, rawd, partd))
-                F.append(lambda partd=partd, td=td, outC=outC, rows=rows, bnd=bnd: ops.bn_finalize(partd, td, outC, rows, bnd.gamma, bnd.beta, bnd.rmean, bnd.rvar, BN_MOMENTUM, BN_EPS, bnd.scale, bnd.shift, bnd.mean, bnd.invstd))
-                E.append(lambda gd=gd, xin=xin, wd=wd, rawd=rawd: ops.conv_fprop(gd, xin, wd, rawd, None))
-                E.append(lambda outC=outC, bnd=bnd: ops.bn_eval_coeffs(outC, bnd.gamma, bnd.beta, bnd.rmean, bnd.rvar, BN_EPS, bnd.scale, bnd.shift))
-                for L in (F, E):
-                    L.append(lambda raw2=raw2, bn2=bn2, rawd=rawd, bnd=bnd, out=out, rows=rows, outC=outC:
-                             ops.bn_act_fwd(raw2, bn2.scale, bn2.shift, rawd, bnd.scale, bnd.shift, out, rows, outC, True))
-            else:
-                for L in (F, E):
-                    L.append(lambda raw2=raw2, bn2=bn2, xin=xin, out=out, rows=rows, outC=outC:
-                             ops.bn_act_fwd(raw2, bn2.scale, bn2.shift, xin, None, None, out, rows, outC, True))
+            def fwd_eval(g1=g1, g2=g2, xin=xin, w1=w1, w2=w2, raw1=raw1, a1=a1, raw2=raw2, out=out, bn1=bn1, bn2=bn2, rows=rows, outC=outC,
+                         has_ds=has_ds, gd=gd if has_ds else None, wd=wd if has_ds else None, rawd=rawd_, bnd=bnd_):
+                steps = [lambda: ops.conv_fprop(g1, xin, w1, raw1, None),
+                         lambda: ops.bn_eval_coeffs(outC, bn1.gamma, bn1.beta, bn1.rmean, bn1.rvar, BN_EPS, bn1.scale, bn1.shift),
+                         lambda: ops.bn_act_fwd(raw1, bn1.scale, bn1.shift, None, None, None, a1, rows, outC, True),
+                         lambda: ops.conv_fprop(g2, a1, w2, raw2, None),
+                         lambda: ops.bn_eval_coeffs(outC, bn2.gamma, bn2.beta, bn2.rmean, bn2.rvar, BN_EPS, bn2.scale, bn2.shift)]
+                if has_ds:
+                    steps.append(lambda: ops.conv_fprop(gd, xin, wd, rawd, None))
+                    steps.append(lambda: ops.bn_eval_coeffs(outC, bnd.gamma, bnd.beta, bnd.rmean, bnd.rvar, BN_EPS, bnd.scale, bnd.shift))
+                    steps.append(lambda: ops.bn_act_fwd(raw2, bn2.scale, bn2.shift, rawd, bnd.scale, bnd.shift, out, rows, outC, True))
+                else:
+                    steps.append(lambda: ops.bn_act_fwd(raw2, bn2.scale, bn2.shift, xin, None, None, out, rows, outC, True))
+                return steps
+
+            F.extend(fwd_train())
+            E.extend(fwd_eval())
 
             # ---------------- backward of this block (closures run in reverse block order)
             if train:
                 d_raw2, d_a1, d_raw1 = (self._act(B, oH, oW, outC) for _ in range(3))
                 d_x_main = self._act(B, curH, curW, inC)
                 g_skip = None if has_ds else self._act(B, oH, oW, outC)
-                blocks2 = ops.bn_bwd_blocks(out, rows, outC)
-                bpart = torch.zeros(blocks2, outC, 2, device=dev)
                 out_grads: List[Optional[torch.Tensor]] = [None, None]  # set by the consumer (next block / avgpool)
                 if has_ds:
                     d_rawd, d_x_ds = self._act(B, oH, oW, outC), self._act(B, curH, curW, inC)
 
                 def bwd_block(g1=g1, g2=g2, xin=xin, a1=a1, raw1=raw1, raw2=raw2, out=out, bn1=bn1, bn2=bn2, rows=rows, outC=outC,
-                              d_raw2=d_raw2, d_a1=d_a1, d_raw1=d_raw1, d_x_main=d_x_main, g_skip=g_skip, bpart=bpart, blocks2=blocks2,
+                              d_raw2=d_raw2, d_a1=d_a1, d_raw1=d_raw1, d_x_main=d_x_main, g_skip=g_skip,
                               out_grads=out_grads, w1t=w1t, w2t=w2t, dw1=dw1, dw2=dw2, has_ds=has_ds,
                               ds=(gd, wdt, dwd, rawd, bnd, d_rawd, d_x_ds) if has_ds else None):
                     dy1, dy2 = out_grads
                     # bn2 (+ residual add + ReLU)
-                    ops.bn_bwd_reduce(dy1, dy2, out, raw2, bn2.mean, bn2.invstd, bpart, rows, outC, True)
-                    ops.bn_bwd_finalize(bpart, blocks2, outC, rows, bn2.gamma, bn2.invstd, bn2.dgamma, bn2.dbeta, bn2.coef)
-                    ops.bn_bwd_apply(dy1, dy2, out, raw2, bn2.mean, bn2.invstd, bn2.coef, d_raw2, g_skip, rows, outC, True)
+                    ops.bn_bwd_reduce(dy1, dy2, out, raw2, bn2.mean, bn2.invstd, bn2.bstat, rows, outC, True)
+                    ops.bn_bwd_apply(dy1, dy2, out, raw2, bn2.mean, bn2.invstd, bn2.gamma, bn2.bstat, bn2.dgamma, bn2.dbeta, d_raw2, g_skip, rows, outC, True)
                     if has_ds:
                         gd_, wdt_, dwd_, rawd_, bnd_, d_rawd_, d_x_ds_ = ds
-                        ops.bn_bwd_reduce(dy1, dy2, out, rawd_, bnd_.mean, bnd_.invstd, bpart, rows, outC, True)
-                        ops.bn_bwd_finalize(bpart, blocks2, outC, rows, bnd_.gamma, bnd_.invstd, bnd_.dgamma, bnd_.dbeta, bnd_.coef)
-                        ops.bn_bwd_apply(dy1, dy2, out, rawd_, bnd_.mean, bnd_.invstd, bnd_.coef, d_rawd_, None, rows, outC, True)
+                        ops.bn_bwd_reduce(dy1, dy2, out, rawd_, bnd_.mean, bnd_.invstd, bnd_.bstat, rows, outC, True)
+                        ops.bn_bwd_apply(dy1, dy2, out, rawd_, bnd_.mean, bnd_.invstd, bnd_.gamma, bnd_.bstat, bnd_.dgamma, bnd_.dbeta, d_rawd_, None, rows, outC, True)
                         ops.conv_wgrad(gd_, xin, d_rawd_, dwd_)
                         ops.conv_dgrad(gd_, d_rawd_, wdt_, d_x_ds_)
                     ops.conv_wgrad(g2, a1, d_raw2, dw2)
                     ops.conv_dgrad(g2, d_raw2, w2t, d_a1)
                     # bn1 + ReLU
-                    ops.bn_bwd_reduce(d_a1, None, a1, raw1, bn1.mean, bn1.invstd, bpart, rows, outC, True)
-                    ops.bn_bwd_finalize(bpart, blocks2, outC, rows, bn1.gamma, bn1.invstd, bn1.dgamma, bn1.dbeta, bn1.coef)
-                    ops.bn_bwd_apply(d_a1, None, a1, raw1, bn1.mean, bn1.invstd, bn1.coef, d_raw1, None, rows, outC, True)
+                    ops.bn_bwd_reduce(d_a1, None, a1, raw1, bn1.mean, bn1.invstd, bn1.bstat, rows, outC, True)
+                    ops.bn_bwd_apply(d_a1, None, a1, raw1, bn1.mean, bn1.invstd, bn1.gamma, bn1.bstat, bn1.dgamma, bn1.dbeta, d_raw1, None, rows, outC, True)
                     ops.conv_wgrad(g1, xin, d_raw1, dw1)
                     ops.conv_dgrad(g1, d_raw1, w1t, d_x_main)
 
@@ -374,15 +375,12 @@ class EncoderPlan:
             Bk.extend(reversed(bwd_stack))
             # stem backward
             d_act0, d_raw0 = self._act(B, P0, Q0, 64), self._act(B, P0, Q0, 64)
-            blocks0 = ops.bn_bwd_blocks(act0, rows0, 64)
-            bpart0 = torch.zeros(blocks0, 64, 2, device=dev)
             ws = torch.zeros(max(ops.stem_wgrad_workspace(x) // 4, 4), device=dev)
 
             def bwd_stem():
                 ops.maxpool_bwd(stem_grad_slots[0], stem_grad_slots[1], amax, d_act0, B, P0, Q0, 64)
-                ops.bn_bwd_reduce(d_act0, None, act0, raw0, bn0.mean, bn0.invstd, bpart0, rows0, 64, True)
-                ops.bn_bwd_finalize(bpart0, blocks0, 64, rows0, bn0.gamma, bn0.invstd, bn0.dgamma, bn0.dbeta, bn0.coef)
-                ops.bn_bwd_apply(d_act0, None, act0, raw0, bn0.mean, bn0.invstd, bn0.coef, d_raw0, None, rows0, 64, True)
+                ops.bn_bwd_reduce(d_act0, None, act0, raw0, bn0.mean, bn0.invstd, bn0.bstat, rows0, 64, True)
+                ops.bn_bwd_apply(d_act0, None, act0, raw0, bn0.mean, bn0.invstd, bn0.gamma, bn0.bstat, bn0.dgamma, bn0.dbeta, d_raw0, None, rows0, 64, True)
                 ops.stem_wgrad(x, mask, d_raw0, dw_stem, ws)
 
             Bk.append(bwd_stem)
@@ -423,6 +421,8 @@ class StandaloneEncoder:
             plan.emb = torch.zeros(x.shape[0], self.enc.hidden_dim, device=x.device)
         plan.x.copy_(x)
         plan.mask.fill_(1.0)
+        if training:
+            plan.stat_arena.zero_()
         for op in (plan.fwd_train if training else plan.fwd_eval):
             op()
         if training:
@@ -523,6 +523,8 @@ class _StepPlan:
         eng, fs = self.eng, self.eng.fs
         p = eng.dropout_p
         fs.G.zero_()
+        self.audio.stat_arena.zero_()
+        self.image.stat_arena.zero_()
         if self._use_dropout() and own_dropout:
             ops.dropout_mask(self.drop_mask, p, eng.seed, fs.step)
         self._both_encoders(self.audio.fwd_train, self.image.fwd_train)
@@ -551,6 +553,8 @@ class _StepPlan:
     def run_forward_train_mode(self) -> None:
         """forward() in train() mode without a step: batch statistics, running stats updated, dropout applied."""
         eng, fs = self.eng, self.eng.fs
+        self.audio.stat_arena.zero_()
+        self.image.stat_arena.zero_()
         if self._use_dropout():
             ops.dropout_mask(self.drop_mask, eng.dropout_p, eng.seed, fs.step)
         self._both_encoders(self.audio.fwd_train, self.image.fwd_train)

@@ -57,17 +57,12 @@ def mask_apply(x: torch.Tensor, mask: torch.Tensor, want_reverse: bool = False):
 
 
 # ---- stem ----------------------------------------------------------------------------------------------------
-def stem_stat_tiles(B, H, W) -> int:
-    from ._lib import load_library
-
-    return load_library().mml_stem_stat_tiles(B, H, W)
-
-
-def stem_fprop(x, mask, w, y, stats_partial) -> None:
+def stem_fprop(x, mask, w, y, stats) -> None:
+    """stats: fp64 [64, 2] accumulator (zeroed by the caller) or None."""
     ctx = _ctx(x)
     B, H, W = x.shape
     ctx.check(ctx.lib.mml_stem_fprop(ctx.handle, _p(x, torch.float32), _p(mask, torch.float32), _p(w, torch.float32), _p(y, BF16),
-                                     _p(stats_partial, torch.float32), B, H, W, _stream(x)), "stem_fprop")
+                                     _p(stats, torch.float64), B, H, W, _stream(x)), "stem_fprop")
 
 
 def stem_wgrad_workspace(x) -> int:
@@ -84,15 +79,10 @@ def stem_wgrad(x, mask, dy, dw, workspace) -> None:
 
 
 # ---- conv ----------------------------------------------------------------------------------------------------
-def conv_stat_tiles(g: ConvGeom) -> int:
-    from ._lib import load_library
-
-    return load_library().mml_conv_stat_tiles(C.byref(g))
-
-
-def conv_fprop(g: ConvGeom, x, w_krsc, y, stats_partial=None) -> None:
+def conv_fprop(g: ConvGeom, x, w_krsc, y, stats=None) -> None:
+    """stats: fp64 [K, 2] accumulator of (sum, sum of squares) of y (zeroed by the caller) or None."""
     ctx = _ctx(x)
-    ctx.check(ctx.lib.mml_conv_fprop(ctx.handle, C.byref(g), _p(x, BF16), _p(w_krsc, BF16), _p(y, BF16), _p(stats_partial, torch.float32),
+    ctx.check(ctx.lib.mml_conv_fprop(ctx.handle, C.byref(g), _p(x, BF16), _p(w_krsc, BF16), _p(y, BF16), _p(stats, torch.float64),
                                      _stream(x)), "conv_fprop")
 
 
@@ -107,10 +97,23 @@ def conv_wgrad(g: ConvGeom, x, dy, dw_krsc) -> None:
 
 
 # ---- batch norm / activations / pooling ---------------------------------------------------------------------------
-def bn_finalize(partial, tiles, Cn, count, gamma, beta, rmean, rvar, momentum, eps, scale, shift, save_mean, save_invstd) -> None:
-    ctx = _ctx(partial)
-    ctx.check(ctx.lib.mml_bn_finalize(ctx.handle, _p(partial, torch.float32), tiles, Cn, count, _p(gamma), _p(beta), _p(rmean), _p(rvar),
-                                      momentum, eps, _p(scale), _p(shift), _p(save_mean), _p(save_invstd), _stream(partial)), "bn_finalize")
+class BNBuffers:
+    """Device pointers of one training-mode BatchNorm: fp64 stats, affine parameters, running and saved statistics."""
+
+    __slots__ = ("stats", "gamma", "beta", "rmean", "rvar", "mean", "invstd")
+
+    def __init__(self, stats, gamma, beta, rmean, rvar, mean, invstd):
+        self.stats, self.gamma, self.beta, self.rmean, self.rvar, self.mean, self.invstd = stats, gamma, beta, rmean, rvar, mean, invstd
+
+
+def bn_train_fwd(x, bn: "BNBuffers", res, rbn, y, rows, Cn, relu, momentum=0.1, eps=1e-5) -> None:
+    """y = relu?(bn(x) [+ res | + rbn(res)]) with batch statistics taken from bn.stats (fp64 sums from the conv epilogue)."""
+    ctx = _ctx(x)
+    z = C.c_void_p(0)
+    r = (_p(rbn.stats, torch.float64), _p(rbn.gamma), _p(rbn.beta), _p(rbn.rmean), _p(rbn.rvar), _p(rbn.mean), _p(rbn.invstd)) if rbn is not None else (z,) * 7
+    ctx.check(ctx.lib.mml_bn_train_fwd(ctx.handle, _p(x, BF16), _p(bn.stats, torch.float64), _p(bn.gamma), _p(bn.beta), _p(bn.rmean), _p(bn.rvar),
+                                       _p(bn.mean), _p(bn.invstd), _p(res), *r, _p(y, BF16), rows, Cn, int(relu), float(momentum), float(eps),
+                                       _stream(x)), "bn_train_fwd")
 
 
 def bn_eval_coeffs(Cn, gamma, beta, rmean, rvar, eps, scale, shift) -> None:
@@ -125,27 +128,17 @@ def bn_act_fwd(x, scale, shift, res, rscale, rshift, y, rows, Cn, relu) -> None:
                                      int(relu), _stream(x)), "bn_act_fwd")
 
 
-def bn_bwd_blocks(t, rows, Cn) -> int:
-    ctx = _ctx(t)
-    return ctx.lib.mml_bn_bwd_blocks(ctx.handle, rows, Cn)
-
-
-def bn_bwd_reduce(dy1, dy2, y, x, mean, invstd, partial, rows, Cn, relu) -> None:
+def bn_bwd_reduce(dy1, dy2, y, x, mean, invstd, bstat, rows, Cn, relu) -> None:
     ctx = _ctx(dy1)
-    ctx.check(ctx.lib.mml_bn_bwd_reduce(ctx.handle, _p(dy1, BF16), _p(dy2), _p(y), _p(x, BF16), _p(mean), _p(invstd), _p(partial), rows, Cn,
-                                        int(relu), _stream(dy1)), "bn_bwd_reduce")
+    ctx.check(ctx.lib.mml_bn_bwd_reduce(ctx.handle, _p(dy1, BF16), _p(dy2), _p(y), _p(x, BF16), _p(mean), _p(invstd), _p(bstat, torch.float64), rows,
+                                        Cn, int(relu), _stream(dy1)), "bn_bwd_reduce")
 
 
-def bn_bwd_finalize(partial, blocks, Cn, count, gamma, invstd, dgamma, dbeta, coef) -> None:
-    ctx = _ctx(partial)
-    ctx.check(ctx.lib.mml_bn_bwd_finalize(ctx.handle, _p(partial), blocks, Cn, count, _p(gamma), _p(invstd), _p(dgamma), _p(dbeta), _p(coef),
-                                          _stream(partial)), "bn_bwd_finalize")
-
-
-def bn_bwd_apply(dy1, dy2, y, x, mean, invstd, coef, dx, g_out, rows, Cn, relu) -> None:
+def bn_bwd_apply(dy1, dy2, y, x, mean, invstd, gamma, bstat, dgamma, dbeta, dx, g_out, rows, Cn, relu) -> None:
     ctx = _ctx(dy1)
-    ctx.check(ctx.lib.mml_bn_bwd_apply(ctx.handle, _p(dy1, BF16), _p(dy2), _p(y), _p(x, BF16), _p(mean), _p(invstd), _p(coef), _p(dx, BF16),
-                                       _p(g_out), rows, Cn, int(relu), _stream(dy1)), "bn_bwd_apply")
+    ctx.check(ctx.lib.mml_bn_bwd_apply(ctx.handle, _p(dy1, BF16), _p(dy2), _p(y), _p(x, BF16), _p(mean), _p(invstd), _p(gamma),
+                                       _p(bstat, torch.float64), _p(dgamma), _p(dbeta), _p(dx, BF16), _p(g_out), rows, Cn, int(relu),
+                                       _stream(dy1)), "bn_bwd_apply")
 
 
 def maxpool_fwd(x, y, argmax, N, H, W, Cn) -> None:

@@ -48,18 +48,17 @@ def test_stem_fprop_wgrad(B, H, W):
     w = torch.randn(64, 1, 7, 7, device="cuda", generator=gen(3)) * 0.2
     P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty(B, P, Q, 64, device="cuda", dtype=BF)
-    tiles = ops.stem_stat_tiles(B, H, W)
-    part = torch.zeros(tiles, 64, 2, device="cuda")
-    ops.stem_fprop(x, m, w.view(64, 49).contiguous(), y, part)
+    stats = torch.zeros(16, 64, 2, device="cuda", dtype=torch.float64)
+    ops.stem_fprop(x, m, w.view(64, 49).contiguous(), y, stats)
     xm = x * m.view(-1, 1, 1)
     ref = F.conv2d(xm.unsqueeze(1), w, stride=2, padding=3).permute(0, 2, 3, 1)
     assert ref.shape == y.shape
     err = (y.float() - ref).abs().max().item()
     assert err <= 2.0 ** -8 * ref.abs().max().item() + 1e-5, err
-    yf = y.float().reshape(-1, 64)
-    s = part.sum(0)
-    assert torch.allclose(s[:, 0], yf.sum(0), rtol=1e-4, atol=1e-2)
-    assert torch.allclose(s[:, 1], (yf * yf).sum(0), rtol=1e-4, atol=1e-2)
+    yf = y.double().reshape(-1, 64)
+    stats = stats.sum(0)
+    assert torch.allclose(stats[:, 0], yf.sum(0), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(stats[:, 1], (yf * yf).sum(0), rtol=1e-5, atol=1e-3)
     # wgrad
     dy = torch.randn(B, P, Q, 64, device="cuda", generator=gen(4)).to(BF)
     ws = torch.empty(ops.stem_wgrad_workspace(x) // 4, device="cuda")
@@ -79,48 +78,55 @@ def test_bn_forward_backward(rows, C):
     res = torch.randn(rows, C, device="cuda", generator=gen(6)).to(BF)
     gamma = torch.rand(C, device="cuda", generator=gen(7)) + 0.5
     beta = torch.randn(C, device="cuda", generator=gen(8)) * 0.1
-    # partials as a conv epilogue would emit them (two "tiles")
     xf = x.float()
-    h = rows // 2
-    part = torch.stack([torch.stack([xf[:h].sum(0), (xf[:h] ** 2).sum(0)], 1), torch.stack([xf[h:].sum(0), (xf[h:] ** 2).sum(0)], 1)]).contiguous()
-    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
-    scale, shift, mean, invstd = (torch.empty(C, device="cuda") for _ in range(4))
-    ops.bn_finalize(part, 2, C, rows, gamma, beta, rm, rv, 0.1, 1e-5, scale, shift, mean, invstd)
+
+    def mk(src):  # what a conv epilogue accumulates: fp64 (sum, sum of squares) of the stored values
+        sd = src.double()
+        st = torch.zeros(16, C, 2, device="cuda", dtype=torch.float64)
+        st[3] = torch.stack([sd.sum(0), (sd * sd).sum(0)], 1) * 0.25   # spread over slots like concurrent CTAs would
+        st[11] = torch.stack([sd.sum(0), (sd * sd).sum(0)], 1) * 0.75
+        return ops.BNBuffers(st, gamma, beta, torch.zeros(C, device="cuda"), torch.ones(C, device="cuda"), torch.empty(C, device="cuda"), torch.empty(C, device="cuda"))
+
+    bn = mk(xf)
     rm_ref, rv_ref = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
     xr = xf.clone().requires_grad_(True)
     gr = gamma.clone().requires_grad_(True)
     br = beta.clone().requires_grad_(True)
     resr = res.float().clone().requires_grad_(True)
-    bn = F.batch_norm(xr.t().reshape(1, C, rows), rm_ref, rv_ref, gr, br, True, 0.1, 1e-5).reshape(C, rows).t()
-    out_ref = F.relu(bn + resr)
-    assert torch.allclose(mean, xf.mean(0), rtol=1e-4, atol=1e-4)
-    assert torch.allclose(rm, rm_ref, rtol=1e-4, atol=1e-5) and torch.allclose(rv, rv_ref, rtol=1e-4, atol=1e-5)
+    bnref = F.batch_norm(xr.t().reshape(1, C, rows), rm_ref, rv_ref, gr, br, True, 0.1, 1e-5).reshape(C, rows).t()
+    out_ref = F.relu(bnref + resr)
     y = torch.empty(rows, C, device="cuda", dtype=BF)
-    ops.bn_act_fwd(x, scale, shift, res, None, None, y, rows, C, True)
+    ops.bn_train_fwd(x, bn, res, None, y, rows, C, True)
+    assert torch.allclose(bn.mean, xf.mean(0), rtol=1e-4, atol=1e-4)
+    assert torch.allclose(bn.rmean, rm_ref, rtol=1e-4, atol=1e-5) and torch.allclose(bn.rvar, rv_ref, rtol=1e-4, atol=1e-5)
     assert (y.float() - out_ref).abs().max().item() <= 2.0 ** -7 * out_ref.abs().max().item() + 1e-3
-    # affine residual variant and no-residual / no-relu variants
+    # residual through its own BN (downsample path), and the plain variant without ReLU
+    rbn = mk(res.float())
     y2 = torch.empty_like(y)
-    ops.bn_act_fwd(x, scale, shift, res, gamma, beta, y2, rows, C, True)
-    ref2 = F.relu(xf * scale + shift + res.float() * gamma + beta)
-    assert (y2.float() - ref2).abs().max().item() <= 2.0 ** -7 * ref2.abs().max().item() + 1e-3
+    ops.bn_train_fwd(x, mk(xf), res, rbn, y2, rows, C, True)
+    rref = F.batch_norm(res.float().t().reshape(1, C, rows), None, None, gamma, beta, True, 0.1, 1e-5).reshape(C, rows).t()
+    ref2 = F.relu(bnref.detach() + rref)
+    assert (y2.float() - ref2).abs().max().item() <= 2.0 ** -7 * ref2.abs().max().item() + 2e-3
     y3 = torch.empty_like(y)
-    ops.bn_act_fwd(x, scale, shift, None, None, None, y3, rows, C, False)
-    ref3 = xf * scale + shift
-    assert (y3.float() - ref3).abs().max().item() <= 2.0 ** -7 * ref3.abs().max().item() + 1e-3
+    ops.bn_train_fwd(x, mk(xf), None, None, y3, rows, C, False)
+    assert (y3.float() - bnref.detach()).abs().max().item() <= 2.0 ** -7 * bnref.abs().max().item() + 1e-3
+    # eval-mode (coefficient) form
+    scale, shift = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    ops.bn_eval_coeffs(C, gamma, beta, bn.rmean, bn.rvar, 1e-5, scale, shift)
+    y4 = torch.empty_like(y)
+    ops.bn_act_fwd(x, scale, shift, res, None, None, y4, rows, C, True)
+    ref4 = F.relu(F.batch_norm(xf.t().reshape(1, C, rows), bn.rmean, bn.rvar, gamma, beta, False, 0.1, 1e-5).reshape(C, rows).t() + res.float())
+    assert (y4.float() - ref4).abs().max().item() <= 2.0 ** -7 * ref4.abs().max().item() + 1e-3
     # backward (two incoming gradients, relu mask from the stored output)
     dy1 = torch.randn(rows, C, device="cuda", generator=gen(9)).to(BF)
     dy2 = torch.randn(rows, C, device="cuda", generator=gen(10)).to(BF)
-    out_from_y = F.relu(bn + resr)  # same graph; use mask of the kernel's stored y for consistency
-    gmask = (y.float() > 0).float()
-    gin = (dy1.float() + dy2.float()) * gmask
-    (bn * gin).sum().backward()  # d/dx of bn with upstream gradient gin (relu mask applied explicitly)
-    blocks = ops.bn_bwd_blocks(x, rows, C)
-    bpart = torch.zeros(blocks, C, 2, device="cuda")
-    ops.bn_bwd_reduce(dy1, dy2, y, x, mean, invstd, bpart, rows, C, True)
-    dgamma, dbeta, coef = torch.empty(C, device="cuda"), torch.empty(C, device="cuda"), torch.empty(3, C, device="cuda")
-    ops.bn_bwd_finalize(bpart, blocks, C, rows, gamma, invstd, dgamma, dbeta, coef)
+    gin = (dy1.float() + dy2.float()) * (y.float() > 0).float()
+    (bnref * gin).sum().backward()  # d/dx of bn with upstream gradient gin (relu mask applied explicitly)
+    bstat = torch.zeros(16, C, 2, device="cuda", dtype=torch.float64)
+    ops.bn_bwd_reduce(dy1, dy2, y, x, bn.mean, bn.invstd, bstat, rows, C, True)
+    dgamma, dbeta = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
     dx, gout = torch.empty(rows, C, device="cuda", dtype=BF), torch.empty(rows, C, device="cuda", dtype=BF)
-    ops.bn_bwd_apply(dy1, dy2, y, x, mean, invstd, coef, dx, gout, rows, C, True)
+    ops.bn_bwd_apply(dy1, dy2, y, x, bn.mean, bn.invstd, gamma, bstat, dgamma, dbeta, dx, gout, rows, C, True)
     tol = 2e-2
     assert (dgamma - gr.grad).abs().max().item() <= tol * gr.grad.abs().max().item() + 1e-2
     assert (dbeta - br.grad).abs().max().item() <= tol * br.grad.abs().max().item() + 1e-2
