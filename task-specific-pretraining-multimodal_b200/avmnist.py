@@ -177,7 +177,6 @@ class AVMNIST(nn.Module):
             plan.drop_mask.copy_(torch.as_tensor(given).reshape(plan.drop_mask.shape).to(torch.uint8), non_blocking=True)
         plan.train_step(given_dropout=given is not None)
         fs._host_step += 1
-        fs._versions = fs.param_versions()
         plan.h_loss.copy_(plan.loss, non_blocking=True)
         plan.h_pred.copy_(plan.pred, non_blocking=True)
         torch.cuda.current_stream(eng.device).synchronize()

@@ -13,7 +13,7 @@ using namespace mml;
 
 namespace {
 
-constexpr int SPC = 8;          // samples per CTA
+constexpr int SPC = 2;          // samples per CTA (B/2 CTAs: one per SM at B = 256..296)
 constexpr int kHeadThreads = 256;
 constexpr int kMaxFeat = 1024;  // FA + FI
 constexpr int kMaxEmb = 512;    // EA + EI
@@ -40,30 +40,49 @@ HeadDims dims_of(const mml_head_params* p) {
   return d;
 }
 
-// out[s][o] = act(b[o] + sum_k in[s][k] * W[o][k]) for the CTA's SPC samples; one output neuron per warp pass.
+// out[s][o] = act(b[o] + sum_k in[s][k] * W[o][k]) for the CTA's SPC samples.  A warp owns OPW output neurons per pass (OPW
+// independent coalesced weight-row streams in flight), lanes split K, shuffles reduce.
+constexpr int OPW = 4;
 template <bool RELU>
 __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const float* __restrict__ bias, int n_out, int n_in,
                                             const float* in_s, int in_ld, float* out_s, int out_ld, int out_off) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int o = warp; o < n_out; o += kHeadThreads / 32) {
-    float acc[SPC];
+  for (int o0 = warp * OPW; o0 < n_out; o0 += (kHeadThreads / 32) * OPW) {
+    float acc[OPW][SPC];
 #pragma unroll
-    for (int s = 0; s < SPC; ++s) acc[s] = 0.f;
-    const float* wrow = W + (size_t)o * n_in;
+    for (int u = 0; u < OPW; ++u)
+#pragma unroll
+      for (int s = 0; s < SPC; ++s) acc[u][s] = 0.f;
+#pragma unroll 2
     for (int k = lane; k < n_in; k += 32) {
-      const float wv = __ldg(wrow + k);
+      float xv[SPC];
 #pragma unroll
-      for (int s = 0; s < SPC; ++s) acc[s] = fmaf(in_s[s * in_ld + k], wv, acc[s]);
+      for (int s = 0; s < SPC; ++s) xv[s] = in_s[s * in_ld + k];
+#pragma unroll
+      for (int u = 0; u < OPW; ++u) {
+        const int o = min(o0 + u, n_out - 1);
+        const float wv = __ldg(W + (size_t)o * n_in + k);
+#pragma unroll
+        for (int s = 0; s < SPC; ++s) acc[u][s] = fmaf(xv[s], wv, acc[u][s]);
+      }
     }
 #pragma unroll
-    for (int s = 0; s < SPC; ++s) acc[s] = warp_sum(acc[s]);
-    if (lane < SPC) {
+    for (int u = 0; u < OPW; ++u)
+#pragma unroll
+      for (int s = 0; s < SPC; ++s) acc[u][s] = warp_sum(acc[u][s]);
+    if (lane < OPW * SPC) {
+      const int u = lane / SPC, sidx = lane % SPC;
       float v = 0.f;
 #pragma unroll
-      for (int s = 0; s < SPC; ++s)
-        if (lane == s) v = acc[s];
-      v += __ldg(bias + o);
-      out_s[lane * out_ld + out_off + o] = RELU ? fmaxf(v, 0.f) : v;
+      for (int uu = 0; uu < OPW; ++uu)
+#pragma unroll
+        for (int s = 0; s < SPC; ++s)
+          if (uu == u && s == sidx) v = acc[uu][s];
+      const int o = o0 + u;
+      if (o < n_out) {
+        v += __ldg(bias + o);
+        out_s[sidx * out_ld + out_off + o] = RELU ? fmaxf(v, 0.f) : v;
+      }
     }
   }
 }
@@ -173,6 +192,7 @@ __device__ __forceinline__ void dense_layer_t(const float* __restrict__ W, int n
     float acc[SPC];
 #pragma unroll
     for (int s = 0; s < SPC; ++s) acc[s] = 0.f;
+#pragma unroll 8
     for (int o = 0; o < n_out; ++o) {
       const float wv = __ldg(W + (size_t)o * n_in + i);
 #pragma unroll
@@ -285,6 +305,7 @@ __global__ void __launch_bounds__(256) head_bwd_weights_kernel(WgradJobs jobs, i
     __syncthreads();
     if ((int)threadIdx.x < nb) dsh[threadIdx.x] = J.dout[(size_t)(b0 + threadIdx.x) * J.dout_ld + o];
     __syncthreads();
+#pragma unroll 8
     for (int s = 0; s < nb; ++s) {
       const float g = dsh[s];
       bsum += g;

@@ -1,12 +1,20 @@
-// stem.cu -- the ResNet stem convolution (7x7, stride 2, pad 3, C_in = 1 -> 64) forward and weight gradient.
+// stem.cu -- the ResNet stem convolution (7x7, stride 2, pad 3, C_in = 1 -> 64) forward and weight gradient on tcgen05.
 //
 // Reference: MML_Suite/models/msa/networks/resnet.py:137 (self.conv1) applied at :205 to the (already masked) fp32
-// input, and data/base_dataset.py:71 (sample = original * mask) which is fused here: the kernel reads the ORIGINAL
-// fp32 input and multiplies by the per-sample mask on load (a true fp32 multiply, bit-identical to mml_mask_apply_f32).
-// K = 49 is too thin for tcgen05 tiles and the op is bandwidth/latency bound on its 64-channel bf16 output, so this is
-// a SIMT fp32 kernel: a CTA owns a 4 x 28 output-pixel tile and all 64 channels, the input patch and the 64x49 filter
-// live in shared memory, every thread accumulates 4 pixels x 8 channels in registers.  The epilogue stores bf16 NHWC
-// and accumulates the BatchNorm sum / sum of squares of the stored values (fp64 atomics).
+// input, and data/base_dataset.py:71 (sample = original * mask) which is fused here: the kernels read the ORIGINAL
+// fp32 input and multiply by the per-sample mask on load (mask_mul: bit-identical to mml_mask_apply_f32), then round
+// the product to bf16 (operand precision of every other convolution on the path).
+//
+// C_in = 1 gives a GEMM-K of only 49, so there is nothing for TMA to tile on the input side.  A tile is `rpt` whole output
+// rows of one image (<= 128 pixels).  The 128 builder threads first stage the tile's input patch ((2*rpt+5) x (2Q+6),
+// masked, rounded to bf16) in shared memory with coalesced loads -- prefetched one tile ahead into registers -- and then
+// each thread gathers the im2col row of "its" pixel: per filter row four 32-bit shared loads give the 7 taps, i.e. one
+// 16-byte chunk (GEMM-K index = r*8 + s, 7 x 8 = 56 of 64, zero elsewhere), stored with the SWIZZLE_128B pattern --
+// exactly the tile TMA would have produced.  The SAME tile is
+//   * the K-major A operand of fprop:   y[px][64 k]  = xcol[px][64] * W[64 k][64]^T
+//   * the MN-major B operand of wgrad:  dW[k][tap]  += dy[px][k]^T * xcol[px][tap]     (dy tile via TMA)
+// Persistent CTAs (2-3 per SM) loop over tiles with two A buffers and two TMEM accumulators so that building tile i+1,
+// the MMA of tile i and the epilogue of tile i-1 overlap.  Warps 0-3: build + epilogue, warp 4: MMA issue.
 #include "mml_common.cuh"
 #include "mml_ctx.h"
 
@@ -14,194 +22,368 @@ using namespace mml;
 
 namespace {
 
-constexpr int TP = 4;    // output rows per tile
-constexpr int TQ = 28;   // output cols per tile
-constexpr int kStemThreads = (TP * TQ / 4) * 8;  // 28 pixel groups x 8 channel groups = 224
-constexpr int PATCH_H = 2 * TP + 5;              // 13
-constexpr int PATCH_W = 2 * TQ + 5;              // 61
-constexpr int PATCH_LD = 64;
+constexpr int kTileM = 128;
+constexpr int kThreadsStem = 160;
+constexpr int kTileBytes = kTileM * 128;  // 16 KB
+constexpr int kPatchMaxHalves = 2048;     // bf16 elements of one input patch (16 per builder thread)
+constexpr int kPatchRegs = kPatchMaxHalves / 128;
 
 struct StemGeom {
-  int B, H, W, P, Q, tiles_p, tiles_q;
+  int B, H, W, P, Q;
+  int rpt;          // output rows per tile
+  int valid;        // rpt * Q pixels per tile (<= 128)
+  int tiles_per_img, tiles;
+  int PH, PWW;      // patch rows, patch row pitch in 32-bit words (2 bf16 each): 2Q+6 halves
+  int patch_halves;
 };
 
-__host__ __device__ inline StemGeom stem_geom(int B, int H, int W) {
-  StemGeom g;
-  g.B = B, g.H = H, g.W = W;
-  g.P = (H + 6 - 7) / 2 + 1;
-  g.Q = (W + 6 - 7) / 2 + 1;
-  g.tiles_p = (g.P + TP - 1) / TP;
-  g.tiles_q = (g.Q + TQ - 1) / TQ;
-  return g;
+inline bool stem_geom(int B, int H, int W, StemGeom* g) {
+  g->B = B, g->H = H, g->W = W;
+  g->P = (H + 6 - 7) / 2 + 1;
+  g->Q = (W + 6 - 7) / 2 + 1;
+  if (g->Q > 128 || g->P < 1 || g->Q < 1) return false;
+  int rpt = 1;
+  for (int d = 1; d <= g->P; ++d)
+    if (g->P % d == 0 && d * g->Q <= kTileM && (2 * d + 5) * (2 * g->Q + 6) <= kPatchMaxHalves) rpt = d;
+  g->rpt = rpt;
+  g->valid = rpt * g->Q;
+  g->tiles_per_img = g->P / rpt;
+  g->tiles = B * g->tiles_per_img;
+  g->PH = 2 * rpt + 5;
+  g->PWW = g->Q + 3;
+  g->patch_halves = g->PH * 2 * g->PWW;
+  return g->patch_halves <= kPatchMaxHalves;
 }
 
-__device__ __forceinline__ void load_patch(float* patch, const float* __restrict__ x, const float* __restrict__ mask, const StemGeom& g,
-                                           int b, int p0, int q0) {
-  const float m = mask ? mask[b] : 1.0f;
-  const int h0 = 2 * p0 - 3, w0 = 2 * q0 - 3;
-  const float* img = x + (size_t)b * g.H * g.W;
-  for (int i = threadIdx.x; i < PATCH_H * PATCH_LD; i += blockDim.x) {
-    const int r = i / PATCH_LD, c = i - r * PATCH_LD;
-    const int h = h0 + r, w = w0 + c;
+// ---- input patch: rows 2*p0-3 .. 2*p0+2*rpt+1, cols -3 .. 2Q+2 of image b, masked, as bf16 ----
+// The (row, column) of the 16 patch elements a builder thread owns do not depend on the tile: computed once.
+struct PatchMap {
+  int off[kPatchRegs];  // r * W + (c - 3)
+  int rr[kPatchRegs];   // patch row r, or a huge value for elements outside the patch / outside the image columns
+};
+__device__ __forceinline__ void patch_map_init(PatchMap& pm, const StemGeom& g) {
+  const int pw = 2 * g.PWW;
+#pragma unroll
+  for (int i = 0; i < kPatchRegs; ++i) {
+    const int e = (int)threadIdx.x + i * 128;
+    const int r = e / pw, c = e - r * pw;
+    const int w = c - 3;
+    const bool ok = e < g.patch_halves && w >= 0 && w < g.W;
+    pm.off[i] = r * g.W + w;
+    pm.rr[i] = ok ? r : (1 << 28);
+  }
+}
+__device__ __forceinline__ void patch_prefetch(float (&reg)[kPatchRegs], const PatchMap& pm, int tile, const float* __restrict__ x,
+                                               const float* __restrict__ mask, const StemGeom& g) {
+  const int b = tile / g.tiles_per_img;
+  const int p0 = (tile - b * g.tiles_per_img) * g.rpt;
+  const float mk = mask ? mask[b] : 1.0f;
+  const int hbase = 2 * p0 - 3;
+  const float* origin = x + (size_t)b * g.H * g.W + (long long)hbase * g.W;
+#pragma unroll
+  for (int i = 0; i < kPatchRegs; ++i) {
     float v = 0.f;
-    if (c < PATCH_W && h >= 0 && h < g.H && w >= 0 && w < g.W) {
-      v = img[(size_t)h * g.W + w];
-      if (mask) v = mask_mul(v, m);  // base_dataset.py:71
+    if ((unsigned)(hbase + pm.rr[i]) < (unsigned)g.H) {
+      v = __ldg(origin + pm.off[i]);
+      if (mask) v = mask_mul(v, mk);  // sample = original * mask, data/base_dataset.py:71
     }
-    patch[i] = v;
+    reg[i] = v;
   }
 }
-
-__global__ void __launch_bounds__(kStemThreads)
-stem_fprop_kernel(const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ w, uint16_t* __restrict__ y,
-                  double* __restrict__ stats, StemGeom g) {
-  __shared__ __align__(16) float wsm[49][64];          // [tap][k]
-  __shared__ __align__(16) float patch[PATCH_H * PATCH_LD];
-  __shared__ float red[TP * TQ / 4][64][2];
-
-  int tile = blockIdx.x;
-  const int tq = tile % g.tiles_q;
-  tile /= g.tiles_q;
-  const int tp = tile % g.tiles_p;
-  const int b = tile / g.tiles_p;
-  const int p0 = tp * TP, q0 = tq * TQ;
-
-  for (int i = threadIdx.x; i < 64 * 49; i += blockDim.x) {
-    const int k = i / 49, t = i - k * 49;
-    wsm[t][k] = w[i];
+__device__ __forceinline__ void patch_store(const float (&reg)[kPatchRegs], uint16_t* patch, const StemGeom& g) {
+#pragma unroll
+  for (int i = 0; i < kPatchRegs; ++i) {
+    const int e = (int)threadIdx.x + i * 128;
+    if (e < g.patch_halves) patch[e] = (uint16_t)(pack_bf16x2(reg[i], 0.f) & 0xFFFFu);
   }
-  load_patch(patch, x, mask, g, b, p0, q0);
-  __syncthreads();
-
-  const int cgrp = threadIdx.x & 7;
-  const int pgrp = threadIdx.x >> 3;       // 0..27
-  const int prow = pgrp / (TQ / 4);        // 0..3
-  const int pq4 = (pgrp % (TQ / 4)) * 4;   // 0,4,..,24
-  float acc[4][8];
+}
+// im2col row of tile pixel `row` -> 128-byte swizzled tile row (7 chunks of [7 taps, 0], last chunk zero)
+__device__ __forceinline__ void gather_row(uint32_t tile_addr, int row, const uint32_t* patch_words, int word0, int pww) {
+  const uint32_t row_addr = tile_addr + (uint32_t)row * 128u;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-
-#pragma unroll 1
   for (int r = 0; r < 7; ++r) {
-    const float* prow_ptr = patch + (2 * prow + r) * PATCH_LD + 2 * pq4;
-    float xin[13];
-#pragma unroll
-    for (int i = 0; i < 13; ++i) xin[i] = prow_ptr[i];
-#pragma unroll
-    for (int s = 0; s < 7; ++s) {
-      const float4 wa = *reinterpret_cast<const float4*>(&wsm[r * 7 + s][cgrp * 8]);
-      const float4 wb = *reinterpret_cast<const float4*>(&wsm[r * 7 + s][cgrp * 8 + 4]);
-      const float wk[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xin[2 * i + s], wk[j], acc[i][j]);
-    }
-  }
-
-  const int p = p0 + prow;
-  float sum[8], sq[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int q = q0 + pq4 + i;
-    if (p < g.P && q < g.Q) {
-      uint4 o;
-      o.x = pack_bf16x2(acc[i][0], acc[i][1]);
-      o.y = pack_bf16x2(acc[i][2], acc[i][3]);
-      o.z = pack_bf16x2(acc[i][4], acc[i][5]);
-      o.w = pack_bf16x2(acc[i][6], acc[i][7]);
-      *reinterpret_cast<uint4*>(y + ((((size_t)b * g.P + p) * g.Q + q) * 64 + cgrp * 8)) = o;
-      const float v[8] = {bf16_lo(o.x), bf16_hi(o.x), bf16_lo(o.y), bf16_hi(o.y), bf16_lo(o.z), bf16_hi(o.z), bf16_lo(o.w), bf16_hi(o.w)};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        sum[j] += v[j];
-        sq[j] = fmaf(v[j], v[j], sq[j]);
-      }
-    }
-  }
-  if (stats) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      red[pgrp][cgrp * 8 + j][0] = sum[j];
-      red[pgrp][cgrp * 8 + j][1] = sq[j];
-    }
-    __syncthreads();
-    if (threadIdx.x < 64) {
-      float a = 0.f, c = 0.f;
-      for (int t = 0; t < TP * TQ / 4; ++t) {
-        a += red[t][threadIdx.x][0];
-        c += red[t][threadIdx.x][1];
-      }
-      stat_add(stats, 64, blockIdx.x, threadIdx.x, a, c);
-    }
+    const uint32_t* src = patch_words + word0 + r * pww;
+    const uint32_t w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3] & 0x0000FFFFu;
+    const uint32_t dst = row_addr + (((uint32_t)r ^ (uint32_t)(row & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// wgrad: dw[k][r][s] = sum_{b,p,q} dy[b,p,q,k] * xm[b, 2p+r-3, 2q+s-3]
-// thread = (2 output channels, one filter row r) -> 14 register accumulators, persistent over tiles; per-CTA
-// partials go to a workspace and a second kernel reduces them in a fixed order (deterministic).
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kStemThreads)
-stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ mask, const uint16_t* __restrict__ dy, float* __restrict__ ws,
-                  StemGeom g, int total_tiles) {
-  __shared__ __align__(16) float patch[PATCH_H * PATCH_LD];
-  __shared__ __align__(16) float dys[TP * TQ][64 + 2];
-  const int kg = threadIdx.x & 31;  // channels 2*kg, 2*kg+1
-  const int r = threadIdx.x >> 5;   // 0..6
-  float acc[2][7];
-#pragma unroll
-  for (int s = 0; s < 7; ++s) acc[0][s] = acc[1][s] = 0.f;
+struct alignas(64) StemMaps {
+  CUtensorMap io;  // 4-D {64, Q, P, B}, box {64, Q, rpt, 1}: fprop stores y through it, wgrad loads dy through it
+};
 
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    int t = tile;
-    const int tq = t % g.tiles_q;
-    t /= g.tiles_q;
-    const int tp = t % g.tiles_p;
-    const int b = t / g.tiles_p;
-    const int p0 = tp * TP, q0 = tq * TQ;
-    __syncthreads();  // previous iteration done with smem
-    load_patch(patch, x, mask, g, b, p0, q0);
-    for (int i = threadIdx.x; i < TP * TQ * 8; i += blockDim.x) {
-      const int pix = i >> 3, c8 = i & 7;
-      const int p = p0 + pix / TQ, q = q0 + pix % TQ;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (p < g.P && q < g.Q) v = __ldg(reinterpret_cast<const uint4*>(dy + ((((size_t)b * g.P + p) * g.Q + q) * 64 + c8 * 8)));
-      float* d = &dys[pix][c8 * 8];
-      d[0] = bf16_lo(v.x), d[1] = bf16_hi(v.x), d[2] = bf16_lo(v.y), d[3] = bf16_hi(v.y);
-      d[4] = bf16_lo(v.z), d[5] = bf16_hi(v.z), d[6] = bf16_lo(v.w), d[7] = bf16_hi(v.w);
+// fprop smem: [A0 | A1 | W | staging | patch0 | patch1 | barriers]
+constexpr int kPatchBytes = kPatchMaxHalves * 2;
+constexpr int kFOffW = 2 * kTileBytes;
+constexpr int kFOffStage = kFOffW + 64 * 128;
+constexpr int kFOffPatch = kFOffStage + kTileBytes;
+constexpr int kFOffBars = kFOffPatch + 2 * kPatchBytes;
+constexpr int kFBytes = kFOffBars + 1024 + 1024;
+
+__global__ void __launch_bounds__(kThreadsStem, 3)
+stem_fprop_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restrict__ x, const float* __restrict__ mask,
+                     const float* __restrict__ w, double* __restrict__ stats, StemGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bars = smem_base + kFOffBars;
+  auto a_full = [&](int b) { return bars + 8u * b; };
+  auto mma_done = [&](int b) { return bars + 8u * (2 + b); };
+  const uint32_t tmem_slot = bars + 8u * 4;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kFOffBars + 8 * 4);
+  float2* stat_scratch = reinterpret_cast<float2*>(smem_gen + kFOffBars + 256);
+
+  {  // tile rows >= valid and chunk 7 of every row are never written by the builders: zero both A buffers once
+    uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* base = reinterpret_cast<uint4*>(smem_gen);
+    for (int i = threadIdx.x; i < 2 * kTileBytes / 16; i += blockDim.x) base[i] = z;
+  }
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&maps.io);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(a_full(b), 128);
+      mbar_init(mma_done(b), 1);
     }
-    __syncthreads();
-#pragma unroll 1
-    for (int pr = 0; pr < TP; ++pr) {
-      const float* xrow = patch + (2 * pr + r) * PATCH_LD;
-#pragma unroll 1
-      for (int q4 = 0; q4 < TQ; q4 += 4) {
-        float xin[13];
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc<128>(tmem_slot);
+  if (threadIdx.x < 64) {  // weights: row k, chunk r = [w[k][r][0..6], 0], chunk 7 = 0; K-major SWIZZLE_128B
+    const int k = threadIdx.x;
+    const uint32_t row_addr = smem_base + kFOffW + (uint32_t)k * 128u;
 #pragma unroll
-        for (int i = 0; i < 13; ++i) xin[i] = xrow[2 * q4 + i];
+    for (int r = 0; r < 8; ++r) {
+      uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+      if (r < 7) {
+        const float* wr = w + k * 49 + r * 7;
+        c0 = pack_bf16x2(wr[0], wr[1]), c1 = pack_bf16x2(wr[2], wr[3]), c2 = pack_bf16x2(wr[4], wr[5]), c3 = pack_bf16x2(wr[6], 0.f);
+      }
+      const uint32_t dst = row_addr + (((uint32_t)r ^ (uint32_t)(k & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  const int n_my = (g.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+      const uint32_t b_addr = smem_base + kFOffW;
+      for (int i = 0; i < n_my; ++i) {
+        const int buf = i & 1;
+        mbar_wait(a_full(buf), (uint32_t)(i >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + buf * kTileBytes;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 d = *reinterpret_cast<const float2*>(&dys[pr * TQ + q4 + i][2 * kg]);
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + buf * 64, umma_desc_sw128(a_addr + k * 32, 16, 1024), umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, k != 0);
+        umma_commit(mma_done(buf));
+      }
+    }
+  } else {
+    const int row = threadIdx.x;  // 0..127: tile row == TMEM lane
+    const int pr = row / g.Q, q = row - pr * g.Q;
+    const int word0 = 2 * pr * g.PWW + q;
+    const bool live = row < g.valid;
+    auto epilogue = [&](int j) {
+      const int buf = j & 1;
+      const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+      mbar_wait(mma_done(buf), (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 64);
+      tmem_ld_32x32(taddr, r0);
+      tmem_ld_32x32(taddr + 32, r1);
+      tmem_ld_wait();
+      if (threadIdx.x == 0) tma_store_wait_read<0>();  // the previous tile's TMA store has finished reading the staging buffer
+      named_bar_sync(1, 128);
+      const uint32_t stage = smem_base + kFOffStage;
+      const uint32_t row_addr = stage + row * 128;
 #pragma unroll
-          for (int s = 0; s < 7; ++s) {
-            acc[0][s] = fmaf(d.x, xin[2 * i + s], acc[0][s]);
-            acc[1][s] = fmaf(d.y, xin[2 * i + s], acc[1][s]);
-          }
+      for (int jj = 0; jj < 8; ++jj) {
+        const uint32_t* src = jj < 4 ? &r0[8 * jj] : &r1[8 * (jj - 4)];
+        const uint32_t dst = row_addr + (((uint32_t)jj ^ (uint32_t)(row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16x2(__uint_as_float(src[0]), __uint_as_float(src[1]))),
+                     "r"(pack_bf16x2(__uint_as_float(src[2]), __uint_as_float(src[3]))),
+                     "r"(pack_bf16x2(__uint_as_float(src[4]), __uint_as_float(src[5]))),
+                     "r"(pack_bf16x2(__uint_as_float(src[6]), __uint_as_float(src[7])))
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (threadIdx.x == 0) {
+        const int b = tile / g.tiles_per_img;
+        const int p0 = (tile - b * g.tiles_per_img) * g.rpt;
+        tma_store_4d(&maps.io, stage, 0, 0, p0, b);  // box = exactly the tile's rpt x Q pixels
+        tma_store_commit();
+      }
+      if (stats != nullptr) {
+        const int c = threadIdx.x & 63, half = threadIdx.x >> 6;
+        const int rbeg = half * 64, rend = min(g.valid, rbeg + 64);
+        float s = 0.f, ss = 0.f;
+        const uint8_t* colp = smem_gen + kFOffStage + (c & 7) * 2;
+        for (int r = rbeg; r < rend; ++r) {
+          const uint16_t raw = *reinterpret_cast<const uint16_t*>(colp + r * 128 + ((((uint32_t)c >> 3) ^ (uint32_t)(r & 7)) << 4));
+          const float v = __uint_as_float((uint32_t)raw << 16);
+          s += v;
+          ss = fmaf(v, v, ss);
+        }
+        if (half == 1) stat_scratch[c] = make_float2(s, ss);
+        named_bar_sync(1, 128);
+        if (half == 0) {
+          const float2 o = stat_scratch[c];
+          stat_add(stats, 64, tile, c, s + o.x, ss + o.y);
         }
       }
+    };
+    float reg[kPatchRegs];
+    PatchMap pm;
+    patch_map_init(pm, g);
+    if (n_my > 0) {
+      patch_prefetch(reg, pm, (int)blockIdx.x, x, mask, g);
+      patch_store(reg, reinterpret_cast<uint16_t*>(smem_gen + kFOffPatch), g);
+    }
+    named_bar_sync(1, 128);
+    for (int i = 0; i < n_my; ++i) {
+      const bool more = i + 1 < n_my;
+      if (more) patch_prefetch(reg, pm, (int)blockIdx.x + (i + 1) * (int)gridDim.x, x, mask, g);  // loads in flight during gather + epilogue
+      if (live) gather_row(smem_base + (i & 1) * kTileBytes, row, reinterpret_cast<const uint32_t*>(smem_gen + kFOffPatch + (i & 1) * kPatchBytes), word0, g.PWW);
+      fence_proxy_async_smem();
+      tc_fence_before();  // orders this thread's earlier TMEM loads before the MMA that will overwrite that accumulator
+      mbar_arrive(a_full(i & 1));
+      if (i >= 1) epilogue(i - 1);
+      if (more) patch_store(reg, reinterpret_cast<uint16_t*>(smem_gen + kFOffPatch + ((i + 1) & 1) * kPatchBytes), g);
+      named_bar_sync(1, 128);
+    }
+    if (n_my >= 1) epilogue(n_my - 1);
+    if (threadIdx.x == 0) tma_store_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<128>(tmem_base);
+}
+
+// wgrad smem: [X0 | X1 | DY0 (2 boxes) | DY1 (2 boxes) | patch0 | patch1 | barriers]
+constexpr int kWOffDy = 2 * kTileBytes;
+constexpr int kWOffPatch = kWOffDy + 2 * 2 * kTileBytes;
+constexpr int kWOffBars = kWOffPatch + 2 * kPatchBytes;
+constexpr int kWBytes = kWOffBars + 1024 + 1024;
+
+__global__ void __launch_bounds__(kThreadsStem, 2)
+stem_wgrad_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restrict__ x, const float* __restrict__ mask,
+                     float* __restrict__ ws, StemGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bars = smem_base + kWOffBars;
+  auto full = [&](int b) { return bars + 8u * b; };
+  auto freeb = [&](int b) { return bars + 8u * (2 + b); };
+  const uint32_t all_done = bars + 8u * 4;
+  const uint32_t tmem_slot = bars + 8u * 5;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kWOffBars + 8 * 5);
+
+  {  // rows >= valid of every tile and the k = 64..127 box of each dy stage are never written: zero everything once
+    uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* base = reinterpret_cast<uint4*>(smem_gen);
+    for (int i = threadIdx.x; i < kWOffPatch / 16; i += blockDim.x) base[i] = z;
+    fence_proxy_async_smem();
+  }
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&maps.io);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(full(b), 129);  // 128 builder rows + the arrive.expect_tx of the dy TMA
+      mbar_init(freeb(b), 1);
+    }
+    mbar_init(all_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc<64>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  const int n_my = (g.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+      const int ksteps = (g.valid + 15) >> 4;
+      for (int i = 0; i < n_my; ++i) {
+        const int buf = i & 1;
+        mbar_wait(full(buf), (uint32_t)(i >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + kWOffDy + buf * 2 * kTileBytes;  // dy^T, MN-major, M = k (64 valid rows)
+        const uint32_t b_addr = smem_base + buf * kTileBytes;                // xcol, MN-major, N = 64 (r*8+s)
+        for (int ks = 0; ks < ksteps; ++ks)
+          umma_bf16(tmem_base, umma_desc_sw128(a_addr + ks * 2048, kTileBytes, 1024), umma_desc_sw128(b_addr + ks * 2048, kTileBytes, 1024), idesc,
+                    (i | ks) != 0);
+        umma_commit(freeb(buf));
+      }
+      umma_commit(all_done);
+    }
+  } else {
+    const int row = threadIdx.x;
+    const int pr = row / g.Q, q = row - pr * g.Q;
+    const int word0 = 2 * pr * g.PWW + q;
+    const bool live = row < g.valid;
+    float reg[kPatchRegs];
+    PatchMap pm;
+    patch_map_init(pm, g);
+    if (n_my > 0) {
+      patch_prefetch(reg, pm, (int)blockIdx.x, x, mask, g);
+      patch_store(reg, reinterpret_cast<uint16_t*>(smem_gen + kWOffPatch), g);
+    }
+    named_bar_sync(1, 128);
+    for (int i = 0; i < n_my; ++i) {
+      const int buf = i & 1;
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      const bool more = i + 1 < n_my;
+      if (more) patch_prefetch(reg, pm, tile + (int)gridDim.x, x, mask, g);
+      if (i >= 2) mbar_wait(freeb(buf), (uint32_t)((i >> 1) - 1) & 1u);
+      if (threadIdx.x == 0) {
+        const int b = tile / g.tiles_per_img;
+        const int p0 = (tile - b * g.tiles_per_img) * g.rpt;
+        mbar_arrive_expect_tx(full(buf), (uint32_t)g.valid * 128u);
+        tma_load_4d(&maps.io, full(buf), smem_base + kWOffDy + buf * 2 * kTileBytes, 0, 0, p0, b);
+      }
+      if (live) gather_row(smem_base + buf * kTileBytes, row, reinterpret_cast<const uint32_t*>(smem_gen + kWOffPatch + buf * kPatchBytes), word0, g.PWW);
+      fence_proxy_async_smem();
+      mbar_arrive(full(buf));
+      if (more) patch_store(reg, reinterpret_cast<uint16_t*>(smem_gen + kWOffPatch + ((i + 1) & 1) * kPatchBytes), g);
+      named_bar_sync(1, 128);
+    }
+    // dW[k][r][s] lives in accumulator row k, column r*8+s
+    float* out = ws + ((size_t)blockIdx.x * 64 + row) * 49;
+    if (n_my >= 1) {
+      mbar_wait(all_done, 0);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+      tmem_ld_32x32(taddr, r0);
+      tmem_ld_32x32(taddr + 32, r1);
+      tmem_ld_wait();
+      if (row < 64) {
+#pragma unroll
+        for (int r = 0; r < 7; ++r)
+#pragma unroll
+          for (int s2 = 0; s2 < 7; ++s2) {
+            const int col = r * 8 + s2;
+            out[r * 7 + s2] = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]);
+          }
+      }
+    } else if (row < 64) {
+      for (int t = 0; t < 49; ++t) out[t] = 0.f;
     }
   }
-  float* out = ws + (size_t)blockIdx.x * (64 * 49);
-#pragma unroll
-  for (int s = 0; s < 7; ++s) {
-    out[(2 * kg) * 49 + r * 7 + s] = acc[0][s];
-    out[(2 * kg + 1) * 49 + r * 7 + s] = acc[1][s];
-  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<64>(tmem_base);
 }
 
 __global__ void stem_wgrad_reduce_kernel(const float* __restrict__ ws, int parts, float* __restrict__ dw) {
@@ -212,30 +394,53 @@ __global__ void stem_wgrad_reduce_kernel(const float* __restrict__ ws, int parts
   dw[i] = a;
 }
 
-int stem_wgrad_ctas(const mml_ctx* ctx, int total_tiles) {
-  int n = ctx->sm_count * 2;
-  if (n > total_tiles) n = total_tiles;
+// several CTAs per SM: each has only 4 builder warps, latency is hidden across CTAs (fprop 66 KB smem -> 3, wgrad 106 KB -> 2)
+int stem_ctas(const mml_ctx* ctx, int tiles, int per_sm) {
+  int n = ctx->sm_count * per_sm;
+  if (n > tiles) n = tiles;
   return n < 1 ? 1 : n;
+}
+
+int encode_px_map(mml_ctx* ctx, CUtensorMap* map, const void* ptr, const StemGeom& g) {
+  cuuint64_t dims[4] = {64, (cuuint64_t)g.Q, (cuuint64_t)g.P, (cuuint64_t)g.B};
+  cuuint64_t strides[3] = {128, (cuuint64_t)g.Q * 128, (cuuint64_t)g.P * g.Q * 128};
+  cuuint32_t box[4] = {64, (cuuint32_t)g.Q, (cuuint32_t)g.rpt, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return mml_set_error(ctx, MML_ERR_CUDA, "stem: cuTensorMapEncodeTiled failed: %d", (int)r);
+  return MML_OK;
 }
 
 }  // namespace
 
 extern "C" {
 
-int mml_stem_fprop(mml_ctx* ctx, const float* x, const float* mask, const float* w, uint16_t* y, double* stats, int B,
-                   int H, int W, void* stream) {
+int mml_stem_fprop(mml_ctx* ctx, const float* x, const float* mask, const float* w, uint16_t* y, double* stats, int B, int H,
+                   int W, void* stream) {
   MML_REQUIRE(ctx, ctx && x && w && y, "stem_fprop: null pointer");
   MML_REQUIRE(ctx, B >= 1 && H >= 1 && W >= 1, "stem_fprop: bad dims");
-  const StemGeom g = stem_geom(B, H, W);
-  stem_fprop_kernel<<<B * g.tiles_p * g.tiles_q, kStemThreads, 0, (cudaStream_t)stream>>>(x, mask, w, y, stats, g);
+  StemGeom g;
+  MML_REQUIRE(ctx, stem_geom(B, H, W, &g), "stem: output width %d not supported (max 128)", (W - 1) / 2 + 1);
+  StemMaps maps;
+  int rc = encode_px_map(ctx, &maps.io, y, g);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    MML_CHECK_CUDA(ctx, cudaFuncSetAttribute(stem_fprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFBytes));
+    MML_CHECK_CUDA(ctx, cudaFuncSetAttribute(stem_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWBytes));
+    configured = true;
+  }
+  stem_fprop_tc_kernel<<<stem_ctas(ctx, g.tiles, 3), kThreadsStem, kFBytes, (cudaStream_t)stream>>>(maps, x, mask, w, stats, g);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }
 
 int64_t mml_stem_wgrad_workspace(const mml_ctx* ctx, int B, int H, int W) {
-  if (!ctx) return 0;
-  const StemGeom g = stem_geom(B, H, W);
-  return (int64_t)stem_wgrad_ctas(ctx, B * g.tiles_p * g.tiles_q) * 64 * 49 * sizeof(float);
+  StemGeom g;
+  if (!ctx || !stem_geom(B, H, W, &g)) return 0;
+  return (int64_t)stem_ctas(ctx, g.tiles, 2) * 64 * 49 * sizeof(float);
 }
 
 int mml_stem_wgrad(mml_ctx* ctx, const float* x, const float* mask, const uint16_t* dy, float* dw, float* workspace,
@@ -243,11 +448,20 @@ int mml_stem_wgrad(mml_ctx* ctx, const float* x, const float* mask, const uint16
   MML_REQUIRE(ctx, ctx && x && dy && dw && workspace, "stem_wgrad: null pointer");
   MML_REQUIRE(ctx, B >= 1 && H >= 1 && W >= 1, "stem_wgrad: bad dims");
   MML_REQUIRE(ctx, workspace_bytes >= mml_stem_wgrad_workspace(ctx, B, H, W), "stem_wgrad: workspace too small");
-  const StemGeom g = stem_geom(B, H, W);
-  const int total = B * g.tiles_p * g.tiles_q;
-  const int ctas = stem_wgrad_ctas(ctx, total);
+  StemGeom g;
+  MML_REQUIRE(ctx, stem_geom(B, H, W, &g), "stem: output width %d not supported (max 128)", (W - 1) / 2 + 1);
+  StemMaps maps;
+  int rc = encode_px_map(ctx, &maps.io, dy, g);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    MML_CHECK_CUDA(ctx, cudaFuncSetAttribute(stem_fprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFBytes));
+    MML_CHECK_CUDA(ctx, cudaFuncSetAttribute(stem_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWBytes));
+    configured = true;
+  }
+  const int ctas = stem_ctas(ctx, g.tiles, 2);
   cudaStream_t st = (cudaStream_t)stream;
-  stem_wgrad_kernel<<<ctas, kStemThreads, 0, st>>>(x, mask, dy, workspace, g, total);
+  stem_wgrad_tc_kernel<<<ctas, kThreadsStem, kWBytes, st>>>(maps, x, mask, workspace, g);
   MML_LAUNCHED(ctx);
   stem_wgrad_reduce_kernel<<<(64 * 49 + 255) / 256, 256, 0, st>>>(workspace, ctas, dw);
   MML_LAUNCHED(ctx);

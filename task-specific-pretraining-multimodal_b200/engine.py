@@ -78,6 +78,8 @@ class FlatState:
         self.hyper_host: Optional[Tuple[float, ...]] = None
         self.step = torch.zeros(1, device=device, dtype=torch.int64)
         self._versions = None
+        self._sentinels = None
+        self._plist = list(module.parameters())
         self.bind(copy_in=True)
 
     # -- views ------------------------------------------------------------------------------------------------
@@ -123,13 +125,16 @@ class FlatState:
         mod._buffers[leaf] = value
 
     def is_bound(self) -> bool:
-        for name, p in self.module.named_parameters():
-            if p.data_ptr() != self.P.data_ptr() + 4 * self.offsets[name]:
-                return False
-        return True
+        """Cheap per-step check (first / last parameter); ``bind`` re-homes everything if an outside ``.to()`` or
+        ``param.data = ...`` moved them."""
+        if self._sentinels is None:
+            named = list(self.module.named_parameters())
+            self._plist = [p for _, p in named]
+            self._sentinels = [(p, self.P.data_ptr() + 4 * self.offsets[n]) for n, p in (named[0], named[len(named) // 2], named[-1])]
+        return all(p.data_ptr() == addr for p, addr in self._sentinels)
 
     def param_versions(self) -> int:
-        return sum(p._version for p in self.module.parameters())
+        return sum(p._version for p in self._plist)
 
     def refresh_shadows(self) -> None:
         """fp32 master -> bf16 operand copies (after load_state_dict / external optimizer steps)."""
@@ -145,6 +150,8 @@ class FlatState:
     # -- optimizer ---------------------------------------------------------------------------------------------
     def adopt_optimizer(self, optimizer: torch.optim.Optimizer) -> None:
         """Validate that ``optimizer`` is the Adam the fused kernel implements and alias its state to M / V."""
+        if getattr(self, "_adopted", None) is optimizer and len(optimizer.param_groups) == self._adopted_groups:
+            return
         if type(optimizer) is not torch.optim.Adam:
             raise NotImplementedError(
                 f"mml_b200 fused train_step implements torch.optim.Adam (the reference's AVMNIST optimizer); got {type(optimizer).__name__}. "
@@ -161,8 +168,6 @@ class FlatState:
         theirs = [p for g in groups for p in g["params"]]
         if {id(p) for p in theirs} != mine or len(theirs) != len(mine):
             raise NotImplementedError("the optimizer must hold exactly the parameters of the model")
-        if getattr(self, "_adopted", None) is optimizer:
-            return
         host_step = torch.tensor(float(self.step.item()))
         for name, p in self.module.named_parameters():
             st = optimizer.state[p]
@@ -176,9 +181,15 @@ class FlatState:
         self.step.fill_(int(host_step.item()))
         self._host_step = host_step
         self._adopted = optimizer
+        self._adopted_groups = len(groups)
 
     def sync_hyper(self, optimizer: torch.optim.Optimizer, grad_scale: float) -> None:
-        g = optimizer.param_groups[0]
+        groups = optimizer.param_groups
+        g = groups[0]
+        if len(groups) > 1:
+            keys = ("lr", "betas", "eps", "weight_decay")
+            if any(tuple(gg[k] for k in keys) != tuple(g[k] for k in keys) for gg in groups[1:]):
+                raise NotImplementedError("mml_b200 fused Adam needs identical hyper-parameters in all param groups")
         h = (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), float(grad_scale), 0.0, 0.0)
         if h != self.hyper_host:
             self.hyper.copy_(torch.tensor(h, dtype=torch.float32), non_blocking=False)

@@ -39,7 +39,7 @@ def test_mask_apply_bit_exact():
         assert np.array_equal(rr.cpu().view(torch.int32).numpy()[0], gold["out"][2 * i + 1])
 
 
-@pytest.mark.parametrize("B,H,W", [(4, 112, 112), (5, 28, 28), (3, 32, 94), (2, 9, 13)])
+@pytest.mark.parametrize("B,H,W", [(4, 112, 112), (5, 28, 28), (3, 32, 94), (2, 9, 13), (256, 28, 28), (37, 112, 112)])
 def test_stem_fprop_wgrad(B, H, W):
     from mml_b200 import ops
 
@@ -50,8 +50,10 @@ def test_stem_fprop_wgrad(B, H, W):
     y = torch.empty(B, P, Q, 64, device="cuda", dtype=BF)
     stats = torch.zeros(16, 64, 2, device="cuda", dtype=torch.float64)
     ops.stem_fprop(x, m, w.view(64, 49).contiguous(), y, stats)
-    xm = x * m.view(-1, 1, 1)
-    ref = F.conv2d(xm.unsqueeze(1), w, stride=2, padding=3).permute(0, 2, 3, 1)
+    # operands are rounded to bf16 by the kernel (after the exact fp32 mask multiply); accumulation is fp32
+    xm = (x * m.view(-1, 1, 1)).to(BF).float()
+    wb = w.to(BF).float()
+    ref = F.conv2d(xm.unsqueeze(1), wb, stride=2, padding=3).permute(0, 2, 3, 1)
     assert ref.shape == y.shape
     err = (y.float() - ref).abs().max().item()
     assert err <= 2.0 ** -8 * ref.abs().max().item() + 1e-5, err
@@ -64,7 +66,7 @@ def test_stem_fprop_wgrad(B, H, W):
     ws = torch.empty(ops.stem_wgrad_workspace(x) // 4, device="cuda")
     dw = torch.empty(64, 49, device="cuda")
     ops.stem_wgrad(x, m, dy, dw, ws)
-    wr = w.clone().requires_grad_(True)
+    wr = wb.clone().requires_grad_(True)
     F.conv2d(xm.unsqueeze(1), wr, stride=2, padding=3).backward(dy.float().permute(0, 3, 1, 2))
     refw = wr.grad.view(64, 49)
     assert (dw - refw).abs().max().item() <= 1e-3 * refw.abs().max().item() + 1e-4  # fp32 sums over up to 10^6 pixels, other order

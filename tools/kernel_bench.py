@@ -1,0 +1,79 @@
+"""Times individual kernels through the C ABI with CUDA events (median of N, L2 flushed between launches)."""
+import os
+import statistics
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mml_b200 import ops  # noqa: E402
+
+BF = torch.bfloat16
+flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+
+def timeit(fn, n=7):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    return statistics.median(ts)
+
+
+def stem(B, H, W):
+    x = torch.rand(B, H, W, device="cuda")
+    m = torch.ones(B, device="cuda")
+    w = torch.randn(64, 49, device="cuda") * 0.1
+    P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty(B, P, Q, 64, device="cuda", dtype=BF)
+    st = torch.zeros(16, 64, 2, device="cuda", dtype=torch.float64)
+    dy = torch.randn(B, P, Q, 64, device="cuda").to(BF)
+    ws = torch.empty(ops.stem_wgrad_workspace(x) // 4, device="cuda")
+    dw = torch.empty(64, 49, device="cuda")
+    print(f"stem B={B} {H}x{W}: fprop {timeit(lambda: ops.stem_fprop(x, m, w, y, st)):.1f} us, wgrad {timeit(lambda: ops.stem_wgrad(x, m, dy, dw, ws)):.1f} us")
+
+
+def conv(N, H, W, C, K, R, st, pad, tag=""):
+    g = ops.make_geom(N, H, W, C, K, R, R, st, pad)
+    P, Q = ops.conv_out_hw(H, W, R, R, st, pad)
+    x = torch.randn(N, H, W, C, device="cuda").to(BF)
+    w = (torch.randn(K, R, R, C, device="cuda") * 0.05).to(BF)
+    y = torch.empty(N, P, Q, K, device="cuda", dtype=BF)
+    dy = torch.randn(N, P, Q, K, device="cuda").to(BF)
+    dx = torch.empty(N, H, W, C, device="cuda", dtype=BF)
+    dw = torch.zeros(K, R, R, C, device="cuda")
+    stt = torch.zeros(16, K, 2, device="cuda", dtype=torch.float64)
+    fl = 2.0 * N * P * Q * K * C * R * R
+    tf = timeit(lambda: ops.conv_fprop(g, x, w, y, stt))
+    td = timeit(lambda: ops.conv_dgrad(g, dy, w, dx))
+    tw = timeit(lambda: ops.conv_wgrad(g, x, dy, dw))
+    print(f"conv {tag:10s} N={N} {H}x{W} C={C} K={K} R={R} s={st}: fprop {tf:6.1f} us ({fl / tf / 1e6:6.0f} TF)  dgrad {td:6.1f} us ({fl / td / 1e6:6.0f} TF)  wgrad {tw:6.1f} us ({fl / tw / 1e6:6.0f} TF)")
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    B = 256
+    if what in ("all", "stem"):
+        stem(B, 112, 112)
+        stem(B, 28, 28)
+    if what in ("all", "conv"):
+        conv(B, 28, 28, 64, 64, 3, 1, 1, "a.l1")
+        conv(B, 28, 28, 64, 128, 3, 2, 1, "a.l2.0c1")
+        conv(B, 14, 14, 128, 128, 3, 1, 1, "a.l2")
+        conv(B, 14, 14, 128, 256, 3, 2, 1, "a.l3.0c1")
+        conv(B, 7, 7, 256, 256, 3, 1, 1, "a.l3")
+        conv(B, 7, 7, 256, 512, 3, 2, 1, "a.l4.0c1")
+        conv(B, 4, 4, 512, 512, 3, 1, 1, "a.l4")
+        conv(B, 7, 7, 64, 64, 3, 1, 1, "i.l1")
+        conv(B, 4, 4, 128, 128, 3, 1, 1, "i.l2")
+        conv(B, 2, 2, 256, 256, 3, 1, 1, "i.l3")
+        conv(B, 1, 1, 512, 512, 3, 1, 1, "i.l4")
