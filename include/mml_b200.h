@@ -52,6 +52,10 @@ int mml_ctx_sm_count(const mml_ctx* ctx);
 /* number of kernels this library has launched since the ctx was created (bench.py's gpu_launches) */
 int64_t mml_ctx_launch_count(const mml_ctx* ctx);
 
+/* tuning / A-B switches for experiments (not part of the reference surface): key 1 = use the halo conv kernel (default 1),
+ * key 2 = halo descriptor base-offset mode (default 0) */
+int mml_debug_set(int key, int value);
+
 /* ---- a1: missing-modality mask -- data/base_dataset.py:70-72  sample[mod] = original * mask -------------------- */
 /* y[b, :] = x[b, :] * mask[b]   (true IEEE multiply, bit-exact with torch CPU); reverse: x * -1 * (mask - 1) */
 int mml_mask_apply_f32(mml_ctx*, const float* x, const float* mask, float* y, float* y_reverse, int64_t batch,

@@ -116,7 +116,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t tx_bytes = (uint32_t)p.valid_rows * 128u + (uint32_t)L::kB;
       int it = 0;
       for (int t = 0; t < p.num_taps; ++t) {
@@ -141,21 +141,26 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // elect.sync + (lo, hi) descriptor words with constant hi: ~5 uniform instructions per MMA (the issue rate of this one
+    // thread is what bounds tiles whose MMAs are short)
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, B_MN ? 1 : 0);
+      constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
+      constexpr uint32_t kLoB = B_MN ? ((8192u >> 4) << 16) : (1u << 16);
+      constexpr uint32_t kBStep = B_MN ? (2048u >> 4) : 2u;
+      const uint32_t a_lo_base = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t b_lo_base = (((smem_base + L::kA) & 0x3FFFFu) >> 4) | kLoB;
       for (int it = 0; it < iters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_base + s * L::kStage;
-        const uint32_t b_addr = a_addr + L::kA;
+        const uint32_t a_lo = a_lo_base + (uint32_t)s * (L::kStage >> 4);
+        const uint32_t b_lo = b_lo_base + (uint32_t)s * (L::kStage >> 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-          // K-major: +32 B per 16 K-elements inside the swizzle atom.  MN-major: 16 K-rows = 2 KB further down; the next
-          // 64 N-elements are one 8 KB box away (LBO).
-          const uint64_t db = B_MN ? umma_desc_sw128(b_addr + k * 2048, 8192, 1024) : umma_desc_sw128(b_addr + k * 32, 16, 1024);
+          const uint64_t da = ((uint64_t)kHi << 32) | (uint64_t)(a_lo + 2u * k);
+          const uint64_t db = ((uint64_t)kHi << 32) | (uint64_t)(b_lo + kBStep * k);
           umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
         }
         umma_commit(empty_bar(s));  // frees the smem slot once these MMAs have read it
@@ -239,6 +244,304 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<BLOCK_N>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// "halo" kernel: stride-1 3x3 convolutions on large feature maps (ResNet18 layer1 / layer2: 28x28x64, 14x14x128), fprop
+// and dgrad.  The tap-shifted GEMM above re-reads every activation tile 9 times and every weight tile once per CTA, which
+// makes those layers L2-bandwidth bound (172 B/cycle/SM needed, ~45 available).  Here a persistent CTA
+//   * loads the (Hb+2) x (Wb+2) x 64 input patch of an output tile ONCE per 64-channel chunk (TMA box with the halo,
+//     zero padding = out-of-bounds fill) and feeds all 9 taps from it: output pixel (h, w) is accumulator row
+//     m = h*(Wb+2) + w, so tap (dh, dw) is simply the SAME shared-memory tile read (dh+1)*(Wb+2) + (dw+1) rows further
+//     down -- a descriptor start-address shift; the 2 junk columns per row are clipped by the TMA store;
+//   * processes T tiles per iteration against one weight stage (weights stay resident in shared memory when they fit);
+//   * keeps 4 patches in flight (TMA latency) and double-buffers the TMEM accumulators, so the epilogue of iteration i
+//     (8 warps in two groups) overlaps the MMAs of i+1.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kPatchRows = 192;
+constexpr int kPatchBytes = kPatchRows * 128;  // 24 KB
+constexpr int kHaloThreads = 320;              // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two groups of 4)
+
+struct alignas(64) HaloMaps {
+  CUtensorMap in;   // {C, W, H, N}, box {64, Wb+2, Hb+2, 1}
+  CUtensorMap w;
+  CUtensorMap out;  // {K, W, H, N}, box {64, Wb+2, Hb, 1}
+};
+
+struct HaloParams {
+  int num_taps;
+  int w_tap_stride;
+  int tiles_h, Hb, Wb;
+  int m_tiles, num_super;
+  int cout;
+  int base_offset_mode;  // 0: descriptor base_offset = 0 (swizzle follows absolute smem address bits), 1: (shift & 7)
+  double* stats;
+  Tap taps[kMaxTaps];
+};
+
+template <int CCH, int BLOCK_N, int T, bool W_RES>
+struct HaloSmem {
+  static constexpr int kWStage = BLOCK_N * 128;
+  static constexpr int kWStages = W_RES ? 9 * CCH : 4;
+  static constexpr int kNPS = 4 / T;  // patch stages (ring over the sequence of (iteration, chunk) pairs): 96 KB of patches
+  static constexpr int kUnits = T * (BLOCK_N / 64);  // epilogue units (tile, 64-channel chunk) per iteration
+  static constexpr int kOffW = kNPS * T * kPatchBytes;
+  static constexpr int kOffStaging = kOffW + kWStages * kWStage;
+  static constexpr int kOffBars = kOffStaging + 2 * kBoxBytes;
+  static constexpr int kBytes = kOffBars + 512 /*barriers*/ + 4096 /*stats scratch*/ + 512 + 1024 /*alignment slack*/;
+  static constexpr int kTmemCols = 2 * T * BLOCK_N;
+  static_assert(kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM columns");
+  static_assert(kBytes <= 232448, "shared memory budget");
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_bo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t base_offset) {
+  return umma_desc_sw128(smem_addr, lbo_bytes, sbo_bytes) | ((uint64_t)(base_offset & 7u) << 49);
+}
+
+template <int CCH, int BLOCK_N, int T, bool W_RES, bool B_MN>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
+  using L = HaloSmem<CCH, BLOCK_N, T, W_RES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t bars = smem_base + L::kOffBars;
+  constexpr int NPS = L::kNPS;
+  auto patch_full = [&](int s) { return bars + 8u * s; };
+  auto patch_empty = [&](int s) { return bars + 8u * (4 + s); };
+  auto acc_full = [&](int s) { return bars + 8u * (8 + s); };
+  auto acc_empty = [&](int s) { return bars + 8u * (10 + s); };
+  auto w_full = [&](int s) { return bars + 8u * (12 + s); };
+  auto w_empty = [&](int s) { return bars + 8u * (12 + L::kWStages + s); };
+  const uint32_t tmem_slot = bars + 8u * (12 + 2 * L::kWStages);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kOffBars + 8 * (12 + 2 * L::kWStages));
+  float4* stat_scratch = reinterpret_cast<float4*>(smem_gen + L::kOffBars + 512);  // [2 groups][4 quarters... 32] float4
+
+  auto patch_addr = [&](int ps, int j) { return smem_base + (uint32_t)((ps * T + j) * kPatchBytes); };
+  const int n_my = (p.num_super - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int wp2 = p.Wb + 2;
+  const int rows_m = p.Hb * wp2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.in);
+    tma_prefetch_desc(&maps.w);
+    tma_prefetch_desc(&maps.out);
+    for (int s = 0; s < NPS; ++s) {
+      mbar_init(patch_full(s), 1);
+      mbar_init(patch_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), L::kUnits == 1 ? 4 : 8);  // one unit per iteration: the two epilogue groups alternate iterations
+    }
+    for (int s = 0; s < L::kWStages; ++s) {
+      mbar_init(w_full(s), 1);
+      mbar_init(w_empty(s), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<L::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  auto load_w_stage = [&](int s, int cc, const Tap& tap, uint32_t bar) {
+    const uint32_t dst = smem_base + L::kOffW + s * L::kWStage;
+    if (!B_MN) {
+      tma_load_2d(&maps.w, bar, dst, tap.widx * p.w_tap_stride + cc * 64, 0);
+    } else {
+#pragma unroll
+      for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(&maps.w, bar, dst + j * 8192, tap.widx * p.w_tap_stride + j * 64, cc * 64);
+    }
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      if (W_RES) {
+        mbar_arrive_expect_tx(w_full(0), (uint32_t)(p.num_taps * CCH * L::kWStage));
+        for (int cc = 0; cc < CCH; ++cc)
+          for (int t = 0; t < p.num_taps; ++t) load_w_stage(cc * p.num_taps + t, cc, p.taps[t], w_full(0));
+      }
+      const uint32_t patch_tx = (uint32_t)((p.Hb + 2) * wp2) * 128u;
+      int wi = 0;
+      for (int it = 0; it < n_my; ++it) {
+        const int st = (int)blockIdx.x + it * (int)gridDim.x;
+        for (int cc = 0; cc < CCH; ++cc) {
+          const int seq = it * CCH + cc, ps = seq % NPS;
+          mbar_wait(patch_empty(ps), (((uint32_t)(seq / NPS)) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(patch_full(ps), patch_tx * T);
+#pragma unroll
+          for (int j = 0; j < T; ++j) {
+            const int m_tile = st * T + j;  // beyond m_tiles -> image index out of range -> TMA zero fill, store clipped
+            const int n = m_tile / p.tiles_h, hb = m_tile - n * p.tiles_h;
+            tma_load_4d(&maps.in, patch_full(ps), patch_addr(ps, j), cc * 64, -1, hb * p.Hb - 1, n);
+          }
+          if (!W_RES) {
+            for (int t = 0; t < p.num_taps; ++t, ++wi) {
+              const int s = wi % L::kWStages;
+              mbar_wait(w_empty(s), (((uint32_t)(wi / L::kWStages)) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(w_full(s), (uint32_t)L::kWStage);
+              load_w_stage(s, cc, p.taps[t], w_full(s));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // The issue rate of this single thread bounds small-N tiles (a 128x64x16 MMA executes in ~32 cycles), so everything
+    // per MMA is kept to a couple of uniform integer adds: descriptors are (lo, hi) pairs, hi is a constant, the nine tap
+    // row-shifts are precomputed, all loops are fully unrolled (the halo kernel always has 9 taps).  elect.sync (not
+    // lane == 0) lets the compiler keep the descriptors in uniform registers without a per-MMA election loop.
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, B_MN ? 1 : 0);
+      constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
+      constexpr uint32_t kLoA = 1u << 16;                               // K-major: LBO field = 1 (unused)
+      constexpr uint32_t kLoB = B_MN ? ((8192u >> 4) << 16) : (1u << 16);
+      constexpr uint32_t kBStep = B_MN ? (2048u >> 4) : 2u;             // per 16 K-elements
+      uint32_t tap_off[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap_off[t] = (uint32_t)(((p.taps[t].dh + 1) * wp2 + (p.taps[t].dw + 1)) * 8);  // rows * 128 B / 16
+      if (W_RES) {
+        mbar_wait(w_full(0), 0);
+        tc_fence_after();
+      }
+      int wi = 0;
+      for (int it = 0; it < n_my; ++it) {
+        const int ab = it & 1;
+        mbar_wait(acc_empty(ab), (((uint32_t)it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < CCH; ++cc) {
+          const int seq = it * CCH + cc, ps = seq % NPS;
+          mbar_wait(patch_full(ps), ((uint32_t)(seq / NPS)) & 1u);
+          tc_fence_after();
+          const uint32_t a_lo0 = ((patch_addr(ps, 0) & 0x3FFFFu) >> 4) | kLoA;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            int s;
+            if (W_RES) {
+              s = cc * 9 + t;
+            } else {
+              s = wi % L::kWStages;
+              mbar_wait(w_full(s), ((uint32_t)(wi / L::kWStages)) & 1u);
+              tc_fence_after();
+            }
+            const uint32_t b_lo = (((smem_base + L::kOffW + (uint32_t)s * L::kWStage) & 0x3FFFFu) >> 4) | kLoB;
+#pragma unroll
+            for (int j = 0; j < T; ++j) {
+              const uint32_t a_lo = a_lo0 + (uint32_t)j * (kPatchBytes >> 4) + tap_off[t];
+              const uint32_t d_tmem = tmem_base + (uint32_t)((ab * T + j) * BLOCK_N);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = ((uint64_t)kHi << 32) | (uint64_t)(a_lo + 2u * k);
+                const uint64_t db = ((uint64_t)kHi << 32) | (uint64_t)(b_lo + kBStep * k);
+                if (cc == 0 && t == 0 && k == 0) umma_bf16(d_tmem, da, db, idesc, 0u);
+                else umma_bf16(d_tmem, da, db, idesc, 1u);
+              }
+            }
+            if (!W_RES) {
+              umma_commit(w_empty(s));
+              ++wi;
+            }
+          }
+          umma_commit(patch_empty(ps));
+        }
+        umma_commit(acc_full(ab));
+      }
+    }
+  } else {
+    // ===================== epilogue: two groups of 4 warps =====================
+    const int gi = (warp - 2) >> 2;       // group
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;        // accumulator row == tile row m = h*(Wb+2) + w
+    const int eg = ((warp - 2) & 3) * 32 + lane;  // 0..127 within the group
+    const uint32_t bar_id = 1 + gi;
+    const uint32_t stage = smem_base + L::kOffStaging + gi * kBoxBytes;
+    const uint8_t* stage_gen = smem_gen + L::kOffStaging + gi * kBoxBytes;
+    // statistics: thread = (word column wc: channels 2wc, 2wc+1) x (row quarter rq); valid rows of the quarter as a bit mask
+    const int wc = eg & 31, rq = eg >> 5;
+    uint32_t vmask = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int r = rq * 32 + b;
+      if (r < rows_m && (r % wp2) < p.Wb) vmask |= 1u << b;
+    }
+    constexpr int kChunks = BLOCK_N / 64;
+    for (int it = 0; it < n_my; ++it) {
+      const int ab = it & 1;
+      if (L::kUnits == 1 && ab != gi) continue;  // single unit per iteration: group g owns accumulator buffer g
+      const int st = (int)blockIdx.x + it * (int)gridDim.x;
+      mbar_wait(acc_full(ab), ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int u = 0; u < L::kUnits; ++u) {
+        if (L::kUnits > 1 && (u & 1) != gi) continue;  // units alternate between the two groups
+        const int j = (T > 1) ? (u % T) : 0;
+        const int ch = (T > 1) ? (u / T) : u;
+        const int m_tile = st * T + j;
+        const int n = m_tile / p.tiles_h, hb = m_tile - n * p.tiles_h;
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * T + j) * BLOCK_N + ch * 64);
+        tmem_ld_32x32(taddr, r0);
+        tmem_ld_32x32(taddr + 32, r1);
+        tmem_ld_wait();
+        if (eg == 0) tma_store_wait_read<0>();  // this group's previous TMA store has finished reading the staging buffer
+        named_bar_sync(bar_id, 128);
+        const uint32_t row_addr = stage + row * 128;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const uint32_t* src = jj < 4 ? &r0[8 * jj] : &r1[8 * (jj - 4)];
+          const uint32_t dst = row_addr + (((uint32_t)jj ^ (uint32_t)(row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16x2(__uint_as_float(src[0]), __uint_as_float(src[1]))),
+                       "r"(pack_bf16x2(__uint_as_float(src[2]), __uint_as_float(src[3]))),
+                       "r"(pack_bf16x2(__uint_as_float(src[4]), __uint_as_float(src[5]))),
+                       "r"(pack_bf16x2(__uint_as_float(src[6]), __uint_as_float(src[7])))
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (eg == 0 && m_tile < p.m_tiles) {
+          tma_store_4d(&maps.out, stage, ch * 64, 0, hb * p.Hb, n);  // box {64, Wb+2, Hb, 1}: the 2 junk columns are clipped
+          tma_store_commit();
+        }
+        if (p.stats != nullptr && m_tile < p.m_tiles) {
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          const uint8_t* colp = stage_gen + (wc & 3) * 4;
+#pragma unroll 8
+          for (int b = 0; b < 32; ++b) {
+            if (vmask & (1u << b)) {
+              const int r = rq * 32 + b;
+              const uint32_t v = *reinterpret_cast<const uint32_t*>(colp + r * 128 + ((((uint32_t)wc >> 2) ^ (uint32_t)(r & 7)) << 4));
+              const float a = bf16_lo(v), c = bf16_hi(v);
+              s0 += a, s1 += c;
+              q0 = fmaf(a, a, q0), q1 = fmaf(c, c, q1);
+            }
+          }
+          float4* sc = stat_scratch + gi * 128;
+          sc[eg] = make_float4(s0, s1, q0, q1);
+          named_bar_sync(bar_id, 128);
+          if (eg < 32) {
+            const float4 a = sc[eg], b2 = sc[eg + 32], c2 = sc[eg + 64], d2 = sc[eg + 96];
+            const int c0 = ch * 64 + 2 * eg;
+            stat_add(p.stats, p.cout, m_tile, c0, a.x + b2.x + c2.x + d2.x, a.z + b2.z + c2.z + d2.z);
+            stat_add(p.stats, p.cout, m_tile, c0 + 1, a.y + b2.y + c2.y + d2.y, a.w + b2.w + c2.w + d2.w);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(ab));
+    }
+    if (eg == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<L::kTmemCols>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -345,21 +648,28 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_C, 1, 1);
+      constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
+      constexpr uint32_t kLo = ((uint32_t)kBoxBytes >> 4) << 16;        // LBO: next 64 channels are one box further
+      const uint32_t a_lo_base = ((smem_base & 0x3FFFFu) >> 4) | kLo;
+      const uint32_t b_lo_base = (((smem_base + L::kA) & 0x3FFFFu) >> 4) | kLo;
       const int ksteps = (p.valid_rows + 15) >> 4;
       for (int it = 0; it < iters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_base + s * L::kStage;
-        const uint32_t b_addr = a_addr + L::kA;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          // 16 pixel rows per MMA = two 8-row groups (SBO = 1024 B apart); next 64 channels are LBO = one box apart
-          const uint64_t da = umma_desc_sw128(a_addr + ks * 2048, kBoxBytes, 1024);
-          const uint64_t db = umma_desc_sw128(b_addr + ks * 2048, kBoxBytes, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (it | ks) != 0 ? 1u : 0u);
+        const uint32_t a_lo = a_lo_base + (uint32_t)s * (L::kStage >> 4);
+        const uint32_t b_lo = b_lo_base + (uint32_t)s * (L::kStage >> 4);
+        // 16 pixel rows per MMA = two 8-row groups (SBO = 1024 B apart) = 2 KB further down per step
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          if (ks < ksteps) {
+            const uint64_t da = ((uint64_t)kHi << 32) | (uint64_t)(a_lo + 128u * ks);
+            const uint64_t db = ((uint64_t)kHi << 32) | (uint64_t)(b_lo + 128u * ks);
+            umma_bf16(tmem_base, da, db, idesc, (it | ks) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(empty_bar(s));
       }
@@ -591,6 +901,72 @@ int build_fprop_taps(const mml_conv_geom* g, int P, int Q, const void* x, View* 
   return n;
 }
 
+// ---- halo kernel dispatch -------------------------------------------------------------------------------------------
+struct HaloGeom {
+  int Wb, Hb, tiles_h, m_tiles;
+};
+
+// eligible: 3x3 taps with |dh|,|dw| <= 1 on one full-resolution view, C == K in {64, 128}, and a tile of Hb x W pixels whose
+// padded-width row index Hb*(W+2) fits the 128 accumulator rows while the deepest tap shift stays inside the 192-row patch
+bool halo_geometry(int outW, int outH, int N, int cin, int cout, HaloGeom* hg) {
+  if (cin != cout || (cin != 64 && cin != 128)) return false;
+  if (outW + 2 > 31 || outW < 3 || outH < 3) return false;
+  int hb = 0;
+  for (int d = 1; d <= outH; ++d)
+    if (outH % d == 0 && (outW + 2) * d <= 128) hb = d;
+  if (hb == 0) return false;
+  if ((outW + 2) * hb < 96) return false;  // too few live rows per 128-row MMA: the tap-shifted kernel packs better
+  if (2 * (outW + 2) + 2 + 128 > kPatchRows) return false;
+  hg->Wb = outW, hg->Hb = hb, hg->tiles_h = outH / hb, hg->m_tiles = (outH / hb) * N;
+  return true;
+}
+
+template <int CCH, int BLOCK_N, int T, bool W_RES, bool B_MN>
+int launch_halo_t(mml_ctx* ctx, const HaloMaps& maps, const HaloParams& p, cudaStream_t st) {
+  using L = HaloSmem<CCH, BLOCK_N, T, W_RES>;
+  static bool configured = false;
+  if (!configured) {
+    int rc = set_smem_limit(ctx, conv_halo_kernel<CCH, BLOCK_N, T, W_RES, B_MN>, L::kBytes);
+    if (rc) return rc;
+    configured = true;
+  }
+  int grid = p.num_super < ctx->sm_count ? p.num_super : ctx->sm_count;
+  conv_halo_kernel<CCH, BLOCK_N, T, W_RES, B_MN><<<grid, kHaloThreads, L::kBytes, st>>>(maps, p);
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
+int g_halo_enable = 1;
+int g_halo_base_offset_mode = 0;
+
+int run_halo(mml_ctx* ctx, const View& in, const void* w, int n_wtaps, int cin, int cout, const View& out, const Tap* taps, int num_taps,
+             double* stats, bool b_mn, const HaloGeom& hg, cudaStream_t st) {
+  HaloMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc;
+  if ((rc = encode_view(ctx, &maps.in, in, hg.Wb + 2, hg.Hb + 2, 1))) return rc;
+  if ((rc = encode_view(ctx, &maps.out, out, hg.Wb + 2, hg.Hb, 1))) return rc;
+  if (!b_mn) {
+    if ((rc = encode_weights(ctx, &maps.w, w, (long long)n_wtaps * cin, cout, cout))) return rc;
+  } else {
+    if ((rc = encode_weights(ctx, &maps.w, w, (long long)n_wtaps * cout, cin, 64))) return rc;
+  }
+  const int T = cin == 64 ? 1 : 2;  // C = 64: weights resident, one tile per iteration, 4 patches in flight
+  HaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.num_taps = num_taps;
+  p.w_tap_stride = b_mn ? cout : cin;
+  p.tiles_h = hg.tiles_h, p.Hb = hg.Hb, p.Wb = hg.Wb;
+  p.m_tiles = hg.m_tiles;
+  p.num_super = (hg.m_tiles + T - 1) / T;
+  p.cout = cout;
+  p.base_offset_mode = g_halo_base_offset_mode;
+  p.stats = stats;
+  for (int i = 0; i < num_taps; ++i) p.taps[i] = taps[i];
+  if (cin == 64) return b_mn ? launch_halo_t<1, 64, 1, true, true>(ctx, maps, p, st) : launch_halo_t<1, 64, 1, true, false>(ctx, maps, p, st);
+  return b_mn ? launch_halo_t<2, 128, 2, false, true>(ctx, maps, p, st) : launch_halo_t<2, 128, 2, false, false>(ctx, maps, p, st);
+}
+
 template <int BLOCK_C, int STAGES>
 int launch_wgrad_t(mml_ctx* ctx, const WgradMaps& maps, const WgradParams& p, dim3 grid, cudaStream_t st) {
   using L = WgradSmem<BLOCK_C, STAGES>;
@@ -608,6 +984,14 @@ int launch_wgrad_t(mml_ctx* ctx, const WgradMaps& maps, const WgradParams& p, di
 }  // namespace
 
 extern "C" {
+
+/* experiment / A-B switches: key 1 = halo kernel enable (0/1), key 2 = halo descriptor base-offset mode (0/1) */
+int mml_debug_set(int key, int value) {
+  if (key == 1) g_halo_enable = value;
+  else if (key == 2) g_halo_base_offset_mode = value;
+  else return MML_ERR_INVALID;
+  return MML_OK;
+}
 
 int mml_conv_fprop(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, const uint16_t* w_krsc, uint16_t* y,
                    double* stats, void* stream) {
@@ -630,6 +1014,9 @@ int mml_conv_fprop(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, cons
   }
   for (int i = 0; i < n_taps; ++i) taps[i].map = (int8_t)remap[taps[i].map];
   View out = make_phase_view(y, g->N, P, Q, g->K, 1, 0, 0);
+  HaloGeom hg;
+  if (g_halo_enable && g->R == 3 && g->stride == 1 && g->pad == 1 && n_taps == 9 && halo_geometry(Q, P, g->N, g->C, g->K, &hg))
+    return run_halo(ctx, used[0], w_krsc, 9, g->C, g->K, out, taps, n_taps, stats, false, hg, (cudaStream_t)stream);
   return run_igemm(ctx, used, n_used, w_krsc, g->R * g->S, g->C, g->K, out, taps, n_taps, stats, false, (cudaStream_t)stream);
 }
 
@@ -673,6 +1060,9 @@ int mml_conv_dgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* dy, con
         ++n_launch;
     }
   if (need_zero) MML_CHECK_CUDA(ctx, cudaMemsetAsync(dx, 0, (size_t)g->N * g->H * g->W * g->C * 2, st));
+  HaloGeom hg;
+  if (g_halo_enable && g->R == 3 && s2 == 1 && g->pad == 1 && n_launch == 1 && launches[0].n == 9 && halo_geometry(g->W, g->H, g->N, g->K, g->C, &hg))
+    return run_halo(ctx, in, w_krsc, 9, g->K, g->C, launches[0].out, launches[0].taps, 9, nullptr, true, hg, st);
   for (int i = 0; i < n_launch; ++i) {
     // GEMM-K = k (rows of the K,R,S,C weight matrix), GEMM-N = c: the fprop weights are read as an MN-major B operand
     rc = run_igemm(ctx, &in, 1, w_krsc, g->R * g->S, g->K, g->C, launches[i].out, launches[i].taps, launches[i].n, nullptr, true, st);

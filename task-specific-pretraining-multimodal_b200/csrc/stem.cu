@@ -171,7 +171,7 @@ stem_fprop_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
   const int n_my = (g.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
       const uint32_t b_addr = smem_base + kFOffW;
       for (int i = 0; i < n_my; ++i) {
@@ -311,7 +311,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
   const int n_my = (g.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
       const int ksteps = (g.valid + 15) >> 4;
       for (int i = 0; i < n_my; ++i) {

@@ -242,5 +242,11 @@ def scale_inplace(x, weights, idx) -> None:
     ctx.check(ctx.lib.mml_scale_inplace(ctx.handle, _p(x, torch.float32), _p(weights, torch.float32), idx, x.numel(), _stream(x)), "scale_inplace")
 
 
+def debug_set(key: int, value: int) -> None:
+    from ._lib import load_library
+
+    load_library().mml_debug_set(int(key), int(value))
+
+
 def launch_count(device_index: int = 0) -> int:
     return Context.get(device_index).launches

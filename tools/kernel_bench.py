@@ -77,3 +77,7 @@ if __name__ == "__main__":
         conv(B, 4, 4, 128, 128, 3, 1, 1, "i.l2")
         conv(B, 2, 2, 256, 256, 3, 1, 1, "i.l3")
         conv(B, 1, 1, 512, 512, 3, 1, 1, "i.l4")
+    if what == "l1":
+        conv(B, 28, 28, 64, 64, 3, 1, 1, "a.l1")
+    if what == "l2":
+        conv(B, 14, 14, 128, 128, 3, 1, 1, "a.l2")
