@@ -716,6 +716,204 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// "halo" wgrad: dW of the stride-1 3x3 layers on large feature maps.  Persistent CTAs walk pixel tiles; per tile they load
+// the input patch (with halo) and the dy tile ONCE, both in the padded-width row order m = h*(Wb+2) + w (dy's two junk
+// columns are out of bounds -> zeros), and feed all filter taps of the CTA from the same patch by row-shifting the
+// descriptor, accumulating in TMEM over all tiles of the CTA:
+//     D[(tap slot, c)][k] += sum_m  X[m + shift(tap)][c] * dY[m][k]          (A = patch window, B = dy, both MN-major)
+//   C = K = 64 : one CTA owns all 9 taps; two taps are stacked in the M = 128 rows of one MMA (the second 64-row group is
+//                simply the same patch a few rows further down: LBO = tap-to-tap row distance) -> 5 accumulators x 64 cols
+//   C = K = 128: M = 128 = the two 64-channel chunks of one tap (LBO = patch stride), a CTA owns one filter row (3 taps)
+//                -> 3 accumulators x 128 cols, grid.y = 3
+// Each CTA finally writes its partial dW to a workspace; a second kernel sums the partials in a fixed order into dW.
+// ------------------------------------------------------------------------------------------------------------------
+struct alignas(64) WHaloMaps {
+  CUtensorMap x;   // {C, W, H, N}, box {64, Wb+2, Hb+2, 1}
+  CUtensorMap dy;  // {K, W, H, N}, box {64, Wb+2, Hb, 1}
+};
+
+struct WHaloParams {
+  int tiles_h, Hb, Wb, m_tiles;
+  int rows_m;       // Hb * (Wb + 2)
+  float* ws;        // [gridDim.x][K][9][C] partials
+};
+
+template <int CH>  // channel count / 64 (C == K): 1 or 2
+struct WHaloCfg {
+  static constexpr int kC = CH * 64;
+  static constexpr int kAcc = CH == 1 ? 5 : 3;                 // accumulators per CTA
+  static constexpr int kStage = CH * kPatchBytes + CH * kBoxBytes;
+  static constexpr int kStages = CH == 1 ? 4 : 2;
+  static constexpr int kOffBars = kStages * kStage;
+  static constexpr int kBytes = kOffBars + 1024 + 1024;
+  static constexpr int kTmemCols = 512;
+  static_assert(kAcc * kC <= 512, "TMEM");
+};
+
+template <int CH>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_halo_kernel(const __grid_constant__ WHaloMaps maps, const WHaloParams p) {
+  using L = WHaloCfg<CH>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bars = smem_base + L::kOffBars;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (L::kStages + s); };
+  const uint32_t done_bar = bars + 8u * (2 * L::kStages);
+  const uint32_t tmem_slot = bars + 8u * (2 * L::kStages + 1);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kOffBars + 8 * (2 * L::kStages + 1));
+
+  const int wp2 = p.Wb + 2;
+  const int n_my = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int trow = (int)blockIdx.y;  // CH == 2: the filter row owned by this CTA
+
+  {  // rows that TMA never writes (patch rows past the halo box, dy rows >= rows_m) feed the MMA: zero everything once
+    uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* base = reinterpret_cast<uint4*>(smem_gen);
+    for (int i = threadIdx.x; i < L::kOffBars / 16; i += blockDim.x) base[i] = z;
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.x);
+    tma_prefetch_desc(&maps.dy);
+    for (int s = 0; s < L::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<L::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t tx = (uint32_t)CH * (uint32_t)((p.Hb + 2) * wp2 + p.rows_m) * 128u;
+      for (int it = 0; it < n_my; ++it) {
+        const int m_tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const int n = m_tile / p.tiles_h, hb = m_tile - n * p.tiles_h;
+        const int s = it % L::kStages;
+        mbar_wait(empty_bar(s), (((uint32_t)(it / L::kStages)) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(full_bar(s), tx);
+        const uint32_t dst = smem_base + s * L::kStage;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          tma_load_4d(&maps.x, full_bar(s), dst + c * kPatchBytes, c * 64, -1, hb * p.Hb - 1, n);
+          tma_load_4d(&maps.dy, full_bar(s), dst + CH * kPatchBytes + c * kBoxBytes, c * 64, 0, hb * p.Hb, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, L::kC, 1, 1);
+      constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      // per accumulator: row shift of its (first) tap and the LBO between the two 64-row groups of the A operand
+      uint32_t a_off[L::kAcc], a_lbo[L::kAcc];
+#pragma unroll
+      for (int a = 0; a < L::kAcc; ++a) {
+        if (CH == 1) {
+          const int t0 = 2 * a, t1 = (2 * a + 1 < 9) ? 2 * a + 1 : 2 * a;  // the 10th slot duplicates tap 8 (ignored)
+          const int sh0 = (t0 / 3) * wp2 + (t0 % 3), sh1 = (t1 / 3) * wp2 + (t1 % 3);
+          a_off[a] = (uint32_t)(sh0 * 8);
+          a_lbo[a] = (uint32_t)(((sh1 - sh0) * 128) >> 4) << 16;
+        } else {
+          a_off[a] = (uint32_t)((trow * wp2 + a) * 8);
+          a_lbo[a] = ((uint32_t)kPatchBytes >> 4) << 16;
+        }
+      }
+      constexpr uint32_t kLoB = ((uint32_t)kBoxBytes >> 4) << 16;
+      const int ksteps = (p.rows_m + 15) >> 4;
+      for (int it = 0; it < n_my; ++it) {
+        const int s = it % L::kStages;
+        mbar_wait(full_bar(s), ((uint32_t)(it / L::kStages)) & 1u);
+        tc_fence_after();
+        const uint32_t x_lo = ((smem_base + (uint32_t)s * L::kStage) & 0x3FFFFu) >> 4;
+        const uint32_t b_lo0 = (((smem_base + (uint32_t)s * L::kStage + CH * kPatchBytes) & 0x3FFFFu) >> 4) | kLoB;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          if (ks < ksteps) {
+            const uint64_t db = ((uint64_t)kHi << 32) | (uint64_t)(b_lo0 + 128u * ks);  // 16 pixel rows = 2 KB per step
+#pragma unroll
+            for (int a = 0; a < L::kAcc; ++a) {
+              const uint64_t da = ((uint64_t)kHi << 32) | (uint64_t)((x_lo + a_off[a] + 128u * ks) | a_lbo[a]);
+              umma_bf16(tmem_base + (uint32_t)(a * L::kC), da, db, idesc, (it | ks) != 0 ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    // epilogue: accumulator row = (tap slot, c), column = k  ->  ws[cta][k][tap][c]
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    float* wsb = p.ws + (size_t)blockIdx.x * (size_t)(L::kC * 9 * L::kC);
+    if (n_my > 0) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int a = 0; a < L::kAcc; ++a) {
+      int tap, c;
+      if (CH == 1) {
+        tap = 2 * a + (row >> 6);
+        c = row & 63;
+      } else {
+        tap = trow * 3 + a;
+        c = row;
+      }
+      const bool live = tap < 9;
+#pragma unroll 1
+      for (int k0 = 0; k0 < L::kC; k0 += 32) {
+        uint32_t r[32];
+        if (n_my > 0) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * L::kC + k0), r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) wsb[((size_t)(k0 + j) * 9 + tap) * L::kC + c] = __uint_as_float(r[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<L::kTmemCols>(tmem_base);
+}
+
+// dw[i] += sum over partials (fixed order => deterministic).  For CH == 2 each grid.y slice wrote only its own filter row.
+__global__ void __launch_bounds__(64) wgrad_partial_reduce_kernel(const float* __restrict__ ws, int parts, long long n, float* __restrict__ dw) {
+  const long long n4 = n >> 2;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 acc = reinterpret_cast<float4*>(dw)[i];
+  const float4* src = reinterpret_cast<const float4*>(ws) + i;
+  int pidx = 0;
+  for (; pidx + 8 <= parts; pidx += 8) {  // 8 independent 16-byte loads in flight per thread
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (size_t)(pidx + u) * n4);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc.x += v[u].x, acc.y += v[u].y, acc.z += v[u].z, acc.w += v[u].w;
+  }
+  for (; pidx < parts; ++pidx) {
+    const float4 v = __ldg(src + (size_t)pidx * n4);
+    acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+  }
+  reinterpret_cast<float4*>(dw)[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // host side: tiling, tensor maps, tap tables
 // ------------------------------------------------------------------------------------------------------------------
 struct TileGeom {
@@ -825,7 +1023,10 @@ int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, in
   int rc;
   for (int i = 0; i < n_views; ++i)
     if ((rc = encode_view(ctx, &maps.in[i], in_views[i], tg.Wb, tg.Hb, tg.Nb))) return rc;
-  const int block_n = cout >= 256 ? 256 : cout;
+  // 128x256 tiles have the best operand reuse, but a grid far below one wave (ResNet18 layer4: 32 pixel tiles) runs faster
+  // with 128x128 tiles on twice as many SMs
+  int block_n = cout >= 256 ? 256 : cout;
+  if (block_n == 256 && tg.tiles_h * tg.tiles_n * (cout / 256) * 2 <= ctx->sm_count) block_n = 128;
   if (!b_mn) {
     if ((rc = encode_weights(ctx, &maps.w, w, (long long)n_wtaps * cin, cout, block_n))) return rc;
   } else {
@@ -967,6 +1168,25 @@ int run_halo(mml_ctx* ctx, const View& in, const void* w, int n_wtaps, int cin, 
   return b_mn ? launch_halo_t<2, 128, 2, false, true>(ctx, maps, p, st) : launch_halo_t<2, 128, 2, false, false>(ctx, maps, p, st);
 }
 
+template <int CH>
+int launch_wgrad_halo_t(mml_ctx* ctx, const WHaloMaps& maps, WHaloParams& p, int ctas, float* dw, cudaStream_t st) {
+  using L = WHaloCfg<CH>;
+  static bool configured = false;
+  if (!configured) {
+    int rc = set_smem_limit(ctx, conv_wgrad_halo_kernel<CH>, L::kBytes);
+    if (rc) return rc;
+    configured = true;
+  }
+  const long long n = (long long)L::kC * 9 * L::kC;
+  dim3 grid(ctas, CH == 1 ? 1 : 3);
+  conv_wgrad_halo_kernel<CH><<<grid, 192, L::kBytes, st>>>(maps, p);
+  MML_LAUNCHED(ctx);
+  int rgrid = (int)mml_ceil_div(n / 4, 64);
+  wgrad_partial_reduce_kernel<<<rgrid, 64, 0, st>>>(p.ws, ctas, n, dw);
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
 template <int BLOCK_C, int STAGES>
 int launch_wgrad_t(mml_ctx* ctx, const WgradMaps& maps, const WgradParams& p, dim3 grid, cudaStream_t st) {
   using L = WgradSmem<BLOCK_C, STAGES>;
@@ -1080,6 +1300,27 @@ int mml_conv_wgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, cons
   int n_views = 0;
   const int n_taps = build_fprop_taps(g, P, Q, x, views, &n_views, taps);
   MML_REQUIRE(ctx, n_taps >= 1, "conv wgrad: no filter tap reaches the input");
+  HaloGeom hg;
+  if (g_halo_enable && g->R == 3 && g->stride == 1 && g->pad == 1 && n_taps == 9 && halo_geometry(Q, P, g->N, g->C, g->K, &hg) && ctx->workspace) {
+    const int CH = g->C / 64;
+    int ctas = CH == 1 ? ctx->sm_count : ctx->sm_count / 3;
+    if (ctas > hg.m_tiles) ctas = hg.m_tiles;
+    const size_t need = (size_t)ctas * g->K * 9 * g->C * sizeof(float);
+    if (need <= ctx->workspace_bytes) {
+      WHaloMaps hm;
+      memset(&hm, 0, sizeof(hm));
+      if ((rc = encode_view(ctx, &hm.x, views[0], hg.Wb + 2, hg.Hb + 2, 1))) return rc;
+      View dyh = make_phase_view(dy, g->N, P, Q, g->K, 1, 0, 0);
+      if ((rc = encode_view(ctx, &hm.dy, dyh, hg.Wb + 2, hg.Hb, 1))) return rc;
+      WHaloParams hp;
+      hp.tiles_h = hg.tiles_h, hp.Hb = hg.Hb, hp.Wb = hg.Wb, hp.m_tiles = hg.m_tiles;
+      hp.rows_m = hg.Hb * (hg.Wb + 2);
+      hp.ws = (float*)ctx->workspace;
+      // CH == 2: the three filter-row CTAs of a column write disjoint taps of the same partial slot
+      return CH == 1 ? launch_wgrad_halo_t<1>(ctx, hm, hp, ctas, dw_krsc, (cudaStream_t)stream)
+                     : launch_wgrad_halo_t<2>(ctx, hm, hp, ctas, dw_krsc, (cudaStream_t)stream);
+    }
+  }
   TileGeom tg;
   MML_REQUIRE(ctx, choose_tile(Q, P, g->N, &tg), "conv wgrad: output width %d not supported", Q);
   WgradMaps maps;

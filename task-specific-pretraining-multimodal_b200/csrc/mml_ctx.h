@@ -18,6 +18,10 @@ struct mml_ctx {
   int sm_count;
   int64_t launches;
   mml_tmap_encode_tiled_fn encode_tiled;
+  // scratch for kernels that reduce per-CTA partials (halo wgrad); allocated once at creation so that nothing allocates
+  // inside a CUDA-graph capture.  One user at a time in stream order (the audio encoder's backward).
+  void* workspace;
+  size_t workspace_bytes;
   char err[512];
 };
 
