@@ -263,15 +263,17 @@ bn_bwd_apply_kernel(const uint16_t* __restrict__ dy1, const uint16_t* __restrict
     }
   }
   __syncthreads();
+  // Traverse from the END of the tensors: pass 1 (bn_bwd_reduce) just streamed the same operands front to back, so
+  // their tails are what is still resident in the 126 MB L2.
   const long long stride = (long long)gridDim.x * kThreads;
-  long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
-  const int cg = (int)(i % c8);
+  long long i = n8 - 1 - (blockIdx.x * (long long)kThreads + threadIdx.x);
+  const int cg = (int)(((i % c8) + c8) % c8);
   const F8 mu = load8f(mean + cg * 8), is = load8f(invstd + cg * 8);
   F8 k0 = load8f(gamma + cg * 8);
   const F8 k1 = load8f(s_k + cg * 8), k2 = load8f(s_k + kMaxC + cg * 8);
 #pragma unroll
   for (int j = 0; j < 8; ++j) k0.v[j] *= is.v[j];  // gamma * invstd
-  for (; i < n8; i += stride) {
+  for (; i >= 0; i -= stride) {
     F8 g = unpack8(ldg16(dy1 + i * 8));
     if (TWO) {
       const F8 g2 = unpack8(ldg16(dy2 + i * 8));
@@ -344,47 +346,74 @@ maxpool_fwd_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, uin
   }
 }
 
+// One thread = the 2x2 input block (2a..2a+1, 2b..2b+1) x 8 channels.  Those four positions only belong to the windows
+// p in {a, a+1}, q in {b, b+1}, which are loaded once (dy [+ dy2] and the argmax bytes) and scattered to the four outputs.
 __global__ void __launch_bounds__(kThreads)
 maxpool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__ dy2, const uint8_t* __restrict__ amax,
                    uint16_t* __restrict__ dx, int N, int H, int W, int C, int P, int Q) {
   const int c8 = C >> 3;
-  const long long total = (long long)N * H * W * c8;
+  const int HB = (H + 1) >> 1, WB = (W + 1) >> 1;
+  const long long total = (long long)N * HB * WB * c8;
   for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
     const int cg = (int)(i % c8);
     long long t = i / c8;
-    const int w = (int)(t % W);
-    t /= W;
-    const int h = (int)(t % H);
-    const int n = (int)(t / H);
-    F8 acc;
+    const int b = (int)(t % WB);
+    t /= WB;
+    const int a = (int)(t % HB);
+    const int n = (int)(t / HB);
+    F8 acc[2][2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
-    // windows p with 2p-1 <= h <= 2p+1
-    const int p_lo = max(0, (h) / 2), p_hi = min(P - 1, (h + 1) / 2);
-    const int q_lo = max(0, (w) / 2), q_hi = min(Q - 1, (w + 1) / 2);
-    for (int p = p_lo; p <= p_hi; ++p) {
-      const int r = h - (2 * p - 1);
-      if (r < 0 || r > 2) continue;
-      for (int q = q_lo; q <= q_hi; ++q) {
-        const int s = w - (2 * q - 1);
-        if (s < 0 || s > 2) continue;
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int v = 0; v < 2; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[u][v].v[j] = 0.f;
+#pragma unroll
+    for (int dp = 0; dp < 2; ++dp) {
+      const int p = a + dp;
+      if (p >= P) continue;
+#pragma unroll
+      for (int dq = 0; dq < 2; ++dq) {
+        const int q = b + dq;
+        if (q >= Q) continue;
         const long long o = ((((long long)n * P + p) * Q + q) * c8 + cg) * 8;
-        const uint2 a = __ldg(reinterpret_cast<const uint2*>(amax + o));
+        const uint2 am = __ldg(reinterpret_cast<const uint2*>(amax + o));
         F8 g = unpack8(ldg16(dy + o));
         if (dy2 != nullptr) {  // gradient arriving over two paths (conv branch + identity skip)
           const F8 g2 = unpack8(ldg16(dy2 + o));
 #pragma unroll
           for (int j = 0; j < 8; ++j) g.v[j] += g2.v[j];
         }
-        const uint32_t want = (uint32_t)(r * 3 + s);
+        // window (p, q) covers rows 2p-1..2p+1: block row u (h = 2a+u) is window row r = 2a+u-(2p-1) = u + 1 - 2*dp
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t got = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xFFu;
-          if (got == want) acc.v[j] += g.v[j];
+        for (int u = 0; u < 2; ++u) {
+          const int r = u + 1 - 2 * dp;
+          if (r < 0 || r > 2) continue;
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const int s2 = v + 1 - 2 * dq;
+            if (s2 < 0 || s2 > 2) continue;
+            const uint32_t want = (uint32_t)(r * 3 + s2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t got = ((j < 4 ? am.x : am.y) >> (8 * (j & 3))) & 0xFFu;
+              if (got == want) acc[u][v].v[j] += g.v[j];
+            }
+          }
         }
       }
     }
-    *reinterpret_cast<uint4*>(dx + i * 8) = pack8(acc);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int h = 2 * a + u;
+      if (h >= H) continue;
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int w = 2 * b + v;
+        if (w >= W) continue;
+        *reinterpret_cast<uint4*>(dx + ((((long long)n * H + h) * W + w) * c8 + cg) * 8) = pack8(acc[u][v]);
+      }
+    }
   }
 }
 
@@ -580,7 +609,8 @@ int mml_maxpool3x3s2_bwd(mml_ctx* ctx, const uint16_t* dy, const uint16_t* dy2, 
                          int W, int C, void* stream) {
   MML_REQUIRE(ctx, ctx && dy && dx && argmax && N >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "maxpool_bwd: bad arguments");
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
-  maxpool_bwd_kernel<<<ew_grid(ctx, (long long)N * H * W * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(dy, dy2, argmax, dx, N, H, W, C, P, Q);
+  maxpool_bwd_kernel<<<ew_grid(ctx, (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(dy, dy2, argmax, dx, N, H, W,
+                                                                                                                                   C, P, Q);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }

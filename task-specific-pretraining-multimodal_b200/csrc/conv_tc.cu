@@ -892,25 +892,39 @@ conv_wgrad_halo_kernel(const __grid_constant__ WHaloMaps maps, const WHaloParams
 }
 
 // dw[i] += sum over partials (fixed order => deterministic).  For CH == 2 each grid.y slice wrote only its own filter row.
-__global__ void __launch_bounds__(64) wgrad_partial_reduce_kernel(const float* __restrict__ ws, int parts, long long n, float* __restrict__ dw) {
+// block = 32 elements (float4) x 8 partial slices; slices are combined through shared memory in a fixed order
+__global__ void __launch_bounds__(256) wgrad_partial_reduce_kernel(const float* __restrict__ ws, int parts, long long n, float* __restrict__ dw) {
+  __shared__ float4 sh[8][33];
   const long long n4 = n >> 2;
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  float4 acc = reinterpret_cast<float4*>(dw)[i];
-  const float4* src = reinterpret_cast<const float4*>(ws) + i;
-  int pidx = 0;
-  for (; pidx + 8 <= parts; pidx += 8) {  // 8 independent 16-byte loads in flight per thread
-    float4 v[8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long i = blockIdx.x * 32ll + tx;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n4) {
+    const float4* src = reinterpret_cast<const float4*>(ws) + i;
+    int pidx = ty;
+    for (; pidx + 24 < parts; pidx += 32) {  // 4 independent 16-byte loads in flight per thread
+      float4 v[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (size_t)(pidx + u) * n4);
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(src + (size_t)(pidx + 8 * u) * n4);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc.x += v[u].x, acc.y += v[u].y, acc.z += v[u].z, acc.w += v[u].w;
+      for (int u = 0; u < 4; ++u) acc.x += v[u].x, acc.y += v[u].y, acc.z += v[u].z, acc.w += v[u].w;
+    }
+    for (; pidx < parts; pidx += 8) {
+      const float4 v = __ldg(src + (size_t)pidx * n4);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
   }
-  for (; pidx < parts; ++pidx) {
-    const float4 v = __ldg(src + (size_t)pidx * n4);
-    acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+  sh[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && i < n4) {
+    float4 tot = reinterpret_cast<float4*>(dw)[i];
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+      const float4 v = sh[y][tx];
+      tot.x += v.x, tot.y += v.y, tot.z += v.z, tot.w += v.w;
+    }
+    reinterpret_cast<float4*>(dw)[i] = tot;
   }
-  reinterpret_cast<float4*>(dw)[i] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1181,8 +1195,8 @@ int launch_wgrad_halo_t(mml_ctx* ctx, const WHaloMaps& maps, WHaloParams& p, int
   dim3 grid(ctas, CH == 1 ? 1 : 3);
   conv_wgrad_halo_kernel<CH><<<grid, 192, L::kBytes, st>>>(maps, p);
   MML_LAUNCHED(ctx);
-  int rgrid = (int)mml_ceil_div(n / 4, 64);
-  wgrad_partial_reduce_kernel<<<rgrid, 64, 0, st>>>(p.ws, ctas, n, dw);
+  int rgrid = (int)mml_ceil_div(n / 4, 32);
+  wgrad_partial_reduce_kernel<<<rgrid, 256, 0, st>>>(p.ws, ctas, n, dw);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }
