@@ -34,6 +34,9 @@ TRAIN_GFLOP_PER_SAMPLE = 3.1889  # dense nominal fwd+dgrad+wgrad, SURVEY.md sect
 CPU_SAMPLE_BATCH = 32            # BASELINE.json configs[0]: the reference's own CPU-runnable case
 
 
+_emit = print
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -134,7 +137,7 @@ def run_reference_arm(args):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(json.dumps(line))
 
 
 def workload_config(args, world):
@@ -182,6 +185,11 @@ def dominant_kernel_roofline(torch, ops, B, pk):
             "flops_per_launch": flops, "us_per_launch": t * 1e6}
 
 
+def _dbg(rank, msg):
+    if os.environ.get("MML_BENCH_DEBUG"):
+        print(f"[bench r{rank} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -195,6 +203,7 @@ def run_b200_arm(args):
     import late_fusion_oracle as O  # synthetic input generator + cpu_baseline leg only
 
     rank, local_rank, world = mdist.init_from_env("nccl")
+    _dbg(rank, f"process group ready, world {world}")
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local_rank)
@@ -224,8 +233,9 @@ def run_b200_arm(args):
         torch.cuda.synchronize(dev)
 
     # ---- warm-up through the public API (also builds the plan and captures the CUDA graph) --------------------------
-    for _ in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3)):
         model.train_step(host, opt, loss_fns, dev, None)
+        _dbg(rank, f"warm-up step {i} done")
     plan = next(iter(eng.plans.values()))
     launches_per_step = plan.launches_per_step
 
@@ -238,7 +248,9 @@ def run_b200_arm(args):
     for _ in range(args.steps):
         plan.train_step(given_dropout=False)
     e1.record()
+    _dbg(rank, "device-resident loop enqueued")
     barrier()
+    _dbg(rank, "device-resident loop done")
     clocks = sampler.stop()
     dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
     if world > 1:
@@ -258,6 +270,7 @@ def run_b200_arm(args):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     t_e2e = float(dt.item())
     d2h = 4 + 4 * B
+    _dbg(rank, "e2e loop done")
 
     if rank != 0:
         return
@@ -280,7 +293,7 @@ def run_b200_arm(args):
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "last_loss": out["loss"],
     }
-    print(json.dumps(line))
+    _emit(json.dumps(line))
 
 
 def main():
@@ -291,6 +304,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU (BASELINE.json configs[1])")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: library chatter (e.g. "NCCL version ...") is diverted to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global _emit
+    _emit = lambda line: (real_stdout.write(line + "\n"), real_stdout.flush())
     if args.impl == "reference":
         run_reference_arm(args)
     else:
@@ -299,7 +317,13 @@ def main():
         import torch.distributed as dist
 
         if dist.is_initialized():
-            dist.destroy_process_group()
+            # ranks != 0 wait here while rank 0 finishes the single-GPU roofline probe and the CPU baseline.  The process
+            # group is NOT destroyed: tearing down an NCCL communicator whose kernels live in captured CUDA graphs can
+            # block; all ranks leave together through os._exit instead.
+            dist.barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
     except Exception:
         pass
 
