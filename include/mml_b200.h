@@ -110,6 +110,15 @@ int mml_maxpool3x3s2_fwd(mml_ctx*, const uint16_t* x, uint16_t* y, uint8_t* argm
 /* dx = scatter of (dy [+ dy2]) to the argmax positions; dy2 may be NULL */
 int mml_maxpool3x3s2_bwd(mml_ctx*, const uint16_t* dy, const uint16_t* dy2, const uint8_t* argmax, uint16_t* dx, int N, int H,
                          int W, int C, void* stream);
+/* stem tail, fused: y = maxpool3x3s2(relu(bn(x))) without materialising the activation (resnet.py:138-140, :206-208).
+ * train: stats != NULL (fp64 sums from mml_stem_fprop; saves mean/invstd, updates running stats); eval: scale/shift != NULL */
+int mml_stem_bn_pool_fwd(mml_ctx*, const uint16_t* x, const double* stats, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, float* save_mean, float* save_invstd, const float* scale, const float* shift, uint16_t* y,
+                         uint8_t* argmax, int N, int H, int W, int C, float momentum, float eps, void* stream);
+/* its backward: dx (grad of the raw stem output) from the pooled gradient(s); ReLU mask recomputed from x; two passes */
+int mml_stem_bn_pool_bwd(mml_ctx*, const uint16_t* dy, const uint16_t* dy2, const uint8_t* argmax, const uint16_t* x, const float* mean,
+                         const float* invstd, const float* gamma, const float* beta, double* bstat, float* dgamma, float* dbeta, uint16_t* dx,
+                         int N, int H, int W, int C, void* stream);
 int mml_avgpool_fwd(mml_ctx*, const uint16_t* x, float* y, int N, int HW, int C, void* stream);
 int mml_avgpool_bwd(mml_ctx*, const float* dy, uint16_t* dx, int N, int HW, int C, void* stream);
 

@@ -56,6 +56,8 @@ SIGNATURES = {
     "mml_bn_bwd_apply": (I32, [P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I32, I32, P]),
     "mml_maxpool3x3s2_fwd": (I32, [P, P, P, P, I32, I32, I32, I32, P]),
     "mml_maxpool3x3s2_bwd": (I32, [P, P, P, P, P, I32, I32, I32, I32, P]),
+    "mml_stem_bn_pool_fwd": (I32, [P] * 13 + [I32, I32, I32, I32, F32, F32, P]),
+    "mml_stem_bn_pool_bwd": (I32, [P] * 13 + [I32, I32, I32, I32, P]),
     "mml_avgpool_fwd": (I32, [P, P, P, I32, I32, I32, P]),
     "mml_avgpool_bwd": (I32, [P, P, P, I32, I32, I32, P]),
     "mml_head_scratch_per_sample": (I32, [C.POINTER(HeadParams)]),

@@ -417,6 +417,214 @@ maxpool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Stem tail, fused: BatchNorm (train or eval) + ReLU + MaxPool2d(3,2,1) in one pass over the raw stem output, and its
+// backward.  The post-ReLU activation (the largest tensor of the network: 103 MB at batch 256) is never materialised:
+// backward recomputes the ReLU mask from raw*scale+shift and scatters the pooled gradient through the saved argmax.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool TRAIN>
+__global__ void __launch_bounds__(kThreads)
+stem_bn_pool_fwd_kernel(const uint16_t* __restrict__ x, BnTrain bn, const float* __restrict__ scale_in, const float* __restrict__ shift_in,
+                        uint16_t* __restrict__ y, uint8_t* __restrict__ amax, int N, int H, int W, int C, int P, int Q, double inv_count,
+                        double unbias, float momentum, float eps) {
+  __shared__ __align__(16) float s_coef[2 * kMaxC];
+  if (TRAIN) {
+    bn_prologue(bn, C, inv_count, unbias, momentum, eps, s_coef, s_coef + kMaxC);
+  } else {
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      s_coef[c] = scale_in[c];
+      s_coef[kMaxC + c] = shift_in[c];
+    }
+  }
+  __syncthreads();
+  const int c8 = C >> 3;
+  const long long total = (long long)N * P * Q * c8;
+  const long long stride = (long long)gridDim.x * kThreads;
+  long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
+  const int cg = (int)(i % c8);
+  const F8 sc = load8f(s_coef + cg * 8), sh = load8f(s_coef + kMaxC + cg * 8);
+  for (; i < total; i += stride) {
+    long long t = i / c8;
+    const int q = (int)(t % Q);
+    t /= Q;
+    const int p = (int)(t % P);
+    const int n = (int)(t / P);
+    float best[8];
+    int idx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = -INFINITY;
+      idx[j] = -1;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * p - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int w = 2 * q - 1 + s2;
+        if (w < 0 || w >= W) continue;
+        const F8 v = unpack8(ldg16(x + (((long long)n * H + h) * W + w) * C + cg * 8));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // the stored activation would have been bf16(relu(bn(x))): round the same way so that ties resolve identically
+          const float a = bf16_lo(pack_bf16x2(fmaxf(fmaf(v.v[j], sc.v[j], sh.v[j]), 0.f), 0.f));
+          if (idx[j] < 0 || a > best[j] || a != a) {  // torch: (val > maxval) || isnan(val)
+            best[j] = a;
+            idx[j] = r * 3 + s2;
+          }
+        }
+      }
+    }
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = best[j];
+    *reinterpret_cast<uint4*>(y + i * 8) = pack8(o);
+    uint2 a;
+    a.x = (uint32_t)idx[0] | ((uint32_t)idx[1] << 8) | ((uint32_t)idx[2] << 16) | ((uint32_t)idx[3] << 24);
+    a.y = (uint32_t)idx[4] | ((uint32_t)idx[5] << 8) | ((uint32_t)idx[6] << 16) | ((uint32_t)idx[7] << 24);
+    *reinterpret_cast<uint2*>(amax + i * 8) = a;
+  }
+}
+
+// gradient of the pooled output scattered to the 2x2 input block (2a.., 2b..) of one thread (see maxpool_bwd_kernel)
+__device__ __forceinline__ void pool_scatter_2x2(const uint16_t* __restrict__ dy, const uint16_t* __restrict__ dy2,
+                                                 const uint8_t* __restrict__ amax, int n, int a, int b, int cg, int c8, int P, int Q, F8 (&acc)[2][2]) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[u][v].v[j] = 0.f;
+#pragma unroll
+  for (int dp = 0; dp < 2; ++dp) {
+    const int p = a + dp;
+    if (p >= P) continue;
+#pragma unroll
+    for (int dq = 0; dq < 2; ++dq) {
+      const int q = b + dq;
+      if (q >= Q) continue;
+      const long long o = ((((long long)n * P + p) * Q + q) * c8 + cg) * 8;
+      const uint2 am = __ldg(reinterpret_cast<const uint2*>(amax + o));
+      F8 g = unpack8(ldg16(dy + o));
+      if (dy2 != nullptr) {
+        const F8 g2 = unpack8(ldg16(dy2 + o));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.v[j] += g2.v[j];
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int r = u + 1 - 2 * dp;
+        if (r < 0 || r > 2) continue;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int s2 = v + 1 - 2 * dq;
+          if (s2 < 0 || s2 > 2) continue;
+          const uint32_t want = (uint32_t)(r * 3 + s2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t got = ((j < 4 ? am.x : am.y) >> (8 * (j & 3))) & 0xFFu;
+            if (got == want) acc[u][v].v[j] += g.v[j];
+          }
+        }
+      }
+    }
+  }
+}
+
+// PASS 0: bstat += (sum g, sum g*xhat) and dx = g (the generic bn_bwd_apply kernel then finishes in place);
+// PASS 1 (kept for reference / tests): recompute g and write dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))
+// g = scatter(dpool) * (bn(x) > 0);  bn(x) = gamma*(x-mean)*invstd + beta
+template <int PASS>
+__global__ void __launch_bounds__(kThreads)
+stem_bn_pool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__ dy2, const uint8_t* __restrict__ amax,
+                        const uint16_t* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, double* __restrict__ bstat, float inv_count,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta, uint16_t* __restrict__ dx, int N, int H, int W, int C, int P, int Q) {
+  __shared__ float sh[PASS == 0 ? kThreads : 1][17];
+  __shared__ __align__(16) float s_k[PASS == 1 ? 2 * kMaxC : 4];
+  const int c8 = C >> 3;
+  if (PASS == 1) {
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      double sg, sgx;
+      stat_load(bstat, C, c, sg, sgx);
+      s_k[c] = (float)sg * inv_count;
+      s_k[kMaxC + c] = (float)sgx * inv_count;
+      if (blockIdx.x == 0) {
+        if (dbeta) dbeta[c] = (float)sg;
+        if (dgamma) dgamma[c] = (float)sgx;
+      }
+    }
+    __syncthreads();
+  }
+  const int HB = (H + 1) >> 1, WB = (W + 1) >> 1;
+  const long long total = (long long)N * HB * WB * c8;
+  const long long stride = (long long)gridDim.x * kThreads;
+  long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
+  const int cg = (int)(i % c8);
+  const F8 mu = load8f(mean + cg * 8), is = load8f(invstd + cg * 8), ga = load8f(gamma + cg * 8), be = load8f(beta + cg * 8);
+  F8 k1, k2;
+  if (PASS == 1) {
+    k1 = load8f(s_k + cg * 8);
+    k2 = load8f(s_k + kMaxC + cg * 8);
+  }
+  float sg[8], sgx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sg[j] = sgx[j] = 0.f;
+  for (; i < total; i += stride) {
+    long long t = i / c8;
+    const int b = (int)(t % WB);
+    t /= WB;
+    const int a = (int)(t % HB);
+    const int n = (int)(t / HB);
+    F8 acc[2][2];
+    pool_scatter_2x2(dy, dy2, amax, n, a, b, cg, c8, P, Q, acc);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int h = 2 * a + u;
+      if (h >= H) continue;
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int w = 2 * b + v;
+        if (w >= W) continue;
+        const long long o = ((((long long)n * H + h) * W + w) * c8 + cg) * 8;
+        const F8 xv = unpack8(ldg16(x + o));
+        F8 out;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv.v[j] - mu.v[j]) * is.v[j];
+          const float g = fmaf(ga.v[j], xh, be.v[j]) > 0.f ? acc[u][v].v[j] : 0.f;  // ReLU mask recomputed
+          if (PASS == 0) {
+            sg[j] += g;
+            sgx[j] = fmaf(g, xh, sgx[j]);
+            out.v[j] = g;  // materialised once: the apply pass is then a plain elementwise kernel (no second scatter)
+          } else {
+            out.v[j] = ga.v[j] * is.v[j] * (g - k1.v[j] - xh * k2.v[j]);
+          }
+        }
+        *reinterpret_cast<uint4*>(dx + o) = pack8(out);
+      }
+    }
+  }
+  if (PASS == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sh[threadIdx.x][j] = sg[j];
+      sh[threadIdx.x][8 + j] = sgx[j];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < C; o += kThreads) {
+      const int g = o >> 3, j = o & 7;
+      float aa = 0.f, bb = 0.f;
+      for (int t = g; t < kThreads; t += c8) {
+        aa += sh[t][j];
+        bb += sh[t][8 + j];
+      }
+      stat_add(bstat, C, blockIdx.x, o, aa, bb);
+    }
+  }
+}
+
 // AdaptiveAvgPool2d((1,1)) + flatten: [N, HW, C] bf16 -> [N, C] fp32
 __global__ void avgpool_fwd_kernel(const uint16_t* __restrict__ x, float* __restrict__ y, int N, int HW, int C) {
   const int c8 = C >> 3;
@@ -611,6 +819,55 @@ int mml_maxpool3x3s2_bwd(mml_ctx* ctx, const uint16_t* dy, const uint16_t* dy2, 
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
   maxpool_bwd_kernel<<<ew_grid(ctx, (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(dy, dy2, argmax, dx, N, H, W,
                                                                                                                                    C, P, Q);
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
+int mml_stem_bn_pool_fwd(mml_ctx* ctx, const uint16_t* x, const double* stats, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, float* save_mean, float* save_invstd, const float* scale, const float* shift, uint16_t* y,
+                         uint8_t* argmax, int N, int H, int W, int C, float momentum, float eps, void* stream) {
+  MML_REQUIRE(ctx, ctx && x && y && argmax && N >= 1 && H >= 1 && W >= 1, "stem_bn_pool_fwd: bad arguments");
+  MML_REQUIRE(ctx, (stats != nullptr) != (scale != nullptr), "stem_bn_pool_fwd: give either batch statistics (train) or scale/shift (eval)");
+  int rc = check_rows_c(ctx, (int64_t)N * H * W, C);
+  if (rc) return rc;
+  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+  const int64_t rows = (int64_t)N * H * W;
+  const int grid = ew_grid(ctx, (long long)N * P * Q * (C / 8));
+  BnTrain bn{stats, gamma, beta, running_mean, running_var, save_mean, save_invstd};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (stats) {
+    MML_REQUIRE(ctx, gamma && beta && save_mean && save_invstd, "stem_bn_pool_fwd: null BN pointer");
+    stem_bn_pool_fwd_kernel<true><<<grid, kThreads, 0, st>>>(x, bn, nullptr, nullptr, y, argmax, N, H, W, C, P, Q, 1.0 / (double)rows,
+                                                              rows > 1 ? (double)rows / (double)(rows - 1) : 1.0, momentum, eps);
+  } else {
+    MML_REQUIRE(ctx, shift != nullptr, "stem_bn_pool_fwd: shift is NULL");
+    stem_bn_pool_fwd_kernel<false><<<grid, kThreads, 0, st>>>(x, bn, scale, shift, y, argmax, N, H, W, C, P, Q, 0.0, 0.0, momentum, eps);
+  }
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
+int mml_stem_bn_pool_bwd(mml_ctx* ctx, const uint16_t* dy, const uint16_t* dy2, const uint8_t* argmax, const uint16_t* x, const float* mean,
+                         const float* invstd, const float* gamma, const float* beta, double* bstat, float* dgamma, float* dbeta, uint16_t* dx,
+                         int N, int H, int W, int C, void* stream) {
+  MML_REQUIRE(ctx, ctx && dy && argmax && x && mean && invstd && gamma && beta && bstat && dx && N >= 1 && H >= 1 && W >= 1,
+              "stem_bn_pool_bwd: bad arguments");
+  int rc = check_rows_c(ctx, (int64_t)N * H * W, C);
+  if (rc) return rc;
+  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+  const long long items = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  const float inv_count = 1.0f / (float)((int64_t)N * H * W);
+  cudaStream_t st = (cudaStream_t)stream;
+  int g0 = (int)mml_ceil_div(items, (long long)kThreads * 2);
+  if (g0 > ctx->sm_count * 4) g0 = ctx->sm_count * 4;
+  if (g0 < 1) g0 = 1;
+  stem_bn_pool_bwd_kernel<0><<<g0, kThreads, 0, st>>>(dy, dy2, argmax, x, mean, invstd, gamma, beta, bstat, inv_count, dgamma, dbeta, dx, N, H, W,
+                                                      C, P, Q);
+  MML_LAUNCHED(ctx);
+  // pass 2 in place over the buffer that now holds g: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))
+  const long long n8 = (long long)N * H * W * (C / 8);
+  bn_bwd_apply_kernel<false, false, false><<<ew_grid(ctx, n8), kThreads, 0, st>>>(dx, nullptr, nullptr, x, mean, invstd, gamma, bstat, inv_count,
+                                                                                  dgamma, dbeta, dx, nullptr, n8, C / 8);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }

@@ -259,19 +259,17 @@ class EncoderPlan:
         P1, Q1 = (P0 - 1) // 2 + 1, (Q0 - 1) // 2 + 1
         w_stem = fs.flat_slice(fs.P, pre + "conv1.weight")
         dw_stem = fs.flat_slice(fs.G, pre + "conv1.weight")
-        raw0, act0 = self._act(B, P0, Q0, 64), self._act(B, P0, Q0, 64)
+        raw0 = self._act(B, P0, Q0, 64)  # the post-ReLU activation is never materialised (fused BN+ReLU+maxpool)
         pool, amax = self._act(B, P1, Q1, 64), torch.zeros(B, P1, Q1, 64, device=dev, dtype=torch.uint8)
-        self.taps.update({"conv1": raw0, "relu1": act0, "maxpool": pool})
+        self.taps.update({"conv1": raw0, "maxpool": pool})
         bn0 = self._bn("bn1", 64)
         rows0 = B * P0 * Q0
         x, mask = self.x, self.mask
         F.append(lambda: ops.stem_fprop(x, mask, w_stem, raw0, bn0.stats))
-        F.append(lambda: ops.bn_train_fwd(raw0, bn0, None, None, act0, rows0, 64, True, BN_MOMENTUM, BN_EPS))
+        F.append(lambda: ops.stem_bn_pool_fwd(raw0, bn0, None, None, pool, amax, B, P0, Q0, 64, True, BN_MOMENTUM, BN_EPS))
         E.append(lambda: ops.stem_fprop(x, mask, w_stem, raw0, None))
         E.append(lambda: ops.bn_eval_coeffs(64, bn0.gamma, bn0.beta, bn0.rmean, bn0.rvar, BN_EPS, bn0.scale, bn0.shift))
-        E.append(lambda: ops.bn_act_fwd(raw0, bn0.scale, bn0.shift, None, None, None, act0, rows0, 64, True))
-        for L in (F, E):
-            L.append(lambda: ops.maxpool_fwd(act0, pool, amax, B, P0, Q0, 64))
+        E.append(lambda: ops.stem_bn_pool_fwd(raw0, bn0, bn0.scale, bn0.shift, pool, amax, B, P0, Q0, 64, False))
         # backward of the stem is emitted last (see end of _build); needs the two gradients of `pool`
         cur, curH, curW, curC = pool, P1, Q1, 64
         grads_of_cur: List[Optional[torch.Tensor]] = [None, None]  # filled by the first block's backward
@@ -385,13 +383,11 @@ class EncoderPlan:
             Bk.append(lambda: ops.avgpool_bwd(dpooled, d_last, B, HW, 512))
             Bk.extend(reversed(bwd_stack))
             # stem backward
-            d_act0, d_raw0 = self._act(B, P0, Q0, 64), self._act(B, P0, Q0, 64)
+            d_raw0 = self._act(B, P0, Q0, 64)
             ws = torch.zeros(max(ops.stem_wgrad_workspace(x) // 4, 4), device=dev)
 
             def bwd_stem():
-                ops.maxpool_bwd(stem_grad_slots[0], stem_grad_slots[1], amax, d_act0, B, P0, Q0, 64)
-                ops.bn_bwd_reduce(d_act0, None, act0, raw0, bn0.mean, bn0.invstd, bn0.bstat, rows0, 64, True)
-                ops.bn_bwd_apply(d_act0, None, act0, raw0, bn0.mean, bn0.invstd, bn0.gamma, bn0.bstat, bn0.dgamma, bn0.dbeta, d_raw0, None, rows0, 64, True)
+                ops.stem_bn_pool_bwd(stem_grad_slots[0], stem_grad_slots[1], amax, raw0, bn0, bn0.bstat, bn0.dgamma, bn0.dbeta, d_raw0, B, P0, Q0, 64)
                 ops.stem_wgrad(x, mask, d_raw0, dw_stem, ws)
 
             Bk.append(bwd_stem)

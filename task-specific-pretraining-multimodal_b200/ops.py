@@ -151,6 +151,25 @@ def maxpool_bwd(dy, dy2, argmax, dx, N, H, W, Cn) -> None:
     ctx.check(ctx.lib.mml_maxpool3x3s2_bwd(ctx.handle, _p(dy, BF16), _p(dy2), _p(argmax, torch.uint8), _p(dx, BF16), N, H, W, Cn, _stream(dy)), "maxpool_bwd")
 
 
+def stem_bn_pool_fwd(x, bn: "BNBuffers", scale, shift, y, argmax, N, H, W, Cn, train: bool, momentum=0.1, eps=1e-5) -> None:
+    """y = maxpool3x3s2(relu(bn(x))); train: batch statistics from bn.stats, eval: precomputed scale / shift."""
+    ctx = _ctx(x)
+    z = C.c_void_p(0)
+    if train:
+        a = (_p(bn.stats, torch.float64), _p(bn.gamma), _p(bn.beta), _p(bn.rmean), _p(bn.rvar), _p(bn.mean), _p(bn.invstd), z, z)
+    else:
+        a = (z, _p(bn.gamma), _p(bn.beta), z, z, z, z, _p(scale), _p(shift))
+    ctx.check(ctx.lib.mml_stem_bn_pool_fwd(ctx.handle, _p(x, BF16), *a, _p(y, BF16), _p(argmax, torch.uint8), N, H, W, Cn, float(momentum), float(eps),
+                                           _stream(x)), "stem_bn_pool_fwd")
+
+
+def stem_bn_pool_bwd(dy, dy2, argmax, x, bn: "BNBuffers", bstat, dgamma, dbeta, dx, N, H, W, Cn) -> None:
+    ctx = _ctx(dy)
+    ctx.check(ctx.lib.mml_stem_bn_pool_bwd(ctx.handle, _p(dy, BF16), _p(dy2), _p(argmax, torch.uint8), _p(x, BF16), _p(bn.mean), _p(bn.invstd),
+                                           _p(bn.gamma), _p(bn.beta), _p(bstat, torch.float64), _p(dgamma), _p(dbeta), _p(dx, BF16), N, H, W, Cn,
+                                           _stream(dy)), "stem_bn_pool_bwd")
+
+
 def avgpool_fwd(x, y, N, HW, Cn) -> None:
     ctx = _ctx(x)
     ctx.check(ctx.lib.mml_avgpool_fwd(ctx.handle, _p(x, BF16), _p(y, torch.float32), N, HW, Cn, _stream(x)), "avgpool_fwd")

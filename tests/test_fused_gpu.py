@@ -159,6 +159,53 @@ def test_maxpool(N, H, W, C):
     assert (dx.float() - refdx)[pos].abs().max().item() <= 2.0 ** -6 * refdx.abs().max().item()
 
 
+@pytest.mark.parametrize("N,H,W", [(3, 56, 56), (2, 14, 14), (2, 16, 47), (1, 5, 7)])
+def test_stem_bn_relu_maxpool_fused(N, H, W):
+    """BN(train) + ReLU + MaxPool(3,2,1) in one pass, and its backward with the ReLU mask recomputed from the raw tensor."""
+    from mml_b200 import ops
+
+    C = 64
+    x = (torch.randn(N, H, W, C, device="cuda", generator=gen(60)) * 1.5 + 0.3).to(BF)
+    gamma = torch.rand(C, device="cuda", generator=gen(61)) + 0.5
+    beta = torch.randn(C, device="cuda", generator=gen(62)) * 0.2
+    xd = x.double().reshape(-1, C)
+    st = torch.zeros(16, C, 2, device="cuda", dtype=torch.float64)
+    st[5] = torch.stack([xd.sum(0), (xd * xd).sum(0)], 1)
+    bn = ops.BNBuffers(st, gamma, beta, torch.zeros(C, device="cuda"), torch.ones(C, device="cuda"), torch.empty(C, device="cuda"), torch.empty(C, device="cuda"))
+    P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty(N, P, Q, C, device="cuda", dtype=BF)
+    am = torch.empty(N, P, Q, C, device="cuda", dtype=torch.uint8)
+    ops.stem_bn_pool_fwd(x, bn, None, None, y, am, N, H, W, C, True)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    act = F.relu(F.batch_norm(xr, rm, rv, gr, br, True, 0.1, 1e-5))
+    act = act + (act.to(BF).float() - act).detach()  # the kernel pools the bf16-rounded activation
+    ref = F.max_pool2d(act, 3, 2, 1)
+    assert (y.float() - ref.detach().permute(0, 2, 3, 1)).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item() + 1e-3
+    assert torch.allclose(bn.rmean, rm, rtol=1e-4, atol=1e-5) and torch.allclose(bn.rvar, rv, rtol=1e-4, atol=1e-5)
+    dy1 = torch.randn(N, P, Q, C, device="cuda", generator=gen(63)).to(BF)
+    dy2 = torch.randn(N, P, Q, C, device="cuda", generator=gen(64)).to(BF)
+    ref.backward((dy1.float() + dy2.float()).permute(0, 3, 1, 2))
+    bstat = torch.zeros(16, C, 2, device="cuda", dtype=torch.float64)
+    dgamma, dbeta = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    dx = torch.empty(N, H, W, C, device="cuda", dtype=BF)
+    ops.stem_bn_pool_bwd(dy1, dy2, am, x, bn, bstat, dgamma, dbeta, dx, N, H, W, C)
+    refdx = xr.grad.permute(0, 2, 3, 1)
+    tol = 3e-2
+    assert (dgamma - gr.grad).abs().max().item() <= tol * gr.grad.abs().max().item() + 1e-2
+    assert (dbeta - br.grad).abs().max().item() <= tol * br.grad.abs().max().item() + 1e-2
+    # a handful of elements may differ where two window candidates round to the same bf16 value (tie order); compare in L2
+    assert float((dx.float() - refdx).norm() / refdx.norm()) <= tol
+    # eval form: coefficients instead of batch statistics
+    scale, shift = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    ops.bn_eval_coeffs(C, gamma, beta, bn.rmean, bn.rvar, 1e-5, scale, shift)
+    y2 = torch.empty_like(y)
+    ops.stem_bn_pool_fwd(x, bn, scale, shift, y2, am, N, H, W, C, False)
+    ref2 = F.max_pool2d(F.relu(F.batch_norm(x.float().permute(0, 3, 1, 2), bn.rmean, bn.rvar, gamma, beta, False, 0.1, 1e-5)), 3, 2, 1)
+    assert (y2.float() - ref2.permute(0, 2, 3, 1)).abs().max().item() <= 2.0 ** -7 * ref2.abs().max().item() + 1e-3
+
+
 @pytest.mark.parametrize("N,HW,C", [(256, 16, 512), (5, 1, 512), (3, 3, 512)])
 def test_avgpool(N, HW, C):
     from mml_b200 import ops

@@ -115,3 +115,16 @@ def test_shim_registers_yaml_tags_and_swaps_reference_model():
         assert resolve_model_name("avmnist") is AVMNIST
         cfg = yaml.safe_load("a: !ResNet18\n  in_channels: 1\n  hidden_dim: 64\n")
         assert isinstance(cfg["a"], ResNetEncoder)
+
+
+def test_ctypes_signatures_match_header_arity():
+    """Every ctypes argtypes list has exactly as many entries as the C prototype has parameters."""
+    from mml_b200 import _lib
+
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "mml_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    for m in re.finditer(r"\b(mml_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        name, params = m.group(1), m.group(2).strip()
+        n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+        assert name in _lib.SIGNATURES, name
+        assert len(_lib.SIGNATURES[name][1]) == n, f"{name}: header has {n} parameters, binding declares {len(_lib.SIGNATURES[name][1])}"

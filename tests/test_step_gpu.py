@@ -52,12 +52,16 @@ def nchw(t):
     return t.detach().float().cpu().permute(0, 3, 1, 2).contiguous()
 
 
-def forced_from_plan(plan):
+def forced_from_plan(plan, state):
+    """Activations the GPU stored, in the oracle's tap names.  The post-ReLU stem activation is never materialised by the
+    fused stem tail; it is rebuilt here exactly as the kernel forms it: bf16(relu(bn_train(raw stem output)))."""
     forced = {}
     for pre, ep in (("audio_encoder.", plan.audio), ("image_encoder.", plan.image)):
         for name, t in ep.taps.items():
             forced[pre + name] = nchw(t)
         forced[pre + "avgpool"] = ep.pooled.detach().cpu().clone()
+        act = torch.nn.functional.batch_norm(forced[pre + "conv1"], None, None, state[pre + "bn1.weight"], state[pre + "bn1.bias"], True, 0.1, 1e-5)
+        forced[pre + "relu1"] = torch.relu(act).to(torch.bfloat16).float()
     return forced
 
 
@@ -72,7 +76,7 @@ def test_forced_backward_parity(B, hw):
     plan = next(iter(model._engine.plans.values()))
     A = O.apply_missing_mask(d["audio"], d["audio_mask"])
     I = O.apply_missing_mask(d["image"], d["image_mask"])
-    ref = O.train_step(copy.deepcopy(state), {}, A, I, d["labels"], d["dropout_mask"], 0.5, apply_update=False, forced=forced_from_plan(plan))
+    ref = O.train_step(copy.deepcopy(state), {}, A, I, d["labels"], d["dropout_mask"], 0.5, apply_update=False, forced=forced_from_plan(plan, state))
     assert abs(out["loss"] - ref["loss"]) < 1e-4
     assert (plan.logits.cpu() - ref["logits"]).abs().max().item() < 1e-4
     assert torch.equal(plan.pred.cpu().long(), ref["predictions"])
