@@ -185,9 +185,15 @@ def dominant_kernel_roofline(torch, ops, B, pk):
     t = statistics.median(times)
     flops = 2.0 * N * H * W * K * C * 9
     ach = flops / t / 1e12
-    return {"bound": "tensor", "kernel": "conv_igemm_kernel<64,3,2> fprop C=K=64 28x28 (ResNet18 layer1)", "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s",
-            "frac": ach / pk["tf_burst"], "traffic": None, "peak_source": f"{pk['src']} bf16 burst (kernel timed alone, L2 flushed between launches)",
-            "flops_per_launch": flops, "us_per_launch": t * 1e6}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_dominant_kernel_traffic.json")
+    if os.path.exists(tpath) and N == 256:
+        with open(tpath) as f:
+            traffic = json.load(f).get("traffic_bytes")  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
+    return {"bound": "tensor", "kernel": "conv_halo_kernel<1,64,1> fprop C=K=64 28x28 (ResNet18 layer1; the conv family is 55% of the step)", "achieved": ach,
+            "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": traffic,
+            "peak_source": f"{pk['src']} bf16 burst (kernel timed alone, L2 flushed between launches)",
+            "flops_per_launch": flops, "algorithmic_bytes_per_launch": 2.0 * N * H * W * C * 2 + K * 9 * C * 2, "us_per_launch": t * 1e6}
 
 
 def _dbg(rank, msg):

@@ -142,20 +142,24 @@ int mml_head_scratch_per_sample(const mml_head_params* p);
 int mml_head_fwd(mml_ctx*, const mml_head_params* p, const float* pooledA, const float* pooledI, const int64_t* labels,
                  const uint8_t* dropout_mask, float dropout_scale, float* scratch, float* logits, float* loss_out,
                  int32_t* pred, int B, void* stream);
-/* backward of mean CE: fills weight grads, dpooledA [B][FA], dpooledI [B][FI].  loss_scale multiplies dlogits. */
+/* backward of mean CE.  phases bit 0: data gradients (dpooledA [B][FA], dpooledI [B][FI], per-sample deltas into scratch);
+ * bit 1: weight / bias gradients from those deltas (independent of the encoders' backward, so it can run on another
+ * stream); 3 = both.  loss_scale multiplies dlogits. */
 int mml_head_bwd(mml_ctx*, const mml_head_params* p, const mml_head_grads* g, const float* pooledA, const float* pooledI,
                  const int64_t* labels, const uint8_t* dropout_mask, float dropout_scale, float* scratch,
-                 float loss_scale, float* dpooledA, float* dpooledI, int B, void* stream);
+                 float loss_scale, float* dpooledA, float* dpooledI, int B, int phases, void* stream);
 /* stand-alone nn.Linear forward (encoder fc outside the fused head, resnet.py:218): y [B][n_out] = x [B][n_in] W^T + b */
 int mml_linear_fwd(mml_ctx*, const float* x, const float* w, const float* bias, float* y, int B, int n_in, int n_out, void* stream);
 /* Philox-free counter RNG for the throughput path: mask[i] = hash(seed, *step_counter, i) >= p ? 1 : 0 */
 int mml_dropout_mask(mml_ctx*, uint8_t* mask, int64_t n, float p, uint64_t seed, const int64_t* step_counter, void* stream);
 
 /* ---- a9: torch.optim.Adam (coupled weight decay) over the flat parameter buffer -- avmnist.py:303 ---------------- */
-/* hyper (device, fp32[8]): lr, beta1, beta2, eps, weight_decay, grad_scale, -, -;  step (device int64[1]) is
- * incremented by the kernel (so a captured graph advances it).  p/g/m/v fp32 [n]; p_bf16 (optional) gets bf16(p). */
+/* hyper (device, fp32[8]): lr, beta1, beta2, eps, weight_decay, grad_scale, -, -;  step (device int64[1]) holds the number
+ * of completed steps: the update uses t = step + 1, and the counter is incremented on the device when advance_step != 0 (so a
+ * captured graph advances it; a step split over several parameter ranges advances it with the last range only).
+ * p/g/m/v fp32 [n]; p_bf16 (optional) gets bf16(p). */
 int mml_adam_step(mml_ctx*, float* p, const float* g, float* m, float* v, uint16_t* p_bf16, int64_t n, const float* hyper,
-                  int64_t* step, void* stream);
+                  int64_t* step, int advance_step, void* stream);
 /* fp32 -> bf16 copy (shadow refresh after load_state_dict) */
 int mml_cast_f32_bf16(mml_ctx*, const float* src, uint16_t* dst, int64_t n, void* stream);
 /* batched KRSC -> CRSK transposes of the bf16 shadow weights (dgrad operand).  table (device int64[n_convs][6]):

@@ -62,10 +62,10 @@ SIGNATURES = {
     "mml_avgpool_bwd": (I32, [P, P, P, I32, I32, I32, P]),
     "mml_head_scratch_per_sample": (I32, [C.POINTER(HeadParams)]),
     "mml_head_fwd": (I32, [P, C.POINTER(HeadParams), P, P, P, P, F32, P, P, P, P, I32, P]),
-    "mml_head_bwd": (I32, [P, C.POINTER(HeadParams), C.POINTER(HeadGrads), P, P, P, P, F32, P, F32, P, P, I32, P]),
+    "mml_head_bwd": (I32, [P, C.POINTER(HeadParams), C.POINTER(HeadGrads), P, P, P, P, F32, P, F32, P, P, I32, I32, P]),
     "mml_linear_fwd": (I32, [P, P, P, P, P, I32, I32, I32, P]),
     "mml_dropout_mask": (I32, [P, P, I64, F32, U64, P, P]),
-    "mml_adam_step": (I32, [P, P, P, P, P, P, I64, P, P, P]),
+    "mml_adam_step": (I32, [P, P, P, P, P, P, I64, P, P, I32, P]),
     "mml_cast_f32_bf16": (I32, [P, P, P, I64, P]),
     "mml_weights_transpose": (I32, [P, P, P, P, I32, I32, P]),
     "mml_fedavg": (I32, [P, P, P, I32, P, I64, P]),

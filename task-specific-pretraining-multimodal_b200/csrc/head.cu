@@ -396,7 +396,7 @@ int mml_head_fwd(mml_ctx* ctx, const mml_head_params* p, const float* pooledA, c
 
 int mml_head_bwd(mml_ctx* ctx, const mml_head_params* p, const mml_head_grads* g, const float* pooledA, const float* pooledI,
                  const int64_t* labels, const uint8_t* dropout_mask, float dropout_scale, float* scratch,
-                 float loss_scale, float* dpooledA, float* dpooledI, int B, void* stream) {
+                 float loss_scale, float* dpooledA, float* dpooledI, int B, int phases, void* stream) {
   int rc = check_head(ctx, p);
   if (rc) return rc;
   MML_REQUIRE(ctx, g && pooledA && pooledI && labels && scratch && dpooledA && dpooledI && B >= 1, "head_bwd: bad arguments");
@@ -408,9 +408,13 @@ int mml_head_bwd(mml_ctx* ctx, const mml_head_params* p, const mml_head_grads* g
   const int smem = SPC * (d.NC + d.H2 + d.H1 + d.emb() + FM) * (int)sizeof(float);
   MML_REQUIRE(ctx, smem <= 96 * 1024, "head_bwd: dims need %d bytes of shared memory", smem);
   cudaStream_t st = (cudaStream_t)stream;
-  head_bwd_data_kernel<<<(B + SPC - 1) / SPC, kHeadThreads, smem, st>>>(*p, d, (const long long*)labels, dropout_mask, dropout_scale,
-                                                                       scratch, loss_scale, dpooledA, dpooledI, B);
-  MML_LAUNCHED(ctx);
+  MML_REQUIRE(ctx, phases >= 1 && phases <= 3, "head_bwd: phases must be 1 (data), 2 (weights) or 3 (both)");
+  if (phases & 1) {
+    head_bwd_data_kernel<<<(B + SPC - 1) / SPC, kHeadThreads, smem, st>>>(*p, d, (const long long*)labels, dropout_mask, dropout_scale,
+                                                                         scratch, loss_scale, dpooledA, dpooledI, B);
+    MML_LAUNCHED(ctx);
+  }
+  if (!(phases & 2)) return MML_OK;
   const int PS = d.per_sample();
   WgradJobs jobs;
   int fb = 0;

@@ -152,15 +152,17 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 extern "C" {
 
 int mml_adam_step(mml_ctx* ctx, float* p, const float* g, float* m, float* v, uint16_t* p_bf16, int64_t n, const float* hyper,
-                  int64_t* step, void* stream) {
+                  int64_t* step, int advance_step, void* stream) {
   MML_REQUIRE(ctx, ctx && p && g && m && v && hyper && step && n >= 1, "adam_step: bad arguments");
   MML_REQUIRE(ctx, aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && (!p_bf16 || ((uintptr_t)p_bf16 & 7u) == 0),
               "adam_step: buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   adam_kernel<<<flat_grid(ctx, n), 256, 0, st>>>(p, g, m, v, p_bf16, n, hyper, (const long long*)step);
   MML_LAUNCHED(ctx);
-  step_inc_kernel<<<1, 1, 0, st>>>((long long*)step);
-  MML_LAUNCHED(ctx);
+  if (advance_step) {
+    step_inc_kernel<<<1, 1, 0, st>>>((long long*)step);
+    MML_LAUNCHED(ctx);
+  }
   return MML_OK;
 }
 

@@ -47,7 +47,9 @@ class DataParallel:
         engine.world = self.world_size
         engine.allreduce = self._allreduce if self.world_size > 1 else None
 
-    def _allreduce(self, plan, idx: int) -> None:
+    def _allreduce(self, plan, idx: int, update=None) -> None:
+        """All-reduce bucket ``idx`` of G on the communication stream, then run ``update`` (the Adam launch for that range)
+        on the same stream; the last bucket joins the communication stream back into the producer stream."""
         eng = self.engine
         if idx >= len(self.buckets):
             return
@@ -56,8 +58,10 @@ class DataParallel:
         self.comm_stream.wait_stream(producer)
         with torch.cuda.stream(self.comm_stream):
             dist.all_reduce(eng.fs.G[a:b], op=dist.ReduceOp.SUM, group=self.group)
+            if update is not None:
+                update()
         if idx == len(self.buckets) - 1:
-            producer.wait_stream(self.comm_stream)  # Adam (on the main stream) consumes the reduced gradients
+            producer.wait_stream(self.comm_stream)  # everything of this step is ordered before what follows on the main stream
 
     def broadcast_state(self, engine) -> None:
         """Make every rank start from rank 0's weights / Adam state / running statistics."""

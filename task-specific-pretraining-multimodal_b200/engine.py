@@ -498,6 +498,11 @@ class _StepPlan:
         self.eager_steps = 0
         self.launches_per_step = 0
         self.side_stream: Optional[torch.cuda.Stream] = None
+        import os as _os
+        # schedule variants (A/B-tested on B200): defaults are the measured best
+        self.tune = {"adam_split": _os.environ.get("MML_ADAM_SPLIT", "1") == "1", "head_side": _os.environ.get("MML_HEAD_SIDE", "0") == "1"}
+        img = [o for n, o in fs.offsets.items() if n.startswith("image_encoder.")]
+        self.param_split = min(img) if img else 0  # flat ranges: [0, split) audio encoder, [split, total) image encoder + head
 
     # -- schedules -----------------------------------------------------------------------------------------------
     def _use_dropout(self) -> bool:
@@ -539,18 +544,46 @@ class _StepPlan:
         scale = 1.0 / (1.0 - p) if self._use_dropout() else 1.0
         ops.head_fwd(self.hp, self.audio.pooled, self.image.pooled, self.labels, dm, scale, self.scratch, self.logits, self.loss, self.pred)
         ops.head_bwd(self.hp, self.hg, self.audio.pooled, self.image.pooled, self.labels, dm, scale, self.scratch, 1.0,
-                     self.audio.dpooled, self.image.dpooled)
-        # the image encoder holds 2/3 of the parameters but few FLOPs: its gradient bucket (+ the head's) is all-reduced
-        # as soon as its backward is done, under the audio encoder's backward
-        ar0 = (lambda: eng.allreduce(self, 0)) if eng.allreduce is not None else None
-        self._both_encoders(self.audio.bwd, self.image.bwd, after_image=ar0)
-        if eng.allreduce is not None:
-            eng.allreduce(self, 1)
+                     self.audio.dpooled, self.image.dpooled, phases=1)
+
+        def head_weight_grads():  # needs only the per-sample deltas: runs on the side stream, off the audio critical path
+            ops.head_bwd(self.hp, self.hg, self.audio.pooled, self.image.pooled, self.labels, dm, scale, self.scratch, 1.0,
+                         self.audio.dpooled, self.image.dpooled, phases=2)
+        # The image encoder holds 2/3 of the parameters but few FLOPs.  As soon as its backward is done (side stream) its
+        # gradient range (image encoder + head) is all-reduced (DP) and its Adam update runs -- all under the audio
+        # encoder's backward.  The audio range follows on the main stream and advances the step counter.
+        split = self.param_split
+
+        def finish_image_range():
+            if eng.allreduce is not None:
+                eng.allreduce(self, 0, update=lambda: self._adam_range(split, fs.total, False))
+            else:
+                self._adam_range(split, fs.total, False)
+
+        if self.tune["head_side"]:
+            self._both_encoders(self.audio.bwd, [head_weight_grads] + self.image.bwd, after_image=finish_image_range if self.tune["adam_split"] else None)
+        else:
+            head_weight_grads()
+            self._both_encoders(self.audio.bwd, self.image.bwd, after_image=finish_image_range if self.tune["adam_split"] else None)
         fs.NBT += 1
 
-    def run_update(self) -> None:
+    def _adam_range(self, a: int, b: int, advance: bool) -> None:
         fs = self.eng.fs
-        ops.adam_step(fs.P, fs.G, fs.M, fs.V, fs.Wb, fs.hyper, fs.step)
+        ops.adam_step(fs.P[a:b], fs.G[a:b], fs.M[a:b], fs.V[a:b], fs.Wb[a:b], fs.hyper, fs.step, advance)
+
+    def run_update(self) -> None:
+        eng, fs = self.eng, self.eng.fs
+        if not self.tune["adam_split"]:
+            if eng.allreduce is not None:
+                eng.allreduce(self, 0)
+                eng.allreduce(self, 1, update=lambda: self._adam_range(0, fs.total, True))
+            else:
+                self._adam_range(0, fs.total, True)
+            return
+        if eng.allreduce is not None:
+            eng.allreduce(self, 1, update=lambda: self._adam_range(0, self.param_split, True))
+        else:
+            self._adam_range(0, self.param_split, True)
 
     def run_eval(self, with_loss: bool) -> None:
         self._both_encoders(self.audio.fwd_eval, self.image.fwd_eval)

@@ -212,11 +212,12 @@ def head_fwd(hp, pooledA, pooledI, labels, drop_mask, drop_scale, scratch, logit
                                    float(drop_scale), _p(scratch), _p(logits), _p(loss_out), _p(pred, torch.int32), B, _stream(pooledA)), "head_fwd")
 
 
-def head_bwd(hp, hg, pooledA, pooledI, labels, drop_mask, drop_scale, scratch, loss_scale, dpooledA, dpooledI) -> None:
+def head_bwd(hp, hg, pooledA, pooledI, labels, drop_mask, drop_scale, scratch, loss_scale, dpooledA, dpooledI, phases: int = 3) -> None:
     ctx = _ctx(pooledA)
     B = pooledA.shape[0]
     ctx.check(ctx.lib.mml_head_bwd(ctx.handle, C.byref(hp), C.byref(hg), _p(pooledA), _p(pooledI), _p(labels, torch.int64), _p(drop_mask),
-                                   float(drop_scale), _p(scratch), float(loss_scale), _p(dpooledA), _p(dpooledI), B, _stream(pooledA)), "head_bwd")
+                                   float(drop_scale), _p(scratch), float(loss_scale), _p(dpooledA), _p(dpooledI), B, int(phases), _stream(pooledA)),
+              "head_bwd")
 
 
 def linear_fwd(x, w, bias, y) -> None:
@@ -232,10 +233,10 @@ def dropout_mask(mask, p, seed, step_counter) -> None:
 
 
 # ---- optimizer / aggregation ----------------------------------------------------------------------------------------
-def adam_step(p, g, m, v, p_bf16, hyper, step) -> None:
+def adam_step(p, g, m, v, p_bf16, hyper, step, advance_step: bool = True) -> None:
     ctx = _ctx(p)
     ctx.check(ctx.lib.mml_adam_step(ctx.handle, _p(p, torch.float32), _p(g, torch.float32), _p(m, torch.float32), _p(v, torch.float32), _p(p_bf16),
-                                    p.numel(), _p(hyper, torch.float32), _p(step, torch.int64), _stream(p)), "adam_step")
+                                    p.numel(), _p(hyper, torch.float32), _p(step, torch.int64), int(advance_step), _stream(p)), "adam_step")
 
 
 def cast_f32_bf16(src, dst) -> None:

@@ -284,7 +284,9 @@ def test_adam_matches_torch():
         g = torch.randn(n, device="cuda", generator=gen(17 + it)) * 0.01
         pt.grad = g.clone()
         opt.step()
-        ops.adam_step(p, g, m, v, pb, hyper, step)
+        half = n // 2 // 4 * 4
+        ops.adam_step(p[:half], g[:half], m[:half], v[:half], pb[:half], hyper, step, False)  # a step split over two ranges
+        ops.adam_step(p[half:], g[half:], m[half:], v[half:], pb[half:], hyper, step, True)
     assert int(step.item()) == 5
     assert torch.allclose(p, pt.detach(), rtol=1e-5, atol=1e-7), (p - pt.detach()).abs().max()
     assert torch.allclose(m, opt.state[pt]["exp_avg"], rtol=1e-5, atol=1e-9)
