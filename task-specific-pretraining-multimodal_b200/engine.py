@@ -220,6 +220,7 @@ class EncoderPlan:
         self.pooled = torch.zeros(B, 512, device=dev)
         self.dpooled = torch.zeros(B, 512, device=dev)
         self.taps: Dict[str, torch.Tensor] = {}  # stored intermediates by name (NHWC bf16), for tests / inspection
+        self.wgrad_stream: Optional[torch.cuda.Stream] = None  # set by the step plan
         n_stat = STAT_SLOTS * 4 * sum(m.num_features for m in enc.modules() if isinstance(m, nn.BatchNorm2d))
         self.stat_arena = torch.zeros(n_stat, device=dev, dtype=torch.float64)  # zeroed once per step
         self._stat_off = 0
@@ -249,6 +250,22 @@ class EncoderPlan:
 
     def _act(self, *shape) -> torch.Tensor:
         return torch.zeros(*shape, device=self.fs.device, dtype=BF16)
+
+    def _offload(self, fn) -> None:
+        """Run a weight-gradient kernel off the dependency chain.  dgrad -> BN backward -> dgrad is the critical chain of the
+        backward pass; the wgrads only consume what the chain has already produced, so they go to a separate (normal
+        priority) stream where their tensor-pipe work overlaps the HBM-bound BN kernels.  Joined by ``join_offload``."""
+        ws = self.wgrad_stream
+        if ws is None:
+            fn()
+            return
+        ws.wait_stream(torch.cuda.current_stream(self.fs.device))
+        with torch.cuda.stream(ws):
+            fn()
+
+    def join_offload(self) -> None:
+        if self.wgrad_stream is not None:
+            torch.cuda.current_stream(self.fs.device).wait_stream(self.wgrad_stream)
 
     def _build(self, train: bool) -> None:
         fs, B, dev, pre = self.fs, self.B, self.fs.device, self.prefix
@@ -353,14 +370,14 @@ class EncoderPlan:
                         gd_, wdt_, dwd_, rawd_, bnd_, d_rawd_, d_x_ds_ = ds
                         ops.bn_bwd_reduce(dy1, dy2, out, rawd_, bnd_.mean, bnd_.invstd, bnd_.bstat, rows, outC, True)
                         ops.bn_bwd_apply(dy1, dy2, out, rawd_, bnd_.mean, bnd_.invstd, bnd_.gamma, bnd_.bstat, bnd_.dgamma, bnd_.dbeta, d_rawd_, None, rows, outC, True)
-                        ops.conv_wgrad(gd_, xin, d_rawd_, dwd_)
+                        self._offload(lambda: ops.conv_wgrad(gd_, xin, d_rawd_, dwd_))
                         ops.conv_dgrad(gd_, d_rawd_, wdt_, d_x_ds_)
-                    ops.conv_wgrad(g2, a1, d_raw2, dw2)
+                    self._offload(lambda: ops.conv_wgrad(g2, a1, d_raw2, dw2))
                     ops.conv_dgrad(g2, d_raw2, w2t, d_a1)
                     # bn1 + ReLU
                     ops.bn_bwd_reduce(d_a1, None, a1, raw1, bn1.mean, bn1.invstd, bn1.bstat, rows, outC, True)
                     ops.bn_bwd_apply(d_a1, None, a1, raw1, bn1.mean, bn1.invstd, bn1.gamma, bn1.bstat, bn1.dgamma, bn1.dbeta, d_raw1, None, rows, outC, True)
-                    ops.conv_wgrad(g1, xin, d_raw1, dw1)
+                    self._offload(lambda: ops.conv_wgrad(g1, xin, d_raw1, dw1))
                     ops.conv_dgrad(g1, d_raw1, w1t, d_x_main)
 
                 bwd_stack.append(bwd_block)
@@ -389,6 +406,7 @@ class EncoderPlan:
             def bwd_stem():
                 ops.stem_bn_pool_bwd(stem_grad_slots[0], stem_grad_slots[1], amax, raw0, bn0, bn0.bstat, bn0.dgamma, bn0.dbeta, d_raw0, B, P0, Q0, 64)
                 ops.stem_wgrad(x, mask, d_raw0, dw_stem, ws)
+                self.join_offload()
 
             Bk.append(bwd_stem)
 
@@ -500,7 +518,11 @@ class _StepPlan:
         self.side_stream: Optional[torch.cuda.Stream] = None
         import os as _os
         # schedule variants (A/B-tested on B200): defaults are the measured best
-        self.tune = {"adam_split": _os.environ.get("MML_ADAM_SPLIT", "1") == "1", "head_side": _os.environ.get("MML_HEAD_SIDE", "0") == "1"}
+        self.tune = {"adam_split": _os.environ.get("MML_ADAM_SPLIT", "1") == "1", "head_side": _os.environ.get("MML_HEAD_SIDE", "0") == "1",
+                     "skip": _os.environ.get("MML_SKIP_ENCODER", ""), "side_prio": _os.environ.get("MML_SIDE_PRIO", "-1")}
+        if _os.environ.get("MML_WGRAD_STREAMS", "1") == "1":
+            self.audio.wgrad_stream = torch.cuda.Stream(device=dev)
+            self.image.wgrad_stream = torch.cuda.Stream(device=dev)
         img = [o for n, o in fs.offsets.items() if n.startswith("image_encoder.")]
         self.param_split = min(img) if img else 0  # flat ranges: [0, split) audio encoder, [split, total) image encoder + head
 
@@ -510,7 +532,10 @@ class _StepPlan:
 
     def _side(self) -> torch.cuda.Stream:
         if self.side_stream is None:
-            self.side_stream = torch.cuda.Stream(device=self.eng.device)
+            # High priority: the image encoder is a long serial chain of tiny kernels (a few CTAs each); letting them jump
+            # the queue of the audio encoder's large grids keeps that chain off the critical path at almost no cost.
+            prio = int(self.tune.get("side_prio", -1))
+            self.side_stream = torch.cuda.Stream(device=self.eng.device, priority=prio)
         return self.side_stream
 
     def _both_encoders(self, audio_ops, image_ops, after_image=None) -> None:
@@ -519,6 +544,11 @@ class _StepPlan:
         ResNet34 on 28x28 images is ~360 tiny latency-bound launches (1..128 CTAs each); run alone they cost more
         wall time than the 7x bigger audio encoder.  Forked onto a second stream they fill SMs the audio kernels leave idle.
         """
+        skip = self.tune.get("skip", "")  # timing experiments only (results are then meaningless)
+        if skip == "image":
+            image_ops = []
+        elif skip == "audio":
+            audio_ops = []
         main = torch.cuda.current_stream(self.eng.device)
         side = self._side()
         side.wait_stream(main)
@@ -563,7 +593,9 @@ class _StepPlan:
         if self.tune["head_side"]:
             self._both_encoders(self.audio.bwd, [head_weight_grads] + self.image.bwd, after_image=finish_image_range if self.tune["adam_split"] else None)
         else:
-            head_weight_grads()
+            # the head's weight gradients are off the chain too: they share the image encoder's wgrad stream, which is joined
+            # before that range's all-reduce / Adam
+            self.image._offload(head_weight_grads)
             self._both_encoders(self.audio.bwd, self.image.bwd, after_image=finish_image_range if self.tune["adam_split"] else None)
         fs.NBT += 1
 
