@@ -71,3 +71,28 @@ def federated_allreduce(model: torch.nn.Module, my_num_samples: float, group=Non
         dist.all_reduce(buf, group=group)
     dist.broadcast(eng.fs.NBT, src=0, group=group)
     eng.fs.refresh_shadows()
+
+
+class FederatedSimulator:
+    """K simulated clients on one GPU -- the driver ``MML_Suite/train_congruent_federated.py`` would be (that file is empty in
+    the reference).  Every client is a full model with its own optimizer; a round = ``local_steps`` fused train steps per
+    client on that client's batches, then the FedAvg kernel over the clients' flat parameter / running-statistics buffers
+    (weights n_k / sum n), pushed back into every client.  Adam moments stay local (plain FedAvg)."""
+
+    def __init__(self, model_factory, optimizer_factory, num_clients: int, device):
+        self.device = torch.device(device)
+        self.clients = [model_factory().to(self.device) for _ in range(num_clients)]
+        self.optimizers = [optimizer_factory(m) for m in self.clients]
+        for m in self.clients[1:]:
+            m.load_state_dict(self.clients[0].state_dict())  # congruent start
+
+    def round(self, client_batches, loss_functions, num_samples, local_steps: int = 1):
+        """client_batches[k] = list of batch dicts for client k; returns the mean local loss per client."""
+        losses = []
+        for m, opt, batches in zip(self.clients, self.optimizers, client_batches):
+            tot = 0.0
+            for s in range(local_steps):
+                tot += m.train_step(batches[s % len(batches)], opt, loss_functions, self.device, None)["loss"]
+            losses.append(tot / local_steps)
+        federated_round(self.clients, num_samples)
+        return losses

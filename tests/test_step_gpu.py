@@ -214,3 +214,45 @@ def test_unsupported_requests_fail_loudly():
         model.train_step(make_batch(d, 4), sgd, LOSS, torch.device(DEV), None)
     with pytest.raises(NotImplementedError):
         model.forward(A=d["audio"].to(DEV), I=None)
+
+
+def test_fedavg_round_matches_oracle_and_simulator_trains():
+    """config 5: K simulated clients, on-GPU weighted aggregation == oracle fedavg of their state dicts."""
+    from mml_b200 import fedavg
+    from mml_b200.avmnist import AVMNIST
+    from mml_b200.resnet import ResNet18, ResNet34
+
+    K, B = 3, 8
+    seeds = iter(range(100, 100 + K))
+
+    def factory():
+        torch.manual_seed(next(seeds))
+        return AVMNIST(ResNet18(1, 64), ResNet34(1, 128), 128, dropout=0.5)
+
+    models = [factory().to(DEV) for _ in range(K)]
+    for i, m in enumerate(models):  # make BN running stats / counters differ too
+        m.audio_encoder.bn1.running_mean.add_(0.1 * (i + 1))
+    states = [OrderedDict((k, v.detach().cpu().clone().contiguous()) for k, v in m.state_dict().items()) for m in models]
+    n_k = [1000.0, 2000.0, 5000.0]
+    ref = O.fedavg(states, n_k)
+    fedavg.federated_round(models, n_k)
+    for m in models:
+        sd = m.state_dict()
+        for k, v in ref.items():
+            got = sd[k].detach().cpu()
+            if v.dtype.is_floating_point:
+                assert torch.allclose(got, v, rtol=1e-5, atol=1e-7), k
+            else:
+                assert int(got) == int(v), k
+    # simulator: two clients, two rounds, loss goes down and the clients agree after every round
+    torch.manual_seed(0)
+    sim = fedavg.FederatedSimulator(lambda: AVMNIST(ResNet18(1, 64), ResNet34(1, 128), 128, dropout=0.0),
+                                    lambda m: torch.optim.Adam(m.parameters(), lr=5e-4, weight_decay=1e-4), 2, DEV)
+    data = [O.synthetic_batch(B, 40 + k, (112, 112)) for k in range(2)]
+    batches = [[make_batch(d, B)] for d in data]
+    first = sim.round(batches, LOSS, [B, B], local_steps=2)
+    for _ in range(4):
+        last = sim.round(batches, LOSS, [B, B], local_steps=2)
+    assert sum(last) < sum(first)
+    a, b = sim.clients[0].state_dict(), sim.clients[1].state_dict()
+    assert all(torch.equal(a[k], b[k]) for k in a)
