@@ -104,8 +104,14 @@ def import_reference():
     from models.avmnist import AVMNIST
     from models.msa.networks.resnet import ResNet18, ResNet34
     from modalities import Modality
+    from models.gates import GatedBiModalNetwork
+    from models.mmimdb import MLPGenreClassifier, MMIMDb, MMIMDbModalityEncoder
 
     ns = types.SimpleNamespace(
+        MMIMDb=MMIMDb,
+        MMIMDbModalityEncoder=MMIMDbModalityEncoder,
+        MLPGenreClassifier=MLPGenreClassifier,
+        GatedBiModalNetwork=GatedBiModalNetwork,
         AVMNIST=AVMNIST,
         ResNet18=ResNet18,
         ResNet34=ResNet34,

@@ -81,3 +81,38 @@ def test_data_parallel_semantics_and_fedavg():
     avg = O.fedavg([state, s2], [1000, 3000])
     k = "net.5.bias"
     assert torch.allclose(avg[k], state[k] * 0.25 + s2[k] * 0.75)
+
+
+def test_mmimdb_train_steps_match_reference():
+    """config 3: gated_fusion_oracle against the reference MMIMDb run recorded by oracle/make_golden.py."""
+    import gated_fusion_oracle as G
+
+    g = np.load(os.path.join(GOLD, "mmimdb_b16.npz"))
+    batch, seed, steps = (int(v) for v in g["meta"])
+    lr, wd = (float(v) for v in g["hyper"])
+    torch.manual_seed(0)
+    state = G.init_mmimdb_state()
+    assert len(state) == 38 and sum(v.numel() for k, v in state.items() if G.is_parameter(k)) == 3_849_327  # SURVEY 8 a11
+    data = G.synthetic_batch(batch, seed)
+    I, T, y = data["image_masked"], data["text_masked"], data["labels"]
+    assert set(data["pattern_name"]) == {"it", "i", "t"}  # all three missing patterns are in the fixture
+    assert np.allclose(g["input_checksum"], [float(I.double().sum()), float(T.double().sum()), float(y.sum())])
+    opt_state = {}
+    for step in range(steps):
+        out = G.train_step(state, opt_state, I, T, y, data["dropout_masks"], lr=lr, weight_decay=wd)
+        assert abs(out["loss"] - float(g["losses"][step])) < (1e-5 if step == 0 else 2e-3)
+        if step == 0:
+            assert np.allclose(out["logits"].numpy(), g["logits"], rtol=1e-4, atol=1e-5)
+            assert np.array_equal(out["predictions"].numpy(), g["predictions"])
+            keys = list(g["grad_keys"])
+            l2 = np.array([float(out["grads"][k].double().norm()) for k in keys])
+            assert np.allclose(l2, g["grad_l2"], rtol=1e-3, atol=1e-9)
+            for k in g.files:
+                if k.startswith("grad::"):
+                    ref, got = g[k], out["grads"][k[6:]].numpy()
+                    assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-8, k
+    keys = list(g["state_keys"])
+    l2 = np.array([float(state[k].double().norm()) for k in keys])
+    assert np.allclose(l2, g["state_l2"], rtol=2e-3, atol=1e-6)
+    ev = G.validation_step(state, I, T, y)
+    assert np.abs(ev["logits"].numpy() - g["eval_logits"]).max() < 1e-2
