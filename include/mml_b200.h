@@ -153,6 +153,54 @@ int mml_linear_fwd(mml_ctx*, const float* x, const float* w, const float* bias, 
 /* Philox-free counter RNG for the throughput path: mask[i] = hash(seed, *step_counter, i) >= p ? 1 : 0 */
 int mml_dropout_mask(mml_ctx*, uint8_t* mask, int64_t n, float p, uint64_t seed, const int64_t* step_counter, void* stream);
 
+/* ---- a11 (config 3): MMIMDb gated late fusion -- MML_Suite/models/mmimdb.py:20-245 ------------------------------- */
+/* The Linear layers of this model run on mml_conv_fprop / _dgrad / _wgrad as 1x1 convolutions over [B,1,1,C] bf16 rows
+ * (nn.Linear's [out][in] weight IS the K,R,S,C layout).  A bias is carried as one more input column: activations have a
+ * constant 1 at column `in`, the weight row has the bias there (row pitch rounded up to 64), so fprop adds it and wgrad
+ * produces its gradient.  The entry points below are everything between those GEMMs. */
+enum { MML_BN1D_INPUT = 0, MML_BN1D_GATED = 1, MML_BN1D_MAXOUT = 2 };
+/* nn.BatchNorm1d over the batch (mmimdb.py:38,43,46,80) fused with the op that PRODUCES its input:
+ *   INPUT : v[b][c] = x[b*ldx + c] * mask[b]        missing-modality mask (base_dataset.py:71); mask may be NULL
+ *   GATED : v = gate[b]*h1 + (1-gate[b])*h2         GatedBiModalNetwork.forward, gated_bimodal.py:59 (fp32 [B][C])
+ *   MAXOUT: v = max(pre[b][c], pre[b][C+c]) * (keep ? keep[b][c]*keep_scale : 1)   MaxOut (maxout.py:37-41) + Dropout;
+ *           pre bf16 [B][2C] = both units' GEMM output side by side; keep uint8 [B][C] or NULL
+ * train != 0: batch statistics (biased variance), running statistics updated with the unbiased one; else running stats.
+ * Outputs: xhat fp32 [B][C] and invstd [C] (saved for backward, optional), y = gamma*xhat+beta as bf16 rows of pitch ldy
+ * (the next GEMM's A operand) and / or fp32 [B][C]. */
+typedef struct mml_bn1d_desc {
+  int32_t mode, B, C, train;
+  const float* x; const float* mask; int64_t ldx;
+  const float* h1; const float* h2; const float* gate;
+  const uint16_t* pre; const uint8_t* keep; float keep_scale; float momentum; float eps; float reserved;
+  const float* gamma; const float* beta; float* running_mean; float* running_var;
+  float* xhat; float* invstd; uint16_t* y_bf16; int64_t ldy; float* y_f32;
+} mml_bn1d_desc;
+int mml_bn1d_fwd(mml_ctx*, const mml_bn1d_desc*, void* stream);
+/* backward of the same: dy bf16 rows (pitch lddy) -> dgamma, dbeta [C] (stored, not accumulated) and
+ *   INPUT : nothing else;  GATED: dz fp32 [B][C];  MAXOUT: dpre bf16 [B][2C] (winner takes the gradient, ties split). */
+typedef struct mml_bn1d_bwd_desc {
+  int32_t mode, B, C, reserved;
+  const uint16_t* dy; int64_t lddy; const float* xhat; const float* gamma; const float* invstd;
+  float* dgamma; float* dbeta;
+  const uint16_t* pre; const uint8_t* keep; float keep_scale; float reserved2; uint16_t* dpre;
+  float* dz;
+} mml_bn1d_bwd_desc;
+int mml_bn1d_bwd(mml_ctx*, const mml_bn1d_bwd_desc*, void* stream);
+/* GMU (gated_bimodal.py:52-59): h1 = tanh(h1pre), h2 = tanh(h2pre) (bf16 [B][H] GEMM outputs -> fp32), and the scalar
+ * gate[b] = sigmoid(wz . [h1|h2]).  Backward: dz fp32 [B][H] -> dh1pre, dh2pre bf16 and dwz [2H] (ACCUMULATED). */
+int mml_gmu_fwd(mml_ctx*, const uint16_t* h1pre, const uint16_t* h2pre, const float* wz, float* h1, float* h2, float* gate, int B,
+                int H, void* stream);
+int mml_gmu_bwd(mml_ctx*, const float* dz, const float* h1, const float* h2, const float* gate, const float* wz, float* dwz,
+                uint16_t* dh1pre, uint16_t* dh2pre, int B, int H, void* stream);
+/* classifier tail (mmimdb.py:47, loss.py:52, mmimdb.py:238-239): logits = xn W^T + b, loss = mean BCE-with-logits over
+ * B x NC, dlogits = (sigmoid - y) * grad_scale / (B NC), pred = sigmoid(logit) > threshold.  labels / loss / dlogits /
+ * pred are optional; scratch: mml_bce_head_scratch_floats(B) floats, zero-initialised once by the caller. */
+int64_t mml_bce_head_scratch_floats(int B);
+int mml_bce_head_fwd(mml_ctx*, const float* xn, const float* w, const float* bias, const float* labels, float* logits, float* loss,
+                     float* dlogits, uint8_t* pred, float* scratch, float threshold, float grad_scale, int B, int H, int NC, void* stream);
+int mml_bce_head_bwd(mml_ctx*, const float* dlogits, const float* xn, const float* w, float* dw, float* db, uint16_t* dxn, int B, int H,
+                     int NC, void* stream);
+
 /* ---- a9: torch.optim.Adam (coupled weight decay) over the flat parameter buffer -- avmnist.py:303 ---------------- */
 /* hyper (device, fp32[8]): lr, beta1, beta2, eps, weight_decay, grad_scale, -, -;  step (device int64[1]) holds the number
  * of completed steps: the update uses t = step + 1, and the counter is incremented on the device when advance_step != 0 (so a

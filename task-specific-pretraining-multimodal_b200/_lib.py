@@ -31,6 +31,24 @@ class HeadGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("fcA_w", "fcA_b", "fcI_w", "fcI_b", "w0", "b0", "w3", "b3", "w5", "b5")]
 
 
+class BN1dDesc(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("B", C.c_int32), ("C", C.c_int32), ("train", C.c_int32),
+                ("x", C.c_void_p), ("mask", C.c_void_p), ("ldx", C.c_int64),
+                ("h1", C.c_void_p), ("h2", C.c_void_p), ("gate", C.c_void_p),
+                ("pre", C.c_void_p), ("keep", C.c_void_p), ("keep_scale", C.c_float), ("momentum", C.c_float), ("eps", C.c_float),
+                ("reserved", C.c_float),
+                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
+                ("xhat", C.c_void_p), ("invstd", C.c_void_p), ("y_bf16", C.c_void_p), ("ldy", C.c_int64), ("y_f32", C.c_void_p)]
+
+
+class BN1dBwdDesc(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("B", C.c_int32), ("C", C.c_int32), ("reserved", C.c_int32),
+                ("dy", C.c_void_p), ("lddy", C.c_int64), ("xhat", C.c_void_p), ("gamma", C.c_void_p), ("invstd", C.c_void_p),
+                ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+                ("pre", C.c_void_p), ("keep", C.c_void_p), ("keep_scale", C.c_float), ("reserved2", C.c_float), ("dpre", C.c_void_p),
+                ("dz", C.c_void_p)]
+
+
 P, I32, I64, F32, U64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
 
 # name -> (restype, argtypes); every symbol declared in include/mml_b200.h
@@ -65,6 +83,13 @@ SIGNATURES = {
     "mml_head_bwd": (I32, [P, C.POINTER(HeadParams), C.POINTER(HeadGrads), P, P, P, P, F32, P, F32, P, P, I32, I32, P]),
     "mml_linear_fwd": (I32, [P, P, P, P, P, I32, I32, I32, P]),
     "mml_dropout_mask": (I32, [P, P, I64, F32, U64, P, P]),
+    "mml_bn1d_fwd": (I32, [P, C.POINTER(BN1dDesc), P]),
+    "mml_bn1d_bwd": (I32, [P, C.POINTER(BN1dBwdDesc), P]),
+    "mml_gmu_fwd": (I32, [P, P, P, P, P, P, P, I32, I32, P]),
+    "mml_gmu_bwd": (I32, [P, P, P, P, P, P, P, P, P, I32, I32, P]),
+    "mml_bce_head_scratch_floats": (I64, [I32]),
+    "mml_bce_head_fwd": (I32, [P, P, P, P, P, P, P, P, P, P, F32, F32, I32, I32, I32, P]),
+    "mml_bce_head_bwd": (I32, [P, P, P, P, P, P, P, I32, I32, I32, P]),
     "mml_adam_step": (I32, [P, P, P, P, P, P, I64, P, P, I32, P]),
     "mml_cast_f32_bf16": (I32, [P, P, P, I64, P]),
     "mml_weights_transpose": (I32, [P, P, P, P, I32, I32, P]),

@@ -1039,8 +1039,11 @@ int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, in
     if ((rc = encode_view(ctx, &maps.in[i], in_views[i], tg.Wb, tg.Hb, tg.Nb))) return rc;
   // 128x256 tiles have the best operand reuse, but a grid far below one wave (ResNet18 layer4: 32 pixel tiles) runs faster
   // with 128x128 tiles on twice as many SMs
-  int block_n = cout >= 256 ? 256 : cout;
+  int block_n = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
   if (block_n == 256 && tg.tiles_h * tg.tiles_n * (cout / 256) * 2 <= ctx->sm_count) block_n = 128;
+  // a single pixel tile (the Linear layers of the MMIMDb step: M = batch <= 128): spread the output columns over as many SMs
+  // as possible, every CTA streams the whole A operand from L2 anyway
+  if (tg.tiles_h * tg.tiles_n == 1) block_n = 64;
   if (!b_mn) {
     if ((rc = encode_weights(ctx, &maps.w, w, (long long)n_wtaps * cin, cout, block_n))) return rc;
   } else {
@@ -1349,7 +1352,7 @@ int mml_conv_wgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, cons
   }
   View dyv = make_phase_view(dy, g->N, P, Q, g->K, 1, 0, 0);
   if ((rc = encode_view(ctx, &maps.dy, dyv, tg.Wb, tg.Hb, tg.Nb))) return rc;
-  const int block_c = g->C >= 256 ? 256 : g->C;
+  const int block_c = g->C % 256 == 0 ? 256 : (g->C % 128 == 0 ? 128 : 64);
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.num_taps = n_taps;

@@ -1,0 +1,388 @@
+// gated_fusion.cu -- the memory-bound kernels of the MMIMDb gated late-fusion step (BASELINE config 3).
+//
+// The six Linear layers of that model are GEMMs with M = batch (128 = exactly one UMMA M tile) and run on the tcgen05
+// kernels of conv_tc.cu as 1x1 "convolutions" over [B,1,1,C] activations (fprop / dgrad / wgrad, bf16 operands, fp32
+// accumulation).  Everything BETWEEN the GEMMs is here, fused so that each activation makes one trip through HBM/L2:
+//
+//   bn1d_fwd   BatchNorm1d over the batch (exact two-pass mean / variance in fp32) with the PRODUCER of its input fused in:
+//                INPUT   v = x * mask[b]                      (missing-modality mask, base_dataset.py:71; mmimdb.py:80)
+//                GATED   v = g*h1 + (1-g)*h2                  (GMU mix, gated_bimodal.py:59; mmimdb.py:38)
+//                MAXOUT  v = max(pre[:, :C], pre[:, C:]) * keep/(1-p)   (maxout.py:37-41 + Dropout; mmimdb.py:41,44)
+//              and the CONSUMER's operand format fused out: bf16 rows (next GEMM's A operand) or fp32 (final Linear).
+//   bn1d_bwd   dgamma / dbeta / dx of the same, routed back through the producer (max routing + dropout, or plain dz).
+//   gmu_fwd / gmu_bwd   tanh, the per-sample scalar gate sigmoid(w_z . [h1|h2]) and their backward (row reductions).
+//   bce_head_fwd / bwd  Linear(H -> classes) + BCEWithLogits (mean over B x classes) + sigmoid > threshold, and backward.
+//
+// Thread layout of the column kernels: 32 columns x 32 row-groups per CTA; a warp reads 32 consecutive columns of one row
+// (128 B fp32 / 64 B bf16 segments), the batch reduction is a shared-memory tree over the 32 row-groups, so the statistics
+// never leave the CTA (no atomics, deterministic).
+#include <cuda_bf16.h>
+
+#include "mml_common.cuh"
+#include "mml_ctx.h"
+
+namespace {
+using namespace mml;
+
+constexpr int kCols = 32;
+constexpr int kRowGroups = 32;
+
+__device__ __forceinline__ float bf16_val(uint16_t v) { return __uint_as_float((uint32_t)v << 16); }
+__device__ __forceinline__ uint16_t to_bf16(float f) { return __bfloat16_as_ushort(__float2bfloat16_rn(f)); }
+
+template <int MODE>
+__device__ __forceinline__ float produce(const mml_bn1d_desc& d, int b, int c) {
+  if (MODE == MML_BN1D_INPUT) {
+    const float x = d.x[(size_t)b * d.ldx + c];
+    return d.mask ? mask_mul(x, d.mask[b]) : x;
+  } else if (MODE == MML_BN1D_GATED) {
+    const float g = d.gate[b];
+    const size_t i = (size_t)b * d.C + c;
+    return g * d.h1[i] + (1.f - g) * d.h2[i];
+  } else {
+    const size_t i = (size_t)b * 2 * d.C + c;
+    float v = fmaxf(bf16_val(d.pre[i]), bf16_val(d.pre[i + d.C]));
+    if (d.keep) v = d.keep[(size_t)b * d.C + c] ? v * d.keep_scale : 0.f;
+    return v;
+  }
+}
+
+// column sums over the 32 row-groups; result valid in every thread of the column
+__device__ __forceinline__ float column_total(float v, float (*red)[kCols + 1], float* out, int tx, int ty) {
+  red[ty][tx] = v;
+  __syncthreads();
+  if (ty == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kRowGroups; ++k) t += red[k][tx];
+    out[tx] = t;
+  }
+  __syncthreads();
+  return out[tx];
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kCols* kRowGroups) bn1d_fwd_kernel(const mml_bn1d_desc d) {
+  __shared__ float red[kRowGroups][kCols + 1];
+  __shared__ float tot[kCols];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * kCols + tx;
+  const bool valid = c < d.C;
+  const int cc = valid ? c : d.C - 1;  // out-of-range columns shadow the last one and never store
+  float mean, inv;
+  if (d.train) {
+    float s = 0.f;
+    for (int b = ty; b < d.B; b += kRowGroups) s += produce<MODE>(d, b, cc);
+    mean = column_total(s, red, tot, tx, ty) / (float)d.B;
+    float ss = 0.f;
+    for (int b = ty; b < d.B; b += kRowGroups) {
+      const float dv = produce<MODE>(d, b, cc) - mean;
+      ss += dv * dv;
+    }
+    const float var = column_total(ss, red, tot, tx, ty) / (float)d.B;  // biased, used for normalisation
+    inv = 1.0f / sqrtf(var + d.eps);
+    if (ty == 0 && valid) {
+      if (d.invstd) d.invstd[c] = inv;
+      const float unbiased = d.B > 1 ? var * (float)d.B / (float)(d.B - 1) : var;
+      d.running_mean[c] = (1.f - d.momentum) * d.running_mean[c] + d.momentum * mean;
+      d.running_var[c] = (1.f - d.momentum) * d.running_var[c] + d.momentum * unbiased;
+    }
+  } else {
+    mean = d.running_mean[cc];
+    inv = 1.0f / sqrtf(d.running_var[cc] + d.eps);
+  }
+  if (!valid) return;
+  const float g = d.gamma[c], be = d.beta[c];
+  for (int b = ty; b < d.B; b += kRowGroups) {
+    const float xh = (produce<MODE>(d, b, c) - mean) * inv;
+    if (d.xhat) d.xhat[(size_t)b * d.C + c] = xh;
+    const float y = xh * g + be;
+    if (d.y_bf16) d.y_bf16[(size_t)b * d.ldy + c] = to_bf16(y);
+    if (d.y_f32) d.y_f32[(size_t)b * d.C + c] = y;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kCols* kRowGroups) bn1d_bwd_kernel(const mml_bn1d_bwd_desc d) {
+  __shared__ float red[kRowGroups][kCols + 1];
+  __shared__ float tot[kCols];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * kCols + tx;
+  const bool valid = c < d.C;
+  const int cc = valid ? c : d.C - 1;
+  float s1 = 0.f, s2 = 0.f;
+  for (int b = ty; b < d.B; b += kRowGroups) {
+    const float dy = bf16_val(d.dy[(size_t)b * d.lddy + cc]);
+    s1 += dy;
+    s2 += dy * d.xhat[(size_t)b * d.C + cc];
+  }
+  const float sdy = column_total(s1, red, tot, tx, ty);
+  const float sdyx = column_total(s2, red, tot, tx, ty);
+  if (!valid) return;
+  if (ty == 0) {
+    d.dbeta[c] = sdy;
+    d.dgamma[c] = sdyx;
+  }
+  if (MODE == MML_BN1D_INPUT) return;  // the network input needs no gradient
+  const float k = d.gamma[c] * d.invstd[c], invB = 1.f / (float)d.B;
+  for (int b = ty; b < d.B; b += kRowGroups) {
+    const float dy = bf16_val(d.dy[(size_t)b * d.lddy + c]);
+    const float xh = d.xhat[(size_t)b * d.C + c];
+    float dv = k * (dy - sdy * invB - xh * sdyx * invB);
+    if (MODE == MML_BN1D_GATED) {
+      d.dz[(size_t)b * d.C + c] = dv;
+    } else {
+      if (d.keep) dv = d.keep[(size_t)b * d.C + c] ? dv * d.keep_scale : 0.f;
+      const size_t i = (size_t)b * 2 * d.C + c;
+      const float a = bf16_val(d.pre[i]), o = bf16_val(d.pre[i + d.C]);
+      // torch.max(a, b) backward: the winner takes the gradient, an exact tie splits it evenly
+      const float ga = a > o ? dv : (a == o ? 0.5f * dv : 0.f);
+      d.dpre[i] = to_bf16(ga);
+      d.dpre[i + d.C] = to_bf16(dv - ga);
+    }
+  }
+}
+
+// ---- GMU: one warp per sample ---------------------------------------------------------------------------------------
+constexpr int kGmuWarps = 8;
+
+__global__ void __launch_bounds__(kGmuWarps * 32) gmu_fwd_kernel(const uint16_t* __restrict__ h1pre, const uint16_t* __restrict__ h2pre,
+                                                                 const float* __restrict__ wz, float* __restrict__ h1,
+                                                                 float* __restrict__ h2, float* __restrict__ gate, int B, int H) {
+  const int row = blockIdx.x * kGmuWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= B) return;
+  float acc = 0.f;
+  for (int c = lane; c < H; c += 32) {
+    const size_t i = (size_t)row * H + c;
+    const float a = tanhf(bf16_val(h1pre[i])), b = tanhf(bf16_val(h2pre[i]));
+    h1[i] = a;
+    h2[i] = b;
+    acc += a * wz[c] + b * wz[H + c];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) gate[row] = 1.f / (1.f + expf(-acc));
+}
+
+__global__ void __launch_bounds__(kGmuWarps * 32) gmu_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ h1,
+                                                                 const float* __restrict__ h2, const float* __restrict__ gate,
+                                                                 const float* __restrict__ wz, float* __restrict__ dwz,
+                                                                 uint16_t* __restrict__ dh1pre, uint16_t* __restrict__ dh2pre, int B, int H) {
+  __shared__ float s_dgp[kGmuWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * kGmuWarps, row = row0 + warp;
+  float dgp = 0.f;
+  if (row < B) {
+    float dg = 0.f;
+    for (int c = lane; c < H; c += 32) {
+      const size_t i = (size_t)row * H + c;
+      dg += dz[i] * (h1[i] - h2[i]);
+    }
+    dg = warp_sum(dg);
+    const float g = gate[row];
+    dgp = dg * g * (1.f - g);  // gradient at the gate's pre-activation
+    for (int c = lane; c < H; c += 32) {
+      const size_t i = (size_t)row * H + c;
+      const float a = h1[i], b = h2[i], z = dz[i];
+      dh1pre[i] = to_bf16((z * g + dgp * wz[c]) * (1.f - a * a));
+      dh2pre[i] = to_bf16((z * (1.f - g) + dgp * wz[H + c]) * (1.f - b * b));
+    }
+  }
+  if (lane == 0) s_dgp[warp] = dgp;
+  __syncthreads();
+  // d w_z[c] = sum over samples of dgp * [h1|h2][c]: the CTA's rows are summed here, CTAs meet in global atomics
+  for (int c = threadIdx.x; c < 2 * H; c += blockDim.x) {
+    const float* h = c < H ? h1 : h2;
+    const int cc = c < H ? c : c - H;
+    float s = 0.f;
+    for (int r = 0; r < kGmuWarps && row0 + r < B; ++r) s += s_dgp[r] * h[(size_t)(row0 + r) * H + cc];
+    atomicAdd(dwz + c, s);
+  }
+}
+
+// ---- final Linear + BCE-with-logits ---------------------------------------------------------------------------------
+constexpr int kHeadWarps = 8;
+
+__global__ void __launch_bounds__(kHeadWarps * 32) bce_head_fwd_kernel(const float* __restrict__ xn, const float* __restrict__ w,
+                                                                      const float* __restrict__ bias, const float* __restrict__ labels,
+                                                                      float* __restrict__ logits, float* __restrict__ loss,
+                                                                      float* __restrict__ dlogits, uint8_t* __restrict__ pred,
+                                                                      float* __restrict__ scratch, float threshold, float grad_scale,
+                                                                      int B, int H, int NC) {
+  extern __shared__ float s_row[];  // [kHeadWarps][H]
+  __shared__ float s_loss[kHeadWarps];
+  __shared__ bool s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kHeadWarps + warp;
+  float row_loss = 0.f;
+  if (row < B) {
+    float* xr = s_row + warp * H;
+    for (int c = lane; c < H; c += 32) xr[c] = xn[(size_t)row * H + c];
+    __syncwarp();
+    float mine = 0.f;
+    for (int j = 0; j < NC; ++j) {
+      const float* wr = w + (size_t)j * H;
+      float acc = 0.f;
+      for (int c = lane; c < H; c += 32) acc += xr[c] * wr[c];
+      acc = warp_sum(acc);
+      if (lane == j) mine = acc + bias[j];
+    }
+    if (lane < NC) {
+      const size_t i = (size_t)row * NC + lane;
+      logits[i] = mine;
+      const float sig = 1.f / (1.f + expf(-mine));
+      if (pred) pred[i] = sig > threshold ? 1 : 0;
+      if (labels) {
+        const float y = labels[i];
+        row_loss = fmaxf(mine, 0.f) - mine * y + log1pf(expf(-fabsf(mine)));
+        if (dlogits) dlogits[i] = (sig - y) * grad_scale / ((float)B * (float)NC);
+      }
+    }
+    row_loss = warp_sum(row_loss);
+  }
+  if (!loss) return;
+  if (lane == 0) s_loss[warp] = row_loss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < kHeadWarps; ++k) t += s_loss[k];
+    scratch[1 + blockIdx.x] = t;
+    __threadfence();
+    const unsigned ticket = atomicAdd((unsigned*)scratch, 1u);
+    s_last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {  // fixed summation order -> the loss is bit-reproducible
+    __threadfence();
+    float t = 0.f;
+    for (unsigned k = 0; k < gridDim.x; ++k) t += ((volatile float*)scratch)[1 + k];
+    loss[0] = t / ((float)B * (float)NC);
+    *(unsigned*)scratch = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(kCols * 8) bce_head_bwd_kernel(const float* __restrict__ dl, const float* __restrict__ xn,
+                                                                const float* __restrict__ w, float* __restrict__ dw,
+                                                                float* __restrict__ db, uint16_t* __restrict__ dxn, int B, int H, int NC) {
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * kCols + tx;
+  if (c < H) {
+    // d xn[b][c] = sum_j dl[b][j] W[j][c]   (dl reads are warp-wide broadcasts)
+    for (int b = ty; b < B; b += 8) {
+      float acc = 0.f;
+      for (int j = 0; j < NC; ++j) acc += dl[(size_t)b * NC + j] * w[(size_t)j * H + c];
+      dxn[(size_t)b * H + c] = to_bf16(acc);
+    }
+    // d W[j][c] = sum_b dl[b][j] xn[b][c]
+    for (int j = ty; j < NC; j += 8) {
+      float acc = 0.f;
+      for (int b = 0; b < B; ++b) acc += dl[(size_t)b * NC + j] * xn[(size_t)b * H + c];
+      dw[(size_t)j * H + c] = acc;
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (int j = ty; j < NC; j += 8) {
+      float acc = 0.f;
+      for (int b = tx; b < B; b += 32) acc += dl[(size_t)b * NC + j];
+      acc = warp_sum(acc);
+      if (tx == 0) db[j] = acc;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mml_bn1d_fwd(mml_ctx* ctx, const mml_bn1d_desc* d, void* stream) {
+  MML_REQUIRE(ctx, ctx && d, "bn1d_fwd: null ctx/desc");
+  MML_REQUIRE(ctx, d->B >= 1 && d->C >= 1 && d->gamma && d->beta && d->running_mean && d->running_var, "bn1d_fwd: bad arguments");
+  MML_REQUIRE(ctx, !d->train || d->B > 1, "bn1d_fwd: Expected more than 1 value per channel when training (batch %d)", d->B);
+  MML_REQUIRE(ctx, d->y_bf16 || d->y_f32, "bn1d_fwd: no output");
+  MML_REQUIRE(ctx, !d->y_bf16 || d->ldy >= d->C, "bn1d_fwd: ldy < C");
+  const dim3 block(kCols, kRowGroups), grid((unsigned)mml_ceil_div(d->C, kCols));
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d->mode) {
+    case MML_BN1D_INPUT:
+      MML_REQUIRE(ctx, d->x && d->ldx >= d->C, "bn1d_fwd(INPUT): x / ldx");
+      bn1d_fwd_kernel<MML_BN1D_INPUT><<<grid, block, 0, st>>>(*d);
+      break;
+    case MML_BN1D_GATED:
+      MML_REQUIRE(ctx, d->h1 && d->h2 && d->gate, "bn1d_fwd(GATED): h1 / h2 / gate");
+      bn1d_fwd_kernel<MML_BN1D_GATED><<<grid, block, 0, st>>>(*d);
+      break;
+    case MML_BN1D_MAXOUT:
+      MML_REQUIRE(ctx, d->pre, "bn1d_fwd(MAXOUT): pre");
+      bn1d_fwd_kernel<MML_BN1D_MAXOUT><<<grid, block, 0, st>>>(*d);
+      break;
+    default:
+      return mml_set_error(ctx, MML_ERR_INVALID, "bn1d_fwd: unknown mode %d", d->mode);
+  }
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
+int mml_bn1d_bwd(mml_ctx* ctx, const mml_bn1d_bwd_desc* d, void* stream) {
+  MML_REQUIRE(ctx, ctx && d, "bn1d_bwd: null ctx/desc");
+  MML_REQUIRE(ctx, d->B > 1 && d->C >= 1 && d->dy && d->lddy >= d->C && d->xhat && d->dgamma && d->dbeta, "bn1d_bwd: bad arguments");
+  const dim3 block(kCols, kRowGroups), grid((unsigned)mml_ceil_div(d->C, kCols));
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d->mode) {
+    case MML_BN1D_INPUT:
+      bn1d_bwd_kernel<MML_BN1D_INPUT><<<grid, block, 0, st>>>(*d);
+      break;
+    case MML_BN1D_GATED:
+      MML_REQUIRE(ctx, d->gamma && d->invstd && d->dz, "bn1d_bwd(GATED): gamma / invstd / dz");
+      bn1d_bwd_kernel<MML_BN1D_GATED><<<grid, block, 0, st>>>(*d);
+      break;
+    case MML_BN1D_MAXOUT:
+      MML_REQUIRE(ctx, d->gamma && d->invstd && d->pre && d->dpre, "bn1d_bwd(MAXOUT): gamma / invstd / pre / dpre");
+      bn1d_bwd_kernel<MML_BN1D_MAXOUT><<<grid, block, 0, st>>>(*d);
+      break;
+    default:
+      return mml_set_error(ctx, MML_ERR_INVALID, "bn1d_bwd: unknown mode %d", d->mode);
+  }
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
+int mml_gmu_fwd(mml_ctx* ctx, const uint16_t* h1pre, const uint16_t* h2pre, const float* wz, float* h1, float* h2, float* gate, int B,
+                int H, void* stream) {
+  MML_REQUIRE(ctx, ctx && h1pre && h2pre && wz && h1 && h2 && gate && B >= 1 && H >= 1, "gmu_fwd: bad arguments");
+  gmu_fwd_kernel<<<(unsigned)mml_ceil_div(B, kGmuWarps), kGmuWarps * 32, 0, (cudaStream_t)stream>>>(h1pre, h2pre, wz, h1, h2, gate, B, H);
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
+int mml_gmu_bwd(mml_ctx* ctx, const float* dz, const float* h1, const float* h2, const float* gate, const float* wz, float* dwz,
+                uint16_t* dh1pre, uint16_t* dh2pre, int B, int H, void* stream) {
+  MML_REQUIRE(ctx, ctx && dz && h1 && h2 && gate && wz && dwz && dh1pre && dh2pre && B >= 1 && H >= 1, "gmu_bwd: bad arguments");
+  gmu_bwd_kernel<<<(unsigned)mml_ceil_div(B, kGmuWarps), kGmuWarps * 32, 0, (cudaStream_t)stream>>>(dz, h1, h2, gate, wz, dwz, dh1pre, dh2pre,
+                                                                                                   B, H);
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
+int64_t mml_bce_head_scratch_floats(int B) { return 1 + mml_ceil_div(B, kHeadWarps); }
+
+int mml_bce_head_fwd(mml_ctx* ctx, const float* xn, const float* w, const float* bias, const float* labels, float* logits, float* loss,
+                     float* dlogits, uint8_t* pred, float* scratch, float threshold, float grad_scale, int B, int H, int NC, void* stream) {
+  MML_REQUIRE(ctx, ctx && xn && w && bias && logits && B >= 1 && H >= 1, "bce_head_fwd: bad arguments");
+  MML_REQUIRE(ctx, NC >= 1 && NC <= 32, "bce_head_fwd: 1..32 classes supported (got %d)", NC);
+  MML_REQUIRE(ctx, !loss || (labels && scratch), "bce_head_fwd: the loss needs labels and scratch");
+  const size_t smem = (size_t)kHeadWarps * H * sizeof(float);
+  MML_REQUIRE(ctx, smem <= 48 * 1024, "bce_head_fwd: H = %d too large", H);
+  bce_head_fwd_kernel<<<(unsigned)mml_ceil_div(B, kHeadWarps), kHeadWarps * 32, smem, (cudaStream_t)stream>>>(
+      xn, w, bias, labels, logits, loss, dlogits, pred, scratch, threshold, grad_scale, B, H, NC);
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
+int mml_bce_head_bwd(mml_ctx* ctx, const float* dlogits, const float* xn, const float* w, float* dw, float* db, uint16_t* dxn, int B, int H,
+                     int NC, void* stream) {
+  MML_REQUIRE(ctx, ctx && dlogits && xn && w && dw && db && dxn && B >= 1 && H >= 1 && NC >= 1, "bce_head_bwd: bad arguments");
+  bce_head_bwd_kernel<<<(unsigned)mml_ceil_div(H, kCols), dim3(kCols, 8), 0, (cudaStream_t)stream>>>(dlogits, xn, w, dw, db, dxn, B, H, NC);
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
+}  // extern "C"

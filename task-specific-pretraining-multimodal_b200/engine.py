@@ -40,8 +40,14 @@ def _round_up(n: int, a: int) -> int:
 # flat parameter / buffer storage
 # =====================================================================================================================
 class FlatState:
-    def __init__(self, module: nn.Module, device: torch.device):
+    def __init__(self, module: nn.Module, device: torch.device, augment: Optional[Dict[str, str]] = None):
+        """``augment`` = {linear weight name: its bias name}: such a pair is stored as ONE [out][ld] matrix, ld = in + 1
+        rounded up to 64, with the bias in column ``in`` (the tensor-core GEMM then adds the bias through a constant-1
+        activation column and its wgrad yields the bias gradient); ``weight`` / ``bias`` stay visible as strided views."""
         self.module = module
+        self.aug: Dict[str, Tuple[int, int, int, int]] = {}  # weight or bias name -> (offset, out, in, ld)
+        augment = augment or {}
+        aug_bias = set(augment.values())
         self.device = device
         self.param_names: List[str] = []
         self.offsets: Dict[str, int] = {}
@@ -50,6 +56,16 @@ class FlatState:
         off = 0
         for name, p in module.named_parameters():
             self.param_names.append(name)
+            if name in aug_bias:
+                continue  # placed together with its weight
+            if name in augment:
+                n_out, n_in = p.shape
+                ld = _round_up(n_in + 1, ALIGN)
+                self.aug[name] = self.aug[augment[name]] = (off, n_out, n_in, ld)
+                self.offsets[name], self.numels[name] = off, n_out * ld
+                self.offsets[augment[name]], self.numels[augment[name]] = off + n_in, n_out
+                off = _round_up(off + n_out * ld, ALIGN)
+                continue
             self.offsets[name] = off
             self.numels[name] = p.numel()
             if p.dim() == 4 and p.shape[1] >= 64:
@@ -84,6 +100,10 @@ class FlatState:
 
     # -- views ------------------------------------------------------------------------------------------------
     def _view(self, flat: torch.Tensor, name: str, like: torch.Tensor) -> torch.Tensor:
+        if name in self.aug:
+            o, n_out, n_in, ld = self.aug[name]
+            m = flat[o:o + n_out * ld].view(n_out, ld)
+            return m[:, :n_in] if like.dim() == 2 else m[:, n_in]
         o, n = self.offsets[name], self.numels[name]
         v = flat[o:o + n]
         if like.dim() == 4:
@@ -94,6 +114,11 @@ class FlatState:
     def flat_slice(self, flat: torch.Tensor, name: str) -> torch.Tensor:
         o, n = self.offsets[name], self.numels[name]
         return flat[o:o + n]
+
+    def aug_matrix(self, flat: torch.Tensor, weight_name: str) -> torch.Tensor:
+        """[out][ld] weight-plus-bias-column matrix of an augmented Linear."""
+        o, n_out, _, ld = self.aug[weight_name]
+        return flat[o:o + n_out * ld].view(n_out, ld)
 
     def bind(self, copy_in: bool) -> None:
         """Point every parameter / buffer of the module at its slot (copying current values in first)."""

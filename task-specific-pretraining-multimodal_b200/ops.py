@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from ._lib import ConvGeom, Context, HeadGrads, HeadParams, MMLError
+from ._lib import BN1dBwdDesc, BN1dDesc, ConvGeom, Context, HeadGrads, HeadParams, MMLError
 
 BF16 = torch.bfloat16
 
@@ -270,3 +270,100 @@ def debug_set(key: int, value: int) -> None:
 
 def launch_count(device_index: int = 0) -> int:
     return Context.get(device_index).launches
+
+
+# ---- MMIMDb gated late fusion (config 3) ----------------------------------------------------------------------------
+BN1D_INPUT, BN1D_GATED, BN1D_MAXOUT = 0, 1, 2
+
+
+def bn1d_fwd_desc(mode: int, B: int, Cn: int, gamma, beta, rmean, rvar, *, x=None, mask=None, h1=None, h2=None, gate=None, pre=None,
+                  keep=None, keep_scale: float = 1.0, xhat=None, invstd=None, y_bf16=None, y_f32=None, momentum=0.1, eps=1e-5) -> BN1dDesc:
+    """Descriptor for ``bn1d_fwd`` (built once per plan; ``train`` / ``keep`` are set per launch)."""
+    d = BN1dDesc()
+    d.mode, d.B, d.C, d.train = mode, B, Cn, 1
+    d.x, d.mask, d.ldx = _p(x, torch.float32), _p(mask, torch.float32), (x.stride(0) if x is not None else 0)
+    d.h1, d.h2, d.gate = _p(h1, torch.float32), _p(h2, torch.float32), _p(gate, torch.float32)
+    d.pre, d.keep, d.keep_scale = _p(pre, torch.bfloat16), _p(keep, torch.uint8), keep_scale
+    d.momentum, d.eps = momentum, eps
+    d.gamma, d.beta, d.running_mean, d.running_var = (_p(t, torch.float32) for t in (gamma, beta, rmean, rvar))
+    d.xhat, d.invstd = _p(xhat, torch.float32), _p(invstd, torch.float32)
+    d.y_bf16, d.ldy, d.y_f32 = _p(y_bf16, torch.bfloat16), (y_bf16.stride(0) if y_bf16 is not None else 0), _p(y_f32, torch.float32)
+    d._keep_alive = (x, mask, h1, h2, gate, pre, keep, gamma, beta, rmean, rvar, xhat, invstd, y_bf16, y_f32)
+    d._device = gamma
+    return d
+
+
+def bn1d_fwd(d: BN1dDesc, train: bool, use_keep: bool = True) -> None:
+    ref = d._device
+    c = _ctx(ref)
+    keep = d.keep
+    d.train = 1 if train else 0
+    if not (train and use_keep):
+        d.keep = None
+    try:
+        c.check(c.lib.mml_bn1d_fwd(c.handle, C.byref(d), _stream(ref)), "mml_bn1d_fwd")
+    finally:
+        d.keep = keep
+
+
+def bn1d_bwd_desc(mode: int, B: int, Cn: int, dy, xhat, gamma, invstd, dgamma, dbeta, *, pre=None, keep=None, keep_scale: float = 1.0,
+                  dpre=None, dz=None) -> BN1dBwdDesc:
+    d = BN1dBwdDesc()
+    d.mode, d.B, d.C = mode, B, Cn
+    d.dy, d.lddy = _p(dy, torch.bfloat16), dy.stride(0)
+    d.xhat, d.gamma, d.invstd = _p(xhat, torch.float32), _p(gamma, torch.float32), _p(invstd, torch.float32)
+    d.dgamma, d.dbeta = _p(dgamma, torch.float32), _p(dbeta, torch.float32)
+    d.pre, d.keep, d.keep_scale, d.dpre = _p(pre, torch.bfloat16), _p(keep, torch.uint8), keep_scale, _p(dpre, torch.bfloat16)
+    d.dz = _p(dz, torch.float32)
+    d._keep_alive = (dy, xhat, gamma, invstd, dgamma, dbeta, pre, keep, dpre, dz)
+    d._device = xhat
+    return d
+
+
+def bn1d_bwd(d: BN1dBwdDesc, use_keep: bool = True) -> None:
+    ref = d._device
+    c = _ctx(ref)
+    keep = d.keep
+    if not use_keep:
+        d.keep = None
+    try:
+        c.check(c.lib.mml_bn1d_bwd(c.handle, C.byref(d), _stream(ref)), "mml_bn1d_bwd")
+    finally:
+        d.keep = keep
+
+
+def gmu_fwd(h1pre, h2pre, wz, h1, h2, gate) -> None:
+    B, H = h1.shape
+    c = _ctx(h1)
+    c.check(c.lib.mml_gmu_fwd(c.handle, _p(h1pre, torch.bfloat16), _p(h2pre, torch.bfloat16), _p(wz, torch.float32), _p(h1, torch.float32),
+                              _p(h2, torch.float32), _p(gate, torch.float32), B, H, _stream(h1)), "mml_gmu_fwd")
+
+
+def gmu_bwd(dz, h1, h2, gate, wz, dwz, dh1pre, dh2pre) -> None:
+    B, H = h1.shape
+    c = _ctx(h1)
+    c.check(c.lib.mml_gmu_bwd(c.handle, _p(dz, torch.float32), _p(h1, torch.float32), _p(h2, torch.float32), _p(gate, torch.float32),
+                              _p(wz, torch.float32), _p(dwz, torch.float32), _p(dh1pre, torch.bfloat16), _p(dh2pre, torch.bfloat16), B, H,
+                              _stream(h1)), "mml_gmu_bwd")
+
+
+def bce_head_scratch_floats(B: int) -> int:
+    from ._lib import load_library
+    return int(load_library().mml_bce_head_scratch_floats(int(B)))
+
+
+def bce_head_fwd(xn, w, bias, labels, logits, loss, dlogits, pred, scratch, threshold: float, grad_scale: float = 1.0) -> None:
+    B, H = xn.shape
+    NC = w.shape[0]
+    c = _ctx(xn)
+    c.check(c.lib.mml_bce_head_fwd(c.handle, _p(xn, torch.float32), _p(w, torch.float32), _p(bias, torch.float32), _p(labels, torch.float32),
+                                   _p(logits, torch.float32), _p(loss, torch.float32), _p(dlogits, torch.float32), _p(pred, torch.uint8),
+                                   _p(scratch, torch.float32), float(threshold), float(grad_scale), B, H, NC, _stream(xn)), "mml_bce_head_fwd")
+
+
+def bce_head_bwd(dlogits, xn, w, dw, db, dxn) -> None:
+    B, H = xn.shape
+    NC = w.shape[0]
+    c = _ctx(xn)
+    c.check(c.lib.mml_bce_head_bwd(c.handle, _p(dlogits, torch.float32), _p(xn, torch.float32), _p(w, torch.float32), _p(dw, torch.float32),
+                                   _p(db, torch.float32), _p(dxn, torch.bfloat16), B, H, NC, _stream(xn)), "mml_bce_head_bwd")

@@ -8,7 +8,10 @@ What it re-binds (reference file:line):
   * ``resolve_model_name("avmnist")`` (MML_Suite/config/resolvers.py:18-22 does ``from models.avmnist import AVMNIST``
     at call time) -> the attribute ``models.avmnist.AVMNIST`` is replaced by ``mml_b200.avmnist.AVMNIST``;
   * ``models.msa.networks.resnet.ResNet18/ResNet34/ResNetEncoder`` for scripts that import them directly
-    (MML_Suite/train_monomodal.py).
+    (MML_Suite/train_monomodal.py);
+  * config 3: YAML tags ``!MMIMDb`` / ``!MMIMDbModalityEncoder`` / ``!GatedBiModalNetwork`` / ``!MLPGenreClassifier``
+    (yaml_constructors.py:126-142) and the attributes ``models.mmimdb.MMIMDb`` (+ the three part classes) ->
+    ``mml_b200.mmimdb``.
 Works without the reference on the path too (then only the YAML tags are registered).
 """
 from __future__ import annotations
@@ -35,6 +38,12 @@ def install(patch_reference_modules: bool = True) -> Dict[str, object]:
     register("!ResNet18", ResNet18)
     register("!ResNet34", ResNet34)
     register("!ResNetEncoder", ResNetEncoder)
+    from . import mmimdb as _mm
+
+    gated = {"MMIMDb": _mm.MMIMDb, "MMIMDbModalityEncoder": _mm.MMIMDbModalityEncoder, "GatedBiModalNetwork": _mm.GatedBiModalNetwork,
+             "MLPGenreClassifier": _mm.MLPGenreClassifier}
+    for cname, cls in gated.items():
+        register("!" + cname, cls)
     if patch_reference_modules:
         ref_av = sys.modules.get("models.avmnist")
         if ref_av is None:
@@ -45,8 +54,14 @@ def install(patch_reference_modules: bool = True) -> Dict[str, object]:
         if ref_av is not None:
             _installed["reference.AVMNIST"] = getattr(ref_av, "AVMNIST", None)
             ref_av.AVMNIST = AVMNIST
+        ref_mm = sys.modules.get("models.mmimdb")
+        if ref_mm is not None:
+            _installed["reference.MMIMDb"] = getattr(ref_mm, "MMIMDb", None)
+            for cname, cls in gated.items():
+                setattr(ref_mm, cname, cls)
         ref_rn = sys.modules.get("models.msa.networks.resnet")
         if ref_rn is not None:
             ref_rn.ResNet18, ref_rn.ResNet34, ref_rn.ResNetEncoder = ResNet18, ResNet34, ResNetEncoder
     _installed["AVMNIST"] = AVMNIST
+    _installed["MMIMDb"] = _mm.MMIMDb
     return dict(_installed)
