@@ -61,7 +61,9 @@ __device__ __forceinline__ float column_total(float v, float (*red)[kCols + 1], 
   return out[tx];
 }
 
-template <int MODE>
+// REG = true: B <= 4 * kRowGroups, every thread keeps its (at most 4) produced values in registers -> one trip to memory
+// instead of three (the statistics passes re-run the producer otherwise).
+template <int MODE, bool REG>
 __global__ void __launch_bounds__(kCols* kRowGroups) bn1d_fwd_kernel(const mml_bn1d_desc d) {
   __shared__ float red[kRowGroups][kCols + 1];
   __shared__ float tot[kCols];
@@ -69,15 +71,31 @@ __global__ void __launch_bounds__(kCols* kRowGroups) bn1d_fwd_kernel(const mml_b
   const int c = blockIdx.x * kCols + tx;
   const bool valid = c < d.C;
   const int cc = valid ? c : d.C - 1;  // out-of-range columns shadow the last one and never store
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (REG) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (ty + k * kRowGroups < d.B) v[k] = produce<MODE>(d, ty + k * kRowGroups, cc);
+  }
   float mean, inv;
   if (d.train) {
     float s = 0.f;
-    for (int b = ty; b < d.B; b += kRowGroups) s += produce<MODE>(d, b, cc);
+    if (REG) {
+      s = (v[0] + v[1]) + (v[2] + v[3]);
+    } else {
+      for (int b = ty; b < d.B; b += kRowGroups) s += produce<MODE>(d, b, cc);
+    }
     mean = column_total(s, red, tot, tx, ty) / (float)d.B;
     float ss = 0.f;
-    for (int b = ty; b < d.B; b += kRowGroups) {
-      const float dv = produce<MODE>(d, b, cc) - mean;
-      ss += dv * dv;
+    if (REG) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ty + k * kRowGroups < d.B) ss += (v[k] - mean) * (v[k] - mean);
+    } else {
+      for (int b = ty; b < d.B; b += kRowGroups) {
+        const float dv = produce<MODE>(d, b, cc) - mean;
+        ss += dv * dv;
+      }
     }
     const float var = column_total(ss, red, tot, tx, ty) / (float)d.B;  // biased, used for normalisation
     inv = 1.0f / sqrtf(var + d.eps);
@@ -93,16 +111,23 @@ __global__ void __launch_bounds__(kCols* kRowGroups) bn1d_fwd_kernel(const mml_b
   }
   if (!valid) return;
   const float g = d.gamma[c], be = d.beta[c];
-  for (int b = ty; b < d.B; b += kRowGroups) {
-    const float xh = (produce<MODE>(d, b, c) - mean) * inv;
+  auto emit = [&](int b, float val) {
+    const float xh = (val - mean) * inv;
     if (d.xhat) d.xhat[(size_t)b * d.C + c] = xh;
     const float y = xh * g + be;
     if (d.y_bf16) d.y_bf16[(size_t)b * d.ldy + c] = to_bf16(y);
     if (d.y_f32) d.y_f32[(size_t)b * d.C + c] = y;
+  };
+  if (REG) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (ty + k * kRowGroups < d.B) emit(ty + k * kRowGroups, v[k]);
+  } else {
+    for (int b = ty; b < d.B; b += kRowGroups) emit(b, produce<MODE>(d, b, c));
   }
 }
 
-template <int MODE>
+template <int MODE, bool REG>
 __global__ void __launch_bounds__(kCols* kRowGroups) bn1d_bwd_kernel(const mml_bn1d_bwd_desc d) {
   __shared__ float red[kRowGroups][kCols + 1];
   __shared__ float tot[kCols];
@@ -111,10 +136,24 @@ __global__ void __launch_bounds__(kCols* kRowGroups) bn1d_bwd_kernel(const mml_b
   const bool valid = c < d.C;
   const int cc = valid ? c : d.C - 1;
   float s1 = 0.f, s2 = 0.f;
-  for (int b = ty; b < d.B; b += kRowGroups) {
-    const float dy = bf16_val(d.dy[(size_t)b * d.lddy + cc]);
-    s1 += dy;
-    s2 += dy * d.xhat[(size_t)b * d.C + cc];
+  float vdy[4] = {0.f, 0.f, 0.f, 0.f}, vxh[4] = {0.f, 0.f, 0.f, 0.f};
+  if (REG) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int b = ty + k * kRowGroups;
+      if (b < d.B) {
+        vdy[k] = bf16_val(d.dy[(size_t)b * d.lddy + cc]);
+        vxh[k] = d.xhat[(size_t)b * d.C + cc];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s1 += vdy[k], s2 += vdy[k] * vxh[k];
+  } else {
+    for (int b = ty; b < d.B; b += kRowGroups) {
+      const float dy = bf16_val(d.dy[(size_t)b * d.lddy + cc]);
+      s1 += dy;
+      s2 += dy * d.xhat[(size_t)b * d.C + cc];
+    }
   }
   const float sdy = column_total(s1, red, tot, tx, ty);
   const float sdyx = column_total(s2, red, tot, tx, ty);
@@ -125,9 +164,7 @@ __global__ void __launch_bounds__(kCols* kRowGroups) bn1d_bwd_kernel(const mml_b
   }
   if (MODE == MML_BN1D_INPUT) return;  // the network input needs no gradient
   const float k = d.gamma[c] * d.invstd[c], invB = 1.f / (float)d.B;
-  for (int b = ty; b < d.B; b += kRowGroups) {
-    const float dy = bf16_val(d.dy[(size_t)b * d.lddy + c]);
-    const float xh = d.xhat[(size_t)b * d.C + c];
+  auto emit = [&](int b, float dy, float xh) {
     float dv = k * (dy - sdy * invB - xh * sdyx * invB);
     if (MODE == MML_BN1D_GATED) {
       d.dz[(size_t)b * d.C + c] = dv;
@@ -140,6 +177,13 @@ __global__ void __launch_bounds__(kCols* kRowGroups) bn1d_bwd_kernel(const mml_b
       d.dpre[i] = to_bf16(ga);
       d.dpre[i + d.C] = to_bf16(dv - ga);
     }
+  };
+  if (REG) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (ty + q * kRowGroups < d.B) emit(ty + q * kRowGroups, vdy[q], vxh[q]);
+  } else {
+    for (int b = ty; b < d.B; b += kRowGroups) emit(b, bf16_val(d.dy[(size_t)b * d.lddy + c]), d.xhat[(size_t)b * d.C + c]);
   }
 }
 
@@ -152,6 +196,7 @@ __global__ void __launch_bounds__(kGmuWarps * 32) gmu_fwd_kernel(const uint16_t*
   const int row = blockIdx.x * kGmuWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= B) return;
   float acc = 0.f;
+#pragma unroll 4
   for (int c = lane; c < H; c += 32) {
     const size_t i = (size_t)row * H + c;
     const float a = tanhf(bf16_val(h1pre[i])), b = tanhf(bf16_val(h2pre[i]));
@@ -173,6 +218,7 @@ __global__ void __launch_bounds__(kGmuWarps * 32) gmu_bwd_kernel(const float* __
   float dgp = 0.f;
   if (row < B) {
     float dg = 0.f;
+#pragma unroll 8
     for (int c = lane; c < H; c += 32) {
       const size_t i = (size_t)row * H + c;
       dg += dz[i] * (h1[i] - h2[i]);
@@ -180,6 +226,7 @@ __global__ void __launch_bounds__(kGmuWarps * 32) gmu_bwd_kernel(const float* __
     dg = warp_sum(dg);
     const float g = gate[row];
     dgp = dg * g * (1.f - g);  // gradient at the gate's pre-activation
+#pragma unroll 4
     for (int c = lane; c < H; c += 32) {
       const size_t i = (size_t)row * H + c;
       const float a = h1[i], b = h2[i], z = dz[i];
@@ -194,7 +241,9 @@ __global__ void __launch_bounds__(kGmuWarps * 32) gmu_bwd_kernel(const float* __
     const float* h = c < H ? h1 : h2;
     const int cc = c < H ? c : c - H;
     float s = 0.f;
-    for (int r = 0; r < kGmuWarps && row0 + r < B; ++r) s += s_dgp[r] * h[(size_t)(row0 + r) * H + cc];
+#pragma unroll
+    for (int r = 0; r < kGmuWarps; ++r)
+      if (row0 + r < B) s += s_dgp[r] * h[(size_t)(row0 + r) * H + cc];
     atomicAdd(dwz + c, s);
   }
 }
@@ -208,20 +257,46 @@ __global__ void __launch_bounds__(kHeadWarps * 32) bce_head_fwd_kernel(const flo
                                                                       float* __restrict__ dlogits, uint8_t* __restrict__ pred,
                                                                       float* __restrict__ scratch, float threshold, float grad_scale,
                                                                       int B, int H, int NC) {
-  extern __shared__ float s_row[];  // [kHeadWarps][H]
+  // [NC][H] weights + [kHeadWarps][H] rows.  Both are staged with wide, fully independent loads (one round trip to L2);
+  // the 23 dots per sample then run out of shared memory.  (Dots straight from global were a chain of dependent
+  // load->FMA pairs: 132 us for 128 samples.)
+  extern __shared__ __align__(16) float s_head[];
+  float* s_w = s_head;
+  float* s_row = s_head + (size_t)NC * H;
   __shared__ float s_loss[kHeadWarps];
   __shared__ bool s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * kHeadWarps + warp;
+  const int row0 = blockIdx.x * kHeadWarps, row = row0 + warp;
+  {
+    const int nw4 = NC * H / 4, rows = min(kHeadWarps, B - row0), nr4 = rows * H / 4;
+    const float4* gw = reinterpret_cast<const float4*>(w);
+    const float4* gx = reinterpret_cast<const float4*>(xn + (size_t)row0 * H);
+    float4* sw4 = reinterpret_cast<float4*>(s_w);
+    float4* sr4 = reinterpret_cast<float4*>(s_row);
+    for (int i0 = 0; i0 < nw4; i0 += 8 * blockDim.x) {
+      float4 t[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = i0 + k * blockDim.x + threadIdx.x;
+        if (i < nw4) t[k] = gw[i];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = i0 + k * blockDim.x + threadIdx.x;
+        if (i < nw4) sw4[i] = t[k];
+      }
+    }
+    for (int i = threadIdx.x; i < nr4; i += blockDim.x) sr4[i] = gx[i];
+  }
+  __syncthreads();
   float row_loss = 0.f;
   if (row < B) {
-    float* xr = s_row + warp * H;
-    for (int c = lane; c < H; c += 32) xr[c] = xn[(size_t)row * H + c];
-    __syncwarp();
+    const float* xr = s_row + warp * H;
     float mine = 0.f;
     for (int j = 0; j < NC; ++j) {
-      const float* wr = w + (size_t)j * H;
+      const float* wr = s_w + (size_t)j * H;
       float acc = 0.f;
+#pragma unroll 4
       for (int c = lane; c < H; c += 32) acc += xr[c] * wr[c];
       acc = warp_sum(acc);
       if (lane == j) mine = acc + bias[j];
@@ -263,29 +338,56 @@ __global__ void __launch_bounds__(kHeadWarps * 32) bce_head_fwd_kernel(const flo
 __global__ void __launch_bounds__(kCols * 8) bce_head_bwd_kernel(const float* __restrict__ dl, const float* __restrict__ xn,
                                                                 const float* __restrict__ w, float* __restrict__ dw,
                                                                 float* __restrict__ db, uint16_t* __restrict__ dxn, int B, int H, int NC) {
-  const int tx = threadIdx.x, ty = threadIdx.y;
+  constexpr int kTile = 128;
+  __shared__ float s_dl[kTile * 32];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kCols + tx;
   const int c = blockIdx.x * kCols + tx;
-  if (c < H) {
-    // d xn[b][c] = sum_j dl[b][j] W[j][c]   (dl reads are warp-wide broadcasts)
-    for (int b = ty; b < B; b += 8) {
+  const bool valid = c < H;
+  const int cc = valid ? c : H - 1;
+  float wreg[32];  // column cc of W
+#pragma unroll
+  for (int j = 0; j < 32; ++j) wreg[j] = j < NC ? w[(size_t)j * H + cc] : 0.f;
+  float accw[4] = {0.f, 0.f, 0.f, 0.f};  // d W[ty + 8 q][c]
+  float accb[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int b0 = 0; b0 < B; b0 += kTile) {
+    const int rows = min(kTile, B - b0);
+    __syncthreads();
+    for (int i = tid; i < rows * NC; i += kCols * 8) s_dl[i] = dl[(size_t)b0 * NC + i];
+    __syncthreads();
+    // d xn[b][c] = sum_j dl[b][j] W[j][c]   (s_dl reads are warp-wide broadcasts)
+    for (int r = ty; r < rows; r += 8) {
       float acc = 0.f;
-      for (int j = 0; j < NC; ++j) acc += dl[(size_t)b * NC + j] * w[(size_t)j * H + c];
-      dxn[(size_t)b * H + c] = to_bf16(acc);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < NC) acc += s_dl[r * NC + j] * wreg[j];
+      if (valid) dxn[(size_t)(b0 + r) * H + c] = to_bf16(acc);
     }
-    // d W[j][c] = sum_b dl[b][j] xn[b][c]
-    for (int j = ty; j < NC; j += 8) {
-      float acc = 0.f;
-      for (int b = 0; b < B; ++b) acc += dl[(size_t)b * NC + j] * xn[(size_t)b * H + c];
-      dw[(size_t)j * H + c] = acc;
+    // d W[j][c] += sum_b dl[b][j] xn[b][c]: 16 rows of the xn column per batch of loads
+    for (int r0 = 0; r0 < rows; r0 += 16) {
+      float xv[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) xv[k] = r0 + k < rows ? xn[(size_t)(b0 + r0 + k) * H + cc] : 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        if (r0 + k < rows) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = ty + 8 * q;
+            if (j < NC) {
+              const float dv = s_dl[(r0 + k) * NC + j];
+              accw[q] += dv * xv[k];
+              accb[q] += dv;
+            }
+          }
+        }
+      }
     }
   }
-  if (blockIdx.x == 0) {
-    for (int j = ty; j < NC; j += 8) {
-      float acc = 0.f;
-      for (int b = tx; b < B; b += 32) acc += dl[(size_t)b * NC + j];
-      acc = warp_sum(acc);
-      if (tx == 0) db[j] = acc;
-    }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int j = ty + 8 * q;
+    if (j < NC && valid) dw[(size_t)j * H + c] = accw[q];
+    if (j < NC && blockIdx.x == 0 && tx == 0) db[j] = accb[q];
   }
 }
 
@@ -301,18 +403,22 @@ int mml_bn1d_fwd(mml_ctx* ctx, const mml_bn1d_desc* d, void* stream) {
   MML_REQUIRE(ctx, !d->y_bf16 || d->ldy >= d->C, "bn1d_fwd: ldy < C");
   const dim3 block(kCols, kRowGroups), grid((unsigned)mml_ceil_div(d->C, kCols));
   cudaStream_t st = (cudaStream_t)stream;
+  const bool reg = d->B <= 4 * kRowGroups;
   switch (d->mode) {
     case MML_BN1D_INPUT:
       MML_REQUIRE(ctx, d->x && d->ldx >= d->C, "bn1d_fwd(INPUT): x / ldx");
-      bn1d_fwd_kernel<MML_BN1D_INPUT><<<grid, block, 0, st>>>(*d);
+      if (reg) bn1d_fwd_kernel<MML_BN1D_INPUT, true><<<grid, block, 0, st>>>(*d);
+      else bn1d_fwd_kernel<MML_BN1D_INPUT, false><<<grid, block, 0, st>>>(*d);
       break;
     case MML_BN1D_GATED:
       MML_REQUIRE(ctx, d->h1 && d->h2 && d->gate, "bn1d_fwd(GATED): h1 / h2 / gate");
-      bn1d_fwd_kernel<MML_BN1D_GATED><<<grid, block, 0, st>>>(*d);
+      if (reg) bn1d_fwd_kernel<MML_BN1D_GATED, true><<<grid, block, 0, st>>>(*d);
+      else bn1d_fwd_kernel<MML_BN1D_GATED, false><<<grid, block, 0, st>>>(*d);
       break;
     case MML_BN1D_MAXOUT:
       MML_REQUIRE(ctx, d->pre, "bn1d_fwd(MAXOUT): pre");
-      bn1d_fwd_kernel<MML_BN1D_MAXOUT><<<grid, block, 0, st>>>(*d);
+      if (reg) bn1d_fwd_kernel<MML_BN1D_MAXOUT, true><<<grid, block, 0, st>>>(*d);
+      else bn1d_fwd_kernel<MML_BN1D_MAXOUT, false><<<grid, block, 0, st>>>(*d);
       break;
     default:
       return mml_set_error(ctx, MML_ERR_INVALID, "bn1d_fwd: unknown mode %d", d->mode);
@@ -326,17 +432,21 @@ int mml_bn1d_bwd(mml_ctx* ctx, const mml_bn1d_bwd_desc* d, void* stream) {
   MML_REQUIRE(ctx, d->B > 1 && d->C >= 1 && d->dy && d->lddy >= d->C && d->xhat && d->dgamma && d->dbeta, "bn1d_bwd: bad arguments");
   const dim3 block(kCols, kRowGroups), grid((unsigned)mml_ceil_div(d->C, kCols));
   cudaStream_t st = (cudaStream_t)stream;
+  const bool reg = d->B <= 4 * kRowGroups;
   switch (d->mode) {
     case MML_BN1D_INPUT:
-      bn1d_bwd_kernel<MML_BN1D_INPUT><<<grid, block, 0, st>>>(*d);
+      if (reg) bn1d_bwd_kernel<MML_BN1D_INPUT, true><<<grid, block, 0, st>>>(*d);
+      else bn1d_bwd_kernel<MML_BN1D_INPUT, false><<<grid, block, 0, st>>>(*d);
       break;
     case MML_BN1D_GATED:
       MML_REQUIRE(ctx, d->gamma && d->invstd && d->dz, "bn1d_bwd(GATED): gamma / invstd / dz");
-      bn1d_bwd_kernel<MML_BN1D_GATED><<<grid, block, 0, st>>>(*d);
+      if (reg) bn1d_bwd_kernel<MML_BN1D_GATED, true><<<grid, block, 0, st>>>(*d);
+      else bn1d_bwd_kernel<MML_BN1D_GATED, false><<<grid, block, 0, st>>>(*d);
       break;
     case MML_BN1D_MAXOUT:
       MML_REQUIRE(ctx, d->gamma && d->invstd && d->pre && d->dpre, "bn1d_bwd(MAXOUT): gamma / invstd / pre / dpre");
-      bn1d_bwd_kernel<MML_BN1D_MAXOUT><<<grid, block, 0, st>>>(*d);
+      if (reg) bn1d_bwd_kernel<MML_BN1D_MAXOUT, true><<<grid, block, 0, st>>>(*d);
+      else bn1d_bwd_kernel<MML_BN1D_MAXOUT, false><<<grid, block, 0, st>>>(*d);
       break;
     default:
       return mml_set_error(ctx, MML_ERR_INVALID, "bn1d_bwd: unknown mode %d", d->mode);
@@ -369,8 +479,14 @@ int mml_bce_head_fwd(mml_ctx* ctx, const float* xn, const float* w, const float*
   MML_REQUIRE(ctx, ctx && xn && w && bias && logits && B >= 1 && H >= 1, "bce_head_fwd: bad arguments");
   MML_REQUIRE(ctx, NC >= 1 && NC <= 32, "bce_head_fwd: 1..32 classes supported (got %d)", NC);
   MML_REQUIRE(ctx, !loss || (labels && scratch), "bce_head_fwd: the loss needs labels and scratch");
-  const size_t smem = (size_t)kHeadWarps * H * sizeof(float);
-  MML_REQUIRE(ctx, smem <= 48 * 1024, "bce_head_fwd: H = %d too large", H);
+  MML_REQUIRE(ctx, H % 4 == 0, "bce_head_fwd: H must be a multiple of 4 (got %d)", H);
+  const size_t smem = (size_t)(kHeadWarps + NC) * H * sizeof(float);
+  MML_REQUIRE(ctx, smem <= 200 * 1024, "bce_head_fwd: (classes + 8) x H = %zu bytes of shared memory", smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    MML_CHECK_CUDA(ctx, cudaFuncSetAttribute(bce_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
   bce_head_fwd_kernel<<<(unsigned)mml_ceil_div(B, kHeadWarps), kHeadWarps * 32, smem, (cudaStream_t)stream>>>(
       xn, w, bias, labels, logits, loss, dlogits, pred, scratch, threshold, grad_scale, B, H, NC);
   MML_LAUNCHED(ctx);
@@ -380,6 +496,7 @@ int mml_bce_head_fwd(mml_ctx* ctx, const float* xn, const float* w, const float*
 int mml_bce_head_bwd(mml_ctx* ctx, const float* dlogits, const float* xn, const float* w, float* dw, float* db, uint16_t* dxn, int B, int H,
                      int NC, void* stream) {
   MML_REQUIRE(ctx, ctx && dlogits && xn && w && dw && db && dxn && B >= 1 && H >= 1 && NC >= 1, "bce_head_bwd: bad arguments");
+  MML_REQUIRE(ctx, NC <= 32, "bce_head_bwd: 1..32 classes supported (got %d)", NC);
   bce_head_bwd_kernel<<<(unsigned)mml_ceil_div(H, kCols), dim3(kCols, 8), 0, (cudaStream_t)stream>>>(dlogits, xn, w, dw, db, dxn, B, H, NC);
   MML_LAUNCHED(ctx);
   return MML_OK;

@@ -86,8 +86,8 @@ class _GatedPlan:
         self.xh0, self.xn0 = f32(B, E), b16(B, E)
         self.pre1, self.xh1, self.xn1 = b16(B, 2 * H), f32(B, H), b16(B, H)
         self.pre2, self.xh2, self.xn2 = b16(B, 2 * H), f32(B, H), f32(B, H)
-        self.keep1 = torch.ones(B, H, device=dev, dtype=torch.uint8)
-        self.keep2 = torch.ones(B, H, device=dev, dtype=torch.uint8)
+        self.keep = torch.ones(2, B, H, device=dev, dtype=torch.uint8)  # both dropout masks: one generator launch
+        self.keep1, self.keep2 = self.keep[0], self.keep[1]
         self.inv = {k: f32(n) for k, n in (("I", DI), ("T", DT), ("0", E), ("1", H), ("2", H))}
         self.logits, self.dlogits = f32(B, NC), f32(B, NC)
         self.loss = f32(1)
@@ -103,6 +103,12 @@ class _GatedPlan:
         self.h_pred = torch.zeros(B, NC, dtype=torch.uint8).pin_memory()
         self.threshold = 0.5
         self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
+        import os as _os
+        # schedule: the text branch runs next to the image branch on a side stream, weight gradients (needed by Adam only)
+        # on a third one; MML_GATED_STREAMS=0 serialises everything on one stream (A/B timing)
+        multi = _os.environ.get("MML_GATED_STREAMS", "1") == "1"
+        self.side = torch.cuda.Stream(device=dev) if multi else None
+        self.wstream = torch.cuda.Stream(device=dev) if multi else None
         self.eager_steps = 0
         self.launches_per_step = 0
         self._build(params, LI, LT)
@@ -172,19 +178,37 @@ class _GatedPlan:
     def _fprop(gem, x, y):
         ops.conv_fprop(gem[0], x, gem[1], y, None)
 
-    @staticmethod
-    def _bprop(gem, x, dy, dx):
-        ops.conv_wgrad(gem[0], x, dy, gem[2])
+    def _bprop(self, gem, x, dy, dx):
+        """dgrad on the current stream (critical path), wgrad on the weight-gradient stream."""
+        if self.wstream is None:
+            ops.conv_wgrad(gem[0], x, dy, gem[2])
+        else:
+            self.wstream.wait_stream(torch.cuda.current_stream(self.eng.device))
+            with torch.cuda.stream(self.wstream):
+                ops.conv_wgrad(gem[0], x, dy, gem[2])
         if dx is not None:
             ops.conv_dgrad(gem[0], dy, gem[1], dx)
 
+    def _fork(self, main_ops, side_ops) -> None:
+        """two independent kernel chains: ``main_ops`` on the current stream, ``side_ops`` on the side stream; joined."""
+        if self.side is None:
+            for op in main_ops + side_ops:
+                op()
+            return
+        main = torch.cuda.current_stream(self.eng.device)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            for op in side_ops:
+                op()
+        for op in main_ops:
+            op()
+        main.wait_stream(self.side)
+
     def run_forward(self, train: bool, dropout: bool, with_loss: bool, with_grad: bool) -> None:
-        ops.bn1d_fwd(self.f_bnI, train)
-        ops.bn1d_fwd(self.f_bnT, train)
-        self._fprop(self.gemI, self.xnI, self.eI)
-        self._fprop(self.gemT, self.xnT, self.eT)
-        self._fprop(self.gem1, self.eI, self.h1p)
-        self._fprop(self.gem2, self.eT, self.h2p)
+        self._fork([lambda: ops.bn1d_fwd(self.f_bnI, train), lambda: self._fprop(self.gemI, self.xnI, self.eI),
+                    lambda: self._fprop(self.gem1, self.eI, self.h1p)],
+                   [lambda: ops.bn1d_fwd(self.f_bnT, train), lambda: self._fprop(self.gemT, self.xnT, self.eT),
+                    lambda: self._fprop(self.gem2, self.eT, self.h2p)])
         ops.gmu_fwd(self.h1p, self.h2p, self.wz, self.h1, self.h2, self.gate)
         ops.bn1d_fwd(self.f_bn0, train)
         self._fprop(self.gemM1, self.xn0, self.pre1)
@@ -198,8 +222,7 @@ class _GatedPlan:
         eng, fs = self.eng, self.eng.fs
         fs.G.zero_()
         if own_dropout:
-            ops.dropout_mask(self.keep1, DROPOUT_P, eng.seed, fs.step)
-            ops.dropout_mask(self.keep2, DROPOUT_P, eng.seed ^ 0x9E3779B9, fs.step)
+            ops.dropout_mask(self.keep, DROPOUT_P, eng.seed, fs.step)
         self.run_forward(True, True, True, True)
         ops.bce_head_bwd(self.dlogits, self.xn2, self.w7, self.dw7, self.db7, self.dxn2)
         ops.bn1d_bwd(self.b_bn2)
@@ -208,13 +231,12 @@ class _GatedPlan:
         self._bprop(self.gemM1, self.xn0, self.dpre1, self.dxn0)
         ops.bn1d_bwd(self.b_bn0)
         ops.gmu_bwd(self.dz, self.h1, self.h2, self.gate, self.wz, self.dwz, self.dh1p, self.dh2p)
-        self._bprop(self.gem1, self.eI, self.dh1p, self.deI)
-        self._bprop(self.gem2, self.eT, self.dh2p, self.deT)
-        self._bprop(self.gemI, self.xnI, self.deI, self.dxnI)
-        self._bprop(self.gemT, self.xnT, self.deT, self.dxnT)
-        ops.bn1d_bwd(self.b_bnI)
-        ops.bn1d_bwd(self.b_bnT)
-        fs.NBT += 1
+        self._fork([lambda: self._bprop(self.gem1, self.eI, self.dh1p, self.deI), lambda: self._bprop(self.gemI, self.xnI, self.deI, self.dxnI),
+                    lambda: ops.bn1d_bwd(self.b_bnI)],
+                   [lambda: self._bprop(self.gem2, self.eT, self.dh2p, self.deT), lambda: self._bprop(self.gemT, self.xnT, self.deT, self.dxnT),
+                    lambda: ops.bn1d_bwd(self.b_bnT), lambda: fs.NBT.add_(1)])
+        if self.wstream is not None:
+            torch.cuda.current_stream(eng.device).wait_stream(self.wstream)
 
     def run_update(self) -> None:
         eng, fs = self.eng, self.eng.fs
@@ -271,7 +293,6 @@ class _GatedPlan:
 
     def run_forward_train_mode(self) -> None:
         eng, fs = self.eng, self.eng.fs
-        ops.dropout_mask(self.keep1, DROPOUT_P, eng.seed, fs.step)
-        ops.dropout_mask(self.keep2, DROPOUT_P, eng.seed ^ 0x9E3779B9, fs.step)
+        ops.dropout_mask(self.keep, DROPOUT_P, eng.seed, fs.step)
         self.run_forward(True, True, False, False)
         fs.NBT += 1
