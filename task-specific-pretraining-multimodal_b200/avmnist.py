@@ -55,6 +55,18 @@ class AVMNIST(nn.Module):
         self.world_size = 1
         self._dp = None
 
+    # ---- mode switching -----------------------------------------------------------------------------------------
+    def train(self, mode: bool = True):
+        super().train(mode)
+        self._uniform_mode = bool(mode)  # every sub-module now agrees with ``self.training``
+        return self
+
+    def _set_mode(self, training: bool) -> None:
+        """``self.train()`` / ``self.eval()`` of the reference's step methods without walking ~190 sub-modules on every
+        step (0.3 ms of host time per call, i.e. ~8 % of a B200 step) when the mode is already set."""
+        if getattr(self, "_uniform_mode", None) is not training or self.training is not training:
+            self.train(training)
+
     # ---- engine plumbing ---------------------------------------------------------------------------------------
     def _get_engine(self, device: torch.device):
         from .engine import LateFusionEngine
@@ -167,7 +179,7 @@ class AVMNIST(nn.Module):
         eng = self._get_engine(device)
         self._check_loss(loss_functions)
         A, I, mask_a, mask_i, labels, miss_type = self._unpack(batch)
-        self.train()
+        self._set_mode(True)
         fs = eng.fs
         fs.adopt_optimizer(optimizer)
         fs.sync_hyper(optimizer, 1.0 / self.world_size)
@@ -178,7 +190,8 @@ class AVMNIST(nn.Module):
         plan.train_step(given_dropout=given is not None)
         fs._host_step += 1
         plan.h_loss.copy_(plan.loss, non_blocking=True)
-        plan.h_pred.copy_(plan.pred, non_blocking=True)
+        if metric_recorder is not None:
+            plan.h_pred.copy_(plan.pred, non_blocking=True)
         torch.cuda.current_stream(eng.device).synchronize()
         loss = float(plan.h_loss[0])
         if metric_recorder is not None:
@@ -193,7 +206,7 @@ class AVMNIST(nn.Module):
         eng = self._get_engine(device)
         self._check_loss(loss_functions)
         A, I, mask_a, mask_i, labels, miss_type = self._unpack(batch)
-        self.eval()
+        self._set_mode(False)
         plan = self._stage(eng, A, I, mask_a, mask_i, labels)
         plan.run_eval(with_loss=True)
         plan.h_loss.copy_(plan.loss, non_blocking=True)
@@ -214,7 +227,7 @@ class AVMNIST(nn.Module):
         from collections import defaultdict
 
         out = defaultdict(list)
-        self.eval()
+        self._set_mode(False)
         self._get_engine(device)
         for batch in dataloader:
             A, I = _find(batch, "audio"), _find(batch, "image")

@@ -108,6 +108,18 @@ class MMIMDb(nn.Module):
         image_encoder._mml_owner = (weakref.ref(self), "image")
         text_encoder._mml_owner = (weakref.ref(self), "text")
 
+    # ---- mode switching -----------------------------------------------------------------------------------------
+    def train(self, mode: bool = True):
+        super().train(mode)
+        self._uniform_mode = bool(mode)  # every sub-module now agrees with ``self.training``
+        return self
+
+    def _set_mode(self, training: bool) -> None:
+        """``self.train()`` / ``self.eval()`` of the reference's step methods without walking ~190 sub-modules on every
+        step (0.3 ms of host time per call, i.e. ~8 % of a B200 step) when the mode is already set."""
+        if getattr(self, "_uniform_mode", None) is not training or self.training is not training:
+            self.train(training)
+
     # ---- engine plumbing --------------------------------------------------------------------------------------------
     def _get_engine(self, device):
         from .gated_engine import GatedFusionEngine
@@ -209,7 +221,7 @@ class MMIMDb(nn.Module):
         eng = self._get_engine(device)
         self._check_loss(loss_functions)
         I, T, mask_i, mask_t, labels, miss_type = self._unpack(batch)
-        self.train()
+        self._set_mode(True)
         fs = eng.fs
         fs.adopt_optimizer(optimizer)
         fs.sync_hyper(optimizer, 1.0 / self.world_size)
@@ -227,14 +239,15 @@ class MMIMDb(nn.Module):
         eng = self._get_engine(device)
         self._check_loss(loss_functions)
         I, T, mask_i, mask_t, labels, miss_type = self._unpack(batch)
-        self.eval()
+        self._set_mode(False)
         plan = self._stage(eng, I, T, mask_i, mask_t, labels)
         plan.run_eval(with_loss=True)
         return self._finish(eng, plan, labels, miss_type, metric_recorder, return_test_info)
 
     def _finish(self, eng, plan, labels, miss_type, metric_recorder, return_test_info):
         plan.h_loss.copy_(plan.loss, non_blocking=True)
-        plan.h_pred.copy_(plan.pred, non_blocking=True)
+        if metric_recorder is not None or return_test_info:
+            plan.h_pred.copy_(plan.pred, non_blocking=True)
         torch.cuda.current_stream(eng.device).synchronize()
         loss = float(plan.h_loss[0])
         if metric_recorder is None and not return_test_info:
@@ -251,7 +264,7 @@ class MMIMDb(nn.Module):
     def get_embeddings(self, dataloader, device) -> Dict[Any, Any]:
         """mmimdb.py:296-338: per-modality embeddings of the fully-available samples."""
         embeddings = defaultdict(list)
-        self.eval()
+        self._set_mode(False)
         self._get_engine(device)
         for batch in dataloader:
             I, T = _find(batch, "image"), _find(batch, "text")

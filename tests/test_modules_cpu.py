@@ -128,3 +128,35 @@ def test_ctypes_signatures_match_header_arity():
         n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
         assert name in _lib.SIGNATURES, name
         assert len(_lib.SIGNATURES[name][1]) == n, f"{name}: header has {n} parameters, binding declares {len(_lib.SIGNATURES[name][1])}"
+
+
+def test_pattern_generation_matches_reference_fixture_and_masks():
+    """mml_b200.data.generate_patterns against tests/golden/patterns.txt (written from the reference's MissingPatternConfig)."""
+    import os
+    from collections import OrderedDict
+
+    import torch
+
+    from mml_b200 import data
+
+    cases = {
+        "avmnist_audio02": (OrderedDict([("audio", (0.2, None)), ("image", (0.0, None))]), ["ai"]),
+        "avmnist_all": (OrderedDict([("audio", (0.2, None)), ("image", (0.3, None))]), None),
+        "avmnist_apply": (OrderedDict([("audio", (0.25, ["a"])), ("image", (0.5, ["ai", "i"]))]), None),
+        "mosi_3": (OrderedDict([("audio", (0.2, None)), ("video", (0.0, None)), ("text", (0.9, None))]), None),
+    }
+    want = {}
+    with open(os.path.join(os.path.dirname(__file__), "golden", "patterns.txt")) as f:
+        for line in f:
+            c, pat, mod, v = line.strip().split("|")
+            want.setdefault(c, {}).setdefault(pat, {})[mod] = float(v)
+    for cname, (mods, sel) in cases.items():
+        got = data.generate_patterns(mods, sel)
+        assert {k: dict(v) for k, v in got.items()} == want[cname], cname
+    pats = data.generate_patterns(cases["avmnist_audio02"][0], ["ai"])
+    masks = data.draw_missing_masks(pats, 20000, torch.Generator().manual_seed(1))
+    assert set(masks["ai"]["audio"].unique().tolist()) == {0.0, 1.0}
+    assert abs(float(masks["ai"]["audio"].mean()) - 0.8) < 0.01 and float(masks["ai"]["image"].min()) == 1.0
+    b = data.attach_masks({"audio": torch.zeros(2, 4), "image": torch.zeros(2, 3), "labels": torch.zeros(2)},
+                          {"audio": torch.ones(2), "image": torch.ones(2)}, ["audio", "image"])
+    assert set(b) == {"audio_original", "audio_missing_index", "image_original", "image_missing_index", "labels"}

@@ -256,3 +256,32 @@ def test_fedavg_round_matches_oracle_and_simulator_trains():
     assert sum(last) < sum(first)
     a, b = sim.clients[0].state_dict(), sim.clients[1].state_dict()
     assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_device_prefetcher_batches_and_training_equivalence():
+    """mml_b200.data.DevicePrefetcher: same tensors as the host batches, slots reused safely, same training trajectory."""
+    from mml_b200.data import DevicePrefetcher
+
+    B = 8
+    datas = [O.synthetic_batch(B, s, (32, 94)) for s in (1, 2, 3, 4, 5)]
+    batches = []
+    for d in datas:
+        b = make_batch(d, B)
+        batches.append({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()})
+    pf = DevicePrefetcher(iter(batches), DEV, depth=1)
+    n = 0
+    for host, dev_b in zip(batches, pf):
+        for k, v in host.items():
+            if torch.is_tensor(v):
+                assert dev_b[k].is_cuda and torch.equal(dev_b[k].cpu(), v), k
+            else:
+                assert dev_b[k] == v
+        n += 1
+    assert n == len(batches) and pf.h2d_bytes == sum(v.numel() * v.element_size() for b in batches for v in b.values() if torch.is_tensor(v))
+    losses = []
+    for use_pf in (False, True):
+        model = build(dropout=0.0)
+        opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
+        it = DevicePrefetcher(iter(batches), DEV) if use_pf else iter(batches)
+        losses.append([model.train_step(b, opt, LOSS, torch.device(DEV), None)["loss"] for b in it])
+    assert np.allclose(losses[0], losses[1], rtol=2e-2, atol=2e-2), losses
