@@ -13,7 +13,7 @@ using namespace mml;
 
 namespace {
 
-constexpr int SPC = 2;          // samples per CTA (B/2 CTAs: one per SM at B = 256..296)
+constexpr int SPC = 4;          // samples per CTA of the MLP kernels (every CTA streams the 132 KB of MLP weights once)
 constexpr int kHeadThreads = 256;
 constexpr int kMaxFeat = 1024;  // FA + FI
 constexpr int kMaxEmb = 512;    // EA + EI
@@ -40,51 +40,173 @@ HeadDims dims_of(const mml_head_params* p) {
   return d;
 }
 
-// out[s][o] = act(b[o] + sum_k in[s][k] * W[o][k]) for the CTA's SPC samples.  A warp owns OPW output neurons per pass (OPW
-// independent coalesced weight-row streams in flight), lanes split K, shuffles reduce.
-constexpr int OPW = 4;
+// out[s][o] = act(b[o] + sum_k in[s][k] * W[o][k]) for the CTA's SPC samples.
+// Thread -> (output neuron o, k-slice kq): consecutive threads own consecutive outputs and the same k range, so the
+// activation reads are shared-memory broadcasts and every thread walks its own weight row in 16-byte steps (the 128-byte
+// lines stay in L1 for the next steps).  Loads are issued in explicit batches of 8 x float4 before any FMA touches them:
+// the first version (a warp per output, shuffle reduction, loads interleaved with their dependent FMAs) was a chain of
+// exposed L2 latencies -- 48 us forward / 86 us backward for 256 samples.  Partials of the k-slices meet in ``red``.
+__device__ __forceinline__ int pow2_slices(int n_items, int n_reduce) {
+  int q = 1;
+  while (q * 2 * n_items <= kHeadThreads && n_reduce / (q * 2) >= 8) q *= 2;
+  return q;
+}
+
 template <bool RELU>
 __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const float* __restrict__ bias, int n_out, int n_in,
-                                            const float* in_s, int in_ld, float* out_s, int out_ld, int out_off) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int o0 = warp * OPW; o0 < n_out; o0 += (kHeadThreads / 32) * OPW) {
-    float acc[OPW][SPC];
+                                            const float* in_s, int in_ld, float* out_s, int out_ld, int out_off, float* red) {
+  const int KQ = pow2_slices(n_out, n_in);
+  const int per = kHeadThreads / KQ;  // outputs per pass
+  const int ol = threadIdx.x % per, kq = threadIdx.x / per;
+  const int klen = ((n_in + KQ - 1) / KQ + 3) & ~3;
+  const int k0 = kq * klen, k1 = min(n_in, k0 + klen);
+  const bool vec = (n_in & 3) == 0 && (in_ld & 3) == 0 && ((size_t)in_s & 15) == 0 && ((size_t)W & 15) == 0;
+  for (int o0 = 0; o0 < n_out; o0 += per) {
+    const int o = o0 + ol;
+    float acc[SPC];
 #pragma unroll
-    for (int u = 0; u < OPW; ++u)
+    for (int s = 0; s < SPC; ++s) acc[s] = 0.f;
+    if (o < n_out) {
+      const float* wr = W + (size_t)o * n_in;
+      if (vec) {
+        for (int k = k0; k < k1; k += 32) {
+          float4 wv[8];
 #pragma unroll
-      for (int s = 0; s < SPC; ++s) acc[u][s] = 0.f;
-#pragma unroll 2
-    for (int k = lane; k < n_in; k += 32) {
-      float xv[SPC];
+          for (int u = 0; u < 8; ++u) wv[u] = k + 4 * u < k1 ? __ldg(reinterpret_cast<const float4*>(wr + k + 4 * u)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int s = 0; s < SPC; ++s) xv[s] = in_s[s * in_ld + k];
+          for (int u = 0; u < 8; ++u) {
+            if (k + 4 * u < k1) {
 #pragma unroll
-      for (int u = 0; u < OPW; ++u) {
-        const int o = min(o0 + u, n_out - 1);
-        const float wv = __ldg(W + (size_t)o * n_in + k);
+              for (int s = 0; s < SPC; ++s) {
+                const float4 xv = *reinterpret_cast<const float4*>(in_s + s * in_ld + k + 4 * u);
+                acc[s] = fmaf(xv.x, wv[u].x, fmaf(xv.y, wv[u].y, fmaf(xv.z, wv[u].z, fmaf(xv.w, wv[u].w, acc[s]))));
+              }
+            }
+          }
+        }
+      } else {
+        for (int k = k0; k < k1; ++k) {
+          const float wv = __ldg(wr + k);
 #pragma unroll
-        for (int s = 0; s < SPC; ++s) acc[u][s] = fmaf(xv[s], wv, acc[u][s]);
+          for (int s = 0; s < SPC; ++s) acc[s] = fmaf(in_s[s * in_ld + k], wv, acc[s]);
+        }
       }
     }
+    if (KQ > 1) {
 #pragma unroll
-    for (int u = 0; u < OPW; ++u)
+      for (int s = 0; s < SPC; ++s) red[threadIdx.x * SPC + s] = acc[s];
+      __syncthreads();
+      if (kq == 0) {
+        for (int q = 1; q < KQ; ++q)
 #pragma unroll
-      for (int s = 0; s < SPC; ++s) acc[u][s] = warp_sum(acc[u][s]);
-    if (lane < OPW * SPC) {
-      const int u = lane / SPC, sidx = lane % SPC;
-      float v = 0.f;
-#pragma unroll
-      for (int uu = 0; uu < OPW; ++uu)
-#pragma unroll
-        for (int s = 0; s < SPC; ++s)
-          if (uu == u && s == sidx) v = acc[uu][s];
-      const int o = o0 + u;
-      if (o < n_out) {
-        v += __ldg(bias + o);
-        out_s[sidx * out_ld + out_off + o] = RELU ? fmaxf(v, 0.f) : v;
+          for (int s = 0; s < SPC; ++s) acc[s] += red[(q * per + ol) * SPC + s];
       }
+    }
+    if (kq == 0 && o < n_out) {
+      const float bv = __ldg(bias + o);
+#pragma unroll
+      for (int s = 0; s < SPC; ++s) {
+        const float v = acc[s] + bv;
+        out_s[s * out_ld + out_off + o] = RELU ? fmaxf(v, 0.f) : v;
+      }
+    }
+    if (KQ > 1) __syncthreads();  // ``red`` is reused by the next pass / layer
+  }
+}
+
+// ---- encoder fc layers as tiled fp32 GEMMs --------------------------------------------------------------------------
+// The two encoder fc layers hold 98 k of the head's 131 k weights.  Inside the per-sample-group kernel every CTA had to
+// stream all of them (524 KB per CTA, a chain of exposed L2 round trips); as a 32 x 32-tiled GEMM over the whole batch each
+// CTA reads 128 KB, in 8 K-chunks whose loads are all issued before the previous chunk is consumed.
+struct FcJob {
+  const float* x;     // [B][K]     (fwd: pooled features;   bwd: d emb, row pitch ldx)
+  const float* w;     // [N][K]     (fwd)  or  [K][N] row-major read as W^T (bwd)
+  const float* bias;  // [N] or null
+  float* y;           // [B][ldy] (+ column offset applied)
+  int K, N, ldx, ldy, tiles_n;
+};
+struct FcJobs {
+  FcJob j[2];
+};
+
+constexpr int kFcTile = 32, kFcChunk = 64;
+
+// y[b][n] = bias[n] + sum_k x[b][k] * w[n][k]
+__global__ void __launch_bounds__(256) fc_fwd_kernel(FcJobs jobs, int B) {
+  const FcJob J = jobs.j[blockIdx.z];
+  if ((int)blockIdx.y >= J.tiles_n) return;
+  __shared__ float xs[kFcTile][kFcChunk + 1], wsm[kFcTile][kFcChunk + 1];
+  const int tid = threadIdx.x, b0 = blockIdx.x * kFcTile, n0 = blockIdx.y * kFcTile;
+  const int tr = tid / 16, tc = tid % 16;           // micro-tile: rows tr, tr+16; columns tc, tc+16
+  const int lr = tid / 8, lc = (tid % 8) * 8;       // loader: row lr, 8 consecutive k
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float px[8], pw[8];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + lc + u;
+      px[u] = (b0 + lr < B && k < J.K) ? __ldg(J.x + (size_t)(b0 + lr) * J.ldx + k) : 0.f;
+      pw[u] = (n0 + lr < J.N && k < J.K) ? __ldg(J.w + (size_t)(n0 + lr) * J.K + k) : 0.f;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < J.K; k0 += kFcChunk) {
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) xs[lr][lc + u] = px[u], wsm[lr][lc + u] = pw[u];
+    __syncthreads();
+    if (k0 + kFcChunk < J.K) fetch(k0 + kFcChunk);
+#pragma unroll 16
+    for (int k = 0; k < kFcChunk; ++k) {
+      const float a0 = xs[tr][k], a1 = xs[tr + 16][k], w0 = wsm[tc][k], w1 = wsm[tc + 16][k];
+      acc[0][0] = fmaf(a0, w0, acc[0][0]);
+      acc[0][1] = fmaf(a0, w1, acc[0][1]);
+      acc[1][0] = fmaf(a1, w0, acc[1][0]);
+      acc[1][1] = fmaf(a1, w1, acc[1][1]);
     }
   }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int b = b0 + tr + 16 * i, n = n0 + tc + 16 * j;
+      if (b < B && n < J.N) J.y[(size_t)b * J.ldy + n] = acc[i][j] + (J.bias ? __ldg(J.bias + n) : 0.f);
+    }
+}
+
+// y[b][n] = sum_k x[b][k] * w[k][n]      (d pooled = d emb . W_fc;  K = embedding width, N = feature width)
+__global__ void __launch_bounds__(256) fc_bwd_data_kernel(FcJobs jobs, int B) {
+  const FcJob J = jobs.j[blockIdx.z];
+  if ((int)blockIdx.y >= J.tiles_n) return;
+  __shared__ float xs[kFcTile][kFcChunk + 1], wsm[kFcChunk][kFcTile + 1];
+  const int tid = threadIdx.x, b0 = blockIdx.x * kFcTile, n0 = blockIdx.y * kFcTile;
+  const int tr = tid / 16, tc = tid % 16;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < J.K; k0 += kFcChunk) {
+    __syncthreads();
+    for (int i = tid; i < kFcTile * kFcChunk; i += 256) {
+      const int r = i / kFcChunk, k = i % kFcChunk;
+      xs[r][k] = (b0 + r < B && k0 + k < J.K) ? __ldg(J.x + (size_t)(b0 + r) * J.ldx + k0 + k) : 0.f;
+      const int kk = i / kFcTile, n = i % kFcTile;  // weights: consecutive threads -> consecutive n (coalesced)
+      wsm[kk][n] = (k0 + kk < J.K && n0 + n < J.N) ? __ldg(J.w + (size_t)(k0 + kk) * J.N + n0 + n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 16
+    for (int k = 0; k < kFcChunk; ++k) {
+      const float a0 = xs[tr][k], a1 = xs[tr + 16][k], w0 = wsm[k][tc], w1 = wsm[k][tc + 16];
+      acc[0][0] = fmaf(a0, w0, acc[0][0]);
+      acc[0][1] = fmaf(a0, w1, acc[0][1]);
+      acc[1][0] = fmaf(a1, w0, acc[1][0]);
+      acc[1][1] = fmaf(a1, w1, acc[1][1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int b = b0 + tr + 16 * i, n = n0 + tc + 16 * j;
+      if (b < B && n < J.N) J.y[(size_t)b * J.ldy + n] = acc[i][j];
+    }
 }
 
 __global__ void __launch_bounds__(kHeadThreads)
@@ -92,25 +214,19 @@ head_fwd_kernel(mml_head_params p, HeadDims d, const float* __restrict__ pooledA
                 const long long* __restrict__ labels, const uint8_t* __restrict__ drop, float drop_scale, float* __restrict__ scratch,
                 float* __restrict__ logits, int* __restrict__ pred, int B) {
   extern __shared__ float sm[];
-  float* xs = sm;                          // [SPC][FA+FI]
-  float* es = xs + SPC * (d.FA + d.FI);    // [SPC][emb]
+  float* es = sm;                          // [SPC][emb]   (encoder fc outputs, computed by fc_fwd_kernel into scratch)
   float* h1 = es + SPC * d.emb();          // [SPC][H1]
   float* h2 = h1 + SPC * d.H1;             // [SPC][H2]
   float* lg = h2 + SPC * d.H2;             // [SPC][NC]
+  __shared__ float red[kHeadThreads * SPC];
   const int s0 = blockIdx.x * SPC;
-  const int F = d.FA + d.FI;
-  for (int i = threadIdx.x; i < SPC * F; i += kHeadThreads) {
-    const int s = i / F, k = i - s * F;
-    const int b = s0 + s;
-    float v = 0.f;
-    if (b < B) v = k < d.FA ? pooledA[(size_t)b * d.FA + k] : pooledI[(size_t)b * d.FI + (k - d.FA)];
-    xs[i] = v;
+  const int PS = d.per_sample();
+  for (int i = threadIdx.x; i < SPC * d.emb(); i += kHeadThreads) {
+    const int s = i / d.emb(), j = i - s * d.emb();
+    es[i] = s0 + s < B ? scratch[(size_t)(s0 + s) * PS + j] : 0.f;  // concat == column offset inside the scratch row
   }
   __syncthreads();
-  dense_layer<false>(p.fcA_w, p.fcA_b, d.EA, d.FA, xs, F, es, d.emb(), 0);
-  dense_layer<false>(p.fcI_w, p.fcI_b, d.EI, d.FI, xs + d.FA, F, es, d.emb(), d.EA);  // concat == column offset
-  __syncthreads();
-  dense_layer<true>(p.w0, p.b0, d.H1, d.emb(), es, d.emb(), h1, d.H1, 0);
+  dense_layer<true>(p.w0, p.b0, d.H1, d.emb(), es, d.emb(), h1, d.H1, 0, red);
   __syncthreads();
   if (drop != nullptr) {
     for (int i = threadIdx.x; i < SPC * d.H1; i += kHeadThreads) {
@@ -120,16 +236,11 @@ head_fwd_kernel(mml_head_params p, HeadDims d, const float* __restrict__ pooledA
     }
     __syncthreads();
   }
-  dense_layer<true>(p.w3, p.b3, d.H2, d.H1, h1, d.H1, h2, d.H2, 0);
+  dense_layer<true>(p.w3, p.b3, d.H2, d.H1, h1, d.H1, h2, d.H2, 0, red);
   __syncthreads();
-  dense_layer<false>(p.w5, p.b5, d.NC, d.H2, h2, d.H2, lg, d.NC, 0);
+  dense_layer<false>(p.w5, p.b5, d.NC, d.H2, h2, d.H2, lg, d.NC, 0, red);
   __syncthreads();
-  // save activations for backward
-  const int PS = d.per_sample();
-  for (int i = threadIdx.x; i < SPC * d.emb(); i += kHeadThreads) {
-    const int s = i / d.emb(), j = i - s * d.emb();
-    if (s0 + s < B) scratch[(size_t)(s0 + s) * PS + j] = es[i];
-  }
+  // save activations for backward (the embeddings are already in scratch)
   for (int i = threadIdx.x; i < SPC * d.H1; i += kHeadThreads) {
     const int s = i / d.H1, j = i - s * d.H1;
     if (s0 + s < B) scratch[(size_t)(s0 + s) * PS + d.off_h1() + j] = h1[i];
@@ -185,21 +296,49 @@ __global__ void head_loss_kernel(const float* __restrict__ scratch, int PS, int 
   if (threadIdx.x == 0) loss_out[0] = sh[0] / (float)B;
 }
 
-// dst[s][i] = sum_o W[o][i] * src[s][o]   (W^T product; thread per input column i, coalesced over i)
+// dst[s][i] = sum_o W[o][i] * src[s][o]   (W^T product).  Thread -> (input column i, o-slice): consecutive threads read
+// consecutive columns of a weight row (coalesced), 16 rows per explicit load batch; o-slices meet in ``red``.
 __device__ __forceinline__ void dense_layer_t(const float* __restrict__ W, int n_out, int n_in, const float* src_s, int src_ld,
-                                              float* dst_s, int dst_ld) {
-  for (int i = threadIdx.x; i < n_in; i += kHeadThreads) {
+                                              float* dst_s, int dst_ld, float* red) {
+  const int OQ = pow2_slices(n_in, n_out);
+  const int per = kHeadThreads / OQ;  // columns per pass
+  const int il = threadIdx.x % per, oq = threadIdx.x / per;
+  const int olen = (n_out + OQ - 1) / OQ;
+  const int o0 = oq * olen, o1 = min(n_out, o0 + olen);
+  for (int i0 = 0; i0 < n_in; i0 += per) {
+    const int i = i0 + il;
     float acc[SPC];
 #pragma unroll
     for (int s = 0; s < SPC; ++s) acc[s] = 0.f;
-#pragma unroll 8
-    for (int o = 0; o < n_out; ++o) {
-      const float wv = __ldg(W + (size_t)o * n_in + i);
+    if (i < n_in) {
+      for (int o = o0; o < o1; o += 16) {
+        float wv[16];
 #pragma unroll
-      for (int s = 0; s < SPC; ++s) acc[s] = fmaf(src_s[s * src_ld + o], wv, acc[s]);
+        for (int u = 0; u < 16; ++u) wv[u] = o + u < o1 ? __ldg(W + (size_t)(o + u) * n_in + i) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          if (o + u < o1) {
+#pragma unroll
+            for (int s = 0; s < SPC; ++s) acc[s] = fmaf(src_s[s * src_ld + o + u], wv[u], acc[s]);
+          }
+        }
+      }
     }
+    if (OQ > 1) {
 #pragma unroll
-    for (int s = 0; s < SPC; ++s) dst_s[s * dst_ld + i] = acc[s];
+      for (int s = 0; s < SPC; ++s) red[threadIdx.x * SPC + s] = acc[s];
+      __syncthreads();
+      if (oq == 0) {
+        for (int q = 1; q < OQ; ++q)
+#pragma unroll
+          for (int s = 0; s < SPC; ++s) acc[s] += red[(q * per + il) * SPC + s];
+      }
+    }
+    if (oq == 0 && i < n_in) {
+#pragma unroll
+      for (int s = 0; s < SPC; ++s) dst_s[s * dst_ld + i] = acc[s];
+    }
+    if (OQ > 1) __syncthreads();
   }
 }
 
@@ -212,7 +351,7 @@ head_bwd_data_kernel(mml_head_params p, HeadDims d, const long long* __restrict_
   float* dh2 = dlog + SPC * d.NC;         // [SPC][H2]
   float* dh1 = dh2 + SPC * d.H2;          // [SPC][H1]
   float* demb = dh1 + SPC * d.H1;         // [SPC][emb]
-  float* dpool = demb + SPC * d.emb();    // [SPC][max(FA,FI)]
+  __shared__ float red[kHeadThreads * SPC];
   const int s0 = blockIdx.x * SPC;
   const int PS = d.per_sample();
   const float invB = loss_scale / (float)B;
@@ -228,7 +367,7 @@ head_bwd_data_kernel(mml_head_params p, HeadDims d, const long long* __restrict_
     dlog[i] = g;
   }
   __syncthreads();
-  dense_layer_t(p.w5, d.NC, d.H2, dlog, d.NC, dh2, d.H2);
+  dense_layer_t(p.w5, d.NC, d.H2, dlog, d.NC, dh2, d.H2, red);
   __syncthreads();
   for (int i = threadIdx.x; i < SPC * d.H2; i += kHeadThreads) {
     const int s = i / d.H2, j = i - s * d.H2;
@@ -241,7 +380,7 @@ head_bwd_data_kernel(mml_head_params p, HeadDims d, const long long* __restrict_
     dh2[i] = g;
   }
   __syncthreads();
-  dense_layer_t(p.w3, d.H2, d.H1, dh2, d.H2, dh1, d.H1);
+  dense_layer_t(p.w3, d.H2, d.H1, dh2, d.H2, dh1, d.H1, red);
   __syncthreads();
   for (int i = threadIdx.x; i < SPC * d.H1; i += kHeadThreads) {
     const int s = i / d.H1, j = i - s * d.H1;
@@ -256,25 +395,11 @@ head_bwd_data_kernel(mml_head_params p, HeadDims d, const long long* __restrict_
     dh1[i] = g;
   }
   __syncthreads();
-  dense_layer_t(p.w0, d.H1, d.emb(), dh1, d.H1, demb, d.emb());
+  dense_layer_t(p.w0, d.H1, d.emb(), dh1, d.H1, demb, d.emb(), red);
   __syncthreads();
   for (int i = threadIdx.x; i < SPC * d.emb(); i += kHeadThreads) {
     const int s = i / d.emb(), j = i - s * d.emb();
     if (s0 + s < B) scratch[(size_t)(s0 + s) * PS + d.off_demb() + j] = demb[i];
-  }
-  const int FM = d.FA > d.FI ? d.FA : d.FI;
-  dense_layer_t(p.fcA_w, d.EA, d.FA, demb, d.emb(), dpool, FM);
-  __syncthreads();
-  for (int i = threadIdx.x; i < SPC * d.FA; i += kHeadThreads) {
-    const int s = i / d.FA, k = i - s * d.FA;
-    if (s0 + s < B) dpooledA[(size_t)(s0 + s) * d.FA + k] = dpool[s * FM + k];
-  }
-  __syncthreads();
-  dense_layer_t(p.fcI_w, d.EI, d.FI, demb + d.EA, d.emb(), dpool, FM);
-  __syncthreads();
-  for (int i = threadIdx.x; i < SPC * d.FI; i += kHeadThreads) {
-    const int s = i / d.FI, k = i - s * d.FI;
-    if (s0 + s < B) dpooledI[(size_t)(s0 + s) * d.FI + k] = dpool[s * FM + k];
   }
 }
 
@@ -375,7 +500,7 @@ int mml_head_fwd(mml_ctx* ctx, const mml_head_params* p, const float* pooledA, c
   MML_REQUIRE(ctx, pooledA && pooledI && scratch && logits && pred && B >= 1, "head_fwd: bad arguments");
   MML_REQUIRE(ctx, labels == nullptr || loss_out != nullptr, "head_fwd: labels given without loss_out");
   const HeadDims d = dims_of(p);
-  const int smem = SPC * (d.FA + d.FI + d.emb() + d.H1 + d.H2 + d.NC) * (int)sizeof(float);
+  const int smem = SPC * (d.emb() + d.H1 + d.H2 + d.NC) * (int)sizeof(float);
   static bool configured = false;
   if (!configured) {
     MML_CHECK_CUDA(ctx, cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -384,6 +509,15 @@ int mml_head_fwd(mml_ctx* ctx, const mml_head_params* p, const float* pooledA, c
   }
   MML_REQUIRE(ctx, smem <= 96 * 1024, "head_fwd: dims need %d bytes of shared memory", smem);
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    FcJobs jobs;
+    const int PS = d.per_sample();
+    jobs.j[0] = {pooledA, p->fcA_w, p->fcA_b, scratch, d.FA, d.EA, d.FA, PS, (int)mml_ceil_div(d.EA, kFcTile)};
+    jobs.j[1] = {pooledI, p->fcI_w, p->fcI_b, scratch + d.EA, d.FI, d.EI, d.FI, PS, (int)mml_ceil_div(d.EI, kFcTile)};
+    const int ty = jobs.j[0].tiles_n > jobs.j[1].tiles_n ? jobs.j[0].tiles_n : jobs.j[1].tiles_n;
+    fc_fwd_kernel<<<dim3((unsigned)mml_ceil_div(B, kFcTile), ty, 2), 256, 0, st>>>(jobs, B);
+    MML_LAUNCHED(ctx);
+  }
   head_fwd_kernel<<<(B + SPC - 1) / SPC, kHeadThreads, smem, st>>>(*p, d, pooledA, pooledI, (const long long*)labels, dropout_mask,
                                                                   dropout_scale, scratch, logits, pred, B);
   MML_LAUNCHED(ctx);
@@ -404,14 +538,20 @@ int mml_head_bwd(mml_ctx* ctx, const mml_head_params* p, const mml_head_grads* g
               "head_bwd: null gradient pointer");
 
   const HeadDims d = dims_of(p);
-  const int FM = d.FA > d.FI ? d.FA : d.FI;
-  const int smem = SPC * (d.NC + d.H2 + d.H1 + d.emb() + FM) * (int)sizeof(float);
+  const int smem = SPC * (d.NC + d.H2 + d.H1 + d.emb()) * (int)sizeof(float);
   MML_REQUIRE(ctx, smem <= 96 * 1024, "head_bwd: dims need %d bytes of shared memory", smem);
   cudaStream_t st = (cudaStream_t)stream;
   MML_REQUIRE(ctx, phases >= 1 && phases <= 3, "head_bwd: phases must be 1 (data), 2 (weights) or 3 (both)");
   if (phases & 1) {
     head_bwd_data_kernel<<<(B + SPC - 1) / SPC, kHeadThreads, smem, st>>>(*p, d, (const long long*)labels, dropout_mask, dropout_scale,
                                                                          scratch, loss_scale, dpooledA, dpooledI, B);
+    MML_LAUNCHED(ctx);
+    FcJobs jobs;
+    const int PS = d.per_sample();
+    jobs.j[0] = {scratch + d.off_demb(), p->fcA_w, nullptr, dpooledA, d.EA, d.FA, PS, d.FA, (int)mml_ceil_div(d.FA, kFcTile)};
+    jobs.j[1] = {scratch + d.off_demb() + d.EA, p->fcI_w, nullptr, dpooledI, d.EI, d.FI, PS, d.FI, (int)mml_ceil_div(d.FI, kFcTile)};
+    const int ty = jobs.j[0].tiles_n > jobs.j[1].tiles_n ? jobs.j[0].tiles_n : jobs.j[1].tiles_n;
+    fc_bwd_data_kernel<<<dim3((unsigned)mml_ceil_div(B, kFcTile), ty, 2), 256, 0, st>>>(jobs, B);
     MML_LAUNCHED(ctx);
   }
   if (!(phases & 2)) return MML_OK;

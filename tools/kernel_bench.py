@@ -59,6 +59,23 @@ def conv(N, H, W, C, K, R, st, pad, tag=""):
     print(f"conv {tag:10s} N={N} {H}x{W} C={C} K={K} R={R} s={st}: fprop {tf:6.1f} us ({fl / tf / 1e6:6.0f} TF)  dgrad {td:6.1f} us ({fl / td / 1e6:6.0f} TF)  wgrad {tw:6.1f} us ({fl / tw / 1e6:6.0f} TF)")
 
 
+def head(B):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    r = lambda *sh: torch.randn(*sh, device="cuda", generator=g) * 0.05
+    ws = [r(64, 512), r(64), r(128, 512), r(128), r(128, 192), r(128), r(64, 128), r(64), r(10, 64), r(10)]
+    gs = [torch.zeros_like(w) for w in ws]
+    hp, hg = ops.head_params(*ws), ops.head_grads(*gs)
+    pa, pi = r(B, 512).abs(), r(B, 512).abs()
+    labels = torch.randint(0, 10, (B,), device="cuda")
+    scratch = torch.zeros(B, ops.head_scratch_per_sample(hp), device="cuda")
+    logits, loss, pred = torch.zeros(B, 10, device="cuda"), torch.zeros(1, device="cuda"), torch.zeros(B, device="cuda", dtype=torch.int32)
+    da, di = torch.zeros(B, 512, device="cuda"), torch.zeros(B, 512, device="cuda")
+    f = timeit(lambda: ops.head_fwd(hp, pa, pi, labels, None, 1.0, scratch, logits, loss, pred))
+    b1 = timeit(lambda: ops.head_bwd(hp, hg, pa, pi, labels, None, 1.0, scratch, 1.0, da, di, phases=1))
+    b2 = timeit(lambda: ops.head_bwd(hp, hg, pa, pi, labels, None, 1.0, scratch, 1.0, da, di, phases=2))
+    print(f"head B={B}: fwd(+loss) {f:.1f} us, bwd data {b1:.1f} us, bwd weights {b2:.1f} us")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     B = 256
@@ -77,6 +94,8 @@ if __name__ == "__main__":
         conv(B, 4, 4, 128, 128, 3, 1, 1, "i.l2")
         conv(B, 2, 2, 256, 256, 3, 1, 1, "i.l3")
         conv(B, 1, 1, 512, 512, 3, 1, 1, "i.l4")
+    if what in ("all", "head"):
+        head(B)
     if what == "l1":
         conv(B, 28, 28, 64, 64, 3, 1, 1, "a.l1")
     if what == "l2":
