@@ -158,10 +158,12 @@ int mml_dropout_mask(mml_ctx*, uint8_t* mask, int64_t n, float p, uint64_t seed,
  * (nn.Linear's [out][in] weight IS the K,R,S,C layout).  A bias is carried as one more input column: activations have a
  * constant 1 at column `in`, the weight row has the bias there (row pitch rounded up to 64), so fprop adds it and wgrad
  * produces its gradient.  The entry points below are everything between those GEMMs. */
-enum { MML_BN1D_INPUT = 0, MML_BN1D_GATED = 1, MML_BN1D_MAXOUT = 2 };
+enum { MML_BN1D_INPUT = 0, MML_BN1D_GATED = 1, MML_BN1D_MAXOUT = 2, MML_BN1D_MAX2 = 3 };
 /* nn.BatchNorm1d over the batch (mmimdb.py:38,43,46,80) fused with the op that PRODUCES its input:
  *   INPUT : v[b][c] = x[b*ldx + c] * mask[b]        missing-modality mask (base_dataset.py:71); mask may be NULL
- *   GATED : v = gate[b]*h1 + (1-gate[b])*h2         GatedBiModalNetwork.forward, gated_bimodal.py:59 (fp32 [B][C])
+ *   GATED : v = gate[b]*h1 + (1-gate[b])*h2         GatedBiModalNetwork.forward, gated_bimodal.py:59 (fp32 [B][C]);
+ *           with gate == NULL: v = mix_a*h1 + mix_b*h2  (MultimodalPooling "avg" = .5/.5, "sum" = 1/1; pooling.py:105-111)
+ *   MAX2  : v = max(h1, h2)                          MultimodalPooling "max" (pooling.py:101-103)
  *   MAXOUT: v = max(pre[b][c], pre[b][C+c]) * (keep ? keep[b][c]*keep_scale : 1)   MaxOut (maxout.py:37-41) + Dropout;
  *           pre bf16 [B][2C] = both units' GEMM output side by side; keep uint8 [B][C] or NULL
  * train != 0: batch statistics (biased variance), running statistics updated with the unbiased one; else running stats.
@@ -171,13 +173,14 @@ typedef struct mml_bn1d_desc {
   int32_t mode, B, C, train;
   const float* x; const float* mask; int64_t ldx;
   const float* h1; const float* h2; const float* gate;
-  const uint16_t* pre; const uint8_t* keep; float keep_scale; float momentum; float eps; float reserved;
+  const uint16_t* pre; const uint8_t* keep; float keep_scale; float momentum; float eps; float mix_a; float mix_b; float reserved;
   const float* gamma; const float* beta; float* running_mean; float* running_var;
   float* xhat; float* invstd; uint16_t* y_bf16; int64_t ldy; float* y_f32;
 } mml_bn1d_desc;
 int mml_bn1d_fwd(mml_ctx*, const mml_bn1d_desc*, void* stream);
 /* backward of the same: dy bf16 rows (pitch lddy) -> dgamma, dbeta [C] (stored, not accumulated) and
- *   INPUT : nothing else;  GATED: dz fp32 [B][C];  MAXOUT: dpre bf16 [B][2C] (winner takes the gradient, ties split). */
+ *   INPUT : nothing else;  GATED / MAX2: dz fp32 [B][C] (gradient of the mixed value, routed on by mml_gmu_bwd /
+ *   mml_pool_bwd);  MAXOUT: dpre bf16 [B][2C] (winner takes the gradient, ties split). */
 typedef struct mml_bn1d_bwd_desc {
   int32_t mode, B, C, reserved;
   const uint16_t* dy; int64_t lddy; const float* xhat; const float* gamma; const float* invstd;
@@ -192,6 +195,15 @@ int mml_gmu_fwd(mml_ctx*, const uint16_t* h1pre, const uint16_t* h2pre, const fl
                 int H, void* stream);
 int mml_gmu_bwd(mml_ctx*, const float* dz, const float* h1, const float* h2, const float* gate, const float* wz, float* dwz,
                 uint16_t* dh1pre, uint16_t* dh2pre, int B, int H, void* stream);
+/* MultimodalPooling branches (pooling.py:92-98): h = dropout(tanh(pre + bias)) for both modalities; pre bf16 [B][H] (GEMM
+ * outputs of proj_a / proj_b), keep uint8 [B][H] or NULL, outputs fp32 [B][H] (consumed by mml_bn1d_fwd GATED / MAX2).
+ * Backward: dz fp32 [B][H] (from mml_bn1d_bwd) -> dpre bf16 for both branches + bias gradients [H] (stored).
+ * kind: 0 = max (winner takes the gradient, ties split), 1 = linear mix with mix_a / mix_b. */
+int mml_pool_fwd(mml_ctx*, const uint16_t* pre_a, const uint16_t* pre_b, const float* bias_a, const float* bias_b, const uint8_t* keep_a,
+                 const uint8_t* keep_b, float keep_scale, float* h_a, float* h_b, int B, int H, void* stream);
+int mml_pool_bwd(mml_ctx*, const float* dz, const float* h_a, const float* h_b, const uint8_t* keep_a, const uint8_t* keep_b,
+                 float keep_scale, int kind, float mix_a, float mix_b, uint16_t* dpre_a, uint16_t* dpre_b, float* dbias_a,
+                 float* dbias_b, int B, int H, void* stream);
 /* classifier tail (mmimdb.py:47, loss.py:52, mmimdb.py:238-239): logits = xn W^T + b, loss = mean BCE-with-logits over
  * B x NC, dlogits = (sigmoid - y) * grad_scale / (B NC), pred = sigmoid(logit) > threshold.  labels / loss / dlogits /
  * pred are optional; scratch: mml_bce_head_scratch_floats(B) floats, zero-initialised once by the caller. */

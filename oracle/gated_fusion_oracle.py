@@ -63,6 +63,67 @@ def init_mmimdb_state(image_dim: int = 4096, text_dim: int = 300, embed: int = 5
     return st
 
 
+def init_mmimdb_pooling_state(pooling_type: str = "max", image_dim: int = 4096, text_dim: int = 300, embed: int = 512, hidden: int = 512,
+                              classes: int = 23, pool_hidden: int = 512) -> "OrderedDict[str, Tensor]":
+    """MMIMDb(..., multimodal_pooling={...}) (mmimdb.py:132-146, pooling.py:17-74).  RNG order of mmimdb_pooling.yaml: the two
+    encoders and the classifier are built by the YAML loader, MultimodalPooling inside MMIMDb.__init__ afterwards; the
+    state_dict order is registration order (image_model, text_model, fusion_module, mm_mlp)."""
+    enc: "OrderedDict[str, Tensor]" = OrderedDict()
+    for prefix, d in (("image_model", image_dim), ("text_model", text_dim)):
+        _bn_entries(enc, prefix + ".net.0", d)
+        enc[prefix + ".net.1.weight"], enc[prefix + ".net.1.bias"] = _linear_params(embed, d)
+    mlp: "OrderedDict[str, Tensor]" = OrderedDict()
+    _bn_entries(mlp, "mm_mlp.net.0", embed)
+    mlp["mm_mlp.net.1.layers.0.weight"] = _linear_nobias(hidden, embed)
+    mlp["mm_mlp.net.1.layers.1.weight"] = _linear_nobias(hidden, embed)
+    _bn_entries(mlp, "mm_mlp.net.3", hidden)
+    mlp["mm_mlp.net.4.layers.0.weight"] = _linear_nobias(hidden, hidden)
+    mlp["mm_mlp.net.4.layers.1.weight"] = _linear_nobias(hidden, hidden)
+    _bn_entries(mlp, "mm_mlp.net.6", hidden)
+    mlp["mm_mlp.net.7.weight"], mlp["mm_mlp.net.7.bias"] = _linear_params(classes, hidden)
+    fus: "OrderedDict[str, Tensor]" = OrderedDict()
+    fus["fusion_module.proj_a.weight"], fus["fusion_module.proj_a.bias"] = _linear_params(embed, embed)
+    fus["fusion_module.proj_b.weight"], fus["fusion_module.proj_b.bias"] = _linear_params(embed, embed)
+    pt = pooling_type.lower()
+    if pt == "attention":
+        fus["fusion_module.attention_layer.0.weight"], fus["fusion_module.attention_layer.0.bias"] = _linear_params(pool_hidden, 2 * embed)
+        fus["fusion_module.attention_layer.2.weight"], fus["fusion_module.attention_layer.2.bias"] = _linear_params(2, pool_hidden)
+    elif pt == "gated":
+        fus["fusion_module.gate_layer.0.weight"], fus["fusion_module.gate_layer.0.bias"] = _linear_params(pool_hidden, 2 * embed)
+        fus["fusion_module.gate_layer.2.weight"], fus["fusion_module.gate_layer.2.bias"] = _linear_params(1, pool_hidden)
+    st: "OrderedDict[str, Tensor]" = OrderedDict()
+    for part in (enc, fus, mlp):
+        st.update(part)
+    return st
+
+
+def pooling_fusion(st: Dict[str, Tensor], ei: Tensor, et: Tensor, pooling_type: str, training: bool,
+                   pool_masks: Optional[Tuple[Tensor, Tensor]], pool_p: float, q: bool) -> Tensor:
+    """MultimodalPooling.forward (pooling.py:76-126)."""
+    a = torch.tanh(_qg(_q(F.linear(ei, _qw(st["fusion_module.proj_a.weight"], q)), q), q) + st["fusion_module.proj_a.bias"])
+    b = torch.tanh(_qg(_q(F.linear(et, _qw(st["fusion_module.proj_b.weight"], q)), q), q) + st["fusion_module.proj_b.bias"])
+    if training and pool_masks is not None and pool_p > 0:
+        a = a * pool_masks[0] / (1.0 - pool_p)
+        b = b * pool_masks[1] / (1.0 - pool_p)
+    pt = pooling_type.lower()
+    if pt == "max":
+        return torch.max(a, b)
+    if pt in ("avg", "average"):
+        return (a + b) / 2
+    if pt == "sum":
+        return a + b
+    combined = torch.cat([a, b], dim=1)
+    if pt == "attention":
+        h = torch.tanh(F.linear(combined, st["fusion_module.attention_layer.0.weight"], st["fusion_module.attention_layer.0.bias"]))
+        att = torch.softmax(F.linear(h, st["fusion_module.attention_layer.2.weight"], st["fusion_module.attention_layer.2.bias"]), dim=1)
+        return att[:, 0:1] * a + att[:, 1:2] * b
+    if pt == "gated":
+        h = torch.tanh(F.linear(combined, st["fusion_module.gate_layer.0.weight"], st["fusion_module.gate_layer.0.bias"]))
+        gate = torch.sigmoid(F.linear(h, st["fusion_module.gate_layer.2.weight"], st["fusion_module.gate_layer.2.bias"]))
+        return gate * a + (1 - gate) * b
+    raise ValueError(f"Unknown pooling type: {pooling_type}")
+
+
 def is_parameter(key: str) -> bool:
     return not key.endswith(("running_mean", "running_var", "num_batches_tracked"))
 
@@ -80,7 +141,8 @@ def _bn1d(st: Dict[str, Tensor], prefix: str, x: Tensor, training: bool) -> Tens
 
 def gated_fusion_forward(st: Dict[str, Tensor], I: Tensor, T: Tensor, training: bool,
                          dropout_masks: Optional[Tuple[Tensor, Tensor]] = None, emulate_bf16: bool = False,
-                         taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
+                         taps: Optional[Dict[str, Tensor]] = None, pooling_type: Optional[str] = None,
+                         pool_masks: Optional[Tuple[Tensor, Tensor]] = None, pool_p: float = 0.0) -> Tensor:
     """logits [B, classes].  ``dropout_masks`` = two {0,1} keep-masks [B, hidden] (train mode; None = no dropout).
     ``emulate_bf16`` rounds where the B200 path stores bf16 (GEMM operands and outputs); debugging aid only."""
     q = emulate_bf16
@@ -92,12 +154,19 @@ def gated_fusion_forward(st: Dict[str, Tensor], I: Tensor, T: Tensor, training: 
     et = _qg(_q(F.linear(xt, _qw(st["text_model.net.1.weight"], q), _qw(st["text_model.net.1.bias"], q)), q), q)
     tap("image_embedding", ei)
     tap("text_embedding", et)
+    if "fusion_module.proj_a.weight" in st:  # multimodal_pooling variant (mmimdb.py:132-146)
+        z = pooling_fusion(st, ei, et, pooling_type or "max", training, pool_masks, pool_p, q)
+        return _mlp_tail(st, z, training, dropout_masks, q, tap)
     # GMU (gated_bimodal.py:40-60): one scalar gate per sample
     h1 = torch.tanh(_qg(_q(F.linear(ei, _qw(st["fusion_module.fc_one.weight"], q)), q), q))
     h2 = torch.tanh(_qg(_q(F.linear(et, _qw(st["fusion_module.fc_two.weight"], q)), q), q))
     gate = torch.sigmoid(F.linear(torch.cat([h1, h2], dim=1), st["fusion_module.hidden_sigmoid.weight"]))
     z = gate.view(-1, 1) * h1 + (1 - gate).view(-1, 1) * h2
     tap("gate", gate)
+    return _mlp_tail(st, z, training, dropout_masks, q, tap)
+
+
+def _mlp_tail(st, z, training, dropout_masks, q, tap) -> Tensor:
     tap("fused", z)
     # MaxOut MLP (mmimdb.py:37-46)
     x = z
@@ -119,13 +188,14 @@ def total_loss(logits: Tensor, labels: Tensor) -> Tensor:
 
 def train_step(st: "OrderedDict[str, Tensor]", opt_state: Dict, I: Tensor, T: Tensor, labels: Tensor,
                dropout_masks: Optional[Tuple[Tensor, Tensor]] = None, lr: float = 1e-5, weight_decay: float = 1e-3,
-               apply_update: bool = True, emulate_bf16: bool = False, threshold: float = 0.5) -> Dict[str, object]:
+               apply_update: bool = True, emulate_bf16: bool = False, threshold: float = 0.5, pooling_type: Optional[str] = None,
+               pool_masks: Optional[Tuple[Tensor, Tensor]] = None, pool_p: float = 0.0) -> Dict[str, object]:
     """mmimdb.py:202-245 body: zero_grad, forward (train mode), BCE, backward, Adam.step, sigmoid > threshold."""
     params = {k: v for k, v in st.items() if is_parameter(k)}
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
     work = dict(st)
     work.update(leaves)
-    logits = gated_fusion_forward(work, I, T, True, dropout_masks, emulate_bf16)
+    logits = gated_fusion_forward(work, I, T, True, dropout_masks, emulate_bf16, pooling_type=pooling_type, pool_masks=pool_masks, pool_p=pool_p)
     loss = total_loss(logits, labels)
     gl = torch.autograd.grad(loss, list(leaves.values()))
     grads = dict(zip(leaves.keys(), gl))
@@ -140,8 +210,9 @@ def train_step(st: "OrderedDict[str, Tensor]", opt_state: Dict, I: Tensor, T: Te
 
 
 @torch.no_grad()
-def validation_step(st: Dict[str, Tensor], I: Tensor, T: Tensor, labels: Tensor, threshold: float = 0.5) -> Dict[str, object]:
-    logits = gated_fusion_forward(dict(st), I, T, False)
+def validation_step(st: Dict[str, Tensor], I: Tensor, T: Tensor, labels: Tensor, threshold: float = 0.5,
+                    pooling_type: Optional[str] = None) -> Dict[str, object]:
+    logits = gated_fusion_forward(dict(st), I, T, False, pooling_type=pooling_type)
     return {"loss": float(total_loss(logits, labels).item()), "logits": logits, "predictions": (torch.sigmoid(logits) > threshold).to(torch.int64)}
 
 
@@ -162,5 +233,7 @@ def synthetic_batch(batch: int, seed: int, image_dim: int = 4096, text_dim: int 
     mt = torch.tensor([PATTERNS[n][1] for n in names])
     d1 = (torch.rand(batch, hidden, generator=g) < 0.5).float()
     d2 = (torch.rand(batch, hidden, generator=g) < 0.5).float()
-    return {"image": I, "text": T, "labels": y, "pattern_name": names, "image_mask": mi, "text_mask": mt, "dropout_masks": (d1, d2),
+    pa = (torch.rand(batch, hidden, generator=g) >= 0.1).float()  # MultimodalPooling dropout 0.1 (mmimdb_pooling.yaml), one mask per branch
+    pb = (torch.rand(batch, hidden, generator=g) >= 0.1).float()
+    return {"pool_masks": (pa, pb),"image": I, "text": T, "labels": y, "pattern_name": names, "image_mask": mi, "text_mask": mt, "dropout_masks": (d1, d2),
             "image_masked": apply_missing_mask(I, mi), "text_masked": apply_missing_mask(T, mt)}

@@ -36,7 +36,7 @@ class BN1dDesc(C.Structure):
                 ("x", C.c_void_p), ("mask", C.c_void_p), ("ldx", C.c_int64),
                 ("h1", C.c_void_p), ("h2", C.c_void_p), ("gate", C.c_void_p),
                 ("pre", C.c_void_p), ("keep", C.c_void_p), ("keep_scale", C.c_float), ("momentum", C.c_float), ("eps", C.c_float),
-                ("reserved", C.c_float),
+                ("mix_a", C.c_float), ("mix_b", C.c_float), ("reserved", C.c_float),
                 ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
                 ("xhat", C.c_void_p), ("invstd", C.c_void_p), ("y_bf16", C.c_void_p), ("ldy", C.c_int64), ("y_f32", C.c_void_p)]
 
@@ -87,6 +87,8 @@ SIGNATURES = {
     "mml_bn1d_bwd": (I32, [P, C.POINTER(BN1dBwdDesc), P]),
     "mml_gmu_fwd": (I32, [P, P, P, P, P, P, P, I32, I32, P]),
     "mml_gmu_bwd": (I32, [P, P, P, P, P, P, P, P, P, I32, I32, P]),
+    "mml_pool_fwd": (I32, [P, P, P, P, P, P, P, F32, P, P, I32, I32, P]),
+    "mml_pool_bwd": (I32, [P, P, P, P, P, P, F32, I32, F32, F32, P, P, P, P, I32, I32, P]),
     "mml_bce_head_scratch_floats": (I64, [I32]),
     "mml_bce_head_fwd": (I32, [P, P, P, P, P, P, P, P, P, P, F32, F32, I32, I32, I32, P]),
     "mml_bce_head_bwd": (I32, [P, P, P, P, P, P, P, I32, I32, I32, P]),

@@ -36,9 +36,13 @@ __device__ __forceinline__ float produce(const mml_bn1d_desc& d, int b, int c) {
     const float x = d.x[(size_t)b * d.ldx + c];
     return d.mask ? mask_mul(x, d.mask[b]) : x;
   } else if (MODE == MML_BN1D_GATED) {
-    const float g = d.gate[b];
     const size_t i = (size_t)b * d.C + c;
+    if (d.gate == nullptr) return d.mix_a * d.h1[i] + d.mix_b * d.h2[i];
+    const float g = d.gate[b];
     return g * d.h1[i] + (1.f - g) * d.h2[i];
+  } else if (MODE == MML_BN1D_MAX2) {
+    const size_t i = (size_t)b * d.C + c;
+    return fmaxf(d.h1[i], d.h2[i]);
   } else {
     const size_t i = (size_t)b * 2 * d.C + c;
     float v = fmaxf(bf16_val(d.pre[i]), bf16_val(d.pre[i + d.C]));
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(kCols* kRowGroups) bn1d_bwd_kernel(const mml_b
   const float k = d.gamma[c] * d.invstd[c], invB = 1.f / (float)d.B;
   auto emit = [&](int b, float dy, float xh) {
     float dv = k * (dy - sdy * invB - xh * sdyx * invB);
-    if (MODE == MML_BN1D_GATED) {
+    if (MODE == MML_BN1D_GATED || MODE == MML_BN1D_MAX2) {
       d.dz[(size_t)b * d.C + c] = dv;
     } else {
       if (d.keep) dv = d.keep[(size_t)b * d.C + c] ? dv * d.keep_scale : 0.f;
@@ -245,6 +249,67 @@ __global__ void __launch_bounds__(kGmuWarps * 32) gmu_bwd_kernel(const float* __
     for (int r = 0; r < kGmuWarps; ++r)
       if (row0 + r < B) s += s_dgp[r] * h[(size_t)(row0 + r) * H + cc];
     atomicAdd(dwz + c, s);
+  }
+}
+
+// ---- MultimodalPooling branches (pooling.py:92-98) --------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_fwd_kernel(const uint16_t* __restrict__ pre_a, const uint16_t* __restrict__ pre_b,
+                                                      const float* __restrict__ bias_a, const float* __restrict__ bias_b,
+                                                      const uint8_t* __restrict__ keep_a, const uint8_t* __restrict__ keep_b, float keep_scale,
+                                                      float* __restrict__ h_a, float* __restrict__ h_b, int B, int H) {
+  const size_t n = (size_t)B * H;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % H);
+    float a = tanhf(bf16_val(pre_a[i]) + bias_a[c]), b = tanhf(bf16_val(pre_b[i]) + bias_b[c]);
+    if (keep_a) a = keep_a[i] ? a * keep_scale : 0.f;
+    if (keep_b) b = keep_b[i] ? b * keep_scale : 0.f;
+    h_a[i] = a;
+    h_b[i] = b;
+  }
+}
+
+// column-sliced like the BatchNorm kernels: the bias gradients are batch sums, reduced inside the CTA
+__global__ void __launch_bounds__(kCols* kRowGroups) pool_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ h_a,
+                                                                    const float* __restrict__ h_b, const uint8_t* __restrict__ keep_a,
+                                                                    const uint8_t* __restrict__ keep_b, float keep_scale, int kind, float mix_a,
+                                                                    float mix_b, uint16_t* __restrict__ dpre_a, uint16_t* __restrict__ dpre_b,
+                                                                    float* __restrict__ dbias_a, float* __restrict__ dbias_b, int B, int H) {
+  __shared__ float red[kRowGroups][kCols + 1];
+  __shared__ float tot[kCols];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * kCols + tx;
+  const bool valid = c < H;
+  float sa = 0.f, sb = 0.f;
+  if (valid) {
+    const float inv_scale = 1.f / keep_scale;
+    for (int b = ty; b < B; b += kRowGroups) {
+      const size_t i = (size_t)b * H + c;
+      const float z = dz[i], a = h_a[i], o = h_b[i];
+      float da, db;
+      if (kind == 0) {  // max: winner takes the gradient, an exact tie splits it (torch.max backward)
+        da = a > o ? z : (a == o ? 0.5f * z : 0.f);
+        db = z - da;
+      } else {
+        da = z * mix_a;
+        db = z * mix_b;
+      }
+      // through dropout (h = tanh * scale where kept) and tanh
+      const bool ka = keep_a ? keep_a[i] != 0 : true, kb = keep_b ? keep_b[i] != 0 : true;
+      const float sc = keep_a ? keep_scale : 1.f, isc = keep_a ? inv_scale : 1.f;
+      const float ta = a * isc, tb = o * isc;
+      const float ga = ka ? da * sc * (1.f - ta * ta) : 0.f;
+      const float gb = kb ? db * sc * (1.f - tb * tb) : 0.f;
+      dpre_a[i] = to_bf16(ga);
+      dpre_b[i] = to_bf16(gb);
+      sa += ga;
+      sb += gb;
+    }
+  }
+  const float ta = column_total(sa, red, tot, tx, ty);
+  const float tb = column_total(sb, red, tot, tx, ty);
+  if (valid && ty == 0) {
+    dbias_a[c] = ta;
+    dbias_b[c] = tb;
   }
 }
 
@@ -411,9 +476,14 @@ int mml_bn1d_fwd(mml_ctx* ctx, const mml_bn1d_desc* d, void* stream) {
       else bn1d_fwd_kernel<MML_BN1D_INPUT, false><<<grid, block, 0, st>>>(*d);
       break;
     case MML_BN1D_GATED:
-      MML_REQUIRE(ctx, d->h1 && d->h2 && d->gate, "bn1d_fwd(GATED): h1 / h2 / gate");
+      MML_REQUIRE(ctx, d->h1 && d->h2, "bn1d_fwd(GATED): h1 / h2");
       if (reg) bn1d_fwd_kernel<MML_BN1D_GATED, true><<<grid, block, 0, st>>>(*d);
       else bn1d_fwd_kernel<MML_BN1D_GATED, false><<<grid, block, 0, st>>>(*d);
+      break;
+    case MML_BN1D_MAX2:
+      MML_REQUIRE(ctx, d->h1 && d->h2, "bn1d_fwd(MAX2): h1 / h2");
+      if (reg) bn1d_fwd_kernel<MML_BN1D_MAX2, true><<<grid, block, 0, st>>>(*d);
+      else bn1d_fwd_kernel<MML_BN1D_MAX2, false><<<grid, block, 0, st>>>(*d);
       break;
     case MML_BN1D_MAXOUT:
       MML_REQUIRE(ctx, d->pre, "bn1d_fwd(MAXOUT): pre");
@@ -439,6 +509,7 @@ int mml_bn1d_bwd(mml_ctx* ctx, const mml_bn1d_bwd_desc* d, void* stream) {
       else bn1d_bwd_kernel<MML_BN1D_INPUT, false><<<grid, block, 0, st>>>(*d);
       break;
     case MML_BN1D_GATED:
+    case MML_BN1D_MAX2:  // same kernel: both hand the gradient of the mixed value on as dz
       MML_REQUIRE(ctx, d->gamma && d->invstd && d->dz, "bn1d_bwd(GATED): gamma / invstd / dz");
       if (reg) bn1d_bwd_kernel<MML_BN1D_GATED, true><<<grid, block, 0, st>>>(*d);
       else bn1d_bwd_kernel<MML_BN1D_GATED, false><<<grid, block, 0, st>>>(*d);
@@ -468,6 +539,29 @@ int mml_gmu_bwd(mml_ctx* ctx, const float* dz, const float* h1, const float* h2,
   MML_REQUIRE(ctx, ctx && dz && h1 && h2 && gate && wz && dwz && dh1pre && dh2pre && B >= 1 && H >= 1, "gmu_bwd: bad arguments");
   gmu_bwd_kernel<<<(unsigned)mml_ceil_div(B, kGmuWarps), kGmuWarps * 32, 0, (cudaStream_t)stream>>>(dz, h1, h2, gate, wz, dwz, dh1pre, dh2pre,
                                                                                                    B, H);
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
+int mml_pool_fwd(mml_ctx* ctx, const uint16_t* pre_a, const uint16_t* pre_b, const float* bias_a, const float* bias_b, const uint8_t* keep_a,
+                 const uint8_t* keep_b, float keep_scale, float* h_a, float* h_b, int B, int H, void* stream) {
+  MML_REQUIRE(ctx, ctx && pre_a && pre_b && bias_a && bias_b && h_a && h_b && B >= 1 && H >= 1, "pool_fwd: bad arguments");
+  MML_REQUIRE(ctx, (keep_a == nullptr) == (keep_b == nullptr), "pool_fwd: both dropout masks or none");
+  int grid = (int)mml_ceil_div((int64_t)B * H, 256);
+  if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+  pool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pre_a, pre_b, bias_a, bias_b, keep_a, keep_b, keep_scale, h_a, h_b, B, H);
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
+int mml_pool_bwd(mml_ctx* ctx, const float* dz, const float* h_a, const float* h_b, const uint8_t* keep_a, const uint8_t* keep_b,
+                 float keep_scale, int kind, float mix_a, float mix_b, uint16_t* dpre_a, uint16_t* dpre_b, float* dbias_a,
+                 float* dbias_b, int B, int H, void* stream) {
+  MML_REQUIRE(ctx, ctx && dz && h_a && h_b && dpre_a && dpre_b && dbias_a && dbias_b && B >= 1 && H >= 1, "pool_bwd: bad arguments");
+  MML_REQUIRE(ctx, (keep_a == nullptr) == (keep_b == nullptr), "pool_bwd: both dropout masks or none");
+  MML_REQUIRE(ctx, kind == 0 || kind == 1, "pool_bwd: kind must be 0 (max) or 1 (linear mix)");
+  pool_bwd_kernel<<<(unsigned)mml_ceil_div(H, kCols), dim3(kCols, kRowGroups), 0, (cudaStream_t)stream>>>(
+      dz, h_a, h_b, keep_a, keep_b, keep_scale, kind, mix_a, mix_b, dpre_a, dpre_b, dbias_a, dbias_b, B, H);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }

@@ -56,9 +56,14 @@ class _GatedPlan:
         E = params["image_model.net.1.weight"].shape[0]
         H = params["mm_mlp.net.1.layers.0.weight"].shape[0]
         NC = params["mm_mlp.net.7.weight"].shape[0]
-        if params["fusion_module.fc_one.weight"].shape != (E, E) or params["fusion_module.fc_two.weight"].shape != (E, E) \
+        self.pooling = getattr(model, "fusion_type", "gated") == "pooling"
+        wa, wb = ("fusion_module.proj_a.weight", "fusion_module.proj_b.weight") if self.pooling else \
+            ("fusion_module.fc_one.weight", "fusion_module.fc_two.weight")
+        if params[wa].shape != (E, E) or params[wb].shape != (E, E) \
                 or params["mm_mlp.net.1.layers.0.weight"].shape[1] != E or params["text_model.net.1.weight"].shape[0] != E:
             raise NotImplementedError("mml_b200 gated fusion expects equal embedding / gate widths (mmimdb_baseline.yaml: 512)")
+        self.pool_type = model.fusion_module.pooling_type if self.pooling else None
+        self.pool_p = float(model.fusion_module.dropout) if self.pooling else 0.0
         if E % 64 or H % 64:
             raise NotImplementedError("embedding and hidden widths must be multiples of 64 for the tensor-core GEMMs")
         if len(model.mm_mlp.net[1].layers) != 2 or len(model.mm_mlp.net[4].layers) != 2:
@@ -88,6 +93,8 @@ class _GatedPlan:
         self.pre2, self.xh2, self.xn2 = b16(B, 2 * H), f32(B, H), f32(B, H)
         self.keep = torch.ones(2, B, H, device=dev, dtype=torch.uint8)  # both dropout masks: one generator launch
         self.keep1, self.keep2 = self.keep[0], self.keep[1]
+        self.keepAB = torch.ones(2, B, E, device=dev, dtype=torch.uint8)  # MultimodalPooling dropout, one mask per branch
+        self.keepA, self.keepB = self.keepAB[0], self.keepAB[1]
         self.inv = {k: f32(n) for k, n in (("I", DI), ("T", DT), ("0", E), ("1", H), ("2", H))}
         self.logits, self.dlogits = f32(B, NC), f32(B, NC)
         self.loss = f32(1)
@@ -138,8 +145,14 @@ class _GatedPlan:
                                        y_bf16=self.xnI, **kw)
         self.f_bnT = ops.bn1d_fwd_desc(ops.BN1D_INPUT, B, self.DT, gT, bT, rmT, rvT, x=self.xT, mask=self.mT, xhat=self.xhT, invstd=self.inv["T"],
                                        y_bf16=self.xnT, **kw)
-        self.f_bn0 = ops.bn1d_fwd_desc(ops.BN1D_GATED, B, E, g0, b0, rm0, rv0, h1=self.h1, h2=self.h2, gate=self.gate, xhat=self.xh0,
-                                       invstd=self.inv["0"], y_bf16=self.xn0, **kw)
+        if not self.pooling:
+            self.f_bn0 = ops.bn1d_fwd_desc(ops.BN1D_GATED, B, E, g0, b0, rm0, rv0, h1=self.h1, h2=self.h2, gate=self.gate, xhat=self.xh0,
+                                           invstd=self.inv["0"], y_bf16=self.xn0, **kw)
+        else:  # pooling.py:100-111: max | (a + b) / 2 | a + b
+            self.mix = {"max": (1.0, 1.0), "avg": (0.5, 0.5), "average": (0.5, 0.5), "sum": (1.0, 1.0)}[self.pool_type]
+            mode0 = ops.BN1D_MAX2 if self.pool_type == "max" else ops.BN1D_GATED
+            self.f_bn0 = ops.bn1d_fwd_desc(mode0, B, E, g0, b0, rm0, rv0, h1=self.h1, h2=self.h2, xhat=self.xh0, invstd=self.inv["0"],
+                                           y_bf16=self.xn0, mix_a=self.mix[0], mix_b=self.mix[1], **kw)
         self.f_bn1 = ops.bn1d_fwd_desc(ops.BN1D_MAXOUT, B, H, g1, b1, rm1, rv1, pre=self.pre1, keep=self.keep1, keep_scale=scale, xhat=self.xh1,
                                        invstd=self.inv["1"], y_bf16=self.xn1, **kw)
         self.f_bn2 = ops.bn1d_fwd_desc(ops.BN1D_MAXOUT, B, H, g2, b2, rm2, rv2, pre=self.pre2, keep=self.keep2, keep_scale=scale, xhat=self.xh2,
@@ -148,7 +161,7 @@ class _GatedPlan:
                                        keep_scale=scale, dpre=self.dpre2)
         self.b_bn1 = ops.bn1d_bwd_desc(ops.BN1D_MAXOUT, B, H, self.dxn1, self.xh1, g1, self.inv["1"], dg1, db1, pre=self.pre1, keep=self.keep1,
                                        keep_scale=scale, dpre=self.dpre1)
-        self.b_bn0 = ops.bn1d_bwd_desc(ops.BN1D_GATED, B, E, self.dxn0, self.xh0, g0, self.inv["0"], dg0, db0, dz=self.dz)
+        self.b_bn0 = ops.bn1d_bwd_desc(ops.BN1D_GATED, B, E, self.dxn0, self.xh0, g0, self.inv["0"], dg0, db0, dz=self.dz)  # also serves MAX2
         self.b_bnI = ops.bn1d_bwd_desc(ops.BN1D_INPUT, B, self.DI, self.dxnI, self.xhI, gI, self.inv["I"], dgI, dbI)
         self.b_bnT = ops.bn1d_bwd_desc(ops.BN1D_INPUT, B, self.DT, self.dxnT, self.xhT, gT, self.inv["T"], dgT, dbT)
         # ---- GEMMs: (geometry, weights bf16, weight gradient fp32)
@@ -157,8 +170,10 @@ class _GatedPlan:
 
         self.gemI = (gemm(LI, E), fs.aug_matrix(Wb, "image_model.net.1.weight"), fs.aug_matrix(G, "image_model.net.1.weight"))
         self.gemT = (gemm(LT, E), fs.aug_matrix(Wb, "text_model.net.1.weight"), fs.aug_matrix(G, "text_model.net.1.weight"))
-        self.gem1 = (gemm(E, E), par(Wb, "fusion_module.fc_one.weight"), par(G, "fusion_module.fc_one.weight"))
-        self.gem2 = (gemm(E, E), par(Wb, "fusion_module.fc_two.weight"), par(G, "fusion_module.fc_two.weight"))
+        n1, n2 = ("fusion_module.proj_a.weight", "fusion_module.proj_b.weight") if self.pooling else \
+            ("fusion_module.fc_one.weight", "fusion_module.fc_two.weight")
+        self.gem1 = (gemm(E, E), par(Wb, n1), par(G, n1))
+        self.gem2 = (gemm(E, E), par(Wb, n2), par(G, n2))
 
         def maxout(prefix, n_in):
             a, b = prefix + ".layers.0.weight", prefix + ".layers.1.weight"
@@ -169,7 +184,11 @@ class _GatedPlan:
 
         self.gemM1 = maxout("mm_mlp.net.1", E)
         self.gemM2 = maxout("mm_mlp.net.4", H)
-        self.wz, self.dwz = fs.flat_slice(P, "fusion_module.hidden_sigmoid.weight"), fs.flat_slice(G, "fusion_module.hidden_sigmoid.weight")
+        if self.pooling:
+            self.pb = (par(P, "fusion_module.proj_a.bias"), par(P, "fusion_module.proj_b.bias"))
+            self.dpb = (par(G, "fusion_module.proj_a.bias"), par(G, "fusion_module.proj_b.bias"))
+        else:
+            self.wz, self.dwz = fs.flat_slice(P, "fusion_module.hidden_sigmoid.weight"), fs.flat_slice(G, "fusion_module.hidden_sigmoid.weight")
         self.w7, self.b7 = par(P, "mm_mlp.net.7.weight"), par(P, "mm_mlp.net.7.bias")
         self.dw7, self.db7 = par(G, "mm_mlp.net.7.weight"), par(G, "mm_mlp.net.7.bias")
 
@@ -209,7 +228,12 @@ class _GatedPlan:
                     lambda: self._fprop(self.gem1, self.eI, self.h1p)],
                    [lambda: ops.bn1d_fwd(self.f_bnT, train), lambda: self._fprop(self.gemT, self.xnT, self.eT),
                     lambda: self._fprop(self.gem2, self.eT, self.h2p)])
-        ops.gmu_fwd(self.h1p, self.h2p, self.wz, self.h1, self.h2, self.gate)
+        if self.pooling:
+            drop = train and dropout and self.pool_p > 0
+            ops.pool_fwd(self.h1p, self.h2p, self.pb[0], self.pb[1], self.keepA if drop else None, self.keepB if drop else None,
+                         1.0 / (1.0 - self.pool_p), self.h1, self.h2)
+        else:
+            ops.gmu_fwd(self.h1p, self.h2p, self.wz, self.h1, self.h2, self.gate)
         ops.bn1d_fwd(self.f_bn0, train)
         self._fprop(self.gemM1, self.xn0, self.pre1)
         ops.bn1d_fwd(self.f_bn1, train, use_keep=dropout)
@@ -223,6 +247,8 @@ class _GatedPlan:
         fs.G.zero_()
         if own_dropout:
             ops.dropout_mask(self.keep, DROPOUT_P, eng.seed, fs.step)
+            if self.pooling and self.pool_p > 0:
+                ops.dropout_mask(self.keepAB, self.pool_p, eng.seed ^ 0x51ED, fs.step)
         self.run_forward(True, True, True, True)
         ops.bce_head_bwd(self.dlogits, self.xn2, self.w7, self.dw7, self.db7, self.dxn2)
         ops.bn1d_bwd(self.b_bn2)
@@ -230,7 +256,12 @@ class _GatedPlan:
         ops.bn1d_bwd(self.b_bn1)
         self._bprop(self.gemM1, self.xn0, self.dpre1, self.dxn0)
         ops.bn1d_bwd(self.b_bn0)
-        ops.gmu_bwd(self.dz, self.h1, self.h2, self.gate, self.wz, self.dwz, self.dh1p, self.dh2p)
+        if self.pooling:
+            drop = self.pool_p > 0
+            ops.pool_bwd(self.dz, self.h1, self.h2, self.keepA if drop else None, self.keepB if drop else None, 1.0 / (1.0 - self.pool_p),
+                         0 if self.pool_type == "max" else 1, self.mix[0], self.mix[1], self.dh1p, self.dh2p, self.dpb[0], self.dpb[1])
+        else:
+            ops.gmu_bwd(self.dz, self.h1, self.h2, self.gate, self.wz, self.dwz, self.dh1p, self.dh2p)
         self._fork([lambda: self._bprop(self.gem1, self.eI, self.dh1p, self.deI), lambda: self._bprop(self.gemI, self.xnI, self.deI, self.dxnI),
                     lambda: ops.bn1d_bwd(self.b_bnI)],
                    [lambda: self._bprop(self.gem2, self.eT, self.dh2p, self.deT), lambda: self._bprop(self.gemT, self.xnT, self.deT, self.dxnT),
@@ -294,5 +325,7 @@ class _GatedPlan:
     def run_forward_train_mode(self) -> None:
         eng, fs = self.eng, self.eng.fs
         ops.dropout_mask(self.keep, DROPOUT_P, eng.seed, fs.step)
+        if self.pooling and self.pool_p > 0:
+            ops.dropout_mask(self.keepAB, self.pool_p, eng.seed ^ 0x51ED, fs.step)
         self.run_forward(True, True, False, False)
         fs.NBT += 1

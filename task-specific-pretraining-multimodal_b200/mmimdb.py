@@ -5,7 +5,8 @@ Same classes and constructors as the YAML tags build them (configs/mmimdb/centra
 ``MMIMDbModalityEncoder(input_dim, output_dim)``, ``GatedBiModalNetwork(input_one_dim, input_two_dim, output_one_dim,
 output_two_dim, use_bias=False)``, ``MaxOut``, ``MLPGenreClassifier(input_size, output_size, hidden_size)`` and
 ``MMIMDb(image_encoder, text_encoder, gated_bimodal_network=..., classifier=..., binary_threshold=0.5)``; same sub-module
-names, hence the same 38-entry ``state_dict()``; same ``forward(I, T)`` / ``train_step`` / ``validation_step`` /
+names, hence the same 38-entry ``state_dict()`` (``multimodal_pooling={...}`` builds ``MultimodalPooling`` with the max /
+avg / sum pooling types instead of the GMU, mmimdb_pooling.yaml); same ``forward(I, T)`` / ``train_step`` / ``validation_step`` /
 ``get_embeddings`` / ``get_encoder`` / ``logits_transform``.  The torch modules inside are parameter CONTAINERS only (they
 give the reference's initialisation and names); the arithmetic of a step is one fused schedule in libmml_b200.so
 (``gated_engine.py``).  Unsupported requests (pooling fusion, biased GMU, embeddings as inputs, other optimizers or
@@ -53,6 +54,30 @@ class GatedBiModalNetwork(nn.Module):
         raise NotImplementedError("mml_b200.GatedBiModalNetwork is evaluated inside the fused MMIMDb step only")
 
 
+class MultimodalPooling(nn.Module):
+    """pooling.py:6-126 -- tanh(proj) of both embeddings, dropout, then an element-wise max / average / sum (container; fused
+    into the step).  The ``attention`` and ``gated`` pooling types are not built yet and raise."""
+
+    def __init__(self, input_dim_a: int, input_dim_b: int, output_dim: int, pooling_type: str = "gated", hidden_dim: Optional[int] = None,
+                 dropout: float = 0.0):
+        super().__init__()
+        self.pooling_type = pooling_type.lower()
+        if self.pooling_type in ("attention", "gated"):
+            raise NotImplementedError(f"mml_b200 MultimodalPooling: pooling_type '{pooling_type}' is not built yet (max / avg / sum are)")
+        if self.pooling_type not in ("max", "avg", "average", "sum"):
+            raise ValueError(f"Unknown pooling type: {pooling_type}")
+        self.input_dim_a, self.input_dim_b, self.output_dim = input_dim_a, input_dim_b, output_dim
+        self.hidden_dim = hidden_dim or max(input_dim_a, input_dim_b)
+        self.dropout = dropout
+        self.proj_a = nn.Linear(input_dim_a, output_dim)
+        self.proj_b = nn.Linear(input_dim_b, output_dim)
+        self.dropout_layer = nn.Dropout(dropout) if dropout > 0 else nn.Identity()
+        self.activation = nn.Tanh()
+
+    def forward(self, x_a, x_b):
+        raise NotImplementedError("mml_b200.MultimodalPooling is evaluated inside the fused MMIMDb step only")
+
+
 class MLPGenreClassifier(nn.Module):
     """mmimdb.py:20-60."""
 
@@ -91,13 +116,17 @@ class MMIMDb(nn.Module):
         super().__init__()
         self.image_model = image_encoder
         self.text_model = text_encoder
-        if multimodal_pooling is not None:
-            raise NotImplementedError("mml_b200.MMIMDb implements the GMU fusion of mmimdb_baseline.yaml; MultimodalPooling "
-                                      "(models/pooling.py) variants are not built yet")
-        if gated_bimodal_network is None:
+        if multimodal_pooling is not None:  # mmimdb.py:132-146
+            self.fusion_module = MultimodalPooling(
+                input_dim_a=image_encoder.net[-1].out_features, input_dim_b=text_encoder.net[-1].out_features, output_dim=classifier.input_size,
+                pooling_type=multimodal_pooling.get("pooling_type", "gated"), hidden_dim=multimodal_pooling.get("hidden_dim", None),
+                dropout=multimodal_pooling.get("dropout", 0.0))
+            self.fusion_type = "pooling"
+        elif gated_bimodal_network is not None:
+            self.fusion_module = gated_bimodal_network
+            self.fusion_type = "gated"
+        else:
             raise ValueError("Either gated_bimodal_network or multimodal_pooling must be provided")
-        self.fusion_module = gated_bimodal_network
-        self.fusion_type = "gated"
         self.mm_mlp = classifier
         self.binary_threshold = binary_threshold
         self.monitor = None
@@ -230,6 +259,12 @@ class MMIMDb(nn.Module):
         if given is not None:
             plan.keep1.copy_(torch.as_tensor(given[0]).reshape(plan.keep1.shape).to(torch.uint8), non_blocking=True)
             plan.keep2.copy_(torch.as_tensor(given[1]).reshape(plan.keep2.shape).to(torch.uint8), non_blocking=True)
+            pool = kwargs.get("pool_masks")
+            if plan.pooling and plan.pool_p > 0:
+                if pool is None:
+                    raise ValueError("dropout_masks given for a pooling model with dropout: pool_masks=(mask_a, mask_b) is needed too")
+                plan.keepA.copy_(torch.as_tensor(pool[0]).reshape(plan.keepA.shape).to(torch.uint8), non_blocking=True)
+                plan.keepB.copy_(torch.as_tensor(pool[1]).reshape(plan.keepB.shape).to(torch.uint8), non_blocking=True)
         plan.train_step(given_dropout=given is not None)
         fs._host_step += 1
         return self._finish(eng, plan, labels, miss_type, metric_recorder, False)

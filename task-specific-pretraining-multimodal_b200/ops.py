@@ -273,18 +273,19 @@ def launch_count(device_index: int = 0) -> int:
 
 
 # ---- MMIMDb gated late fusion (config 3) ----------------------------------------------------------------------------
-BN1D_INPUT, BN1D_GATED, BN1D_MAXOUT = 0, 1, 2
+BN1D_INPUT, BN1D_GATED, BN1D_MAXOUT, BN1D_MAX2 = 0, 1, 2, 3
 
 
 def bn1d_fwd_desc(mode: int, B: int, Cn: int, gamma, beta, rmean, rvar, *, x=None, mask=None, h1=None, h2=None, gate=None, pre=None,
-                  keep=None, keep_scale: float = 1.0, xhat=None, invstd=None, y_bf16=None, y_f32=None, momentum=0.1, eps=1e-5) -> BN1dDesc:
+                  keep=None, keep_scale: float = 1.0, xhat=None, invstd=None, y_bf16=None, y_f32=None, momentum=0.1, eps=1e-5,
+                  mix_a: float = 1.0, mix_b: float = 1.0) -> BN1dDesc:
     """Descriptor for ``bn1d_fwd`` (built once per plan; ``train`` / ``keep`` are set per launch)."""
     d = BN1dDesc()
     d.mode, d.B, d.C, d.train = mode, B, Cn, 1
     d.x, d.mask, d.ldx = _p(x, torch.float32), _p(mask, torch.float32), (x.stride(0) if x is not None else 0)
     d.h1, d.h2, d.gate = _p(h1, torch.float32), _p(h2, torch.float32), _p(gate, torch.float32)
     d.pre, d.keep, d.keep_scale = _p(pre, torch.bfloat16), _p(keep, torch.uint8), keep_scale
-    d.momentum, d.eps = momentum, eps
+    d.momentum, d.eps, d.mix_a, d.mix_b = momentum, eps, mix_a, mix_b
     d.gamma, d.beta, d.running_mean, d.running_var = (_p(t, torch.float32) for t in (gamma, beta, rmean, rvar))
     d.xhat, d.invstd = _p(xhat, torch.float32), _p(invstd, torch.float32)
     d.y_bf16, d.ldy, d.y_f32 = _p(y_bf16, torch.bfloat16), (y_bf16.stride(0) if y_bf16 is not None else 0), _p(y_f32, torch.float32)
@@ -367,3 +368,19 @@ def bce_head_bwd(dlogits, xn, w, dw, db, dxn) -> None:
     c = _ctx(xn)
     c.check(c.lib.mml_bce_head_bwd(c.handle, _p(dlogits, torch.float32), _p(xn, torch.float32), _p(w, torch.float32), _p(dw, torch.float32),
                                    _p(db, torch.float32), _p(dxn, torch.bfloat16), B, H, NC, _stream(xn)), "mml_bce_head_bwd")
+
+
+def pool_fwd(pre_a, pre_b, bias_a, bias_b, keep_a, keep_b, keep_scale: float, h_a, h_b) -> None:
+    B, H = h_a.shape
+    c = _ctx(h_a)
+    c.check(c.lib.mml_pool_fwd(c.handle, _p(pre_a, torch.bfloat16), _p(pre_b, torch.bfloat16), _p(bias_a, torch.float32), _p(bias_b, torch.float32),
+                               _p(keep_a, torch.uint8), _p(keep_b, torch.uint8), float(keep_scale), _p(h_a, torch.float32), _p(h_b, torch.float32),
+                               B, H, _stream(h_a)), "mml_pool_fwd")
+
+
+def pool_bwd(dz, h_a, h_b, keep_a, keep_b, keep_scale: float, kind: int, mix_a: float, mix_b: float, dpre_a, dpre_b, dbias_a, dbias_b) -> None:
+    B, H = h_a.shape
+    c = _ctx(h_a)
+    c.check(c.lib.mml_pool_bwd(c.handle, _p(dz, torch.float32), _p(h_a, torch.float32), _p(h_b, torch.float32), _p(keep_a, torch.uint8),
+                               _p(keep_b, torch.uint8), float(keep_scale), int(kind), float(mix_a), float(mix_b), _p(dpre_a, torch.bfloat16),
+                               _p(dpre_b, torch.bfloat16), _p(dbias_a, torch.float32), _p(dbias_b, torch.float32), B, H, _stream(h_a)), "mml_pool_bwd")

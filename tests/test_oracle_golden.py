@@ -116,3 +116,21 @@ def test_mmimdb_train_steps_match_reference():
     assert np.allclose(l2, g["state_l2"], rtol=2e-3, atol=1e-6)
     ev = G.validation_step(state, I, T, y)
     assert np.abs(ev["logits"].numpy() - g["eval_logits"]).max() < 1e-2
+
+
+@pytest.mark.parametrize("pooling_type", ["max", "sum"])
+def test_mmimdb_pooling_matches_reference(pooling_type):
+    import gated_fusion_oracle as G
+
+    g = np.load(os.path.join(GOLD, f"mmimdb_pool_{pooling_type}_b16.npz"))
+    batch, seed = (int(v) for v in g["meta"])
+    torch.manual_seed(0)
+    state = G.init_mmimdb_pooling_state(pooling_type)
+    d = G.synthetic_batch(batch, seed)
+    out = G.train_step(state, {}, d["image_masked"], d["text_masked"], d["labels"], d["dropout_masks"], apply_update=False,
+                       pooling_type=pooling_type, pool_masks=d["pool_masks"], pool_p=0.1)
+    assert abs(out["loss"] - float(g["loss"])) < 1e-5 and np.allclose(out["logits"].numpy(), g["logits"], rtol=1e-4, atol=1e-5)
+    l2 = np.array([float(out["grads"][k].double().norm()) for k in g["grad_keys"]])
+    assert np.allclose(l2, g["grad_l2"], rtol=1e-3, atol=1e-9)
+    ev = G.validation_step(state, d["image_masked"], d["text_masked"], d["labels"], pooling_type=pooling_type)
+    assert np.abs(ev["logits"].numpy() - g["eval_logits"]).max() < 1e-4
