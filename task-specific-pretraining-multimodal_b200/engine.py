@@ -90,8 +90,10 @@ class FlatState:
         self.S = torch.zeros(max(soff, 4), device=device)
         self.nbt_names = nbt
         self.NBT = torch.zeros(max(len(nbt), 1), device=device, dtype=torch.int64)
-        self.hyper = torch.zeros(8, device=device)
-        self.hyper_host: Optional[Tuple[float, ...]] = None
+        self.hyper = torch.zeros(self.MAX_GROUPS, 8, device=device)
+        self.hyper_host: List[Optional[Tuple[float, ...]]] = [None] * self.MAX_GROUPS
+        self.ranges = None
+        self.range_version = 0
         self.step = torch.zeros(1, device=device, dtype=torch.int64)
         self._versions = None
         self._sentinels = None
@@ -173,52 +175,91 @@ class FlatState:
             self.refresh_shadows()
 
     # -- optimizer ---------------------------------------------------------------------------------------------
+    MAX_GROUPS = 8
+
     def adopt_optimizer(self, optimizer: torch.optim.Optimizer) -> None:
-        """Validate that ``optimizer`` is the Adam the fused kernel implements and alias its state to M / V."""
-        if getattr(self, "_adopted", None) is optimizer and len(optimizer.param_groups) == self._adopted_groups:
+        """Validate that ``optimizer`` is the Adam the fused kernel implements, alias its state to M / V and map its param
+        groups onto contiguous ranges of the flat buffers (one Adam launch per range, each with its own lr / betas / eps /
+        weight_decay -- the reference's pretrained-encoder runs use per-encoder groups, train_multimodal.py:213-300)."""
+        groups = optimizer.param_groups
+        sig = tuple(tuple(id(p) for p in g["params"]) for g in groups)
+        if getattr(self, "_adopted", None) is optimizer and sig == getattr(self, "_adopted_sig", None):
             return
         if type(optimizer) is not torch.optim.Adam:
             raise NotImplementedError(
-                f"mml_b200 fused train_step implements torch.optim.Adam (the reference's AVMNIST optimizer); got {type(optimizer).__name__}. "
+                f"mml_b200 fused train_step implements torch.optim.Adam (the optimizer of the reference's YAMLs); got {type(optimizer).__name__}. "
                 "There is no silent fallback.")
-        groups = optimizer.param_groups
-        keys = ("lr", "betas", "eps", "weight_decay", "amsgrad", "maximize")
-        h0 = tuple(groups[0][k] for k in keys)
-        for g in groups[1:]:
-            if tuple(g[k] for k in keys) != h0:
-                raise NotImplementedError("mml_b200 fused Adam needs identical hyper-parameters in all param groups")
-        if groups[0]["amsgrad"] or groups[0]["maximize"]:
-            raise NotImplementedError("amsgrad / maximize are not supported by the fused Adam kernel")
-        mine = {id(p) for p in self.module.parameters()}
-        theirs = [p for g in groups for p in g["params"]]
-        if {id(p) for p in theirs} != mine or len(theirs) != len(mine):
+        if len(groups) > self.MAX_GROUPS:
+            raise NotImplementedError(f"at most {self.MAX_GROUPS} optimizer param groups are supported")
+        for g in groups:
+            if g["amsgrad"] or g["maximize"]:
+                raise NotImplementedError("amsgrad / maximize are not supported by the fused Adam kernel")
+        group_of = {id(p): gi for gi, g in enumerate(groups) for p in g["params"]}
+        named = list(self.module.named_parameters())
+        if set(group_of) != {id(p) for _, p in named} or sum(len(g["params"]) for g in groups) != len(named):
             raise NotImplementedError("the optimizer must hold exactly the parameters of the model")
+        # contiguous flat ranges of equal group (alignment padding between tensors belongs to the range; it is zero and stays zero)
+        spans = []
+        for name, p in named:
+            gi = group_of[id(p)]
+            if name in self.aug:
+                o, n_out, _, ld = self.aug[name]
+                other = [q for q in self.aug if self.aug[q] == self.aug[name] and q != name]
+                if other and group_of[id(dict(named)[other[0]])] != gi:
+                    raise NotImplementedError(f"{name} and its bias are stored as one matrix and must share an optimizer param group")
+                spans.append((o, _round_up(o + n_out * ld, ALIGN), gi))
+            else:
+                o = self.offsets[name]
+                spans.append((o, _round_up(o + self.numels[name], ALIGN), gi))
+        spans.sort()
+        ranges: List[List[int]] = []
+        for a0, b0, gi in spans:
+            if ranges and ranges[-1][2] == gi and a0 <= ranges[-1][1]:
+                ranges[-1][1] = max(ranges[-1][1], b0)
+            elif ranges and a0 < ranges[-1][1]:
+                continue  # the bias half of an augmented pair (same block, same group)
+            else:
+                ranges.append([a0, b0, gi])
+        ranges[-1][1] = self.total
+        new_ranges = [tuple(r) for r in ranges]
+        if new_ranges != getattr(self, "ranges", None):
+            self.ranges = new_ranges
+            self.range_version = getattr(self, "range_version", 0) + 1  # captured graphs bake the launch ranges in
         host_step = torch.tensor(float(self.step.item()))
-        for name, p in self.module.named_parameters():
+        for name, p in named:
             st = optimizer.state[p]
-            if "exp_avg" in st and st["exp_avg"].data_ptr() != self.M.data_ptr() + 4 * self.offsets[name]:
-                self._view(self.M, name, p).copy_(st["exp_avg"])
+            mv = self._view(self.M, name, p)
+            if "exp_avg" in st and st["exp_avg"].data_ptr() != mv.data_ptr():
+                mv.copy_(st["exp_avg"])
                 self._view(self.V, name, p).copy_(st["exp_avg_sq"])
                 host_step = torch.as_tensor(st["step"]).detach().float().cpu().reshape(())
-            st["exp_avg"] = self._view(self.M, name, p)
+            st["exp_avg"] = mv
             st["exp_avg_sq"] = self._view(self.V, name, p)
             st["step"] = host_step  # one shared host scalar, advanced by the engine
         self.step.fill_(int(host_step.item()))
         self._host_step = host_step
         self._adopted = optimizer
-        self._adopted_groups = len(groups)
+        self._adopted_sig = sig
+        self.hyper_host = [None] * self.MAX_GROUPS
 
     def sync_hyper(self, optimizer: torch.optim.Optimizer, grad_scale: float) -> None:
-        groups = optimizer.param_groups
-        g = groups[0]
-        if len(groups) > 1:
-            keys = ("lr", "betas", "eps", "weight_decay")
-            if any(tuple(gg[k] for k in keys) != tuple(g[k] for k in keys) for gg in groups[1:]):
-                raise NotImplementedError("mml_b200 fused Adam needs identical hyper-parameters in all param groups")
-        h = (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), float(grad_scale), 0.0, 0.0)
-        if h != self.hyper_host:
-            self.hyper.copy_(torch.tensor(h, dtype=torch.float32), non_blocking=False)
-            self.hyper_host = h
+        for gi, g in enumerate(optimizer.param_groups):
+            h = (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), float(grad_scale), 0.0, 0.0)
+            if h != self.hyper_host[gi]:
+                self.hyper[gi].copy_(torch.tensor(h, dtype=torch.float32), non_blocking=False)
+                self.hyper_host[gi] = h
+
+    def adam_ranges(self, a: int, b: int) -> List[Tuple[int, int, int]]:
+        """(begin, end, group) pieces of [a, b) with uniform hyper-parameters."""
+        rs = getattr(self, "ranges", None) or [(0, self.total, 0)]
+        return [(max(a, ra), min(b, rb), g) for ra, rb, g in rs if max(a, ra) < min(b, rb)]
+
+    def adam(self, a: int, b: int, advance: bool) -> None:
+        """torch.optim.Adam.step over the flat range [a, b): one fused launch per param-group piece."""
+        pieces = self.adam_ranges(a, b)
+        for i, (ra, rb, g) in enumerate(pieces):
+            ops.adam_step(self.P[ra:rb], self.G[ra:rb], self.M[ra:rb], self.V[ra:rb], self.Wb[ra:rb], self.hyper[g], self.step,
+                          advance and i == len(pieces) - 1)
 
 
 # =====================================================================================================================
@@ -625,8 +666,7 @@ class _StepPlan:
         fs.NBT += 1
 
     def _adam_range(self, a: int, b: int, advance: bool) -> None:
-        fs = self.eng.fs
-        ops.adam_step(fs.P[a:b], fs.G[a:b], fs.M[a:b], fs.V[a:b], fs.Wb[a:b], fs.hyper, fs.step, advance)
+        self.eng.fs.adam(a, b, advance)
 
     def run_update(self) -> None:
         eng, fs = self.eng, self.eng.fs
@@ -668,6 +708,9 @@ class _StepPlan:
             self.run_update()
             return
         attr = "graph_train_nodrop" if given_dropout else "graph_train"
+        if getattr(self, "_range_version", None) != eng.fs.range_version:  # new optimizer grouping: the Adam launches changed
+            self.graph_train = self.graph_train_nodrop = None
+            self._range_version = eng.fs.range_version
         g = getattr(self, attr)
         if g is None:
             if self.eager_steps < 2:

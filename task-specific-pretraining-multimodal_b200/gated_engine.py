@@ -273,7 +273,7 @@ class _GatedPlan:
         eng, fs = self.eng, self.eng.fs
 
         def adam():
-            ops.adam_step(fs.P, fs.G, fs.M, fs.V, fs.Wb, fs.hyper, fs.step, True)
+            fs.adam(0, fs.total, True)
 
         if eng.allreduce is not None:
             eng.allreduce(self, 0, update=adam)
@@ -287,6 +287,9 @@ class _GatedPlan:
             self.run_update()
             return
         key = "train_given" if given_dropout else "train"
+        if getattr(self, "_range_version", None) != eng.fs.range_version:  # new optimizer grouping: the Adam launches changed
+            self.graphs.pop("train", None), self.graphs.pop("train_given", None)
+            self._range_version = eng.fs.range_version
         g = self.graphs.get(key)
         if g is None:
             if self.eager_steps < 2:

@@ -285,3 +285,41 @@ def test_device_prefetcher_batches_and_training_equivalence():
         it = DevicePrefetcher(iter(batches), DEV) if use_pf else iter(batches)
         losses.append([model.train_step(b, opt, LOSS, torch.device(DEV), None)["loss"] for b in it])
     assert np.allclose(losses[0], losses[1], rtol=2e-2, atol=2e-2), losses
+
+
+def test_adam_param_groups_follow_the_optimizer():
+    """Per-encoder lr / weight_decay groups (train_multimodal.py:213-300): every group's range gets its own fused Adam launch."""
+    B = 8
+    model = build(dropout=0.0)
+    d = O.synthetic_batch(B, 77, (32, 94))
+    groups = [{"params": list(model.audio_encoder.parameters()), "lr": 1e-4, "weight_decay": 2e-4},
+              {"params": list(model.image_encoder.parameters()), "lr": 2e-4, "weight_decay": 0.0},
+              {"params": list(model.net.parameters()), "lr": 5e-4, "weight_decay": 1e-4}]
+    opt = torch.optim.Adam(groups)
+    before = {k: v.detach().clone() for k, v in model.named_parameters()}
+    for step in range(3):  # eager, eager, graph
+        if step == 2:
+            opt.param_groups[0]["lr"] = 3e-5  # what ReduceLROnPlateau does between epochs
+        p0 = {k: v.detach().clone() for k, v in model.named_parameters()}
+        m0 = {k: opt.state[p]["exp_avg"].clone() if p in opt.state and "exp_avg" in opt.state[p] else torch.zeros_like(p) for k, p in model.named_parameters()}
+        v0 = {k: opt.state[p]["exp_avg_sq"].clone() if p in opt.state and "exp_avg_sq" in opt.state[p] else torch.zeros_like(p) for k, p in model.named_parameters()}
+        model.train_step(make_batch(d, B), opt, LOSS, torch.device(DEV), None)
+        t = step + 1
+        for k, p in model.named_parameters():
+            gi = 0 if k.startswith("audio_encoder") else (1 if k.startswith("image_encoder") else 2)
+            lr, wd = opt.param_groups[gi]["lr"], opt.param_groups[gi]["weight_decay"]
+            g = p.grad.detach() + wd * p0[k]
+            m = 0.9 * m0[k] + 0.1 * g
+            v = 0.999 * v0[k] + 0.001 * g * g
+            ref = p0[k] - (lr / (1 - 0.9 ** t)) * m / ((v.sqrt() / (1 - 0.999 ** t) ** 0.5) + 1e-8)
+            assert torch.allclose(p.detach(), ref, rtol=1e-5, atol=2e-7), (step, k)
+    assert len(model._engine.fs.ranges) == 3
+    # the first step moves every element by ~lr of ITS group
+    model2 = build(dropout=0.0)
+    opt2 = torch.optim.Adam([{"params": list(model2.audio_encoder.parameters()), "lr": 1e-4}, {"params": list(model2.image_encoder.parameters()), "lr": 2e-4},
+                             {"params": list(model2.net.parameters()), "lr": 5e-4}])
+    b2 = {k: v.detach().clone() for k, v in model2.named_parameters()}
+    model2.train_step(make_batch(d, B), opt2, LOSS, torch.device(DEV), None)
+    for k, lr in (("audio_encoder.layer1.0.conv1.weight", 1e-4), ("image_encoder.layer1.0.conv1.weight", 2e-4), ("net.0.weight", 5e-4)):
+        step_size = float((dict(model2.named_parameters())[k].detach() - b2[k]).abs().median())
+        assert abs(step_size - lr) < 0.05 * lr, (k, step_size)
