@@ -148,6 +148,16 @@ int mml_head_fwd(mml_ctx*, const mml_head_params* p, const float* pooledA, const
 int mml_head_bwd(mml_ctx*, const mml_head_params* p, const mml_head_grads* g, const float* pooledA, const float* pooledI,
                  const int64_t* labels, const uint8_t* dropout_mask, float dropout_scale, float* scratch,
                  float loss_scale, float* dpooledA, float* dpooledI, int B, int phases, void* stream);
+/* MonomodalEncoder tail (train_monomodal.py:64-92,224-232): emb = pooled W_fc^T + b_fc (the encoder's own fc, resnet.py:218),
+ * logits = emb W_cls^T + b_cls, mean cross-entropy, argmax, dlogits = (softmax - onehot) * loss_scale / B.  labels / dlogits /
+ * row_loss [B] / loss_out / pred are optional (forward only).  Backward: weight / bias gradients of both Linears (stored) and
+ * dpooled [B][F]; demb [B][E] is scratch. */
+int mml_mono_head_fwd(mml_ctx*, const float* pooled, const float* fc_w, const float* fc_b, const float* cls_w, const float* cls_b,
+                      const int64_t* labels, float* emb, float* logits, float* dlogits, float* row_loss, float* loss_out, int32_t* pred,
+                      float loss_scale, int B, int F, int E, int NC, void* stream);
+int mml_mono_head_bwd(mml_ctx*, const float* pooled, const float* emb, const float* dlogits, const float* fc_w, const float* cls_w,
+                      float* d_fc_w, float* d_fc_b, float* d_cls_w, float* d_cls_b, float* demb, float* dpooled, int B, int F, int E, int NC,
+                      void* stream);
 /* stand-alone nn.Linear forward (encoder fc outside the fused head, resnet.py:218): y [B][n_out] = x [B][n_in] W^T + b */
 int mml_linear_fwd(mml_ctx*, const float* x, const float* w, const float* bias, float* y, int B, int n_in, int n_out, void* stream);
 /* Philox-free counter RNG for the throughput path: mask[i] = hash(seed, *step_counter, i) >= p ? 1 : 0 */

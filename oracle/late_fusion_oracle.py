@@ -427,6 +427,45 @@ def validation_step(state: Dict[str, Tensor], A: Tensor, I: Tensor, labels: Tens
 
 
 # ----------------------------------------------------------------------------------------------
+# 8f rank 3 -- monomodal encoder pre-training (train_monomodal.py:64-92, 224-232): encoder -> Linear -> CE -> Adam
+# ----------------------------------------------------------------------------------------------
+def init_monomodal_state(arch: str = "resnet18", in_channels: int = 1, hidden_dim: int = 64, num_classes: int = NUM_CLASSES) -> "OrderedDict[str, Tensor]":
+    """MonomodalEncoder(ResNetXX(in_channels, hidden_dim), output_dim=hidden_dim, num_classes): the encoder is built by the YAML
+    loader first, the classifier Linear in the wrapper's constructor (train_monomodal.py:68-71)."""
+    st = init_resnet_state("encoder.", arch, in_channels, hidden_dim)
+    st["classifier.weight"], st["classifier.bias"] = _linear_params(num_classes, hidden_dim)
+    return st
+
+
+def monomodal_forward(state: Dict[str, Tensor], x: Tensor, training: bool, emulate_bf16: bool = False,
+                      forced: Optional[Dict[str, Tensor]] = None, taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    emb = resnet_forward(state, "encoder.", x, training, taps=taps, emulate_bf16=emulate_bf16, forced=forced)
+    return F.linear(emb.reshape(emb.shape[0], -1), state["classifier.weight"], state["classifier.bias"])
+
+
+def monomodal_train_step(state: "OrderedDict[str, Tensor]", opt_state: Dict, x: Tensor, labels: Tensor, lr: float = 5e-4,
+                         weight_decay: float = 1e-4, apply_update: bool = True, emulate_bf16: bool = False,
+                         forced: Optional[Dict[str, Tensor]] = None) -> Dict[str, object]:
+    params = {k: v for k, v in state.items() if is_parameter(k)}
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    work = dict(state)
+    work.update(leaves)
+    logits = monomodal_forward(work, x, True, emulate_bf16, forced)
+    loss = total_loss(logits, labels)
+    gl = torch.autograd.grad(loss, list(leaves.values()))
+    grads = dict(zip(leaves.keys(), gl))
+    for k in state:
+        if k.endswith("num_batches_tracked"):
+            state[k] = work[k]
+    if apply_update:
+        with torch.no_grad():
+            adam_step(params, grads, opt_state, lr=lr, weight_decay=weight_decay)
+    preds = torch.argmax(logits.detach(), dim=1)  # train_monomodal.py:239
+    return {"loss": float(loss.item()), "logits": logits.detach(), "predictions": preds, "grads": grads,
+            "accuracy": float((preds == labels).float().mean())}
+
+
+# ----------------------------------------------------------------------------------------------
 # e -- data parallel semantics: N replicas, per-replica BatchNorm, gradients averaged
 # ----------------------------------------------------------------------------------------------
 def data_parallel_grads(

@@ -7,6 +7,7 @@ Sub-modules (imported lazily so that ``import mml_b200`` works on a CPU-only box
   avmnist   AVMNIST late-fusion model: forward / train_step / validation_step / get_embeddings
   engine    the fused training / inference step (static buffers, kernel schedule, CUDA graph)
   mmimdb    MMIMDb gated late-fusion model (config 3) + gated_engine, its fused step
+  mono      MonomodalEncoder (encoder pre-training: one ResNet encoder + Linear + CE)
   data      missing-modality patterns and on-device mask application
   dist      one-process-per-GPU data parallelism (NCCL) with bucketed gradient allreduce
   fedavg    FedAvg weighted aggregation

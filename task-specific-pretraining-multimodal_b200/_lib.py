@@ -81,6 +81,8 @@ SIGNATURES = {
     "mml_head_scratch_per_sample": (I32, [C.POINTER(HeadParams)]),
     "mml_head_fwd": (I32, [P, C.POINTER(HeadParams), P, P, P, P, F32, P, P, P, P, I32, P]),
     "mml_head_bwd": (I32, [P, C.POINTER(HeadParams), C.POINTER(HeadGrads), P, P, P, P, F32, P, F32, P, P, I32, I32, P]),
+    "mml_mono_head_fwd": (I32, [P] * 13 + [F32, I32, I32, I32, I32, P]),
+    "mml_mono_head_bwd": (I32, [P] * 12 + [I32, I32, I32, I32, P]),
     "mml_linear_fwd": (I32, [P, P, P, P, P, I32, I32, I32, P]),
     "mml_dropout_mask": (I32, [P, P, I64, F32, U64, P, P]),
     "mml_bn1d_fwd": (I32, [P, C.POINTER(BN1dDesc), P]),

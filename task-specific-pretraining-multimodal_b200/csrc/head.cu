@@ -6,6 +6,8 @@
 // These are tiny fp32 GEMMs (M = batch, at most 512 x 128): latency-bound, so one kernel does the whole chain for a
 // group of 8 samples with the activations in shared memory; the concat is just a column offset.  Weight rows are read
 // coalesced by a warp (one output neuron per warp pass) and reduced with shuffles.
+#include <string.h>
+
 #include "mml_common.cuh"
 #include "mml_ctx.h"
 
@@ -476,6 +478,33 @@ __global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, long long n, flo
   }
 }
 
+// softmax cross-entropy over [B][NC] logits (NC <= 32), one warp per sample: probabilities -> dlogits = (p - onehot) * scale / B,
+// per-sample loss, argmax (first maximum, like torch.argmax)
+__global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
+                                                        float* __restrict__ dlogits, float* __restrict__ row_loss, int* __restrict__ pred,
+                                                        float scale, int B, int NC) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float v = lane < NC ? logits[(size_t)b * NC + lane] : -INFINITY;
+  float mx = v;
+  int arg = lane < NC ? lane : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ov > mx || (ov == mx && oa < arg)) mx = ov, arg = oa;
+  }
+  const float e = lane < NC ? expf(v - mx) : 0.f;
+  const float se = warp_sum(e);
+  const int y = labels ? (int)labels[b] : -1;
+  if (lane < NC && dlogits) dlogits[(size_t)b * NC + lane] = (e / se - (lane == y ? 1.f : 0.f)) * scale / (float)B;
+  const float vy = __shfl_sync(0xffffffffu, v, y >= 0 && y < NC ? y : 0);
+  if (lane == 0) {
+    if (pred) pred[b] = arg;
+    if (row_loss) row_loss[b] = (y >= 0 && y < NC) ? (logf(se) + mx - vy) : 0.f;
+  }
+}
+
 int check_head(mml_ctx* ctx, const mml_head_params* p) {
   MML_REQUIRE(ctx, ctx && p, "head: null ctx/params");
   MML_REQUIRE(ctx, p->fcA_w && p->fcA_b && p->fcI_w && p->fcI_b && p->w0 && p->b0 && p->w3 && p->b3 && p->w5 && p->b5,
@@ -569,6 +598,55 @@ int mml_head_bwd(mml_ctx* ctx, const mml_head_params* p, const mml_head_grads* g
   set(3, scratch + d.off_dh2(), PS, scratch + d.off_h1(), PS, g->w3, g->b3, d.H2, d.H1);
   set(4, scratch + d.off_dlog(), PS, scratch + d.off_h2(), PS, g->w5, g->b5, d.NC, d.H2);
   head_bwd_weights_kernel<<<fb, 256, 0, st>>>(jobs, B);
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
+int mml_mono_head_fwd(mml_ctx* ctx, const float* pooled, const float* fc_w, const float* fc_b, const float* cls_w, const float* cls_b,
+                      const int64_t* labels, float* emb, float* logits, float* dlogits, float* row_loss, float* loss_out, int32_t* pred,
+                      float loss_scale, int B, int F, int E, int NC, void* stream) {
+  MML_REQUIRE(ctx, ctx && pooled && fc_w && fc_b && cls_w && cls_b && emb && logits && B >= 1 && F >= 1 && E >= 1, "mono_head_fwd: bad arguments");
+  MML_REQUIRE(ctx, NC >= 1 && NC <= 32, "mono_head_fwd: 1..32 classes supported (got %d)", NC);
+  MML_REQUIRE(ctx, !loss_out || (labels && row_loss), "mono_head_fwd: the loss needs labels and row_loss");
+  cudaStream_t st = (cudaStream_t)stream;
+  FcJobs jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  jobs.j[0] = {pooled, fc_w, fc_b, emb, F, E, F, E, (int)mml_ceil_div(E, kFcTile)};
+  fc_fwd_kernel<<<dim3((unsigned)mml_ceil_div(B, kFcTile), jobs.j[0].tiles_n, 1), 256, 0, st>>>(jobs, B);
+  MML_LAUNCHED(ctx);
+  jobs.j[0] = {emb, cls_w, cls_b, logits, E, NC, E, NC, (int)mml_ceil_div(NC, kFcTile)};
+  fc_fwd_kernel<<<dim3((unsigned)mml_ceil_div(B, kFcTile), jobs.j[0].tiles_n, 1), 256, 0, st>>>(jobs, B);
+  MML_LAUNCHED(ctx);
+  softmax_ce_kernel<<<(unsigned)mml_ceil_div(B, 8), 256, 0, st>>>(logits, (const long long*)labels, dlogits, row_loss, pred, loss_scale, B, NC);
+  MML_LAUNCHED(ctx);
+  if (loss_out) {
+    head_loss_kernel<<<1, 256, 0, st>>>(row_loss, 1, 0, B, loss_out);
+    MML_LAUNCHED(ctx);
+  }
+  return MML_OK;
+}
+
+int mml_mono_head_bwd(mml_ctx* ctx, const float* pooled, const float* emb, const float* dlogits, const float* fc_w, const float* cls_w,
+                      float* d_fc_w, float* d_fc_b, float* d_cls_w, float* d_cls_b, float* demb, float* dpooled, int B, int F, int E, int NC,
+                      void* stream) {
+  MML_REQUIRE(ctx, ctx && pooled && emb && dlogits && fc_w && cls_w && d_fc_w && d_fc_b && d_cls_w && d_cls_b && demb && dpooled && B >= 1,
+              "mono_head_bwd: bad arguments");
+  MML_REQUIRE(ctx, F <= 1024 && E <= 1024, "mono_head_bwd: feature / embedding width above 1024");
+  cudaStream_t st = (cudaStream_t)stream;
+  FcJobs jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  jobs.j[0] = {dlogits, cls_w, nullptr, demb, NC, E, NC, E, (int)mml_ceil_div(E, kFcTile)};     // d emb = d logits . W_cls
+  fc_bwd_data_kernel<<<dim3((unsigned)mml_ceil_div(B, kFcTile), jobs.j[0].tiles_n, 1), 256, 0, st>>>(jobs, B);
+  MML_LAUNCHED(ctx);
+  jobs.j[0] = {demb, fc_w, nullptr, dpooled, E, F, E, F, (int)mml_ceil_div(F, kFcTile)};        // d pooled = d emb . W_fc
+  fc_bwd_data_kernel<<<dim3((unsigned)mml_ceil_div(B, kFcTile), jobs.j[0].tiles_n, 1), 256, 0, st>>>(jobs, B);
+  MML_LAUNCHED(ctx);
+  WgradJobs wj;
+  memset(&wj, 0, sizeof(wj));
+  wj.j[0] = {demb, pooled, d_fc_w, d_fc_b, E, F, E, F, 0};
+  wj.j[1] = {dlogits, emb, d_cls_w, d_cls_b, NC, E, NC, E, E};
+  for (int t = 2; t < 5; ++t) wj.j[t].first_block = E + NC;  // unused
+  head_bwd_weights_kernel<<<E + NC, 256, 0, st>>>(wj, B);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }

@@ -1,0 +1,262 @@
+"""Monomodal encoder pre-training -- drop-in for ``MonomodalEncoder`` (MML_Suite/train_monomodal.py:64-420) on a B200.
+
+``MonomodalEncoder(encoder, output_dim, num_classes)`` wraps ONE modality encoder and a ``Linear(output_dim, num_classes)``;
+its ``train_step`` is encoder forward -> classifier -> CrossEntropy -> backward -> Adam on the ORIGINAL (un-masked) modality
+tensor.  Here that is the same fused machinery as the late-fusion step with one encoder: the tcgen05 conv / BatchNorm
+schedule of ``engine.EncoderPlan`` plus a small tail (encoder fc, classifier, softmax-CE; ``mml_mono_head_fwd/bwd``), one
+CUDA graph per (batch, input size).  ``get_encoder().state_dict()`` is what ``train_monomodal.py:790-801`` saves and
+``train_multimodal.py:186-187`` loads into the fusion model -- same names, shapes and dtypes as the reference.
+
+Only ResNet encoders (``mml_b200.resnet``) are built; anything else raises.  File-path batches (the reference loads
+``.pt`` paths inside ``train_step``, :138-160) are host I/O and are not accepted -- pass tensors.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .engine import EncoderPlan, FlatState
+
+_SKIP = ("labels", "label", "genres", "imdb_ids", "pattern_name", "missing_masks", "sample_idx")
+
+
+class _MonoPlan:
+    def __init__(self, eng: "MonoEngine", B: int, H: int, W: int):
+        self.eng, self.B = eng, B
+        fs, dev, model = eng.fs, eng.device, eng.model
+        self.enc = EncoderPlan(fs, model.encoder, "encoder.", B, H, W, train=True)
+        self.enc.wgrad_stream = torch.cuda.Stream(device=dev)
+        params = dict(model.named_parameters())
+
+        def par(flat, name):
+            return fs.flat_slice(flat, name).view(params[name].shape)
+
+        self.fc_w, self.fc_b = par(fs.P, "encoder.fc.weight"), par(fs.P, "encoder.fc.bias")
+        self.cls_w, self.cls_b = par(fs.P, "classifier.weight"), par(fs.P, "classifier.bias")
+        self.d_fc_w, self.d_fc_b = par(fs.G, "encoder.fc.weight"), par(fs.G, "encoder.fc.bias")
+        self.d_cls_w, self.d_cls_b = par(fs.G, "classifier.weight"), par(fs.G, "classifier.bias")
+        E, NC = self.fc_w.shape[0], self.cls_w.shape[0]
+        if self.cls_w.shape[1] != E:
+            raise ValueError(f"classifier expects {self.cls_w.shape[1]} features but the encoder produces {E}")
+        self.labels = torch.zeros(B, device=dev, dtype=torch.int64)
+        self.emb, self.demb = torch.zeros(B, E, device=dev), torch.zeros(B, E, device=dev)
+        self.logits, self.dlogits = torch.zeros(B, NC, device=dev), torch.zeros(B, NC, device=dev)
+        self.row_loss, self.loss = torch.zeros(B, device=dev), torch.zeros(1, device=dev)
+        self.pred = torch.zeros(B, device=dev, dtype=torch.int32)
+        self.h_loss = torch.zeros(1).pin_memory()
+        self.h_pred = torch.zeros(B, dtype=torch.int32).pin_memory()
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.eager_steps = 0
+        self.launches_per_step = 0
+
+    def _head_fwd(self, with_loss: bool, with_grad: bool) -> None:
+        ops.mono_head_fwd(self.enc.pooled, self.fc_w, self.fc_b, self.cls_w, self.cls_b, self.labels if with_loss else None, self.emb, self.logits,
+                          self.dlogits if with_grad else None, self.row_loss if with_loss else None, self.loss if with_loss else None, self.pred, 1.0)
+
+    def run_train(self) -> None:
+        fs = self.eng.fs
+        fs.G.zero_()
+        self.enc.stat_arena.zero_()
+        for op in self.enc.fwd_train:
+            op()
+        self._head_fwd(True, True)
+        ops.mono_head_bwd(self.enc.pooled, self.emb, self.dlogits, self.fc_w, self.cls_w, self.d_fc_w, self.d_fc_b, self.d_cls_w, self.d_cls_b,
+                          self.demb, self.enc.dpooled)
+        for op in self.enc.bwd:
+            op()
+        fs.NBT += 1
+        if self.eng.allreduce is not None:
+            self.eng.allreduce(self, 0, update=lambda: fs.adam(0, fs.total, True))
+        else:
+            fs.adam(0, fs.total, True)
+
+    def train_step(self) -> None:
+        eng = self.eng
+        if getattr(self, "_range_version", None) != eng.fs.range_version:
+            self.graph, self._range_version = None, eng.fs.range_version
+        if not eng.use_graphs:
+            return self.run_train()
+        if self.graph is None:
+            if self.eager_steps < 2:
+                before = ops.launch_count(eng.device.index)
+                self.run_train()
+                self.launches_per_step = ops.launch_count(eng.device.index) - before
+                self.eager_steps += 1
+                return
+            torch.cuda.synchronize(eng.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.run_train()
+        self.graph.replay()
+
+    def run_forward(self, training: bool, with_loss: bool) -> None:
+        if training:
+            self.enc.stat_arena.zero_()
+        for op in (self.enc.fwd_train if training else self.enc.fwd_eval):
+            op()
+        self._head_fwd(with_loss, False)
+        if training:
+            self.eng.fs.NBT += 1
+
+
+class MonoEngine:
+    def __init__(self, model: nn.Module, device: torch.device):
+        self.model, self.device = model, device
+        self.fs = FlatState(model, device)
+        self.plans: Dict[Tuple[int, int, int], _MonoPlan] = {}
+        self.world = 1
+        self.allreduce = None
+        self.use_graphs = True
+
+    def plan_for(self, B: int, H: int, W: int) -> _MonoPlan:
+        key = (B, H, W)
+        plan = self.plans.get(key)
+        if plan is None:
+            plan = self.plans[key] = _MonoPlan(self, B, H, W)
+        return plan
+
+
+class MonomodalEncoder(nn.Module):
+    def __init__(self, encoder: nn.Module, output_dim: int, num_classes: int):
+        super().__init__()
+        from .resnet import ResNetEncoder
+
+        if not isinstance(encoder, ResNetEncoder):
+            raise NotImplementedError(f"mml_b200.MonomodalEncoder wraps the ResNet encoders of mml_b200.resnet; got {type(encoder).__name__}")
+        self.encoder = encoder
+        self.classifier = nn.Linear(output_dim, num_classes)
+        self._engine: Optional[MonoEngine] = None
+        self._dp = None
+        self.world_size = 1
+
+    # ---- plumbing ------------------------------------------------------------------------------------------------------
+    def train(self, mode: bool = True):
+        super().train(mode)
+        self._uniform_mode = bool(mode)
+        return self
+
+    def _set_mode(self, training: bool) -> None:
+        if getattr(self, "_uniform_mode", None) is not training or self.training is not training:
+            self.train(training)
+
+    def _get_engine(self, device) -> MonoEngine:
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("mml_b200.MonomodalEncoder runs on a B200 GPU only: there is no CPU / PyTorch fallback path")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        eng = self._engine
+        if eng is None or eng.device != device:
+            eng = self._engine = MonoEngine(self, device)
+            import weakref
+            self.encoder._mml_owner = (weakref.ref(eng), "encoder.")  # stand-alone encoder calls share this flat storage
+            if self._dp is not None:
+                self._dp.attach(eng)
+        eng.fs.ensure_fresh()
+        return eng
+
+    def enable_data_parallel(self, dp) -> None:
+        self._dp, self.world_size = dp, dp.world_size
+        if self._engine is not None:
+            dp.attach(self._engine)
+
+    def get_encoder(self) -> nn.Module:
+        return self.encoder
+
+    # ---- batch handling (train_monomodal.py:96-135, 196-222) ---------------------------------------------------------------
+    @staticmethod
+    def _unpack(batch: Dict[Any, Any], config=None):
+        want = None
+        name = getattr(getattr(config, "experiment", None), "name", "") or ""
+        if "AVMNIST_Image_Encoder" in name:
+            want = "IMAGE"
+        elif "AVMNIST_Audio_Encoder" in name:
+            want = "AUDIO"
+        key = None
+        for k in batch.keys():
+            ks = str(k)
+            if ks in _SKIP or ks.endswith(("_missing_index", "_reverse", "_original")):
+                continue
+            key = k
+            if want is not None and want in ks.upper():
+                break
+        if key is None:
+            raise ValueError(f"No modality data found in batch. Available keys: {list(batch.keys())}")
+        data = batch[f"{key}_original"] if f"{key}_original" in batch else batch[key]
+        if isinstance(data, (list, tuple)):
+            if len(data) and isinstance(data[0], str):
+                raise NotImplementedError("file-path batches are host I/O: load them in the dataset / collate function and pass tensors")
+            data = torch.stack([torch.as_tensor(t) for t in data])
+        labels = next((batch[k] for k in ("label", "labels", "genres") if k in batch), None)
+        if labels is None:
+            raise ValueError(f"No labels found in batch. Available keys: {list(batch.keys())}")
+        labels = torch.as_tensor(labels)
+        if labels.dim() != 1:
+            raise NotImplementedError("multi-label monomodal targets (MMIMDb encoders) are not built yet")
+        return key, data, labels
+
+    def _stage(self, eng: MonoEngine, x: torch.Tensor, labels: Optional[torch.Tensor]) -> _MonoPlan:
+        if x.dim() == 4:
+            if x.shape[1] != 1:
+                raise ValueError("expected a 1-channel tensor")
+            x = x[:, 0]
+        if x.dim() != 3:
+            raise ValueError(f"expected [B,H,W] or [B,1,H,W], got {tuple(x.shape)}")
+        plan = eng.plan_for(x.shape[0], x.shape[1], x.shape[2])
+        plan.enc.x.copy_(x, non_blocking=True)
+        plan.enc.mask.fill_(1.0)
+        if labels is not None:
+            plan.labels.copy_(labels.reshape(-1), non_blocking=True)
+        return plan
+
+    # ---- forward / steps --------------------------------------------------------------------------------------------------
+    def forward(self, x) -> torch.Tensor:
+        if isinstance(x, list):
+            x = torch.stack(x)
+        eng = self._get_engine(x.device if x.is_cuda else next(self.parameters()).device)
+        plan = self._stage(eng, x, None)
+        plan.run_forward(self.training, with_loss=False)
+        return plan.logits.clone()
+
+    def train_step(self, batch, optimizer, loss_functions, device, metric_recorder=None, config=None, **kwargs) -> Dict[str, Any]:
+        from .avmnist import AVMNIST
+
+        eng = self._get_engine(device)
+        AVMNIST._check_loss(loss_functions)
+        key, x, labels = self._unpack(batch, config)
+        self._set_mode(True)
+        fs = eng.fs
+        fs.adopt_optimizer(optimizer)
+        fs.sync_hyper(optimizer, 1.0 / self.world_size)
+        plan = self._stage(eng, x, labels)
+        plan.train_step()
+        fs._host_step += 1
+        return self._finish(eng, plan, key, labels, metric_recorder)
+
+    def validation_step(self, batch, loss_functions, device, metric_recorder=None, config=None, **kwargs) -> Dict[str, Any]:
+        from .avmnist import AVMNIST
+
+        eng = self._get_engine(device)
+        AVMNIST._check_loss(loss_functions)
+        key, x, labels = self._unpack(batch, config)
+        self._set_mode(False)
+        plan = self._stage(eng, x, labels)
+        plan.run_forward(False, with_loss=True)
+        return self._finish(eng, plan, key, labels, metric_recorder)
+
+    def _finish(self, eng, plan, key, labels, metric_recorder) -> Dict[str, Any]:
+        plan.h_loss.copy_(plan.loss, non_blocking=True)
+        plan.h_pred.copy_(plan.pred, non_blocking=True)
+        torch.cuda.current_stream(eng.device).synchronize()
+        loss = float(plan.h_loss[0])
+        preds = plan.h_pred.to(torch.int64)
+        targets = labels.detach().cpu().reshape(-1)
+        acc = float((preds == targets).float().mean())
+        if metric_recorder is not None:
+            for group_name in metric_recorder.config.groups:
+                metric_recorder.update_group(group_name=group_name, predictions=preds, targets=targets, modality=str(key))
+        return {"loss": loss, "metrics": {"loss": loss, "accuracy": acc}}

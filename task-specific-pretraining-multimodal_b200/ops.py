@@ -384,3 +384,24 @@ def pool_bwd(dz, h_a, h_b, keep_a, keep_b, keep_scale: float, kind: int, mix_a: 
     c.check(c.lib.mml_pool_bwd(c.handle, _p(dz, torch.float32), _p(h_a, torch.float32), _p(h_b, torch.float32), _p(keep_a, torch.uint8),
                                _p(keep_b, torch.uint8), float(keep_scale), int(kind), float(mix_a), float(mix_b), _p(dpre_a, torch.bfloat16),
                                _p(dpre_b, torch.bfloat16), _p(dbias_a, torch.float32), _p(dbias_b, torch.float32), B, H, _stream(h_a)), "mml_pool_bwd")
+
+
+# ---- MonomodalEncoder tail (encoder fc -> classifier -> CE) ----------------------------------------------------------
+def mono_head_fwd(pooled, fc_w, fc_b, cls_w, cls_b, labels, emb, logits, dlogits, row_loss, loss, pred, loss_scale: float = 1.0) -> None:
+    B, Fd = pooled.shape
+    E, NC = fc_w.shape[0], cls_w.shape[0]
+    c = _ctx(pooled)
+    f32 = torch.float32
+    c.check(c.lib.mml_mono_head_fwd(c.handle, _p(pooled, f32), _p(fc_w, f32), _p(fc_b, f32), _p(cls_w, f32), _p(cls_b, f32), _p(labels, torch.int64),
+                                    _p(emb, f32), _p(logits, f32), _p(dlogits, f32), _p(row_loss, f32), _p(loss, f32), _p(pred, torch.int32),
+                                    float(loss_scale), B, Fd, E, NC, _stream(pooled)), "mml_mono_head_fwd")
+
+
+def mono_head_bwd(pooled, emb, dlogits, fc_w, cls_w, d_fc_w, d_fc_b, d_cls_w, d_cls_b, demb, dpooled) -> None:
+    B, Fd = pooled.shape
+    E, NC = fc_w.shape[0], cls_w.shape[0]
+    c = _ctx(pooled)
+    f32 = torch.float32
+    c.check(c.lib.mml_mono_head_bwd(c.handle, _p(pooled, f32), _p(emb, f32), _p(dlogits, f32), _p(fc_w, f32), _p(cls_w, f32), _p(d_fc_w, f32),
+                                    _p(d_fc_b, f32), _p(d_cls_w, f32), _p(d_cls_b, f32), _p(demb, f32), _p(dpooled, f32), B, Fd, E, NC,
+                                    _stream(pooled)), "mml_mono_head_bwd")

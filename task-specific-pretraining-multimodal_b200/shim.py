@@ -64,4 +64,11 @@ def install(patch_reference_modules: bool = True) -> Dict[str, object]:
             ref_rn.ResNet18, ref_rn.ResNet34, ref_rn.ResNetEncoder = ResNet18, ResNet34, ResNetEncoder
     _installed["AVMNIST"] = AVMNIST
     _installed["MMIMDb"] = _mm.MMIMDb
+    from .mono import MonomodalEncoder
+
+    ref_tm = sys.modules.get("train_monomodal")
+    if patch_reference_modules and ref_tm is not None:  # MonomodalEncoder lives in the training script itself (train_monomodal.py:64)
+        _installed["reference.MonomodalEncoder"] = getattr(ref_tm, "MonomodalEncoder", None)
+        ref_tm.MonomodalEncoder = MonomodalEncoder
+    _installed["MonomodalEncoder"] = MonomodalEncoder
     return dict(_installed)

@@ -134,3 +134,22 @@ def test_mmimdb_pooling_matches_reference(pooling_type):
     assert np.allclose(l2, g["grad_l2"], rtol=1e-3, atol=1e-9)
     ev = G.validation_step(state, d["image_masked"], d["text_masked"], d["labels"], pooling_type=pooling_type)
     assert np.abs(ev["logits"].numpy() - g["eval_logits"]).max() < 1e-4
+
+
+def test_monomodal_oracle_matches_reference():
+    g = np.load(os.path.join(GOLD, "mono_resnet18_b4.npz"))
+    batch, H, W, seed, steps, hidden = (int(v) for v in g["meta"])
+    torch.manual_seed(0)
+    state = O.init_monomodal_state("resnet18", 1, hidden, 10)
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.rand(batch, H, W, generator=gen)
+    y = torch.randint(0, 10, (batch,), generator=gen)
+    opt_state = {}
+    for step in range(steps):
+        out = O.monomodal_train_step(state, opt_state, x, y)
+        assert abs(out["loss"] - float(g["losses"][step])) < (1e-5 if step == 0 else 5e-3)
+        if step == 0:
+            assert np.allclose(out["logits"].numpy(), g["logits"], rtol=1e-4, atol=1e-5)
+            l2 = np.array([float(out["grads"][k].double().norm()) for k in g["grad_keys"]])
+            assert np.allclose(l2, g["grad_l2"], rtol=1e-3, atol=1e-7)
+            assert np.abs(out["grads"]["classifier.weight"].numpy() - g["grad::classifier.weight"]).max() < 1e-6
