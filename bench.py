@@ -287,6 +287,130 @@ def run_gated_arm(args):
         "last_loss": out["loss"]}))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# --workload mono: monomodal encoder pre-training (8f rank 3; configs/avmnist/mono/train_audio_encoder_resnet.yaml)
+# ---------------------------------------------------------------------------------------------------------------------
+def run_mono_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from mml_b200 import dist as mdist
+    from mml_b200.data import DevicePrefetcher
+    from mml_b200.mono import MonomodalEncoder
+    from mml_b200.resnet import ResNet18
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import late_fusion_oracle as O
+
+    B = args.batch
+    metric = "avmnist_audio_encoder_pretrain_samples_per_s"
+    cfg = {"workload": "monomodal pre-training step: ResNet18 audio encoder 112x112 + Linear(64,10), CE, Adam", "batch_per_gpu": B,
+           "l2_policy": "per-step working set (~2 GB of bf16 activations) exceeds the 126 MB L2; no explicit flush",
+           "timing": "CUDA events around K CUDA-graph replays, barrier + synchronize on both sides, max over ranks"}
+
+    def cpu_run(budget):
+        torch.set_num_threads(os.cpu_count() or 1)
+        torch.manual_seed(0)
+        st = O.init_monomodal_state("resnet18", 1, 64, 10)
+        g = torch.Generator().manual_seed(0)
+        x, y = torch.rand(CPU_SAMPLE_BATCH, 112, 112, generator=g), torch.randint(0, 10, (CPU_SAMPLE_BATCH,), generator=g)
+        os_, ts = {}, []
+        O.monomodal_train_step(st, os_, x, y)
+        t_begin = time.perf_counter()
+        while len(ts) < 3 or (time.perf_counter() - t_begin < budget and len(ts) < 50):
+            t0 = time.perf_counter()
+            O.monomodal_train_step(st, os_, x, y)
+            ts.append(time.perf_counter() - t0)
+        per = statistics.median(ts)
+        return {"value": CPU_SAMPLE_BATCH / per, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                "sample": f"{len(ts)} train steps of the monomodal oracle port at batch {CPU_SAMPLE_BATCH}, fp32, torch CPU, median step {per * 1e3:.0f} ms",
+                "steps_timed": len(ts), "ms_per_step": per * 1e3}
+
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            r = cpu_run(60.0)
+            _emit(json.dumps({"impl": "reference", "metric": metric, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps_timed"],
+                              "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                              "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                              "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+    rank, local_rank, world = mdist.init_from_env("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(0)
+    model = MonomodalEncoder(ResNet18(1, 64), 64, 10).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
+    loss_fns = {"cross_entropy": _Term(torch.nn.CrossEntropyLoss())}
+    if world > 1:
+        dp = mdist.DataParallel()
+        model.enable_data_parallel(dp)
+    eng = model._get_engine(dev)
+    if world > 1:
+        dp.broadcast_state(eng)
+
+    def pinned(seed):
+        g = torch.Generator().manual_seed(seed)
+        return {"audio": torch.rand(B, 112, 112, generator=g).pin_memory(), "labels": torch.randint(0, 10, (B,), generator=g).pin_memory()}
+
+    host = [pinned(100 * rank + i) for i in range(3)]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        model.train_step(host[i % 3], opt, loss_fns, dev, None)
+    plan = next(iter(eng.plans.values()))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(40):
+        plan.train_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        barrier()
+        e0.record()
+        fn()
+        e1.record()
+        barrier()
+        dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item())
+
+    def dev_loop():
+        for _ in range(args.steps):
+            plan.train_step()
+
+    def e2e_loop():
+        for b in DevicePrefetcher((host[i % 3] for i in range(args.steps)), dev):
+            model.train_step(b, opt, loss_fns, dev, None)
+
+    t_dev = timed(dev_loop)
+    eng.fs._host_step += args.steps + 40
+    t_e2e = timed(e2e_loop)
+    clocks = sampler.stop()
+    if rank != 0:
+        return
+    pk = peaks()
+    gflop = 3 * 0.93042  # 930.42 MFLOP/sample forward, x3 for fwd + dgrad + wgrad
+    tf = gflop * B * args.steps / t_dev / 1e3
+    cpu = cpu_run(15.0)
+    cfg.update({"global_batch": B * world, "parallelism": f"dp{world}"})
+    _emit(json.dumps({
+        "metric": metric, "value": B * world * args.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": cfg, "e2e": {"value": B * world * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 + 4 * B,
+                               "ms_per_step": t_e2e / args.steps * 1e3},
+        "gpu_launches": plan.launches_per_step * args.steps, "launches_per_step": plan.launches_per_step, "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"], "traffic": None,
+                     "note": f"whole step: {gflop:.3f} dense-nominal GFLOP/sample x samples/s vs {pk['src']} sustained bf16"},
+        "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}}))
+
+
 def workload_config(args, world):
     return {"workload": "AVMNIST late-fusion train step: ResNet18 audio 112x112 + ResNet34 image 28x28, concat head, CE, Adam; audio missing_rate 0.2",
             "batch_per_gpu": args.batch, "global_batch": args.batch * world, "parallelism": f"dp{world}",
@@ -503,7 +627,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU (BASELINE.json configs[1])")
-    ap.add_argument("--workload", default="avmnist", choices=["avmnist", "mmimdb"], help="avmnist = the headline line (configs[1]); mmimdb = configs[2]")
+    ap.add_argument("--workload", default="avmnist", choices=["avmnist", "mmimdb", "mono"],
+                    help="avmnist = the headline line (configs[1]); mmimdb = configs[2]; mono = monomodal audio-encoder pre-training")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: library chatter (e.g. "NCCL version ...") is diverted to stderr
     real_stdout = os.fdopen(os.dup(1), "w")
@@ -512,6 +637,8 @@ def main():
     _emit = lambda line: (real_stdout.write(line + "\n"), real_stdout.flush())
     if args.workload == "mmimdb":
         run_gated_arm(args)
+    elif args.workload == "mono":
+        run_mono_arm(args)
     elif args.impl == "reference":
         run_reference_arm(args)
     else:
