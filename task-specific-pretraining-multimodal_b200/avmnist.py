@@ -35,6 +35,17 @@ def _find(batch: Dict[Any, Any], name: str):
     return None
 
 
+def _copy_in(dst: torch.Tensor, src: torch.Tensor) -> None:
+    """Stage ``src`` into the plan's static input buffer.  Host sources are an H2D memcpy.  Device sources (a prefetched batch)
+    are copied by a KERNEL: a device-to-device ``cudaMemcpyAsync`` is served by a copy engine and queues behind the
+    prefetcher's in-flight H2D transfer of the next batch, which put the whole copy back on the critical path (measured:
+    4.3 ms/step instead of 3.45)."""
+    if src.is_cuda and src.dtype == dst.dtype and src.shape == dst.shape:
+        torch.mul(src, 1, out=dst)
+    else:
+        dst.copy_(src, non_blocking=True)
+
+
 class AVMNIST(nn.Module):
     def __init__(self, audio_encoder: nn.Module, image_encoder: nn.Module, hidden_dim: int, *, dropout: float = 0.0,
                  fusion_fn: str = "concat") -> None:
@@ -124,15 +135,15 @@ class AVMNIST(nn.Module):
         if I.shape[0] != B:
             raise ValueError("audio and image batch sizes differ")
         plan = eng.plan_for(B, A.shape[1], A.shape[2], I.shape[1], I.shape[2])
-        plan.audio.x.copy_(A, non_blocking=True)
-        plan.image.x.copy_(I, non_blocking=True)
+        _copy_in(plan.audio.x, A)
+        _copy_in(plan.image.x, I)
         for enc_plan, m in ((plan.audio, mask_a), (plan.image, mask_i)):
             if m is None:
                 enc_plan.mask.fill_(1.0)
             else:
-                enc_plan.mask.copy_(torch.as_tensor(m).reshape(B), non_blocking=True)
+                _copy_in(enc_plan.mask, torch.as_tensor(m).reshape(B))
         if labels is not None:
-            plan.labels.copy_(labels.reshape(B), non_blocking=True)
+            _copy_in(plan.labels, labels.reshape(B))
         return plan
 
     # ---- forward ---------------------------------------------------------------------------------------------------

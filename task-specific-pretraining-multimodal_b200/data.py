@@ -77,25 +77,49 @@ def attach_masks(batch: Dict[Any, Any], masks: Mapping[str, torch.Tensor], modal
 class DevicePrefetcher:
     """Iterate a loader of batch dicts with the host->device copies of batch n+1 running under step n.
 
-    Tensors go to fixed per-slot device buffers on a dedicated copy stream (pinned host memory makes the copies truly
-    asynchronous: use ``DataLoader(pin_memory=True)``); non-tensor entries pass through.  The consumer's stream waits on
-    the slot's copy event, and a slot is only overwritten after the consumer's stream has been waited on, so there is no
-    allocator traffic and no race.  ``depth`` batches are kept in flight (1 is enough to hide one batch's copy).
+    Tensors go to fixed per-slot device buffers (pinned host memory makes the copies truly asynchronous: use
+    ``DataLoader(pin_memory=True)``); non-tensor entries pass through.  The consumer's stream waits on the slot's copy event,
+    and a slot is only overwritten after the consumer's stream has been waited on, so there is no allocator traffic and no race.
+
+    Which stream carries the copies is CALIBRATED, not assumed: CUDA multiplexes streams onto a limited number of hardware
+    queues, and a copy stream that happens to share a queue with one of the streams inside the step's CUDA graph serialises
+    with it (measured on B200: the 3.3 ms AVMNIST step became 4.4-4.9 ms with an unlucky stream, 3.45 ms with a lucky one).
+    The first ``len(candidates) * rounds`` batches rotate over a few candidate streams and over "inline" (copy on the
+    consumer's stream, no overlap); the candidate with the smallest median step time is kept for the device (class-level, so
+    later prefetchers on the same device reuse it).
     """
 
-    def __init__(self, loader: Iterable[Dict[Any, Any]], device, depth: int = 1):
+    _streams: Dict[Any, list] = {}
+    _choice: Dict[Any, int] = {}
+    calibration: Dict[int, float] = {}
+    N_CANDIDATES, ROUNDS = 3, 3
+
+    def __init__(self, loader: Iterable[Dict[Any, Any]], device, depth: int = 1, calibrate: bool = True):
         self.loader, self.device, self.depth = loader, torch.device(device), max(1, int(depth))
         if self.device.type != "cuda":
             raise RuntimeError("DevicePrefetcher stages batches onto a CUDA device")
-        self.stream = torch.cuda.Stream(device=self.device)
+        key = (self.device.type, self.device.index if self.device.index is not None else torch.cuda.current_device())
+        if key not in DevicePrefetcher._streams:
+            DevicePrefetcher._streams[key] = [None] + [torch.cuda.Stream(device=self.device) for _ in range(self.N_CANDIDATES)]
+        self._key = key
+        self.candidates = DevicePrefetcher._streams[key]  # [inline, stream, stream, ...]
+        if not calibrate and key not in DevicePrefetcher._choice:
+            DevicePrefetcher._choice[key] = 1
         self.slots = [dict() for _ in range(self.depth + 1)]
         self.h2d_bytes = 0
 
-    def _stage(self, batch: Dict[Any, Any], slot: Dict[Any, torch.Tensor]):
+    @property
+    def chosen(self) -> Optional[int]:
+        """Index into ``candidates`` picked by the calibration (0 = inline), or None while calibrating."""
+        return DevicePrefetcher._choice.get(self._key)
+
+    def _stage(self, batch: Dict[Any, Any], slot: Dict[Any, torch.Tensor], cand: int):
         main = torch.cuda.current_stream(self.device)
-        self.stream.wait_stream(main)  # the slot's previous consumer is done before it is overwritten
+        stream = self.candidates[cand] or main
+        if stream is not main:
+            stream.wait_stream(main)  # the slot's previous consumer is done before it is overwritten
         out = {}
-        with torch.cuda.stream(self.stream):
+        with torch.cuda.stream(stream):
             for k, v in batch.items():
                 if torch.is_tensor(v):
                     buf = slot.get(k)
@@ -107,25 +131,45 @@ class DevicePrefetcher:
                 else:
                     out[k] = v
         ev = torch.cuda.Event()
-        ev.record(self.stream)
+        ev.record(stream)
         return out, ev
 
     def __iter__(self) -> Iterator[Dict[Any, Any]]:
+        import time
+
         it = iter(self.loader)
         queue: deque = deque()
         n = 0
+        samples: Dict[int, list] = {c: [] for c in range(len(self.candidates))}
+
+        def next_candidate() -> int:
+            if self.chosen is not None:
+                return self.chosen
+            return n % len(self.candidates)
+
         for _ in range(self.depth):
             try:
-                queue.append(self._stage(next(it), self.slots[n % len(self.slots)]))
+                queue.append(self._stage(next(it), self.slots[n % len(self.slots)], next_candidate()))
                 n += 1
             except StopIteration:
                 break
         while queue:
             out, ev = queue.popleft()
+            staged_with = None
             try:
-                queue.append(self._stage(next(it), self.slots[n % len(self.slots)]))
+                staged_with = next_candidate()
+                queue.append(self._stage(next(it), self.slots[n % len(self.slots)], staged_with))
                 n += 1
             except StopIteration:
-                pass
+                staged_with = None
             torch.cuda.current_stream(self.device).wait_event(ev)
+            t0 = time.perf_counter()
             yield out
+            if self.chosen is None and staged_with is not None:
+                # the consumer's step on ``out`` ran while the copy staged with ``staged_with`` was in flight; consumers that
+                # return a loss synchronise, so the wall time of the step reflects how well that copy overlapped
+                samples[staged_with].append(time.perf_counter() - t0)
+                if all(len(v) >= self.ROUNDS for v in samples.values()):
+                    med = {c: sorted(v)[len(v) // 2] for c, v in samples.items()}
+                    DevicePrefetcher._choice[self._key] = min(med, key=med.get)
+                    DevicePrefetcher.calibration = med  # seconds per step by candidate (0 = inline), for inspection

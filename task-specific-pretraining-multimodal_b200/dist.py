@@ -7,7 +7,8 @@ gradients are summed over ranks and divided by the world size inside the Adam ke
 The flat gradient buffer ``G`` is reduced in two contiguous buckets, ordered so that communication hides under compute:
 the image encoder has 2/3 of the parameters but few FLOPs, so its backward runs FIRST and bucket 0 (image encoder +
 head, ~85 MB) is all-reduced on a side stream while the audio encoder's backward (87 % of the FLOPs) is still running;
-bucket 1 (audio encoder, ~45 MB) follows.  The wgrad kernels write straight into ``G``, so there is no pack/copy step.
+the audio encoder follows in two ranges: layer3..fc (94 % of its parameters, ~42 MB) as soon as layer3's backward is
+done -- under the backward of layer2 / layer1 / the stem -- and the small remainder (~3 MB) at the end of the step.  The wgrad kernels write straight into ``G``, so there is no pack/copy step.
 ``torch.distributed`` (NCCL over NVLink/NVSwitch) is the plumbing; both the collectives and the cross-stream
 dependencies are captured into the step's CUDA graph.
 """
@@ -46,6 +47,8 @@ class DataParallel:
         self.comm_stream = torch.cuda.Stream(device=engine.device)
         engine.world = self.world_size
         engine.allreduce = self._allreduce if self.world_size > 1 else None
+        if hasattr(engine, "allreduce_range"):
+            engine.allreduce_range = self._allreduce_range if self.world_size > 1 else None
 
     def _allreduce(self, plan, idx: int, update=None) -> None:
         """All-reduce bucket ``idx`` of G on the communication stream, then run ``update`` (the Adam launch for that range)
@@ -62,6 +65,20 @@ class DataParallel:
                 update()
         if idx == len(self.buckets) - 1:
             producer.wait_stream(self.comm_stream)  # everything of this step is ordered before what follows on the main stream
+
+    def _allreduce_range(self, a: int, b: int, producers, update=None, join: bool = False) -> None:
+        """All-reduce G[a:b) on the communication stream once every stream in ``producers`` has finished what it has queued,
+        then run ``update`` (that range's Adam launch) there; ``join``: the current stream waits for the communication stream
+        (last range of a step).  Ranges are issued in the same order on every rank (same captured schedule)."""
+        eng = self.engine
+        for st in producers:
+            self.comm_stream.wait_stream(st)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(eng.fs.G[a:b], op=dist.ReduceOp.SUM, group=self.group)
+            if update is not None:
+                update()
+        if join:
+            torch.cuda.current_stream(eng.device).wait_stream(self.comm_stream)
 
     def broadcast_state(self, engine) -> None:
         """Make every rank start from rank 0's weights / Adam state / running statistics."""

@@ -337,6 +337,7 @@ class EncoderPlan:
         fs, B, dev, pre = self.fs, self.B, self.fs.device, self.prefix
         F, E, Bk = self.fwd_train, self.fwd_eval, self.bwd
         bwd_stack: List[Callable[[], None]] = []  # appended in forward order, executed reversed
+        bwd_stack_names: List[str] = []
         # ---------------- stem: conv7x7/s2 (+mask) -> BN -> ReLU -> maxpool3/s2
         P0, Q0 = (self.H - 1) // 2 + 1, (self.W - 1) // 2 + 1
         P1, Q1 = (P0 - 1) // 2 + 1, (Q0 - 1) // 2 + 1
@@ -447,6 +448,7 @@ class EncoderPlan:
                     ops.conv_dgrad(g1, d_raw1, w1t, d_x_main)
 
                 bwd_stack.append(bwd_block)
+                bwd_stack_names.append(bname)
                 # the gradient of this block's INPUT arrives over two paths
                 grads_of_cur[0] = d_x_main
                 grads_of_cur[1] = d_x_ds if has_ds else g_skip
@@ -465,6 +467,7 @@ class EncoderPlan:
             dpooled = self.dpooled
             Bk.append(lambda: ops.avgpool_bwd(dpooled, d_last, B, HW, 512))
             Bk.extend(reversed(bwd_stack))
+            self.bwd_names = ["avgpool"] + list(reversed(bwd_stack_names)) + ["stem"]  # one name per closure of ``bwd``
             # stem backward
             d_raw0 = self._act(B, P0, Q0, 64)
             ws = torch.zeros(max(ops.stem_wgrad_workspace(x) // 4, 4), device=dev)
@@ -540,6 +543,7 @@ class LateFusionEngine:
         self.plans: Dict[Tuple, "_StepPlan"] = {}
         self.world = 1
         self.allreduce: Optional[Callable[["_StepPlan"], None]] = None
+        self.allreduce_range: Optional[Callable] = None  # (a, b, producer streams, update, join) -- set by dist.DataParallel
         self.use_graphs = True
 
     def plan_for(self, B: int, aH: int, aW: int, iH: int, iW: int) -> "_StepPlan":
@@ -591,6 +595,11 @@ class _StepPlan:
             self.image.wgrad_stream = torch.cuda.Stream(device=dev)
         img = [o for n, o in fs.offsets.items() if n.startswith("image_encoder.")]
         self.param_split = min(img) if img else 0  # flat ranges: [0, split) audio encoder, [split, total) image encoder + head
+        # [audio_mid, split) = audio layer3 .. fc: 94 % of the audio encoder's parameters, complete once layer3's backward is
+        # done; its all-reduce / Adam then runs under the backward of layer2 / layer1 / stem (MML_AUDIO_MID=0: one audio range)
+        mid_name = "audio_encoder.layer3.0.conv1.weight"
+        self.audio_mid = fs.offsets.get(mid_name, 0) if _os.environ.get("MML_AUDIO_MID", "1") == "1" and self.tune["adam_split"] else 0
+        self.mid_stream: Optional[torch.cuda.Stream] = None
 
     # -- schedules -----------------------------------------------------------------------------------------------
     def _use_dropout(self) -> bool:
@@ -656,13 +665,36 @@ class _StepPlan:
             else:
                 self._adam_range(split, fs.total, False)
 
+        audio_bwd = self.audio.bwd
+        if self.audio_mid > 0 and eng.allreduce_range is None:
+            self.audio_mid = 0  # single GPU: nothing to hide (measured: no gain, and one more stream to alias with the copies)
+        if self.audio_mid > 0:
+            mid_a = self.audio_mid
+
+            def finish_audio_mid():
+                # producers of that range's gradients: BatchNorm gradients on this stream, conv weight gradients on the audio
+                # wgrad stream, the audio fc gradients from the head's weight-gradient launch (image wgrad stream)
+                cur = torch.cuda.current_stream(eng.device)
+                producers = [st for st in (cur, self.audio.wgrad_stream, self.image.wgrad_stream) if st is not None]
+                if eng.allreduce_range is not None:
+                    eng.allreduce_range(mid_a, split, producers, update=lambda: self._adam_range(mid_a, split, False))
+                else:
+                    if self.mid_stream is None:
+                        self.mid_stream = torch.cuda.Stream(device=eng.device)
+                    for st in producers:
+                        self.mid_stream.wait_stream(st)
+                    with torch.cuda.stream(self.mid_stream):
+                        self._adam_range(mid_a, split, False)
+
+            k = self.audio.bwd_names.index("layer3.0") + 1
+            audio_bwd = self.audio.bwd[:k] + [finish_audio_mid] + self.audio.bwd[k:]
         if self.tune["head_side"]:
-            self._both_encoders(self.audio.bwd, [head_weight_grads] + self.image.bwd, after_image=finish_image_range if self.tune["adam_split"] else None)
+            self._both_encoders(audio_bwd, [head_weight_grads] + self.image.bwd, after_image=finish_image_range if self.tune["adam_split"] else None)
         else:
             # the head's weight gradients are off the chain too: they share the image encoder's wgrad stream, which is joined
             # before that range's all-reduce / Adam
             self.image._offload(head_weight_grads)
-            self._both_encoders(self.audio.bwd, self.image.bwd, after_image=finish_image_range if self.tune["adam_split"] else None)
+            self._both_encoders(audio_bwd, self.image.bwd, after_image=finish_image_range if self.tune["adam_split"] else None)
         fs.NBT += 1
 
     def _adam_range(self, a: int, b: int, advance: bool) -> None:
@@ -677,10 +709,13 @@ class _StepPlan:
             else:
                 self._adam_range(0, fs.total, True)
             return
-        if eng.allreduce is not None:
-            eng.allreduce(self, 1, update=lambda: self._adam_range(0, self.param_split, True))
+        last = self.audio_mid if self.audio_mid > 0 else self.param_split  # what is left of the audio encoder: [0, last)
+        if eng.allreduce_range is not None:
+            eng.allreduce_range(0, last, [torch.cuda.current_stream(eng.device)], update=lambda: self._adam_range(0, last, True), join=True)
         else:
-            self._adam_range(0, self.param_split, True)
+            if self.mid_stream is not None:
+                torch.cuda.current_stream(eng.device).wait_stream(self.mid_stream)
+            self._adam_range(0, last, True)
 
     def run_eval(self, with_loss: bool) -> None:
         self._both_encoders(self.audio.fwd_eval, self.image.fwd_eval)

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .avmnist import _find
+from .avmnist import _copy_in, _find
 
 FULL_PATTERN = "it"  # MMIMDbDataset.get_full_modality() (data/mmimdb.py)
 
@@ -198,15 +198,15 @@ class MMIMDb(nn.Module):
         if I.shape[1] != plan.DI or T.shape[1] != plan.DT:
             raise ValueError(f"feature widths {I.shape[1]}/{T.shape[1]} do not match the encoders ({plan.DI}/{plan.DT})")
         plan.threshold = float(self.binary_threshold)
-        plan.xI.copy_(I, non_blocking=True)
-        plan.xT.copy_(T, non_blocking=True)
+        _copy_in(plan.xI, I)
+        _copy_in(plan.xT, T)
         for dst, m in ((plan.mI, mask_i), (plan.mT, mask_t)):
             if m is None:
                 dst.fill_(1.0)
             else:
-                dst.copy_(torch.as_tensor(m).reshape(B), non_blocking=True)
+                _copy_in(dst, torch.as_tensor(m).reshape(B))
         if labels is not None:
-            plan.labels.copy_(labels.reshape(B, plan.NC), non_blocking=True)
+            _copy_in(plan.labels, labels.reshape(B, plan.NC))
         return plan
 
     def forward(self, I: torch.Tensor, T: torch.Tensor, *, is_embd_I: bool = False, is_embd_T: bool = False) -> torch.Tensor:

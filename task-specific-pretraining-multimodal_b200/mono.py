@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .avmnist import _copy_in
 from .engine import EncoderPlan, FlatState
 
 _SKIP = ("labels", "label", "genres", "imdb_ids", "pattern_name", "missing_masks", "sample_idx")
@@ -207,10 +208,10 @@ class MonomodalEncoder(nn.Module):
         if x.dim() != 3:
             raise ValueError(f"expected [B,H,W] or [B,1,H,W], got {tuple(x.shape)}")
         plan = eng.plan_for(x.shape[0], x.shape[1], x.shape[2])
-        plan.enc.x.copy_(x, non_blocking=True)
+        _copy_in(plan.enc.x, x)
         plan.enc.mask.fill_(1.0)
         if labels is not None:
-            plan.labels.copy_(labels.reshape(-1), non_blocking=True)
+            _copy_in(plan.labels, labels.reshape(-1))
         return plan
 
     # ---- forward / steps --------------------------------------------------------------------------------------------------

@@ -24,7 +24,9 @@ N = 100
 def timed(name, fn):
     torch.cuda.synchronize(); t0 = time.perf_counter(); fn(); torch.cuda.synchronize(); print(f"{name:50s} {(time.perf_counter()-t0)/N*1e3:.3f} ms/step", flush=True)
 def copies_only():
-    for b in DevicePrefetcher((hb[i % 3] for i in range(N)), dev): pass
+    pf = DevicePrefetcher((hb[i % 3] for i in range(N)), dev); saved = dict(DevicePrefetcher._choice); DevicePrefetcher._choice[pf._key] = 1
+    for b in pf: pass
+    DevicePrefetcher._choice.clear(); DevicePrefetcher._choice.update(saved)
 def direct():
     for i in range(N): model.train_step(hb[i % 3], opt, loss, dev, None)
 def pipelined():
@@ -47,6 +49,10 @@ timed("graph replay + sync each", replay_sync_each)
 timed("graph replay + background H2D + sync each", replay_with_background_copy)
 timed("train_step direct (blocking H2D)", direct)
 timed("train_step via DevicePrefetcher", pipelined)
+print("calibration (ms/step by candidate, 0 = inline):", {k: round(v * 1e3, 3) for k, v in DevicePrefetcher.calibration.items()}, "chosen", DevicePrefetcher._choice)
+timed("train_step via DevicePrefetcher (calibrated)", pipelined)
+timed("train_step direct (blocking H2D) again", direct)
+timed("train_step via DevicePrefetcher (calibrated) again", pipelined)
 if os.environ.get("MML_PROFILE"):
     import cProfile, pstats
     pr = cProfile.Profile(); pr.enable(); pipelined(); pr.disable()
