@@ -208,12 +208,22 @@ int mml_gmu_bwd(mml_ctx*, const float* dz, const float* h1, const float* h2, con
 /* MultimodalPooling branches (pooling.py:92-98): h = dropout(tanh(pre + bias)) for both modalities; pre bf16 [B][H] (GEMM
  * outputs of proj_a / proj_b), keep uint8 [B][H] or NULL, outputs fp32 [B][H] (consumed by mml_bn1d_fwd GATED / MAX2).
  * Backward: dz fp32 [B][H] (from mml_bn1d_bwd) -> dpre bf16 for both branches + bias gradients [H] (stored).
- * kind: 0 = max (winner takes the gradient, ties split), 1 = linear mix with mix_a / mix_b. */
+ * kind: 0 = max (winner takes the gradient, ties split), 1 = linear mix with mix_a / mix_b.
+ * comb (optional): bf16 [B][2H] = [h_a | h_b], the A operand of the attention / gate GEMM.  gate (optional, kind 1): per-sample
+ * mix g / 1-g instead of mix_a / mix_b;  dcomb (optional): bf16 [B][2H] gradient that came back through that GEMM, added in. */
 int mml_pool_fwd(mml_ctx*, const uint16_t* pre_a, const uint16_t* pre_b, const float* bias_a, const float* bias_b, const uint8_t* keep_a,
-                 const uint8_t* keep_b, float keep_scale, float* h_a, float* h_b, int B, int H, void* stream);
+                 const uint8_t* keep_b, float keep_scale, float* h_a, float* h_b, uint16_t* comb, int B, int H, void* stream);
 int mml_pool_bwd(mml_ctx*, const float* dz, const float* h_a, const float* h_b, const uint8_t* keep_a, const uint8_t* keep_b,
-                 float keep_scale, int kind, float mix_a, float mix_b, uint16_t* dpre_a, uint16_t* dpre_b, float* dbias_a,
-                 float* dbias_b, int B, int H, void* stream);
+                 float keep_scale, int kind, float mix_a, float mix_b, const float* gate, const uint16_t* dcomb, uint16_t* dpre_a,
+                 uint16_t* dpre_b, float* dbias_a, float* dbias_b, int B, int H, void* stream);
+/* "attention" / "gated" pooling head (pooling.py:55-72,113-126): hid bf16 [B][Hd] = GEMM output of layer 0 (bias b0 added here),
+ * t = tanh(hid + b0) (fp32, saved), s = W2 t + b2 with NS = 2 (attention: softmax over the two scores == (g, 1-g),
+ * g = sigmoid(s0 - s1)) or NS = 1 (gated: g = sigmoid(s0)); gate[b] = g feeds mml_bn1d_fwd(GATED).  Backward: dz fp32 [B][H] ->
+ * dw2 [NS][Hd], db2 [NS], db0 [Hd] (ACCUMULATED) and dhid bf16 [B][Hd] (dgrad / wgrad of layer 0 follow on the GEMM path). */
+int mml_att_fwd(mml_ctx*, const uint16_t* hid, const float* b0, const float* w2, const float* b2, float* t, float* gate, int B, int Hd,
+                int NS, void* stream);
+int mml_att_bwd(mml_ctx*, const float* dz, const float* h_a, const float* h_b, const float* gate, const float* t, const float* w2,
+                float* dw2, float* db2, float* db0, uint16_t* dhid, int B, int H, int Hd, int NS, void* stream);
 /* classifier tail (mmimdb.py:47, loss.py:52, mmimdb.py:238-239): logits = xn W^T + b, loss = mean BCE-with-logits over
  * B x NC, dlogits = (sigmoid - y) * grad_scale / (B NC), pred = sigmoid(logit) > threshold.  labels / loss / dlogits /
  * pred are optional; scratch: mml_bce_head_scratch_floats(B) floats, zero-initialised once by the caller. */

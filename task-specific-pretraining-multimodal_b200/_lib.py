@@ -89,8 +89,10 @@ SIGNATURES = {
     "mml_bn1d_bwd": (I32, [P, C.POINTER(BN1dBwdDesc), P]),
     "mml_gmu_fwd": (I32, [P, P, P, P, P, P, P, I32, I32, P]),
     "mml_gmu_bwd": (I32, [P, P, P, P, P, P, P, P, P, I32, I32, P]),
-    "mml_pool_fwd": (I32, [P, P, P, P, P, P, P, F32, P, P, I32, I32, P]),
-    "mml_pool_bwd": (I32, [P, P, P, P, P, P, F32, I32, F32, F32, P, P, P, P, I32, I32, P]),
+    "mml_pool_fwd": (I32, [P, P, P, P, P, P, P, F32, P, P, P, I32, I32, P]),
+    "mml_pool_bwd": (I32, [P, P, P, P, P, P, F32, I32, F32, F32, P, P, P, P, P, P, I32, I32, P]),
+    "mml_att_fwd": (I32, [P, P, P, P, P, P, P, I32, I32, I32, P]),
+    "mml_att_bwd": (I32, [P, P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, P]),
     "mml_bce_head_scratch_floats": (I64, [I32]),
     "mml_bce_head_fwd": (I32, [P, P, P, P, P, P, P, P, P, P, F32, F32, I32, I32, I32, P]),
     "mml_bce_head_bwd": (I32, [P, P, P, P, P, P, P, I32, I32, I32, P]),

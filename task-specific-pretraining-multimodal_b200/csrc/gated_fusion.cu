@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kGmuWarps * 32) gmu_bwd_kernel(const float* __
 __global__ void __launch_bounds__(256) pool_fwd_kernel(const uint16_t* __restrict__ pre_a, const uint16_t* __restrict__ pre_b,
                                                       const float* __restrict__ bias_a, const float* __restrict__ bias_b,
                                                       const uint8_t* __restrict__ keep_a, const uint8_t* __restrict__ keep_b, float keep_scale,
-                                                      float* __restrict__ h_a, float* __restrict__ h_b, int B, int H) {
+                                                      float* __restrict__ h_a, float* __restrict__ h_b, uint16_t* __restrict__ comb, int B, int H) {
   const size_t n = (size_t)B * H;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % H);
@@ -265,6 +265,11 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const uint16_t* __restric
     if (keep_b) b = keep_b[i] ? b * keep_scale : 0.f;
     h_a[i] = a;
     h_b[i] = b;
+    if (comb) {  // [h_a | h_b] rows as the bf16 A operand of the attention / gate GEMM (pooling.py:115)
+      const size_t r = i / H;
+      comb[r * 2 * H + c] = to_bf16(a);
+      comb[r * 2 * H + H + c] = to_bf16(b);
+    }
   }
 }
 
@@ -272,7 +277,8 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const uint16_t* __restric
 __global__ void __launch_bounds__(kCols* kRowGroups) pool_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ h_a,
                                                                     const float* __restrict__ h_b, const uint8_t* __restrict__ keep_a,
                                                                     const uint8_t* __restrict__ keep_b, float keep_scale, int kind, float mix_a,
-                                                                    float mix_b, uint16_t* __restrict__ dpre_a, uint16_t* __restrict__ dpre_b,
+                                                                    float mix_b, const float* __restrict__ gate, const uint16_t* __restrict__ dcomb,
+                                                                    uint16_t* __restrict__ dpre_a, uint16_t* __restrict__ dpre_b,
                                                                     float* __restrict__ dbias_a, float* __restrict__ dbias_b, int B, int H) {
   __shared__ float red[kRowGroups][kCols + 1];
   __shared__ float tot[kCols];
@@ -289,9 +295,17 @@ __global__ void __launch_bounds__(kCols* kRowGroups) pool_bwd_kernel(const float
       if (kind == 0) {  // max: winner takes the gradient, an exact tie splits it (torch.max backward)
         da = a > o ? z : (a == o ? 0.5f * z : 0.f);
         db = z - da;
+      } else if (gate) {  // attention / gated pooling: per-sample mix + the gradient that came back through the gate network
+        const float g = gate[b];
+        da = z * g;
+        db = z * (1.f - g);
       } else {
         da = z * mix_a;
         db = z * mix_b;
+      }
+      if (dcomb) {
+        da += bf16_val(dcomb[(size_t)b * 2 * H + c]);
+        db += bf16_val(dcomb[(size_t)b * 2 * H + H + c]);
       }
       // through dropout (h = tanh * scale where kept) and tanh
       const bool ka = keep_a ? keep_a[i] != 0 : true, kb = keep_b ? keep_b[i] != 0 : true;
@@ -310,6 +324,79 @@ __global__ void __launch_bounds__(kCols* kRowGroups) pool_bwd_kernel(const float
   if (valid && ty == 0) {
     dbias_a[c] = ta;
     dbias_b[c] = tb;
+  }
+}
+
+// ---- attention / gated pooling head (pooling.py:55-72, 113-126): t = tanh(hid + b0); s = W2 t + b2;
+// attention: (att_a, att_b) = softmax(s0, s1) = (g, 1 - g) with g = sigmoid(s0 - s1);  gated: g = sigmoid(s0).  One warp per sample.
+__global__ void __launch_bounds__(kGmuWarps * 32) att_fwd_kernel(const uint16_t* __restrict__ hid, const float* __restrict__ b0,
+                                                                 const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ t,
+                                                                 float* __restrict__ gate, int B, int Hd, int NS) {
+  const int row = blockIdx.x * kGmuWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= B) return;
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+  for (int k = lane; k < Hd; k += 32) {
+    const float v = tanhf(bf16_val(hid[(size_t)row * Hd + k]) + b0[k]);
+    t[(size_t)row * Hd + k] = v;
+    s0 += v * w2[k];
+    if (NS == 2) s1 += v * w2[Hd + k];
+  }
+  s0 = warp_sum(s0) + b2[0];
+  if (NS == 2) s0 -= warp_sum(s1) + b2[1];
+  if (lane == 0) gate[row] = 1.f / (1.f + expf(-s0));
+}
+
+__global__ void __launch_bounds__(kGmuWarps * 32) att_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ h_a,
+                                                                 const float* __restrict__ h_b, const float* __restrict__ gate,
+                                                                 const float* __restrict__ t, const float* __restrict__ w2, float* __restrict__ dw2,
+                                                                 float* __restrict__ db2, float* __restrict__ db0, uint16_t* __restrict__ dhid, int B,
+                                                                 int H, int Hd, int NS) {
+  __shared__ float s_ds[kGmuWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * kGmuWarps, row = row0 + warp;
+  float ds = 0.f;  // gradient at s0 (attention: d s1 = -d s0)
+  if (row < B) {
+    float dg = 0.f;
+#pragma unroll 4
+    for (int c = lane; c < H; c += 32) {
+      const size_t i = (size_t)row * H + c;
+      dg += dz[i] * (h_a[i] - h_b[i]);
+    }
+    dg = warp_sum(dg);
+    const float g = gate[row];
+    ds = dg * g * (1.f - g);
+#pragma unroll 4
+    for (int k = lane; k < Hd; k += 32) {
+      const float tv = t[(size_t)row * Hd + k];
+      const float wv = NS == 2 ? w2[k] - w2[Hd + k] : w2[k];
+      dhid[(size_t)row * Hd + k] = to_bf16(ds * wv * (1.f - tv * tv));
+    }
+  }
+  if (lane == 0) s_ds[warp] = ds;
+  __syncthreads();
+  // parameter gradients: the CTA's rows are summed here, CTAs meet in global atomics (the buffers are zeroed once per step)
+  float bsum = 0.f;
+  for (int k = threadIdx.x; k < Hd; k += blockDim.x) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int r = 0; r < kGmuWarps; ++r) {
+      if (row0 + r < B) {
+        const float tv = t[(size_t)(row0 + r) * Hd + k];
+        const float wv = NS == 2 ? w2[k] - w2[Hd + k] : w2[k];
+        a += s_ds[r] * tv;
+        b += s_ds[r] * wv * (1.f - tv * tv);
+      }
+    }
+    atomicAdd(dw2 + k, a);
+    if (NS == 2) atomicAdd(dw2 + Hd + k, -a);
+    atomicAdd(db0 + k, b);
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int r = 0; r < kGmuWarps; ++r) bsum += s_ds[r];
+    atomicAdd(db2, bsum);
+    if (NS == 2) atomicAdd(db2 + 1, -bsum);
   }
 }
 
@@ -544,24 +631,43 @@ int mml_gmu_bwd(mml_ctx* ctx, const float* dz, const float* h1, const float* h2,
 }
 
 int mml_pool_fwd(mml_ctx* ctx, const uint16_t* pre_a, const uint16_t* pre_b, const float* bias_a, const float* bias_b, const uint8_t* keep_a,
-                 const uint8_t* keep_b, float keep_scale, float* h_a, float* h_b, int B, int H, void* stream) {
+                 const uint8_t* keep_b, float keep_scale, float* h_a, float* h_b, uint16_t* comb, int B, int H, void* stream) {
   MML_REQUIRE(ctx, ctx && pre_a && pre_b && bias_a && bias_b && h_a && h_b && B >= 1 && H >= 1, "pool_fwd: bad arguments");
   MML_REQUIRE(ctx, (keep_a == nullptr) == (keep_b == nullptr), "pool_fwd: both dropout masks or none");
   int grid = (int)mml_ceil_div((int64_t)B * H, 256);
   if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-  pool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pre_a, pre_b, bias_a, bias_b, keep_a, keep_b, keep_scale, h_a, h_b, B, H);
+  pool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pre_a, pre_b, bias_a, bias_b, keep_a, keep_b, keep_scale, h_a, h_b, comb, B, H);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }
 
 int mml_pool_bwd(mml_ctx* ctx, const float* dz, const float* h_a, const float* h_b, const uint8_t* keep_a, const uint8_t* keep_b,
-                 float keep_scale, int kind, float mix_a, float mix_b, uint16_t* dpre_a, uint16_t* dpre_b, float* dbias_a,
-                 float* dbias_b, int B, int H, void* stream) {
+                 float keep_scale, int kind, float mix_a, float mix_b, const float* gate, const uint16_t* dcomb, uint16_t* dpre_a,
+                 uint16_t* dpre_b, float* dbias_a, float* dbias_b, int B, int H, void* stream) {
   MML_REQUIRE(ctx, ctx && dz && h_a && h_b && dpre_a && dpre_b && dbias_a && dbias_b && B >= 1 && H >= 1, "pool_bwd: bad arguments");
   MML_REQUIRE(ctx, (keep_a == nullptr) == (keep_b == nullptr), "pool_bwd: both dropout masks or none");
   MML_REQUIRE(ctx, kind == 0 || kind == 1, "pool_bwd: kind must be 0 (max) or 1 (linear mix)");
   pool_bwd_kernel<<<(unsigned)mml_ceil_div(H, kCols), dim3(kCols, kRowGroups), 0, (cudaStream_t)stream>>>(
-      dz, h_a, h_b, keep_a, keep_b, keep_scale, kind, mix_a, mix_b, dpre_a, dpre_b, dbias_a, dbias_b, B, H);
+      dz, h_a, h_b, keep_a, keep_b, keep_scale, kind, mix_a, mix_b, gate, dcomb, dpre_a, dpre_b, dbias_a, dbias_b, B, H);
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
+int mml_att_fwd(mml_ctx* ctx, const uint16_t* hid, const float* b0, const float* w2, const float* b2, float* t, float* gate, int B, int Hd,
+                int NS, void* stream) {
+  MML_REQUIRE(ctx, ctx && hid && b0 && w2 && b2 && t && gate && B >= 1 && Hd >= 1, "att_fwd: bad arguments");
+  MML_REQUIRE(ctx, NS == 1 || NS == 2, "att_fwd: 1 (gated) or 2 (attention) scores");
+  att_fwd_kernel<<<(unsigned)mml_ceil_div(B, kGmuWarps), kGmuWarps * 32, 0, (cudaStream_t)stream>>>(hid, b0, w2, b2, t, gate, B, Hd, NS);
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
+int mml_att_bwd(mml_ctx* ctx, const float* dz, const float* h_a, const float* h_b, const float* gate, const float* t, const float* w2,
+                float* dw2, float* db2, float* db0, uint16_t* dhid, int B, int H, int Hd, int NS, void* stream) {
+  MML_REQUIRE(ctx, ctx && dz && h_a && h_b && gate && t && w2 && dw2 && db2 && db0 && dhid && B >= 1 && H >= 1 && Hd >= 1, "att_bwd: bad arguments");
+  MML_REQUIRE(ctx, NS == 1 || NS == 2, "att_bwd: 1 (gated) or 2 (attention) scores");
+  att_bwd_kernel<<<(unsigned)mml_ceil_div(B, kGmuWarps), kGmuWarps * 32, 0, (cudaStream_t)stream>>>(dz, h_a, h_b, gate, t, w2, dw2, db2, db0, dhid,
+                                                                                                   B, H, Hd, NS);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }

@@ -64,6 +64,11 @@ class _GatedPlan:
             raise NotImplementedError("mml_b200 gated fusion expects equal embedding / gate widths (mmimdb_baseline.yaml: 512)")
         self.pool_type = model.fusion_module.pooling_type if self.pooling else None
         self.pool_p = float(model.fusion_module.dropout) if self.pooling else 0.0
+        self.pool_net = {"attention": "fusion_module.attention_layer", "gated": "fusion_module.gate_layer"}.get(self.pool_type)
+        if self.pool_net is not None:
+            self.Hd = params[self.pool_net + ".0.weight"].shape[0]
+            if self.Hd % 64:
+                raise NotImplementedError("the pooling network's hidden width must be a multiple of 64 for the tensor-core GEMM")
         if E % 64 or H % 64:
             raise NotImplementedError("embedding and hidden widths must be multiples of 64 for the tensor-core GEMMs")
         if len(model.mm_mlp.net[1].layers) != 2 or len(model.mm_mlp.net[4].layers) != 2:
@@ -105,6 +110,9 @@ class _GatedPlan:
         self.dz = f32(B, E)
         self.dh1p, self.dh2p, self.deI, self.deT = b16(B, E), b16(B, E), b16(B, E), b16(B, E)
         self.dxnI, self.dxnT = b16(B, LI), b16(B, LT)
+        if self.pool_net is not None:  # attention / gated pooling: [a | b] -> Linear -> tanh -> Linear -> softmax / sigmoid
+            self.comb, self.dcomb = b16(B, 2 * E), b16(B, 2 * E)
+            self.hidp, self.dhidp, self.tpool = b16(B, self.Hd), b16(B, self.Hd), f32(B, self.Hd)
         # ---- pinned host mirrors
         self.h_loss = torch.zeros(1).pin_memory()
         self.h_pred = torch.zeros(B, NC, dtype=torch.uint8).pin_memory()
@@ -148,11 +156,11 @@ class _GatedPlan:
         if not self.pooling:
             self.f_bn0 = ops.bn1d_fwd_desc(ops.BN1D_GATED, B, E, g0, b0, rm0, rv0, h1=self.h1, h2=self.h2, gate=self.gate, xhat=self.xh0,
                                            invstd=self.inv["0"], y_bf16=self.xn0, **kw)
-        else:  # pooling.py:100-111: max | (a + b) / 2 | a + b
-            self.mix = {"max": (1.0, 1.0), "avg": (0.5, 0.5), "average": (0.5, 0.5), "sum": (1.0, 1.0)}[self.pool_type]
+        else:  # pooling.py:100-126: max | (a + b) / 2 | a + b | att_a a + att_b b | g a + (1 - g) b
+            self.mix = {"max": (1.0, 1.0), "avg": (0.5, 0.5), "average": (0.5, 0.5), "sum": (1.0, 1.0)}.get(self.pool_type, (0.0, 0.0))
             mode0 = ops.BN1D_MAX2 if self.pool_type == "max" else ops.BN1D_GATED
-            self.f_bn0 = ops.bn1d_fwd_desc(mode0, B, E, g0, b0, rm0, rv0, h1=self.h1, h2=self.h2, xhat=self.xh0, invstd=self.inv["0"],
-                                           y_bf16=self.xn0, mix_a=self.mix[0], mix_b=self.mix[1], **kw)
+            self.f_bn0 = ops.bn1d_fwd_desc(mode0, B, E, g0, b0, rm0, rv0, h1=self.h1, h2=self.h2, gate=self.gate if self.pool_net else None,
+                                           xhat=self.xh0, invstd=self.inv["0"], y_bf16=self.xn0, mix_a=self.mix[0], mix_b=self.mix[1], **kw)
         self.f_bn1 = ops.bn1d_fwd_desc(ops.BN1D_MAXOUT, B, H, g1, b1, rm1, rv1, pre=self.pre1, keep=self.keep1, keep_scale=scale, xhat=self.xh1,
                                        invstd=self.inv["1"], y_bf16=self.xn1, **kw)
         self.f_bn2 = ops.bn1d_fwd_desc(ops.BN1D_MAXOUT, B, H, g2, b2, rm2, rv2, pre=self.pre2, keep=self.keep2, keep_scale=scale, xhat=self.xh2,
@@ -187,6 +195,11 @@ class _GatedPlan:
         if self.pooling:
             self.pb = (par(P, "fusion_module.proj_a.bias"), par(P, "fusion_module.proj_b.bias"))
             self.dpb = (par(G, "fusion_module.proj_a.bias"), par(G, "fusion_module.proj_b.bias"))
+            if self.pool_net is not None:
+                n0, n2 = self.pool_net + ".0", self.pool_net + ".2"
+                self.gemA = (gemm(2 * E, self.Hd), par(Wb, n0 + ".weight"), par(G, n0 + ".weight"))
+                self.att = (par(P, n0 + ".bias"), par(P, n2 + ".weight"), par(P, n2 + ".bias"))
+                self.datt = (par(G, n0 + ".bias"), par(G, n2 + ".weight"), par(G, n2 + ".bias"))
         else:
             self.wz, self.dwz = fs.flat_slice(P, "fusion_module.hidden_sigmoid.weight"), fs.flat_slice(G, "fusion_module.hidden_sigmoid.weight")
         self.w7, self.b7 = par(P, "mm_mlp.net.7.weight"), par(P, "mm_mlp.net.7.bias")
@@ -231,7 +244,10 @@ class _GatedPlan:
         if self.pooling:
             drop = train and dropout and self.pool_p > 0
             ops.pool_fwd(self.h1p, self.h2p, self.pb[0], self.pb[1], self.keepA if drop else None, self.keepB if drop else None,
-                         1.0 / (1.0 - self.pool_p), self.h1, self.h2)
+                         1.0 / (1.0 - self.pool_p), self.h1, self.h2, self.comb if self.pool_net else None)
+            if self.pool_net is not None:
+                self._fprop(self.gemA, self.comb, self.hidp)
+                ops.att_fwd(self.hidp, self.att[0], self.att[1], self.att[2], self.tpool, self.gate)
         else:
             ops.gmu_fwd(self.h1p, self.h2p, self.wz, self.h1, self.h2, self.gate)
         ops.bn1d_fwd(self.f_bn0, train)
@@ -258,8 +274,12 @@ class _GatedPlan:
         ops.bn1d_bwd(self.b_bn0)
         if self.pooling:
             drop = self.pool_p > 0
+            if self.pool_net is not None:
+                ops.att_bwd(self.dz, self.h1, self.h2, self.gate, self.tpool, self.att[1], self.datt[1], self.datt[2], self.datt[0], self.dhidp)
+                self._bprop(self.gemA, self.comb, self.dhidp, self.dcomb)
             ops.pool_bwd(self.dz, self.h1, self.h2, self.keepA if drop else None, self.keepB if drop else None, 1.0 / (1.0 - self.pool_p),
-                         0 if self.pool_type == "max" else 1, self.mix[0], self.mix[1], self.dh1p, self.dh2p, self.dpb[0], self.dpb[1])
+                         0 if self.pool_type == "max" else 1, self.mix[0], self.mix[1], self.dh1p, self.dh2p, self.dpb[0], self.dpb[1],
+                         gate=self.gate if self.pool_net else None, dcomb=self.dcomb if self.pool_net else None)
         else:
             ops.gmu_bwd(self.dz, self.h1, self.h2, self.gate, self.wz, self.dwz, self.dh1p, self.dh2p)
         self._fork([lambda: self._bprop(self.gem1, self.eI, self.dh1p, self.deI), lambda: self._bprop(self.gemI, self.xnI, self.deI, self.dxnI),

@@ -5,8 +5,8 @@ Same classes and constructors as the YAML tags build them (configs/mmimdb/centra
 ``MMIMDbModalityEncoder(input_dim, output_dim)``, ``GatedBiModalNetwork(input_one_dim, input_two_dim, output_one_dim,
 output_two_dim, use_bias=False)``, ``MaxOut``, ``MLPGenreClassifier(input_size, output_size, hidden_size)`` and
 ``MMIMDb(image_encoder, text_encoder, gated_bimodal_network=..., classifier=..., binary_threshold=0.5)``; same sub-module
-names, hence the same 38-entry ``state_dict()`` (``multimodal_pooling={...}`` builds ``MultimodalPooling`` with the max /
-avg / sum pooling types instead of the GMU, mmimdb_pooling.yaml); same ``forward(I, T)`` / ``train_step`` / ``validation_step`` /
+names, hence the same 38-entry ``state_dict()`` (``multimodal_pooling={...}`` builds ``MultimodalPooling`` -- max / avg / sum /
+attention / gated -- instead of the GMU, mmimdb_pooling.yaml); same ``forward(I, T)`` / ``train_step`` / ``validation_step`` /
 ``get_embeddings`` / ``get_encoder`` / ``logits_transform``.  The torch modules inside are parameter CONTAINERS only (they
 give the reference's initialisation and names); the arithmetic of a step is one fused schedule in libmml_b200.so
 (``gated_engine.py``).  Unsupported requests (pooling fusion, biased GMU, embeddings as inputs, other optimizers or
@@ -55,16 +55,14 @@ class GatedBiModalNetwork(nn.Module):
 
 
 class MultimodalPooling(nn.Module):
-    """pooling.py:6-126 -- tanh(proj) of both embeddings, dropout, then an element-wise max / average / sum (container; fused
-    into the step).  The ``attention`` and ``gated`` pooling types are not built yet and raise."""
+    """pooling.py:6-126 -- tanh(proj) of both embeddings, dropout, then an element-wise max / average / sum, or a per-sample
+    mix whose weights come from a small attention / gate network on [a | b] (container; fused into the step)."""
 
     def __init__(self, input_dim_a: int, input_dim_b: int, output_dim: int, pooling_type: str = "gated", hidden_dim: Optional[int] = None,
                  dropout: float = 0.0):
         super().__init__()
         self.pooling_type = pooling_type.lower()
-        if self.pooling_type in ("attention", "gated"):
-            raise NotImplementedError(f"mml_b200 MultimodalPooling: pooling_type '{pooling_type}' is not built yet (max / avg / sum are)")
-        if self.pooling_type not in ("max", "avg", "average", "sum"):
+        if self.pooling_type not in ("max", "avg", "average", "sum", "attention", "gated"):
             raise ValueError(f"Unknown pooling type: {pooling_type}")
         self.input_dim_a, self.input_dim_b, self.output_dim = input_dim_a, input_dim_b, output_dim
         self.hidden_dim = hidden_dim or max(input_dim_a, input_dim_b)
@@ -73,6 +71,10 @@ class MultimodalPooling(nn.Module):
         self.proj_b = nn.Linear(input_dim_b, output_dim)
         self.dropout_layer = nn.Dropout(dropout) if dropout > 0 else nn.Identity()
         self.activation = nn.Tanh()
+        if self.pooling_type == "attention":  # pooling.py:55-63
+            self.attention_layer = nn.Sequential(nn.Linear(output_dim * 2, self.hidden_dim), nn.Tanh(), nn.Linear(self.hidden_dim, 2), nn.Softmax(dim=1))
+        elif self.pooling_type == "gated":    # pooling.py:65-72
+            self.gate_layer = nn.Sequential(nn.Linear(output_dim * 2, self.hidden_dim), nn.Tanh(), nn.Linear(self.hidden_dim, 1), nn.Sigmoid())
 
     def forward(self, x_a, x_b):
         raise NotImplementedError("mml_b200.MultimodalPooling is evaluated inside the fused MMIMDb step only")

@@ -370,19 +370,21 @@ def bce_head_bwd(dlogits, xn, w, dw, db, dxn) -> None:
                                    _p(db, torch.float32), _p(dxn, torch.bfloat16), B, H, NC, _stream(xn)), "mml_bce_head_bwd")
 
 
-def pool_fwd(pre_a, pre_b, bias_a, bias_b, keep_a, keep_b, keep_scale: float, h_a, h_b) -> None:
+def pool_fwd(pre_a, pre_b, bias_a, bias_b, keep_a, keep_b, keep_scale: float, h_a, h_b, comb=None) -> None:
     B, H = h_a.shape
     c = _ctx(h_a)
     c.check(c.lib.mml_pool_fwd(c.handle, _p(pre_a, torch.bfloat16), _p(pre_b, torch.bfloat16), _p(bias_a, torch.float32), _p(bias_b, torch.float32),
                                _p(keep_a, torch.uint8), _p(keep_b, torch.uint8), float(keep_scale), _p(h_a, torch.float32), _p(h_b, torch.float32),
-                               B, H, _stream(h_a)), "mml_pool_fwd")
+                               _p(comb, torch.bfloat16), B, H, _stream(h_a)), "mml_pool_fwd")
 
 
-def pool_bwd(dz, h_a, h_b, keep_a, keep_b, keep_scale: float, kind: int, mix_a: float, mix_b: float, dpre_a, dpre_b, dbias_a, dbias_b) -> None:
+def pool_bwd(dz, h_a, h_b, keep_a, keep_b, keep_scale: float, kind: int, mix_a: float, mix_b: float, dpre_a, dpre_b, dbias_a, dbias_b,
+             gate=None, dcomb=None) -> None:
     B, H = h_a.shape
     c = _ctx(h_a)
     c.check(c.lib.mml_pool_bwd(c.handle, _p(dz, torch.float32), _p(h_a, torch.float32), _p(h_b, torch.float32), _p(keep_a, torch.uint8),
-                               _p(keep_b, torch.uint8), float(keep_scale), int(kind), float(mix_a), float(mix_b), _p(dpre_a, torch.bfloat16),
+                               _p(keep_b, torch.uint8), float(keep_scale), int(kind), float(mix_a), float(mix_b), _p(gate, torch.float32),
+                               _p(dcomb, torch.bfloat16), _p(dpre_a, torch.bfloat16),
                                _p(dpre_b, torch.bfloat16), _p(dbias_a, torch.float32), _p(dbias_b, torch.float32), B, H, _stream(h_a)), "mml_pool_bwd")
 
 
@@ -405,3 +407,19 @@ def mono_head_bwd(pooled, emb, dlogits, fc_w, cls_w, d_fc_w, d_fc_b, d_cls_w, d_
     c.check(c.lib.mml_mono_head_bwd(c.handle, _p(pooled, f32), _p(emb, f32), _p(dlogits, f32), _p(fc_w, f32), _p(cls_w, f32), _p(d_fc_w, f32),
                                     _p(d_fc_b, f32), _p(d_cls_w, f32), _p(d_cls_b, f32), _p(demb, f32), _p(dpooled, f32), B, Fd, E, NC,
                                     _stream(pooled)), "mml_mono_head_bwd")
+
+
+def att_fwd(hid, b0, w2, b2, t, gate) -> None:
+    B, Hd = t.shape
+    c = _ctx(t)
+    c.check(c.lib.mml_att_fwd(c.handle, _p(hid, torch.bfloat16), _p(b0, torch.float32), _p(w2, torch.float32), _p(b2, torch.float32),
+                              _p(t, torch.float32), _p(gate, torch.float32), B, Hd, w2.shape[0], _stream(t)), "mml_att_fwd")
+
+
+def att_bwd(dz, h_a, h_b, gate, t, w2, dw2, db2, db0, dhid) -> None:
+    B, H = h_a.shape
+    Hd = t.shape[1]
+    c = _ctx(t)
+    c.check(c.lib.mml_att_bwd(c.handle, _p(dz, torch.float32), _p(h_a, torch.float32), _p(h_b, torch.float32), _p(gate, torch.float32),
+                              _p(t, torch.float32), _p(w2, torch.float32), _p(dw2, torch.float32), _p(db2, torch.float32), _p(db0, torch.float32),
+                              _p(dhid, torch.bfloat16), B, H, Hd, w2.shape[0], _stream(t)), "mml_att_bwd")

@@ -360,8 +360,8 @@ def test_unsupported_requests_raise():
     from mml_b200.mmimdb import GatedBiModalNetwork, MLPGenreClassifier, MMIMDb, MMIMDbModalityEncoder
 
     dev = torch.device(DEV)
-    with pytest.raises(NotImplementedError):
-        MMIMDb(MMIMDbModalityEncoder(8, 64), MMIMDbModalityEncoder(8, 64), multimodal_pooling={"pooling_type": "attention"}, classifier=MLPGenreClassifier(64, 3, 64))
+    with pytest.raises(ValueError):
+        MMIMDb(MMIMDbModalityEncoder(8, 64), MMIMDbModalityEncoder(8, 64), multimodal_pooling={"pooling_type": "bilinear"}, classifier=MLPGenreClassifier(64, 3, 64))
     with pytest.raises(NotImplementedError):
         GatedBiModalNetwork(64, 64, 64, 64, use_bias=True)
     model = build()
@@ -420,7 +420,42 @@ def build_pooling(pooling_type, graphs=True):
     return model
 
 
-@pytest.mark.parametrize("pooling_type", ["max", "avg", "sum"])
+@pytest.mark.parametrize("B,H,Hd,NS", [(128, 512, 512, 2), (128, 512, 512, 1), (7, 64, 128, 2)])
+def test_attention_pool_kernels(B, H, Hd, NS):
+    """att_fwd / att_bwd / pool_bwd(gate, dcomb) against torch autograd of pooling.py:113-126 (given the layer-0 GEMM output)."""
+    from mml_b200 import ops
+
+    g = torch.Generator().manual_seed(B + NS)
+    a0, b0_ = torch.tanh(torch.randn(B, H, generator=g)), torch.tanh(torch.randn(B, H, generator=g))
+    hid = _bf16(torch.randn(B, Hd, generator=g))
+    bias0, w2, bias2 = torch.randn(Hd, generator=g) * 0.1, torch.randn(NS, Hd, generator=g) * 0.1, torch.randn(NS, generator=g) * 0.1
+    dz = torch.randn(B, H, generator=g)
+    a, b = a0.clone().requires_grad_(True), b0_.clone().requires_grad_(True)
+    hd, v0, vw, v2 = hid.clone().requires_grad_(True), bias0.clone().requires_grad_(True), w2.clone().requires_grad_(True), bias2.clone().requires_grad_(True)
+    t = torch.tanh(hd + v0)
+    s = t @ vw.t() + v2
+    gate = torch.softmax(s, 1)[:, 0:1] if NS == 2 else torch.sigmoid(s)
+    z = gate * a + (1 - gate) * b
+    z.backward(dz)
+    dev = lambda x, dt=None: (x if dt is None else x.to(dt)).to(DEV).contiguous()
+    tt, gt = torch.zeros(B, Hd, device=DEV), torch.zeros(B, device=DEV)
+    ops.att_fwd(dev(hid, torch.bfloat16), dev(bias0), dev(w2), dev(bias2), tt, gt)
+    assert torch.allclose(gt.cpu(), gate.detach().reshape(-1), rtol=1e-5, atol=1e-6) and torch.allclose(tt.cpu(), t.detach(), rtol=1e-5, atol=1e-6)
+    dw2, db2, db0 = torch.zeros(NS, Hd, device=DEV), torch.zeros(NS, device=DEV), torch.zeros(Hd, device=DEV)
+    dhid = torch.zeros(B, Hd, device=DEV, dtype=torch.bfloat16)
+    ha, hb = dev(a0), dev(b0_)
+    ops.att_bwd(dev(dz), ha, hb, gt, tt, dev(w2), dw2, db2, db0, dhid)
+    assert rel(dw2.cpu(), vw.grad) < 1e-4 and rel(db2.cpu(), v2.grad) < 1e-4 and rel(db0.cpu(), v0.grad) < 1e-4
+    assert rel(dhid.float().cpu(), hd.grad) < 5e-3
+    # the branch gradients: per-sample mix (da = dz g, db = dz (1 - g)), no dropout; tanh backward is applied by pool_bwd, so compare
+    # against a.grad * (1 - a^2)
+    da, db_ = torch.zeros(B, H, device=DEV, dtype=torch.bfloat16), torch.zeros(B, H, device=DEV, dtype=torch.bfloat16)
+    gba, gbb = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    ops.pool_bwd(dev(dz), ha, hb, None, None, 1.0, 1, 0.0, 0.0, da, db_, gba, gbb, gate=gt, dcomb=None)
+    assert rel(da.float().cpu(), a.grad * (1 - a0 * a0)) < 5e-3 and rel(db_.float().cpu(), b.grad * (1 - b0_ * b0_)) < 5e-3
+
+
+@pytest.mark.parametrize("pooling_type", ["max", "avg", "sum", "attention", "gated"])
 def test_pooling_variants_match_oracle(pooling_type):
     B, seed = 16, 5
     model = build_pooling(pooling_type, graphs=False)
