@@ -107,7 +107,13 @@ def import_reference():
     from models.gates import GatedBiModalNetwork
     from models.mmimdb import MLPGenreClassifier, MMIMDb, MMIMDbModalityEncoder
 
+    from models.msa.networks.classifier import FcClassifier
+    from models.msa.networks.lstm import LSTMEncoder
+    from models.msa.networks.textcnn import TextCNN
+    from models.msa.utt_fusion import UttFusionModel
+
     ns = types.SimpleNamespace(
+        UttFusionModel=UttFusionModel, LSTMEncoder=LSTMEncoder, TextCNN=TextCNN, FcClassifier=FcClassifier,
         MMIMDb=MMIMDb,
         MMIMDbModalityEncoder=MMIMDbModalityEncoder,
         MLPGenreClassifier=MLPGenreClassifier,

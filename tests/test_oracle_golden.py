@@ -153,3 +153,30 @@ def test_monomodal_oracle_matches_reference():
             l2 = np.array([float(out["grads"][k].double().norm()) for k in g["grad_keys"]])
             assert np.allclose(l2, g["grad_l2"], rtol=1e-3, atol=1e-7)
             assert np.abs(out["grads"]["classifier.weight"].numpy() - g["grad::classifier.weight"]).max() < 1e-6
+
+
+def test_mosi_utt_fusion_oracle_matches_reference():
+    """config 4: the oracle for the MOSI / UttFusion step against the recorded reference run -- LSTM x2, TextCNN,
+    FcClassifier, CE, clip_grad_norm_(1.0), Adam; zero-padded variable-length sequences and all seven missing patterns."""
+    import utt_fusion_oracle as U
+
+    g = np.load(os.path.join(GOLD, "mosi_b8.npz"))
+    batch, seed, steps = (int(v) for v in g["meta"])
+    torch.manual_seed(0)
+    state = U.init_utt_state()
+    assert len(state) == 24 and sum(v.numel() for v in state.values()) == 1_296_451
+    d = U.synthetic_batch(batch, seed)
+    assert int(d["lengths"].min()) < 50 and len(set(d["pattern_name"])) >= 4
+    opt_state = {}
+    for step in range(steps):
+        out = U.train_step(state, opt_state, d["audio_masked"], d["video_masked"], d["text_masked"], d["labels"], d["keeps"])
+        assert abs(out["loss"] - float(g["losses"][step])) < (1e-5 if step == 0 else 2e-3)
+        if step == 0:
+            assert np.allclose(out["logits"].numpy(), g["logits"], rtol=1e-4, atol=1e-5)
+            assert abs(out["grad_norm"] - float(g["grad_norm"])) < 1e-4
+            l2 = np.array([float(out["grads"][k].double().norm()) for k in g["grad_keys"]])
+            assert np.allclose(l2, g["grad_l2"], rtol=1e-3, atol=1e-9)
+            assert np.abs(out["grads"]["netA.rnn.bias_hh_l0"].numpy() - g["grad::netA.rnn.bias_hh_l0"]).max() < 1e-6
+    assert np.allclose(np.array([float(v.double().norm()) for v in state.values()]), g["state_l2"], rtol=2e-3)
+    ev = U.validation_step(state, d["audio_masked"], d["video_masked"], d["text_masked"], d["labels"])
+    assert np.abs(ev["logits"].numpy() - g["eval_logits"]).max() < 1e-2
