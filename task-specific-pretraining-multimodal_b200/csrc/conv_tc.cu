@@ -22,6 +22,8 @@
 using namespace mml;
 
 namespace {
+int g_reserve_sms = 0;  // SMs left free by the persistent kernels (for the concurrent small-kernel stream); mml_debug_set key 3
+
 
 struct Tap {
   int8_t map;   // which input view
@@ -1148,7 +1150,8 @@ int launch_halo_t(mml_ctx* ctx, const HaloMaps& maps, const HaloParams& p, cudaS
     if (rc) return rc;
     configured = true;
   }
-  int grid = p.num_super < ctx->sm_count ? p.num_super : ctx->sm_count;
+  const int sms = ctx->sm_count - g_reserve_sms > 8 ? ctx->sm_count - g_reserve_sms : 8;
+  int grid = p.num_super < sms ? p.num_super : sms;
   conv_halo_kernel<CCH, BLOCK_N, T, W_RES, B_MN><<<grid, kHaloThreads, L::kBytes, st>>>(maps, p);
   MML_LAUNCHED(ctx);
   return MML_OK;
@@ -1225,6 +1228,7 @@ extern "C" {
 /* experiment / A-B switches: key 1 = halo kernel enable (0/1), key 2 = halo descriptor base-offset mode (0/1) */
 int mml_debug_set(int key, int value) {
   if (key == 1) g_halo_enable = value;
+  if (key == 3) g_reserve_sms = value < 0 ? 0 : value;
   else if (key == 2) g_halo_base_offset_mode = value;
   else return MML_ERR_INVALID;
   return MML_OK;
@@ -1320,7 +1324,8 @@ int mml_conv_wgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, cons
   HaloGeom hg;
   if (g_halo_enable && g->R == 3 && g->stride == 1 && g->pad == 1 && n_taps == 9 && halo_geometry(Q, P, g->N, g->C, g->K, &hg) && ctx->workspace) {
     const int CH = g->C / 64;
-    int ctas = CH == 1 ? ctx->sm_count : ctx->sm_count / 3;
+    const int sms = ctx->sm_count - g_reserve_sms > 8 ? ctx->sm_count - g_reserve_sms : 8;
+    int ctas = CH == 1 ? sms : sms / 3;
     if (ctas > hg.m_tiles) ctas = hg.m_tiles;
     const size_t need = (size_t)ctas * g->K * 9 * g->C * sizeof(float);
     if (need <= ctx->workspace_bytes) {

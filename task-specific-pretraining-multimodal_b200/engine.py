@@ -590,6 +590,8 @@ class _StepPlan:
         # schedule variants (A/B-tested on B200): defaults are the measured best
         self.tune = {"adam_split": _os.environ.get("MML_ADAM_SPLIT", "1") == "1", "head_side": _os.environ.get("MML_HEAD_SIDE", "0") == "1",
                      "skip": _os.environ.get("MML_SKIP_ENCODER", ""), "side_prio": _os.environ.get("MML_SIDE_PRIO", "-1")}
+        if _os.environ.get("MML_RESERVE_SMS"):  # experiment: persistent conv kernels leave SMs free for the image-encoder stream
+            ops.debug_set(3, int(_os.environ["MML_RESERVE_SMS"]))
         if _os.environ.get("MML_WGRAD_STREAMS", "1") == "1":
             self.audio.wgrad_stream = torch.cuda.Stream(device=dev)
             self.image.wgrad_stream = torch.cuda.Stream(device=dev)
