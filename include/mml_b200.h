@@ -51,6 +51,9 @@ const char* mml_last_error(const mml_ctx* ctx); /* ctx may be NULL: error of a f
 int mml_ctx_sm_count(const mml_ctx* ctx);
 /* number of kernels this library has launched since the ctx was created (bench.py's gpu_launches) */
 int64_t mml_ctx_launch_count(const mml_ctx* ctx);
+/* SMs the persistent convolution kernels may occupy from now on (0 or > SM count = all).  Read at launch time, so it can differ
+ * per launch; the two-encoder step keeps a few SMs free for the image encoder's stream of small kernels. */
+int mml_ctx_set_sm_budget(mml_ctx* ctx, int sms);
 
 /* tuning / A-B switches for experiments (not part of the reference surface): key 1 = use the halo conv kernel (default 1),
  * key 2 = halo descriptor base-offset mode (default 0) */

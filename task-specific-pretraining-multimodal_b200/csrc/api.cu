@@ -23,6 +23,11 @@ const char* mml_last_error(const mml_ctx* ctx) { return ctx ? ctx->err : g_creat
 int mml_ctx_sm_count(const mml_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
 int64_t mml_ctx_launch_count(const mml_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int mml_ctx_set_sm_budget(mml_ctx* ctx, int sms) {
+  if (!ctx) return MML_ERR_INVALID;
+  ctx->sm_budget = sms <= 0 || sms > ctx->sm_count ? 0 : (sms < 8 ? 8 : sms);
+  return MML_OK;
+}
 
 int mml_ctx_create(int device, mml_ctx** out) {
   if (!out) return mml_set_error(nullptr, MML_ERR_INVALID, "mml_ctx_create: out is NULL");

@@ -22,7 +22,7 @@
 using namespace mml;
 
 namespace {
-int g_reserve_sms = 0;  // SMs left free by the persistent kernels (for the concurrent small-kernel stream); mml_debug_set key 3
+inline int persistent_sms(const mml_ctx* ctx) { return ctx->sm_budget > 0 ? ctx->sm_budget : ctx->sm_count; }
 
 
 struct Tap {
@@ -1150,7 +1150,7 @@ int launch_halo_t(mml_ctx* ctx, const HaloMaps& maps, const HaloParams& p, cudaS
     if (rc) return rc;
     configured = true;
   }
-  const int sms = ctx->sm_count - g_reserve_sms > 8 ? ctx->sm_count - g_reserve_sms : 8;
+  const int sms = persistent_sms(ctx);
   int grid = p.num_super < sms ? p.num_super : sms;
   conv_halo_kernel<CCH, BLOCK_N, T, W_RES, B_MN><<<grid, kHaloThreads, L::kBytes, st>>>(maps, p);
   MML_LAUNCHED(ctx);
@@ -1228,7 +1228,6 @@ extern "C" {
 /* experiment / A-B switches: key 1 = halo kernel enable (0/1), key 2 = halo descriptor base-offset mode (0/1) */
 int mml_debug_set(int key, int value) {
   if (key == 1) g_halo_enable = value;
-  if (key == 3) g_reserve_sms = value < 0 ? 0 : value;
   else if (key == 2) g_halo_base_offset_mode = value;
   else return MML_ERR_INVALID;
   return MML_OK;
@@ -1324,7 +1323,7 @@ int mml_conv_wgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, cons
   HaloGeom hg;
   if (g_halo_enable && g->R == 3 && g->stride == 1 && g->pad == 1 && n_taps == 9 && halo_geometry(Q, P, g->N, g->C, g->K, &hg) && ctx->workspace) {
     const int CH = g->C / 64;
-    const int sms = ctx->sm_count - g_reserve_sms > 8 ? ctx->sm_count - g_reserve_sms : 8;
+    const int sms = persistent_sms(ctx);
     int ctas = CH == 1 ? sms : sms / 3;
     if (ctas > hg.m_tiles) ctas = hg.m_tiles;
     const size_t need = (size_t)ctas * g->K * 9 * g->C * sizeof(float);

@@ -22,6 +22,9 @@ struct mml_ctx {
   // inside a CUDA-graph capture.  One user at a time in stream order (the audio encoder's backward).
   void* workspace;
   size_t workspace_bytes;
+  // SMs the persistent kernels may occupy (0 = all): a caller that runs a second stream of small kernels next to them can keep a
+  // few SMs free so those kernels never wait for a whole persistent grid to drain (mml_ctx_set_sm_budget)
+  int sm_budget;
   char err[512];
 };
 

@@ -268,6 +268,16 @@ def debug_set(key: int, value: int) -> None:
     load_library().mml_debug_set(int(key), int(value))
 
 
+def _ctx_sm_count(device_index: int) -> int:
+    return Context.get(device_index).sm_count
+
+
+def set_sm_budget(device_index: int, sms: int) -> None:
+    """SMs the persistent conv kernels may occupy for the launches that follow (0 = all)."""
+    c = Context.get(device_index)
+    c.check(c.lib.mml_ctx_set_sm_budget(c.handle, int(sms)), "mml_ctx_set_sm_budget")
+
+
 def launch_count(device_index: int = 0) -> int:
     return Context.get(device_index).launches
 
