@@ -151,6 +151,10 @@ int mml_head_fwd(mml_ctx*, const mml_head_params* p, const float* pooledA, const
 int mml_head_bwd(mml_ctx*, const mml_head_params* p, const mml_head_grads* g, const float* pooledA, const float* pooledI,
                  const int64_t* labels, const uint8_t* dropout_mask, float dropout_scale, float* scratch,
                  float loss_scale, float* dpooledA, float* dpooledI, int B, int phases, void* stream);
+/* mean softmax cross-entropy over [B][NC] logits (CrossEntropyLoss() defaults, loss.py:48): dlogits = (softmax - onehot) * loss_scale / B,
+ * row_loss [B] scratch, loss_out = mean, pred = argmax; labels / dlogits / row_loss / loss_out / pred optional. */
+int mml_softmax_ce(mml_ctx*, const float* logits, const int64_t* labels, float* dlogits, float* row_loss, float* loss_out, int32_t* pred,
+                   float loss_scale, int B, int NC, void* stream);
 /* MonomodalEncoder tail (train_monomodal.py:64-92,224-232): emb = pooled W_fc^T + b_fc (the encoder's own fc, resnet.py:218),
  * logits = emb W_cls^T + b_cls, mean cross-entropy, argmax, dlogits = (softmax - onehot) * loss_scale / B.  labels / dlogits /
  * row_loss [B] / loss_out / pred are optional (forward only).  Backward: weight / bias gradients of both Linears (stored) and
@@ -235,6 +239,37 @@ int mml_bce_head_fwd(mml_ctx*, const float* xn, const float* w, const float* bia
                      float* dlogits, uint8_t* pred, float* scratch, float threshold, float grad_scale, int B, int H, int NC, void* stream);
 int mml_bce_head_bwd(mml_ctx*, const float* dlogits, const float* xn, const float* w, float* dw, float* db, uint16_t* dxn, int B, int H,
                      int NC, void* stream);
+
+/* ---- a12 (config 4): MOSI / UttFusion -- MML_Suite/models/msa/utt_fusion.py:106-198 ----------------------------------------- */
+/* TextCNN convolutions (textcnn.py:29-49) run on mml_conv_fprop / mml_conv_wgrad: Conv2d(1, 128, (k, 768)).weight is a K,R,S,C tensor
+ * with R = k, S = 1, C = 768 and the text input [B][T][768] is NHWC [B][T][1][768] (bf16 copy via mml_cast_f32_bf16). */
+#define MML_CLIP_PARTIALS 256
+/* one-layer batch_first nn.LSTM from zero state (lstm.py:17,62-64; gate order i,f,g,o): x fp32 [B][T][IN], w_ih [4H][IN], w_hh [4H][H],
+ * b_ih, b_hh [4H] -> h_last [B][H] ("last" embedding); saved for BPTT: gates [B][T][4H] (activated), cs, hs [B][T][H].  H = 64, IN <= 32.
+ * Backward: dh_last [B][H] -> dw_ih, dw_hh, db_ih, db_hh (ACCUMULATED); the input gets no gradient. */
+int mml_lstm_fwd(mml_ctx*, const float* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* gates,
+                 float* cs, float* hs, float* h_last, int B, int T, int IN, int H, void* stream);
+int mml_lstm_bwd(mml_ctx*, const float* x, const float* w_hh, const float* gates, const float* cs, const float* hs, const float* dh_last,
+                 float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, int B, int T, int IN, int H, void* stream);
+/* TextCNN conv_block tail (textcnn.py:51-58) + Dropout (:66): y[b][y_off + c] = keep * scale * max_t relu(conv[b][t][c] + bias[c]) over the
+ * P valid positions, conv bf16 [B][P][C]; arg = arg-max position or -1 (ReLU inactive).  Backward: dconv bf16 [B][P][C] (zero except at
+ * the arg-max), dbias [C] (stored).  y / dy / keep / arg are [B][ldy] (the concatenation of the three blocks). */
+int mml_relumax_fwd(mml_ctx*, const uint16_t* conv, const float* bias, const uint8_t* keep, float keep_scale, float* y, int32_t* arg, int B,
+                    int P, int C, int ldy, int y_off, void* stream);
+int mml_relumax_bwd(mml_ctx*, const float* dy, const int32_t* arg, const uint8_t* keep, float keep_scale, uint16_t* dconv, float* dbias, int B,
+                    int P, int C, int ldy, int y_off, void* stream);
+/* small-batch dense layer (textcnn.py:25-28 embd, classifier.py:100-117): y = dropout(relu(x W^T + b)); x [B][ldx], y [B][ldy] (so the
+ * concatenation of embeddings is a column offset), keep uint8 [B][N] or NULL.  Backward (dy [B][N] is overwritten by the gradient at the
+ * pre-activation): dx [B][lddx] (optional), dw [N][K], db [N] (stored). */
+int mml_dense_fwd(mml_ctx*, const float* x, int ldx, const float* w, const float* bias, const uint8_t* keep, float keep_scale, int relu,
+                  float* y, int ldy, int B, int K, int N, void* stream);
+int mml_dense_bwd(mml_ctx*, float* dy, const float* y, int ldy, const uint8_t* keep, float keep_scale, int relu, const float* x, int ldx,
+                  const float* w, float* dx, int lddx, float* dw, float* db, int B, int K, int N, void* stream);
+/* torch.nn.utils.clip_grad_norm_ (utt_fusion.py:181-182) folded into the optimizer: norm = ||g||_2 * base_scale over the flat gradient
+ * buffer, hyper[row][5] = base_scale * min(1, clip / (norm + 1e-6)) for rows 0..groups-1 (the Adam kernel multiplies gradients by it);
+ * partial: MML_CLIP_PARTIALS doubles of scratch; norm_out (optional) receives the norm. */
+int mml_clip_grad_scale(mml_ctx*, const float* g, int64_t n, float clip, float base_scale, float* hyper, int groups, double* partial,
+                        float* norm_out, void* stream);
 
 /* ---- a9: torch.optim.Adam (coupled weight decay) over the flat parameter buffer -- avmnist.py:303 ---------------- */
 /* hyper (device, fp32[8]): lr, beta1, beta2, eps, weight_decay, grad_scale, -, -;  step (device int64[1]) holds the number

@@ -24,7 +24,7 @@ from typing import Dict, Optional, Sequence, Tuple
 import torch
 import torch.nn.functional as F
 
-from late_fusion_oracle import _linear_params, adam_step, apply_missing_mask
+from late_fusion_oracle import _linear_params, _q, _qg, _qw, adam_step, apply_missing_mask
 
 Tensor = torch.Tensor
 PATTERNS = {"atv": (1, 1, 1), "at": (1, 1, 0), "av": (1, 0, 1), "tv": (0, 1, 1), "a": (1, 0, 0), "t": (0, 1, 0), "v": (0, 0, 1)}  # (audio, text, video)
@@ -81,12 +81,15 @@ def lstm_last(st: Dict[str, Tensor], prefix: str, x: Tensor) -> Tensor:
     return h
 
 
-def textcnn(st: Dict[str, Tensor], x: Tensor, keep: Optional[Tensor], p: float) -> Tensor:
+def textcnn(st: Dict[str, Tensor], x: Tensor, keep: Optional[Tensor], p: float, emulate_bf16: bool = False) -> Tensor:
+    """``emulate_bf16`` (debugging aid for the CUDA path, not part of the reference): round where the B200 path stores bf16 -- the
+    text input, the convolution weights, the convolution output (bias is added afterwards in fp32) and its gradient."""
     B, T, D = x.shape
-    frame = x.view(B, 1, T, D)
+    q = emulate_bf16
+    frame = _q(x, q).view(B, 1, T, D)
     outs = []
     for i in range(len(KERNEL_HEIGHTS)):
-        conv = F.conv2d(frame, st[f"netT.conv{i + 1}.weight"], st[f"netT.conv{i + 1}.bias"])  # [B, C, T-k+1, 1]
+        conv = _qg(_q(F.conv2d(frame, _qw(st[f"netT.conv{i + 1}.weight"], q), None), q), q) + st[f"netT.conv{i + 1}.bias"].view(1, -1, 1, 1)
         outs.append(F.relu(conv.squeeze(3)).max(dim=2).values)
     allo = torch.cat(outs, 1)
     if keep is not None:
@@ -94,11 +97,12 @@ def textcnn(st: Dict[str, Tensor], x: Tensor, keep: Optional[Tensor], p: float) 
     return F.relu(F.linear(allo, st["netT.embd.0.weight"], st["netT.embd.0.bias"]))
 
 
-def utt_forward(st: Dict[str, Tensor], A: Tensor, V: Tensor, T: Tensor, keeps: Optional[Sequence[Tensor]] = None, p: float = 0.5) -> Tensor:
+def utt_forward(st: Dict[str, Tensor], A: Tensor, V: Tensor, T: Tensor, keeps: Optional[Sequence[Tensor]] = None, p: float = 0.5,
+                emulate_bf16: bool = False) -> Tensor:
     """logits [B, classes]; ``keeps`` = four {0,1} keep-masks (TextCNN dropout [B,384], classifier dropouts [B,192], [B,64], [B,32])
     in train mode, None in eval mode."""
     a, v = lstm_last(st, "netA", A), lstm_last(st, "netV", V)
-    t = textcnn(st, T, keeps[0] if keeps is not None else None, p)
+    t = textcnn(st, T, keeps[0] if keeps is not None else None, p, emulate_bf16)
     x = torch.cat([a, v, t], dim=-1)  # utt_fusion.py:147
     i = 0
     while f"netC.module.{3 * i}.weight" in st:
@@ -110,10 +114,11 @@ def utt_forward(st: Dict[str, Tensor], A: Tensor, V: Tensor, T: Tensor, keeps: O
 
 
 def train_step(st: "OrderedDict[str, Tensor]", opt_state: Dict, A: Tensor, V: Tensor, T: Tensor, labels: Tensor, keeps: Optional[Sequence[Tensor]],
-               lr: float = 1e-3, weight_decay: float = 1e-3, clip: Optional[float] = 1.0, apply_update: bool = True) -> Dict[str, object]:
+               lr: float = 1e-3, weight_decay: float = 1e-3, clip: Optional[float] = 1.0, apply_update: bool = True,
+               emulate_bf16: bool = False) -> Dict[str, object]:
     """utt_fusion.py:151-198: forward (train), CE on squeezed logits / labels, backward, clip_grad_norm_(clip), Adam.step."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in st.items()}
-    logits = utt_forward(leaves, A, V, T, keeps)
+    logits = utt_forward(leaves, A, V, T, keeps, emulate_bf16=emulate_bf16)
     loss = F.cross_entropy(logits.squeeze(), labels.squeeze()) * 1.0
     gl = torch.autograd.grad(loss, list(leaves.values()))
     grads = dict(zip(leaves.keys(), gl))

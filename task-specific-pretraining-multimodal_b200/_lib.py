@@ -82,6 +82,7 @@ SIGNATURES = {
     "mml_head_scratch_per_sample": (I32, [C.POINTER(HeadParams)]),
     "mml_head_fwd": (I32, [P, C.POINTER(HeadParams), P, P, P, P, F32, P, P, P, P, I32, P]),
     "mml_head_bwd": (I32, [P, C.POINTER(HeadParams), C.POINTER(HeadGrads), P, P, P, P, F32, P, F32, P, P, I32, I32, P]),
+    "mml_softmax_ce": (I32, [P, P, P, P, P, P, P, F32, I32, I32, P]),
     "mml_mono_head_fwd": (I32, [P] * 13 + [F32, I32, I32, I32, I32, P]),
     "mml_mono_head_bwd": (I32, [P] * 12 + [I32, I32, I32, I32, P]),
     "mml_linear_fwd": (I32, [P, P, P, P, P, I32, I32, I32, P]),
@@ -97,6 +98,13 @@ SIGNATURES = {
     "mml_bce_head_scratch_floats": (I64, [I32]),
     "mml_bce_head_fwd": (I32, [P, P, P, P, P, P, P, P, P, P, F32, F32, I32, I32, I32, P]),
     "mml_bce_head_bwd": (I32, [P, P, P, P, P, P, P, I32, I32, I32, P]),
+    "mml_lstm_fwd": (I32, [P] * 10 + [I32, I32, I32, I32, P]),
+    "mml_lstm_bwd": (I32, [P] * 11 + [I32, I32, I32, I32, P]),
+    "mml_relumax_fwd": (I32, [P, P, P, P, F32, P, P, I32, I32, I32, I32, I32, P]),
+    "mml_relumax_bwd": (I32, [P, P, P, P, F32, P, P, I32, I32, I32, I32, I32, P]),
+    "mml_dense_fwd": (I32, [P, P, I32, P, P, P, F32, I32, P, I32, I32, I32, I32, P]),
+    "mml_dense_bwd": (I32, [P, P, P, I32, P, F32, I32, P, I32, P, P, I32, P, P, I32, I32, I32, P]),
+    "mml_clip_grad_scale": (I32, [P, P, I64, F32, F32, P, I32, P, P, P]),
     "mml_adam_step": (I32, [P, P, P, P, P, P, I64, P, P, I32, P]),
     "mml_cast_f32_bf16": (I32, [P, P, P, I64, P]),
     "mml_weights_transpose": (I32, [P, P, P, P, I32, I32, P]),

@@ -1085,9 +1085,10 @@ int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, in
 int check_geom(mml_ctx* ctx, const mml_conv_geom* g, int* P, int* Q) {
   MML_REQUIRE(ctx, ctx && g, "conv: null ctx/geom");
   MML_REQUIRE(ctx, g->N >= 1 && g->H >= 1 && g->W >= 1, "conv: bad input dims");
-  MML_REQUIRE(ctx, (g->R == 3 && g->S == 3) || (g->R == 1 && g->S == 1), "conv: only 3x3 and 1x1 filters (got %dx%d)", g->R, g->S);
+  // 3x3 / 1x1 (ResNet), k x 1 (TextCNN over time, W == 1): any filter of at most kMaxTaps taps is a tap-shifted GEMM
+  MML_REQUIRE(ctx, g->R >= 1 && g->S >= 1 && g->R * g->S <= kMaxTaps, "conv: at most %d filter taps (got %dx%d)", kMaxTaps, g->R, g->S);
   MML_REQUIRE(ctx, g->stride == 1 || g->stride == 2, "conv: stride must be 1 or 2");
-  MML_REQUIRE(ctx, g->pad >= 0 && g->pad < g->R, "conv: bad padding");
+  MML_REQUIRE(ctx, g->pad >= 0 && g->pad < g->R && (g->pad == 0 || g->pad < g->S), "conv: bad padding");
   *P = (g->H + 2 * g->pad - g->R) / g->stride + 1;
   *Q = (g->W + 2 * g->pad - g->S) / g->stride + 1;
   MML_REQUIRE(ctx, *P >= 1 && *Q >= 1, "conv: empty output");

@@ -602,6 +602,22 @@ int mml_head_bwd(mml_ctx* ctx, const mml_head_params* p, const mml_head_grads* g
   return MML_OK;
 }
 
+int mml_softmax_ce(mml_ctx* ctx, const float* logits, const int64_t* labels, float* dlogits, float* row_loss, float* loss_out, int32_t* pred,
+                   float loss_scale, int B, int NC, void* stream) {
+  MML_REQUIRE(ctx, ctx && logits && B >= 1, "softmax_ce: bad arguments");
+  MML_REQUIRE(ctx, NC >= 1 && NC <= 32, "softmax_ce: 1..32 classes supported (got %d)", NC);
+  MML_REQUIRE(ctx, !loss_out || (labels && row_loss), "softmax_ce: the loss needs labels and row_loss");
+  MML_REQUIRE(ctx, !dlogits || labels, "softmax_ce: the gradient needs labels");
+  cudaStream_t st = (cudaStream_t)stream;
+  softmax_ce_kernel<<<(unsigned)mml_ceil_div(B, 8), 256, 0, st>>>(logits, (const long long*)labels, dlogits, row_loss, pred, loss_scale, B, NC);
+  MML_LAUNCHED(ctx);
+  if (loss_out) {
+    head_loss_kernel<<<1, 256, 0, st>>>(row_loss, 1, 0, B, loss_out);
+    MML_LAUNCHED(ctx);
+  }
+  return MML_OK;
+}
+
 int mml_mono_head_fwd(mml_ctx* ctx, const float* pooled, const float* fc_w, const float* fc_b, const float* cls_w, const float* cls_b,
                       const int64_t* labels, float* emb, float* logits, float* dlogits, float* row_loss, float* loss_out, int32_t* pred,
                       float loss_scale, int B, int F, int E, int NC, void* stream) {

@@ -433,3 +433,65 @@ def att_bwd(dz, h_a, h_b, gate, t, w2, dw2, db2, db0, dhid) -> None:
     c.check(c.lib.mml_att_bwd(c.handle, _p(dz, torch.float32), _p(h_a, torch.float32), _p(h_b, torch.float32), _p(gate, torch.float32),
                               _p(t, torch.float32), _p(w2, torch.float32), _p(dw2, torch.float32), _p(db2, torch.float32), _p(db0, torch.float32),
                               _p(dhid, torch.bfloat16), B, H, Hd, w2.shape[0], _stream(t)), "mml_att_bwd")
+
+
+# ---- MOSI / UttFusion (config 4) -----------------------------------------------------------------------------------------
+def lstm_fwd(x, w_ih, w_hh, b_ih, b_hh, gates, cs, hs, h_last) -> None:
+    B, T, IN = x.shape
+    c = _ctx(x)
+    f = torch.float32
+    c.check(c.lib.mml_lstm_fwd(c.handle, _p(x, f), _p(w_ih, f), _p(w_hh, f), _p(b_ih, f), _p(b_hh, f), _p(gates, f), _p(cs, f), _p(hs, f),
+                               _p(h_last, f), B, T, IN, w_hh.shape[1], _stream(x)), "mml_lstm_fwd")
+
+
+def lstm_bwd(x, w_hh, gates, cs, hs, dh_last, dw_ih, dw_hh, db_ih, db_hh) -> None:
+    B, T, IN = x.shape
+    c = _ctx(x)
+    f = torch.float32
+    c.check(c.lib.mml_lstm_bwd(c.handle, _p(x, f), _p(w_hh, f), _p(gates, f), _p(cs, f), _p(hs, f), _p(dh_last, f), _p(dw_ih, f), _p(dw_hh, f),
+                               _p(db_ih, f), _p(db_hh, f), B, T, IN, w_hh.shape[1], _stream(x)), "mml_lstm_bwd")
+
+
+def relumax_fwd(conv, bias, keep, keep_scale: float, y, arg, y_off: int) -> None:
+    B, P, Cn = conv.shape
+    c = _ctx(y)
+    c.check(c.lib.mml_relumax_fwd(c.handle, _p(conv, torch.bfloat16), _p(bias, torch.float32), _p(keep, torch.uint8), float(keep_scale),
+                                  _p(y, torch.float32), _p(arg, torch.int32), B, P, Cn, y.shape[1], int(y_off), _stream(y)), "mml_relumax_fwd")
+
+
+def relumax_bwd(dy, arg, keep, keep_scale: float, dconv, dbias, y_off: int) -> None:
+    B, P, Cn = dconv.shape
+    c = _ctx(dy)
+    c.check(c.lib.mml_relumax_bwd(c.handle, _p(dy, torch.float32), _p(arg, torch.int32), _p(keep, torch.uint8), float(keep_scale),
+                                  _p(dconv, torch.bfloat16), _p(dbias, torch.float32), B, P, Cn, dy.shape[1], int(y_off), _stream(dy)), "mml_relumax_bwd")
+
+
+def dense_fwd(x, ldx: int, w, bias, keep, keep_scale: float, relu: bool, y, ldy: int, B: int) -> None:
+    N, K = w.shape
+    c = _ctx(w)
+    f = torch.float32
+    c.check(c.lib.mml_dense_fwd(c.handle, C.c_void_p(x.data_ptr()), int(ldx), _p(w, f), _p(bias, f), _p(keep, torch.uint8), float(keep_scale),
+                                int(relu), C.c_void_p(y.data_ptr()), int(ldy), B, K, N, _stream(w)), "mml_dense_fwd")
+
+
+def dense_bwd(dy, y, ldy: int, keep, keep_scale: float, relu: bool, x, ldx: int, w, dx, lddx: int, dw, db, B: int) -> None:
+    N, K = w.shape
+    c = _ctx(w)
+    f = torch.float32
+    c.check(c.lib.mml_dense_bwd(c.handle, _p(dy, f), C.c_void_p(y.data_ptr()), int(ldy), _p(keep, torch.uint8), float(keep_scale), int(relu),
+                                C.c_void_p(x.data_ptr()), int(ldx), _p(w, f), C.c_void_p(dx.data_ptr()) if dx is not None else C.c_void_p(0), int(lddx),
+                                _p(dw, f), _p(db, f), B, K, N, _stream(w)), "mml_dense_bwd")
+
+
+def clip_grad_scale(g, clip: float, base_scale: float, hyper, groups: int, partial, norm_out=None) -> None:
+    c = _ctx(g)
+    c.check(c.lib.mml_clip_grad_scale(c.handle, _p(g, torch.float32), g.numel(), float(clip), float(base_scale), _p(hyper, torch.float32), int(groups),
+                                      _p(partial, torch.float64), _p(norm_out, torch.float32), _stream(g)), "mml_clip_grad_scale")
+
+
+def softmax_ce(logits, labels, dlogits, row_loss, loss, pred, loss_scale: float = 1.0) -> None:
+    B, NC = logits.shape
+    c = _ctx(logits)
+    f = torch.float32
+    c.check(c.lib.mml_softmax_ce(c.handle, _p(logits, f), _p(labels, torch.int64), _p(dlogits, f), _p(row_loss, f), _p(loss, f), _p(pred, torch.int32),
+                                 float(loss_scale), B, NC, _stream(logits)), "mml_softmax_ce")

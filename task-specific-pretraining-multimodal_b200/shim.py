@@ -64,6 +64,19 @@ def install(patch_reference_modules: bool = True) -> Dict[str, object]:
             ref_rn.ResNet18, ref_rn.ResNet34, ref_rn.ResNetEncoder = ResNet18, ResNet34, ResNetEncoder
     _installed["AVMNIST"] = AVMNIST
     _installed["MMIMDb"] = _mm.MMIMDb
+    from . import utt_fusion as _uf
+
+    utt = {"UttFusionModel": _uf.UttFusionModel, "LSTMEncoder": _uf.LSTMEncoder, "TextCNN": _uf.TextCNN, "FcClassifier": _uf.FcClassifier}
+    for cname, cls in utt.items():  # yaml_constructors.py registers the same tags for models/msa/*
+        register("!" + cname, cls)
+    if patch_reference_modules:
+        for modname, names in (("models.msa.utt_fusion", ("UttFusionModel",)), ("models.msa.networks.lstm", ("LSTMEncoder",)),
+                               ("models.msa.networks.textcnn", ("TextCNN",)), ("models.msa.networks.classifier", ("FcClassifier",))):
+            mod = sys.modules.get(modname)
+            if mod is not None:
+                for n in names:
+                    setattr(mod, n, utt[n])
+    _installed["UttFusionModel"] = _uf.UttFusionModel
     from .mono import MonomodalEncoder
 
     ref_tm = sys.modules.get("train_monomodal")
