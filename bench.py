@@ -411,6 +411,138 @@ def run_mono_arm(args):
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}}))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# --workload mosi: BASELINE config 4 (MOSI / UttFusion; configs/mosi/centralised/utt_fusion_base_training.yaml)
+# ---------------------------------------------------------------------------------------------------------------------
+def run_mosi_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from mml_b200 import dist as mdist
+    from mml_b200.data import DevicePrefetcher
+    from mml_b200.utt_fusion import FcClassifier, LSTMEncoder, TextCNN, UttFusionModel
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import utt_fusion_oracle as U
+
+    B = args.batch if args.batch != 256 else 32  # utt_fusion_base_training.yaml:50
+    metric = "mosi_utt_fusion_train_samples_per_s"
+    cfg = {"workload": "MOSI UttFusion train step (config 4): LSTM(5->64) + LSTM(20->64) over T=50, TextCNN 768 x {3,4,5} -> 64, FcClassifier 192-192-64-32-3, "
+           "CE, clip_grad_norm 1.0, Adam; zero-padded sequences, 7 missing patterns", "batch_per_gpu": B,
+           "l2_policy": "working set (5 MB of parameters, 10 MB of activations) is L2 resident by design; latency-bound step, no flush",
+           "timing": "CUDA events around K CUDA-graph replays, barrier + synchronize on both sides, max over ranks"}
+
+    def cpu_run(budget):
+        torch.set_num_threads(os.cpu_count() or 1)
+        torch.manual_seed(0)
+        st = U.init_utt_state()
+        d = U.synthetic_batch(B, 0)
+        os_, ts = {}, []
+        U.train_step(st, os_, d["audio_masked"], d["video_masked"], d["text_masked"], d["labels"], d["keeps"])
+        t_begin = time.perf_counter()
+        while len(ts) < 3 or (time.perf_counter() - t_begin < budget and len(ts) < 300):
+            t0 = time.perf_counter()
+            U.train_step(st, os_, d["audio_masked"], d["video_masked"], d["text_masked"], d["labels"], d["keeps"])
+            ts.append(time.perf_counter() - t0)
+        per = statistics.median(ts)
+        return {"value": B / per, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                "sample": f"{len(ts)} train steps of the UttFusion oracle port at batch {B}, fp32, torch CPU, median step {per * 1e3:.1f} ms",
+                "steps_timed": len(ts), "ms_per_step": per * 1e3}
+
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            r = cpu_run(30.0)
+            _emit(json.dumps({"impl": "reference", "metric": metric, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps_timed"],
+                              "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                              "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                              "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+    rank, local_rank, world = mdist.init_from_env("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(0)
+    model = UttFusionModel(LSTMEncoder(5, 64, "last"), LSTMEncoder(20, 64, "last"),
+                           TextCNN(768, embd_size=64, dropout=0.5, in_channels=1, out_channels=128, kernel_heights=[3, 4, 5]),
+                           FcClassifier(192, [192, 64, 32], 3, dropout=0.5), clip=1.0).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3)
+    loss_fns = {"cross_entropy": _Term(torch.nn.CrossEntropyLoss())}
+    if world > 1:
+        dp = mdist.DataParallel()
+        model.enable_data_parallel(dp)
+    eng = model._get_engine(dev)
+    if world > 1:
+        dp.broadcast_state(eng)
+
+    def pinned(seed):
+        d = U.synthetic_batch(B, seed)
+        b = {"audio_original": d["audio"], "audio_missing_index": d["audio_mask"], "video_original": d["video"], "video_missing_index": d["video_mask"],
+             "text_original": d["text"], "text_missing_index": d["text_mask"], "label": d["labels"]}
+        b = {k: v.pin_memory() for k, v in b.items()}
+        b["pattern_name"] = d["pattern_name"]
+        return b
+
+    host = [pinned(10 * rank + i) for i in range(3)]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values() if hasattr(v, "numel"))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        model.train_step(host[i % 3], opt, loss_fns, dev, None)
+    plan = next(iter(eng.plans.values()))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(1000):
+        plan.train_step(False)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        barrier()
+        e0.record()
+        fn()
+        e1.record()
+        barrier()
+        dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item())
+
+    def dev_loop():
+        for _ in range(args.steps):
+            plan.train_step(False)
+
+    def e2e_loop():
+        for b in DevicePrefetcher((host[i % 3] for i in range(args.steps)), dev):
+            model.train_step(b, opt, loss_fns, dev, None)
+
+    for b in DevicePrefetcher((host[i % 3] for i in range(16)), dev):
+        model.train_step(b, opt, loss_fns, dev, None)
+    t_dev = timed(dev_loop)
+    eng.fs._host_step += args.steps + 1000
+    t_e2e = timed(e2e_loop)
+    clocks = sampler.stop()
+    if rank != 0:
+        return
+    pk = peaks()
+    # dense-nominal tensor work of the three TextCNN convolutions, forward + weight gradient (the input needs no gradient)
+    conv_gflop = 2 * sum(2.0 * B * (50 - k + 1) * 128 * k * 768 for k in (3, 4, 5)) / 1e9
+    cpu = cpu_run(10.0)
+    cfg.update({"global_batch": B * world, "parallelism": f"dp{world}"})
+    _emit(json.dumps({
+        "metric": metric, "value": B * world * args.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": cfg, "e2e": {"value": B * world * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                               "ms_per_step": t_e2e / args.steps * 1e3},
+        "gpu_launches": plan.launches_per_step * args.steps, "launches_per_step": plan.launches_per_step, "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": conv_gflop / (t_dev / args.steps) / 1e3, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": conv_gflop / (t_dev / args.steps) / 1e3 / pk["tf_sustained"], "traffic": None,
+                     "note": f"whole step: {conv_gflop:.2f} GFLOP of TextCNN tensor work over the step time; the step is latency-bound "
+                             f"({plan.launches_per_step} dependent launches, two 50-step LSTM recurrences)"},
+        "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}}))
+
+
 def workload_config(args, world):
     return {"workload": "AVMNIST late-fusion train step: ResNet18 audio 112x112 + ResNet34 image 28x28, concat head, CE, Adam; audio missing_rate 0.2",
             "batch_per_gpu": args.batch, "global_batch": args.batch * world, "parallelism": f"dp{world}",
@@ -632,8 +764,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU (BASELINE.json configs[1])")
-    ap.add_argument("--workload", default="avmnist", choices=["avmnist", "mmimdb", "mono"],
-                    help="avmnist = the headline line (configs[1]); mmimdb = configs[2]; mono = monomodal audio-encoder pre-training")
+    ap.add_argument("--workload", default="avmnist", choices=["avmnist", "mmimdb", "mono", "mosi"],
+                    help="avmnist = the headline line (configs[1]); mmimdb = configs[2]; mono = monomodal audio-encoder pre-training; mosi = configs[3]")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: library chatter (e.g. "NCCL version ...") is diverted to stderr
     real_stdout = os.fdopen(os.dup(1), "w")
@@ -644,6 +776,8 @@ def main():
         run_gated_arm(args)
     elif args.workload == "mono":
         run_mono_arm(args)
+    elif args.workload == "mosi":
+        run_mosi_arm(args)
     elif args.impl == "reference":
         run_reference_arm(args)
     else:

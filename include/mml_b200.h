@@ -253,7 +253,7 @@ int mml_lstm_bwd(mml_ctx*, const float* x, const float* w_hh, const float* gates
                  float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, int B, int T, int IN, int H, void* stream);
 /* TextCNN conv_block tail (textcnn.py:51-58) + Dropout (:66): y[b][y_off + c] = keep * scale * max_t relu(conv[b][t][c] + bias[c]) over the
  * P valid positions, conv bf16 [B][P][C]; arg = arg-max position or -1 (ReLU inactive).  Backward: dconv bf16 [B][P][C] (zero except at
- * the arg-max), dbias [C] (stored).  y / dy / keep / arg are [B][ldy] (the concatenation of the three blocks). */
+ * the arg-max), dbias [C] (ACCUMULATED).  y / dy / keep / arg are [B][ldy] (the concatenation of the three blocks). */
 int mml_relumax_fwd(mml_ctx*, const uint16_t* conv, const float* bias, const uint8_t* keep, float keep_scale, float* y, int32_t* arg, int B,
                     int P, int C, int ldy, int y_off, void* stream);
 int mml_relumax_bwd(mml_ctx*, const float* dy, const int32_t* arg, const uint8_t* keep, float keep_scale, uint16_t* dconv, float* dbias, int B,

@@ -157,25 +157,22 @@ __global__ void relumax_fwd_kernel(const uint16_t* __restrict__ conv, const floa
   arg[(size_t)b * ldy + y_off + c] = at;
 }
 
-// backward of the same: dconv bf16 [B][P][C] is zero except at the arg-max position; dbias[c] = sum_b of those gradients (stored)
+// backward of the same: dconv bf16 [B][P][C] is zero except at the arg-max position; dbias[c] = sum_b of those gradients.
+// One thread per (b, c): P coalesced 2-byte stores down the time axis; the bias gradient meets in a global atomic (dbias is part of the
+// flat gradient buffer, zeroed once per step).
 __global__ void relumax_bwd_kernel(const float* __restrict__ dy, const int* __restrict__ arg, const uint8_t* __restrict__ keep, float keep_scale,
                                    uint16_t* __restrict__ dconv, float* __restrict__ dbias, int B, int P, int C, int ldy, int y_off) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float sb = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const size_t yi = (size_t)b * ldy + y_off + c;
-    float g = dy[yi];
-    if (keep) g = keep[yi] ? g * keep_scale : 0.f;
-    const int at = arg[yi];
-    for (int t = 0; t < P; ++t) dconv[((size_t)b * P + t) * C + c] = 0;
-    if (at >= 0) {
-      const __nv_bfloat16 gb = __float2bfloat16_rn(g);
-      dconv[((size_t)b * P + at) * C + c] = *reinterpret_cast<const uint16_t*>(&gb);
-      sb += g;
-    }
-  }
-  dbias[c] = sb;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  const size_t yi = (size_t)b * ldy + y_off + c;
+  float g = dy[yi];
+  if (keep) g = keep[yi] ? g * keep_scale : 0.f;
+  const int at = arg[yi];
+  const __nv_bfloat16 gb = __float2bfloat16_rn(g);
+  const uint16_t gbits = *reinterpret_cast<const uint16_t*>(&gb);
+  for (int t = 0; t < P; ++t) dconv[((size_t)b * P + t) * C + c] = t == at ? gbits : (uint16_t)0;
+  if (at >= 0 && g != 0.f) atomicAdd(dbias + c, g);
 }
 
 // y[b][o] = act(bias[o] + sum_k x[b][k] w[o][k]) (* keep * scale): one warp per output, small batch (B = 32)
@@ -253,9 +250,11 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 
 __global__ void clip_scale_kernel(const double* __restrict__ partial, int parts, float clip, float base_scale, float* __restrict__ hyper, int groups,
                                   float* __restrict__ norm_out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double s = 0.0;
-  for (int i = 0; i < parts; ++i) s += partial[i];
+  for (int i = threadIdx.x; i < parts; i += 32) s += partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x != 0) return;
   const float norm = (float)sqrt(s) * base_scale;  // the norm of the gradients Adam will see (base_scale = 1 / world size)
   float coef = clip / (norm + 1e-6f);
   if (coef > 1.f) coef = 1.f;
@@ -312,7 +311,8 @@ int mml_relumax_fwd(mml_ctx* ctx, const uint16_t* conv, const float* bias, const
 int mml_relumax_bwd(mml_ctx* ctx, const float* dy, const int32_t* arg, const uint8_t* keep, float keep_scale, uint16_t* dconv, float* dbias, int B,
                     int P, int C, int ldy, int y_off, void* stream) {
   MML_REQUIRE(ctx, ctx && dy && arg && dconv && dbias && B >= 1 && P >= 1 && C >= 1 && ldy >= y_off + C, "relumax_bwd: bad arguments");
-  relumax_bwd_kernel<<<(unsigned)mml_ceil_div(C, 64), 64, 0, (cudaStream_t)stream>>>(dy, arg, keep, keep_scale, dconv, dbias, B, P, C, ldy, y_off);
+  relumax_bwd_kernel<<<(unsigned)mml_ceil_div((int64_t)B * C, 128), 128, 0, (cudaStream_t)stream>>>(dy, arg, keep, keep_scale, dconv, dbias, B, P, C,
+                                                                                                   ldy, y_off);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }

@@ -165,6 +165,28 @@ class _UttPlan:
         self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self.eager_steps = 0
         self.launches_per_step = 0
+        import os as _os
+        # the two LSTM recurrences (50 dependent steps each) and the text branch are independent: three streams (MML_UTT_STREAMS=0: one)
+        multi = _os.environ.get("MML_UTT_STREAMS", "1") == "1"
+        self.streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if multi else None
+
+    def _parallel(self, main_ops, *side_chains) -> None:
+        """``main_ops`` on the current stream, every chain of ``side_chains`` on its own stream; fork before, join after."""
+        if self.streams is None:
+            for chain in (main_ops,) + side_chains:
+                for op in chain:
+                    op()
+            return
+        main = torch.cuda.current_stream(self.eng.device)
+        for st, chain in zip(self.streams, side_chains):
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                for op in chain:
+                    op()
+        for op in main_ops:
+            op()
+        for st, _ in zip(self.streams, side_chains):
+            main.wait_stream(st)
 
     # ---- schedule --------------------------------------------------------------------------------------------------------
     def _mask_inputs(self) -> None:
@@ -176,15 +198,21 @@ class _UttPlan:
     def run_forward(self, train: bool, with_loss: bool, with_grad: bool) -> None:
         B, H = self.B, self.H
         self._mask_inputs()
-        for off, key in ((0, "A"), (H, "V")):
-            L = self.lstm[key]
-            ops.lstm_fwd(L["x"], *L["w"], L["gates"], L["cs"], L["hs"], L["h_last"])
-            self.fused[:, off:off + H].copy_(L["h_last"])  # torch.cat([a, v, t]) (utt_fusion.py:147) is a column offset
         dropT = train and self.pT > 0
-        for i, cv in enumerate(self.convs):
-            ops.conv_fprop(cv["geom"], self.xT16, cv["w16"], cv["out"], None)
-            ops.relumax_fwd(cv["out"], cv["bias"], self.keepT if dropT else None, 1.0 / (1.0 - self.pT) if dropT else 1.0, self.pooled, self.arg, i * self.C)
-        ops.dense_fwd(self.pooled, self.pooled.shape[1], self.embd["w"], self.embd["b"], None, 1.0, True, self.fused[:, 2 * H:], self.fused.shape[1], B)
+
+        def lstm_chain(off, key):
+            L = self.lstm[key]
+            return [lambda: ops.lstm_fwd(L["x"], *L["w"], L["gates"], L["cs"], L["hs"], L["h_last"]),
+                    lambda: self.fused[:, off:off + H].copy_(L["h_last"])]  # torch.cat([a, v, t]) (utt_fusion.py:147) is a column offset
+
+        def text_chain():
+            for i, cv in enumerate(self.convs):
+                ops.conv_fprop(cv["geom"], self.xT16, cv["w16"], cv["out"], None)
+                ops.relumax_fwd(cv["out"], cv["bias"], self.keepT if dropT else None, 1.0 / (1.0 - self.pT) if dropT else 1.0, self.pooled, self.arg,
+                                i * self.C)
+            ops.dense_fwd(self.pooled, self.pooled.shape[1], self.embd["w"], self.embd["b"], None, 1.0, True, self.fused[:, 2 * H:], self.fused.shape[1], B)
+
+        self._parallel([text_chain], lstm_chain(0, "A"), lstm_chain(H, "V"))
         dropC = train and self.pC > 0
         for layer in self.dense:
             ops.dense_fwd(layer["x"], layer["ldx"], layer["w"], layer["b"], layer["keep"] if dropC else None, 1.0 / (1.0 - self.pC) if dropC else 1.0, True,
@@ -215,20 +243,24 @@ class _UttPlan:
             ops.dense_bwd(layer["dy"], layer["y"], layer["y"].shape[1], layer["keep"], scale_c, True, layer["x"], layer["ldx"], layer["w"], dx, lddx,
                           layer["dw"], layer["db"], B)
         # text branch: embd Linear+ReLU -> dropout / max over time -> conv weight gradients
-        self.demb.copy_(self.dfused[:, 2 * H:])
-        self.lstm["A"]["dh"].copy_(self.dfused[:, :H])
-        self.lstm["V"]["dh"].copy_(self.dfused[:, H:2 * H])
         e = self.embd
-        ops.dense_bwd(self.demb, self.fused[:, 2 * H:], self.fused.shape[1], None, 1.0, True, self.pooled, self.pooled.shape[1], e["w"], self.dpooled,
-                      self.dpooled.shape[1], e["dw"], e["db"], B)
         dropT = self.pT > 0
-        for i, cv in enumerate(self.convs):
-            ops.relumax_bwd(self.dpooled, self.arg, self.keepT if dropT else None, 1.0 / (1.0 - self.pT) if dropT else 1.0, cv["dout"], cv["dbias"], i * self.C)
-            ops.conv_wgrad(cv["geom"], self.xT16, cv["dout"], cv["dw"])
-        # LSTM BPTT
-        for key in ("A", "V"):
+
+        def text_bwd():
+            self.demb.copy_(self.dfused[:, 2 * H:])
+            ops.dense_bwd(self.demb, self.fused[:, 2 * H:], self.fused.shape[1], None, 1.0, True, self.pooled, self.pooled.shape[1], e["w"], self.dpooled,
+                          self.dpooled.shape[1], e["dw"], e["db"], B)
+            for i, cv in enumerate(self.convs):
+                ops.relumax_bwd(self.dpooled, self.arg, self.keepT if dropT else None, 1.0 / (1.0 - self.pT) if dropT else 1.0, cv["dout"], cv["dbias"],
+                                i * self.C)
+                ops.conv_wgrad(cv["geom"], self.xT16, cv["dout"], cv["dw"])
+
+        def lstm_bwd_chain(off, key):  # BPTT from d h_T = this encoder's columns of d fused
             L = self.lstm[key]
-            ops.lstm_bwd(L["x"], L["w"][1], L["gates"], L["cs"], L["hs"], L["dh"], *L["dw"])
+            return [lambda: L["dh"].copy_(self.dfused[:, off:off + H]),
+                    lambda: ops.lstm_bwd(L["x"], L["w"][1], L["gates"], L["cs"], L["hs"], L["dh"], *L["dw"])]
+
+        self._parallel([text_bwd], lstm_bwd_chain(0, "A"), lstm_bwd_chain(H, "V"))
 
     def run_update(self) -> None:
         eng, fs = self.eng, self.eng.fs
