@@ -466,6 +466,75 @@ def monomodal_train_step(state: "OrderedDict[str, Tensor]", opt_state: Dict, x: 
 
 
 # ----------------------------------------------------------------------------------------------
+# 8f rank 4 -- AVMNIST with the ConvBlock encoders (models/avmnist.py:34-185, models/conv.py:16-59; configs/avmnist/centralised/
+# train_avmnist.yaml).  ORACLE ONLY in round 1: the CUDA path for 32-channel biased convolutions is not built.
+# ----------------------------------------------------------------------------------------------
+CONVBLOCK_CHANNELS = {"audio_encoder": ((1, 32), (32, 32), (32, 64), (64, 64)), "image_encoder": ((1, 32), (32, 64), (64, 64), (64, 64))}
+CONVBLOCK_POOLS = {"audio_encoder": (2, 3), "image_encoder": (2, 2)}   # MaxPool2d kernel sizes (stride = kernel)
+CONVBLOCK_FLAT = {"audio_encoder": 4800, "image_encoder": 3136}
+
+
+def _conv_params_bias(out_c: int, in_c: int, k: int) -> Tuple[Tensor, Tensor]:
+    w = _conv_weight(out_c, in_c, k)  # nn.Conv2d.reset_parameters: weight, then bias ~ U(+-1/sqrt(fan_in))
+    bound = 1.0 / math.sqrt(in_c * k * k)
+    return w, torch.empty(out_c).uniform_(-bound, bound)
+
+
+def init_convblock_avmnist_state(audio_hidden: int = 64, image_hidden: int = 128, hidden_dim: int = 128) -> "OrderedDict[str, Tensor]":
+    """AVMNIST(MNISTAudio(...), MNISTImage(...), hidden_dim) built in YAML order; inside a ConvBlock the registration (and RNG)
+    order is conv_one, conv_two, batch_norm_one, batch_norm_two (conv.py:24-45)."""
+    st: "OrderedDict[str, Tensor]" = OrderedDict()
+    for enc, hid in (("audio_encoder", audio_hidden), ("image_encoder", image_hidden)):
+        ch = CONVBLOCK_CHANNELS[enc]
+        for bi, slot in enumerate((0, 2)):  # Sequential: ConvBlock, MaxPool2d, ConvBlock, MaxPool2d, Flatten, Linear
+            (i1, o1), (i2, o2) = ch[2 * bi], ch[2 * bi + 1]
+            p = f"{enc}.net.{slot}"
+            st[p + ".conv_one.weight"], st[p + ".conv_one.bias"] = _conv_params_bias(o1, i1, 3)
+            st[p + ".conv_two.weight"], st[p + ".conv_two.bias"] = _conv_params_bias(o2, i2, 3)
+            _bn_entries(st, p + ".batch_norm_one", o1)
+            _bn_entries(st, p + ".batch_norm_two", o2)
+        st[f"{enc}.net.5.weight"], st[f"{enc}.net.5.bias"] = _linear_params(hid, CONVBLOCK_FLAT[enc])
+    for idx, (o, i) in zip((0, 3, 5), ((hidden_dim, audio_hidden + image_hidden), (hidden_dim // 2, hidden_dim), (NUM_CLASSES, hidden_dim // 2))):
+        st[f"net.{idx}.weight"], st[f"net.{idx}.bias"] = _linear_params(o, i)
+    return st
+
+
+def convblock_encoder_forward(state: Dict[str, Tensor], enc: str, x: Tensor, training: bool) -> Tensor:
+    """MNISTAudio.forward / MNISTImage.forward (avmnist.py:108-118, 177-184)."""
+    if x.dim() == 3:
+        x = x.unsqueeze(1)
+    for slot, pool in zip((0, 2), CONVBLOCK_POOLS[enc]):
+        p = f"{enc}.net.{slot}"
+        x = F.conv2d(x, state[p + ".conv_one.weight"], state[p + ".conv_one.bias"], stride=1, padding=1)
+        x = F.relu(_batch_norm(state, p + ".batch_norm_one", x, training, True))
+        x = F.conv2d(x, state[p + ".conv_two.weight"], state[p + ".conv_two.bias"], stride=1, padding=1)
+        x = F.relu(_batch_norm(state, p + ".batch_norm_two", x, training, True))
+        x = F.max_pool2d(x, kernel_size=pool)
+    return F.linear(torch.flatten(x, 1), state[f"{enc}.net.5.weight"], state[f"{enc}.net.5.bias"])
+
+
+def convblock_train_step(state: "OrderedDict[str, Tensor]", opt_state: Dict, A: Tensor, I: Tensor, labels: Tensor,
+                         dropout_mask: Optional[Tensor] = None, dropout_p: float = 0.5, lr: float = 5e-4, weight_decay: float = 1e-4,
+                         apply_update: bool = True) -> Dict[str, object]:
+    params = {k: v for k, v in state.items() if is_parameter(k)}
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    work = dict(state)
+    work.update(leaves)
+    logits = head_forward(work, convblock_encoder_forward(work, "audio_encoder", A, True), convblock_encoder_forward(work, "image_encoder", I, True),
+                          dropout_mask, dropout_p)
+    loss = total_loss(logits, labels)
+    gl = torch.autograd.grad(loss, list(leaves.values()))
+    grads = dict(zip(leaves.keys(), gl))
+    for k in state:
+        if k.endswith("num_batches_tracked"):
+            state[k] = work[k]
+    if apply_update:
+        with torch.no_grad():
+            adam_step(params, grads, opt_state, lr=lr, weight_decay=weight_decay)
+    return {"loss": float(loss.item()), "logits": logits.detach(), "predictions": torch.softmax(logits.detach(), 1).argmax(1), "grads": grads}
+
+
+# ----------------------------------------------------------------------------------------------
 # e -- data parallel semantics: N replicas, per-replica BatchNorm, gradients averaged
 # ----------------------------------------------------------------------------------------------
 def data_parallel_grads(

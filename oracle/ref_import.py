@@ -107,12 +107,15 @@ def import_reference():
     from models.gates import GatedBiModalNetwork
     from models.mmimdb import MLPGenreClassifier, MMIMDb, MMIMDbModalityEncoder
 
+    from models.avmnist import MNISTAudio, MNISTImage
+    from models.conv import ConvBlockArgs
     from models.msa.networks.classifier import FcClassifier
     from models.msa.networks.lstm import LSTMEncoder
     from models.msa.networks.textcnn import TextCNN
     from models.msa.utt_fusion import UttFusionModel
 
     ns = types.SimpleNamespace(
+        MNISTAudio=MNISTAudio, MNISTImage=MNISTImage, ConvBlockArgs=ConvBlockArgs,
         UttFusionModel=UttFusionModel, LSTMEncoder=LSTMEncoder, TextCNN=TextCNN, FcClassifier=FcClassifier,
         MMIMDb=MMIMDb,
         MMIMDbModalityEncoder=MMIMDbModalityEncoder,

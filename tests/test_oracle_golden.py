@@ -180,3 +180,21 @@ def test_mosi_utt_fusion_oracle_matches_reference():
     assert np.allclose(np.array([float(v.double().norm()) for v in state.values()]), g["state_l2"], rtol=2e-3)
     ev = U.validation_step(state, d["audio_masked"], d["video_masked"], d["text_masked"], d["labels"])
     assert np.abs(ev["logits"].numpy() - g["eval_logits"]).max() < 1e-2
+
+
+def test_convblock_avmnist_oracle_matches_reference():
+    """SURVEY 8f rank 4 (oracle only in round 1): AVMNIST with the MNISTAudio / MNISTImage ConvBlock encoders."""
+    g = np.load(os.path.join(GOLD, "avmnist_convblock_b4.npz"))
+    batch, seed, steps = (int(v) for v in g["meta"])
+    torch.manual_seed(0)
+    state = O.init_convblock_avmnist_state()
+    d = O.synthetic_batch(batch, seed, (32, 94))
+    A, I = O.apply_missing_mask(d["audio"], d["audio_mask"]), O.apply_missing_mask(d["image"], d["image_mask"])
+    opt_state = {}
+    for step in range(steps):
+        out = O.convblock_train_step(state, opt_state, A, I, d["labels"], d["dropout_mask"], 0.5)
+        assert abs(out["loss"] - float(g["losses"][step])) < (1e-5 if step == 0 else 5e-3)
+        if step == 0:
+            assert np.allclose(out["logits"].numpy(), g["logits"], rtol=1e-4, atol=1e-5)
+            l2 = np.array([float(out["grads"][k].double().norm()) for k in g["grad_keys"]])
+            assert np.allclose(l2, g["grad_l2"], rtol=1e-3, atol=1e-8)
