@@ -22,6 +22,7 @@ using namespace mml;
 constexpr int kLstmMaxIn = 32;
 constexpr int kLstmH = 64;
 constexpr int kGates = 4 * kLstmH;  // 256 = one thread per gate row (i, f, g, o blocks of 64)
+constexpr int kLstmStageT = 64;     // sequences up to this length are staged in shared memory by the forward kernel
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -38,19 +39,33 @@ __global__ void __launch_bounds__(kGates) lstm_fwd_kernel(const float* __restric
   float* s_x = s_h + kLstmH;
   float* s_g = s_x + kLstmMaxIn;              // [256]
   const int b = blockIdx.x, g = threadIdx.x;
+  float* s_xall = s_g + kGates;               // [kLstmStageT][IN]: the sample's input sequence (no global load inside the recurrence)
   for (int i = g; i < kGates * kLstmH; i += kGates) s_whh[(i / kLstmH) * 65 + (i % kLstmH)] = w_hh[i];
   for (int i = g; i < kGates * IN; i += kGates) s_wih[(i / IN) * (kLstmMaxIn + 1) + (i % IN)] = w_ih[i];
+  const bool staged = T <= kLstmStageT;
+  if (staged)
+    for (int i = g; i < T * IN; i += kGates) s_xall[i] = x[(size_t)b * T * IN + i];
   if (g < kLstmH) s_h[g] = 0.f;
   const float bias = b_ih[g] + b_hh[g];
   float c = 0.f;  // threads 0..63 own one cell each
   __syncthreads();
   for (int t = 0; t < T; ++t) {
-    if (g < IN) s_x[g] = x[((size_t)b * T + t) * IN + g];
-    __syncthreads();
-    float pre = bias;
-    for (int k = 0; k < IN; ++k) pre = fmaf(s_wih[g * (kLstmMaxIn + 1) + k], s_x[k], pre);
-#pragma unroll 16
-    for (int k = 0; k < kLstmH; ++k) pre = fmaf(s_whh[g * 65 + k], s_h[k], pre);
+    const float* xt = s_xall + t * IN;
+    if (!staged) {
+      if (g < IN) s_x[g] = x[((size_t)b * T + t) * IN + g];
+      __syncthreads();
+      xt = s_x;
+    }
+    float p0 = bias, p1 = 0.f, p2 = 0.f, p3 = 0.f;  // four independent chains instead of one 84-deep dependent FMA chain
+    for (int k = 0; k < IN; ++k) p1 = fmaf(s_wih[g * (kLstmMaxIn + 1) + k], xt[k], p1);
+#pragma unroll
+    for (int k = 0; k < kLstmH; k += 4) {
+      p0 = fmaf(s_whh[g * 65 + k], s_h[k], p0);
+      p1 = fmaf(s_whh[g * 65 + k + 1], s_h[k + 1], p1);
+      p2 = fmaf(s_whh[g * 65 + k + 2], s_h[k + 2], p2);
+      p3 = fmaf(s_whh[g * 65 + k + 3], s_h[k + 3], p3);
+    }
+    const float pre = (p0 + p1) + (p2 + p3);
     const float act = (g >= 2 * kLstmH && g < 3 * kLstmH) ? tanhf(pre) : sigmoidf_(pre);
     s_g[g] = act;
     gates[((size_t)b * T + t) * kGates + g] = act;
@@ -93,12 +108,23 @@ __global__ void __launch_bounds__(kGates) lstm_bwd_kernel(const float* __restric
   float dc = 0.f;  // threads 0..63: gradient of the cell state flowing back in time
   if (g < kLstmH) s_dh[g] = dh_last[(size_t)b * kLstmH + g];
   __syncthreads();
-  for (int t = T - 1; t >= 0; --t) {
+  // saved state of step t, loaded one step ahead (the loads of step t-1 are in flight while step t computes)
+  float n_i = 0.f, n_f = 0.f, n_g = 0.f, n_o = 0.f, n_c = 0.f, n_cp = 0.f, n_hp = 0.f, n_x = 0.f;
+  auto fetch = [&](int t) {
     const size_t bt = (size_t)b * T + t;
     if (g < kLstmH) {
-      const float i_ = gates[bt * kGates + g], f_ = gates[bt * kGates + kLstmH + g], g_ = gates[bt * kGates + 2 * kLstmH + g],
-                  o_ = gates[bt * kGates + 3 * kLstmH + g];
-      const float c_t = cs[bt * kLstmH + g], c_prev = t > 0 ? cs[(bt - 1) * kLstmH + g] : 0.f;
+      n_i = gates[bt * kGates + g], n_f = gates[bt * kGates + kLstmH + g], n_g = gates[bt * kGates + 2 * kLstmH + g], n_o = gates[bt * kGates + 3 * kLstmH + g];
+      n_c = cs[bt * kLstmH + g];
+      n_cp = t > 0 ? cs[(bt - 1) * kLstmH + g] : 0.f;
+      n_hp = t > 0 ? hs[(bt - 1) * kLstmH + g] : 0.f;
+    }
+    if (g < IN) n_x = x[bt * IN + g];
+  };
+  fetch(T - 1);
+  for (int t = T - 1; t >= 0; --t) {
+    const float i_ = n_i, f_ = n_f, g_ = n_g, o_ = n_o, c_t = n_c, c_prev = n_cp, h_prev = n_hp, x_t = n_x;
+    if (t > 0) fetch(t - 1);
+    if (g < kLstmH) {
       const float tc = tanhf(c_t), dh = s_dh[g];
       dc += dh * o_ * (1.f - tc * tc);
       s_dg[g] = dc * g_ * i_ * (1.f - i_);
@@ -106,9 +132,9 @@ __global__ void __launch_bounds__(kGates) lstm_bwd_kernel(const float* __restric
       s_dg[2 * kLstmH + g] = dc * i_ * (1.f - g_ * g_);
       s_dg[3 * kLstmH + g] = dh * tc * o_ * (1.f - o_);
       dc *= f_;
-      s_hp[g] = t > 0 ? hs[(bt - 1) * kLstmH + g] : 0.f;
+      s_hp[g] = h_prev;
     }
-    if (g < IN) s_x[g] = x[bt * IN + g];
+    if (g < IN) s_x[g] = x_t;
     __syncthreads();
     const float d = s_dg[g];
     acc_b += d;
@@ -262,7 +288,7 @@ __global__ void clip_scale_kernel(const double* __restrict__ partial, int parts,
   if (norm_out) norm_out[0] = norm;
 }
 
-size_t lstm_fwd_smem() { return sizeof(float) * (kGates * 65 + kGates * (kLstmMaxIn + 1) + kLstmH + kLstmMaxIn + kGates); }
+size_t lstm_fwd_smem() { return sizeof(float) * (kGates * 65 + kGates * (kLstmMaxIn + 1) + kLstmH + kLstmMaxIn + kGates + kLstmStageT * kLstmMaxIn); }
 size_t lstm_bwd_smem() { return sizeof(float) * (kGates * 65 + kGates + kLstmH + kLstmMaxIn + 4 * kLstmH + kLstmH); }
 
 }  // namespace

@@ -54,7 +54,7 @@ def cpu_state(model):
     return OrderedDict((k, v.detach().cpu().clone().contiguous()) for k, v in model.state_dict().items())
 
 
-@pytest.mark.parametrize("B,T,IN", [(32, 50, 5), (32, 50, 20), (3, 7, 32)])
+@pytest.mark.parametrize("B,T,IN", [(32, 50, 5), (32, 50, 20), (3, 7, 32), (2, 70, 5)])
 def test_lstm_kernels(B, T, IN):
     from mml_b200 import ops
 
