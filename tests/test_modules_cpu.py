@@ -160,3 +160,63 @@ def test_pattern_generation_matches_reference_fixture_and_masks():
     b = data.attach_masks({"audio": torch.zeros(2, 4), "image": torch.zeros(2, 3), "labels": torch.zeros(2)},
                           {"audio": torch.ones(2), "image": torch.ones(2)}, ["audio", "image"])
     assert set(b) == {"audio_original", "audio_missing_index", "image_original", "image_missing_index", "labels"}
+
+
+def test_shim_builds_the_other_configs_from_the_reference_yaml_tags():
+    """The YAML tags of configs 3 / 4 build the B200 classes with the reference's state_dict layout (CPU: construction only)."""
+    import yaml
+
+    import gated_fusion_oracle as G
+    import utt_fusion_oracle as U
+    from mml_b200 import mmimdb, mono, shim, utt_fusion
+    from mml_b200.resnet import ResNet18
+
+    got = shim.install()
+    assert got["MMIMDb"] is mmimdb.MMIMDb and got["UttFusionModel"] is utt_fusion.UttFusionModel and got["MonomodalEncoder"] is mono.MonomodalEncoder
+    # mmimdb_baseline.yaml:10-31
+    torch.manual_seed(0)
+    cfg = yaml.safe_load(
+        "img: !MMIMDbModalityEncoder {input_dim: 4096, output_dim: 512}\n"
+        "txt: !MMIMDbModalityEncoder {input_dim: 300, output_dim: 512}\n"
+        "gmu: !GatedBiModalNetwork {input_one_dim: 512, output_one_dim: 512, input_two_dim: 512, output_two_dim: 512}\n"
+        "clf: !MLPGenreClassifier {input_size: 512, hidden_size: 512, output_size: 23}\n")
+    model = mmimdb.MMIMDb(cfg["img"], cfg["txt"], gated_bimodal_network=cfg["gmu"], classifier=cfg["clf"])
+    torch.manual_seed(0)
+    ref = G.init_mmimdb_state()
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(ref.keys()) and all(torch.equal(sd[k], ref[k]) for k in ref)
+    # mmimdb_pooling.yaml: pooling built inside the model constructor, after the classifier
+    for pt in ("max", "avg", "sum", "attention", "gated"):
+        torch.manual_seed(0)
+        m2 = mmimdb.MMIMDb(mmimdb.MMIMDbModalityEncoder(4096, 512), mmimdb.MMIMDbModalityEncoder(300, 512),
+                           multimodal_pooling={"pooling_type": pt, "hidden_dim": 512, "dropout": 0.1}, classifier=mmimdb.MLPGenreClassifier(512, 23, 512))
+        torch.manual_seed(0)
+        r2 = G.init_mmimdb_pooling_state(pt)
+        s2 = m2.state_dict()
+        assert list(s2.keys()) == list(r2.keys()) and all(torch.equal(s2[k], r2[k]) for k in r2), pt
+    # utt_fusion_base_training.yaml:14-46
+    torch.manual_seed(0)
+    cfg = yaml.safe_load(
+        "a: !LSTMEncoder {input_size: 5, hidden_size: 64, embd_method: last}\n"
+        "v: !LSTMEncoder {input_size: 20, hidden_size: 64, embd_method: last}\n"
+        "t: !TextCNN {input_size: 768, embd_size: 64, dropout: 0.5, in_channels: 1, out_channels: 128, kernel_heights: [3, 4, 5]}\n"
+        "c: !FcClassifier {input_dim: 192, layers: [192, 64, 32], output_dim: 3, dropout: 0.5}\n")
+    um = utt_fusion.UttFusionModel(cfg["a"], cfg["v"], cfg["t"], cfg["c"], clip=1.0)
+    torch.manual_seed(0)
+    ru = U.init_utt_state()
+    su = um.state_dict()
+    assert list(su.keys()) == list(ru.keys()) and all(torch.equal(su[k], ru[k]) for k in ru)
+    # monomodal wrapper (train_monomodal.py:68-71)
+    torch.manual_seed(0)
+    mm = mono.MonomodalEncoder(ResNet18(1, 64), 64, 10)
+    torch.manual_seed(0)
+    rm = O.init_monomodal_state("resnet18", 1, 64, 10)
+    sm = mm.state_dict()
+    assert list(sm.keys()) == list(rm.keys()) and all(torch.equal(sm[k], rm[k]) for k in rm)
+    # no CPU execution path anywhere
+    with pytest.raises(RuntimeError):
+        model.train_step({"image": torch.zeros(2, 4096), "text": torch.zeros(2, 300), "label": torch.zeros(2, 23), "pattern_name": ["it"] * 2},
+                         torch.optim.Adam(model.parameters()), None, torch.device("cpu"), None)
+    with pytest.raises(RuntimeError):
+        um.train_step({"audio": torch.zeros(2, 50, 5), "video": torch.zeros(2, 50, 20), "text": torch.zeros(2, 50, 768), "label": torch.zeros(2, dtype=torch.long),
+                       "pattern_name": ["atv"] * 2}, torch.optim.Adam(um.parameters()), None, torch.device("cpu"), None)
