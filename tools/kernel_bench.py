@@ -98,5 +98,7 @@ if __name__ == "__main__":
         head(B)
     if what == "l1":
         conv(B, 28, 28, 64, 64, 3, 1, 1, "a.l1")
+    if what == "l3":
+        conv(B, 7, 7, 256, 256, 3, 1, 1, "a.l3")
     if what == "l2":
         conv(B, 14, 14, 128, 128, 3, 1, 1, "a.l2")
