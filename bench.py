@@ -594,6 +594,56 @@ def dominant_kernel_roofline(torch, ops, B, pk):
             "flops_per_launch": flops, "algorithmic_bytes_per_launch": 2.0 * N * H * W * C * 2 + K * 9 * C * 2, "us_per_launch": t * 1e6}
 
 
+def hbm_kernel_rooflines(torch, ops, B, pk):
+    """Achieved HBM GB/s of the two memory-bound kernel families timed alone (L2 flushed): the fused BatchNorm-apply + ReLU +
+    residual forward on the ResNet18 layer1 tensor and the Adam update over the full parameter vector.  Never fatal."""
+    out = {}
+    try:
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+        def timeit(fn):
+            for _ in range(2):
+                fn()
+            ts = []
+            for _ in range(8):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e-3)
+            return statistics.median(ts)
+
+        rows, Cn = B * 28 * 28, 64
+        x = torch.randn(rows, Cn, device="cuda").to(torch.bfloat16)
+        res = torch.randn(rows, Cn, device="cuda").to(torch.bfloat16)
+        y = torch.empty_like(x)
+        stats = torch.zeros(16, Cn, 2, device="cuda", dtype=torch.float64)
+        xf = x.float()
+        stats[0, :, 0] = xf.sum(0).double()
+        stats[0, :, 1] = (xf * xf).sum(0).double()
+        f = lambda *sh: torch.zeros(*sh, device="cuda")
+        bn = ops.BNBuffers(stats, torch.ones(Cn, device="cuda"), f(Cn), f(Cn), torch.ones(Cn, device="cuda"), f(Cn), f(Cn))
+        t = timeit(lambda: ops.bn_train_fwd(x, bn, res, None, y, rows, Cn, True))
+        bytes_bn = 3.0 * rows * Cn * 2  # read raw + residual, write output (bf16)
+        out["bn_relu_residual_fwd"] = {"bound": "hbm", "achieved": bytes_bn / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                       "frac": bytes_bn / t / 1e9 / pk["hbm_gbs"], "us_per_launch": t * 1e6, "algorithmic_bytes_per_launch": bytes_bn}
+        n = 32_580_800
+        p_, g_, m_, v_ = (torch.randn(n, device="cuda") * 0.01 for _ in range(4))
+        v_.abs_()
+        wb = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+        hyper = torch.tensor([5e-4, 0.9, 0.999, 1e-8, 1e-4, 1.0, 0.0, 0.0], device="cuda")
+        step = torch.zeros(1, device="cuda", dtype=torch.int64)
+        t = timeit(lambda: ops.adam_step(p_, g_, m_, v_, wb, hyper, step, True))
+        bytes_adam = 30.0 * n  # read p, g, m, v; write p, m, v (fp32) + the bf16 shadow
+        out["adam"] = {"bound": "hbm", "achieved": bytes_adam / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": bytes_adam / t / 1e9 / pk["hbm_gbs"],
+                       "us_per_launch": t * 1e6, "algorithmic_bytes_per_launch": bytes_adam}
+    except Exception as exc:  # a diagnostic must never cost the bench line
+        out["error"] = repr(exc)[:200]
+    return out
+
+
 def _dbg(rank, msg):
     if os.environ.get("MML_BENCH_DEBUG"):
         print(f"[bench r{rank} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
@@ -713,6 +763,7 @@ def run_b200_arm(args):
     value = B * world * args.steps / t_dev
     e2e_value = B * world * args.steps / t_e2e
     roof = dominant_kernel_roofline(torch, ops, B, pk)
+    hbm_roofs = hbm_kernel_rooflines(torch, ops, B, pk)
     step_tf = TRAIN_GFLOP_PER_SAMPLE * B * args.steps / t_dev / 1e3
     # config 5 (FedAvg, K = 8 clients x 32.58 M fp32 parameters): algorithmic bytes (K+1)*4 per parameter
     Kc, npar = 8, eng.fs.total
@@ -747,6 +798,7 @@ def run_b200_arm(args):
         "launches_per_step": launches_per_step,
         "clocks": clocks,
         "roofline": roof,
+        "hbm_rooflines": hbm_roofs,
         "step_tensor_roofline": {"achieved": step_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": step_tf / pk["tf_sustained"],
                                  "note": f"{TRAIN_GFLOP_PER_SAMPLE} dense-nominal GFLOP/sample x samples/s per GPU vs {pk['src']} sustained bf16"},
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
