@@ -220,3 +220,51 @@ def test_shim_builds_the_other_configs_from_the_reference_yaml_tags():
     with pytest.raises(RuntimeError):
         um.train_step({"audio": torch.zeros(2, 50, 5), "video": torch.zeros(2, 50, 20), "text": torch.zeros(2, 50, 768), "label": torch.zeros(2, dtype=torch.long),
                        "pattern_name": ["atv"] * 2}, torch.optim.Adam(um.parameters()), None, torch.device("cpu"), None)
+
+
+def test_flat_state_layout_and_param_group_ranges(monkeypatch):
+    """Host logic of FlatState on CPU tensors (the bf16 shadow cast is the only device call; it is patched out here):
+    augmented weight|bias blocks, strided views, load_state_dict through them, optimizer param groups -> flat ranges."""
+    from mml_b200 import engine, ops
+
+    monkeypatch.setattr(ops, "cast_f32_bf16", lambda src, dst: dst.copy_(src))
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.enc = torch.nn.Sequential(torch.nn.BatchNorm1d(300), torch.nn.Linear(300, 64))
+            self.head = torch.nn.Linear(64, 10)
+
+    torch.manual_seed(0)
+    net = Net()
+    ref = {k: v.clone() for k, v in net.state_dict().items()}
+    fs = engine.FlatState(net, torch.device("cpu"), augment={"enc.1.weight": "enc.1.bias"})
+    o, n_out, n_in, ld = fs.aug["enc.1.weight"]
+    assert (n_out, n_in, ld) == (64, 300, 320) and fs.aug["enc.1.bias"] == fs.aug["enc.1.weight"]
+    m = fs.aug_matrix(fs.P, "enc.1.weight")
+    assert torch.equal(m[:, :300], ref["enc.1.weight"]) and torch.equal(m[:, 300], ref["enc.1.bias"]) and float(m[:, 301:].abs().max()) == 0.0
+    assert net.enc[1].weight.data_ptr() == m.data_ptr() and net.enc[1].bias.data_ptr() == m[:, 300].data_ptr()
+    assert net.enc[1].weight.grad.data_ptr() == fs.aug_matrix(fs.G, "enc.1.weight").data_ptr()
+    for k, v in net.state_dict().items():  # names, shapes and values survive the re-homing
+        assert v.shape == ref[k].shape and torch.equal(v, ref[k]), k
+    # load_state_dict writes through the strided views into the flat buffer
+    new = {k: (torch.full_like(v, 0.5) if v.is_floating_point() else v) for k, v in ref.items()}
+    net.load_state_dict(new)
+    assert float(m[:, :301].min()) == 0.5 and float(m[:, 301:].abs().max()) == 0.0 and fs.is_bound()
+    # param groups: encoder (BN + augmented Linear) and head with different hyper-parameters -> two contiguous ranges
+    opt = torch.optim.Adam([{"params": list(net.enc.parameters()), "lr": 1e-4, "weight_decay": 2e-4}, {"params": list(net.head.parameters()), "lr": 5e-4}])
+    fs.adopt_optimizer(opt)
+    fs.sync_hyper(opt, 0.5)
+    assert len(fs.ranges) == 2 and fs.ranges[0][0] == 0 and fs.ranges[0][1] == fs.ranges[1][0] == fs.offsets["head.weight"] and fs.ranges[1][1] == fs.total
+    assert fs.adam_ranges(0, fs.total) == [(0, fs.ranges[0][1], 0), (fs.ranges[0][1], fs.total, 1)]
+    assert abs(float(fs.hyper[0, 0]) - 1e-4) < 1e-10 and abs(float(fs.hyper[1, 0]) - 5e-4) < 1e-10 and float(fs.hyper[1, 5]) == 0.5
+    assert opt.state[net.head.weight]["exp_avg"].data_ptr() == fs.M.data_ptr() + 4 * fs.offsets["head.weight"]
+    v0 = fs.range_version
+    fs.adopt_optimizer(opt)  # same grouping: nothing changes
+    assert fs.range_version == v0
+    fs.adopt_optimizer(torch.optim.Adam(net.parameters(), lr=1e-3))
+    assert fs.ranges == [(0, fs.total, 0)] and fs.range_version == v0 + 1
+    with pytest.raises(NotImplementedError):  # weight and bias of an augmented Linear cannot be in different groups
+        fs.adopt_optimizer(torch.optim.Adam([{"params": [net.enc[1].weight]}, {"params": [p for p in net.parameters() if p is not net.enc[1].weight]}]))
+    with pytest.raises(NotImplementedError):
+        fs.adopt_optimizer(torch.optim.SGD(net.parameters(), lr=0.1))
