@@ -268,3 +268,42 @@ def test_flat_state_layout_and_param_group_ranges(monkeypatch):
         fs.adopt_optimizer(torch.optim.Adam([{"params": [net.enc[1].weight]}, {"params": [p for p in net.parameters() if p is not net.enc[1].weight]}]))
     with pytest.raises(NotImplementedError):
         fs.adopt_optimizer(torch.optim.SGD(net.parameters(), lr=0.1))
+
+
+def test_batch_unpacking_follows_the_reference_batch_contracts():
+    """Batch dict handling of the four step methods (keys are ``modalities.Modality`` members in the reference, str() lower-case)."""
+    import enum
+
+    from mml_b200.avmnist import AVMNIST
+    from mml_b200.mmimdb import MMIMDb
+    from mml_b200.mono import MonomodalEncoder
+    from mml_b200.utt_fusion import UttFusionModel
+
+    class Modality(enum.Enum):
+        AUDIO, IMAGE, TEXT, VIDEO = "audio", "image", "text", "video"
+
+        def __str__(self):
+            return self.value
+
+    t = lambda *s: torch.zeros(*s)
+    # AVMNIST: reference contract (already masked tensors) and the device-mask extension
+    A, I, ma, mi, y, pat = AVMNIST._unpack(None, {Modality.AUDIO: t(2, 4, 4), Modality.IMAGE: t(2, 1, 3, 3), "labels": t(2), "pattern_name": ["ai", "a"]})
+    assert A.shape == (2, 4, 4) and ma is None and mi is None and pat == ["ai", "a"]
+    A, I, ma, mi, y, pat = AVMNIST._unpack(None, {"audio_original": t(2, 4, 4) + 1, "audio_missing_index": t(2), "image": t(2, 1, 3, 3), "labels": t(2)})
+    assert float(A.min()) == 1.0 and ma is not None and mi is None
+    with pytest.raises(KeyError):
+        AVMNIST._unpack(None, {"audio": t(2, 4, 4), "labels": t(2)})
+    # MMIMDb: "label" (singular), image / text
+    Ib, Tb, m_i, m_t, yb, pb = MMIMDb._unpack(None, {Modality.IMAGE: t(2, 8), Modality.TEXT: t(2, 5), "label": t(2, 23), "pattern_name": ["it", "t"]})
+    assert Ib.shape == (2, 8) and Tb.shape == (2, 5) and yb.shape == (2, 23) and m_i is None
+    # UttFusion: three modalities, any subset given as original + mask
+    out = UttFusionModel._unpack(None, {Modality.AUDIO: t(2, 6, 5), Modality.VIDEO: t(2, 6, 20), "text_original": t(2, 6, 768) + 2, "text_missing_index": t(2),
+                                        "label": t(2), "pattern_name": ["atv", "av"]})
+    assert out[3][0] is None and out[3][1] is None and out[3][2] is not None and float(out[2].min()) == 2.0
+    # monomodal: prefers <modality>_original (the un-masked tensor), config name selects the modality
+    cfg = type("C", (), {"experiment": type("E", (), {"name": "AVMNIST_Image_Encoder_Resnet_Pretrain"})()})()
+    key, x, lab = MonomodalEncoder._unpack({"AUDIO": t(2, 4, 4), "IMAGE": t(2, 3, 3), "IMAGE_original": t(2, 3, 3) + 3, "IMAGE_missing_index": t(2),
+                                            "labels": torch.zeros(2, dtype=torch.long), "pattern_name": ["ai"] * 2}, cfg)
+    assert key == "IMAGE" and float(x.min()) == 3.0
+    with pytest.raises(NotImplementedError):
+        MonomodalEncoder._unpack({"AUDIO": ["a.pt", "b.pt"], "labels": torch.zeros(2, dtype=torch.long)}, None)
