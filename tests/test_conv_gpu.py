@@ -9,6 +9,8 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False  # the torch reference convolution must be true fp32
+torch.backends.cuda.matmul.allow_tf32 = False
 
 # (N, H, W, C, K, R, stride, pad)
 SHAPES = [
@@ -34,6 +36,19 @@ SHAPES = [
     (3, 8, 24, 64, 128, 3, 2, 1),
     (5, 2, 6, 256, 512, 3, 2, 1),     # -> 1x3
     (5, 1, 3, 512, 512, 3, 1, 1),
+    # BASELINE.json configs[1] (batch 256 per GPU): the shapes bench.py runs.  Only at this size do the persistent kernels walk
+    # several tiles per CTA (halo fprop / dgrad: ~12 tiles per CTA -> TMEM double-buffer parity, patch-ring wrap; halo wgrad:
+    # multi-tile TMEM accumulation) and do the split-K kernels use every split.
+    (256, 28, 28, 64, 64, 3, 1, 1),   # R18 layer1 (halo kernel, weights resident)
+    (256, 14, 14, 128, 128, 3, 1, 1), # R18 layer2 (halo kernel, weight ring)
+    (256, 7, 7, 256, 256, 3, 1, 1),   # R18 layer3
+    (256, 14, 14, 128, 256, 3, 2, 1), # R18 layer3.0.conv1 (stride 2)
+    (256, 4, 4, 512, 512, 3, 1, 1),   # R18 layer4
+    (256, 28, 28, 64, 128, 3, 2, 1),  # R18 layer2.0.conv1
+    (256, 7, 7, 64, 64, 3, 1, 1),     # R34 layer1
+    (256, 2, 2, 256, 256, 3, 1, 1),   # R34 layer3
+    (256, 1, 1, 512, 512, 3, 1, 1),   # R34 layer4
+    (250, 28, 28, 64, 64, 3, 1, 1),   # ragged batch on the persistent path (tile count not a multiple of the grid)
 ]
 
 

@@ -65,7 +65,8 @@ def forced_from_plan(plan, state):
     return forced
 
 
-@pytest.mark.parametrize("B,hw", [(16, (112, 112)), (6, (32, 94))])
+# B = 256 is BASELINE.json configs[1], the configuration bench.py times: the persistent conv kernels then walk ~12 tiles per CTA
+@pytest.mark.parametrize("B,hw", [(16, (112, 112)), (6, (32, 94)), (256, (112, 112))])
 def test_forced_backward_parity(B, hw):
     model = build(graphs=False)
     torch.manual_seed(0)
@@ -112,7 +113,7 @@ def test_unforced_loss_logits_and_adam_update():
     ref = O.train_step(copy.deepcopy(state), {}, A, d["image"], d["labels"], d["dropout_mask"], 0.5, apply_update=False)
     assert abs(out["loss"] - ref["loss"]) < 1e-2
     rng = float(ref["logits"].max() - ref["logits"].min())
-    assert (plan.logits.cpu() - ref["logits"]).abs().max().item() < 0.10 * rng
+    assert (plan.logits.cpu() - ref["logits"]).abs().max().item() < LOGIT_TOL * rng  # see test_unforced_logits_against_bf16_rounding_oracle
     # Adam: the fused update applied exactly torch's rule to the GPU's own gradients
     for n, p in model.named_parameters():
         g = p.grad.detach()
@@ -332,3 +333,80 @@ def test_adam_param_groups_follow_the_optimizer():
     for k, lr in (("audio_encoder.layer1.0.conv1.weight", 1e-4), ("image_encoder.layer1.0.conv1.weight", 2e-4), ("net.0.weight", 5e-4)):
         step_size = float((dict(model2.named_parameters())[k].detach() - b2[k]).abs().median())
         assert abs(step_size - lr) < 0.05 * lr, (k, step_size)
+
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", ["avmnist_b4_112", "avmnist_b6_32x94"])
+def test_reference_golden_fixture_on_gpu(name):
+    """The CUDA path against the fixtures written by the UNMODIFIED reference (oracle/make_golden.py), without the oracle in
+    between: same seed => bit-identical initial weights, same synthetic batch, same dropout mask; loss / logits of step 0, the
+    loss sequence of the recorded steps and the eval-mode logits afterwards.  Tolerances are the bf16-storage ones of the module
+    docstring (the reference is fp32)."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    batch, aH, aW, seed, steps = (int(v) for v in g["meta"])
+    model = build(graphs=False)
+    d = O.synthetic_batch(batch, seed, (aH, aW))
+    A = O.apply_missing_mask(d["audio"], d["audio_mask"])
+    assert np.allclose(g["input_checksum"], [float(A.double().sum()), float(d["image"].double().sum()), float(d["labels"].sum())])
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
+    losses = []
+    for step in range(steps):
+        out = model.train_step(make_batch(d, batch), opt, LOSS, torch.device(DEV), None, dropout_mask=d["dropout_mask"])
+        losses.append(out["loss"])
+        if step == 0:
+            plan = next(iter(model._engine.plans.values()))
+            rng = float(g["logits"].max() - g["logits"].min())
+            err = float(np.abs(plan.logits.cpu().numpy() - g["logits"]).max())
+            print(f"{name}: step-0 loss {out['loss']:.5f} vs reference {float(g['loss']):.5f}; logit error {err:.4f} = {err / rng:.4f} of the logit range")
+            assert abs(out["loss"] - float(g["loss"])) < 1e-2
+            assert err < LOGIT_TOL * rng
+            # gradient norms per tensor: un-forced gradients are ill-conditioned (module docstring), the NORMS of the big tensors are not
+            keys = list(g["grad_keys"])
+            got = {n: float(p.grad.detach().double().norm()) for n, p in model.named_parameters()}
+            tot_g = np.sqrt(sum(got[k] ** 2 for k in keys))
+            tot_r = float(np.sqrt((g["grad_l2"] ** 2).sum()))
+            print(f"{name}: global gradient norm {tot_g:.5f} vs reference {tot_r:.5f}")
+            assert abs(tot_g - tot_r) < 0.25 * tot_r
+    print(f"{name}: losses {np.round(losses, 4)} vs reference {np.round(g['losses'], 4)}")
+    assert np.abs(np.array(losses) - g["losses"]).max() < 8e-2
+    model.eval()
+    ev = model.forward(A=A.to(DEV), I=d["image"].to(DEV)).cpu().numpy()
+    rng = float(g["eval_logits"].max() - g["eval_logits"].min())
+    assert np.abs(ev - g["eval_logits"]).max() < 0.10 * rng + 5e-2
+
+
+# measured on B200 (printed by the test below): |GPU - fp32 oracle| is 2-4 % of the logit range at random initialisation, of which
+# the oracle ITSELF moves by about the same amount when it rounds where the kernels round (emulate_bf16); the bound is ~2x measured
+LOGIT_TOL = 0.08
+LOGIT_TOL_EMULATED = 0.06
+
+
+@pytest.mark.parametrize("B,hw", [(32, (112, 112)), (256, (112, 112))])
+def test_unforced_logits_against_bf16_rounding_oracle(B, hw):
+    """Un-forced forward error pinned: GPU vs the fp32 oracle, GPU vs the oracle that rounds activations / weights to bf16 at the
+    points where the kernels store bf16 (late_fusion_oracle emulate_bf16), and that oracle vs its fp32 self."""
+    model = build(graphs=False)
+    torch.manual_seed(0)
+    state = O.init_avmnist_state()
+    d = O.synthetic_batch(B, 77, hw)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
+    out = model.train_step(make_batch(d, B), opt, LOSS, torch.device(DEV), None, dropout_mask=d["dropout_mask"])
+    plan = next(iter(model._engine.plans.values()))
+    A = O.apply_missing_mask(d["audio"], d["audio_mask"])
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref = O.train_step(copy.deepcopy(state), {}, A, d["image"], d["labels"], d["dropout_mask"], 0.5, apply_update=False)
+    emu = O.train_step(copy.deepcopy(state), {}, A, d["image"], d["labels"], d["dropout_mask"], 0.5, apply_update=False, emulate_bf16=True)
+    rng = float(ref["logits"].max() - ref["logits"].min())
+    got = plan.logits.cpu()
+    e_ref = float((got - ref["logits"]).abs().max()) / rng
+    e_emu = float((got - emu["logits"]).abs().max()) / rng
+    e_self = float((emu["logits"] - ref["logits"]).abs().max()) / rng
+    print(f"B={B}: |gpu - fp32 oracle| = {e_ref:.4f}, |gpu - bf16-rounding oracle| = {e_emu:.4f}, |bf16-rounding oracle - fp32 oracle| = {e_self:.4f} (fractions of the logit range {rng:.3f}); "
+          f"loss gpu {out['loss']:.5f} fp32 {ref['loss']:.5f} rounded {emu['loss']:.5f}")
+    assert e_ref < LOGIT_TOL, e_ref
+    assert e_emu < LOGIT_TOL_EMULATED, e_emu
+    assert abs(out["loss"] - ref["loss"]) < 1e-2
+    agree = float((plan.pred.cpu().long() == ref["predictions"]).float().mean())
+    assert agree >= 0.9, agree
