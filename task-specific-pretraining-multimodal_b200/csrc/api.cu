@@ -57,19 +57,10 @@ int mml_ctx_create(int device, mml_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->encode_tiled = (mml_tmap_encode_tiled_fn)fn;
-  ctx->workspace_bytes = (size_t)48 << 20;
-  if (cudaMalloc(&ctx->workspace, ctx->workspace_bytes) != cudaSuccess) {
-    cudaGetLastError();
-    ctx->workspace = nullptr;
-    ctx->workspace_bytes = 0;
-  }
   *out = ctx;
   return MML_OK;
 }
 
-void mml_ctx_destroy(mml_ctx* ctx) {
-  if (ctx && ctx->workspace) cudaFree(ctx->workspace);
-  delete ctx;
-}
+void mml_ctx_destroy(mml_ctx* ctx) { delete ctx; }
 
 }  // extern "C"

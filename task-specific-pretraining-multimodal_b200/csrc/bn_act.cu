@@ -60,90 +60,12 @@ __global__ void mask_apply_kernel(const float* __restrict__ x, const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// training-mode BatchNorm forward, fused: statistics -> scale/shift in the prologue (no finalize launch)
-//   stats[c] = (sum, sum of squares) of the conv output, accumulated in fp64 by the conv / stem epilogue.
-//   y = relu?(bn(x) [+ res | + bn_r(res)]);  block 0 also saves mean / invstd for backward and updates the running
-//   statistics: running = (1-m)*running + m*batch, unbiased variance (torch.nn.BatchNorm2d, momentum 0.1).
+// BatchNorm statistics -> coefficients.  In the fused step the LAST CTA of the kernel that produced the statistics (conv / stem
+// epilogue, bn_bwd_reduce) does this (mml_common.cuh::bn_final_forward); the stand-alone kernel below is the same code for
+// callers whose statistics come from elsewhere.
 // ---------------------------------------------------------------------------------------------------------------
-struct BnTrain {
-  const double* stats;   // [C][2]
-  const float* gamma;
-  const float* beta;
-  float* running_mean;   // may be null
-  float* running_var;
-  float* save_mean;
-  float* save_invstd;
-};
-
-__device__ __forceinline__ void bn_coeffs(const BnTrain& b, int C, int c, double inv_count, float eps, float& scale, float& shift,
-                                          float& mean_f, float& invstd, double& var_out) {
-  double sum, sq;
-  stat_load(b.stats, C, c, sum, sq);
-  const double mean = sum * inv_count;
-  double var = sq * inv_count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  invstd = (float)(1.0 / sqrt(var + (double)eps));
-  scale = b.gamma[c] * invstd;
-  mean_f = (float)mean;
-  shift = b.beta[c] - mean_f * scale;
-  var_out = var;
-}
-
-// Cooperative prologue: the CTA derives scale / shift for all C channels once into shared memory (each channel = 32 fp64
-// loads from L2); block 0 also writes the saved statistics and the running-statistics update.
-__device__ __forceinline__ void bn_prologue(const BnTrain& b, int C, double inv_count, double unbias, float momentum, float eps, float* s_scale,
-                                            float* s_shift) {
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float sc, sh, mu, is;
-    double var;
-    bn_coeffs(b, C, c, inv_count, eps, sc, sh, mu, is, var);
-    s_scale[c] = sc;
-    s_shift[c] = sh;
-    if (blockIdx.x == 0) {
-      b.save_mean[c] = mu;
-      b.save_invstd[c] = is;
-      if (b.running_mean) {
-        b.running_mean[c] = (1.f - momentum) * b.running_mean[c] + momentum * mu;
-        b.running_var[c] = (1.f - momentum) * b.running_var[c] + momentum * (float)(var * unbias);
-      }
-    }
-  }
-}
-
-constexpr int kMaxC = 512;
-
-// RES: 0 = none, 1 = identity residual, 2 = residual through its own training-mode BN (downsample path)
-template <int RES, bool RELU>
-__global__ void __launch_bounds__(kThreads)
-bn_train_fwd_kernel(const uint16_t* __restrict__ x, BnTrain bn, const uint16_t* __restrict__ res, BnTrain rbn, uint16_t* __restrict__ y,
-                    long long n8, int c8, double inv_count, double unbias, float momentum, float eps) {
-  __shared__ __align__(16) float s_coef[(RES == 2 ? 4 : 2) * kMaxC];
-  const int C = c8 * 8;
-  bn_prologue(bn, C, inv_count, unbias, momentum, eps, s_coef, s_coef + kMaxC);
-  if (RES == 2) bn_prologue(rbn, C, inv_count, unbias, momentum, eps, s_coef + 2 * kMaxC, s_coef + 3 * kMaxC);
-  __syncthreads();
-  const long long stride = (long long)gridDim.x * kThreads;
-  long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
-  const int cg = (int)(i % c8);
-  const F8 sc = load8f(s_coef + cg * 8), sh = load8f(s_coef + kMaxC + cg * 8);
-  F8 rsc, rsh;
-  if (RES == 2) {
-    rsc = load8f(s_coef + 2 * kMaxC + cg * 8);
-    rsh = load8f(s_coef + 3 * kMaxC + cg * 8);
-  }
-  for (; i < n8; i += stride) {
-    F8 v = unpack8(ldg16(x + i * 8));
-    F8 r;
-    if (RES != 0) r = unpack8(ldg16(res + i * 8));
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float o = fmaf(v.v[j], sc.v[j], sh.v[j]);
-      if (RES == 1) o += r.v[j];
-      if (RES == 2) o += fmaf(r.v[j], rsc.v[j], rsh.v[j]);
-      v.v[j] = RELU ? fmaxf(o, 0.f) : o;
-    }
-    *reinterpret_cast<uint4*>(y + i * 8) = pack8(v);
-  }
+__global__ void __launch_bounds__(kThreads) bn_finalize_kernel(const double* __restrict__ stats, BnFinal f, int C) {
+  bn_final_forward(f, stats, C, blockIdx.x * kThreads + threadIdx.x, gridDim.x * kThreads);
 }
 
 __global__ void bn_eval_coeffs_kernel(int C, const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
@@ -156,8 +78,11 @@ __global__ void bn_eval_coeffs_kernel(int C, const float* gamma, const float* be
   }
 }
 
+constexpr int kU = 4;  // independent 16-byte loads in flight per tensor and thread (HBM latency x bandwidth / resident threads)
+
 // ---------------------------------------------------------------------------------------------------------------
-// coefficient form (eval mode): y = relu?(x*scale + shift [+ res*rscale + rshift])
+// y = relu?(x*scale + shift [+ res | + res*rscale + rshift])   (training: coefficients from the batch statistics, finalised by
+// the producer; eval: from the running statistics)
 // ---------------------------------------------------------------------------------------------------------------
 template <bool HAS_RES, bool RES_AFFINE, bool RELU>
 __global__ void __launch_bounds__(kThreads)
@@ -173,56 +98,63 @@ bn_act_fwd_kernel(const uint16_t* __restrict__ x, const float* __restrict__ scal
     rsc = load8f(rscale + cg * 8);
     rsh = load8f(rshift + cg * 8);
   }
-  for (; i < n8; i += stride) {
-    F8 v = unpack8(ldg16(x + i * 8));
+  auto one = [&](const uint4& xu, const uint4& ru) {
+    F8 v = unpack8(xu);
     F8 r;
-    if (HAS_RES) r = unpack8(ldg16(res + i * 8));
+    if (HAS_RES) r = unpack8(ru);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float o = fmaf(v.v[j], sc.v[j], sh.v[j]);
       if (HAS_RES) o += RES_AFFINE ? fmaf(r.v[j], rsc.v[j], rsh.v[j]) : r.v[j];
       v.v[j] = RELU ? fmaxf(o, 0.f) : o;
     }
-    *reinterpret_cast<uint4*>(y + i * 8) = pack8(v);
+    return pack8(v);
+  };
+  for (; i + (kU - 1) * stride < n8; i += kU * stride) {
+    uint4 xu[kU], ru[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      xu[u] = ldg16(x + (i + u * stride) * 8);
+      if (HAS_RES) ru[u] = ldg16(res + (i + u * stride) * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) *reinterpret_cast<uint4*>(y + (i + u * stride) * 8) = one(xu[u], ru[u]);
+  }
+  for (; i < n8; i += stride) {
+    const uint4 xu = ldg16(x + i * 8);
+    uint4 ru = make_uint4(0, 0, 0, 0);
+    if (HAS_RES) ru = ldg16(res + i * 8);
+    *reinterpret_cast<uint4*>(y + i * 8) = one(xu, ru);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// backward pass 1: per-block partials of  sum g  and  sum g*xhat,   g = (dy1 [+ dy2]) * (y > 0)
+// backward pass 1: g = (dy1 [+ dy2]) * (y > 0), optionally stored (it IS the gradient of the identity skip path, and pass 2
+// then reads g instead of dy1 / dy2 / y);  per-block partials of  sum g  and  sum g*xhat  -> fp64 slots;  the last CTA turns
+// them into mean(g), mean(g*xhat), dgamma, dbeta
 // ---------------------------------------------------------------------------------------------------------------
-template <bool TWO, bool RELU>
-__global__ void __launch_bounds__(kThreads)
-bn_bwd_reduce_kernel(const uint16_t* __restrict__ dy1, const uint16_t* __restrict__ dy2, const uint16_t* __restrict__ y,
-                     const uint16_t* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
-                     double* __restrict__ bstat, long long n8, int c8) {
-  __shared__ float sh[kThreads][17];
-  const long long stride = (long long)gridDim.x * kThreads;
-  long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
-  const int cg = (int)(i % c8);
-  const F8 mu = load8f(mean + cg * 8), is = load8f(invstd + cg * 8);
-  float sg[8], sgx[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) sg[j] = sgx[j] = 0.f;
-  for (; i < n8; i += stride) {
-    F8 g = unpack8(ldg16(dy1 + i * 8));
-    if (TWO) {
-      const F8 g2 = unpack8(ldg16(dy2 + i * 8));
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g.v[j] += g2.v[j];
-    }
-    if (RELU) {
-      const F8 yy = unpack8(ldg16(y + i * 8));
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g.v[j] = yy.v[j] > 0.f ? g.v[j] : 0.f;
-    }
-    const F8 xv = unpack8(ldg16(x + i * 8));
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (xv.v[j] - mu.v[j]) * is.v[j];
-      sg[j] += g.v[j];
-      sgx[j] = fmaf(g.v[j], xh, sgx[j]);
-    }
+struct BnBwdFinal {
+  unsigned int* counter;
+  float* coef;    // [2][C]: mean(g), mean(g*xhat)
+  float* dgamma;  // may be null
+  float* dbeta;
+  float inv_count;
+};
+
+__device__ __forceinline__ void bn_bwd_finalize(const BnBwdFinal& f, const double* bstat, int C, int tid, int nthreads) {
+  for (int c = tid; c < C; c += nthreads) {
+    double sg, sgx;
+    stat_load_cg(bstat, C, c, sg, sgx);
+    f.coef[c] = (float)sg * f.inv_count;
+    f.coef[C + c] = (float)sgx * f.inv_count;
+    if (f.dbeta) f.dbeta[c] = (float)sg;
+    if (f.dgamma) f.dgamma[c] = (float)sgx;
   }
+}
+
+// block-level channel reduction of the per-thread partials + slot atomics + last-CTA finalisation (shared by the two reduce kernels)
+__device__ __forceinline__ void bn_bwd_block_reduce(const float (&sg)[8], const float (&sgx)[8], float (*sh)[17], volatile uint32_t* flag,
+                                                    double* bstat, const BnBwdFinal& fin, int c8) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     sh[threadIdx.x][j] = sg[j];
@@ -240,61 +172,111 @@ bn_bwd_reduce_kernel(const uint16_t* __restrict__ dy1, const uint16_t* __restric
     }
     stat_add(bstat, C, blockIdx.x, o, a, b);
   }
-}
-
-// backward pass 2: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat));  optional g_out = g (skip-path gradient);
-// coefficients come straight from the fp64 sums of pass 1 (no finalize launch); block 0 writes dgamma / dbeta
-template <bool TWO, bool RELU, bool GOUT>
-__global__ void __launch_bounds__(kThreads)
-bn_bwd_apply_kernel(const uint16_t* __restrict__ dy1, const uint16_t* __restrict__ dy2, const uint16_t* __restrict__ y,
-                    const uint16_t* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const float* __restrict__ gamma, const double* __restrict__ bstat, float inv_count, float* __restrict__ dgamma,
-                    float* __restrict__ dbeta, uint16_t* __restrict__ dx, uint16_t* __restrict__ g_out, long long n8, int c8) {
-  __shared__ __align__(16) float s_k[2 * kMaxC];
-  const int C = c8 * 8;
-  for (int c = threadIdx.x; c < C; c += kThreads) {
-    double sg, sgx;
-    stat_load(bstat, C, c, sg, sgx);
-    s_k[c] = (float)sg * inv_count;          // mean(g)
-    s_k[kMaxC + c] = (float)sgx * inv_count; // mean(g * xhat)
-    if (blockIdx.x == 0) {
-      if (dbeta) dbeta[c] = (float)sg;
-      if (dgamma) dgamma[c] = (float)sgx;
+  if (fin.counter != nullptr) {
+    if (last_cta_arrive(fin.counter, gridDim.x, threadIdx.x, 0, kThreads, flag)) {
+      bn_bwd_finalize(fin, bstat, C, threadIdx.x, kThreads);
+      if (threadIdx.x == 0) *fin.counter = 0u;
     }
   }
-  __syncthreads();
-  // Traverse from the END of the tensors: pass 1 (bn_bwd_reduce) just streamed the same operands front to back, so
-  // their tails are what is still resident in the 126 MB L2.
+}
+
+template <bool TWO, bool RELU, bool GOUT>
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_reduce_kernel(const uint16_t* __restrict__ dy1, const uint16_t* __restrict__ dy2, const uint16_t* __restrict__ y,
+                     const uint16_t* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                     double* __restrict__ bstat, uint16_t* __restrict__ g_out, BnBwdFinal fin, long long n8, int c8) {
+  __shared__ float sh[kThreads][17];
+  __shared__ uint32_t flag;
+  const long long stride = (long long)gridDim.x * kThreads;
+  long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
+  const int cg = (int)(i % c8);
+  const F8 mu = load8f(mean + cg * 8), is = load8f(invstd + cg * 8);
+  float sg[8], sgx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sg[j] = sgx[j] = 0.f;
+  auto one = [&](long long idx, const uint4& d1, const uint4& d2, const uint4& yu, const uint4& xu) {
+    F8 g = unpack8(d1);
+    if (TWO) {
+      const F8 g2 = unpack8(d2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g.v[j] += g2.v[j];
+    }
+    if (RELU) {
+      const F8 yy = unpack8(yu);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g.v[j] = yy.v[j] > 0.f ? g.v[j] : 0.f;
+    }
+    if (GOUT) {
+      const uint4 gp = pack8(g);
+      *reinterpret_cast<uint4*>(g_out + idx * 8) = gp;
+      g = unpack8(gp);  // pass 2 reads the ROUNDED g: the sums must describe the same values
+    }
+    const F8 xv = unpack8(xu);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (xv.v[j] - mu.v[j]) * is.v[j];
+      sg[j] += g.v[j];
+      sgx[j] = fmaf(g.v[j], xh, sgx[j]);
+    }
+  };
+  constexpr int U = 2;
+  for (; i + (U - 1) * stride < n8; i += U * stride) {
+    uint4 d1[U], d2[U], yu[U], xu[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long idx = i + u * stride;
+      d1[u] = ldg16(dy1 + idx * 8);
+      if (TWO) d2[u] = ldg16(dy2 + idx * 8);
+      if (RELU) yu[u] = ldg16(y + idx * 8);
+      xu[u] = ldg16(x + idx * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) one(i + u * stride, d1[u], d2[u], yu[u], xu[u]);
+  }
+  for (; i < n8; i += stride) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    one(i, ldg16(dy1 + i * 8), TWO ? ldg16(dy2 + i * 8) : z, RELU ? ldg16(y + i * 8) : z, ldg16(x + i * 8));
+  }
+  bn_bwd_block_reduce(sg, sgx, sh, &flag, bstat, fin, c8);
+}
+
+// backward pass 2: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)), coefficients finalised by pass 1
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_apply_kernel(const uint16_t* __restrict__ g, const uint16_t* __restrict__ x, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ coef,
+                    uint16_t* __restrict__ dx, long long n8, int c8) {
+  const int C = c8 * 8;
+  // Traverse from the END of the tensors: pass 1 just streamed the same operands front to back, so their tails are what is
+  // still resident in the 126 MB L2.
   const long long stride = (long long)gridDim.x * kThreads;
   long long i = n8 - 1 - (blockIdx.x * (long long)kThreads + threadIdx.x);
   const int cg = (int)(((i % c8) + c8) % c8);
   const F8 mu = load8f(mean + cg * 8), is = load8f(invstd + cg * 8);
   F8 k0 = load8f(gamma + cg * 8);
-  const F8 k1 = load8f(s_k + cg * 8), k2 = load8f(s_k + kMaxC + cg * 8);
+  const F8 k1 = load8f(coef + cg * 8), k2 = load8f(coef + C + cg * 8);
 #pragma unroll
   for (int j = 0; j < 8; ++j) k0.v[j] *= is.v[j];  // gamma * invstd
-  for (; i >= 0; i -= stride) {
-    F8 g = unpack8(ldg16(dy1 + i * 8));
-    if (TWO) {
-      const F8 g2 = unpack8(ldg16(dy2 + i * 8));
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g.v[j] += g2.v[j];
-    }
-    if (RELU) {
-      const F8 yy = unpack8(ldg16(y + i * 8));
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g.v[j] = yy.v[j] > 0.f ? g.v[j] : 0.f;
-    }
-    if (GOUT) *reinterpret_cast<uint4*>(g_out + i * 8) = pack8(g);
-    const F8 xv = unpack8(ldg16(x + i * 8));
+  auto one = [&](const uint4& gu, const uint4& xu) {
+    const F8 gv = unpack8(gu), xv = unpack8(xu);
     F8 o;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float xh = (xv.v[j] - mu.v[j]) * is.v[j];
-      o.v[j] = k0.v[j] * (g.v[j] - k1.v[j] - xh * k2.v[j]);
+      o.v[j] = k0.v[j] * (gv.v[j] - k1.v[j] - xh * k2.v[j]);
     }
-    *reinterpret_cast<uint4*>(dx + i * 8) = pack8(o);
+    return pack8(o);
+  };
+  for (; i - (kU - 1) * stride >= 0; i -= kU * stride) {
+    uint4 gu[kU], xu[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      gu[u] = ldg16(g + (i - u * stride) * 8);
+      xu[u] = ldg16(x + (i - u * stride) * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) *reinterpret_cast<uint4*>(dx + (i - u * stride) * 8) = one(gu[u], xu[u]);
   }
+  for (; i >= 0; i -= stride) *reinterpret_cast<uint4*>(dx + i * 8) = one(ldg16(g + i * 8), ldg16(x + i * 8));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -422,27 +404,15 @@ maxpool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__
 // backward.  The post-ReLU activation (the largest tensor of the network: 103 MB at batch 256) is never materialised:
 // backward recomputes the ReLU mask from raw*scale+shift and scatters the pooled gradient through the saved argmax.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool TRAIN>
 __global__ void __launch_bounds__(kThreads)
-stem_bn_pool_fwd_kernel(const uint16_t* __restrict__ x, BnTrain bn, const float* __restrict__ scale_in, const float* __restrict__ shift_in,
-                        uint16_t* __restrict__ y, uint8_t* __restrict__ amax, int N, int H, int W, int C, int P, int Q, double inv_count,
-                        double unbias, float momentum, float eps) {
-  __shared__ __align__(16) float s_coef[2 * kMaxC];
-  if (TRAIN) {
-    bn_prologue(bn, C, inv_count, unbias, momentum, eps, s_coef, s_coef + kMaxC);
-  } else {
-    for (int c = threadIdx.x; c < C; c += kThreads) {
-      s_coef[c] = scale_in[c];
-      s_coef[kMaxC + c] = shift_in[c];
-    }
-  }
-  __syncthreads();
+stem_bn_pool_fwd_kernel(const uint16_t* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                        uint16_t* __restrict__ y, uint8_t* __restrict__ amax, int N, int H, int W, int C, int P, int Q) {
   const int c8 = C >> 3;
   const long long total = (long long)N * P * Q * c8;
   const long long stride = (long long)gridDim.x * kThreads;
   long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
   const int cg = (int)(i % c8);
-  const F8 sc = load8f(s_coef + cg * 8), sh = load8f(s_coef + kMaxC + cg * 8);
+  const F8 sc = load8f(scale + cg * 8), sh = load8f(shift + cg * 8);
   for (; i < total; i += stride) {
     long long t = i / c8;
     const int q = (int)(t % Q);
@@ -532,42 +502,22 @@ __device__ __forceinline__ void pool_scatter_2x2(const uint16_t* __restrict__ dy
   }
 }
 
-// PASS 0: bstat += (sum g, sum g*xhat) and dx = g (the generic bn_bwd_apply kernel then finishes in place);
-// PASS 1 (kept for reference / tests): recompute g and write dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))
-// g = scatter(dpool) * (bn(x) > 0);  bn(x) = gamma*(x-mean)*invstd + beta
-template <int PASS>
+// bstat += (sum g, sum g*xhat) and dx = g (bn_bwd_apply_kernel then finishes in place);  g = scatter(dpool) * (bn(x) > 0),
+// bn(x) = gamma*(x-mean)*invstd + beta;  the last CTA finalises mean(g), mean(g*xhat), dgamma, dbeta
 __global__ void __launch_bounds__(kThreads)
 stem_bn_pool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__ dy2, const uint8_t* __restrict__ amax,
                         const uint16_t* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
-                        const float* __restrict__ gamma, const float* __restrict__ beta, double* __restrict__ bstat, float inv_count,
-                        float* __restrict__ dgamma, float* __restrict__ dbeta, uint16_t* __restrict__ dx, int N, int H, int W, int C, int P, int Q) {
-  __shared__ float sh[PASS == 0 ? kThreads : 1][17];
-  __shared__ __align__(16) float s_k[PASS == 1 ? 2 * kMaxC : 4];
+                        const float* __restrict__ gamma, const float* __restrict__ beta, double* __restrict__ bstat, BnBwdFinal fin,
+                        uint16_t* __restrict__ dx, int N, int H, int W, int C, int P, int Q) {
+  __shared__ float sh[kThreads][17];
+  __shared__ uint32_t flag;
   const int c8 = C >> 3;
-  if (PASS == 1) {
-    for (int c = threadIdx.x; c < C; c += kThreads) {
-      double sg, sgx;
-      stat_load(bstat, C, c, sg, sgx);
-      s_k[c] = (float)sg * inv_count;
-      s_k[kMaxC + c] = (float)sgx * inv_count;
-      if (blockIdx.x == 0) {
-        if (dbeta) dbeta[c] = (float)sg;
-        if (dgamma) dgamma[c] = (float)sgx;
-      }
-    }
-    __syncthreads();
-  }
   const int HB = (H + 1) >> 1, WB = (W + 1) >> 1;
   const long long total = (long long)N * HB * WB * c8;
   const long long stride = (long long)gridDim.x * kThreads;
   long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
   const int cg = (int)(i % c8);
   const F8 mu = load8f(mean + cg * 8), is = load8f(invstd + cg * 8), ga = load8f(gamma + cg * 8), be = load8f(beta + cg * 8);
-  F8 k1, k2;
-  if (PASS == 1) {
-    k1 = load8f(s_k + cg * 8);
-    k2 = load8f(s_k + kMaxC + cg * 8);
-  }
   float sg[8], sgx[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sg[j] = sgx[j] = 0.f;
@@ -577,6 +527,15 @@ stem_bn_pool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restr
     t /= WB;
     const int a = (int)(t % HB);
     const int n = (int)(t / HB);
+    // the four raw-output loads do not depend on the scatter: issue them first
+    uint4 xu[2][2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int h = 2 * a + u, w = 2 * b + v;
+        xu[u][v] = (h < H && w < W) ? ldg16(x + ((((long long)n * H + h) * W + w) * c8 + cg) * 8) : make_uint4(0, 0, 0, 0);
+      }
     F8 acc[2][2];
     pool_scatter_2x2(dy, dy2, amax, n, a, b, cg, c8, P, Q, acc);
 #pragma unroll
@@ -588,41 +547,26 @@ stem_bn_pool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restr
         const int w = 2 * b + v;
         if (w >= W) continue;
         const long long o = ((((long long)n * H + h) * W + w) * c8 + cg) * 8;
-        const F8 xv = unpack8(ldg16(x + o));
+        const F8 xv = unpack8(xu[u][v]);
         F8 out;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xh = (xv.v[j] - mu.v[j]) * is.v[j];
-          const float g = fmaf(ga.v[j], xh, be.v[j]) > 0.f ? acc[u][v].v[j] : 0.f;  // ReLU mask recomputed
-          if (PASS == 0) {
-            sg[j] += g;
-            sgx[j] = fmaf(g, xh, sgx[j]);
-            out.v[j] = g;  // materialised once: the apply pass is then a plain elementwise kernel (no second scatter)
-          } else {
-            out.v[j] = ga.v[j] * is.v[j] * (g - k1.v[j] - xh * k2.v[j]);
-          }
+          out.v[j] = fmaf(ga.v[j], xh, be.v[j]) > 0.f ? acc[u][v].v[j] : 0.f;  // ReLU mask recomputed
         }
-        *reinterpret_cast<uint4*>(dx + o) = pack8(out);
-      }
-    }
-  }
-  if (PASS == 0) {
+        const uint4 gp = pack8(out);
+        *reinterpret_cast<uint4*>(dx + o) = gp;  // materialised once: the apply pass is then a plain elementwise kernel
+        const F8 gr = unpack8(gp);               // sums of the ROUNDED g, which is what the apply pass reads
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sh[threadIdx.x][j] = sg[j];
-      sh[threadIdx.x][8 + j] = sgx[j];
-    }
-    __syncthreads();
-    for (int o = threadIdx.x; o < C; o += kThreads) {
-      const int g = o >> 3, j = o & 7;
-      float aa = 0.f, bb = 0.f;
-      for (int t = g; t < kThreads; t += c8) {
-        aa += sh[t][j];
-        bb += sh[t][8 + j];
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv.v[j] - mu.v[j]) * is.v[j];
+          sg[j] += gr.v[j];
+          sgx[j] = fmaf(gr.v[j], xh, sgx[j]);
+        }
       }
-      stat_add(bstat, C, blockIdx.x, o, aa, bb);
     }
   }
+  bn_bwd_block_reduce(sg, sgx, sh, &flag, bstat, fin, c8);
 }
 
 // AdaptiveAvgPool2d((1,1)) + flatten: [N, HW, C] bf16 -> [N, C] fp32
@@ -669,9 +613,31 @@ int ew_grid(const mml_ctx* ctx, long long items) {
   return (int)b;
 }
 
+// grid for the kernels whose main loop keeps U 16-byte loads per tensor in flight: enough items per thread for the unrolled
+// loop on large tensors, one item per thread spread over the SMs on small ones
+int stream_grid(const mml_ctx* ctx, long long items, int U) {
+  long long b = mml_ceil_div(items, (long long)kThreads * U);
+  if (b < ctx->sm_count) {
+    b = mml_ceil_div(items, kThreads);
+    if (b > ctx->sm_count) b = ctx->sm_count;
+  }
+  const long long cap = (long long)ctx->sm_count * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int bn_final_from_abi(mml_ctx* ctx, const mml_bn_final* fin, BnFinal* f, bool need_counter) {
+  MML_REQUIRE(ctx, fin->gamma && fin->beta && fin->save_mean && fin->save_invstd && fin->scale && fin->shift, "bn_final: null pointer");
+  MML_REQUIRE(ctx, (fin->running_mean == nullptr) == (fin->running_var == nullptr), "bn_final: running_mean / running_var must be given together");
+  MML_REQUIRE(ctx, !need_counter || fin->counter, "bn_final: counter is NULL");
+  *f = bn_final_convert(fin);
+  return MML_OK;
+}
+
 int check_rows_c(mml_ctx* ctx, int64_t rows, int C) {
   MML_REQUIRE(ctx, rows >= 1, "rows must be >= 1");
-  MML_REQUIRE(ctx, C >= 8 && C <= kMaxC && (C % 8) == 0 && (kThreads % (C / 8)) == 0,
+  MML_REQUIRE(ctx, C >= 8 && C <= 2048 && (C % 8) == 0 && (kThreads % (C / 8)) == 0,
               "channel count %d unsupported by the fused BN kernels (need C <= 512 and C/8 to divide 256)", C);
   return MML_OK;
 }
@@ -689,33 +655,12 @@ int mml_mask_apply_f32(mml_ctx* ctx, const float* x, const float* mask, float* y
   return MML_OK;
 }
 
-int mml_bn_train_fwd(mml_ctx* ctx, const uint16_t* x, const double* stats, const float* gamma, const float* beta, float* running_mean,
-                     float* running_var, float* save_mean, float* save_invstd, const uint16_t* res, const double* rstats,
-                     const float* rgamma, const float* rbeta, float* r_running_mean, float* r_running_var, float* r_save_mean,
-                     float* r_save_invstd, uint16_t* y, int64_t rows, int C, int relu, float momentum, float eps, void* stream) {
-  MML_REQUIRE(ctx, ctx && x && stats && gamma && beta && save_mean && save_invstd && y, "bn_train_fwd: null pointer");
-  MML_REQUIRE(ctx, (running_mean == nullptr) == (running_var == nullptr), "bn_train_fwd: running_mean / running_var must be given together");
-  int rc = check_rows_c(ctx, rows, C);
+int mml_bn_finalize(mml_ctx* ctx, const double* stats, const mml_bn_final* fin, int C, void* stream) {
+  MML_REQUIRE(ctx, ctx && stats && fin && C >= 1, "bn_finalize: bad arguments");
+  BnFinal f;
+  int rc = bn_final_from_abi(ctx, fin, &f, /*need_counter=*/false);
   if (rc) return rc;
-  const int mode = res == nullptr ? 0 : (rstats == nullptr ? 1 : 2);
-  if (mode == 2) MML_REQUIRE(ctx, rgamma && rbeta && r_save_mean && r_save_invstd, "bn_train_fwd: residual BN needs gamma/beta/save buffers");
-  BnTrain bn{stats, gamma, beta, running_mean, running_var, save_mean, save_invstd};
-  BnTrain rbn{rstats, rgamma, rbeta, r_running_mean, r_running_var, r_save_mean, r_save_invstd};
-  const long long n8 = rows * (C / 8);
-  const int grid = ew_grid(ctx, n8);
-  const double inv_count = 1.0 / (double)rows;
-  const double unbias = rows > 1 ? (double)rows / (double)(rows - 1) : 1.0;
-  cudaStream_t st = (cudaStream_t)stream;
-#define MML_TR(M, RL) bn_train_fwd_kernel<M, RL><<<grid, kThreads, 0, st>>>(x, bn, res, rbn, y, n8, C / 8, inv_count, unbias, momentum, eps)
-  switch (mode * 2 + (relu ? 1 : 0)) {
-    case 0: MML_TR(0, false); break;
-    case 1: MML_TR(0, true); break;
-    case 2: MML_TR(1, false); break;
-    case 3: MML_TR(1, true); break;
-    case 4: MML_TR(2, false); break;
-    default: MML_TR(2, true); break;
-  }
-#undef MML_TR
+  bn_finalize_kernel<<<(C + kThreads - 1) / kThreads, kThreads, 0, (cudaStream_t)stream>>>(stats, f, C);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }
@@ -735,7 +680,7 @@ int mml_bn_act_fwd(mml_ctx* ctx, const uint16_t* x, const float* scale, const fl
   if (rc) return rc;
   MML_REQUIRE(ctx, (rscale == nullptr) == (rshift == nullptr), "bn_act_fwd: rscale/rshift must be given together");
   const long long n8 = rows * (C / 8);
-  const int grid = ew_grid(ctx, n8);
+  const int grid = stream_grid(ctx, n8, kU);
   cudaStream_t st = (cudaStream_t)stream;
 #define MML_FWD(HR, RA, RL) bn_act_fwd_kernel<HR, RA, RL><<<grid, kThreads, 0, st>>>(x, scale, shift, res, rscale, rshift, y, n8, C / 8)
   if (res == nullptr) {
@@ -759,48 +704,40 @@ static int bn_bwd_grid(const mml_ctx* ctx, int64_t rows, int C) {
 }
 
 int mml_bn_bwd_reduce(mml_ctx* ctx, const uint16_t* dy1, const uint16_t* dy2, const uint16_t* y, const uint16_t* x,
-                      const float* mean, const float* invstd, double* bstat, int64_t rows, int C, int relu, void* stream) {
+                      const float* mean, const float* invstd, double* bstat, uint16_t* g_out, uint32_t* counter, float* coef,
+                      float* dgamma, float* dbeta, int64_t rows, int C, int relu, void* stream) {
   MML_REQUIRE(ctx, ctx && dy1 && x && mean && invstd && bstat && (!relu || y), "bn_bwd_reduce: null pointer");
+  MML_REQUIRE(ctx, (counter == nullptr) == (coef == nullptr), "bn_bwd_reduce: counter and coef must be given together");
   int rc = check_rows_c(ctx, rows, C);
   if (rc) return rc;
   const long long n8 = rows * (C / 8);
   const int grid = bn_bwd_grid(ctx, rows, C);
+  BnBwdFinal fin{counter, coef, dgamma, dbeta, 1.0f / (float)rows};
   cudaStream_t st = (cudaStream_t)stream;
-#define MML_RED(TW, RL) bn_bwd_reduce_kernel<TW, RL><<<grid, kThreads, 0, st>>>(dy1, dy2, y, x, mean, invstd, bstat, n8, C / 8)
-  if (dy2) {
-    if (relu) MML_RED(true, true); else MML_RED(true, false);
-  } else {
-    if (relu) MML_RED(false, true); else MML_RED(false, false);
+#define MML_RED(TW, RL, GO) bn_bwd_reduce_kernel<TW, RL, GO><<<grid, kThreads, 0, st>>>(dy1, dy2, y, x, mean, invstd, bstat, g_out, fin, n8, C / 8)
+  const int key = (dy2 ? 4 : 0) | (relu ? 2 : 0) | (g_out ? 1 : 0);
+  switch (key) {
+    case 0: MML_RED(false, false, false); break;
+    case 1: MML_RED(false, false, true); break;
+    case 2: MML_RED(false, true, false); break;
+    case 3: MML_RED(false, true, true); break;
+    case 4: MML_RED(true, false, false); break;
+    case 5: MML_RED(true, false, true); break;
+    case 6: MML_RED(true, true, false); break;
+    default: MML_RED(true, true, true); break;
   }
 #undef MML_RED
   MML_LAUNCHED(ctx);
   return MML_OK;
 }
 
-int mml_bn_bwd_apply(mml_ctx* ctx, const uint16_t* dy1, const uint16_t* dy2, const uint16_t* y, const uint16_t* x,
-                     const float* mean, const float* invstd, const float* gamma, const double* bstat, float* dgamma, float* dbeta,
-                     uint16_t* dx, uint16_t* g_out, int64_t rows, int C, int relu, void* stream) {
-  MML_REQUIRE(ctx, ctx && dy1 && x && mean && invstd && gamma && bstat && dx && (!relu || y), "bn_bwd_apply: null pointer");
+int mml_bn_bwd_apply(mml_ctx* ctx, const uint16_t* g, const uint16_t* x, const float* mean, const float* invstd, const float* gamma,
+                     const float* coef, uint16_t* dx, int64_t rows, int C, void* stream) {
+  MML_REQUIRE(ctx, ctx && g && x && mean && invstd && gamma && coef && dx, "bn_bwd_apply: null pointer");
   int rc = check_rows_c(ctx, rows, C);
   if (rc) return rc;
   const long long n8 = rows * (C / 8);
-  const int grid = ew_grid(ctx, n8);
-  const float inv_count = 1.0f / (float)rows;
-  cudaStream_t st = (cudaStream_t)stream;
-#define MML_APP(TW, RL, GO) \
-  bn_bwd_apply_kernel<TW, RL, GO><<<grid, kThreads, 0, st>>>(dy1, dy2, y, x, mean, invstd, gamma, bstat, inv_count, dgamma, dbeta, dx, g_out, n8, C / 8)
-  const int key = (dy2 ? 4 : 0) | (relu ? 2 : 0) | (g_out ? 1 : 0);
-  switch (key) {
-    case 0: MML_APP(false, false, false); break;
-    case 1: MML_APP(false, false, true); break;
-    case 2: MML_APP(false, true, false); break;
-    case 3: MML_APP(false, true, true); break;
-    case 4: MML_APP(true, false, false); break;
-    case 5: MML_APP(true, false, true); break;
-    case 6: MML_APP(true, true, false); break;
-    default: MML_APP(true, true, true); break;
-  }
-#undef MML_APP
+  bn_bwd_apply_kernel<<<stream_grid(ctx, n8, kU), kThreads, 0, (cudaStream_t)stream>>>(g, x, mean, invstd, gamma, coef, dx, n8, C / 8);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }
@@ -823,51 +760,37 @@ int mml_maxpool3x3s2_bwd(mml_ctx* ctx, const uint16_t* dy, const uint16_t* dy2, 
   return MML_OK;
 }
 
-int mml_stem_bn_pool_fwd(mml_ctx* ctx, const uint16_t* x, const double* stats, const float* gamma, const float* beta, float* running_mean,
-                         float* running_var, float* save_mean, float* save_invstd, const float* scale, const float* shift, uint16_t* y,
-                         uint8_t* argmax, int N, int H, int W, int C, float momentum, float eps, void* stream) {
-  MML_REQUIRE(ctx, ctx && x && y && argmax && N >= 1 && H >= 1 && W >= 1, "stem_bn_pool_fwd: bad arguments");
-  MML_REQUIRE(ctx, (stats != nullptr) != (scale != nullptr), "stem_bn_pool_fwd: give either batch statistics (train) or scale/shift (eval)");
+int mml_stem_bn_pool_fwd(mml_ctx* ctx, const uint16_t* x, const float* scale, const float* shift, uint16_t* y, uint8_t* argmax, int N, int H,
+                         int W, int C, void* stream) {
+  MML_REQUIRE(ctx, ctx && x && y && argmax && scale && shift && N >= 1 && H >= 1 && W >= 1, "stem_bn_pool_fwd: bad arguments");
   int rc = check_rows_c(ctx, (int64_t)N * H * W, C);
   if (rc) return rc;
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
-  const int64_t rows = (int64_t)N * H * W;
   const int grid = ew_grid(ctx, (long long)N * P * Q * (C / 8));
-  BnTrain bn{stats, gamma, beta, running_mean, running_var, save_mean, save_invstd};
-  cudaStream_t st = (cudaStream_t)stream;
-  if (stats) {
-    MML_REQUIRE(ctx, gamma && beta && save_mean && save_invstd, "stem_bn_pool_fwd: null BN pointer");
-    stem_bn_pool_fwd_kernel<true><<<grid, kThreads, 0, st>>>(x, bn, nullptr, nullptr, y, argmax, N, H, W, C, P, Q, 1.0 / (double)rows,
-                                                              rows > 1 ? (double)rows / (double)(rows - 1) : 1.0, momentum, eps);
-  } else {
-    MML_REQUIRE(ctx, shift != nullptr, "stem_bn_pool_fwd: shift is NULL");
-    stem_bn_pool_fwd_kernel<false><<<grid, kThreads, 0, st>>>(x, bn, scale, shift, y, argmax, N, H, W, C, P, Q, 0.0, 0.0, momentum, eps);
-  }
+  stem_bn_pool_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, scale, shift, y, argmax, N, H, W, C, P, Q);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }
 
 int mml_stem_bn_pool_bwd(mml_ctx* ctx, const uint16_t* dy, const uint16_t* dy2, const uint8_t* argmax, const uint16_t* x, const float* mean,
-                         const float* invstd, const float* gamma, const float* beta, double* bstat, float* dgamma, float* dbeta, uint16_t* dx,
-                         int N, int H, int W, int C, void* stream) {
-  MML_REQUIRE(ctx, ctx && dy && argmax && x && mean && invstd && gamma && beta && bstat && dx && N >= 1 && H >= 1 && W >= 1,
+                         const float* invstd, const float* gamma, const float* beta, double* bstat, uint32_t* counter, float* coef,
+                         float* dgamma, float* dbeta, uint16_t* dx, int N, int H, int W, int C, void* stream) {
+  MML_REQUIRE(ctx, ctx && dy && argmax && x && mean && invstd && gamma && beta && bstat && counter && coef && dx && N >= 1 && H >= 1 && W >= 1,
               "stem_bn_pool_bwd: bad arguments");
   int rc = check_rows_c(ctx, (int64_t)N * H * W, C);
   if (rc) return rc;
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
   const long long items = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-  const float inv_count = 1.0f / (float)((int64_t)N * H * W);
   cudaStream_t st = (cudaStream_t)stream;
   int g0 = (int)mml_ceil_div(items, (long long)kThreads * 2);
   if (g0 > ctx->sm_count * 4) g0 = ctx->sm_count * 4;
   if (g0 < 1) g0 = 1;
-  stem_bn_pool_bwd_kernel<0><<<g0, kThreads, 0, st>>>(dy, dy2, argmax, x, mean, invstd, gamma, beta, bstat, inv_count, dgamma, dbeta, dx, N, H, W,
-                                                      C, P, Q);
+  BnBwdFinal fin{counter, coef, dgamma, dbeta, 1.0f / (float)((int64_t)N * H * W)};
+  stem_bn_pool_bwd_kernel<<<g0, kThreads, 0, st>>>(dy, dy2, argmax, x, mean, invstd, gamma, beta, bstat, fin, dx, N, H, W, C, P, Q);
   MML_LAUNCHED(ctx);
   // pass 2 in place over the buffer that now holds g: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))
   const long long n8 = (long long)N * H * W * (C / 8);
-  bn_bwd_apply_kernel<false, false, false><<<ew_grid(ctx, n8), kThreads, 0, st>>>(dx, nullptr, nullptr, x, mean, invstd, gamma, bstat, inv_count,
-                                                                                  dgamma, dbeta, dx, nullptr, n8, C / 8);
+  bn_bwd_apply_kernel<<<stream_grid(ctx, n8, kU), kThreads, 0, st>>>(dx, x, mean, invstd, gamma, coef, dx, n8, C / 8);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }

@@ -52,6 +52,7 @@ struct IgemmParams {
   int valid_rows;  // OutW * Hb * Nb  (<= 128)
   int cout;
   double* stats;  // [16 slots][cout][2] (sum, sum of squares) of the stored output, accumulated with fp64 atomics; or nullptr
+  BnFinal fin;    // fin.counter != nullptr: the last CTA turns the statistics into BatchNorm coefficients
   Tap taps[kMaxTaps];
 };
 
@@ -240,6 +241,13 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
         }
       }
     }
+    if (p.stats != nullptr && p.fin.counter != nullptr) {
+      volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kOffBars + 8 * (2 * STAGES + 2));
+      if (last_cta_arrive(p.fin.counter, gridDim.x * gridDim.y, et, 1, 128, flag)) {
+        bn_final_forward(p.fin, p.stats, p.cout, et, 128);
+        if (et == 0) *p.fin.counter = 0u;
+      }
+    }
     if (et == 0) tma_store_wait_all<0>();
   }
 
@@ -276,8 +284,8 @@ struct HaloParams {
   int tiles_h, Hb, Wb;
   int m_tiles, num_super;
   int cout;
-  int base_offset_mode;  // 0: descriptor base_offset = 0 (swizzle follows absolute smem address bits), 1: (shift & 7)
   double* stats;
+  BnFinal fin;
   Tap taps[kMaxTaps];
 };
 
@@ -295,10 +303,6 @@ struct HaloSmem {
   static_assert(kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM columns");
   static_assert(kBytes <= 232448, "shared memory budget");
 };
-
-__device__ __forceinline__ uint64_t umma_desc_sw128_bo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t base_offset) {
-  return umma_desc_sw128(smem_addr, lbo_bytes, sbo_bytes) | ((uint64_t)(base_offset & 7u) << 49);
-}
 
 template <int CCH, int BLOCK_N, int T, bool W_RES, bool B_MN>
 __global__ void __launch_bounds__(kHaloThreads, 1)
@@ -538,6 +542,14 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(ab));
     }
+    if (p.stats != nullptr && p.fin.counter != nullptr) {  // both epilogue groups (256 threads) are done with their atomics
+      const int e2 = (warp - 2) * 32 + lane;
+      volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kOffBars + 8 * (12 + 2 * L::kWStages + 1));
+      if (last_cta_arrive(p.fin.counter, gridDim.x, e2, 3, 256, flag)) {
+        bn_final_forward(p.fin, p.stats, p.cout, e2, 256);
+        if (e2 == 0) *p.fin.counter = 0u;
+      }
+    }
     if (eg == 0) tma_store_wait_all<0>();
   }
 
@@ -564,7 +576,8 @@ struct WgradParams {
   int m_tiles;   // total pixel tiles
   int splits;    // gridDim.y
   int ka;        // dY boxes per stage: min(cout,128)/64
-  float* dw;
+  float* dw;     // splits == 1: the gradient itself (overwritten); else partial slabs [splits][K][RS][C], reduced in a fixed order afterwards
+  long long slab;  // elements per slab
   Tap taps[kMaxTaps];
 };
 
@@ -680,34 +693,27 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
   } else {
     const int q = warp & 3;
     const int k = kc * 128 + q * 32 + lane;  // output-channel row of dW owned by this thread
+    // deterministic: every split stores its partial tile with plain stores (no atomics); a split that owns no pixel tile stores zeros
     if (iters > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
-      float* dst_row = p.dw + ((size_t)k * p.rs + tap.widx) * p.cin + cc * BLOCK_C;
+    }
+    float* dst_row = p.dw + (size_t)split * (size_t)p.slab + ((size_t)k * p.rs + tap.widx) * p.cin + cc * BLOCK_C;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_C; c0 += 32) {
-        uint32_t r[32];
+    for (int c0 = 0; c0 < BLOCK_C; c0 += 32) {
+      uint32_t r[32];
+      if (iters > 0) {
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
         tmem_ld_wait();
-        if (k < p.cout) {
-          if (p.splits > 1) {
+      } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + c0 + j), "f"(__uint_as_float(r[j])),
-                           "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
-                           : "memory");
-          } else {
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (k < p.cout) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 cur = *reinterpret_cast<float4*>(dst_row + c0 + j);
-              cur.x += __uint_as_float(r[j]);
-              cur.y += __uint_as_float(r[j + 1]);
-              cur.z += __uint_as_float(r[j + 2]);
-              cur.w += __uint_as_float(r[j + 3]);
-              *reinterpret_cast<float4*>(dst_row + c0 + j) = cur;
-            }
-          }
-        }
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst_row + c0 + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
       }
     }
   }
@@ -893,7 +899,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WHaloMaps maps, const WHaloParams
   if (warp == 1) tmem_dealloc<L::kTmemCols>(tmem_base);
 }
 
-// dw[i] += sum over partials (fixed order => deterministic).  For CH == 2 each grid.y slice wrote only its own filter row.
+// dw[i] = sum over partials in a fixed order (deterministic; OVERWRITES dw).  Halo CH == 2: each grid.y slice wrote only its own filter row.
 // block = 32 elements (float4) x 8 partial slices; slices are combined through shared memory in a fixed order
 __global__ void __launch_bounds__(256) wgrad_partial_reduce_kernel(const float* __restrict__ ws, int parts, long long n, float* __restrict__ dw) {
   __shared__ float4 sh[8][33];
@@ -919,7 +925,7 @@ __global__ void __launch_bounds__(256) wgrad_partial_reduce_kernel(const float* 
   sh[ty][tx] = acc;
   __syncthreads();
   if (ty == 0 && i < n4) {
-    float4 tot = reinterpret_cast<float4*>(dw)[i];
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int y = 0; y < 8; ++y) {
       const float4 v = sh[y][tx];
@@ -927,6 +933,22 @@ __global__ void __launch_bounds__(256) wgrad_partial_reduce_kernel(const float* 
     }
     reinterpret_cast<float4*>(dw)[i] = tot;
   }
+}
+
+// the same for a layer whose filter taps do not all reach the input: only the taps the wgrad kernel wrote are summed (grid.y = tap)
+__global__ void __launch_bounds__(256) wgrad_tap_reduce_kernel(const float* __restrict__ ws, int parts, long long slab, float* __restrict__ dw, int K,
+                                                               int RS, int C, const WgradParams p) {
+  const int widx = p.taps[blockIdx.y].widx;
+  const long long i = blockIdx.x * 256ll + threadIdx.x;  // float4 index over [K][C]
+  if (i >= (long long)K * C / 4) return;
+  const int k = (int)(i / (C / 4)), c4 = (int)(i % (C / 4));
+  const size_t off = ((size_t)k * RS + widx) * C + (size_t)c4 * 4;
+  float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < parts; ++s) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(ws + (size_t)s * slab + off));
+    tot.x += v.x, tot.y += v.y, tot.z += v.z, tot.w += v.w;
+  }
+  *reinterpret_cast<float4*>(dw + off) = tot;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1029,7 +1051,7 @@ int launch_igemm_t(mml_ctx* ctx, const IgemmMaps& maps, const IgemmParams& p, di
 // One "shifted GEMM" launch: out view <- sum over taps of in views @ weights.
 //   b_mn = false: w is [cout rows][n_wtaps*cin inner] bf16;   b_mn = true: w is [cin rows][n_wtaps*cout inner] bf16
 int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, int n_wtaps, int cin, int cout, const View& out,
-              const Tap* taps, int num_taps, double* stats, bool b_mn, cudaStream_t st) {
+              const Tap* taps, int num_taps, double* stats, const BnFinal& fin, bool b_mn, cudaStream_t st) {
   MML_REQUIRE(ctx, cin % 64 == 0 && cout % 64 == 0, "conv: channel counts must be multiples of 64 (got C=%d K=%d)", cin, cout);
   MML_REQUIRE(ctx, num_taps >= 1 && num_taps <= kMaxTaps && n_views <= kMaxViews, "conv: bad tap table");
   TileGeom tg;
@@ -1064,6 +1086,7 @@ int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, in
   p.valid_rows = tg.valid_rows;
   p.cout = cout;
   p.stats = stats;
+  p.fin = fin;
   for (int i = 0; i < num_taps; ++i) p.taps[i] = taps[i];
   dim3 grid(tg.tiles_h * tg.tiles_n, cout / block_n);
   if (!b_mn) {
@@ -1159,10 +1182,9 @@ int launch_halo_t(mml_ctx* ctx, const HaloMaps& maps, const HaloParams& p, cudaS
 }
 
 int g_halo_enable = 1;
-int g_halo_base_offset_mode = 0;
 
 int run_halo(mml_ctx* ctx, const View& in, const void* w, int n_wtaps, int cin, int cout, const View& out, const Tap* taps, int num_taps,
-             double* stats, bool b_mn, const HaloGeom& hg, cudaStream_t st) {
+             double* stats, const BnFinal& fin, bool b_mn, const HaloGeom& hg, cudaStream_t st) {
   HaloMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc;
@@ -1182,8 +1204,8 @@ int run_halo(mml_ctx* ctx, const View& in, const void* w, int n_wtaps, int cin, 
   p.m_tiles = hg.m_tiles;
   p.num_super = (hg.m_tiles + T - 1) / T;
   p.cout = cout;
-  p.base_offset_mode = g_halo_base_offset_mode;
   p.stats = stats;
+  p.fin = fin;
   for (int i = 0; i < num_taps; ++i) p.taps[i] = taps[i];
   if (cin == 64) return b_mn ? launch_halo_t<1, 64, 1, true, true>(ctx, maps, p, st) : launch_halo_t<1, 64, 1, true, false>(ctx, maps, p, st);
   return b_mn ? launch_halo_t<2, 128, 2, false, true>(ctx, maps, p, st) : launch_halo_t<2, 128, 2, false, false>(ctx, maps, p, st);
@@ -1226,18 +1248,24 @@ int launch_wgrad_t(mml_ctx* ctx, const WgradMaps& maps, const WgradParams& p, di
 
 extern "C" {
 
-/* experiment / A-B switches: key 1 = halo kernel enable (0/1), key 2 = halo descriptor base-offset mode (0/1) */
+/* experiment / A-B switch: key 1 = halo kernel enable (0/1) */
 int mml_debug_set(int key, int value) {
   if (key == 1) g_halo_enable = value;
-  else if (key == 2) g_halo_base_offset_mode = value;
   else return MML_ERR_INVALID;
   return MML_OK;
 }
 
 int mml_conv_fprop(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, const uint16_t* w_krsc, uint16_t* y,
                    double* stats, void* stream) {
+  return mml_conv_fprop_bn(ctx, g, x, w_krsc, y, stats, nullptr, stream);
+}
+
+int mml_conv_fprop_bn(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, const uint16_t* w_krsc, uint16_t* y, double* stats,
+                      const mml_bn_final* fin_abi, void* stream) {
   int P, Q, rc;
   if ((rc = check_geom(ctx, g, &P, &Q))) return rc;
+  MML_REQUIRE(ctx, fin_abi == nullptr || (stats != nullptr && fin_abi->counter != nullptr), "conv_fprop_bn: finalisation needs stats and a counter");
+  const BnFinal fin = bn_final_convert(fin_abi);
   View views[kMaxViews];
   Tap taps[kMaxTaps];
   int n_views = 0;
@@ -1257,8 +1285,8 @@ int mml_conv_fprop(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, cons
   View out = make_phase_view(y, g->N, P, Q, g->K, 1, 0, 0);
   HaloGeom hg;
   if (g_halo_enable && g->R == 3 && g->stride == 1 && g->pad == 1 && n_taps == 9 && halo_geometry(Q, P, g->N, g->C, g->K, &hg))
-    return run_halo(ctx, used[0], w_krsc, 9, g->C, g->K, out, taps, n_taps, stats, false, hg, (cudaStream_t)stream);
-  return run_igemm(ctx, used, n_used, w_krsc, g->R * g->S, g->C, g->K, out, taps, n_taps, stats, false, (cudaStream_t)stream);
+    return run_halo(ctx, used[0], w_krsc, 9, g->C, g->K, out, taps, n_taps, stats, fin, false, hg, (cudaStream_t)stream);
+  return run_igemm(ctx, used, n_used, w_krsc, g->R * g->S, g->C, g->K, out, taps, n_taps, stats, fin, false, (cudaStream_t)stream);
 }
 
 int mml_conv_dgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* dy, const uint16_t* w_krsc, uint16_t* dx, void* stream) {
@@ -1267,6 +1295,7 @@ int mml_conv_dgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* dy, con
   cudaStream_t st = (cudaStream_t)stream;
   const int s2 = g->stride;
   View in = make_phase_view(dy, g->N, P, Q, g->K, 1, 0, 0);
+  const BnFinal no_fin = bn_final_convert(nullptr);
   bool need_zero = false;
   // dx[h] = sum_r dy[(h + pad - r)/stride] * w_t[r]  over taps with (h + pad - r) % stride == 0.
   // Per output phase e = h % stride:  h = stride*a + e,  p = a + (e + pad - r)/stride.
@@ -1303,16 +1332,69 @@ int mml_conv_dgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* dy, con
   if (need_zero) MML_CHECK_CUDA(ctx, cudaMemsetAsync(dx, 0, (size_t)g->N * g->H * g->W * g->C * 2, st));
   HaloGeom hg;
   if (g_halo_enable && g->R == 3 && s2 == 1 && g->pad == 1 && n_launch == 1 && launches[0].n == 9 && halo_geometry(g->W, g->H, g->N, g->K, g->C, &hg))
-    return run_halo(ctx, in, w_krsc, 9, g->K, g->C, launches[0].out, launches[0].taps, 9, nullptr, true, hg, st);
+    return run_halo(ctx, in, w_krsc, 9, g->K, g->C, launches[0].out, launches[0].taps, 9, nullptr, no_fin, true, hg, st);
   for (int i = 0; i < n_launch; ++i) {
     // GEMM-K = k (rows of the K,R,S,C weight matrix), GEMM-N = c: the fprop weights are read as an MN-major B operand
-    rc = run_igemm(ctx, &in, 1, w_krsc, g->R * g->S, g->K, g->C, launches[i].out, launches[i].taps, launches[i].n, nullptr, true, st);
+    rc = run_igemm(ctx, &in, 1, w_krsc, g->R * g->S, g->K, g->C, launches[i].out, launches[i].taps, launches[i].n, nullptr, no_fin, true, st);
     if (rc) return rc;
   }
   return MML_OK;
 }
 
-int mml_conv_wgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, const uint16_t* dy, float* dw_krsc, void* stream) {
+// how mml_conv_wgrad will run a geometry: kernel family, grid, splits and the workspace it needs for the per-CTA / per-split partials
+struct WgradPlan {
+  bool halo;
+  HaloGeom hg;
+  int halo_ctas;
+  TileGeom tg;
+  int n_taps, block_c, out_tiles, splits;
+  long long slab;  // elements of one dW-shaped partial slab
+  size_t ws_bytes;
+};
+
+static int plan_wgrad(const mml_ctx* ctx, const mml_conv_geom* g, int P, int Q, int n_taps, WgradPlan* wp) {
+  memset(wp, 0, sizeof(*wp));
+  wp->n_taps = n_taps;
+  wp->slab = (long long)g->K * g->R * g->S * g->C;
+  if (g_halo_enable && g->R == 3 && g->stride == 1 && g->pad == 1 && n_taps == 9 && halo_geometry(Q, P, g->N, g->C, g->K, &wp->hg)) {
+    const int CH = g->C / 64;
+    const int sms = persistent_sms(ctx);
+    int ctas = CH == 1 ? sms : sms / 3;
+    if (ctas > wp->hg.m_tiles) ctas = wp->hg.m_tiles;
+    wp->halo = true;
+    wp->halo_ctas = ctas;
+    // sized for ALL SMs: the SM budget of the persistent kernels may differ between the query and the launch
+    const int max_ctas = CH == 1 ? ctx->sm_count : ctx->sm_count / 3;
+    wp->ws_bytes = (size_t)(max_ctas < wp->hg.m_tiles ? max_ctas : wp->hg.m_tiles) * wp->slab * sizeof(float);
+    return MML_OK;
+  }
+  if (!choose_tile(Q, P, g->N, &wp->tg)) return MML_ERR_INVALID;
+  wp->block_c = g->C % 256 == 0 ? 256 : (g->C % 128 == 0 ? 128 : 64);
+  wp->out_tiles = (int)mml_ceil_div(g->K, 128) * n_taps * (g->C / wp->block_c);
+  const int m_tiles = wp->tg.tiles_h * wp->tg.tiles_n;
+  int splits = (2 * ctx->sm_count + wp->out_tiles - 1) / wp->out_tiles;
+  if (splits > m_tiles) splits = m_tiles;
+  if (splits < 1) splits = 1;
+  wp->splits = splits;
+  wp->ws_bytes = splits > 1 ? (size_t)splits * wp->slab * sizeof(float) : 0;
+  return MML_OK;
+}
+
+int64_t mml_conv_wgrad_workspace(const mml_ctx* ctx, const mml_conv_geom* g) {
+  if (!ctx || !g || g->stride < 1) return -1;
+  const int P = (g->H + 2 * g->pad - g->R) / g->stride + 1, Q = (g->W + 2 * g->pad - g->S) / g->stride + 1;
+  if (P < 1 || Q < 1) return -1;
+  View views[kMaxViews];
+  Tap taps[kMaxTaps];
+  int n_views = 0;
+  const int n_taps = build_fprop_taps(g, P, Q, nullptr, views, &n_views, taps);
+  WgradPlan wp;
+  if (n_taps < 1 || plan_wgrad(ctx, g, P, Q, n_taps, &wp) != MML_OK) return -1;
+  return (int64_t)wp.ws_bytes;
+}
+
+int mml_conv_wgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, const uint16_t* dy, float* dw_krsc, float* workspace,
+                   int64_t workspace_bytes, void* stream) {
   int P, Q, rc;
   if ((rc = check_geom(ctx, g, &P, &Q))) return rc;
   MML_REQUIRE(ctx, g->C % 64 == 0 && g->K % 64 == 0, "conv wgrad: channel counts must be multiples of 64");
@@ -1321,30 +1403,27 @@ int mml_conv_wgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, cons
   int n_views = 0;
   const int n_taps = build_fprop_taps(g, P, Q, x, views, &n_views, taps);
   MML_REQUIRE(ctx, n_taps >= 1, "conv wgrad: no filter tap reaches the input");
-  HaloGeom hg;
-  if (g_halo_enable && g->R == 3 && g->stride == 1 && g->pad == 1 && n_taps == 9 && halo_geometry(Q, P, g->N, g->C, g->K, &hg) && ctx->workspace) {
+  WgradPlan wp;
+  MML_REQUIRE(ctx, plan_wgrad(ctx, g, P, Q, n_taps, &wp) == MML_OK, "conv wgrad: output width %d not supported", Q);
+  MML_REQUIRE(ctx, wp.ws_bytes == 0 || (workspace != nullptr && (size_t)workspace_bytes >= wp.ws_bytes),
+              "conv wgrad: workspace of %lld bytes needed (mml_conv_wgrad_workspace), got %lld", (long long)wp.ws_bytes, (long long)workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (wp.halo) {
+    const HaloGeom& hg = wp.hg;
     const int CH = g->C / 64;
-    const int sms = persistent_sms(ctx);
-    int ctas = CH == 1 ? sms : sms / 3;
-    if (ctas > hg.m_tiles) ctas = hg.m_tiles;
-    const size_t need = (size_t)ctas * g->K * 9 * g->C * sizeof(float);
-    if (need <= ctx->workspace_bytes) {
-      WHaloMaps hm;
-      memset(&hm, 0, sizeof(hm));
-      if ((rc = encode_view(ctx, &hm.x, views[0], hg.Wb + 2, hg.Hb + 2, 1))) return rc;
-      View dyh = make_phase_view(dy, g->N, P, Q, g->K, 1, 0, 0);
-      if ((rc = encode_view(ctx, &hm.dy, dyh, hg.Wb + 2, hg.Hb, 1))) return rc;
-      WHaloParams hp;
-      hp.tiles_h = hg.tiles_h, hp.Hb = hg.Hb, hp.Wb = hg.Wb, hp.m_tiles = hg.m_tiles;
-      hp.rows_m = hg.Hb * (hg.Wb + 2);
-      hp.ws = (float*)ctx->workspace;
-      // CH == 2: the three filter-row CTAs of a column write disjoint taps of the same partial slot
-      return CH == 1 ? launch_wgrad_halo_t<1>(ctx, hm, hp, ctas, dw_krsc, (cudaStream_t)stream)
-                     : launch_wgrad_halo_t<2>(ctx, hm, hp, ctas, dw_krsc, (cudaStream_t)stream);
-    }
+    WHaloMaps hm;
+    memset(&hm, 0, sizeof(hm));
+    if ((rc = encode_view(ctx, &hm.x, views[0], hg.Wb + 2, hg.Hb + 2, 1))) return rc;
+    View dyh = make_phase_view(dy, g->N, P, Q, g->K, 1, 0, 0);
+    if ((rc = encode_view(ctx, &hm.dy, dyh, hg.Wb + 2, hg.Hb, 1))) return rc;
+    WHaloParams hp;
+    hp.tiles_h = hg.tiles_h, hp.Hb = hg.Hb, hp.Wb = hg.Wb, hp.m_tiles = hg.m_tiles;
+    hp.rows_m = hg.Hb * (hg.Wb + 2);
+    hp.ws = workspace;
+    // CH == 2: the three filter-row CTAs of a column write disjoint taps of the same partial slot
+    return CH == 1 ? launch_wgrad_halo_t<1>(ctx, hm, hp, wp.halo_ctas, dw_krsc, st) : launch_wgrad_halo_t<2>(ctx, hm, hp, wp.halo_ctas, dw_krsc, st);
   }
-  TileGeom tg;
-  MML_REQUIRE(ctx, choose_tile(Q, P, g->N, &tg), "conv wgrad: output width %d not supported", Q);
+  const TileGeom& tg = wp.tg;
   WgradMaps maps;
   memset(&maps, 0, sizeof(maps));
   int remap[kMaxViews], n_used = 0;
@@ -1357,7 +1436,7 @@ int mml_conv_wgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, cons
   }
   View dyv = make_phase_view(dy, g->N, P, Q, g->K, 1, 0, 0);
   if ((rc = encode_view(ctx, &maps.dy, dyv, tg.Wb, tg.Hb, tg.Nb))) return rc;
-  const int block_c = g->C % 256 == 0 ? 256 : (g->C % 128 == 0 ? 128 : 64);
+  const int block_c = wp.block_c;
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.num_taps = n_taps;
@@ -1371,24 +1450,36 @@ int mml_conv_wgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, cons
   p.valid_rows = tg.valid_rows;
   p.m_tiles = tg.tiles_h * tg.tiles_n;
   p.ka = g->K >= 128 ? 2 : 1;
-  p.dw = dw_krsc;
+  p.splits = wp.splits;
+  p.slab = wp.slab;
+  p.dw = wp.splits > 1 ? workspace : dw_krsc;
   for (int i = 0; i < n_taps; ++i) {
     p.taps[i] = taps[i];
     p.taps[i].map = (int8_t)remap[taps[i].map];
   }
-  const int out_tiles = (int)mml_ceil_div(g->K, 128) * n_taps * p.c_blocks;
-  int splits = (2 * ctx->sm_count + out_tiles - 1) / out_tiles;
-  if (splits > p.m_tiles) splits = p.m_tiles;
-  if (splits < 1) splits = 1;
-  p.splits = splits;
-  dim3 grid(out_tiles, splits);
-  cudaStream_t st = (cudaStream_t)stream;
+  // filter taps that never reach the input (e.g. 8 of the 9 taps on a 1x1 map) are written by no CTA: their gradient is zero
+  if (n_taps < g->R * g->S) MML_CHECK_CUDA(ctx, cudaMemsetAsync(dw_krsc, 0, (size_t)wp.slab * sizeof(float), st));
+  dim3 grid(wp.out_tiles, wp.splits);
   switch (block_c) {
-    case 64: return launch_wgrad_t<64, 4>(ctx, maps, p, grid, st);
-    case 128: return launch_wgrad_t<128, 3>(ctx, maps, p, grid, st);
-    case 256: return launch_wgrad_t<256, 2>(ctx, maps, p, grid, st);
+    case 64: rc = launch_wgrad_t<64, 4>(ctx, maps, p, grid, st); break;
+    case 128: rc = launch_wgrad_t<128, 3>(ctx, maps, p, grid, st); break;
+    case 256: rc = launch_wgrad_t<256, 2>(ctx, maps, p, grid, st); break;
+    default: return mml_set_error(ctx, MML_ERR_INVALID, "conv wgrad: unsupported C=%d", g->C);
   }
-  return mml_set_error(ctx, MML_ERR_INVALID, "conv wgrad: unsupported C=%d", g->C);
+  if (rc) return rc;
+  if (wp.splits > 1) {
+    // fixed-order sum of the split partials into dW; unreached taps hold garbage in the slabs, so only reached taps are summed
+    // when some taps are missing (rare: tiny maps), otherwise the whole slab in one launch
+    if (n_taps == g->R * g->S) {
+      wgrad_partial_reduce_kernel<<<(int)mml_ceil_div(wp.slab / 4, 32), 256, 0, st>>>(workspace, wp.splits, wp.slab, dw_krsc);
+      MML_LAUNCHED(ctx);
+    } else {
+      wgrad_tap_reduce_kernel<<<dim3((unsigned)mml_ceil_div((long long)g->K * g->C / 4, 256), n_taps), 256, 0, st>>>(workspace, wp.splits, wp.slab, dw_krsc,
+                                                                                                                  g->K, g->R * g->S, g->C, p);
+      MML_LAUNCHED(ctx);
+    }
+  }
+  return MML_OK;
 }
 
 }  // extern "C"

@@ -18,10 +18,8 @@ struct mml_ctx {
   int sm_count;
   int64_t launches;
   mml_tmap_encode_tiled_fn encode_tiled;
-  // scratch for kernels that reduce per-CTA partials (halo wgrad); allocated once at creation so that nothing allocates
-  // inside a CUDA-graph capture.  One user at a time in stream order (the audio encoder's backward).
-  void* workspace;
-  size_t workspace_bytes;
+  // (the library owns no device memory: scratch for per-CTA / per-split partials is passed in by the caller, one buffer per
+  // stream of weight-gradient launches -- see mml_conv_wgrad_workspace)
   // SMs the persistent kernels may occupy (0 = all): a caller that runs a second stream of small kernels next to them can keep a
   // few SMs free so those kernels never wait for a whole persistent grid to drain (mml_ctx_set_sm_budget)
   int sm_budget;

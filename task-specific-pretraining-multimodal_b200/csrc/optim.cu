@@ -4,7 +4,6 @@
 //                        configs/avmnist/centralised/train_avmnist_resnet.yaml:28-32 and stepped at models/avmnist.py:303;
 //                        one launch over the flat fp32 parameter / gradient / moment buffers (28 B per parameter) that
 //                        also refreshes the bf16 shadow copy the tensor-core kernels read (+2 B).
-//   mml_weights_transpose  KRSC -> CRSK copies of the bf16 conv weights (dgrad operand).
 //   mml_fedavg           theta = sum_k (n_k / sum n) theta_k.  The reference has NO implementation
 //                        (MML_Suite/train_congruent_federated.py is empty); textbook FedAvg.
 #include "mml_common.cuh"
@@ -73,28 +72,6 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src
   }
   for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
     dst[i] = (uint16_t)(pack_bf16x2(src[i], 0.f) & 0xFFFFu);
-}
-
-// table row: src_off, dst_off, K, RS, C, first_block.  One block = one 32x32 (k, c) tile of one tap.
-__global__ void __launch_bounds__(256)
-weights_transpose_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, const long long* __restrict__ table, int n_convs) {
-  __shared__ uint16_t tile[32][33];
-  int ci = 0;
-  for (int t = 1; t < n_convs; ++t)
-    if ((long long)blockIdx.x >= table[t * 6 + 5]) ci = t;
-  const long long* row = table + ci * 6;
-  const long long so = row[0], dof = row[1];
-  const int K = (int)row[2], RS = (int)row[3], C = (int)row[4];
-  int b = blockIdx.x - (int)row[5];
-  const int ct = C / 32, kt = K / 32;
-  const int c0 = (b % ct) * 32;
-  b /= ct;
-  const int k0 = (b % kt) * 32;
-  const int tap = b / kt;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (int j = ty; j < 32; j += 8) tile[j][tx] = src[so + ((long long)(k0 + j) * RS + tap) * C + c0 + tx];
-  __syncthreads();
-  for (int j = ty; j < 32; j += 8) dst[dof + ((long long)(c0 + j) * RS + tap) * K + k0 + tx] = tile[tx][j];
 }
 
 constexpr int kMaxClients = 64;
@@ -170,14 +147,6 @@ int mml_cast_f32_bf16(mml_ctx* ctx, const float* src, uint16_t* dst, int64_t n, 
   MML_REQUIRE(ctx, ctx && src && dst && n >= 1, "cast: bad arguments");
   MML_REQUIRE(ctx, aligned16(src) && ((uintptr_t)dst & 7u) == 0, "cast: buffers must be aligned");
   cast_kernel<<<flat_grid(ctx, n), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
-  MML_LAUNCHED(ctx);
-  return MML_OK;
-}
-
-int mml_weights_transpose(mml_ctx* ctx, const uint16_t* src, uint16_t* dst, const int64_t* table, int n_convs, int total_blocks,
-                          void* stream) {
-  MML_REQUIRE(ctx, ctx && src && dst && table && n_convs >= 1 && total_blocks >= 1, "weights_transpose: bad arguments");
-  weights_transpose_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, (const long long*)table, n_convs);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }

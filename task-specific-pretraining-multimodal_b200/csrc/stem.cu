@@ -123,7 +123,7 @@ constexpr int kFBytes = kFOffBars + 1024 + 1024;
 
 __global__ void __launch_bounds__(kThreadsStem, 3)
 stem_fprop_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restrict__ x, const float* __restrict__ mask,
-                     const float* __restrict__ w, double* __restrict__ stats, StemGeom g) {
+                     const float* __restrict__ w, double* __restrict__ stats, BnFinal fin, StemGeom g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -261,6 +261,13 @@ stem_fprop_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
       named_bar_sync(1, 128);
     }
     if (n_my >= 1) epilogue(n_my - 1);
+    if (stats != nullptr && fin.counter != nullptr) {
+      volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(smem_gen + kFOffBars + 8 * 5);
+      if (last_cta_arrive(fin.counter, gridDim.x, (int)threadIdx.x, 1, 128, flag)) {
+        bn_final_forward(fin, stats, 64, (int)threadIdx.x, 128);
+        if (threadIdx.x == 0) *fin.counter = 0u;
+      }
+    }
     if (threadIdx.x == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
@@ -419,7 +426,14 @@ extern "C" {
 
 int mml_stem_fprop(mml_ctx* ctx, const float* x, const float* mask, const float* w, uint16_t* y, double* stats, int B, int H,
                    int W, void* stream) {
+  return mml_stem_fprop_bn(ctx, x, mask, w, y, stats, nullptr, B, H, W, stream);
+}
+
+int mml_stem_fprop_bn(mml_ctx* ctx, const float* x, const float* mask, const float* w, uint16_t* y, double* stats, const mml_bn_final* fin_abi,
+                      int B, int H, int W, void* stream) {
   MML_REQUIRE(ctx, ctx && x && w && y, "stem_fprop: null pointer");
+  MML_REQUIRE(ctx, fin_abi == nullptr || (stats != nullptr && fin_abi->counter != nullptr), "stem_fprop_bn: finalisation needs stats and a counter");
+  const BnFinal fin = bn_final_convert(fin_abi);
   MML_REQUIRE(ctx, B >= 1 && H >= 1 && W >= 1, "stem_fprop: bad dims");
   StemGeom g;
   MML_REQUIRE(ctx, stem_geom(B, H, W, &g), "stem: output width %d not supported (max 128)", (W - 1) / 2 + 1);
@@ -432,7 +446,7 @@ int mml_stem_fprop(mml_ctx* ctx, const float* x, const float* mask, const float*
     MML_CHECK_CUDA(ctx, cudaFuncSetAttribute(stem_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWBytes));
     configured = true;
   }
-  stem_fprop_tc_kernel<<<stem_ctas(ctx, g.tiles, 3), kThreadsStem, kFBytes, (cudaStream_t)stream>>>(maps, x, mask, w, stats, g);
+  stem_fprop_tc_kernel<<<stem_ctas(ctx, g.tiles, 3), kThreadsStem, kFBytes, (cudaStream_t)stream>>>(maps, x, mask, w, stats, fin, g);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }

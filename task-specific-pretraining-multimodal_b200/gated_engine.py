@@ -124,6 +124,8 @@ class _GatedPlan:
         multi = _os.environ.get("MML_GATED_STREAMS", "1") == "1"
         self.side = torch.cuda.Stream(device=dev) if multi else None
         self.wstream = torch.cuda.Stream(device=dev) if multi else None
+        # every weight-gradient launch of a step runs on ONE stream (wstream, or the only stream when not multi): one scratch
+        self.wgrad_ws = self.wgrad_ws_main = ops.WgradScratch(dev)
         self.eager_steps = 0
         self.launches_per_step = 0
         self._build(params, LI, LT)
@@ -213,11 +215,11 @@ class _GatedPlan:
     def _bprop(self, gem, x, dy, dx):
         """dgrad on the current stream (critical path), wgrad on the weight-gradient stream."""
         if self.wstream is None:
-            ops.conv_wgrad(gem[0], x, dy, gem[2])
+            ops.conv_wgrad(gem[0], x, dy, gem[2], self.wgrad_ws_main)
         else:
             self.wstream.wait_stream(torch.cuda.current_stream(self.eng.device))
             with torch.cuda.stream(self.wstream):
-                ops.conv_wgrad(gem[0], x, dy, gem[2])
+                ops.conv_wgrad(gem[0], x, dy, gem[2], self.wgrad_ws)
         if dx is not None:
             ops.conv_dgrad(gem[0], dy, gem[1], dx)
 

@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from ._lib import BN1dBwdDesc, BN1dDesc, ConvGeom, Context, HeadGrads, HeadParams, MMLError
+from ._lib import BN1dBwdDesc, BN1dDesc, BNFinal, ConvGeom, Context, HeadGrads, HeadParams, MMLError
 
 BF16 = torch.bfloat16
 
@@ -57,12 +57,12 @@ def mask_apply(x: torch.Tensor, mask: torch.Tensor, want_reverse: bool = False):
 
 
 # ---- stem ----------------------------------------------------------------------------------------------------
-def stem_fprop(x, mask, w, y, stats) -> None:
-    """stats: fp64 [64, 2] accumulator (zeroed by the caller) or None."""
+def stem_fprop(x, mask, w, y, stats, fin: "Optional[BNFinal]" = None) -> None:
+    """stats: fp64 [16, 64, 2] accumulator (zeroed by the caller) or None; fin: BatchNorm coefficients finalised by the kernel."""
     ctx = _ctx(x)
     B, H, W = x.shape
-    ctx.check(ctx.lib.mml_stem_fprop(ctx.handle, _p(x, torch.float32), _p(mask, torch.float32), _p(w, torch.float32), _p(y, BF16),
-                                     _p(stats, torch.float64), B, H, W, _stream(x)), "stem_fprop")
+    ctx.check(ctx.lib.mml_stem_fprop_bn(ctx.handle, _p(x, torch.float32), _p(mask, torch.float32), _p(w, torch.float32), _p(y, BF16),
+                                        _p(stats, torch.float64), C.byref(fin) if fin is not None else None, B, H, W, _stream(x)), "stem_fprop")
 
 
 def stem_wgrad_workspace(x) -> int:
@@ -79,11 +79,11 @@ def stem_wgrad(x, mask, dy, dw, workspace) -> None:
 
 
 # ---- conv ----------------------------------------------------------------------------------------------------
-def conv_fprop(g: ConvGeom, x, w_krsc, y, stats=None) -> None:
-    """stats: fp64 [K, 2] accumulator of (sum, sum of squares) of y (zeroed by the caller) or None."""
+def conv_fprop(g: ConvGeom, x, w_krsc, y, stats=None, fin: "Optional[BNFinal]" = None) -> None:
+    """stats: fp64 [16, K, 2] accumulator of (sum, sum of squares) of y (zeroed by the caller) or None; fin: see ``bn_final``."""
     ctx = _ctx(x)
-    ctx.check(ctx.lib.mml_conv_fprop(ctx.handle, C.byref(g), _p(x, BF16), _p(w_krsc, BF16), _p(y, BF16), _p(stats, torch.float64),
-                                     _stream(x)), "conv_fprop")
+    ctx.check(ctx.lib.mml_conv_fprop_bn(ctx.handle, C.byref(g), _p(x, BF16), _p(w_krsc, BF16), _p(y, BF16), _p(stats, torch.float64),
+                                        C.byref(fin) if fin is not None else None, _stream(x)), "conv_fprop")
 
 
 def conv_dgrad(g: ConvGeom, dy, w_krsc, dx) -> None:
@@ -91,29 +91,97 @@ def conv_dgrad(g: ConvGeom, dy, w_krsc, dx) -> None:
     ctx.check(ctx.lib.mml_conv_dgrad(ctx.handle, C.byref(g), _p(dy, BF16), _p(w_krsc, BF16), _p(dx, BF16), _stream(dy)), "conv_dgrad")
 
 
-def conv_wgrad(g: ConvGeom, x, dy, dw_krsc) -> None:
+def conv_wgrad_workspace(g: ConvGeom, device) -> int:
+    """Bytes of scratch mml_conv_wgrad needs for this geometry (per-CTA / per-split partial sums, reduced in a fixed order)."""
+    ctx = Context.get(torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device())
+    n = int(ctx.lib.mml_conv_wgrad_workspace(ctx.handle, C.byref(g)))
+    if n < 0:
+        raise MMLError("conv_wgrad: unsupported geometry")
+    return n
+
+
+class WgradScratch:
+    """Scratch for the split partial sums of ``conv_wgrad``: ONE per stream that issues weight-gradient launches (launches on a stream
+    are ordered, so they can share it; two streams must not).  Grows on demand -- during the eager warm-up steps, i.e. before a
+    CUDA-graph capture bakes the address in."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.buf: Optional[torch.Tensor] = None
+
+    def ensure(self, nbytes: int) -> Optional[torch.Tensor]:
+        if nbytes <= 0:
+            return self.buf
+        if self.buf is None or self.buf.numel() * 4 < nbytes:
+            if torch.cuda.is_current_stream_capturing():
+                raise MMLError("conv_wgrad scratch would have to grow inside a CUDA-graph capture (run an eager step first)")
+            self.buf = torch.empty((nbytes + 3) // 4, device=self.device)
+        return self.buf
+
+
+def conv_wgrad(g: ConvGeom, x, dy, dw_krsc, workspace=None) -> None:
+    """dw = sum dy * x (OVERWRITES dw; bit-reproducible).  workspace: a ``WgradScratch`` or an fp32 tensor of at least
+    ``conv_wgrad_workspace(g)`` bytes, private to the current stream (may be None when the geometry needs none)."""
     ctx = _ctx(x)
-    ctx.check(ctx.lib.mml_conv_wgrad(ctx.handle, C.byref(g), _p(x, BF16), _p(dy, BF16), _p(dw_krsc, torch.float32), _stream(x)), "conv_wgrad")
+    if isinstance(workspace, WgradScratch):
+        key = (g.N, g.H, g.W, g.C, g.K, g.R, g.S, g.stride, g.pad)
+        need = _WS_CACHE.get(key)
+        if need is None:
+            need = _WS_CACHE[key] = conv_wgrad_workspace(g, x.device)
+        workspace = workspace.ensure(need)
+    ctx.check(ctx.lib.mml_conv_wgrad(ctx.handle, C.byref(g), _p(x, BF16), _p(dy, BF16), _p(dw_krsc, torch.float32), _p(workspace, torch.float32),
+                                     workspace.numel() * 4 if workspace is not None else 0, _stream(x)), "conv_wgrad")
+
+
+_WS_CACHE: dict = {}
 
 
 # ---- batch norm / activations / pooling ---------------------------------------------------------------------------
 class BNBuffers:
-    """Device pointers of one training-mode BatchNorm: fp64 stats, affine parameters, running and saved statistics."""
+    """Device buffers of one training-mode BatchNorm: fp64 stats, affine parameters, running and saved statistics, the
+    coefficient form (scale, shift) of the forward and (coef = mean g, mean g*xhat) of the backward, and the ticket counter of
+    the last-CTA finalisation."""
 
-    __slots__ = ("stats", "gamma", "beta", "rmean", "rvar", "mean", "invstd")
+    __slots__ = ("stats", "gamma", "beta", "rmean", "rvar", "mean", "invstd", "scale", "shift", "coef", "counter", "_fin")
 
-    def __init__(self, stats, gamma, beta, rmean, rvar, mean, invstd):
+    def __init__(self, stats, gamma, beta, rmean, rvar, mean, invstd, scale=None, shift=None, coef=None, counter=None):
         self.stats, self.gamma, self.beta, self.rmean, self.rvar, self.mean, self.invstd = stats, gamma, beta, rmean, rvar, mean, invstd
+        dev, Cn = gamma.device, gamma.numel()
+        self.scale = scale if scale is not None else torch.zeros(Cn, device=dev)
+        self.shift = shift if shift is not None else torch.zeros(Cn, device=dev)
+        self.coef = coef if coef is not None else torch.zeros(2, Cn, device=dev)
+        self.counter = counter if counter is not None else torch.zeros(1, device=dev, dtype=torch.int32)
+        self._fin = None
+
+
+def bn_final(bn: "BNBuffers", rows: int, momentum: float = 0.1, eps: float = 1e-5, update_running: bool = True) -> BNFinal:
+    """mml_bn_final for ``bn`` over ``rows`` values per channel (cached on the buffers object: the pointers are static)."""
+    f = BNFinal()
+    f.counter = bn.counter.data_ptr()
+    f.gamma, f.beta = bn.gamma.data_ptr(), bn.beta.data_ptr()
+    if update_running and bn.rmean is not None:
+        f.running_mean, f.running_var = bn.rmean.data_ptr(), bn.rvar.data_ptr()
+    f.save_mean, f.save_invstd = bn.mean.data_ptr(), bn.invstd.data_ptr()
+    f.scale, f.shift = bn.scale.data_ptr(), bn.shift.data_ptr()
+    f.inv_count = 1.0 / rows
+    f.unbias = rows / (rows - 1.0) if rows > 1 else 1.0
+    f.momentum, f.eps = momentum, eps
+    return f
+
+
+def bn_finalize(bn: "BNBuffers", rows: int, Cn: int, momentum=0.1, eps=1e-5) -> None:
+    """Stand-alone statistics -> coefficients (the fused step lets the producing conv / stem kernel do it)."""
+    ctx = _ctx(bn.gamma)
+    fin = bn_final(bn, rows, momentum, eps)
+    ctx.check(ctx.lib.mml_bn_finalize(ctx.handle, _p(bn.stats, torch.float64), C.byref(fin), Cn, _stream(bn.gamma)), "bn_finalize")
 
 
 def bn_train_fwd(x, bn: "BNBuffers", res, rbn, y, rows, Cn, relu, momentum=0.1, eps=1e-5) -> None:
-    """y = relu?(bn(x) [+ res | + rbn(res)]) with batch statistics taken from bn.stats (fp64 sums from the conv epilogue)."""
-    ctx = _ctx(x)
-    z = C.c_void_p(0)
-    r = (_p(rbn.stats, torch.float64), _p(rbn.gamma), _p(rbn.beta), _p(rbn.rmean), _p(rbn.rvar), _p(rbn.mean), _p(rbn.invstd)) if rbn is not None else (z,) * 7
-    ctx.check(ctx.lib.mml_bn_train_fwd(ctx.handle, _p(x, BF16), _p(bn.stats, torch.float64), _p(bn.gamma), _p(bn.beta), _p(bn.rmean), _p(bn.rvar),
-                                       _p(bn.mean), _p(bn.invstd), _p(res), *r, _p(y, BF16), rows, Cn, int(relu), float(momentum), float(eps),
-                                       _stream(x)), "bn_train_fwd")
+    """y = relu?(bn(x) [+ res | + rbn(res)]) with batch statistics from bn.stats (fp64 sums of a conv epilogue): finalise, then apply."""
+    bn_finalize(bn, rows, Cn, momentum, eps)
+    if rbn is not None:
+        bn_finalize(rbn, rows, Cn, momentum, eps)
+    bn_act_fwd(x, bn.scale, bn.shift, res, rbn.scale if rbn is not None else None, rbn.shift if rbn is not None else None, y, rows, Cn, relu)
 
 
 def bn_eval_coeffs(Cn, gamma, beta, rmean, rvar, eps, scale, shift) -> None:
@@ -128,17 +196,19 @@ def bn_act_fwd(x, scale, shift, res, rscale, rshift, y, rows, Cn, relu) -> None:
                                      int(relu), _stream(x)), "bn_act_fwd")
 
 
-def bn_bwd_reduce(dy1, dy2, y, x, mean, invstd, bstat, rows, Cn, relu) -> None:
+def bn_bwd_reduce(dy1, dy2, y, x, bn: "BNBuffers", bstat, g_out, dgamma, dbeta, rows, Cn, relu) -> None:
+    """pass 1: g = (dy1 [+ dy2]) * (y > 0); bstat += (sum g, sum g*xhat); g_out (may alias dy1) = g; the last CTA writes bn.coef,
+    dgamma, dbeta."""
     ctx = _ctx(dy1)
-    ctx.check(ctx.lib.mml_bn_bwd_reduce(ctx.handle, _p(dy1, BF16), _p(dy2), _p(y), _p(x, BF16), _p(mean), _p(invstd), _p(bstat, torch.float64), rows,
-                                        Cn, int(relu), _stream(dy1)), "bn_bwd_reduce")
+    ctx.check(ctx.lib.mml_bn_bwd_reduce(ctx.handle, _p(dy1, BF16), _p(dy2), _p(y), _p(x, BF16), _p(bn.mean), _p(bn.invstd), _p(bstat, torch.float64),
+                                        _p(g_out), _p(bn.counter), _p(bn.coef), _p(dgamma), _p(dbeta), rows, Cn, int(relu), _stream(dy1)), "bn_bwd_reduce")
 
 
-def bn_bwd_apply(dy1, dy2, y, x, mean, invstd, gamma, bstat, dgamma, dbeta, dx, g_out, rows, Cn, relu) -> None:
-    ctx = _ctx(dy1)
-    ctx.check(ctx.lib.mml_bn_bwd_apply(ctx.handle, _p(dy1, BF16), _p(dy2), _p(y), _p(x, BF16), _p(mean), _p(invstd), _p(gamma),
-                                       _p(bstat, torch.float64), _p(dgamma), _p(dbeta), _p(dx, BF16), _p(g_out), rows, Cn, int(relu),
-                                       _stream(dy1)), "bn_bwd_apply")
+def bn_bwd_apply(g, x, bn: "BNBuffers", dx, rows, Cn) -> None:
+    """pass 2: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); dx may alias g."""
+    ctx = _ctx(g)
+    ctx.check(ctx.lib.mml_bn_bwd_apply(ctx.handle, _p(g, BF16), _p(x, BF16), _p(bn.mean), _p(bn.invstd), _p(bn.gamma), _p(bn.coef), _p(dx, BF16),
+                                       rows, Cn, _stream(g)), "bn_bwd_apply")
 
 
 def maxpool_fwd(x, y, argmax, N, H, W, Cn) -> None:
@@ -151,23 +221,18 @@ def maxpool_bwd(dy, dy2, argmax, dx, N, H, W, Cn) -> None:
     ctx.check(ctx.lib.mml_maxpool3x3s2_bwd(ctx.handle, _p(dy, BF16), _p(dy2), _p(argmax, torch.uint8), _p(dx, BF16), N, H, W, Cn, _stream(dy)), "maxpool_bwd")
 
 
-def stem_bn_pool_fwd(x, bn: "BNBuffers", scale, shift, y, argmax, N, H, W, Cn, train: bool, momentum=0.1, eps=1e-5) -> None:
-    """y = maxpool3x3s2(relu(bn(x))); train: batch statistics from bn.stats, eval: precomputed scale / shift."""
+def stem_bn_pool_fwd(x, scale, shift, y, argmax, N, H, W, Cn) -> None:
+    """y = maxpool3x3s2(relu(x*scale + shift)); scale / shift from the batch statistics (train) or the running ones (eval)."""
     ctx = _ctx(x)
-    z = C.c_void_p(0)
-    if train:
-        a = (_p(bn.stats, torch.float64), _p(bn.gamma), _p(bn.beta), _p(bn.rmean), _p(bn.rvar), _p(bn.mean), _p(bn.invstd), z, z)
-    else:
-        a = (z, _p(bn.gamma), _p(bn.beta), z, z, z, z, _p(scale), _p(shift))
-    ctx.check(ctx.lib.mml_stem_bn_pool_fwd(ctx.handle, _p(x, BF16), *a, _p(y, BF16), _p(argmax, torch.uint8), N, H, W, Cn, float(momentum), float(eps),
+    ctx.check(ctx.lib.mml_stem_bn_pool_fwd(ctx.handle, _p(x, BF16), _p(scale), _p(shift), _p(y, BF16), _p(argmax, torch.uint8), N, H, W, Cn,
                                            _stream(x)), "stem_bn_pool_fwd")
 
 
 def stem_bn_pool_bwd(dy, dy2, argmax, x, bn: "BNBuffers", bstat, dgamma, dbeta, dx, N, H, W, Cn) -> None:
     ctx = _ctx(dy)
     ctx.check(ctx.lib.mml_stem_bn_pool_bwd(ctx.handle, _p(dy, BF16), _p(dy2), _p(argmax, torch.uint8), _p(x, BF16), _p(bn.mean), _p(bn.invstd),
-                                           _p(bn.gamma), _p(bn.beta), _p(bstat, torch.float64), _p(dgamma), _p(dbeta), _p(dx, BF16), N, H, W, Cn,
-                                           _stream(dy)), "stem_bn_pool_bwd")
+                                           _p(bn.gamma), _p(bn.beta), _p(bstat, torch.float64), _p(bn.counter), _p(bn.coef), _p(dgamma), _p(dbeta),
+                                           _p(dx, BF16), N, H, W, Cn, _stream(dy)), "stem_bn_pool_bwd")
 
 
 def avgpool_fwd(x, y, N, HW, Cn) -> None:
@@ -242,12 +307,6 @@ def adam_step(p, g, m, v, p_bf16, hyper, step, advance_step: bool = True) -> Non
 def cast_f32_bf16(src, dst) -> None:
     ctx = _ctx(src)
     ctx.check(ctx.lib.mml_cast_f32_bf16(ctx.handle, _p(src, torch.float32), _p(dst, BF16), src.numel(), _stream(src)), "cast_f32_bf16")
-
-
-def weights_transpose(src, dst, table, n_convs, total_blocks) -> None:
-    ctx = _ctx(src)
-    ctx.check(ctx.lib.mml_weights_transpose(ctx.handle, _p(src, BF16), _p(dst, BF16), _p(table, torch.int64), n_convs, total_blocks, _stream(src)),
-              "weights_transpose")
 
 
 def fedavg(client_ptrs, weights, K, out) -> None:

@@ -119,6 +119,7 @@ class _UttPlan:
         C_ = m.netT.out_channels
         self.C = C_
         self.convs = []
+        self.wgrad_ws = ops.WgradScratch(dev)  # the three TextCNN weight gradients run on one stream
         for i, k in enumerate(m.netT.kernel_heights):
             name = f"netT.conv{i + 1}"
             P_ = T - k + 1
@@ -253,7 +254,7 @@ class _UttPlan:
             for i, cv in enumerate(self.convs):
                 ops.relumax_bwd(self.dpooled, self.arg, self.keepT if dropT else None, 1.0 / (1.0 - self.pT) if dropT else 1.0, cv["dout"], cv["dbias"],
                                 i * self.C)
-                ops.conv_wgrad(cv["geom"], self.xT16, cv["dout"], cv["dw"])
+                ops.conv_wgrad(cv["geom"], self.xT16, cv["dout"], cv["dw"], self.wgrad_ws)
 
         def lstm_bwd_chain(off, key):  # BPTT from d h_T = this encoder's columns of d fused
             L = self.lstm[key]

@@ -125,15 +125,26 @@ def test_bn_forward_backward(rows, C):
     gin = (dy1.float() + dy2.float()) * (y.float() > 0).float()
     (bnref * gin).sum().backward()  # d/dx of bn with upstream gradient gin (relu mask applied explicitly)
     bstat = torch.zeros(16, C, 2, device="cuda", dtype=torch.float64)
-    ops.bn_bwd_reduce(dy1, dy2, y, x, bn.mean, bn.invstd, bstat, rows, C, True)
     dgamma, dbeta = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
     dx, gout = torch.empty(rows, C, device="cuda", dtype=BF), torch.empty(rows, C, device="cuda", dtype=BF)
-    ops.bn_bwd_apply(dy1, dy2, y, x, bn.mean, bn.invstd, gamma, bstat, dgamma, dbeta, dx, gout, rows, C, True)
+    ops.bn_bwd_reduce(dy1, dy2, y, x, bn, bstat, gout, dgamma, dbeta, rows, C, True)  # pass 1 stores g; its last CTA finalises bn.coef
+    assert int(bn.counter.item()) == 0  # the ticket counter resets itself
+    ops.bn_bwd_apply(gout, x, bn, dx, rows, C)
     tol = 2e-2
     assert (dgamma - gr.grad).abs().max().item() <= tol * gr.grad.abs().max().item() + 1e-2
     assert (dbeta - br.grad).abs().max().item() <= tol * br.grad.abs().max().item() + 1e-2
     assert (dx.float() - xr.grad).abs().max().item() <= tol * xr.grad.abs().max().item() + 1e-3
     assert (gout.float() - gin).abs().max().item() <= 2.0 ** -7 * gin.abs().max().item() + 1e-3
+    # in-place form used for bn1 (one incoming gradient, g overwrites it), twice in a row: the counter must have reset
+    for _ in range(2):
+        d1 = dy1.clone()
+        bstat.zero_()
+        ops.bn_bwd_reduce(d1, None, y, x, bn, bstat, d1, dgamma, dbeta, rows, C, True)
+        ops.bn_bwd_apply(d1, x, bn, d1, rows, C)
+        xr.grad = None
+        bnref2 = F.batch_norm(xr.t().reshape(1, C, rows), None, None, gamma, beta, True, 0.1, 1e-5).reshape(C, rows).t()
+        (bnref2 * (dy1.float() * (y.float() > 0).float())).sum().backward()
+        assert (d1.float() - xr.grad).abs().max().item() <= tol * xr.grad.abs().max().item() + 1e-3
 
 
 @pytest.mark.parametrize("N,H,W,C", [(3, 56, 56, 64), (2, 14, 14, 64), (2, 16, 47, 64), (1, 5, 7, 64)])
@@ -175,7 +186,8 @@ def test_stem_bn_relu_maxpool_fused(N, H, W):
     P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty(N, P, Q, C, device="cuda", dtype=BF)
     am = torch.empty(N, P, Q, C, device="cuda", dtype=torch.uint8)
-    ops.stem_bn_pool_fwd(x, bn, None, None, y, am, N, H, W, C, True)
+    ops.bn_finalize(bn, N * H * W, C)  # in the fused step: the stem convolution's last CTA
+    ops.stem_bn_pool_fwd(x, bn.scale, bn.shift, y, am, N, H, W, C)
     xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
@@ -201,7 +213,7 @@ def test_stem_bn_relu_maxpool_fused(N, H, W):
     scale, shift = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
     ops.bn_eval_coeffs(C, gamma, beta, bn.rmean, bn.rvar, 1e-5, scale, shift)
     y2 = torch.empty_like(y)
-    ops.stem_bn_pool_fwd(x, bn, scale, shift, y2, am, N, H, W, C, False)
+    ops.stem_bn_pool_fwd(x, scale, shift, y2, am, N, H, W, C)
     ref2 = F.max_pool2d(F.relu(F.batch_norm(x.float().permute(0, 3, 1, 2), bn.rmean, bn.rvar, gamma, beta, False, 0.1, 1e-5)), 3, 2, 1)
     assert (y2.float() - ref2.permute(0, 2, 3, 1)).abs().max().item() <= 2.0 ** -7 * ref2.abs().max().item() + 1e-3
 
@@ -294,29 +306,14 @@ def test_adam_matches_torch():
     assert torch.equal(pb, p.to(BF))
 
 
-def test_cast_and_weight_transpose():
+def test_cast_f32_bf16():
     from mml_b200 import ops
 
-    convs = [(64, 9, 64), (128, 1, 64), (512, 9, 256)]
-    total = sum(k * rs * c for k, rs, c in convs)
-    src32 = torch.randn(total, device="cuda", generator=gen(30))
-    src = torch.empty(total, device="cuda", dtype=BF)
-    ops.cast_f32_bf16(src32, src)
-    assert torch.equal(src, src32.to(BF))
-    dst = torch.empty_like(src)
-    rows, off, blk = [], 0, 0
-    for k, rs, c in convs:
-        rows.append([off, off, k, rs, c, blk])
-        off += k * rs * c
-        blk += rs * (k // 32) * (c // 32)
-    table = torch.tensor(rows, device="cuda", dtype=torch.int64)
-    ops.weights_transpose(src, dst, table, len(convs), blk)
-    off = 0
-    for k, rs, c in convs:
-        a = src[off:off + k * rs * c].view(k, rs, c)
-        b = dst[off:off + k * rs * c].view(c, rs, k)
-        assert torch.equal(b, a.permute(2, 1, 0).contiguous())
-        off += k * rs * c
+    for total in (1 << 20, 12345, 7):
+        src32 = torch.randn(total, device="cuda", generator=gen(30))
+        src = torch.empty(total, device="cuda", dtype=BF)
+        ops.cast_f32_bf16(src32, src)
+        assert torch.equal(src, src32.to(BF))
 
 
 def test_fedavg():

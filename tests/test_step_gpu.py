@@ -8,7 +8,8 @@ Tolerances and why (DESIGN.md "Numerics"):
     reference's conditioning, not the kernels.
   * So gradients are checked "teacher forced": the oracle's backward runs over the activations the GPU stored
     (same ReLU masks, same BN statistics), which is a linear, well-conditioned comparison -> tight tolerance.
-  * Un-forced: loss within 1e-2, logits within 10 % of the logit range, and a matched loss curve over 100 steps.
+  * Un-forced: loss within 1e-2, logits within ~2x the MEASURED error (LOGIT_TOL below: the fp32 oracle, and the oracle that rounds
+    to bf16 where the kernels do -- which is itself that far from its fp32 self), and a matched loss curve over 100 steps.
 """
 import copy
 import os
@@ -361,7 +362,7 @@ def test_reference_golden_fixture_on_gpu(name):
             err = float(np.abs(plan.logits.cpu().numpy() - g["logits"]).max())
             print(f"{name}: step-0 loss {out['loss']:.5f} vs reference {float(g['loss']):.5f}; logit error {err:.4f} = {err / rng:.4f} of the logit range")
             assert abs(out["loss"] - float(g["loss"])) < 1e-2
-            assert err < LOGIT_TOL * rng
+            assert err < LOGIT_TOL_SMALL_BATCH * rng
             # gradient norms per tensor: un-forced gradients are ill-conditioned (module docstring), the NORMS of the big tensors are not
             keys = list(g["grad_keys"])
             got = {n: float(p.grad.detach().double().norm()) for n, p in model.named_parameters()}
@@ -377,10 +378,16 @@ def test_reference_golden_fixture_on_gpu(name):
     assert np.abs(ev - g["eval_logits"]).max() < 0.10 * rng + 5e-2
 
 
-# measured on B200 (printed by the test below): |GPU - fp32 oracle| is 2-4 % of the logit range at random initialisation, of which
-# the oracle ITSELF moves by about the same amount when it rounds where the kernels round (emulate_bf16); the bound is ~2x measured
-LOGIT_TOL = 0.08
-LOGIT_TOL_EMULATED = 0.06
+# Measured on B200 (printed by the tests; profiles/r2_parity_measured.txt): at random initialisation the logits span only ~0.6, and
+#   |GPU - fp32 oracle|                      = 0.063 (B = 32), 0.059 (B = 256) of that range  (absolute: ~0.04)
+#   |GPU - bf16-rounding oracle|             = 0.069, 0.066
+#   |bf16-rounding oracle - fp32 oracle|     = 0.064, 0.058   <- the oracle ITSELF moves this much when it rounds where the kernels round
+# i.e. the GPU sits as far from either oracle as the two oracles sit from each other: the error is bf16 storage through 34 BN/ReLU
+# layers, not a kernel defect (teacher-forced, where rounding cannot flip ReLU masks, logits agree to 1e-4).  The 4- and 6-sample
+# reference fixtures are noisier (BatchNorm over 4 samples): 0.093 and 0.071.  Bounds = ~2x the measured values.
+LOGIT_TOL = 0.12
+LOGIT_TOL_EMULATED = 0.13
+LOGIT_TOL_SMALL_BATCH = 0.18
 
 
 @pytest.mark.parametrize("B,hw", [(32, (112, 112)), (256, (112, 112))])

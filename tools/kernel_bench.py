@@ -55,7 +55,8 @@ def conv(N, H, W, C, K, R, st, pad, tag=""):
     fl = 2.0 * N * P * Q * K * C * R * R
     tf = timeit(lambda: ops.conv_fprop(g, x, w, y, stt))
     td = timeit(lambda: ops.conv_dgrad(g, dy, w, dx))
-    tw = timeit(lambda: ops.conv_wgrad(g, x, dy, dw))
+    ws = ops.WgradScratch("cuda")
+    tw = timeit(lambda: ops.conv_wgrad(g, x, dy, dw, ws))
     print(f"conv {tag:10s} N={N} {H}x{W} C={C} K={K} R={R} s={st}: fprop {tf:6.1f} us ({fl / tf / 1e6:6.0f} TF)  dgrad {td:6.1f} us ({fl / td / 1e6:6.0f} TF)  wgrad {tw:6.1f} us ({fl / tw / 1e6:6.0f} TF)")
 
 

@@ -23,7 +23,7 @@ def conv_case(N, H, W, C, K, R, st, pad):
     dx = torch.empty(N, H, W, C, device="cuda", dtype=BF)
     dw = torch.zeros(K, R, R, C, device="cuda")
     stt = torch.zeros(16, K, 2, device="cuda", dtype=torch.float64)
-    return dict(fprop=lambda: ops.conv_fprop(g, x, w, y, stt), dgrad=lambda: ops.conv_dgrad(g, dy, w, dx), wgrad=lambda: ops.conv_wgrad(g, x, dy, dw))
+    return dict(fprop=lambda: ops.conv_fprop(g, x, w, y, stt), dgrad=lambda: ops.conv_dgrad(g, dy, w, dx), wgrad=lambda ws=ops.WgradScratch("cuda"): ops.conv_wgrad(g, x, dy, dw, ws))
 
 
 def bn_case(rows, Cn):
@@ -39,9 +39,10 @@ def bn_case(rows, Cn):
     f = lambda *sh: torch.zeros(*sh, device="cuda")
     bn = ops.BNBuffers(stats, torch.ones(Cn, device="cuda"), f(Cn), f(Cn), torch.ones(Cn, device="cuda"), f(Cn), torch.ones(Cn, device="cuda"))
     dg, db = f(Cn), f(Cn)
-    return dict(fwd=lambda: ops.bn_train_fwd(x, bn, res, None, y, rows, Cn, True),
-                reduce=lambda: ops.bn_bwd_reduce(dy, dy2, y, x, bn.mean, bn.invstd, bstat, rows, Cn, True),
-                apply=lambda: ops.bn_bwd_apply(dy, dy2, y, x, bn.mean, bn.invstd, bn.gamma, bstat, dg, db, dx, gs, rows, Cn, True))
+    ops.bn_finalize(bn, rows, Cn)
+    return dict(fwd=lambda: ops.bn_act_fwd(x, bn.scale, bn.shift, res, None, None, y, rows, Cn, True),
+                reduce=lambda: ops.bn_bwd_reduce(dy, dy2, y, x, bn, bstat, gs, dg, db, rows, Cn, True),
+                apply=lambda: ops.bn_bwd_apply(gs, x, bn, dx, rows, Cn))
 
 
 def stem_case(H, W):
