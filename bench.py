@@ -566,7 +566,7 @@ def dominant_kernel_roofline(torch, ops, B, pk):
     x = torch.randn(N, H, W, C, device="cuda").to(torch.bfloat16)
     w = (torch.randn(K, 3, 3, C, device="cuda") * 0.05).to(torch.bfloat16)
     y = torch.empty(N, H, W, K, device="cuda", dtype=torch.bfloat16)
-    part = torch.zeros(16, K, 2, device="cuda", dtype=torch.float64)
+    part = torch.zeros(K, 2, device="cuda", dtype=torch.float64)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > L2
     for _ in range(3):
         ops.conv_fprop(g, x, w, y, part)
@@ -619,26 +619,25 @@ def hbm_kernel_rooflines(torch, ops, B, pk):
         x = torch.randn(rows, Cn, device="cuda").to(torch.bfloat16)
         res = torch.randn(rows, Cn, device="cuda").to(torch.bfloat16)
         y = torch.empty_like(x)
-        stats = torch.zeros(16, Cn, 2, device="cuda", dtype=torch.float64)
+        stats = torch.zeros(Cn, 2, device="cuda", dtype=torch.float64)
         xf = x.float()
-        stats[0, :, 0] = xf.sum(0).double()
-        stats[0, :, 1] = (xf * xf).sum(0).double()
+        stats[:, 0] = xf.sum(0).double()
+        stats[:, 1] = (xf * xf).sum(0).double()
         f = lambda *sh: torch.zeros(*sh, device="cuda")
         bn = ops.BNBuffers(stats, torch.ones(Cn, device="cuda"), f(Cn), f(Cn), torch.ones(Cn, device="cuda"), f(Cn), torch.ones(Cn, device="cuda"))
-        ops.bn_finalize(bn, rows, Cn)  # in the step: the producing convolution's last CTA
-        t = timeit(lambda: ops.bn_act_fwd(x, bn.scale, bn.shift, res, None, None, y, rows, Cn, True))
+        t = timeit(lambda: ops.bn_train_fwd(x, bn, res, None, y, rows, Cn, True))
         bytes_bn = 3.0 * rows * Cn * 2  # read raw + residual, write output (bf16)
         out["bn_relu_residual_fwd"] = {"bound": "hbm", "achieved": bytes_bn / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                        "frac": bytes_bn / t / 1e9 / pk["hbm_gbs"], "us_per_launch": t * 1e6, "algorithmic_bytes_per_launch": bytes_bn}
         # BatchNorm backward of the same layer (two incoming gradients + ReLU mask): pass 1 reads dy1, dy2, y, x and stores g,
         # pass 2 reads g, x and stores dx -> 8 tensor passes of algorithmic traffic (round 1: 10)
         dy1, dy2, gbuf, dxb = (torch.randn(rows, Cn, device="cuda").to(torch.bfloat16) for _ in range(4))
-        bstat = torch.zeros(16, Cn, 2, device="cuda", dtype=torch.float64)
+        bstat = torch.zeros(Cn, 2, device="cuda", dtype=torch.float64)
         dg, db = f(Cn), f(Cn)
 
         def bn_bwd():
-            ops.bn_bwd_reduce(dy1, dy2, y, x, bn, bstat, gbuf, dg, db, rows, Cn, True)
-            ops.bn_bwd_apply(gbuf, x, bn, dxb, rows, Cn)
+            ops.bn_bwd_reduce(dy1, dy2, y, x, bn.mean, bn.invstd, bstat, gbuf, rows, Cn, True)
+            ops.bn_bwd_apply(gbuf, x, bn.mean, bn.invstd, bn.gamma, bstat, dg, db, dxb, rows, Cn)
 
         t = timeit(bn_bwd)
         bytes_bwd = 8.0 * rows * Cn * 2

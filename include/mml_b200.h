@@ -24,10 +24,9 @@ extern "C" {
 
 typedef struct mml_ctx mml_ctx;
 
-/* BatchNorm statistics accumulators are fp64 arrays [MML_BN_STAT_SLOTS][C][2]: producers (conv / stem epilogues, the BN
- * backward reduce) add their partial sums into one of 16 slots to spread atomic contention, consumers sum the slots.
- * The caller zeroes them once per step. */
-#define MML_BN_STAT_SLOTS 16
+/* BatchNorm statistics accumulators are fp64 arrays [C][2] (sum, sum of squares), one per BatchNorm: producers (conv / stem
+ * epilogues, the BN backward reduce) add their partial sums with fp64 atomics, every consumer derives its coefficients from
+ * them.  The caller zeroes them once per step. */
 
 enum mml_status {
   MML_OK = 0,
@@ -35,20 +34,6 @@ enum mml_status {
   MML_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed */
   MML_ERR_UNSUPPORTED = -3, /* not an sm_100 device, missing driver entry point, ... */
 };
-
-/* BatchNorm coefficients finalised by the PRODUCER of the statistics: the last CTA of the convolution / stem kernel (ticket
- * counter) turns the fp64 sums into scale / shift (y = x*scale + shift == gamma*(x-mean)/sqrt(var+eps)+beta, biased variance),
- * saves mean / invstd for backward and applies nn.BatchNorm2d's running-statistics update (resnet.py:26,31,138,177), so that no
- * consumer has to re-derive them.  counter: device uint32, zero before the first use, left at zero by the kernel. */
-typedef struct mml_bn_final {
-  uint32_t* counter;
-  const float* gamma; const float* beta;     /* [C] */
-  float* running_mean; float* running_var;   /* [C], both or neither */
-  float* save_mean; float* save_invstd;      /* [C] */
-  float* scale; float* shift;                /* [C] */
-  double inv_count, unbias;                  /* 1 / rows, rows / (rows - 1) */
-  float momentum, eps;
-} mml_bn_final;
 
 /* conv geometry: x [N,H,W,C] -> y [N,P,Q,K], filter K x R x S x C, P = (H + 2*pad - R)/stride + 1 (nn.Conv2d, bias=False) */
 typedef struct mml_conv_geom {
@@ -79,24 +64,18 @@ int mml_mask_apply_f32(mml_ctx*, const float* x, const float* mask, float* y, fl
 
 /* ---- a2/a3: ResNetEncoder stem -- models/msa/networks/resnet.py:137 conv1 (7x7, stride 2, pad 3, C_in = 1) ----- */
 /* x fp32 [B,H,W] (optionally multiplied by mask[b], same multiply as above), w fp32 [64][7][7] ->
- * y bf16 [B,P,Q,64]; stats (optional) fp64 [16][64][2] += (sum, sum of squares) of the stored y */
+ * y bf16 [B,P,Q,64]; stats (optional) fp64 [64][2] += (sum, sum of squares) of the stored y */
 int mml_stem_fprop(mml_ctx*, const float* x, const float* mask, const float* w, uint16_t* y, double* stats, int B, int H,
                    int W, void* stream);
-/* the same with the BatchNorm coefficients of y finalised by the kernel's last CTA (fin may be NULL) */
-int mml_stem_fprop_bn(mml_ctx*, const float* x, const float* mask, const float* w, uint16_t* y, double* stats, const mml_bn_final* fin,
-                      int B, int H, int W, void* stream);
 /* dw fp32 [64][49] = sum_{b,p,q} dy[b,p,q,k] * (x*mask)[b, 2p+r-3, 2q+s-3]  (overwrites dw) */
 int mml_stem_wgrad(mml_ctx*, const float* x, const float* mask, const uint16_t* dy, float* dw, float* workspace,
                    int64_t workspace_bytes, int B, int H, int W, void* stream);
 int64_t mml_stem_wgrad_workspace(const mml_ctx*, int B, int H, int W);
 
 /* ---- a2-a4: 3x3 / 1x1 convolutions -- resnet.py:25,30,176 (nn.Conv2d fwd) and their autograd -------------------- */
-/* tcgen05 implicit GEMM.  fprop: y = conv(x, w); stats (optional) fp64 [16][K][2] += per-channel (sum, sum of squares) of y */
+/* tcgen05 implicit GEMM.  fprop: y = conv(x, w); stats (optional) fp64 [K][2] += per-channel (sum, sum of squares) of y */
 int mml_conv_fprop(mml_ctx*, const mml_conv_geom* g, const uint16_t* x, const uint16_t* w_krsc, uint16_t* y, double* stats,
                    void* stream);
-/* the same with the BatchNorm coefficients of y (C = g->K channels) finalised by the kernel's last CTA (fin may be NULL) */
-int mml_conv_fprop_bn(mml_ctx*, const mml_conv_geom* g, const uint16_t* x, const uint16_t* w_krsc, uint16_t* y, double* stats,
-                      const mml_bn_final* fin, void* stream);
 /* dgrad: dx [N,H,W,C] = conv_transpose(dy [N,P,Q,K], w); reads the SAME K,R,S,C weights as fprop (MN-major B operand) */
 int mml_conv_dgrad(mml_ctx*, const mml_conv_geom* g, const uint16_t* dy, const uint16_t* w_krsc, uint16_t* dx, void* stream);
 /* wgrad: dw_krsc fp32 [K][R][S][C] = sum_{n,p,q} dy * x   (OVERWRITES dw; deterministic: split partial sums go to `workspace`
@@ -108,42 +87,45 @@ int mml_conv_wgrad(mml_ctx*, const mml_conv_geom* g, const uint16_t* x, const ui
 int64_t mml_conv_wgrad_workspace(const mml_ctx*, const mml_conv_geom* g); /* bytes; < 0: unsupported geometry */
 
 /* ---- a5: BatchNorm2d (train / eval) + ReLU + residual -- resnet.py:26,31,138,177 and BasicBlock.forward :37-54 --- */
-/* training mode: the fp64 sums (stats [16][C][2], accumulated by the conv / stem epilogue) -> coefficients.  In the fused step
- * the producing kernel does this itself (mml_conv_fprop_bn / mml_stem_fprop_bn); this stand-alone launch is the same code for
- * statistics that come from elsewhere (fin->counter is not used). */
-int mml_bn_finalize(mml_ctx*, const double* stats, const mml_bn_final* fin, int C, void* stream);
+/* training mode, fused: y = relu?(bn(x) [+ res | + bn_r(res)]) with scale/shift derived in-kernel from the fp64 sums the conv
+ * epilogue accumulated (stats [C][2]: 16 bytes per channel per CTA, no finalize launch); block 0 also saves mean / invstd for
+ * backward and updates the running statistics (running = (1-m)*running + m*batch, unbiased var).  res NULL: none; rstats NULL:
+ * identity residual; else the residual goes through its own training-mode BN (downsample path).  count == rows. */
+int mml_bn_train_fwd(mml_ctx*, const uint16_t* x, const double* stats, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float* save_mean, float* save_invstd, const uint16_t* res, const double* rstats,
+                     const float* rgamma, const float* rbeta, float* r_running_mean, float* r_running_var, float* r_save_mean,
+                     float* r_save_invstd, uint16_t* y, int64_t rows, int C, int relu, float momentum, float eps, void* stream);
 /* eval mode: scale/shift from running statistics */
 int mml_bn_eval_coeffs(mml_ctx*, int C, const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, float* scale, float* shift, void* stream);
-/* y = act(x*scale + shift [+ res*rscale + rshift]); res may be NULL; rscale NULL => identity residual.  Training and eval
- * mode differ only in where scale / shift come from. */
+/* y = act(x*scale + shift [+ res*rscale + rshift]); res may be NULL; rscale NULL => identity residual */
 int mml_bn_act_fwd(mml_ctx*, const uint16_t* x, const float* scale, const float* shift, const uint16_t* res,
                    const float* rscale, const float* rshift, uint16_t* y, int64_t rows, int C, int relu, void* stream);
 /* backward of y = relu?(bn(x) [+ r]):  g = (dy1 [+ dy2]) * (y > 0 if relu);
- * pass 1: bstat fp64 [16][C][2] += (sum g, sum g*xhat) (caller zeroes it per step); g_out (optional, may alias dy1) = g as bf16
- * -- it is the gradient of an identity skip path and the input of pass 2; the last CTA (counter: device uint32, zero before
- * the first use) writes coef [2][C] = mean(g), mean(g*xhat) and dgamma = sum g*xhat, dbeta = sum g (optional). */
+ * pass 1: bstat fp64 [C][2] += (sum g, sum g*xhat) (caller zeroes it per step); g_out (optional, may alias dy1) = g as bf16 -- it
+ * is the gradient of an identity skip path and the input of pass 2 (which then reads 2 tensors instead of 4) */
 int mml_bn_bwd_reduce(mml_ctx*, const uint16_t* dy1, const uint16_t* dy2, const uint16_t* y, const uint16_t* x,
-                      const float* mean, const float* invstd, double* bstat, uint16_t* g_out, uint32_t* counter, float* coef,
-                      float* dgamma, float* dbeta, int64_t rows, int C, int relu, void* stream);
-/* pass 2: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) as bf16 (dx may alias g) */
+                      const float* mean, const float* invstd, double* bstat, uint16_t* g_out, int64_t rows, int C, int relu, void* stream);
+/* pass 2: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) as bf16 (dx may alias g); coefficients straight from bstat;
+ * dgamma = sum g*xhat, dbeta = sum g (written, may be NULL) */
 int mml_bn_bwd_apply(mml_ctx*, const uint16_t* g, const uint16_t* x, const float* mean, const float* invstd, const float* gamma,
-                     const float* coef, uint16_t* dx, int64_t rows, int C, void* stream);
+                     const double* bstat, float* dgamma, float* dbeta, uint16_t* dx, int64_t rows, int C, void* stream);
 
 /* ---- pooling -- resnet.py:140 MaxPool2d(3,2,1), :149 AdaptiveAvgPool2d((1,1)) ---------------------------------- */
 int mml_maxpool3x3s2_fwd(mml_ctx*, const uint16_t* x, uint16_t* y, uint8_t* argmax, int N, int H, int W, int C, void* stream);
 /* dx = scatter of (dy [+ dy2]) to the argmax positions; dy2 may be NULL */
 int mml_maxpool3x3s2_bwd(mml_ctx*, const uint16_t* dy, const uint16_t* dy2, const uint8_t* argmax, uint16_t* dx, int N, int H,
                          int W, int C, void* stream);
-/* stem tail, fused: y = maxpool3x3s2(relu(x*scale + shift)) without materialising the activation (resnet.py:138-140, :206-208);
- * scale / shift: batch statistics finalised by mml_stem_fprop_bn (train) or mml_bn_eval_coeffs (eval) */
-int mml_stem_bn_pool_fwd(mml_ctx*, const uint16_t* x, const float* scale, const float* shift, uint16_t* y, uint8_t* argmax, int N, int H,
-                         int W, int C, void* stream);
+/* stem tail, fused: y = maxpool3x3s2(relu(bn(x))) without materialising the activation (resnet.py:138-140, :206-208).
+ * train: stats != NULL (fp64 sums from mml_stem_fprop; saves mean/invstd, updates running stats); eval: scale/shift != NULL */
+int mml_stem_bn_pool_fwd(mml_ctx*, const uint16_t* x, const double* stats, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, float* save_mean, float* save_invstd, const float* scale, const float* shift, uint16_t* y,
+                         uint8_t* argmax, int N, int H, int W, int C, float momentum, float eps, void* stream);
 /* its backward: dx (grad of the raw stem output) from the pooled gradient(s); ReLU mask recomputed from x; two passes
- * (scatter + statistics with last-CTA finalisation into coef [2][C] / dgamma / dbeta, then the in-place apply) */
+ * (scatter + statistics, then the in-place apply) */
 int mml_stem_bn_pool_bwd(mml_ctx*, const uint16_t* dy, const uint16_t* dy2, const uint8_t* argmax, const uint16_t* x, const float* mean,
-                         const float* invstd, const float* gamma, const float* beta, double* bstat, uint32_t* counter, float* coef,
-                         float* dgamma, float* dbeta, uint16_t* dx, int N, int H, int W, int C, void* stream);
+                         const float* invstd, const float* gamma, const float* beta, double* bstat, float* dgamma, float* dbeta, uint16_t* dx,
+                         int N, int H, int W, int C, void* stream);
 int mml_avgpool_fwd(mml_ctx*, const uint16_t* x, float* y, int N, int HW, int C, void* stream);
 int mml_avgpool_bwd(mml_ctx*, const float* dy, uint16_t* dx, int N, int HW, int C, void* stream);
 

@@ -21,12 +21,6 @@ class ConvGeom(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("N", "H", "W", "C", "K", "R", "S", "stride", "pad")]
 
 
-class BNFinal(C.Structure):
-    """mml_bn_final: BatchNorm coefficients finalised by the last CTA of the kernel that produced the statistics."""
-    _fields_ = [(n, C.c_void_p) for n in ("counter", "gamma", "beta", "running_mean", "running_var", "save_mean", "save_invstd", "scale", "shift")] + [
-        ("inv_count", C.c_double), ("unbias", C.c_double), ("momentum", C.c_float), ("eps", C.c_float)]
-
-
 class HeadParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("fcA_w", "fcA_b", "fcI_w", "fcI_b", "w0", "b0", "w3", "b3", "w5", "b5")] + [
         (n, C.c_int32) for n in ("FA", "FI", "EA", "EI", "H1", "H2", "NC")
@@ -69,23 +63,21 @@ SIGNATURES = {
     "mml_debug_set": (I32, [I32, I32]),
     "mml_mask_apply_f32": (I32, [P, P, P, P, P, I64, I64, P]),
     "mml_stem_fprop": (I32, [P, P, P, P, P, P, I32, I32, I32, P]),
-    "mml_stem_fprop_bn": (I32, [P, P, P, P, P, P, C.POINTER(BNFinal), I32, I32, I32, P]),
     "mml_stem_wgrad": (I32, [P, P, P, P, P, P, I64, I32, I32, I32, P]),
     "mml_stem_wgrad_workspace": (I64, [P, I32, I32, I32]),
     "mml_conv_fprop": (I32, [P, C.POINTER(ConvGeom), P, P, P, P, P]),
-    "mml_conv_fprop_bn": (I32, [P, C.POINTER(ConvGeom), P, P, P, P, C.POINTER(BNFinal), P]),
     "mml_conv_dgrad": (I32, [P, C.POINTER(ConvGeom), P, P, P, P]),
     "mml_conv_wgrad": (I32, [P, C.POINTER(ConvGeom), P, P, P, P, I64, P]),
     "mml_conv_wgrad_workspace": (I64, [P, C.POINTER(ConvGeom)]),
-    "mml_bn_finalize": (I32, [P, P, C.POINTER(BNFinal), I32, P]),
+    "mml_bn_train_fwd": (I32, [P] + [P] * 17 + [I64, I32, I32, F32, F32, P]),
     "mml_bn_eval_coeffs": (I32, [P, I32, P, P, P, P, F32, P, P, P]),
     "mml_bn_act_fwd": (I32, [P, P, P, P, P, P, P, P, I64, I32, I32, P]),
-    "mml_bn_bwd_reduce": (I32, [P] * 13 + [I64, I32, I32, P]),
-    "mml_bn_bwd_apply": (I32, [P] * 8 + [I64, I32, P]),
+    "mml_bn_bwd_reduce": (I32, [P] * 9 + [I64, I32, I32, P]),
+    "mml_bn_bwd_apply": (I32, [P] * 10 + [I64, I32, P]),
     "mml_maxpool3x3s2_fwd": (I32, [P, P, P, P, I32, I32, I32, I32, P]),
     "mml_maxpool3x3s2_bwd": (I32, [P, P, P, P, P, I32, I32, I32, I32, P]),
-    "mml_stem_bn_pool_fwd": (I32, [P] * 6 + [I32, I32, I32, I32, P]),
-    "mml_stem_bn_pool_bwd": (I32, [P] * 15 + [I32, I32, I32, I32, P]),
+    "mml_stem_bn_pool_fwd": (I32, [P] * 13 + [I32, I32, I32, I32, F32, F32, P]),
+    "mml_stem_bn_pool_bwd": (I32, [P] * 13 + [I32, I32, I32, I32, P]),
     "mml_avgpool_fwd": (I32, [P, P, P, I32, I32, I32, P]),
     "mml_avgpool_bwd": (I32, [P, P, P, I32, I32, I32, P]),
     "mml_head_scratch_per_sample": (I32, [C.POINTER(HeadParams)]),

@@ -60,12 +60,45 @@ __global__ void mask_apply_kernel(const float* __restrict__ x, const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// BatchNorm statistics -> coefficients.  In the fused step the LAST CTA of the kernel that produced the statistics (conv / stem
-// epilogue, bn_bwd_reduce) does this (mml_common.cuh::bn_final_forward); the stand-alone kernel below is the same code for
-// callers whose statistics come from elsewhere.
+// BatchNorm forward.  Training mode: every CTA derives scale / shift for all C channels from the fp64 sums of the conv epilogue
+// (16 bytes per channel, no finalize launch); block 0 also saves mean / invstd for backward and updates the running statistics:
+// running = (1-m)*running + m*batch, unbiased variance (torch.nn.BatchNorm2d, momentum 0.1).  Eval mode: coefficients given.
+//   y = relu?(x*scale + shift [+ res | + res*rscale + rshift])
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) bn_finalize_kernel(const double* __restrict__ stats, BnFinal f, int C) {
-  bn_final_forward(f, stats, C, blockIdx.x * kThreads + threadIdx.x, gridDim.x * kThreads);
+struct BnTrain {
+  const double* stats;   // [C][2]
+  const float* gamma;
+  const float* beta;
+  float* running_mean;   // may be null
+  float* running_var;
+  float* save_mean;
+  float* save_invstd;
+};
+
+constexpr int kMaxC = 512;
+
+__device__ __forceinline__ void bn_prologue(const BnTrain& b, int C, double inv_count, double unbias, float momentum, float eps, float* s_scale,
+                                            float* s_shift) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double sum, sq;
+    stat_load(b.stats, c, sum, sq);
+    const double mean = sum * inv_count;
+    double var = sq * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = b.gamma[c] * invstd;
+    const float mu = (float)mean;
+    s_scale[c] = sc;
+    s_shift[c] = b.beta[c] - mu * sc;
+    if (blockIdx.x == 0) {
+      b.save_mean[c] = mu;
+      b.save_invstd[c] = invstd;
+      if (b.running_mean) {
+        b.running_mean[c] = (1.f - momentum) * b.running_mean[c] + momentum * mu;
+        b.running_var[c] = (1.f - momentum) * b.running_var[c] + momentum * (float)(var * unbias);
+      }
+    }
+  }
 }
 
 __global__ void bn_eval_coeffs_kernel(int C, const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
@@ -80,32 +113,38 @@ __global__ void bn_eval_coeffs_kernel(int C, const float* gamma, const float* be
 
 constexpr int kU = 4;  // independent 16-byte loads in flight per tensor and thread (HBM latency x bandwidth / resident threads)
 
-// ---------------------------------------------------------------------------------------------------------------
-// y = relu?(x*scale + shift [+ res | + res*rscale + rshift])   (training: coefficients from the batch statistics, finalised by
-// the producer; eval: from the running statistics)
-// ---------------------------------------------------------------------------------------------------------------
-template <bool HAS_RES, bool RES_AFFINE, bool RELU>
+// RES: 0 = none, 1 = identity residual, 2 = residual with its own affine (training: its own batch statistics -- downsample path)
+// TRAIN: coefficients from the statistics (bn / rbn); else from the scale / shift arrays
+template <int RES, bool RELU, bool TRAIN>
 __global__ void __launch_bounds__(kThreads)
-bn_act_fwd_kernel(const uint16_t* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-                  const uint16_t* __restrict__ res, const float* __restrict__ rscale, const float* __restrict__ rshift,
-                  uint16_t* __restrict__ y, long long n8, int c8) {
+bn_fwd_kernel(const uint16_t* __restrict__ x, BnTrain bn, const float* __restrict__ scale, const float* __restrict__ shift,
+              const uint16_t* __restrict__ res, BnTrain rbn, const float* __restrict__ rscale, const float* __restrict__ rshift,
+              uint16_t* __restrict__ y, long long n8, int c8, double inv_count, double unbias, float momentum, float eps) {
+  __shared__ __align__(16) float s_coef[TRAIN ? (RES == 2 ? 4 : 2) * kMaxC : 4];
   const long long stride = (long long)gridDim.x * kThreads;
   long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
   const int cg = (int)(i % c8);
-  const F8 sc = load8f(scale + cg * 8), sh = load8f(shift + cg * 8);
-  F8 rsc, rsh;
-  if (HAS_RES && RES_AFFINE) {
-    rsc = load8f(rscale + cg * 8);
-    rsh = load8f(rshift + cg * 8);
+  F8 sc, sh, rsc, rsh;
+  if (TRAIN) {
+    const int C = c8 * 8;
+    bn_prologue(bn, C, inv_count, unbias, momentum, eps, s_coef, s_coef + kMaxC);
+    if (RES == 2) bn_prologue(rbn, C, inv_count, unbias, momentum, eps, s_coef + 2 * kMaxC, s_coef + 3 * kMaxC);
+    __syncthreads();
+    sc = load8f(s_coef + cg * 8), sh = load8f(s_coef + kMaxC + cg * 8);
+    if (RES == 2) rsc = load8f(s_coef + 2 * kMaxC + cg * 8), rsh = load8f(s_coef + 3 * kMaxC + cg * 8);
+  } else {
+    sc = load8f(scale + cg * 8), sh = load8f(shift + cg * 8);
+    if (RES == 2) rsc = load8f(rscale + cg * 8), rsh = load8f(rshift + cg * 8);
   }
   auto one = [&](const uint4& xu, const uint4& ru) {
     F8 v = unpack8(xu);
     F8 r;
-    if (HAS_RES) r = unpack8(ru);
+    if (RES != 0) r = unpack8(ru);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float o = fmaf(v.v[j], sc.v[j], sh.v[j]);
-      if (HAS_RES) o += RES_AFFINE ? fmaf(r.v[j], rsc.v[j], rsh.v[j]) : r.v[j];
+      if (RES == 1) o += r.v[j];
+      if (RES == 2) o += fmaf(r.v[j], rsc.v[j], rsh.v[j]);
       v.v[j] = RELU ? fmaxf(o, 0.f) : o;
     }
     return pack8(v);
@@ -115,7 +154,7 @@ bn_act_fwd_kernel(const uint16_t* __restrict__ x, const float* __restrict__ scal
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       xu[u] = ldg16(x + (i + u * stride) * 8);
-      if (HAS_RES) ru[u] = ldg16(res + (i + u * stride) * 8);
+      if (RES != 0) ru[u] = ldg16(res + (i + u * stride) * 8);
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) *reinterpret_cast<uint4*>(y + (i + u * stride) * 8) = one(xu[u], ru[u]);
@@ -123,38 +162,17 @@ bn_act_fwd_kernel(const uint16_t* __restrict__ x, const float* __restrict__ scal
   for (; i < n8; i += stride) {
     const uint4 xu = ldg16(x + i * 8);
     uint4 ru = make_uint4(0, 0, 0, 0);
-    if (HAS_RES) ru = ldg16(res + i * 8);
+    if (RES != 0) ru = ldg16(res + i * 8);
     *reinterpret_cast<uint4*>(y + i * 8) = one(xu, ru);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // backward pass 1: g = (dy1 [+ dy2]) * (y > 0), optionally stored (it IS the gradient of the identity skip path, and pass 2
-// then reads g instead of dy1 / dy2 / y);  per-block partials of  sum g  and  sum g*xhat  -> fp64 slots;  the last CTA turns
-// them into mean(g), mean(g*xhat), dgamma, dbeta
+// then reads g instead of dy1 / dy2 / y);  per-block partials of  sum g  and  sum g*xhat  -> one fp64 atomic per channel and CTA
 // ---------------------------------------------------------------------------------------------------------------
-struct BnBwdFinal {
-  unsigned int* counter;
-  float* coef;    // [2][C]: mean(g), mean(g*xhat)
-  float* dgamma;  // may be null
-  float* dbeta;
-  float inv_count;
-};
-
-__device__ __forceinline__ void bn_bwd_finalize(const BnBwdFinal& f, const double* bstat, int C, int tid, int nthreads) {
-  for (int c = tid; c < C; c += nthreads) {
-    double sg, sgx;
-    stat_load_cg(bstat, C, c, sg, sgx);
-    f.coef[c] = (float)sg * f.inv_count;
-    f.coef[C + c] = (float)sgx * f.inv_count;
-    if (f.dbeta) f.dbeta[c] = (float)sg;
-    if (f.dgamma) f.dgamma[c] = (float)sgx;
-  }
-}
-
-// block-level channel reduction of the per-thread partials + slot atomics + last-CTA finalisation (shared by the two reduce kernels)
-__device__ __forceinline__ void bn_bwd_block_reduce(const float (&sg)[8], const float (&sgx)[8], float (*sh)[17], volatile uint32_t* flag,
-                                                    double* bstat, const BnBwdFinal& fin, int c8) {
+// block-level channel reduction of the per-thread partials + atomics (shared by the two reduce kernels)
+__device__ __forceinline__ void bn_bwd_block_reduce(const float (&sg)[8], const float (&sgx)[8], float (*sh)[17], double* bstat, int c8) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     sh[threadIdx.x][j] = sg[j];
@@ -170,13 +188,7 @@ __device__ __forceinline__ void bn_bwd_block_reduce(const float (&sg)[8], const 
       a += sh[t][j];
       b += sh[t][8 + j];
     }
-    stat_add(bstat, C, blockIdx.x, o, a, b);
-  }
-  if (fin.counter != nullptr) {
-    if (last_cta_arrive(fin.counter, gridDim.x, threadIdx.x, 0, kThreads, flag)) {
-      bn_bwd_finalize(fin, bstat, C, threadIdx.x, kThreads);
-      if (threadIdx.x == 0) *fin.counter = 0u;
-    }
+    stat_add(bstat, o, a, b);
   }
 }
 
@@ -184,9 +196,8 @@ template <bool TWO, bool RELU, bool GOUT>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_reduce_kernel(const uint16_t* __restrict__ dy1, const uint16_t* __restrict__ dy2, const uint16_t* __restrict__ y,
                      const uint16_t* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
-                     double* __restrict__ bstat, uint16_t* __restrict__ g_out, BnBwdFinal fin, long long n8, int c8) {
+                     double* __restrict__ bstat, uint16_t* __restrict__ g_out, long long n8, int c8) {
   __shared__ float sh[kThreads][17];
-  __shared__ uint32_t flag;
   const long long stride = (long long)gridDim.x * kThreads;
   long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
   const int cg = (int)(i % c8);
@@ -237,15 +248,28 @@ bn_bwd_reduce_kernel(const uint16_t* __restrict__ dy1, const uint16_t* __restric
     const uint4 z = make_uint4(0, 0, 0, 0);
     one(i, ldg16(dy1 + i * 8), TWO ? ldg16(dy2 + i * 8) : z, RELU ? ldg16(y + i * 8) : z, ldg16(x + i * 8));
   }
-  bn_bwd_block_reduce(sg, sgx, sh, &flag, bstat, fin, c8);
+  bn_bwd_block_reduce(sg, sgx, sh, bstat, c8);
 }
 
-// backward pass 2: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)), coefficients finalised by pass 1
+// backward pass 2: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); coefficients straight from the fp64 sums of pass 1 (no
+// finalize launch); block 0 writes dgamma / dbeta
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_apply_kernel(const uint16_t* __restrict__ g, const uint16_t* __restrict__ x, const float* __restrict__ mean,
-                    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ coef,
-                    uint16_t* __restrict__ dx, long long n8, int c8) {
+                    const float* __restrict__ invstd, const float* __restrict__ gamma, const double* __restrict__ bstat, float inv_count,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, uint16_t* __restrict__ dx, long long n8, int c8) {
+  __shared__ __align__(16) float s_k[2 * kMaxC];
   const int C = c8 * 8;
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    double sg, sgx;
+    stat_load(bstat, c, sg, sgx);
+    s_k[c] = (float)sg * inv_count;          // mean(g)
+    s_k[kMaxC + c] = (float)sgx * inv_count; // mean(g * xhat)
+    if (blockIdx.x == 0) {
+      if (dbeta) dbeta[c] = (float)sg;
+      if (dgamma) dgamma[c] = (float)sgx;
+    }
+  }
+  __syncthreads();
   // Traverse from the END of the tensors: pass 1 just streamed the same operands front to back, so their tails are what is
   // still resident in the 126 MB L2.
   const long long stride = (long long)gridDim.x * kThreads;
@@ -253,7 +277,7 @@ bn_bwd_apply_kernel(const uint16_t* __restrict__ g, const uint16_t* __restrict__
   const int cg = (int)(((i % c8) + c8) % c8);
   const F8 mu = load8f(mean + cg * 8), is = load8f(invstd + cg * 8);
   F8 k0 = load8f(gamma + cg * 8);
-  const F8 k1 = load8f(coef + cg * 8), k2 = load8f(coef + C + cg * 8);
+  const F8 k1 = load8f(s_k + cg * 8), k2 = load8f(s_k + kMaxC + cg * 8);
 #pragma unroll
   for (int j = 0; j < 8; ++j) k0.v[j] *= is.v[j];  // gamma * invstd
   auto one = [&](const uint4& gu, const uint4& xu) {
@@ -404,15 +428,27 @@ maxpool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__
 // backward.  The post-ReLU activation (the largest tensor of the network: 103 MB at batch 256) is never materialised:
 // backward recomputes the ReLU mask from raw*scale+shift and scatters the pooled gradient through the saved argmax.
 // ---------------------------------------------------------------------------------------------------------------
+template <bool TRAIN>
 __global__ void __launch_bounds__(kThreads)
-stem_bn_pool_fwd_kernel(const uint16_t* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-                        uint16_t* __restrict__ y, uint8_t* __restrict__ amax, int N, int H, int W, int C, int P, int Q) {
+stem_bn_pool_fwd_kernel(const uint16_t* __restrict__ x, BnTrain bn, const float* __restrict__ scale_in, const float* __restrict__ shift_in,
+                        uint16_t* __restrict__ y, uint8_t* __restrict__ amax, int N, int H, int W, int C, int P, int Q, double inv_count,
+                        double unbias, float momentum, float eps) {
+  __shared__ __align__(16) float s_coef[2 * kMaxC];
+  if (TRAIN) {
+    bn_prologue(bn, C, inv_count, unbias, momentum, eps, s_coef, s_coef + kMaxC);
+  } else {
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      s_coef[c] = scale_in[c];
+      s_coef[kMaxC + c] = shift_in[c];
+    }
+  }
+  __syncthreads();
   const int c8 = C >> 3;
   const long long total = (long long)N * P * Q * c8;
   const long long stride = (long long)gridDim.x * kThreads;
   long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
   const int cg = (int)(i % c8);
-  const F8 sc = load8f(scale + cg * 8), sh = load8f(shift + cg * 8);
+  const F8 sc = load8f(s_coef + cg * 8), sh = load8f(s_coef + kMaxC + cg * 8);
   for (; i < total; i += stride) {
     long long t = i / c8;
     const int q = (int)(t % Q);
@@ -503,14 +539,13 @@ __device__ __forceinline__ void pool_scatter_2x2(const uint16_t* __restrict__ dy
 }
 
 // bstat += (sum g, sum g*xhat) and dx = g (bn_bwd_apply_kernel then finishes in place);  g = scatter(dpool) * (bn(x) > 0),
-// bn(x) = gamma*(x-mean)*invstd + beta;  the last CTA finalises mean(g), mean(g*xhat), dgamma, dbeta
+// bn(x) = gamma*(x-mean)*invstd + beta
 __global__ void __launch_bounds__(kThreads)
 stem_bn_pool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__ dy2, const uint8_t* __restrict__ amax,
                         const uint16_t* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
-                        const float* __restrict__ gamma, const float* __restrict__ beta, double* __restrict__ bstat, BnBwdFinal fin,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, double* __restrict__ bstat,
                         uint16_t* __restrict__ dx, int N, int H, int W, int C, int P, int Q) {
   __shared__ float sh[kThreads][17];
-  __shared__ uint32_t flag;
   const int c8 = C >> 3;
   const int HB = (H + 1) >> 1, WB = (W + 1) >> 1;
   const long long total = (long long)N * HB * WB * c8;
@@ -566,7 +601,7 @@ stem_bn_pool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restr
       }
     }
   }
-  bn_bwd_block_reduce(sg, sgx, sh, &flag, bstat, fin, c8);
+  bn_bwd_block_reduce(sg, sgx, sh, bstat, c8);
 }
 
 // AdaptiveAvgPool2d((1,1)) + flatten: [N, HW, C] bf16 -> [N, C] fp32
@@ -627,17 +662,9 @@ int stream_grid(const mml_ctx* ctx, long long items, int U) {
   return (int)b;
 }
 
-int bn_final_from_abi(mml_ctx* ctx, const mml_bn_final* fin, BnFinal* f, bool need_counter) {
-  MML_REQUIRE(ctx, fin->gamma && fin->beta && fin->save_mean && fin->save_invstd && fin->scale && fin->shift, "bn_final: null pointer");
-  MML_REQUIRE(ctx, (fin->running_mean == nullptr) == (fin->running_var == nullptr), "bn_final: running_mean / running_var must be given together");
-  MML_REQUIRE(ctx, !need_counter || fin->counter, "bn_final: counter is NULL");
-  *f = bn_final_convert(fin);
-  return MML_OK;
-}
-
 int check_rows_c(mml_ctx* ctx, int64_t rows, int C) {
   MML_REQUIRE(ctx, rows >= 1, "rows must be >= 1");
-  MML_REQUIRE(ctx, C >= 8 && C <= 2048 && (C % 8) == 0 && (kThreads % (C / 8)) == 0,
+  MML_REQUIRE(ctx, C >= 8 && C <= kMaxC && (C % 8) == 0 && (kThreads % (C / 8)) == 0,
               "channel count %d unsupported by the fused BN kernels (need C <= 512 and C/8 to divide 256)", C);
   return MML_OK;
 }
@@ -655,12 +682,34 @@ int mml_mask_apply_f32(mml_ctx* ctx, const float* x, const float* mask, float* y
   return MML_OK;
 }
 
-int mml_bn_finalize(mml_ctx* ctx, const double* stats, const mml_bn_final* fin, int C, void* stream) {
-  MML_REQUIRE(ctx, ctx && stats && fin && C >= 1, "bn_finalize: bad arguments");
-  BnFinal f;
-  int rc = bn_final_from_abi(ctx, fin, &f, /*need_counter=*/false);
+int mml_bn_train_fwd(mml_ctx* ctx, const uint16_t* x, const double* stats, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float* save_mean, float* save_invstd, const uint16_t* res, const double* rstats,
+                     const float* rgamma, const float* rbeta, float* r_running_mean, float* r_running_var, float* r_save_mean,
+                     float* r_save_invstd, uint16_t* y, int64_t rows, int C, int relu, float momentum, float eps, void* stream) {
+  MML_REQUIRE(ctx, ctx && x && stats && gamma && beta && save_mean && save_invstd && y, "bn_train_fwd: null pointer");
+  MML_REQUIRE(ctx, (running_mean == nullptr) == (running_var == nullptr), "bn_train_fwd: running_mean / running_var must be given together");
+  int rc = check_rows_c(ctx, rows, C);
   if (rc) return rc;
-  bn_finalize_kernel<<<(C + kThreads - 1) / kThreads, kThreads, 0, (cudaStream_t)stream>>>(stats, f, C);
+  const int mode = res == nullptr ? 0 : (rstats == nullptr ? 1 : 2);
+  if (mode == 2) MML_REQUIRE(ctx, rgamma && rbeta && r_save_mean && r_save_invstd, "bn_train_fwd: residual BN needs gamma/beta/save buffers");
+  BnTrain bn{stats, gamma, beta, running_mean, running_var, save_mean, save_invstd};
+  BnTrain rbn{rstats, rgamma, rbeta, r_running_mean, r_running_var, r_save_mean, r_save_invstd};
+  const long long n8 = rows * (C / 8);
+  const int grid = stream_grid(ctx, n8, kU);
+  const double inv_count = 1.0 / (double)rows;
+  const double unbias = rows > 1 ? (double)rows / (double)(rows - 1) : 1.0;
+  cudaStream_t st = (cudaStream_t)stream;
+#define MML_TR(M, RL) \
+  bn_fwd_kernel<M, RL, true><<<grid, kThreads, 0, st>>>(x, bn, nullptr, nullptr, res, rbn, nullptr, nullptr, y, n8, C / 8, inv_count, unbias, momentum, eps)
+  switch (mode * 2 + (relu ? 1 : 0)) {
+    case 0: MML_TR(0, false); break;
+    case 1: MML_TR(0, true); break;
+    case 2: MML_TR(1, false); break;
+    case 3: MML_TR(1, true); break;
+    case 4: MML_TR(2, false); break;
+    default: MML_TR(2, true); break;
+  }
+#undef MML_TR
   MML_LAUNCHED(ctx);
   return MML_OK;
 }
@@ -681,14 +730,18 @@ int mml_bn_act_fwd(mml_ctx* ctx, const uint16_t* x, const float* scale, const fl
   MML_REQUIRE(ctx, (rscale == nullptr) == (rshift == nullptr), "bn_act_fwd: rscale/rshift must be given together");
   const long long n8 = rows * (C / 8);
   const int grid = stream_grid(ctx, n8, kU);
+  const int mode = res == nullptr ? 0 : (rscale == nullptr ? 1 : 2);
+  const BnTrain none{};
   cudaStream_t st = (cudaStream_t)stream;
-#define MML_FWD(HR, RA, RL) bn_act_fwd_kernel<HR, RA, RL><<<grid, kThreads, 0, st>>>(x, scale, shift, res, rscale, rshift, y, n8, C / 8)
-  if (res == nullptr) {
-    if (relu) MML_FWD(false, false, true); else MML_FWD(false, false, false);
-  } else if (rscale == nullptr) {
-    if (relu) MML_FWD(true, false, true); else MML_FWD(true, false, false);
-  } else {
-    if (relu) MML_FWD(true, true, true); else MML_FWD(true, true, false);
+#define MML_FWD(M, RL) \
+  bn_fwd_kernel<M, RL, false><<<grid, kThreads, 0, st>>>(x, none, scale, shift, res, none, rscale, rshift, y, n8, C / 8, 0.0, 0.0, 0.f, 0.f)
+  switch (mode * 2 + (relu ? 1 : 0)) {
+    case 0: MML_FWD(0, false); break;
+    case 1: MML_FWD(0, true); break;
+    case 2: MML_FWD(1, false); break;
+    case 3: MML_FWD(1, true); break;
+    case 4: MML_FWD(2, false); break;
+    default: MML_FWD(2, true); break;
   }
 #undef MML_FWD
   MML_LAUNCHED(ctx);
@@ -704,17 +757,14 @@ static int bn_bwd_grid(const mml_ctx* ctx, int64_t rows, int C) {
 }
 
 int mml_bn_bwd_reduce(mml_ctx* ctx, const uint16_t* dy1, const uint16_t* dy2, const uint16_t* y, const uint16_t* x,
-                      const float* mean, const float* invstd, double* bstat, uint16_t* g_out, uint32_t* counter, float* coef,
-                      float* dgamma, float* dbeta, int64_t rows, int C, int relu, void* stream) {
+                      const float* mean, const float* invstd, double* bstat, uint16_t* g_out, int64_t rows, int C, int relu, void* stream) {
   MML_REQUIRE(ctx, ctx && dy1 && x && mean && invstd && bstat && (!relu || y), "bn_bwd_reduce: null pointer");
-  MML_REQUIRE(ctx, (counter == nullptr) == (coef == nullptr), "bn_bwd_reduce: counter and coef must be given together");
   int rc = check_rows_c(ctx, rows, C);
   if (rc) return rc;
   const long long n8 = rows * (C / 8);
   const int grid = bn_bwd_grid(ctx, rows, C);
-  BnBwdFinal fin{counter, coef, dgamma, dbeta, 1.0f / (float)rows};
   cudaStream_t st = (cudaStream_t)stream;
-#define MML_RED(TW, RL, GO) bn_bwd_reduce_kernel<TW, RL, GO><<<grid, kThreads, 0, st>>>(dy1, dy2, y, x, mean, invstd, bstat, g_out, fin, n8, C / 8)
+#define MML_RED(TW, RL, GO) bn_bwd_reduce_kernel<TW, RL, GO><<<grid, kThreads, 0, st>>>(dy1, dy2, y, x, mean, invstd, bstat, g_out, n8, C / 8)
   const int key = (dy2 ? 4 : 0) | (relu ? 2 : 0) | (g_out ? 1 : 0);
   switch (key) {
     case 0: MML_RED(false, false, false); break;
@@ -732,12 +782,13 @@ int mml_bn_bwd_reduce(mml_ctx* ctx, const uint16_t* dy1, const uint16_t* dy2, co
 }
 
 int mml_bn_bwd_apply(mml_ctx* ctx, const uint16_t* g, const uint16_t* x, const float* mean, const float* invstd, const float* gamma,
-                     const float* coef, uint16_t* dx, int64_t rows, int C, void* stream) {
-  MML_REQUIRE(ctx, ctx && g && x && mean && invstd && gamma && coef && dx, "bn_bwd_apply: null pointer");
+                     const double* bstat, float* dgamma, float* dbeta, uint16_t* dx, int64_t rows, int C, void* stream) {
+  MML_REQUIRE(ctx, ctx && g && x && mean && invstd && gamma && bstat && dx, "bn_bwd_apply: null pointer");
   int rc = check_rows_c(ctx, rows, C);
   if (rc) return rc;
   const long long n8 = rows * (C / 8);
-  bn_bwd_apply_kernel<<<stream_grid(ctx, n8, kU), kThreads, 0, (cudaStream_t)stream>>>(g, x, mean, invstd, gamma, coef, dx, n8, C / 8);
+  bn_bwd_apply_kernel<<<stream_grid(ctx, n8, kU), kThreads, 0, (cudaStream_t)stream>>>(g, x, mean, invstd, gamma, bstat, 1.0f / (float)rows, dgamma, dbeta,
+                                                                                       dx, n8, C / 8);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }
@@ -760,37 +811,49 @@ int mml_maxpool3x3s2_bwd(mml_ctx* ctx, const uint16_t* dy, const uint16_t* dy2, 
   return MML_OK;
 }
 
-int mml_stem_bn_pool_fwd(mml_ctx* ctx, const uint16_t* x, const float* scale, const float* shift, uint16_t* y, uint8_t* argmax, int N, int H,
-                         int W, int C, void* stream) {
-  MML_REQUIRE(ctx, ctx && x && y && argmax && scale && shift && N >= 1 && H >= 1 && W >= 1, "stem_bn_pool_fwd: bad arguments");
+int mml_stem_bn_pool_fwd(mml_ctx* ctx, const uint16_t* x, const double* stats, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, float* save_mean, float* save_invstd, const float* scale, const float* shift, uint16_t* y,
+                         uint8_t* argmax, int N, int H, int W, int C, float momentum, float eps, void* stream) {
+  MML_REQUIRE(ctx, ctx && x && y && argmax && N >= 1 && H >= 1 && W >= 1, "stem_bn_pool_fwd: bad arguments");
+  MML_REQUIRE(ctx, (stats != nullptr) != (scale != nullptr), "stem_bn_pool_fwd: give either batch statistics (train) or scale/shift (eval)");
   int rc = check_rows_c(ctx, (int64_t)N * H * W, C);
   if (rc) return rc;
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+  const int64_t rows = (int64_t)N * H * W;
   const int grid = ew_grid(ctx, (long long)N * P * Q * (C / 8));
-  stem_bn_pool_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, scale, shift, y, argmax, N, H, W, C, P, Q);
+  BnTrain bn{stats, gamma, beta, running_mean, running_var, save_mean, save_invstd};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (stats) {
+    MML_REQUIRE(ctx, gamma && beta && save_mean && save_invstd, "stem_bn_pool_fwd: null BN pointer");
+    stem_bn_pool_fwd_kernel<true><<<grid, kThreads, 0, st>>>(x, bn, nullptr, nullptr, y, argmax, N, H, W, C, P, Q, 1.0 / (double)rows,
+                                                              rows > 1 ? (double)rows / (double)(rows - 1) : 1.0, momentum, eps);
+  } else {
+    MML_REQUIRE(ctx, shift != nullptr, "stem_bn_pool_fwd: shift is NULL");
+    stem_bn_pool_fwd_kernel<false><<<grid, kThreads, 0, st>>>(x, bn, scale, shift, y, argmax, N, H, W, C, P, Q, 0.0, 0.0, momentum, eps);
+  }
   MML_LAUNCHED(ctx);
   return MML_OK;
 }
 
 int mml_stem_bn_pool_bwd(mml_ctx* ctx, const uint16_t* dy, const uint16_t* dy2, const uint8_t* argmax, const uint16_t* x, const float* mean,
-                         const float* invstd, const float* gamma, const float* beta, double* bstat, uint32_t* counter, float* coef,
-                         float* dgamma, float* dbeta, uint16_t* dx, int N, int H, int W, int C, void* stream) {
-  MML_REQUIRE(ctx, ctx && dy && argmax && x && mean && invstd && gamma && beta && bstat && counter && coef && dx && N >= 1 && H >= 1 && W >= 1,
+                         const float* invstd, const float* gamma, const float* beta, double* bstat, float* dgamma, float* dbeta, uint16_t* dx,
+                         int N, int H, int W, int C, void* stream) {
+  MML_REQUIRE(ctx, ctx && dy && argmax && x && mean && invstd && gamma && beta && bstat && dx && N >= 1 && H >= 1 && W >= 1,
               "stem_bn_pool_bwd: bad arguments");
   int rc = check_rows_c(ctx, (int64_t)N * H * W, C);
   if (rc) return rc;
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
   const long long items = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  const float inv_count = 1.0f / (float)((int64_t)N * H * W);
   cudaStream_t st = (cudaStream_t)stream;
   int g0 = (int)mml_ceil_div(items, (long long)kThreads * 2);
   if (g0 > ctx->sm_count * 4) g0 = ctx->sm_count * 4;
   if (g0 < 1) g0 = 1;
-  BnBwdFinal fin{counter, coef, dgamma, dbeta, 1.0f / (float)((int64_t)N * H * W)};
-  stem_bn_pool_bwd_kernel<<<g0, kThreads, 0, st>>>(dy, dy2, argmax, x, mean, invstd, gamma, beta, bstat, fin, dx, N, H, W, C, P, Q);
+  stem_bn_pool_bwd_kernel<<<g0, kThreads, 0, st>>>(dy, dy2, argmax, x, mean, invstd, gamma, beta, bstat, dx, N, H, W, C, P, Q);
   MML_LAUNCHED(ctx);
   // pass 2 in place over the buffer that now holds g: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))
   const long long n8 = (long long)N * H * W * (C / 8);
-  bn_bwd_apply_kernel<<<stream_grid(ctx, n8, kU), kThreads, 0, st>>>(dx, x, mean, invstd, gamma, coef, dx, n8, C / 8);
+  bn_bwd_apply_kernel<<<stream_grid(ctx, n8, kU), kThreads, 0, st>>>(dx, x, mean, invstd, gamma, bstat, inv_count, dgamma, dbeta, dx, n8, C / 8);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }

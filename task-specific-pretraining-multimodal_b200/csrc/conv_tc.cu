@@ -51,8 +51,7 @@ struct IgemmParams {
   int Hb, Nb;      // tile = {OutW, Hb, Nb}
   int valid_rows;  // OutW * Hb * Nb  (<= 128)
   int cout;
-  double* stats;  // [16 slots][cout][2] (sum, sum of squares) of the stored output, accumulated with fp64 atomics; or nullptr
-  BnFinal fin;    // fin.counter != nullptr: the last CTA turns the statistics into BatchNorm coefficients
+  double* stats;  // [cout][2] (sum, sum of squares) of the stored output, accumulated with fp64 atomics; or nullptr
   Tap taps[kMaxTaps];
 };
 
@@ -237,15 +236,8 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
         if (half == 0) {
           const float2 o = stat_scratch[c];
           // fp64 atomics: the summation order across CTAs then changes the result far below fp32 resolution
-          stat_add(p.stats, p.cout, m_tile, n_tile * BLOCK_N + ch * 64 + c, s + o.x, ss + o.y);
+          stat_add(p.stats, n_tile * BLOCK_N + ch * 64 + c, s + o.x, ss + o.y);
         }
-      }
-    }
-    if (p.stats != nullptr && p.fin.counter != nullptr) {
-      volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kOffBars + 8 * (2 * STAGES + 2));
-      if (last_cta_arrive(p.fin.counter, gridDim.x * gridDim.y, et, 1, 128, flag)) {
-        bn_final_forward(p.fin, p.stats, p.cout, et, 128);
-        if (et == 0) *p.fin.counter = 0u;
       }
     }
     if (et == 0) tma_store_wait_all<0>();
@@ -285,7 +277,6 @@ struct HaloParams {
   int m_tiles, num_super;
   int cout;
   double* stats;
-  BnFinal fin;
   Tap taps[kMaxTaps];
 };
 
@@ -477,6 +468,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
       if (r < rows_m && (r % wp2) < p.Wb) vmask |= 1u << b;
     }
     constexpr int kChunks = BLOCK_N / 64;
+    float4 st_acc0 = make_float4(0.f, 0.f, 0.f, 0.f), st_acc1 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int it = 0; it < n_my; ++it) {
       const int ab = it & 1;
       if (L::kUnits == 1 && ab != gi) continue;  // single unit per iteration: group g owns accumulator buffer g
@@ -515,6 +507,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
           tma_store_commit();
         }
         if (p.stats != nullptr && m_tile < p.m_tiles) {
+          // BatchNorm partials of the STORED (bf16-rounded) tile, accumulated in registers over all tiles of this CTA
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
           const uint8_t* colp = stage_gen + (wc & 3) * 4;
 #pragma unroll 8
@@ -527,27 +520,27 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
               q0 = fmaf(a, a, q0), q1 = fmaf(c, c, q1);
             }
           }
-          float4* sc = stat_scratch + gi * 128;
-          sc[eg] = make_float4(s0, s1, q0, q1);
-          named_bar_sync(bar_id, 128);
-          if (eg < 32) {
-            const float4 a = sc[eg], b2 = sc[eg + 32], c2 = sc[eg + 64], d2 = sc[eg + 96];
-            const int c0 = ch * 64 + 2 * eg;
-            stat_add(p.stats, p.cout, m_tile, c0, a.x + b2.x + c2.x + d2.x, a.z + b2.z + c2.z + d2.z);
-            stat_add(p.stats, p.cout, m_tile, c0 + 1, a.y + b2.y + c2.y + d2.y, a.w + b2.w + c2.w + d2.w);
-          }
+          if (kChunks == 1 || ch == 0) st_acc0.x += s0, st_acc0.y += s1, st_acc0.z += q0, st_acc0.w += q1;
+          else st_acc1.x += s0, st_acc1.y += s1, st_acc1.z += q0, st_acc1.w += q1;
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(ab));
     }
-    if (p.stats != nullptr && p.fin.counter != nullptr) {  // both epilogue groups (256 threads) are done with their atomics
-      const int e2 = (warp - 2) * 32 + lane;
-      volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kOffBars + 8 * (12 + 2 * L::kWStages + 1));
-      if (last_cta_arrive(p.fin.counter, gridDim.x, e2, 3, 256, flag)) {
-        bn_final_forward(p.fin, p.stats, p.cout, e2, 256);
-        if (e2 == 0) *p.fin.counter = 0u;
+    if (p.stats != nullptr) {  // one atomic per channel, group and CTA
+      float4* sc = stat_scratch + gi * 128;
+#pragma unroll
+      for (int ch = 0; ch < kChunks; ++ch) {
+        named_bar_sync(bar_id, 128);
+        sc[eg] = ch == 0 ? st_acc0 : st_acc1;
+        named_bar_sync(bar_id, 128);
+        if (eg < 32) {
+          const float4 a = sc[eg], b2 = sc[eg + 32], c2 = sc[eg + 64], d2 = sc[eg + 96];
+          const int c0 = ch * 64 + 2 * eg;
+          stat_add(p.stats, c0, a.x + b2.x + c2.x + d2.x, a.z + b2.z + c2.z + d2.z);
+          stat_add(p.stats, c0 + 1, a.y + b2.y + c2.y + d2.y, a.w + b2.w + c2.w + d2.w);
+        }
       }
     }
     if (eg == 0) tma_store_wait_all<0>();
@@ -1051,7 +1044,7 @@ int launch_igemm_t(mml_ctx* ctx, const IgemmMaps& maps, const IgemmParams& p, di
 // One "shifted GEMM" launch: out view <- sum over taps of in views @ weights.
 //   b_mn = false: w is [cout rows][n_wtaps*cin inner] bf16;   b_mn = true: w is [cin rows][n_wtaps*cout inner] bf16
 int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, int n_wtaps, int cin, int cout, const View& out,
-              const Tap* taps, int num_taps, double* stats, const BnFinal& fin, bool b_mn, cudaStream_t st) {
+              const Tap* taps, int num_taps, double* stats, bool b_mn, cudaStream_t st) {
   MML_REQUIRE(ctx, cin % 64 == 0 && cout % 64 == 0, "conv: channel counts must be multiples of 64 (got C=%d K=%d)", cin, cout);
   MML_REQUIRE(ctx, num_taps >= 1 && num_taps <= kMaxTaps && n_views <= kMaxViews, "conv: bad tap table");
   TileGeom tg;
@@ -1086,7 +1079,6 @@ int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, in
   p.valid_rows = tg.valid_rows;
   p.cout = cout;
   p.stats = stats;
-  p.fin = fin;
   for (int i = 0; i < num_taps; ++i) p.taps[i] = taps[i];
   dim3 grid(tg.tiles_h * tg.tiles_n, cout / block_n);
   if (!b_mn) {
@@ -1184,7 +1176,7 @@ int launch_halo_t(mml_ctx* ctx, const HaloMaps& maps, const HaloParams& p, cudaS
 int g_halo_enable = 1;
 
 int run_halo(mml_ctx* ctx, const View& in, const void* w, int n_wtaps, int cin, int cout, const View& out, const Tap* taps, int num_taps,
-             double* stats, const BnFinal& fin, bool b_mn, const HaloGeom& hg, cudaStream_t st) {
+             double* stats, bool b_mn, const HaloGeom& hg, cudaStream_t st) {
   HaloMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc;
@@ -1205,7 +1197,6 @@ int run_halo(mml_ctx* ctx, const View& in, const void* w, int n_wtaps, int cin, 
   p.num_super = (hg.m_tiles + T - 1) / T;
   p.cout = cout;
   p.stats = stats;
-  p.fin = fin;
   for (int i = 0; i < num_taps; ++i) p.taps[i] = taps[i];
   if (cin == 64) return b_mn ? launch_halo_t<1, 64, 1, true, true>(ctx, maps, p, st) : launch_halo_t<1, 64, 1, true, false>(ctx, maps, p, st);
   return b_mn ? launch_halo_t<2, 128, 2, false, true>(ctx, maps, p, st) : launch_halo_t<2, 128, 2, false, false>(ctx, maps, p, st);
@@ -1257,15 +1248,8 @@ int mml_debug_set(int key, int value) {
 
 int mml_conv_fprop(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, const uint16_t* w_krsc, uint16_t* y,
                    double* stats, void* stream) {
-  return mml_conv_fprop_bn(ctx, g, x, w_krsc, y, stats, nullptr, stream);
-}
-
-int mml_conv_fprop_bn(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, const uint16_t* w_krsc, uint16_t* y, double* stats,
-                      const mml_bn_final* fin_abi, void* stream) {
   int P, Q, rc;
   if ((rc = check_geom(ctx, g, &P, &Q))) return rc;
-  MML_REQUIRE(ctx, fin_abi == nullptr || (stats != nullptr && fin_abi->counter != nullptr), "conv_fprop_bn: finalisation needs stats and a counter");
-  const BnFinal fin = bn_final_convert(fin_abi);
   View views[kMaxViews];
   Tap taps[kMaxTaps];
   int n_views = 0;
@@ -1285,8 +1269,8 @@ int mml_conv_fprop_bn(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, c
   View out = make_phase_view(y, g->N, P, Q, g->K, 1, 0, 0);
   HaloGeom hg;
   if (g_halo_enable && g->R == 3 && g->stride == 1 && g->pad == 1 && n_taps == 9 && halo_geometry(Q, P, g->N, g->C, g->K, &hg))
-    return run_halo(ctx, used[0], w_krsc, 9, g->C, g->K, out, taps, n_taps, stats, fin, false, hg, (cudaStream_t)stream);
-  return run_igemm(ctx, used, n_used, w_krsc, g->R * g->S, g->C, g->K, out, taps, n_taps, stats, fin, false, (cudaStream_t)stream);
+    return run_halo(ctx, used[0], w_krsc, 9, g->C, g->K, out, taps, n_taps, stats, false, hg, (cudaStream_t)stream);
+  return run_igemm(ctx, used, n_used, w_krsc, g->R * g->S, g->C, g->K, out, taps, n_taps, stats, false, (cudaStream_t)stream);
 }
 
 int mml_conv_dgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* dy, const uint16_t* w_krsc, uint16_t* dx, void* stream) {
@@ -1295,7 +1279,6 @@ int mml_conv_dgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* dy, con
   cudaStream_t st = (cudaStream_t)stream;
   const int s2 = g->stride;
   View in = make_phase_view(dy, g->N, P, Q, g->K, 1, 0, 0);
-  const BnFinal no_fin = bn_final_convert(nullptr);
   bool need_zero = false;
   // dx[h] = sum_r dy[(h + pad - r)/stride] * w_t[r]  over taps with (h + pad - r) % stride == 0.
   // Per output phase e = h % stride:  h = stride*a + e,  p = a + (e + pad - r)/stride.
@@ -1332,10 +1315,10 @@ int mml_conv_dgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* dy, con
   if (need_zero) MML_CHECK_CUDA(ctx, cudaMemsetAsync(dx, 0, (size_t)g->N * g->H * g->W * g->C * 2, st));
   HaloGeom hg;
   if (g_halo_enable && g->R == 3 && s2 == 1 && g->pad == 1 && n_launch == 1 && launches[0].n == 9 && halo_geometry(g->W, g->H, g->N, g->K, g->C, &hg))
-    return run_halo(ctx, in, w_krsc, 9, g->K, g->C, launches[0].out, launches[0].taps, 9, nullptr, no_fin, true, hg, st);
+    return run_halo(ctx, in, w_krsc, 9, g->K, g->C, launches[0].out, launches[0].taps, 9, nullptr, true, hg, st);
   for (int i = 0; i < n_launch; ++i) {
     // GEMM-K = k (rows of the K,R,S,C weight matrix), GEMM-N = c: the fprop weights are read as an MN-major B operand
-    rc = run_igemm(ctx, &in, 1, w_krsc, g->R * g->S, g->K, g->C, launches[i].out, launches[i].taps, launches[i].n, nullptr, no_fin, true, st);
+    rc = run_igemm(ctx, &in, 1, w_krsc, g->R * g->S, g->K, g->C, launches[i].out, launches[i].taps, launches[i].n, nullptr, true, st);
     if (rc) return rc;
   }
   return MML_OK;
@@ -1372,7 +1355,8 @@ static int plan_wgrad(const mml_ctx* ctx, const mml_conv_geom* g, int P, int Q, 
   wp->block_c = g->C % 256 == 0 ? 256 : (g->C % 128 == 0 ? 128 : 64);
   wp->out_tiles = (int)mml_ceil_div(g->K, 128) * n_taps * (g->C / wp->block_c);
   const int m_tiles = wp->tg.tiles_h * wp->tg.tiles_n;
-  int splits = (2 * ctx->sm_count + wp->out_tiles - 1) / wp->out_tiles;
+  // one wave: every split's partial tile is written to and read back from the workspace, so more CTAs than SMs only add traffic
+  int splits = ctx->sm_count / wp->out_tiles;
   if (splits > m_tiles) splits = m_tiles;
   if (splits < 1) splits = 1;
   wp->splits = splits;

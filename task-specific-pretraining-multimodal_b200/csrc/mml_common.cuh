@@ -8,9 +8,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
-#include <string.h>
-
-#include "../../include/mml_b200.h"
 
 namespace mml {
 
@@ -221,99 +218,18 @@ __device__ __forceinline__ float mask_mul(float x, float m) {
   return r;
 }
 
-// BatchNorm statistics accumulators: fp64 [MML_BN_STAT_SLOTS][C][2]; producers add into slot (block index & 15) so that at
-// most 1/16 of the CTAs of a launch contend for one address; consumers sum the slots.
-constexpr int kStatSlots = 16;
-__device__ __forceinline__ void stat_add(double* stats, int C, int slot, int c, float a, float b) {
-  double* dst = stats + 2 * ((size_t)(slot & (kStatSlots - 1)) * C + c);
-  atomicAdd(dst, (double)a);
-  atomicAdd(dst + 1, (double)b);
+// BatchNorm statistics accumulators: fp64 [C][2] (sum, sum of squares) per BatchNorm, zeroed once per step by the caller.
+// Producers (conv / stem epilogues, the BN backward reduce) add with fp64 atomics -- persistent kernels accumulate over all their
+// tiles first, so an address sees at most a few hundred atomics per launch -- and every consumer CTA derives its coefficients from
+// C x 16 bytes.  (Round 1 spread the atomics over 16 slots; consumers then read 16x as much per CTA, which made the BatchNorm
+// kernels of the small, many-channel tensors L2-bound: 134 MB of slot reads in front of an 8 MB tensor.)
+__device__ __forceinline__ void stat_add(double* stats, int c, float a, float b) {
+  atomicAdd(stats + 2 * c, (double)a);
+  atomicAdd(stats + 2 * c + 1, (double)b);
 }
-__device__ __forceinline__ void stat_load(const double* stats, int C, int c, double& a, double& b) {
-  a = 0.0, b = 0.0;
-#pragma unroll
-  for (int k = 0; k < kStatSlots; ++k) {
-    a += stats[2 * ((size_t)k * C + c)];
-    b += stats[2 * ((size_t)k * C + c) + 1];
-  }
-}
-
-// --------------------------------------------------------------------------------------------
-// BatchNorm finalisation by the LAST CTA of the kernel that produced the statistics
-// --------------------------------------------------------------------------------------------
-// Round 1 let every CTA of every consumer kernel re-derive scale / shift from the 16 fp64 slots (C x 32 loads per CTA: for a
-// 512-channel, 4 MB tensor that was 134 MB of L2 reads in front of 8 MB of useful traffic).  Now the producer's last CTA (ticket
-// counter, self-resetting) does it once and the consumers load two floats per channel.
-struct BnFinal {
-  unsigned int* counter;  // nullptr: no finalisation
-  const float* gamma;
-  const float* beta;
-  float* running_mean;  // may be null (with running_var)
-  float* running_var;
-  float* save_mean;
-  float* save_invstd;
-  float* scale;
-  float* shift;
-  double inv_count, unbias;
-  float momentum, eps;
-};
-
-inline BnFinal bn_final_convert(const mml_bn_final* a) {
-  BnFinal f;
-  memset(&f, 0, sizeof(f));
-  if (a == nullptr) return f;
-  f.counter = a->counter;
-  f.gamma = a->gamma, f.beta = a->beta;
-  f.running_mean = a->running_mean, f.running_var = a->running_var;
-  f.save_mean = a->save_mean, f.save_invstd = a->save_invstd;
-  f.scale = a->scale, f.shift = a->shift;
-  f.inv_count = a->inv_count, f.unbias = a->unbias;
-  f.momentum = a->momentum, f.eps = a->eps;
-  return f;
-}
-
-// All `nthreads` threads (tid 0..nthreads-1, sharing named barrier `bar_id`) call this after their last statistics atomics.
-// True in every thread of the CTA that arrived last of `total_ctas`.
-__device__ __forceinline__ bool last_cta_arrive(unsigned int* counter, unsigned int total_ctas, int tid, uint32_t bar_id, uint32_t nthreads,
-                                                volatile uint32_t* smem_flag) {
-  __threadfence();  // this thread's atomics are performed device-wide before the ticket is taken
-  named_bar_sync(bar_id, nthreads);
-  if (tid == 0) *smem_flag = (atomicAdd(counter, 1u) == total_ctas - 1u) ? 1u : 0u;
-  named_bar_sync(bar_id, nthreads);
-  const bool last = *smem_flag != 0u;
-  if (last) __threadfence();
-  return last;
-}
-
-__device__ __forceinline__ void stat_load_cg(const double* stats, int C, int c, double& a, double& b) {
-  a = 0.0, b = 0.0;
-  double2 v[kStatSlots];
-#pragma unroll
-  for (int k = 0; k < kStatSlots; ++k) v[k] = __ldcg(reinterpret_cast<const double2*>(stats + 2 * ((size_t)k * C + c)));
-#pragma unroll
-  for (int k = 0; k < kStatSlots; ++k) a += v[k].x, b += v[k].y;
-}
-
-// forward: (sum x, sum x^2) -> scale / shift, saved mean / invstd, running statistics (torch.nn.BatchNorm2d, momentum form)
-__device__ __forceinline__ void bn_final_forward(const BnFinal& f, const double* stats, int C, int tid, int nthreads) {
-  for (int c = tid; c < C; c += nthreads) {
-    double sum, sq;
-    stat_load_cg(stats, C, c, sum, sq);
-    const double mean = sum * f.inv_count;
-    double var = sq * f.inv_count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float invstd = (float)(1.0 / sqrt(var + (double)f.eps));
-    const float sc = f.gamma[c] * invstd;
-    const float mu = (float)mean;
-    f.scale[c] = sc;
-    f.shift[c] = f.beta[c] - mu * sc;
-    f.save_mean[c] = mu;
-    f.save_invstd[c] = invstd;
-    if (f.running_mean) {
-      f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mu;
-      f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)(var * f.unbias);
-    }
-  }
+__device__ __forceinline__ void stat_load(const double* stats, int c, double& a, double& b) {
+  const double2 v = __ldcg(reinterpret_cast<const double2*>(stats + 2 * c));
+  a = v.x, b = v.y;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -123,7 +123,7 @@ constexpr int kFBytes = kFOffBars + 1024 + 1024;
 
 __global__ void __launch_bounds__(kThreadsStem, 3)
 stem_fprop_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restrict__ x, const float* __restrict__ mask,
-                     const float* __restrict__ w, double* __restrict__ stats, BnFinal fin, StemGeom g) {
+                     const float* __restrict__ w, double* __restrict__ stats, StemGeom g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -133,7 +133,6 @@ stem_fprop_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
   auto mma_done = [&](int b) { return bars + 8u * (2 + b); };
   const uint32_t tmem_slot = bars + 8u * 4;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kFOffBars + 8 * 4);
-  float2* stat_scratch = reinterpret_cast<float2*>(smem_gen + kFOffBars + 256);
 
   {  // tile rows >= valid and chunk 7 of every row are never written by the builders: zero both A buffers once
     uint4 z = make_uint4(0, 0, 0, 0);
@@ -190,6 +189,7 @@ stem_fprop_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
     const int pr = row / g.Q, q = row - pr * g.Q;
     const int word0 = 2 * pr * g.PWW + q;
     const bool live = row < g.valid;
+    float4 st_acc = make_float4(0.f, 0.f, 0.f, 0.f);
     auto epilogue = [&](int j) {
       const int buf = j & 1;
       const int tile = (int)blockIdx.x + j * (int)gridDim.x;
@@ -223,22 +223,21 @@ stem_fprop_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
         tma_store_commit();
       }
       if (stats != nullptr) {
-        const int c = threadIdx.x & 63, half = threadIdx.x >> 6;
-        const int rbeg = half * 64, rend = min(g.valid, rbeg + 64);
-        float s = 0.f, ss = 0.f;
-        const uint8_t* colp = smem_gen + kFOffStage + (c & 7) * 2;
-        for (int r = rbeg; r < rend; ++r) {
-          const uint16_t raw = *reinterpret_cast<const uint16_t*>(colp + r * 128 + ((((uint32_t)c >> 3) ^ (uint32_t)(r & 7)) << 4));
-          const float v = __uint_as_float((uint32_t)raw << 16);
-          s += v;
-          ss = fmaf(v, v, ss);
+        // BatchNorm partials of the STORED (bf16-rounded) tile: thread = (channel pair wc, row quarter rq), one 32-bit shared load
+        // per row, accumulated in registers over all tiles of this CTA (one atomic per channel and CTA at the end)
+        const int wc = threadIdx.x & 31, rq = threadIdx.x >> 5;
+        const int rend = min(g.valid - rq * 32, 32);
+        const uint8_t* colp = smem_gen + kFOffStage + (wc & 3) * 4;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+        for (int b = 0; b < rend; ++b) {
+          const int r = rq * 32 + b;
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(colp + r * 128 + ((((uint32_t)wc >> 2) ^ (uint32_t)(r & 7)) << 4));
+          const float a = bf16_lo(v), c = bf16_hi(v);
+          s0 += a, s1 += c;
+          q0 = fmaf(a, a, q0), q1 = fmaf(c, c, q1);
         }
-        if (half == 1) stat_scratch[c] = make_float2(s, ss);
-        named_bar_sync(1, 128);
-        if (half == 0) {
-          const float2 o = stat_scratch[c];
-          stat_add(stats, 64, tile, c, s + o.x, ss + o.y);
-        }
+        st_acc.x += s0, st_acc.y += s1, st_acc.z += q0, st_acc.w += q1;
       }
     };
     float reg[kPatchRegs];
@@ -261,11 +260,17 @@ stem_fprop_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
       named_bar_sync(1, 128);
     }
     if (n_my >= 1) epilogue(n_my - 1);
-    if (stats != nullptr && fin.counter != nullptr) {
-      volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(smem_gen + kFOffBars + 8 * 5);
-      if (last_cta_arrive(fin.counter, gridDim.x, (int)threadIdx.x, 1, 128, flag)) {
-        bn_final_forward(fin, stats, 64, (int)threadIdx.x, 128);
-        if (threadIdx.x == 0) *fin.counter = 0u;
+    if (stats != nullptr) {
+      float4* sc = reinterpret_cast<float4*>(smem_gen + kFOffStage);  // the staging buffer is free once the last TMA store has read it
+      if (threadIdx.x == 0) tma_store_wait_read<0>();
+      named_bar_sync(1, 128);
+      sc[threadIdx.x] = st_acc;
+      named_bar_sync(1, 128);
+      if (threadIdx.x < 32) {
+        const float4 a = sc[threadIdx.x], b2 = sc[threadIdx.x + 32], c2 = sc[threadIdx.x + 64], d2 = sc[threadIdx.x + 96];
+        const int c0 = 2 * threadIdx.x;
+        stat_add(stats, c0, a.x + b2.x + c2.x + d2.x, a.z + b2.z + c2.z + d2.z);
+        stat_add(stats, c0 + 1, a.y + b2.y + c2.y + d2.y, a.w + b2.w + c2.w + d2.w);
       }
     }
     if (threadIdx.x == 0) tma_store_wait_all<0>();
@@ -426,14 +431,7 @@ extern "C" {
 
 int mml_stem_fprop(mml_ctx* ctx, const float* x, const float* mask, const float* w, uint16_t* y, double* stats, int B, int H,
                    int W, void* stream) {
-  return mml_stem_fprop_bn(ctx, x, mask, w, y, stats, nullptr, B, H, W, stream);
-}
-
-int mml_stem_fprop_bn(mml_ctx* ctx, const float* x, const float* mask, const float* w, uint16_t* y, double* stats, const mml_bn_final* fin_abi,
-                      int B, int H, int W, void* stream) {
   MML_REQUIRE(ctx, ctx && x && w && y, "stem_fprop: null pointer");
-  MML_REQUIRE(ctx, fin_abi == nullptr || (stats != nullptr && fin_abi->counter != nullptr), "stem_fprop_bn: finalisation needs stats and a counter");
-  const BnFinal fin = bn_final_convert(fin_abi);
   MML_REQUIRE(ctx, B >= 1 && H >= 1 && W >= 1, "stem_fprop: bad dims");
   StemGeom g;
   MML_REQUIRE(ctx, stem_geom(B, H, W, &g), "stem: output width %d not supported (max 128)", (W - 1) / 2 + 1);
@@ -446,7 +444,7 @@ int mml_stem_fprop_bn(mml_ctx* ctx, const float* x, const float* mask, const flo
     MML_CHECK_CUDA(ctx, cudaFuncSetAttribute(stem_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWBytes));
     configured = true;
   }
-  stem_fprop_tc_kernel<<<stem_ctas(ctx, g.tiles, 3), kThreadsStem, kFBytes, (cudaStream_t)stream>>>(maps, x, mask, w, stats, fin, g);
+  stem_fprop_tc_kernel<<<stem_ctas(ctx, g.tiles, 3), kThreadsStem, kFBytes, (cudaStream_t)stream>>>(maps, x, mask, w, stats, g);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }

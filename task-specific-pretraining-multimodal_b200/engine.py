@@ -28,7 +28,7 @@ from ._lib import MMLError
 BF16 = torch.bfloat16
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
-STAT_SLOTS = 16  # MML_BN_STAT_SLOTS
+STAT_SLOTS = 1  # one fp64 (sum, sum of squares) pair per channel and BatchNorm
 ALIGN = 64  # elements; 256 B for fp32, 128 B for bf16 (TMA base alignment)
 
 
@@ -266,7 +266,7 @@ class FlatState:
 # per-encoder plan
 # =====================================================================================================================
 class _BN(ops.BNBuffers):
-    __slots__ = ("C", "bstat", "dgamma", "dbeta")
+    __slots__ = ("C", "scale", "shift", "bstat", "dgamma", "dbeta")
 
     def __init__(self):  # filled field by field in EncoderPlan._bn
         pass
@@ -288,13 +288,9 @@ class EncoderPlan:
         self.taps: Dict[str, torch.Tensor] = {}  # stored intermediates by name (NHWC bf16), for tests / inspection
         self.wgrad_stream: Optional[torch.cuda.Stream] = None  # set by the step plan
         self.wgrad_ws = ops.WgradScratch(dev)  # split partial sums of THIS encoder's weight-gradient launches (one stream)
-        bns = [m for m in enc.modules() if isinstance(m, nn.BatchNorm2d)]
-        n_stat = STAT_SLOTS * 4 * sum(m.num_features for m in bns)
+        n_stat = STAT_SLOTS * 4 * sum(m.num_features for m in enc.modules() if isinstance(m, nn.BatchNorm2d))
         self.stat_arena = torch.zeros(n_stat, device=dev, dtype=torch.float64)  # zeroed once per step
         self._stat_off = 0
-        # ticket counters of the last-CTA finalisations (one per BatchNorm; self-resetting, zeroed only here)
-        self.counters = torch.zeros(len(bns) + 1, device=dev, dtype=torch.int32)
-        self._n_bn = 0
         self._build(train)
 
     # -- helpers -----------------------------------------------------------------------------------------------
@@ -311,10 +307,6 @@ class EncoderPlan:
         o = fs.buf_offsets[f"{self.prefix}{name}.running_var"]
         bn.rvar = fs.S[o:o + C]
         bn.scale, bn.shift, bn.mean, bn.invstd = (torch.zeros(C, device=dev) for _ in range(4))
-        bn.coef = torch.zeros(2, C, device=dev)
-        bn.counter = self.counters[self._n_bn:self._n_bn + 1]
-        self._n_bn += 1
-        bn._fin = None
         # fp64 accumulators: forward (sum x, sum x^2) filled by the conv epilogue, backward (sum g, sum g*xhat)
         o = self._stat_off
         n = STAT_SLOTS * 2 * C
@@ -358,12 +350,11 @@ class EncoderPlan:
         bn0 = self._bn("bn1", 64)
         rows0 = B * P0 * Q0
         x, mask = self.x, self.mask
-        fin0 = ops.bn_final(bn0, rows0, BN_MOMENTUM, BN_EPS)
-        F.append(lambda: ops.stem_fprop(x, mask, w_stem, raw0, bn0.stats, fin0))  # its last CTA finalises bn0.scale / shift
-        F.append(lambda: ops.stem_bn_pool_fwd(raw0, bn0.scale, bn0.shift, pool, amax, B, P0, Q0, 64))
+        F.append(lambda: ops.stem_fprop(x, mask, w_stem, raw0, bn0.stats))
+        F.append(lambda: ops.stem_bn_pool_fwd(raw0, bn0, None, None, pool, amax, B, P0, Q0, 64, True, BN_MOMENTUM, BN_EPS))
         E.append(lambda: ops.stem_fprop(x, mask, w_stem, raw0, None))
         E.append(lambda: ops.bn_eval_coeffs(64, bn0.gamma, bn0.beta, bn0.rmean, bn0.rvar, BN_EPS, bn0.scale, bn0.shift))
-        E.append(lambda: ops.stem_bn_pool_fwd(raw0, bn0.scale, bn0.shift, pool, amax, B, P0, Q0, 64))
+        E.append(lambda: ops.stem_bn_pool_fwd(raw0, bn0, bn0.scale, bn0.shift, pool, amax, B, P0, Q0, 64, False))
         # backward of the stem is emitted last (see end of _build); needs the two gradients of `pool`
         cur, curH, curW, curC = pool, P1, Q1, 64
         grads_of_cur: List[Optional[torch.Tensor]] = [None, None]  # filled by the first block's backward
@@ -396,21 +387,16 @@ class EncoderPlan:
             bnd_ = bnd if has_ds else None
             rawd_ = rawd if has_ds else None
 
-            # training mode: every conv's last CTA turns its statistics into (scale, shift), saves mean / invstd and updates the
-            # running statistics, so BatchNorm-apply is the same coefficient-form kernel as in eval mode
-            fin1, fin2 = ops.bn_final(bn1, rows, BN_MOMENTUM, BN_EPS), ops.bn_final(bn2, rows, BN_MOMENTUM, BN_EPS)
-            find = ops.bn_final(bnd, rows, BN_MOMENTUM, BN_EPS) if has_ds else None
-
             def fwd_train(g1=g1, g2=g2, xin=xin, w1=w1, w2=w2, raw1=raw1, a1=a1, raw2=raw2, out=out, bn1=bn1, bn2=bn2, rows=rows, outC=outC,
-                          has_ds=has_ds, gd=gd if has_ds else None, wd=wd if has_ds else None, rawd=rawd_, bnd=bnd_, fin1=fin1, fin2=fin2, find=find):
-                steps = [lambda: ops.conv_fprop(g1, xin, w1, raw1, bn1.stats, fin1),
-                         lambda: ops.bn_act_fwd(raw1, bn1.scale, bn1.shift, None, None, None, a1, rows, outC, True),
-                         lambda: ops.conv_fprop(g2, a1, w2, raw2, bn2.stats, fin2)]
+                          has_ds=has_ds, gd=gd if has_ds else None, wd=wd if has_ds else None, rawd=rawd_, bnd=bnd_):
+                steps = [lambda: ops.conv_fprop(g1, xin, w1, raw1, bn1.stats),
+                         lambda: ops.bn_train_fwd(raw1, bn1, None, None, a1, rows, outC, True, BN_MOMENTUM, BN_EPS),
+                         lambda: ops.conv_fprop(g2, a1, w2, raw2, bn2.stats)]
                 if has_ds:
-                    steps.append(lambda: ops.conv_fprop(gd, xin, wd, rawd, bnd.stats, find))
-                    steps.append(lambda: ops.bn_act_fwd(raw2, bn2.scale, bn2.shift, rawd, bnd.scale, bnd.shift, out, rows, outC, True))
+                    steps.append(lambda: ops.conv_fprop(gd, xin, wd, rawd, bnd.stats))
+                    steps.append(lambda: ops.bn_train_fwd(raw2, bn2, rawd, bnd, out, rows, outC, True, BN_MOMENTUM, BN_EPS))
                 else:
-                    steps.append(lambda: ops.bn_act_fwd(raw2, bn2.scale, bn2.shift, xin, None, None, out, rows, outC, True))
+                    steps.append(lambda: ops.bn_train_fwd(raw2, bn2, xin, None, out, rows, outC, True, BN_MOMENTUM, BN_EPS))
                 return steps
 
             def fwd_eval(g1=g1, g2=g2, xin=xin, w1=w1, w2=w2, raw1=raw1, a1=a1, raw2=raw2, out=out, bn1=bn1, bn2=bn2, rows=rows, outC=outC,
@@ -446,19 +432,19 @@ class EncoderPlan:
                               ds=(gd, wdt, dwd, rawd, bnd, d_rawd, d_x_ds) if has_ds else None):
                     dy1, dy2 = out_grads
                     # bn2 (+ residual add + ReLU): pass 1 stores g once; every later consumer reads g instead of (dy1, dy2, out)
-                    ops.bn_bwd_reduce(dy1, dy2, out, raw2, bn2, bn2.bstat, g_skip, bn2.dgamma, bn2.dbeta, rows, outC, True)
-                    ops.bn_bwd_apply(g_skip, raw2, bn2, d_raw2, rows, outC)
+                    ops.bn_bwd_reduce(dy1, dy2, out, raw2, bn2.mean, bn2.invstd, bn2.bstat, g_skip, rows, outC, True)
+                    ops.bn_bwd_apply(g_skip, raw2, bn2.mean, bn2.invstd, bn2.gamma, bn2.bstat, bn2.dgamma, bn2.dbeta, d_raw2, rows, outC)
                     if has_ds:
                         gd_, wdt_, dwd_, rawd_, bnd_, d_rawd_, d_x_ds_ = ds
-                        ops.bn_bwd_reduce(g_skip, None, None, rawd_, bnd_, bnd_.bstat, None, bnd_.dgamma, bnd_.dbeta, rows, outC, False)
-                        ops.bn_bwd_apply(g_skip, rawd_, bnd_, d_rawd_, rows, outC)
+                        ops.bn_bwd_reduce(g_skip, None, None, rawd_, bnd_.mean, bnd_.invstd, bnd_.bstat, None, rows, outC, False)
+                        ops.bn_bwd_apply(g_skip, rawd_, bnd_.mean, bnd_.invstd, bnd_.gamma, bnd_.bstat, bnd_.dgamma, bnd_.dbeta, d_rawd_, rows, outC)
                         self._offload(lambda: ops.conv_wgrad(gd_, xin, d_rawd_, dwd_, self.wgrad_ws))
                         ops.conv_dgrad(gd_, d_rawd_, wdt_, d_x_ds_)
                     self._offload(lambda: ops.conv_wgrad(g2, a1, d_raw2, dw2, self.wgrad_ws))
                     ops.conv_dgrad(g2, d_raw2, w2t, d_a1)
                     # bn1 + ReLU (g overwrites d_a1 in place)
-                    ops.bn_bwd_reduce(d_a1, None, a1, raw1, bn1, bn1.bstat, d_a1, bn1.dgamma, bn1.dbeta, rows, outC, True)
-                    ops.bn_bwd_apply(d_a1, raw1, bn1, d_raw1, rows, outC)
+                    ops.bn_bwd_reduce(d_a1, None, a1, raw1, bn1.mean, bn1.invstd, bn1.bstat, d_a1, rows, outC, True)
+                    ops.bn_bwd_apply(d_a1, raw1, bn1.mean, bn1.invstd, bn1.gamma, bn1.bstat, bn1.dgamma, bn1.dbeta, d_raw1, rows, outC)
                     self._offload(lambda: ops.conv_wgrad(g1, xin, d_raw1, dw1, self.wgrad_ws))
                     ops.conv_dgrad(g1, d_raw1, w1t, d_x_main)
 
@@ -662,7 +648,7 @@ class _StepPlan:
     def run_train(self, own_dropout: bool) -> None:
         eng, fs = self.eng, self.eng.fs
         p = eng.dropout_p
-        # no fs.G.zero_(): every producer of a gradient (conv / stem weight gradients, BatchNorm finalisation, head) STORES its
+        # no fs.G.zero_(): every producer of a gradient (conv / stem weight gradients, BatchNorm backward, head) STORES its
         # result; the alignment padding between tensors is never written and stays zero
         self.audio.stat_arena.zero_()
         self.image.stat_arena.zero_()

@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from ._lib import BN1dBwdDesc, BN1dDesc, BNFinal, ConvGeom, Context, HeadGrads, HeadParams, MMLError
+from ._lib import BN1dBwdDesc, BN1dDesc, ConvGeom, Context, HeadGrads, HeadParams, MMLError
 
 BF16 = torch.bfloat16
 
@@ -57,12 +57,12 @@ def mask_apply(x: torch.Tensor, mask: torch.Tensor, want_reverse: bool = False):
 
 
 # ---- stem ----------------------------------------------------------------------------------------------------
-def stem_fprop(x, mask, w, y, stats, fin: "Optional[BNFinal]" = None) -> None:
-    """stats: fp64 [16, 64, 2] accumulator (zeroed by the caller) or None; fin: BatchNorm coefficients finalised by the kernel."""
+def stem_fprop(x, mask, w, y, stats) -> None:
+    """stats: fp64 [64, 2] accumulator (zeroed by the caller) or None."""
     ctx = _ctx(x)
     B, H, W = x.shape
-    ctx.check(ctx.lib.mml_stem_fprop_bn(ctx.handle, _p(x, torch.float32), _p(mask, torch.float32), _p(w, torch.float32), _p(y, BF16),
-                                        _p(stats, torch.float64), C.byref(fin) if fin is not None else None, B, H, W, _stream(x)), "stem_fprop")
+    ctx.check(ctx.lib.mml_stem_fprop(ctx.handle, _p(x, torch.float32), _p(mask, torch.float32), _p(w, torch.float32), _p(y, BF16),
+                                     _p(stats, torch.float64), B, H, W, _stream(x)), "stem_fprop")
 
 
 def stem_wgrad_workspace(x) -> int:
@@ -79,11 +79,11 @@ def stem_wgrad(x, mask, dy, dw, workspace) -> None:
 
 
 # ---- conv ----------------------------------------------------------------------------------------------------
-def conv_fprop(g: ConvGeom, x, w_krsc, y, stats=None, fin: "Optional[BNFinal]" = None) -> None:
-    """stats: fp64 [16, K, 2] accumulator of (sum, sum of squares) of y (zeroed by the caller) or None; fin: see ``bn_final``."""
+def conv_fprop(g: ConvGeom, x, w_krsc, y, stats=None) -> None:
+    """stats: fp64 [K, 2] accumulator of (sum, sum of squares) of y (zeroed by the caller) or None."""
     ctx = _ctx(x)
-    ctx.check(ctx.lib.mml_conv_fprop_bn(ctx.handle, C.byref(g), _p(x, BF16), _p(w_krsc, BF16), _p(y, BF16), _p(stats, torch.float64),
-                                        C.byref(fin) if fin is not None else None, _stream(x)), "conv_fprop")
+    ctx.check(ctx.lib.mml_conv_fprop(ctx.handle, C.byref(g), _p(x, BF16), _p(w_krsc, BF16), _p(y, BF16), _p(stats, torch.float64),
+                                     _stream(x)), "conv_fprop")
 
 
 def conv_dgrad(g: ConvGeom, dy, w_krsc, dx) -> None:
@@ -138,50 +138,22 @@ _WS_CACHE: dict = {}
 
 # ---- batch norm / activations / pooling ---------------------------------------------------------------------------
 class BNBuffers:
-    """Device buffers of one training-mode BatchNorm: fp64 stats, affine parameters, running and saved statistics, the
-    coefficient form (scale, shift) of the forward and (coef = mean g, mean g*xhat) of the backward, and the ticket counter of
-    the last-CTA finalisation."""
+    """Device pointers of one training-mode BatchNorm: fp64 stats, affine parameters, running and saved statistics."""
 
-    __slots__ = ("stats", "gamma", "beta", "rmean", "rvar", "mean", "invstd", "scale", "shift", "coef", "counter", "_fin")
+    __slots__ = ("stats", "gamma", "beta", "rmean", "rvar", "mean", "invstd")
 
-    def __init__(self, stats, gamma, beta, rmean, rvar, mean, invstd, scale=None, shift=None, coef=None, counter=None):
+    def __init__(self, stats, gamma, beta, rmean, rvar, mean, invstd):
         self.stats, self.gamma, self.beta, self.rmean, self.rvar, self.mean, self.invstd = stats, gamma, beta, rmean, rvar, mean, invstd
-        dev, Cn = gamma.device, gamma.numel()
-        self.scale = scale if scale is not None else torch.zeros(Cn, device=dev)
-        self.shift = shift if shift is not None else torch.zeros(Cn, device=dev)
-        self.coef = coef if coef is not None else torch.zeros(2, Cn, device=dev)
-        self.counter = counter if counter is not None else torch.zeros(1, device=dev, dtype=torch.int32)
-        self._fin = None
-
-
-def bn_final(bn: "BNBuffers", rows: int, momentum: float = 0.1, eps: float = 1e-5, update_running: bool = True) -> BNFinal:
-    """mml_bn_final for ``bn`` over ``rows`` values per channel (cached on the buffers object: the pointers are static)."""
-    f = BNFinal()
-    f.counter = bn.counter.data_ptr()
-    f.gamma, f.beta = bn.gamma.data_ptr(), bn.beta.data_ptr()
-    if update_running and bn.rmean is not None:
-        f.running_mean, f.running_var = bn.rmean.data_ptr(), bn.rvar.data_ptr()
-    f.save_mean, f.save_invstd = bn.mean.data_ptr(), bn.invstd.data_ptr()
-    f.scale, f.shift = bn.scale.data_ptr(), bn.shift.data_ptr()
-    f.inv_count = 1.0 / rows
-    f.unbias = rows / (rows - 1.0) if rows > 1 else 1.0
-    f.momentum, f.eps = momentum, eps
-    return f
-
-
-def bn_finalize(bn: "BNBuffers", rows: int, Cn: int, momentum=0.1, eps=1e-5) -> None:
-    """Stand-alone statistics -> coefficients (the fused step lets the producing conv / stem kernel do it)."""
-    ctx = _ctx(bn.gamma)
-    fin = bn_final(bn, rows, momentum, eps)
-    ctx.check(ctx.lib.mml_bn_finalize(ctx.handle, _p(bn.stats, torch.float64), C.byref(fin), Cn, _stream(bn.gamma)), "bn_finalize")
 
 
 def bn_train_fwd(x, bn: "BNBuffers", res, rbn, y, rows, Cn, relu, momentum=0.1, eps=1e-5) -> None:
-    """y = relu?(bn(x) [+ res | + rbn(res)]) with batch statistics from bn.stats (fp64 sums of a conv epilogue): finalise, then apply."""
-    bn_finalize(bn, rows, Cn, momentum, eps)
-    if rbn is not None:
-        bn_finalize(rbn, rows, Cn, momentum, eps)
-    bn_act_fwd(x, bn.scale, bn.shift, res, rbn.scale if rbn is not None else None, rbn.shift if rbn is not None else None, y, rows, Cn, relu)
+    """y = relu?(bn(x) [+ res | + rbn(res)]) with batch statistics taken from bn.stats (fp64 sums from the conv epilogue)."""
+    ctx = _ctx(x)
+    z = C.c_void_p(0)
+    r = (_p(rbn.stats, torch.float64), _p(rbn.gamma), _p(rbn.beta), _p(rbn.rmean), _p(rbn.rvar), _p(rbn.mean), _p(rbn.invstd)) if rbn is not None else (z,) * 7
+    ctx.check(ctx.lib.mml_bn_train_fwd(ctx.handle, _p(x, BF16), _p(bn.stats, torch.float64), _p(bn.gamma), _p(bn.beta), _p(bn.rmean), _p(bn.rvar),
+                                       _p(bn.mean), _p(bn.invstd), _p(res), *r, _p(y, BF16), rows, Cn, int(relu), float(momentum), float(eps),
+                                       _stream(x)), "bn_train_fwd")
 
 
 def bn_eval_coeffs(Cn, gamma, beta, rmean, rvar, eps, scale, shift) -> None:
@@ -196,19 +168,18 @@ def bn_act_fwd(x, scale, shift, res, rscale, rshift, y, rows, Cn, relu) -> None:
                                      int(relu), _stream(x)), "bn_act_fwd")
 
 
-def bn_bwd_reduce(dy1, dy2, y, x, bn: "BNBuffers", bstat, g_out, dgamma, dbeta, rows, Cn, relu) -> None:
-    """pass 1: g = (dy1 [+ dy2]) * (y > 0); bstat += (sum g, sum g*xhat); g_out (may alias dy1) = g; the last CTA writes bn.coef,
-    dgamma, dbeta."""
+def bn_bwd_reduce(dy1, dy2, y, x, mean, invstd, bstat, g_out, rows, Cn, relu) -> None:
+    """pass 1: g = (dy1 [+ dy2]) * (y > 0); bstat += (sum g, sum g*xhat); g_out (optional, may alias dy1) = g."""
     ctx = _ctx(dy1)
-    ctx.check(ctx.lib.mml_bn_bwd_reduce(ctx.handle, _p(dy1, BF16), _p(dy2), _p(y), _p(x, BF16), _p(bn.mean), _p(bn.invstd), _p(bstat, torch.float64),
-                                        _p(g_out), _p(bn.counter), _p(bn.coef), _p(dgamma), _p(dbeta), rows, Cn, int(relu), _stream(dy1)), "bn_bwd_reduce")
+    ctx.check(ctx.lib.mml_bn_bwd_reduce(ctx.handle, _p(dy1, BF16), _p(dy2), _p(y), _p(x, BF16), _p(mean), _p(invstd), _p(bstat, torch.float64),
+                                        _p(g_out), rows, Cn, int(relu), _stream(dy1)), "bn_bwd_reduce")
 
 
-def bn_bwd_apply(g, x, bn: "BNBuffers", dx, rows, Cn) -> None:
-    """pass 2: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); dx may alias g."""
+def bn_bwd_apply(g, x, mean, invstd, gamma, bstat, dgamma, dbeta, dx, rows, Cn) -> None:
+    """pass 2: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); dx may alias g; dgamma / dbeta written."""
     ctx = _ctx(g)
-    ctx.check(ctx.lib.mml_bn_bwd_apply(ctx.handle, _p(g, BF16), _p(x, BF16), _p(bn.mean), _p(bn.invstd), _p(bn.gamma), _p(bn.coef), _p(dx, BF16),
-                                       rows, Cn, _stream(g)), "bn_bwd_apply")
+    ctx.check(ctx.lib.mml_bn_bwd_apply(ctx.handle, _p(g, BF16), _p(x, BF16), _p(mean), _p(invstd), _p(gamma), _p(bstat, torch.float64), _p(dgamma),
+                                       _p(dbeta), _p(dx, BF16), rows, Cn, _stream(g)), "bn_bwd_apply")
 
 
 def maxpool_fwd(x, y, argmax, N, H, W, Cn) -> None:
@@ -221,18 +192,23 @@ def maxpool_bwd(dy, dy2, argmax, dx, N, H, W, Cn) -> None:
     ctx.check(ctx.lib.mml_maxpool3x3s2_bwd(ctx.handle, _p(dy, BF16), _p(dy2), _p(argmax, torch.uint8), _p(dx, BF16), N, H, W, Cn, _stream(dy)), "maxpool_bwd")
 
 
-def stem_bn_pool_fwd(x, scale, shift, y, argmax, N, H, W, Cn) -> None:
-    """y = maxpool3x3s2(relu(x*scale + shift)); scale / shift from the batch statistics (train) or the running ones (eval)."""
+def stem_bn_pool_fwd(x, bn: "BNBuffers", scale, shift, y, argmax, N, H, W, Cn, train: bool, momentum=0.1, eps=1e-5) -> None:
+    """y = maxpool3x3s2(relu(bn(x))); train: batch statistics from bn.stats, eval: precomputed scale / shift."""
     ctx = _ctx(x)
-    ctx.check(ctx.lib.mml_stem_bn_pool_fwd(ctx.handle, _p(x, BF16), _p(scale), _p(shift), _p(y, BF16), _p(argmax, torch.uint8), N, H, W, Cn,
+    z = C.c_void_p(0)
+    if train:
+        a = (_p(bn.stats, torch.float64), _p(bn.gamma), _p(bn.beta), _p(bn.rmean), _p(bn.rvar), _p(bn.mean), _p(bn.invstd), z, z)
+    else:
+        a = (z, _p(bn.gamma), _p(bn.beta), z, z, z, z, _p(scale), _p(shift))
+    ctx.check(ctx.lib.mml_stem_bn_pool_fwd(ctx.handle, _p(x, BF16), *a, _p(y, BF16), _p(argmax, torch.uint8), N, H, W, Cn, float(momentum), float(eps),
                                            _stream(x)), "stem_bn_pool_fwd")
 
 
 def stem_bn_pool_bwd(dy, dy2, argmax, x, bn: "BNBuffers", bstat, dgamma, dbeta, dx, N, H, W, Cn) -> None:
     ctx = _ctx(dy)
     ctx.check(ctx.lib.mml_stem_bn_pool_bwd(ctx.handle, _p(dy, BF16), _p(dy2), _p(argmax, torch.uint8), _p(x, BF16), _p(bn.mean), _p(bn.invstd),
-                                           _p(bn.gamma), _p(bn.beta), _p(bstat, torch.float64), _p(bn.counter), _p(bn.coef), _p(dgamma), _p(dbeta),
-                                           _p(dx, BF16), N, H, W, Cn, _stream(dy)), "stem_bn_pool_bwd")
+                                           _p(bn.gamma), _p(bn.beta), _p(bstat, torch.float64), _p(dgamma), _p(dbeta), _p(dx, BF16), N, H, W, Cn,
+                                           _stream(dy)), "stem_bn_pool_bwd")
 
 
 def avgpool_fwd(x, y, N, HW, Cn) -> None:
