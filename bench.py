@@ -566,7 +566,7 @@ def dominant_kernel_roofline(torch, ops, B, pk):
     x = torch.randn(N, H, W, C, device="cuda").to(torch.bfloat16)
     w = (torch.randn(K, 3, 3, C, device="cuda") * 0.05).to(torch.bfloat16)
     y = torch.empty(N, H, W, K, device="cuda", dtype=torch.bfloat16)
-    part = torch.zeros(K, 2, device="cuda", dtype=torch.float64)
+    part = ops.bn_stats_buffer(K, "cuda")
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > L2
     for _ in range(3):
         ops.conv_fprop(g, x, w, y, part)
@@ -619,10 +619,10 @@ def hbm_kernel_rooflines(torch, ops, B, pk):
         x = torch.randn(rows, Cn, device="cuda").to(torch.bfloat16)
         res = torch.randn(rows, Cn, device="cuda").to(torch.bfloat16)
         y = torch.empty_like(x)
-        stats = torch.zeros(Cn, 2, device="cuda", dtype=torch.float64)
+        stats = ops.bn_stats_buffer(Cn, "cuda")
         xf = x.float()
-        stats[:, 0] = xf.sum(0).double()
-        stats[:, 1] = (xf * xf).sum(0).double()
+        stats[0, :, 0] = xf.sum(0).double()
+        stats[0, :, 1] = (xf * xf).sum(0).double()
         f = lambda *sh: torch.zeros(*sh, device="cuda")
         bn = ops.BNBuffers(stats, torch.ones(Cn, device="cuda"), f(Cn), f(Cn), torch.ones(Cn, device="cuda"), f(Cn), torch.ones(Cn, device="cuda"))
         t = timeit(lambda: ops.bn_train_fwd(x, bn, res, None, y, rows, Cn, True))
@@ -632,7 +632,7 @@ def hbm_kernel_rooflines(torch, ops, B, pk):
         # BatchNorm backward of the same layer (two incoming gradients + ReLU mask): pass 1 reads dy1, dy2, y, x and stores g,
         # pass 2 reads g, x and stores dx -> 8 tensor passes of algorithmic traffic (round 1: 10)
         dy1, dy2, gbuf, dxb = (torch.randn(rows, Cn, device="cuda").to(torch.bfloat16) for _ in range(4))
-        bstat = torch.zeros(Cn, 2, device="cuda", dtype=torch.float64)
+        bstat = ops.bn_stats_buffer(Cn, "cuda")
         dg, db = f(Cn), f(Cn)
 
         def bn_bwd():

@@ -24,9 +24,11 @@ extern "C" {
 
 typedef struct mml_ctx mml_ctx;
 
-/* BatchNorm statistics accumulators are fp64 arrays [C][2] (sum, sum of squares), one per BatchNorm: producers (conv / stem
- * epilogues, the BN backward reduce) add their partial sums with fp64 atomics, every consumer derives its coefficients from
- * them.  The caller zeroes them once per step. */
+/* BatchNorm statistics accumulators are fp64 arrays [S][C][2] (sum, sum of squares), S = mml_bn_stat_slots(C) = clamp(1024 / C,
+ * 2, 16): producers (conv / stem epilogues, the BN backward reduce) add their partial sums with fp64 atomics into slot
+ * (CTA index % S) to spread the contention, every consumer sums the S slots (16 KB per BatchNorm whatever C is).  The caller
+ * zeroes them once per step. */
+int mml_bn_stat_slots(int C);
 
 enum mml_status {
   MML_OK = 0,
@@ -64,7 +66,7 @@ int mml_mask_apply_f32(mml_ctx*, const float* x, const float* mask, float* y, fl
 
 /* ---- a2/a3: ResNetEncoder stem -- models/msa/networks/resnet.py:137 conv1 (7x7, stride 2, pad 3, C_in = 1) ----- */
 /* x fp32 [B,H,W] (optionally multiplied by mask[b], same multiply as above), w fp32 [64][7][7] ->
- * y bf16 [B,P,Q,64]; stats (optional) fp64 [64][2] += (sum, sum of squares) of the stored y */
+ * y bf16 [B,P,Q,64]; stats (optional) fp64 [16][64][2] += (sum, sum of squares) of the stored y */
 int mml_stem_fprop(mml_ctx*, const float* x, const float* mask, const float* w, uint16_t* y, double* stats, int B, int H,
                    int W, void* stream);
 /* dw fp32 [64][49] = sum_{b,p,q} dy[b,p,q,k] * (x*mask)[b, 2p+r-3, 2q+s-3]  (overwrites dw) */
@@ -73,7 +75,7 @@ int mml_stem_wgrad(mml_ctx*, const float* x, const float* mask, const uint16_t* 
 int64_t mml_stem_wgrad_workspace(const mml_ctx*, int B, int H, int W);
 
 /* ---- a2-a4: 3x3 / 1x1 convolutions -- resnet.py:25,30,176 (nn.Conv2d fwd) and their autograd -------------------- */
-/* tcgen05 implicit GEMM.  fprop: y = conv(x, w); stats (optional) fp64 [K][2] += per-channel (sum, sum of squares) of y */
+/* tcgen05 implicit GEMM.  fprop: y = conv(x, w); stats (optional) fp64 [S][K][2] += per-channel (sum, sum of squares) of y */
 int mml_conv_fprop(mml_ctx*, const mml_conv_geom* g, const uint16_t* x, const uint16_t* w_krsc, uint16_t* y, double* stats,
                    void* stream);
 /* dgrad: dx [N,H,W,C] = conv_transpose(dy [N,P,Q,K], w); reads the SAME K,R,S,C weights as fprop (MN-major B operand) */
@@ -88,7 +90,7 @@ int64_t mml_conv_wgrad_workspace(const mml_ctx*, const mml_conv_geom* g); /* byt
 
 /* ---- a5: BatchNorm2d (train / eval) + ReLU + residual -- resnet.py:26,31,138,177 and BasicBlock.forward :37-54 --- */
 /* training mode, fused: y = relu?(bn(x) [+ res | + bn_r(res)]) with scale/shift derived in-kernel from the fp64 sums the conv
- * epilogue accumulated (stats [C][2]: 16 bytes per channel per CTA, no finalize launch); block 0 also saves mean / invstd for
+ * epilogue accumulated (stats [S][C][2]: 16 KB per CTA, no finalize launch); block 0 also saves mean / invstd for
  * backward and updates the running statistics (running = (1-m)*running + m*batch, unbiased var).  res NULL: none; rstats NULL:
  * identity residual; else the residual goes through its own training-mode BN (downsample path).  count == rows. */
 int mml_bn_train_fwd(mml_ctx*, const uint16_t* x, const double* stats, const float* gamma, const float* beta, float* running_mean,
@@ -102,7 +104,7 @@ int mml_bn_eval_coeffs(mml_ctx*, int C, const float* gamma, const float* beta, c
 int mml_bn_act_fwd(mml_ctx*, const uint16_t* x, const float* scale, const float* shift, const uint16_t* res,
                    const float* rscale, const float* rshift, uint16_t* y, int64_t rows, int C, int relu, void* stream);
 /* backward of y = relu?(bn(x) [+ r]):  g = (dy1 [+ dy2]) * (y > 0 if relu);
- * pass 1: bstat fp64 [C][2] += (sum g, sum g*xhat) (caller zeroes it per step); g_out (optional, may alias dy1) = g as bf16 -- it
+ * pass 1: bstat fp64 [S][C][2] += (sum g, sum g*xhat) (caller zeroes it per step); g_out (optional, may alias dy1) = g as bf16 -- it
  * is the gradient of an identity skip path and the input of pass 2 (which then reads 2 tensors instead of 4) */
 int mml_bn_bwd_reduce(mml_ctx*, const uint16_t* dy1, const uint16_t* dy2, const uint16_t* y, const uint16_t* x,
                       const float* mean, const float* invstd, double* bstat, uint16_t* g_out, int64_t rows, int C, int relu, void* stream);

@@ -54,6 +54,7 @@ P, I32, I64, F32, U64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
 # name -> (restype, argtypes); every symbol declared in include/mml_b200.h
 SIGNATURES = {
     "mml_version": (I32, []),
+    "mml_bn_stat_slots": (I32, [I32]),
     "mml_ctx_create": (I32, [I32, C.POINTER(P)]),
     "mml_ctx_destroy": (None, [P]),
     "mml_last_error": (C.c_char_p, [P]),

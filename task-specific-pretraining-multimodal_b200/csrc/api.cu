@@ -16,7 +16,13 @@ int mml_set_error(mml_ctx* ctx, int code, const char* fmt, ...) {
 
 extern "C" {
 
-int mml_version(void) { return 100; }
+int mml_version(void) { return 200; }
+
+int mml_bn_stat_slots(int C) {
+  if (C < 1) return 0;
+  const int s = 1024 / C;
+  return s < 2 ? 2 : (s > 16 ? 16 : s);
+}
 
 const char* mml_last_error(const mml_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
 

@@ -66,7 +66,7 @@ __global__ void mask_apply_kernel(const float* __restrict__ x, const float* __re
 //   y = relu?(x*scale + shift [+ res | + res*rscale + rshift])
 // ---------------------------------------------------------------------------------------------------------------
 struct BnTrain {
-  const double* stats;   // [C][2]
+  const double* stats;   // [stat_slots(C)][C][2]
   const float* gamma;
   const float* beta;
   float* running_mean;   // may be null
@@ -81,7 +81,7 @@ __device__ __forceinline__ void bn_prologue(const BnTrain& b, int C, double inv_
                                             float* s_shift) {
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     double sum, sq;
-    stat_load(b.stats, c, sum, sq);
+    stat_load(b.stats, C, c, sum, sq);
     const double mean = sum * inv_count;
     double var = sq * inv_count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -188,7 +188,7 @@ __device__ __forceinline__ void bn_bwd_block_reduce(const float (&sg)[8], const 
       a += sh[t][j];
       b += sh[t][8 + j];
     }
-    stat_add(bstat, o, a, b);
+    stat_add(bstat, C, blockIdx.x, o, a, b);
   }
 }
 
@@ -261,7 +261,7 @@ bn_bwd_apply_kernel(const uint16_t* __restrict__ g, const uint16_t* __restrict__
   const int C = c8 * 8;
   for (int c = threadIdx.x; c < C; c += kThreads) {
     double sg, sgx;
-    stat_load(bstat, c, sg, sgx);
+    stat_load(bstat, C, c, sg, sgx);
     s_k[c] = (float)sg * inv_count;          // mean(g)
     s_k[kMaxC + c] = (float)sgx * inv_count; // mean(g * xhat)
     if (blockIdx.x == 0) {

@@ -51,7 +51,7 @@ struct IgemmParams {
   int Hb, Nb;      // tile = {OutW, Hb, Nb}
   int valid_rows;  // OutW * Hb * Nb  (<= 128)
   int cout;
-  double* stats;  // [cout][2] (sum, sum of squares) of the stored output, accumulated with fp64 atomics; or nullptr
+  double* stats;  // [stat_slots(cout)][cout][2] (sum, sum of squares) of the stored output, fp64 atomics; or nullptr
   Tap taps[kMaxTaps];
 };
 
@@ -236,7 +236,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
         if (half == 0) {
           const float2 o = stat_scratch[c];
           // fp64 atomics: the summation order across CTAs then changes the result far below fp32 resolution
-          stat_add(p.stats, n_tile * BLOCK_N + ch * 64 + c, s + o.x, ss + o.y);
+          stat_add(p.stats, p.cout, m_tile, n_tile * BLOCK_N + ch * 64 + c, s + o.x, ss + o.y);
         }
       }
     }
@@ -538,8 +538,8 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
         if (eg < 32) {
           const float4 a = sc[eg], b2 = sc[eg + 32], c2 = sc[eg + 64], d2 = sc[eg + 96];
           const int c0 = ch * 64 + 2 * eg;
-          stat_add(p.stats, c0, a.x + b2.x + c2.x + d2.x, a.z + b2.z + c2.z + d2.z);
-          stat_add(p.stats, c0 + 1, a.y + b2.y + c2.y + d2.y, a.w + b2.w + c2.w + d2.w);
+          stat_add(p.stats, p.cout, 2 * (int)blockIdx.x + gi, c0, a.x + b2.x + c2.x + d2.x, a.z + b2.z + c2.z + d2.z);
+          stat_add(p.stats, p.cout, 2 * (int)blockIdx.x + gi, c0 + 1, a.y + b2.y + c2.y + d2.y, a.w + b2.w + c2.w + d2.w);
         }
       }
     }

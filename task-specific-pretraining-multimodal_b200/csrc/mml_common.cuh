@@ -218,18 +218,29 @@ __device__ __forceinline__ float mask_mul(float x, float m) {
   return r;
 }
 
-// BatchNorm statistics accumulators: fp64 [C][2] (sum, sum of squares) per BatchNorm, zeroed once per step by the caller.
-// Producers (conv / stem epilogues, the BN backward reduce) add with fp64 atomics -- persistent kernels accumulate over all their
-// tiles first, so an address sees at most a few hundred atomics per launch -- and every consumer CTA derives its coefficients from
-// C x 16 bytes.  (Round 1 spread the atomics over 16 slots; consumers then read 16x as much per CTA, which made the BatchNorm
-// kernels of the small, many-channel tensors L2-bound: 134 MB of slot reads in front of an 8 MB tensor.)
-__device__ __forceinline__ void stat_add(double* stats, int c, float a, float b) {
-  atomicAdd(stats + 2 * c, (double)a);
-  atomicAdd(stats + 2 * c + 1, (double)b);
+// BatchNorm statistics accumulators: fp64 [S][C][2] (sum, sum of squares) per BatchNorm, S = stat_slots(C), zeroed once per step
+// by the caller.  Producers (conv / stem epilogues, the BN backward reduce) add with fp64 atomics into slot (CTA index % S);
+// persistent kernels accumulate over all their tiles first.  Contended fp64 atomics on ONE address cost ~14 ns each on B200 (a
+// 98-CTA convolution finished 4 us later with a single slot), while every consumer CTA reads S x C x 16 bytes to derive its
+// coefficients (round 1: S = 16 for every C -> 128 KB per CTA at C = 512, 134 MB of L2 reads in front of an 8 MB tensor).
+// S = clamp(1024 / C, 2, 16) keeps the consumer side at 16 KB per BatchNorm: many slots where the producers have many CTAs (64
+// channels: large maps), few where they have few (512 channels: 4x4 / 1x1 maps).
+__host__ __device__ __forceinline__ int stat_slots(int C) {
+  const int s = 1024 / C;
+  return s < 2 ? 2 : (s > 16 ? 16 : s);
 }
-__device__ __forceinline__ void stat_load(const double* stats, int c, double& a, double& b) {
-  const double2 v = __ldcg(reinterpret_cast<const double2*>(stats + 2 * c));
-  a = v.x, b = v.y;
+__device__ __forceinline__ void stat_add(double* stats, int C, int slot, int c, float a, float b) {
+  double* dst = stats + 2 * ((size_t)(slot % stat_slots(C)) * C + c);
+  atomicAdd(dst, (double)a);
+  atomicAdd(dst + 1, (double)b);
+}
+__device__ __forceinline__ void stat_load(const double* stats, int C, int c, double& a, double& b) {
+  a = 0.0, b = 0.0;
+  const int S = stat_slots(C);
+  for (int k = 0; k < S; ++k) {
+    const double2 v = __ldcg(reinterpret_cast<const double2*>(stats + 2 * ((size_t)k * C + c)));
+    a += v.x, b += v.y;
+  }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

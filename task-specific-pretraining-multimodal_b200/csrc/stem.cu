@@ -269,8 +269,8 @@ stem_fprop_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
       if (threadIdx.x < 32) {
         const float4 a = sc[threadIdx.x], b2 = sc[threadIdx.x + 32], c2 = sc[threadIdx.x + 64], d2 = sc[threadIdx.x + 96];
         const int c0 = 2 * threadIdx.x;
-        stat_add(stats, c0, a.x + b2.x + c2.x + d2.x, a.z + b2.z + c2.z + d2.z);
-        stat_add(stats, c0 + 1, a.y + b2.y + c2.y + d2.y, a.w + b2.w + c2.w + d2.w);
+        stat_add(stats, 64, (int)blockIdx.x, c0, a.x + b2.x + c2.x + d2.x, a.z + b2.z + c2.z + d2.z);
+        stat_add(stats, 64, (int)blockIdx.x, c0 + 1, a.y + b2.y + c2.y + d2.y, a.w + b2.w + c2.w + d2.w);
       }
     }
     if (threadIdx.x == 0) tma_store_wait_all<0>();

@@ -28,7 +28,6 @@ from ._lib import MMLError
 BF16 = torch.bfloat16
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
-STAT_SLOTS = 1  # one fp64 (sum, sum of squares) pair per channel and BatchNorm
 ALIGN = 64  # elements; 256 B for fp32, 128 B for bf16 (TMA base alignment)
 
 
@@ -288,7 +287,7 @@ class EncoderPlan:
         self.taps: Dict[str, torch.Tensor] = {}  # stored intermediates by name (NHWC bf16), for tests / inspection
         self.wgrad_stream: Optional[torch.cuda.Stream] = None  # set by the step plan
         self.wgrad_ws = ops.WgradScratch(dev)  # split partial sums of THIS encoder's weight-gradient launches (one stream)
-        n_stat = STAT_SLOTS * 4 * sum(m.num_features for m in enc.modules() if isinstance(m, nn.BatchNorm2d))
+        n_stat = sum(4 * ops.bn_stat_slots(m.num_features) * m.num_features for m in enc.modules() if isinstance(m, nn.BatchNorm2d))
         self.stat_arena = torch.zeros(n_stat, device=dev, dtype=torch.float64)  # zeroed once per step
         self._stat_off = 0
         self._build(train)
@@ -309,7 +308,7 @@ class EncoderPlan:
         bn.scale, bn.shift, bn.mean, bn.invstd = (torch.zeros(C, device=dev) for _ in range(4))
         # fp64 accumulators: forward (sum x, sum x^2) filled by the conv epilogue, backward (sum g, sum g*xhat)
         o = self._stat_off
-        n = STAT_SLOTS * 2 * C
+        n = ops.bn_stat_slots(C) * 2 * C
         self._stat_off += 2 * n
         bn.stats = self.stat_arena[o:o + n]
         bn.bstat = self.stat_arena[o + n:o + 2 * n]

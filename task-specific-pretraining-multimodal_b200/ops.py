@@ -36,6 +36,16 @@ def _p(t: Optional[torch.Tensor], dtype=None) -> C.c_void_p:
     return C.c_void_p(t.data_ptr())
 
 
+def bn_stat_slots(Cn: int) -> int:
+    """Slots of a BatchNorm statistics accumulator: fp64 [slots, C, 2] (mml_bn_stat_slots: clamp(1024 / C, 2, 16))."""
+    s = 1024 // Cn
+    return 2 if s < 2 else (16 if s > 16 else s)
+
+
+def bn_stats_buffer(Cn: int, device) -> torch.Tensor:
+    return torch.zeros(bn_stat_slots(Cn), Cn, 2, device=device, dtype=torch.float64)
+
+
 def conv_out_hw(H: int, W: int, R: int, S: int, stride: int, pad: int) -> Tuple[int, int]:
     return (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
 
@@ -58,7 +68,7 @@ def mask_apply(x: torch.Tensor, mask: torch.Tensor, want_reverse: bool = False):
 
 # ---- stem ----------------------------------------------------------------------------------------------------
 def stem_fprop(x, mask, w, y, stats) -> None:
-    """stats: fp64 [64, 2] accumulator (zeroed by the caller) or None."""
+    """stats: ``bn_stats_buffer(64)`` accumulator (zeroed by the caller) or None."""
     ctx = _ctx(x)
     B, H, W = x.shape
     ctx.check(ctx.lib.mml_stem_fprop(ctx.handle, _p(x, torch.float32), _p(mask, torch.float32), _p(w, torch.float32), _p(y, BF16),
@@ -80,7 +90,7 @@ def stem_wgrad(x, mask, dy, dw, workspace) -> None:
 
 # ---- conv ----------------------------------------------------------------------------------------------------
 def conv_fprop(g: ConvGeom, x, w_krsc, y, stats=None) -> None:
-    """stats: fp64 [K, 2] accumulator of (sum, sum of squares) of y (zeroed by the caller) or None."""
+    """stats: ``bn_stats_buffer(K)`` accumulator of (sum, sum of squares) of y (zeroed by the caller) or None."""
     ctx = _ctx(x)
     ctx.check(ctx.lib.mml_conv_fprop(ctx.handle, C.byref(g), _p(x, BF16), _p(w_krsc, BF16), _p(y, BF16), _p(stats, torch.float64),
                                      _stream(x)), "conv_fprop")

@@ -79,12 +79,13 @@ def test_fprop_and_stats(shape):
     geom = ops.make_geom(N, H, W, C, K, R, R, st, pad)
     P, Q = ops.conv_out_hw(H, W, R, R, st, pad)
     y = torch.full((N, P, Q, K), float("nan"), device="cuda", dtype=torch.bfloat16)
-    stats = torch.zeros(K, 2, device="cuda", dtype=torch.float64)
+    stats = ops.bn_stats_buffer(K, "cuda")
     ops.conv_fprop(geom, x, w, y, stats)
     torch.cuda.synchronize()
     ref = _ref_conv(x, w, st, pad).permute(0, 2, 3, 1)
     _report("fprop", y.float(), ref, 2.0 ** -7)
     yf = y.double().reshape(-1, K)
+    stats = stats.sum(0)
     assert torch.allclose(stats[:, 0], yf.sum(0), rtol=1e-5, atol=1e-3 * yf.abs().max().item()), "BN sum"
     assert torch.allclose(stats[:, 1], (yf * yf).sum(0), rtol=1e-5, atol=1e-4), "BN sum of squares"
 

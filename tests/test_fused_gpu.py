@@ -48,7 +48,7 @@ def test_stem_fprop_wgrad(B, H, W):
     w = torch.randn(64, 1, 7, 7, device="cuda", generator=gen(3)) * 0.2
     P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty(B, P, Q, 64, device="cuda", dtype=BF)
-    stats = torch.zeros(64, 2, device="cuda", dtype=torch.float64)
+    stats = ops.bn_stats_buffer(64, "cuda")
     ops.stem_fprop(x, m, w.view(64, 49).contiguous(), y, stats)
     # operands are rounded to bf16 by the kernel (after the exact fp32 mask multiply); accumulation is fp32
     xm = (x * m.view(-1, 1, 1)).to(BF).float()
@@ -58,6 +58,7 @@ def test_stem_fprop_wgrad(B, H, W):
     err = (y.float() - ref).abs().max().item()
     assert err <= 2.0 ** -8 * ref.abs().max().item() + 1e-5, err
     yf = y.double().reshape(-1, 64)
+    stats = stats.sum(0)
     assert torch.allclose(stats[:, 0], yf.sum(0), rtol=1e-5, atol=1e-3)
     assert torch.allclose(stats[:, 1], (yf * yf).sum(0), rtol=1e-5, atol=1e-3)
     # wgrad
@@ -83,7 +84,9 @@ def test_bn_forward_backward(rows, C):
 
     def mk(src):  # what a conv epilogue accumulates: fp64 (sum, sum of squares) of the stored values
         sd = src.double()
-        st = torch.stack([sd.sum(0), (sd * sd).sum(0)], 1).contiguous()
+        st = ops.bn_stats_buffer(C, "cuda")
+        st[0] = torch.stack([sd.sum(0), (sd * sd).sum(0)], 1) * 0.25   # spread over slots like concurrent CTAs would
+        st[-1] = torch.stack([sd.sum(0), (sd * sd).sum(0)], 1) * 0.75
         return ops.BNBuffers(st, gamma, beta, torch.zeros(C, device="cuda"), torch.ones(C, device="cuda"), torch.empty(C, device="cuda"), torch.empty(C, device="cuda"))
 
     bn = mk(xf)
@@ -121,7 +124,7 @@ def test_bn_forward_backward(rows, C):
     dy2 = torch.randn(rows, C, device="cuda", generator=gen(10)).to(BF)
     gin = (dy1.float() + dy2.float()) * (y.float() > 0).float()
     (bnref * gin).sum().backward()  # d/dx of bn with upstream gradient gin (relu mask applied explicitly)
-    bstat = torch.zeros(C, 2, device="cuda", dtype=torch.float64)
+    bstat = ops.bn_stats_buffer(C, "cuda")
     dgamma, dbeta = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
     dx, gout = torch.empty(rows, C, device="cuda", dtype=BF), torch.empty(rows, C, device="cuda", dtype=BF)
     ops.bn_bwd_reduce(dy1, dy2, y, x, bn.mean, bn.invstd, bstat, gout, rows, C, True)  # pass 1 stores g, pass 2 reads it
@@ -176,7 +179,8 @@ def test_stem_bn_relu_maxpool_fused(N, H, W):
     gamma = torch.rand(C, device="cuda", generator=gen(61)) + 0.5
     beta = torch.randn(C, device="cuda", generator=gen(62)) * 0.2
     xd = x.double().reshape(-1, C)
-    st = torch.stack([xd.sum(0), (xd * xd).sum(0)], 1).contiguous()
+    st = ops.bn_stats_buffer(C, "cuda")
+    st[1] = torch.stack([xd.sum(0), (xd * xd).sum(0)], 1)
     bn = ops.BNBuffers(st, gamma, beta, torch.zeros(C, device="cuda"), torch.ones(C, device="cuda"), torch.empty(C, device="cuda"), torch.empty(C, device="cuda"))
     P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty(N, P, Q, C, device="cuda", dtype=BF)
@@ -193,7 +197,7 @@ def test_stem_bn_relu_maxpool_fused(N, H, W):
     dy1 = torch.randn(N, P, Q, C, device="cuda", generator=gen(63)).to(BF)
     dy2 = torch.randn(N, P, Q, C, device="cuda", generator=gen(64)).to(BF)
     ref.backward((dy1.float() + dy2.float()).permute(0, 3, 1, 2))
-    bstat = torch.zeros(C, 2, device="cuda", dtype=torch.float64)
+    bstat = ops.bn_stats_buffer(C, "cuda")
     dgamma, dbeta = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
     dx = torch.empty(N, H, W, C, device="cuda", dtype=BF)
     ops.stem_bn_pool_bwd(dy1, dy2, am, x, bn, bstat, dgamma, dbeta, dx, N, H, W, C)

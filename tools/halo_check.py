@@ -20,7 +20,7 @@ def run(shape):
     dy = torch.randn(N, H, W, K, device="cuda", generator=g).to(BF)
     geom = ops.make_geom(N, H, W, C, K, 3, 3, 1, 1)
     y = torch.full((N, H, W, K), float("nan"), device="cuda", dtype=BF)
-    stats = torch.zeros(K, 2, device="cuda", dtype=torch.float64)
+    stats = ops.bn_stats_buffer(K, "cuda")
     ops.conv_fprop(geom, x, w, y, stats)
     dx = torch.full((N, H, W, C), float("nan"), device="cuda", dtype=BF)
     ops.conv_dgrad(geom, dy, w, dx)
@@ -31,7 +31,7 @@ def run(shape):
     e1 = (y.float() - ref.detach().permute(0, 2, 3, 1)).abs().max().item() / ref.abs().max().item()
     e2 = (dx.float() - xr.grad.permute(0, 2, 3, 1)).abs().max().item() / xr.grad.abs().max().item()
     yf = y.double().reshape(-1, K)
-    st = stats
+    st = stats.sum(0)
     e3 = ((st[:, 0] - yf.sum(0)).abs().max() / (yf.abs().sum(0).max() + 1e-9)).item()
     e4 = ((st[:, 1] - (yf * yf).sum(0)).abs().max() / (yf * yf).sum(0).max()).item()
     return e1, e2, e3, e4

@@ -35,7 +35,7 @@ def stem(B, H, W):
     w = torch.randn(64, 49, device="cuda") * 0.1
     P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty(B, P, Q, 64, device="cuda", dtype=BF)
-    st = torch.zeros(64, 2, device="cuda", dtype=torch.float64)
+    st = ops.bn_stats_buffer(64, "cuda")
     dy = torch.randn(B, P, Q, 64, device="cuda").to(BF)
     ws = torch.empty(ops.stem_wgrad_workspace(x) // 4, device="cuda")
     dw = torch.empty(64, 49, device="cuda")
@@ -51,7 +51,7 @@ def conv(N, H, W, C, K, R, st, pad, tag=""):
     dy = torch.randn(N, P, Q, K, device="cuda").to(BF)
     dx = torch.empty(N, H, W, C, device="cuda", dtype=BF)
     dw = torch.zeros(K, R, R, C, device="cuda")
-    stt = torch.zeros(K, 2, device="cuda", dtype=torch.float64)
+    stt = ops.bn_stats_buffer(K, "cuda")
     fl = 2.0 * N * P * Q * K * C * R * R
     tf = timeit(lambda: ops.conv_fprop(g, x, w, y, stt))
     td = timeit(lambda: ops.conv_dgrad(g, dy, w, dx))

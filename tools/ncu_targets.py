@@ -22,7 +22,7 @@ def conv_case(N, H, W, C, K, R, st, pad):
     dy = torch.randn(N, P, Q, K, device="cuda").to(BF)
     dx = torch.empty(N, H, W, C, device="cuda", dtype=BF)
     dw = torch.zeros(K, R, R, C, device="cuda")
-    stt = torch.zeros(K, 2, device="cuda", dtype=torch.float64)
+    stt = ops.bn_stats_buffer(K, "cuda")
     return dict(fprop=lambda: ops.conv_fprop(g, x, w, y, stt), dgrad=lambda: ops.conv_dgrad(g, dy, w, dx), wgrad=lambda ws=ops.WgradScratch("cuda"): ops.conv_wgrad(g, x, dy, dw, ws))
 
 
@@ -31,11 +31,11 @@ def bn_case(rows, Cn):
     res = torch.randn(rows, Cn, device="cuda").to(BF)
     y = torch.empty_like(x)
     dy, dy2, dx, gs = (torch.randn(rows, Cn, device="cuda").to(BF) for _ in range(4))
-    stats = torch.zeros(Cn, 2, device="cuda", dtype=torch.float64)
+    stats = ops.bn_stats_buffer(Cn, "cuda")
     xf = x.float()
-    stats[:, 0] = xf.sum(0).double()
-    stats[:, 1] = (xf * xf).sum(0).double()
-    bstat = torch.zeros(Cn, 2, device="cuda", dtype=torch.float64)
+    stats[0, :, 0] = xf.sum(0).double()
+    stats[0, :, 1] = (xf * xf).sum(0).double()
+    bstat = ops.bn_stats_buffer(Cn, "cuda")
     f = lambda *sh: torch.zeros(*sh, device="cuda")
     bn = ops.BNBuffers(stats, torch.ones(Cn, device="cuda"), f(Cn), f(Cn), torch.ones(Cn, device="cuda"), f(Cn), torch.ones(Cn, device="cuda"))
     dg, db = f(Cn), f(Cn)
@@ -50,7 +50,7 @@ def stem_case(H, W):
     w = torch.randn(64, 49, device="cuda") * 0.1
     P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty(B, P, Q, 64, device="cuda", dtype=BF)
-    st = torch.zeros(64, 2, device="cuda", dtype=torch.float64)
+    st = ops.bn_stats_buffer(64, "cuda")
     dy = torch.randn(B, P, Q, 64, device="cuda").to(BF)
     ws = torch.empty(ops.stem_wgrad_workspace(x) // 4, device="cuda")
     dw = torch.empty(64, 49, device="cuda")
