@@ -52,6 +52,10 @@ struct IgemmParams {
   int valid_rows;  // OutW * Hb * Nb  (<= 128)
   int cout;
   double* stats;  // [stat_slots(cout)][cout][2] (sum, sum of squares) of the stored output, fp64 atomics; or nullptr
+  // split-K variant only: the output view as plain addresses (its epilogue stores rows directly instead of through TMA)
+  uint8_t* out_base;
+  long long out_sw, out_sh, out_sn;  // byte strides of the output view along W, H, N
+  int out_w, out_n;                  // view extents (Wb == out_w)
   Tap taps[kMaxTaps];
 };
 
@@ -245,6 +249,192 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if (warp == 1) tmem_dealloc<BLOCK_N>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// split-K variant for grids far below one wave (the ResNet34 image encoder on 4x4 / 2x2 / 1x1 maps: 8..32 pixel tiles).
+// A tap-shifted GEMM CTA streams (128 + BLOCK_N) x 128 bytes per 64-deep K step from L2, and ONE SM sustains only ~45 B/clk of
+// that (measured: 16 CTAs x 1.2 MB each = 15 us for 1.2 GFLOP).  Here the (tap, channel-chunk) iterations of an output tile are
+// split over the S CTAs of a thread-block cluster; every CTA accumulates its share in TMEM, parks the fp32 partial tile in its own
+// shared memory, and after a cluster barrier each CTA sums a 128/S-row slice of the tile over all S partials through distributed
+// shared memory IN A FIXED ORDER (deterministic, no atomics, no workspace), rounds to bf16, stores the rows and adds the BatchNorm
+// partials of what it stored.  grid = (S, pixel tiles, channel tiles), cluster = (S, 1, 1).
+// ------------------------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int STAGES, bool B_MN>
+__global__ void __launch_bounds__(192, 1)
+conv_igemm_splitk_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
+  using L = IgemmSmem<BLOCK_N, STAGES>;
+  static_assert(STAGES * L::kStage >= 128 * BLOCK_N * 4 + 4096, "the fp32 partial tile + statistics scratch reuse the operand stages");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t bars = smem_base + L::kOffBars;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 1);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kOffBars + 8 * (2 * STAGES + 1));
+
+  const int S = (int)gridDim.x;  // == cluster size
+  const int rank = (int)cluster_ctarank();
+  const int m_tile = blockIdx.y;
+  const int n_tile = blockIdx.z;
+  const int n_blk = m_tile / p.tiles_h;
+  const int h_blk = m_tile - n_blk * p.tiles_h;
+  const int a0 = h_blk * p.Hb;
+  const int n0 = n_blk * p.Nb;
+  const int iters_total = p.num_taps * p.c_chunks;
+  const int it_beg = (iters_total * rank) / S, it_end = (iters_total * (rank + 1)) / S;  // host guarantees S <= iters_total
+  const int iters = it_end - it_beg;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.w);
+    tma_prefetch_desc(&maps.in[0]);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<BLOCK_N>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t tx_bytes = (uint32_t)p.valid_rows * 128u + (uint32_t)L::kB;
+      for (int i = 0; i < iters; ++i) {
+        const int it = it_beg + i;
+        const int t = it / p.c_chunks, cc = it - t * p.c_chunks;
+        const Tap tap = p.taps[t];
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_arrive_expect_tx(full_bar(s), tx_bytes);
+        const uint32_t a_dst = smem_base + s * L::kStage;
+        tma_load_4d(&maps.in[tap.map], full_bar(s), a_dst, cc * 64, tap.dw, a0 + tap.dh, n0);
+        if (!B_MN) {
+          tma_load_2d(&maps.w, full_bar(s), a_dst + L::kA, tap.widx * p.w_tap_stride + cc * 64, n_tile * BLOCK_N);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_2d(&maps.w, full_bar(s), a_dst + L::kA + j * 8192, tap.widx * p.w_tap_stride + n_tile * BLOCK_N + j * 64, cc * 64);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, B_MN ? 1 : 0);
+      constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
+      constexpr uint32_t kLoB = B_MN ? ((8192u >> 4) << 16) : (1u << 16);
+      constexpr uint32_t kBStep = B_MN ? (2048u >> 4) : 2u;
+      const uint32_t a_lo_base = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t b_lo_base = (((smem_base + L::kA) & 0x3FFFFu) >> 4) | kLoB;
+      for (int i = 0; i < iters; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_lo = a_lo_base + (uint32_t)s * (L::kStage >> 4);
+        const uint32_t b_lo = b_lo_base + (uint32_t)s * (L::kStage >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = ((uint64_t)kHi << 32) | (uint64_t)(a_lo + 2u * k);
+          const uint64_t db = ((uint64_t)kHi << 32) | (uint64_t)(b_lo + kBStep * k);
+          umma_bf16(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ---- phase A: this CTA's fp32 partial tile TMEM -> own shared memory, [128 rows][BLOCK_N] with the 16-byte chunk index
+    // XOR-swizzled by (row & 7) (conflict-free for the row-per-lane writes here and the chunk-per-lane reads of phase C).  All MMAs
+    // of this CTA have completed when tmem_full fires, so the operand stages are free.
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t prow = smem_base + (uint32_t)row * (uint32_t)(BLOCK_N * 4);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t c4 = (uint32_t)(c0 >> 2) + (uint32_t)j;
+        const uint32_t dst = prow + ((c4 ^ (uint32_t)(row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // every CTA's partial tile is complete and visible cluster-wide
+
+  if (warp >= 2) {
+    // ---- phase C: rows [rank*R, (rank+1)*R) of the tile, summed over the S partials in rank order
+    constexpr int CPR = BLOCK_N / 4;  // 16-byte chunks per row
+    constexpr int G = 128 / CPR;      // row groups handled concurrently by the 128 threads
+    const int et = threadIdx.x - 64;
+    const int c4 = et % CPR, rg = et / CPR;
+    const int R = 128 / S;
+    const int hw = p.Hb * p.out_w;
+    float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int rr = rg; rr < R; rr += G) {
+      const int tr = rank * R + rr;  // tile row
+      const uint32_t off = (uint32_t)tr * (uint32_t)(BLOCK_N * 4) + (((uint32_t)c4 ^ (uint32_t)(tr & 7)) << 4);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int sr = 0; sr < S; ++sr) {
+        const float4 v = ld_dsmem_f4(dsmem_addr(smem_base + off, (uint32_t)sr));
+        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+      }
+      const uint32_t lo = pack_bf16x2(acc.x, acc.y), hi = pack_bf16x2(acc.z, acc.w);
+      const int ni = tr / hw, rem = tr - ni * hw;
+      const int h = rem / p.out_w, w = rem - h * p.out_w;
+      if (tr < p.valid_rows && n0 + ni < p.out_n) {
+        uint8_t* dst = p.out_base + (long long)(n0 + ni) * p.out_sn + (long long)(a0 + h) * p.out_sh + (long long)w * p.out_sw +
+                       (long long)(n_tile * BLOCK_N + c4 * 4) * 2;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+        // BatchNorm partials of the STORED values (rows beyond the tensor are never stored and contribute nothing)
+        const float v0 = bf16_lo(lo), v1 = bf16_hi(lo), v2 = bf16_lo(hi), v3 = bf16_hi(hi);
+        s4[0] += v0, s4[1] += v1, s4[2] += v2, s4[3] += v3;
+        q4[0] = fmaf(v0, v0, q4[0]), q4[1] = fmaf(v1, v1, q4[1]), q4[2] = fmaf(v2, v2, q4[2]), q4[3] = fmaf(v3, v3, q4[3]);
+      }
+    }
+    if (p.stats != nullptr) {
+      // combine the G row groups through shared memory (scratch behind the partial tile), then one atomic pair per channel
+      float4* sc = reinterpret_cast<float4*>(smem_gen + 128 * BLOCK_N * 4);  // [G][CPR][2] float4
+      sc[(rg * CPR + c4) * 2] = make_float4(s4[0], s4[1], s4[2], s4[3]);
+      sc[(rg * CPR + c4) * 2 + 1] = make_float4(q4[0], q4[1], q4[2], q4[3]);
+      named_bar_sync(1, 128);
+      if (rg == 0) {
+        float4 a = sc[c4 * 2], b = sc[c4 * 2 + 1];
+#pragma unroll
+        for (int g2 = 1; g2 < G; ++g2) {
+          const float4 a2 = sc[(g2 * CPR + c4) * 2], b2 = sc[(g2 * CPR + c4) * 2 + 1];
+          a.x += a2.x, a.y += a2.y, a.z += a2.z, a.w += a2.w;
+          b.x += b2.x, b.y += b2.y, b.z += b2.z, b.w += b2.w;
+        }
+        const int cb = n_tile * BLOCK_N + c4 * 4;
+        const int slot = (int)blockIdx.y * S + rank;
+        stat_add(p.stats, p.cout, slot, cb, a.x, b.x);
+        stat_add(p.stats, p.cout, slot, cb + 1, a.y, b.y);
+        stat_add(p.stats, p.cout, slot, cb + 2, a.z, b.z);
+        stat_add(p.stats, p.cout, slot, cb + 3, a.w, b.w);
+      }
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();  // no CTA may exit (and release its shared memory) while a peer is still reading its partial tile
   if (warp == 1) tmem_dealloc<BLOCK_N>(tmem_base);
 }
 
@@ -1041,6 +1231,35 @@ int launch_igemm_t(mml_ctx* ctx, const IgemmMaps& maps, const IgemmParams& p, di
   return MML_OK;
 }
 
+template <int BLOCK_N, int STAGES, bool B_MN>
+int launch_igemm_splitk_t(mml_ctx* ctx, const IgemmMaps& maps, const IgemmParams& p, int S, int m_tiles, int n_tiles, cudaStream_t st) {
+  using L = IgemmSmem<BLOCK_N, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    int rc = set_smem_limit(ctx, conv_igemm_splitk_kernel<BLOCK_N, STAGES, B_MN>, L::kBytes);
+    if (rc) return rc;
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(S, m_tiles, n_tiles);
+  cfg.blockDim = dim3(192, 1, 1);
+  cfg.dynamicSmemBytes = L::kBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MML_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_igemm_splitk_kernel<BLOCK_N, STAGES, B_MN>, maps, p));
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
+int g_splitk_max = 4;  // largest cluster the split-K variant may use (mml_debug_set key 2; 1 disables it)
+
 // One "shifted GEMM" launch: out view <- sum over taps of in views @ weights.
 //   b_mn = false: w is [cout rows][n_wtaps*cin inner] bf16;   b_mn = true: w is [cin rows][n_wtaps*cout inner] bf16
 int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, int n_wtaps, int cin, int cout, const View& out,
@@ -1080,6 +1299,34 @@ int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, in
   p.cout = cout;
   p.stats = stats;
   for (int i = 0; i < num_taps; ++i) p.taps[i] = taps[i];
+  // grids far below one wave: split the K loop over a cluster (see conv_igemm_splitk_kernel).  The cluster size is capped
+  // (default 4) because a cluster needs that many free SMs in ONE GPC at the same time, which a concurrently running persistent
+  // kernel of another stream (the audio encoder) makes unlikely for large clusters.
+  {
+    const int tiles = tg.tiles_h * tg.tiles_n * (cout / block_n);
+    int S = 1;
+    for (int c = 2; c <= g_splitk_max && c <= 8; c *= 2)
+      if (tiles * c <= ctx->sm_count && c <= num_taps * p.c_chunks) S = c;
+    if (S > 1 && tiles * 2 <= ctx->sm_count) {
+      p.out_base = (uint8_t*)const_cast<void*>(out.base);
+      p.out_sw = out.strideW, p.out_sh = out.strideH, p.out_sn = out.strideN;
+      p.out_w = out.Wv, p.out_n = out.N;
+      const int mt = tg.tiles_h * tg.tiles_n, nt = cout / block_n;
+      if (!b_mn) {
+        switch (block_n) {
+          case 64: return launch_igemm_splitk_t<64, 3, false>(ctx, maps, p, S, mt, nt, st);
+          case 128: return launch_igemm_splitk_t<128, 4, false>(ctx, maps, p, S, mt, nt, st);
+          case 256: return launch_igemm_splitk_t<256, 3, false>(ctx, maps, p, S, mt, nt, st);
+        }
+      } else {
+        switch (block_n) {
+          case 64: return launch_igemm_splitk_t<64, 3, true>(ctx, maps, p, S, mt, nt, st);
+          case 128: return launch_igemm_splitk_t<128, 4, true>(ctx, maps, p, S, mt, nt, st);
+          case 256: return launch_igemm_splitk_t<256, 3, true>(ctx, maps, p, S, mt, nt, st);
+        }
+      }
+    }
+  }
   dim3 grid(tg.tiles_h * tg.tiles_n, cout / block_n);
   if (!b_mn) {
     switch (block_n) {
@@ -1239,9 +1486,10 @@ int launch_wgrad_t(mml_ctx* ctx, const WgradMaps& maps, const WgradParams& p, di
 
 extern "C" {
 
-/* experiment / A-B switch: key 1 = halo kernel enable (0/1) */
+/* experiment / A-B switches: key 1 = halo kernel enable (0/1), key 2 = largest split-K cluster (1 = off, 2, 4, 8) */
 int mml_debug_set(int key, int value) {
   if (key == 1) g_halo_enable = value;
+  else if (key == 2 && (value == 1 || value == 2 || value == 4 || value == 8)) g_splitk_max = value;
   else return MML_ERR_INVALID;
   return MML_OK;
 }

@@ -126,6 +126,37 @@ __device__ __forceinline__ void tma_store_wait_all() {
 }
 
 // --------------------------------------------------------------------------------------------
+// thread-block clusters / distributed shared memory
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+// every thread of every CTA of the cluster executes both halves (release: this CTA's shared-memory writes become visible to the
+// peers that acquire)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the location `cta_addr` (a shared::cta address of THIS CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cluster_addr) : "memory");
+  return v;
+}
+
+// --------------------------------------------------------------------------------------------
 // TMEM + tcgen05
 // --------------------------------------------------------------------------------------------
 template <int COLS>

@@ -133,3 +133,53 @@ def test_wgrad(shape):
     ops.conv_wgrad(geom, x, dy, dw2, ws)
     torch.cuda.synchronize()
     assert torch.equal(dw, dw2), "wgrad is not bit-reproducible"
+
+
+SPLITK_SHAPES = [
+    (256, 2, 2, 256, 256, 3, 1, 1),   # R34 layer3 at batch 256: 8 pixel tiles x 2 channel tiles
+    (256, 1, 1, 512, 512, 3, 1, 1),   # R34 layer4: one reachable tap, 8 K chunks
+    (130, 1, 1, 512, 512, 3, 1, 1),   # ragged batch: rows beyond the tensor are neither stored nor counted
+    (256, 4, 4, 128, 128, 3, 1, 1),   # R34 layer2
+    (6, 4, 4, 128, 256, 3, 2, 1),     # stride 2: dgrad writes strided phase views of dx
+    (40, 2, 2, 256, 512, 1, 2, 0),    # 1x1 stride-2 downsample: 4 K iterations only
+    (8, 7, 7, 256, 256, 3, 1, 1),
+    (5, 1, 3, 512, 512, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+@pytest.mark.parametrize("shape", SPLITK_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_splitk_cluster_variant(shape, cluster):
+    """conv_igemm_splitk_kernel (K loop split over a thread-block cluster, fixed-order DSMEM reduction) for every cluster size,
+    fprop + BatchNorm sums and dgrad, and bit-reproducibility of two runs."""
+    from mml_b200 import ops
+
+    N, H, W, C, K, R, st, pad = shape
+    x, w = _mk(shape, 21)
+    geom = ops.make_geom(N, H, W, C, K, R, R, st, pad)
+    P, Q = ops.conv_out_hw(H, W, R, R, st, pad)
+    g = torch.Generator(device="cuda").manual_seed(22)
+    dy = torch.randn(N, P, Q, K, device="cuda", generator=g).to(torch.bfloat16)
+    ops.debug_set(2, cluster)
+    try:
+        outs = []
+        for rep in range(2):
+            y = torch.full((N, P, Q, K), float("nan"), device="cuda", dtype=torch.bfloat16)
+            stats = ops.bn_stats_buffer(K, "cuda")
+            ops.conv_fprop(geom, x, w, y, stats)
+            dx = torch.full((N, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+            ops.conv_dgrad(geom, dy, w, dx)
+            torch.cuda.synchronize()
+            outs.append((y, dx, stats.sum(0)))
+    finally:
+        ops.debug_set(2, 4)
+    y, dx, stats = outs[0]
+    assert torch.equal(y, outs[1][0]) and torch.equal(dx, outs[1][1]), "not bit-reproducible"
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = torch.nn.functional.conv2d(xr, w.float().permute(0, 3, 1, 2), stride=st, padding=pad)
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    _report("fprop", y.float(), ref.detach().permute(0, 2, 3, 1), 2.0 ** -7)
+    _report("dgrad", dx.float(), xr.grad.permute(0, 2, 3, 1), 2.0 ** -7)
+    yf = y.double().reshape(-1, K)
+    assert torch.allclose(stats[:, 0], yf.sum(0), rtol=1e-5, atol=1e-3 * yf.abs().max().item()), "BN sum"
+    assert torch.allclose(stats[:, 1], (yf * yf).sum(0), rtol=1e-5, atol=1e-4), "BN sum of squares"
