@@ -57,7 +57,7 @@ int64_t mml_ctx_launch_count(const mml_ctx* ctx);
 int mml_ctx_set_sm_budget(mml_ctx* ctx, int sms);
 
 /* A-B switches for experiments (not part of the reference surface): key 1 = use the halo conv kernel (default 1); key 2 = largest
- * thread-block cluster of the split-K convolution variant (1 = off, 2, 4 (default), 8) */
+ * thread-block cluster of the split-K convolution variant (1 = off (default), 2, 4, 8) */
 int mml_debug_set(int key, int value);
 
 /* ---- a1: missing-modality mask -- data/base_dataset.py:70-72  sample[mod] = original * mask -------------------- */

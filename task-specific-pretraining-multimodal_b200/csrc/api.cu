@@ -1,4 +1,5 @@
 // api.cu -- context, error reporting and driver entry points of libmml_b200.so.
+#include <stdlib.h>
 #include <string.h>
 
 #include "mml_ctx.h"
@@ -63,6 +64,8 @@ int mml_ctx_create(int device, mml_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->encode_tiled = (mml_tmap_encode_tiled_fn)fn;
+  const char* pdl = getenv("MML_PDL");
+  ctx->pdl = (pdl != nullptr && pdl[0] == '0') ? 0 : 1;
   *out = ctx;
   return MML_OK;
 }

@@ -50,6 +50,7 @@ __device__ __forceinline__ uint4 ldg16(const uint16_t* p) { return __ldg(reinter
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void mask_apply_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ y,
                                   float* __restrict__ yrev, long long batch, long long per_sample) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   const long long total = batch * per_sample;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const float m = mask[i / per_sample];
@@ -103,6 +104,7 @@ __device__ __forceinline__ void bn_prologue(const BnTrain& b, int C, double inv_
 
 __global__ void bn_eval_coeffs_kernel(int C, const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
                                       float* scale, float* shift) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     const float sc = gamma[c] * rsqrtf(rv[c] + eps);
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(kThreads)
 bn_fwd_kernel(const uint16_t* __restrict__ x, BnTrain bn, const float* __restrict__ scale, const float* __restrict__ shift,
               const uint16_t* __restrict__ res, BnTrain rbn, const float* __restrict__ rscale, const float* __restrict__ rshift,
               uint16_t* __restrict__ y, long long n8, int c8, double inv_count, double unbias, float momentum, float eps) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   __shared__ __align__(16) float s_coef[TRAIN ? (RES == 2 ? 4 : 2) * kMaxC : 4];
   const long long stride = (long long)gridDim.x * kThreads;
   long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
@@ -197,6 +200,7 @@ __global__ void __launch_bounds__(kThreads)
 bn_bwd_reduce_kernel(const uint16_t* __restrict__ dy1, const uint16_t* __restrict__ dy2, const uint16_t* __restrict__ y,
                      const uint16_t* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
                      double* __restrict__ bstat, uint16_t* __restrict__ g_out, long long n8, int c8) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   __shared__ float sh[kThreads][17];
   const long long stride = (long long)gridDim.x * kThreads;
   long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
@@ -257,6 +261,7 @@ __global__ void __launch_bounds__(kThreads)
 bn_bwd_apply_kernel(const uint16_t* __restrict__ g, const uint16_t* __restrict__ x, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ gamma, const double* __restrict__ bstat, float inv_count,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, uint16_t* __restrict__ dx, long long n8, int c8) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   __shared__ __align__(16) float s_k[2 * kMaxC];
   const int C = c8 * 8;
   for (int c = threadIdx.x; c < C; c += kThreads) {
@@ -310,6 +315,7 @@ bn_bwd_apply_kernel(const uint16_t* __restrict__ g, const uint16_t* __restrict__
 __global__ void __launch_bounds__(kThreads)
 maxpool_fwd_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, uint8_t* __restrict__ amax, int N, int H, int W, int C,
                    int P, int Q) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   const int c8 = C >> 3;
   const long long total = (long long)N * P * Q * c8;
   for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
@@ -357,6 +363,7 @@ maxpool_fwd_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, uin
 __global__ void __launch_bounds__(kThreads)
 maxpool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__ dy2, const uint8_t* __restrict__ amax,
                    uint16_t* __restrict__ dx, int N, int H, int W, int C, int P, int Q) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   const int c8 = C >> 3;
   const int HB = (H + 1) >> 1, WB = (W + 1) >> 1;
   const long long total = (long long)N * HB * WB * c8;
@@ -433,6 +440,7 @@ __global__ void __launch_bounds__(kThreads)
 stem_bn_pool_fwd_kernel(const uint16_t* __restrict__ x, BnTrain bn, const float* __restrict__ scale_in, const float* __restrict__ shift_in,
                         uint16_t* __restrict__ y, uint8_t* __restrict__ amax, int N, int H, int W, int C, int P, int Q, double inv_count,
                         double unbias, float momentum, float eps) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   __shared__ __align__(16) float s_coef[2 * kMaxC];
   if (TRAIN) {
     bn_prologue(bn, C, inv_count, unbias, momentum, eps, s_coef, s_coef + kMaxC);
@@ -545,6 +553,7 @@ stem_bn_pool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restr
                         const uint16_t* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ gamma, const float* __restrict__ beta, double* __restrict__ bstat,
                         uint16_t* __restrict__ dx, int N, int H, int W, int C, int P, int Q) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   __shared__ float sh[kThreads][17];
   const int c8 = C >> 3;
   const int HB = (H + 1) >> 1, WB = (W + 1) >> 1;
@@ -606,6 +615,7 @@ stem_bn_pool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restr
 
 // AdaptiveAvgPool2d((1,1)) + flatten: [N, HW, C] bf16 -> [N, C] fp32
 __global__ void avgpool_fwd_kernel(const uint16_t* __restrict__ x, float* __restrict__ y, int N, int HW, int C) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   const int c8 = C >> 3;
   const long long total = (long long)N * c8;
   const float inv = 1.f / (float)HW;
@@ -627,6 +637,7 @@ __global__ void avgpool_fwd_kernel(const uint16_t* __restrict__ x, float* __rest
 }
 
 __global__ void avgpool_bwd_kernel(const float* __restrict__ dy, uint16_t* __restrict__ dx, int N, int HW, int C) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   const int c8 = C >> 3;
   const long long total = (long long)N * HW * c8;
   const float inv = 1.f / (float)HW;
@@ -677,8 +688,7 @@ int mml_mask_apply_f32(mml_ctx* ctx, const float* x, const float* mask, float* y
                        int64_t per_sample, void* stream) {
   MML_REQUIRE(ctx, ctx && x && mask && (y || y_reverse) && batch >= 0 && per_sample >= 0, "mask_apply: bad arguments");
   if (batch * per_sample == 0) return MML_OK;
-  mask_apply_kernel<<<ew_grid(ctx, batch * per_sample), kThreads, 0, (cudaStream_t)stream>>>(x, mask, y, y_reverse, batch, per_sample);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, mask_apply_kernel, ew_grid(ctx, batch * per_sample), kThreads, 0, (cudaStream_t)stream, x, mask, y, y_reverse, batch, per_sample);
   return MML_OK;
 }
 
@@ -700,7 +710,7 @@ int mml_bn_train_fwd(mml_ctx* ctx, const uint16_t* x, const double* stats, const
   const double unbias = rows > 1 ? (double)rows / (double)(rows - 1) : 1.0;
   cudaStream_t st = (cudaStream_t)stream;
 #define MML_TR(M, RL) \
-  bn_fwd_kernel<M, RL, true><<<grid, kThreads, 0, st>>>(x, bn, nullptr, nullptr, res, rbn, nullptr, nullptr, y, n8, C / 8, inv_count, unbias, momentum, eps)
+  MML_LAUNCH(ctx, (bn_fwd_kernel<M, RL, true>), grid, kThreads, 0, st, x, bn, nullptr, nullptr, res, rbn, nullptr, nullptr, y, n8, C / 8, inv_count, unbias, momentum, eps)
   switch (mode * 2 + (relu ? 1 : 0)) {
     case 0: MML_TR(0, false); break;
     case 1: MML_TR(0, true); break;
@@ -710,15 +720,13 @@ int mml_bn_train_fwd(mml_ctx* ctx, const uint16_t* x, const double* stats, const
     default: MML_TR(2, true); break;
   }
 #undef MML_TR
-  MML_LAUNCHED(ctx);
   return MML_OK;
 }
 
 int mml_bn_eval_coeffs(mml_ctx* ctx, int C, const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, float* scale, float* shift, void* stream) {
   MML_REQUIRE(ctx, ctx && gamma && beta && running_mean && running_var && scale && shift && C >= 1, "bn_eval_coeffs: bad arguments");
-  bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, running_mean, running_var, eps, scale, shift);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, bn_eval_coeffs_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream, C, gamma, beta, running_mean, running_var, eps, scale, shift);
   return MML_OK;
 }
 
@@ -734,7 +742,7 @@ int mml_bn_act_fwd(mml_ctx* ctx, const uint16_t* x, const float* scale, const fl
   const BnTrain none{};
   cudaStream_t st = (cudaStream_t)stream;
 #define MML_FWD(M, RL) \
-  bn_fwd_kernel<M, RL, false><<<grid, kThreads, 0, st>>>(x, none, scale, shift, res, none, rscale, rshift, y, n8, C / 8, 0.0, 0.0, 0.f, 0.f)
+  MML_LAUNCH(ctx, (bn_fwd_kernel<M, RL, false>), grid, kThreads, 0, st, x, none, scale, shift, res, none, rscale, rshift, y, n8, C / 8, 0.0, 0.0, 0.f, 0.f)
   switch (mode * 2 + (relu ? 1 : 0)) {
     case 0: MML_FWD(0, false); break;
     case 1: MML_FWD(0, true); break;
@@ -744,7 +752,6 @@ int mml_bn_act_fwd(mml_ctx* ctx, const uint16_t* x, const float* scale, const fl
     default: MML_FWD(2, true); break;
   }
 #undef MML_FWD
-  MML_LAUNCHED(ctx);
   return MML_OK;
 }
 
@@ -764,7 +771,7 @@ int mml_bn_bwd_reduce(mml_ctx* ctx, const uint16_t* dy1, const uint16_t* dy2, co
   const long long n8 = rows * (C / 8);
   const int grid = bn_bwd_grid(ctx, rows, C);
   cudaStream_t st = (cudaStream_t)stream;
-#define MML_RED(TW, RL, GO) bn_bwd_reduce_kernel<TW, RL, GO><<<grid, kThreads, 0, st>>>(dy1, dy2, y, x, mean, invstd, bstat, g_out, n8, C / 8)
+#define MML_RED(TW, RL, GO) MML_LAUNCH(ctx, (bn_bwd_reduce_kernel<TW, RL, GO>), grid, kThreads, 0, st, dy1, dy2, y, x, mean, invstd, bstat, g_out, n8, C / 8)
   const int key = (dy2 ? 4 : 0) | (relu ? 2 : 0) | (g_out ? 1 : 0);
   switch (key) {
     case 0: MML_RED(false, false, false); break;
@@ -777,7 +784,6 @@ int mml_bn_bwd_reduce(mml_ctx* ctx, const uint16_t* dy1, const uint16_t* dy2, co
     default: MML_RED(true, true, true); break;
   }
 #undef MML_RED
-  MML_LAUNCHED(ctx);
   return MML_OK;
 }
 
@@ -787,17 +793,15 @@ int mml_bn_bwd_apply(mml_ctx* ctx, const uint16_t* g, const uint16_t* x, const f
   int rc = check_rows_c(ctx, rows, C);
   if (rc) return rc;
   const long long n8 = rows * (C / 8);
-  bn_bwd_apply_kernel<<<stream_grid(ctx, n8, kU), kThreads, 0, (cudaStream_t)stream>>>(g, x, mean, invstd, gamma, bstat, 1.0f / (float)rows, dgamma, dbeta,
+  MML_LAUNCH(ctx, bn_bwd_apply_kernel, stream_grid(ctx, n8, kU), kThreads, 0, (cudaStream_t)stream, g, x, mean, invstd, gamma, bstat, 1.0f / (float)rows, dgamma, dbeta,
                                                                                        dx, n8, C / 8);
-  MML_LAUNCHED(ctx);
   return MML_OK;
 }
 
 int mml_maxpool3x3s2_fwd(mml_ctx* ctx, const uint16_t* x, uint16_t* y, uint8_t* argmax, int N, int H, int W, int C, void* stream) {
   MML_REQUIRE(ctx, ctx && x && y && argmax && N >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "maxpool_fwd: bad arguments");
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
-  maxpool_fwd_kernel<<<ew_grid(ctx, (long long)N * P * Q * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(x, y, argmax, N, H, W, C, P, Q);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, maxpool_fwd_kernel, ew_grid(ctx, (long long)N * P * Q * (C / 8)), kThreads, 0, (cudaStream_t)stream, x, y, argmax, N, H, W, C, P, Q);
   return MML_OK;
 }
 
@@ -805,9 +809,8 @@ int mml_maxpool3x3s2_bwd(mml_ctx* ctx, const uint16_t* dy, const uint16_t* dy2, 
                          int W, int C, void* stream) {
   MML_REQUIRE(ctx, ctx && dy && dx && argmax && N >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "maxpool_bwd: bad arguments");
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
-  maxpool_bwd_kernel<<<ew_grid(ctx, (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(dy, dy2, argmax, dx, N, H, W,
+  MML_LAUNCH(ctx, maxpool_bwd_kernel, ew_grid(ctx, (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8)), kThreads, 0, (cudaStream_t)stream, dy, dy2, argmax, dx, N, H, W,
                                                                                                                                    C, P, Q);
-  MML_LAUNCHED(ctx);
   return MML_OK;
 }
 
@@ -825,13 +828,12 @@ int mml_stem_bn_pool_fwd(mml_ctx* ctx, const uint16_t* x, const double* stats, c
   cudaStream_t st = (cudaStream_t)stream;
   if (stats) {
     MML_REQUIRE(ctx, gamma && beta && save_mean && save_invstd, "stem_bn_pool_fwd: null BN pointer");
-    stem_bn_pool_fwd_kernel<true><<<grid, kThreads, 0, st>>>(x, bn, nullptr, nullptr, y, argmax, N, H, W, C, P, Q, 1.0 / (double)rows,
+    MML_LAUNCH(ctx, stem_bn_pool_fwd_kernel<true>, grid, kThreads, 0, st, x, bn, nullptr, nullptr, y, argmax, N, H, W, C, P, Q, 1.0 / (double)rows,
                                                               rows > 1 ? (double)rows / (double)(rows - 1) : 1.0, momentum, eps);
   } else {
     MML_REQUIRE(ctx, shift != nullptr, "stem_bn_pool_fwd: shift is NULL");
-    stem_bn_pool_fwd_kernel<false><<<grid, kThreads, 0, st>>>(x, bn, scale, shift, y, argmax, N, H, W, C, P, Q, 0.0, 0.0, momentum, eps);
+    MML_LAUNCH(ctx, stem_bn_pool_fwd_kernel<false>, grid, kThreads, 0, st, x, bn, scale, shift, y, argmax, N, H, W, C, P, Q, 0.0, 0.0, momentum, eps);
   }
-  MML_LAUNCHED(ctx);
   return MML_OK;
 }
 
@@ -849,26 +851,22 @@ int mml_stem_bn_pool_bwd(mml_ctx* ctx, const uint16_t* dy, const uint16_t* dy2, 
   int g0 = (int)mml_ceil_div(items, (long long)kThreads * 2);
   if (g0 > ctx->sm_count * 4) g0 = ctx->sm_count * 4;
   if (g0 < 1) g0 = 1;
-  stem_bn_pool_bwd_kernel<<<g0, kThreads, 0, st>>>(dy, dy2, argmax, x, mean, invstd, gamma, beta, bstat, dx, N, H, W, C, P, Q);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, stem_bn_pool_bwd_kernel, g0, kThreads, 0, st, dy, dy2, argmax, x, mean, invstd, gamma, beta, bstat, dx, N, H, W, C, P, Q);
   // pass 2 in place over the buffer that now holds g: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))
   const long long n8 = (long long)N * H * W * (C / 8);
-  bn_bwd_apply_kernel<<<stream_grid(ctx, n8, kU), kThreads, 0, st>>>(dx, x, mean, invstd, gamma, bstat, inv_count, dgamma, dbeta, dx, n8, C / 8);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, bn_bwd_apply_kernel, stream_grid(ctx, n8, kU), kThreads, 0, st, dx, x, mean, invstd, gamma, bstat, inv_count, dgamma, dbeta, dx, n8, C / 8);
   return MML_OK;
 }
 
 int mml_avgpool_fwd(mml_ctx* ctx, const uint16_t* x, float* y, int N, int HW, int C, void* stream) {
   MML_REQUIRE(ctx, ctx && x && y && N >= 1 && HW >= 1 && C >= 8 && C % 8 == 0, "avgpool_fwd: bad arguments");
-  avgpool_fwd_kernel<<<ew_grid(ctx, (long long)N * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(x, y, N, HW, C);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, avgpool_fwd_kernel, ew_grid(ctx, (long long)N * (C / 8)), kThreads, 0, (cudaStream_t)stream, x, y, N, HW, C);
   return MML_OK;
 }
 
 int mml_avgpool_bwd(mml_ctx* ctx, const float* dy, uint16_t* dx, int N, int HW, int C, void* stream) {
   MML_REQUIRE(ctx, ctx && dy && dx && N >= 1 && HW >= 1 && C >= 8 && C % 8 == 0, "avgpool_bwd: bad arguments");
-  avgpool_bwd_kernel<<<ew_grid(ctx, (long long)N * HW * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(dy, dx, N, HW, C);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, avgpool_bwd_kernel, ew_grid(ctx, (long long)N * HW * (C / 8)), kThreads, 0, (cudaStream_t)stream, dy, dx, N, HW, C);
   return MML_OK;
 }
 

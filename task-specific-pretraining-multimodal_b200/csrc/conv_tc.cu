@@ -119,6 +119,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_sync();  // barriers, TMEM and tensor-map prefetch are set up; everything below touches memory earlier kernels produced
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -306,6 +307,7 @@ conv_igemm_splitk_kernel(const __grid_constant__ IgemmMaps maps, const IgemmPara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_sync();  // barriers, TMEM and tensor-map prefetch are set up; everything below touches memory earlier kernels produced
 
   if (warp == 0) {
     if (elect_one()) {
@@ -392,11 +394,15 @@ conv_igemm_splitk_kernel(const __grid_constant__ IgemmMaps maps, const IgemmPara
     for (int rr = rg; rr < R; rr += G) {
       const int tr = rank * R + rr;  // tile row
       const uint32_t off = (uint32_t)tr * (uint32_t)(BLOCK_N * 4) + (((uint32_t)c4 ^ (uint32_t)(tr & 7)) << 4);
+      // all S loads in flight before the first add (a distributed-shared-memory load takes ~200 cycles); summed in rank order
+      float4 v[8];
+#pragma unroll
+      for (int sr = 0; sr < 8; ++sr)
+        if (sr < S) v[sr] = ld_dsmem_f4(dsmem_addr(smem_base + off, (uint32_t)sr));
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int sr = 0; sr < S; ++sr) {
-        const float4 v = ld_dsmem_f4(dsmem_addr(smem_base + off, (uint32_t)sr));
-        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
-      }
+#pragma unroll
+      for (int sr = 0; sr < 8; ++sr)
+        if (sr < S) acc.x += v[sr].x, acc.y += v[sr].y, acc.z += v[sr].z, acc.w += v[sr].w;
       const uint32_t lo = pack_bf16x2(acc.x, acc.y), hi = pack_bf16x2(acc.z, acc.w);
       const int ni = tr / hw, rem = tr - ni * hw;
       const int h = rem / p.out_w, w = rem - h * p.out_w;
@@ -534,6 +540,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_sync();  // barriers, TMEM and tensor-map prefetch are set up; everything below touches memory earlier kernels produced
 
   auto load_w_stage = [&](int s, int cc, const Tap& tap, uint32_t bar) {
     const uint32_t dst = smem_base + L::kOffW + s * L::kWStage;
@@ -825,6 +832,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_sync();  // barriers, TMEM and tensor-map prefetch are set up; everything below touches memory earlier kernels produced
 
   if (warp == 0) {
     if (lane == 0) {
@@ -981,6 +989,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WHaloMaps maps, const WHaloParams
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_sync();  // barriers, TMEM and tensor-map prefetch are set up; everything below touches memory earlier kernels produced
 
   if (warp == 0) {
     if (elect_one()) {
@@ -1085,6 +1094,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WHaloMaps maps, const WHaloParams
 // dw[i] = sum over partials in a fixed order (deterministic; OVERWRITES dw).  Halo CH == 2: each grid.y slice wrote only its own filter row.
 // block = 32 elements (float4) x 8 partial slices; slices are combined through shared memory in a fixed order
 __global__ void __launch_bounds__(256) wgrad_partial_reduce_kernel(const float* __restrict__ ws, int parts, long long n, float* __restrict__ dw) {
+  pdl_sync();
   __shared__ float4 sh[8][33];
   const long long n4 = n >> 2;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -1121,6 +1131,7 @@ __global__ void __launch_bounds__(256) wgrad_partial_reduce_kernel(const float* 
 // the same for a layer whose filter taps do not all reach the input: only the taps the wgrad kernel wrote are summed (grid.y = tap)
 __global__ void __launch_bounds__(256) wgrad_tap_reduce_kernel(const float* __restrict__ ws, int parts, long long slab, float* __restrict__ dw, int K,
                                                                int RS, int C, const WgradParams p) {
+  pdl_sync();
   const int widx = p.taps[blockIdx.y].widx;
   const long long i = blockIdx.x * 256ll + threadIdx.x;  // float4 index over [K][C]
   if (i >= (long long)K * C / 4) return;
@@ -1226,8 +1237,7 @@ int launch_igemm_t(mml_ctx* ctx, const IgemmMaps& maps, const IgemmParams& p, di
     if (rc) return rc;
     configured = true;
   }
-  conv_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS, B_MN><<<grid, 192, L::kBytes, st>>>(maps, p);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, (conv_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS, B_MN>), grid, 192, L::kBytes, st, maps, p);
   return MML_OK;
 }
 
@@ -1246,19 +1256,21 @@ int launch_igemm_splitk_t(mml_ctx* ctx, const IgemmMaps& maps, const IgemmParams
   cfg.blockDim = dim3(192, 1, 1);
   cfg.dynamicSmemBytes = L::kBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = S;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = ctx->pdl ? 2 : 1;
   MML_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_igemm_splitk_kernel<BLOCK_N, STAGES, B_MN>, maps, p));
   MML_LAUNCHED(ctx);
   return MML_OK;
 }
 
-int g_splitk_max = 4;  // largest cluster the split-K variant may use (mml_debug_set key 2; 1 disables it)
+int g_splitk_max = 1;  // largest cluster the split-K variant may use (mml_debug_set key 2; 1 = off, the default: see DESIGN.md)
 
 // One "shifted GEMM" launch: out view <- sum over taps of in views @ weights.
 //   b_mn = false: w is [cout rows][n_wtaps*cin inner] bf16;   b_mn = true: w is [cin rows][n_wtaps*cout inner] bf16
@@ -1415,8 +1427,7 @@ int launch_halo_t(mml_ctx* ctx, const HaloMaps& maps, const HaloParams& p, cudaS
   }
   const int sms = persistent_sms(ctx);
   int grid = p.num_super < sms ? p.num_super : sms;
-  conv_halo_kernel<CCH, BLOCK_N, T, W_RES, B_MN><<<grid, kHaloThreads, L::kBytes, st>>>(maps, p);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, (conv_halo_kernel<CCH, BLOCK_N, T, W_RES, B_MN>), grid, kHaloThreads, L::kBytes, st, maps, p);
   return MML_OK;
 }
 
@@ -1460,11 +1471,9 @@ int launch_wgrad_halo_t(mml_ctx* ctx, const WHaloMaps& maps, WHaloParams& p, int
   }
   const long long n = (long long)L::kC * 9 * L::kC;
   dim3 grid(ctas, CH == 1 ? 1 : 3);
-  conv_wgrad_halo_kernel<CH><<<grid, 192, L::kBytes, st>>>(maps, p);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, conv_wgrad_halo_kernel<CH>, grid, 192, L::kBytes, st, maps, p);
   int rgrid = (int)mml_ceil_div(n / 4, 32);
-  wgrad_partial_reduce_kernel<<<rgrid, 256, 0, st>>>(p.ws, ctas, n, dw);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, wgrad_partial_reduce_kernel, rgrid, 256, 0, st, p.ws, ctas, n, dw);
   return MML_OK;
 }
 
@@ -1477,8 +1486,7 @@ int launch_wgrad_t(mml_ctx* ctx, const WgradMaps& maps, const WgradParams& p, di
     if (rc) return rc;
     configured = true;
   }
-  conv_wgrad_kernel<BLOCK_C, STAGES><<<grid, 192, L::kBytes, st>>>(maps, p);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, (conv_wgrad_kernel<BLOCK_C, STAGES>), grid, 192, L::kBytes, st, maps, p);
   return MML_OK;
 }
 
@@ -1703,12 +1711,10 @@ int mml_conv_wgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* x, cons
     // fixed-order sum of the split partials into dW; unreached taps hold garbage in the slabs, so only reached taps are summed
     // when some taps are missing (rare: tiny maps), otherwise the whole slab in one launch
     if (n_taps == g->R * g->S) {
-      wgrad_partial_reduce_kernel<<<(int)mml_ceil_div(wp.slab / 4, 32), 256, 0, st>>>(workspace, wp.splits, wp.slab, dw_krsc);
-      MML_LAUNCHED(ctx);
+      MML_LAUNCH(ctx, wgrad_partial_reduce_kernel, (int)mml_ceil_div(wp.slab / 4, 32), 256, 0, st, workspace, wp.splits, wp.slab, dw_krsc);
     } else {
-      wgrad_tap_reduce_kernel<<<dim3((unsigned)mml_ceil_div((long long)g->K * g->C / 4, 256), n_taps), 256, 0, st>>>(workspace, wp.splits, wp.slab, dw_krsc,
+      MML_LAUNCH(ctx, wgrad_tap_reduce_kernel, dim3((unsigned)mml_ceil_div((long long)g->K * g->C / 4, 256), n_taps), 256, 0, st, workspace, wp.splits, wp.slab, dw_krsc,
                                                                                                                   g->K, g->R * g->S, g->C, p);
-      MML_LAUNCHED(ctx);
     }
   }
   return MML_OK;

@@ -135,6 +135,7 @@ constexpr int kFcTile = 32, kFcChunk = 64;
 
 // y[b][n] = bias[n] + sum_k x[b][k] * w[n][k]
 __global__ void __launch_bounds__(256) fc_fwd_kernel(FcJobs jobs, int B) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   const FcJob J = jobs.j[blockIdx.z];
   if ((int)blockIdx.y >= J.tiles_n) return;
   __shared__ float xs[kFcTile][kFcChunk + 1], wsm[kFcTile][kFcChunk + 1];
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(256) fc_fwd_kernel(FcJobs jobs, int B) {
 
 // y[b][n] = sum_k x[b][k] * w[k][n]      (d pooled = d emb . W_fc;  K = embedding width, N = feature width)
 __global__ void __launch_bounds__(256) fc_bwd_data_kernel(FcJobs jobs, int B) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   const FcJob J = jobs.j[blockIdx.z];
   if ((int)blockIdx.y >= J.tiles_n) return;
   __shared__ float xs[kFcTile][kFcChunk + 1], wsm[kFcChunk][kFcTile + 1];
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(kHeadThreads)
 head_fwd_kernel(mml_head_params p, HeadDims d, const float* __restrict__ pooledA, const float* __restrict__ pooledI,
                 const long long* __restrict__ labels, const uint8_t* __restrict__ drop, float drop_scale, float* __restrict__ scratch,
                 float* __restrict__ logits, int* __restrict__ pred, int B) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   extern __shared__ float sm[];
   float* es = sm;                          // [SPC][emb]   (encoder fc outputs, computed by fc_fwd_kernel into scratch)
   float* h1 = es + SPC * d.emb();          // [SPC][H1]
@@ -286,6 +289,7 @@ head_fwd_kernel(mml_head_params p, HeadDims d, const float* __restrict__ pooledA
 }
 
 __global__ void head_loss_kernel(const float* __restrict__ scratch, int PS, int off_loss, int B, float* __restrict__ loss_out) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   __shared__ float sh[256];
   float a = 0.f;
   for (int b = threadIdx.x; b < B; b += 256) a += scratch[(size_t)b * PS + off_loss];
@@ -348,6 +352,7 @@ __global__ void __launch_bounds__(kHeadThreads)
 head_bwd_data_kernel(mml_head_params p, HeadDims d, const long long* __restrict__ labels, const uint8_t* __restrict__ drop,
                      float drop_scale, float* __restrict__ scratch, float loss_scale, float* __restrict__ dpooledA,
                      float* __restrict__ dpooledI, int B) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   extern __shared__ float sm[];
   float* dlog = sm;                       // [SPC][NC]
   float* dh2 = dlog + SPC * d.NC;         // [SPC][H2]
@@ -418,6 +423,7 @@ struct WgradJobs {
 };
 
 __global__ void __launch_bounds__(256) head_bwd_weights_kernel(WgradJobs jobs, int B) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   int ji = 0;
 #pragma unroll
   for (int t = 1; t < 5; ++t)
@@ -455,6 +461,7 @@ __global__ void __launch_bounds__(256) head_bwd_weights_kernel(WgradJobs jobs, i
 // y[b][o] = bias[o] + sum_k x[b][k] * W[o][k]: the encoder fc used stand-alone (resnet.py:150,218); one warp per output
 __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
                                                          float* __restrict__ y, int B, int n_in, int n_out) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B * n_out) return;
   const int b = warp / n_out, o = warp - b * n_out;
@@ -466,6 +473,7 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict
 
 __global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, long long n, float p, unsigned long long seed,
                                     const long long* __restrict__ step) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   const unsigned long long st = step ? (unsigned long long)step[0] : 0ull;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     // splitmix64 of (seed, step, index): counter-based, graph-replay safe (step lives on the device)
@@ -483,6 +491,7 @@ __global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, long long n, flo
 __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
                                                         float* __restrict__ dlogits, float* __restrict__ row_loss, int* __restrict__ pred,
                                                         float scale, int B, int NC) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
   const float v = lane < NC ? logits[(size_t)b * NC + lane] : -INFINITY;
@@ -544,15 +553,12 @@ int mml_head_fwd(mml_ctx* ctx, const mml_head_params* p, const float* pooledA, c
     jobs.j[0] = {pooledA, p->fcA_w, p->fcA_b, scratch, d.FA, d.EA, d.FA, PS, (int)mml_ceil_div(d.EA, kFcTile)};
     jobs.j[1] = {pooledI, p->fcI_w, p->fcI_b, scratch + d.EA, d.FI, d.EI, d.FI, PS, (int)mml_ceil_div(d.EI, kFcTile)};
     const int ty = jobs.j[0].tiles_n > jobs.j[1].tiles_n ? jobs.j[0].tiles_n : jobs.j[1].tiles_n;
-    fc_fwd_kernel<<<dim3((unsigned)mml_ceil_div(B, kFcTile), ty, 2), 256, 0, st>>>(jobs, B);
-    MML_LAUNCHED(ctx);
+    MML_LAUNCH(ctx, fc_fwd_kernel, dim3((unsigned)mml_ceil_div(B, kFcTile), ty, 2), 256, 0, st, jobs, B);
   }
-  head_fwd_kernel<<<(B + SPC - 1) / SPC, kHeadThreads, smem, st>>>(*p, d, pooledA, pooledI, (const long long*)labels, dropout_mask,
+  MML_LAUNCH(ctx, head_fwd_kernel, (B + SPC - 1) / SPC, kHeadThreads, smem, st, *p, d, pooledA, pooledI, (const long long*)labels, dropout_mask,
                                                                   dropout_scale, scratch, logits, pred, B);
-  MML_LAUNCHED(ctx);
   if (labels != nullptr) {
-    head_loss_kernel<<<1, 256, 0, st>>>(scratch, d.per_sample(), d.off_loss(), B, loss_out);
-    MML_LAUNCHED(ctx);
+    MML_LAUNCH(ctx, head_loss_kernel, 1, 256, 0, st, scratch, d.per_sample(), d.off_loss(), B, loss_out);
   }
   return MML_OK;
 }
@@ -572,16 +578,14 @@ int mml_head_bwd(mml_ctx* ctx, const mml_head_params* p, const mml_head_grads* g
   cudaStream_t st = (cudaStream_t)stream;
   MML_REQUIRE(ctx, phases >= 1 && phases <= 3, "head_bwd: phases must be 1 (data), 2 (weights) or 3 (both)");
   if (phases & 1) {
-    head_bwd_data_kernel<<<(B + SPC - 1) / SPC, kHeadThreads, smem, st>>>(*p, d, (const long long*)labels, dropout_mask, dropout_scale,
+    MML_LAUNCH(ctx, head_bwd_data_kernel, (B + SPC - 1) / SPC, kHeadThreads, smem, st, *p, d, (const long long*)labels, dropout_mask, dropout_scale,
                                                                          scratch, loss_scale, dpooledA, dpooledI, B);
-    MML_LAUNCHED(ctx);
     FcJobs jobs;
     const int PS = d.per_sample();
     jobs.j[0] = {scratch + d.off_demb(), p->fcA_w, nullptr, dpooledA, d.EA, d.FA, PS, d.FA, (int)mml_ceil_div(d.FA, kFcTile)};
     jobs.j[1] = {scratch + d.off_demb() + d.EA, p->fcI_w, nullptr, dpooledI, d.EI, d.FI, PS, d.FI, (int)mml_ceil_div(d.FI, kFcTile)};
     const int ty = jobs.j[0].tiles_n > jobs.j[1].tiles_n ? jobs.j[0].tiles_n : jobs.j[1].tiles_n;
-    fc_bwd_data_kernel<<<dim3((unsigned)mml_ceil_div(B, kFcTile), ty, 2), 256, 0, st>>>(jobs, B);
-    MML_LAUNCHED(ctx);
+    MML_LAUNCH(ctx, fc_bwd_data_kernel, dim3((unsigned)mml_ceil_div(B, kFcTile), ty, 2), 256, 0, st, jobs, B);
   }
   if (!(phases & 2)) return MML_OK;
   const int PS = d.per_sample();
@@ -597,8 +601,7 @@ int mml_head_bwd(mml_ctx* ctx, const mml_head_params* p, const mml_head_grads* g
   set(2, scratch + d.off_dpre1(), PS, scratch, PS, g->w0, g->b0, d.H1, d.emb());
   set(3, scratch + d.off_dh2(), PS, scratch + d.off_h1(), PS, g->w3, g->b3, d.H2, d.H1);
   set(4, scratch + d.off_dlog(), PS, scratch + d.off_h2(), PS, g->w5, g->b5, d.NC, d.H2);
-  head_bwd_weights_kernel<<<fb, 256, 0, st>>>(jobs, B);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, head_bwd_weights_kernel, fb, 256, 0, st, jobs, B);
   return MML_OK;
 }
 
@@ -609,11 +612,9 @@ int mml_softmax_ce(mml_ctx* ctx, const float* logits, const int64_t* labels, flo
   MML_REQUIRE(ctx, !loss_out || (labels && row_loss), "softmax_ce: the loss needs labels and row_loss");
   MML_REQUIRE(ctx, !dlogits || labels, "softmax_ce: the gradient needs labels");
   cudaStream_t st = (cudaStream_t)stream;
-  softmax_ce_kernel<<<(unsigned)mml_ceil_div(B, 8), 256, 0, st>>>(logits, (const long long*)labels, dlogits, row_loss, pred, loss_scale, B, NC);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, softmax_ce_kernel, (unsigned)mml_ceil_div(B, 8), 256, 0, st, logits, (const long long*)labels, dlogits, row_loss, pred, loss_scale, B, NC);
   if (loss_out) {
-    head_loss_kernel<<<1, 256, 0, st>>>(row_loss, 1, 0, B, loss_out);
-    MML_LAUNCHED(ctx);
+    MML_LAUNCH(ctx, head_loss_kernel, 1, 256, 0, st, row_loss, 1, 0, B, loss_out);
   }
   return MML_OK;
 }
@@ -628,16 +629,12 @@ int mml_mono_head_fwd(mml_ctx* ctx, const float* pooled, const float* fc_w, cons
   FcJobs jobs;
   memset(&jobs, 0, sizeof(jobs));
   jobs.j[0] = {pooled, fc_w, fc_b, emb, F, E, F, E, (int)mml_ceil_div(E, kFcTile)};
-  fc_fwd_kernel<<<dim3((unsigned)mml_ceil_div(B, kFcTile), jobs.j[0].tiles_n, 1), 256, 0, st>>>(jobs, B);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, fc_fwd_kernel, dim3((unsigned)mml_ceil_div(B, kFcTile), jobs.j[0].tiles_n, 1), 256, 0, st, jobs, B);
   jobs.j[0] = {emb, cls_w, cls_b, logits, E, NC, E, NC, (int)mml_ceil_div(NC, kFcTile)};
-  fc_fwd_kernel<<<dim3((unsigned)mml_ceil_div(B, kFcTile), jobs.j[0].tiles_n, 1), 256, 0, st>>>(jobs, B);
-  MML_LAUNCHED(ctx);
-  softmax_ce_kernel<<<(unsigned)mml_ceil_div(B, 8), 256, 0, st>>>(logits, (const long long*)labels, dlogits, row_loss, pred, loss_scale, B, NC);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, fc_fwd_kernel, dim3((unsigned)mml_ceil_div(B, kFcTile), jobs.j[0].tiles_n, 1), 256, 0, st, jobs, B);
+  MML_LAUNCH(ctx, softmax_ce_kernel, (unsigned)mml_ceil_div(B, 8), 256, 0, st, logits, (const long long*)labels, dlogits, row_loss, pred, loss_scale, B, NC);
   if (loss_out) {
-    head_loss_kernel<<<1, 256, 0, st>>>(row_loss, 1, 0, B, loss_out);
-    MML_LAUNCHED(ctx);
+    MML_LAUNCH(ctx, head_loss_kernel, 1, 256, 0, st, row_loss, 1, 0, B, loss_out);
   }
   return MML_OK;
 }
@@ -652,26 +649,22 @@ int mml_mono_head_bwd(mml_ctx* ctx, const float* pooled, const float* emb, const
   FcJobs jobs;
   memset(&jobs, 0, sizeof(jobs));
   jobs.j[0] = {dlogits, cls_w, nullptr, demb, NC, E, NC, E, (int)mml_ceil_div(E, kFcTile)};     // d emb = d logits . W_cls
-  fc_bwd_data_kernel<<<dim3((unsigned)mml_ceil_div(B, kFcTile), jobs.j[0].tiles_n, 1), 256, 0, st>>>(jobs, B);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, fc_bwd_data_kernel, dim3((unsigned)mml_ceil_div(B, kFcTile), jobs.j[0].tiles_n, 1), 256, 0, st, jobs, B);
   jobs.j[0] = {demb, fc_w, nullptr, dpooled, E, F, E, F, (int)mml_ceil_div(F, kFcTile)};        // d pooled = d emb . W_fc
-  fc_bwd_data_kernel<<<dim3((unsigned)mml_ceil_div(B, kFcTile), jobs.j[0].tiles_n, 1), 256, 0, st>>>(jobs, B);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, fc_bwd_data_kernel, dim3((unsigned)mml_ceil_div(B, kFcTile), jobs.j[0].tiles_n, 1), 256, 0, st, jobs, B);
   WgradJobs wj;
   memset(&wj, 0, sizeof(wj));
   wj.j[0] = {demb, pooled, d_fc_w, d_fc_b, E, F, E, F, 0};
   wj.j[1] = {dlogits, emb, d_cls_w, d_cls_b, NC, E, NC, E, E};
   for (int t = 2; t < 5; ++t) wj.j[t].first_block = E + NC;  // unused
-  head_bwd_weights_kernel<<<E + NC, 256, 0, st>>>(wj, B);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, head_bwd_weights_kernel, E + NC, 256, 0, st, wj, B);
   return MML_OK;
 }
 
 int mml_linear_fwd(mml_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int n_in, int n_out, void* stream) {
   MML_REQUIRE(ctx, ctx && x && w && y && B >= 1 && n_in >= 1 && n_out >= 1, "linear_fwd: bad arguments");
   const long long warps = (long long)B * n_out;
-  linear_fwd_kernel<<<(unsigned)mml_ceil_div(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, n_in, n_out);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, linear_fwd_kernel, (unsigned)mml_ceil_div(warps * 32, 256), 256, 0, (cudaStream_t)stream, x, w, bias, y, B, n_in, n_out);
   return MML_OK;
 }
 
@@ -679,8 +672,7 @@ int mml_dropout_mask(mml_ctx* ctx, uint8_t* mask, int64_t n, float p, uint64_t s
   MML_REQUIRE(ctx, ctx && mask && n >= 1 && p >= 0.f && p < 1.f, "dropout_mask: bad arguments");
   int grid = (int)mml_ceil_div(n, 256);
   if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
-  dropout_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mask, n, p, seed, (const long long*)step_counter);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, dropout_mask_kernel, grid, 256, 0, (cudaStream_t)stream, mask, n, p, seed, (const long long*)step_counter);
   return MML_OK;
 }
 

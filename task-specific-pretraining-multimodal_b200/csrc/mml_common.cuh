@@ -126,6 +126,19 @@ __device__ __forceinline__ void tma_store_wait_all() {
 }
 
 // --------------------------------------------------------------------------------------------
+// programmatic dependent launch (see mml_ctx.h::mml_launch_kernel): a kernel first sets up what does not depend on earlier
+// kernels, then waits for them (completion + memory visibility), then allows the NEXT kernel of the stream to be scheduled.
+// Triggering only after the wait keeps the pre-launch depth at one kernel: a chain of small kernels cannot pile up idle CTAs
+// (holding shared memory / TMEM) on SMs another stream needs.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+  pdl_wait();
+  pdl_launch_dependents();
+}
+
+// --------------------------------------------------------------------------------------------
 // thread-block clusters / distributed shared memory
 // --------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {

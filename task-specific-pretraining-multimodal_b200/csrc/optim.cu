@@ -16,6 +16,7 @@ namespace {
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             uint16_t* __restrict__ pb, long long n, const float* __restrict__ hyper, const long long* __restrict__ step) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   __shared__ float sh[2];
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], gs = hyper[5];
   if (threadIdx.x == 0) {
@@ -61,9 +62,13 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
-__global__ void step_inc_kernel(long long* step) { step[0] += 1; }
+__global__ void step_inc_kernel(long long* step) {
+  pdl_sync();
+  step[0] += 1;
+}
 
 __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -78,6 +83,7 @@ constexpr int kMaxClients = 64;
 
 __global__ void __launch_bounds__(256)
 fedavg_kernel(const float* const* __restrict__ clients, const float* __restrict__ weights, int K, float* __restrict__ out, long long n) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   __shared__ const float* ptr[kMaxClients];
   __shared__ float wk[kMaxClients];
   if ((int)threadIdx.x < K) {
@@ -104,6 +110,7 @@ fedavg_kernel(const float* const* __restrict__ clients, const float* __restrict_
 }
 
 __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ x, const float* __restrict__ weights, int idx, long long n) {
+  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
   const float w = weights[idx];
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -134,11 +141,9 @@ int mml_adam_step(mml_ctx* ctx, float* p, const float* g, float* m, float* v, ui
   MML_REQUIRE(ctx, aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && (!p_bf16 || ((uintptr_t)p_bf16 & 7u) == 0),
               "adam_step: buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  adam_kernel<<<flat_grid(ctx, n), 256, 0, st>>>(p, g, m, v, p_bf16, n, hyper, (const long long*)step);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, adam_kernel, flat_grid(ctx, n), 256, 0, st, p, g, m, v, p_bf16, n, hyper, (const long long*)step);
   if (advance_step) {
-    step_inc_kernel<<<1, 1, 0, st>>>((long long*)step);
-    MML_LAUNCHED(ctx);
+    MML_LAUNCH(ctx, step_inc_kernel, 1, 1, 0, st, (long long*)step);
   }
   return MML_OK;
 }
@@ -146,8 +151,7 @@ int mml_adam_step(mml_ctx* ctx, float* p, const float* g, float* m, float* v, ui
 int mml_cast_f32_bf16(mml_ctx* ctx, const float* src, uint16_t* dst, int64_t n, void* stream) {
   MML_REQUIRE(ctx, ctx && src && dst && n >= 1, "cast: bad arguments");
   MML_REQUIRE(ctx, aligned16(src) && ((uintptr_t)dst & 7u) == 0, "cast: buffers must be aligned");
-  cast_kernel<<<flat_grid(ctx, n), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, cast_kernel, flat_grid(ctx, n), 256, 0, (cudaStream_t)stream, src, dst, n);
   return MML_OK;
 }
 
@@ -155,15 +159,13 @@ int mml_fedavg(mml_ctx* ctx, const float* const* clients, const float* weights, 
   MML_REQUIRE(ctx, ctx && clients && weights && out && n >= 1, "fedavg: bad arguments");
   MML_REQUIRE(ctx, K >= 1 && K <= kMaxClients, "fedavg: K must be in [1, %d]", kMaxClients);
   MML_REQUIRE(ctx, aligned16(out), "fedavg: out must be 16-byte aligned");
-  fedavg_kernel<<<flat_grid(ctx, n), 256, 0, (cudaStream_t)stream>>>(clients, weights, K, out, n);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, fedavg_kernel, flat_grid(ctx, n), 256, 0, (cudaStream_t)stream, clients, weights, K, out, n);
   return MML_OK;
 }
 
 int mml_scale_inplace(mml_ctx* ctx, float* x, const float* weights, int idx, int64_t n, void* stream) {
   MML_REQUIRE(ctx, ctx && x && weights && idx >= 0 && n >= 1 && aligned16(x), "scale_inplace: bad arguments");
-  scale_kernel<<<flat_grid(ctx, n), 256, 0, (cudaStream_t)stream>>>(x, weights, idx, n);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, scale_kernel, flat_grid(ctx, n), 256, 0, (cudaStream_t)stream, x, weights, idx, n);
   return MML_OK;
 }
 

@@ -148,6 +148,7 @@ stem_fprop_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
     fence_mbar_init();
   }
   if (warp == 4) tmem_alloc<128>(tmem_slot);
+  pdl_wait();  // the weights below were written by an earlier kernel (Adam)
   if (threadIdx.x < 64) {  // weights: row k, chunk r = [w[k][r][0..6], 0], chunk 7 = 0; K-major SWIZZLE_128B
     const int k = threadIdx.x;
     const uint32_t row_addr = smem_base + kFOffW + (uint32_t)k * 128u;
@@ -167,6 +168,7 @@ stem_fprop_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_launch_dependents();
   const int n_my = (g.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 4) {
@@ -320,6 +322,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_sync();
   const int n_my = (g.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 4) {
@@ -399,6 +402,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
 }
 
 __global__ void stem_wgrad_reduce_kernel(const float* __restrict__ ws, int parts, float* __restrict__ dw) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * 49) return;
   float a = 0.f;
@@ -444,8 +448,7 @@ int mml_stem_fprop(mml_ctx* ctx, const float* x, const float* mask, const float*
     MML_CHECK_CUDA(ctx, cudaFuncSetAttribute(stem_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWBytes));
     configured = true;
   }
-  stem_fprop_tc_kernel<<<stem_ctas(ctx, g.tiles, 3), kThreadsStem, kFBytes, (cudaStream_t)stream>>>(maps, x, mask, w, stats, g);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, stem_fprop_tc_kernel, stem_ctas(ctx, g.tiles, 3), kThreadsStem, kFBytes, (cudaStream_t)stream, maps, x, mask, w, stats, g);
   return MML_OK;
 }
 
@@ -473,10 +476,8 @@ int mml_stem_wgrad(mml_ctx* ctx, const float* x, const float* mask, const uint16
   }
   const int ctas = stem_ctas(ctx, g.tiles, 2);
   cudaStream_t st = (cudaStream_t)stream;
-  stem_wgrad_tc_kernel<<<ctas, kThreadsStem, kWBytes, st>>>(maps, x, mask, workspace, g);
-  MML_LAUNCHED(ctx);
-  stem_wgrad_reduce_kernel<<<(64 * 49 + 255) / 256, 256, 0, st>>>(workspace, ctas, dw);
-  MML_LAUNCHED(ctx);
+  MML_LAUNCH(ctx, stem_wgrad_tc_kernel, ctas, kThreadsStem, kWBytes, st, maps, x, mask, workspace, g);
+  MML_LAUNCH(ctx, stem_wgrad_reduce_kernel, (64 * 49 + 255) / 256, 256, 0, st, workspace, ctas, dw);
   return MML_OK;
 }
 
