@@ -61,6 +61,7 @@ SIGNATURES = {
     "mml_ctx_sm_count": (I32, [P]),
     "mml_ctx_launch_count": (I64, [P]),
     "mml_ctx_set_sm_budget": (I32, [P, I32]),
+    "mml_ctx_set_pdl": (I32, [P, I32]),
     "mml_debug_set": (I32, [I32, I32]),
     "mml_mask_apply_f32": (I32, [P, P, P, P, P, I64, I64, P]),
     "mml_stem_fprop": (I32, [P, P, P, P, P, P, I32, I32, I32, P]),

@@ -36,6 +36,12 @@ int mml_ctx_set_sm_budget(mml_ctx* ctx, int sms) {
   return MML_OK;
 }
 
+int mml_ctx_set_pdl(mml_ctx* ctx, int enable) {
+  if (!ctx) return MML_ERR_INVALID;
+  ctx->pdl = enable ? 1 : 0;
+  return MML_OK;
+}
+
 int mml_ctx_create(int device, mml_ctx** out) {
   if (!out) return mml_set_error(nullptr, MML_ERR_INVALID, "mml_ctx_create: out is NULL");
   *out = nullptr;

@@ -481,8 +481,10 @@ stem_bn_pool_fwd_kernel(const uint16_t* __restrict__ x, BnTrain bn, const float*
         const F8 v = unpack8(ldg16(x + (((long long)n * H + h) * W + w) * C + cg * 8));
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          // the stored activation would have been bf16(relu(bn(x))): round the same way so that ties resolve identically
-          const float a = bf16_lo(pack_bf16x2(fmaxf(fmaf(v.v[j], sc.v[j], sh.v[j]), 0.f), 0.f));
+          // ReLU and the bf16 rounding of the (never stored) activation are monotone, so they commute with the max: compare the
+          // fp32 BatchNorm outputs and apply both once to the winner (a window whose maximum is <= 0 yields 0; its argmax is
+          // irrelevant because backward recomputes the ReLU mask)
+          const float a = fmaf(v.v[j], sc.v[j], sh.v[j]);
           if (idx[j] < 0 || a > best[j] || a != a) {  // torch: (val > maxval) || isnan(val)
             best[j] = a;
             idx[j] = r * 3 + s2;
@@ -492,7 +494,7 @@ stem_bn_pool_fwd_kernel(const uint16_t* __restrict__ x, BnTrain bn, const float*
     }
     F8 o;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o.v[j] = best[j];
+    for (int j = 0; j < 8; ++j) o.v[j] = best[j] != best[j] ? best[j] : fmaxf(best[j], 0.f);  // relu(NaN) = NaN like torch
     *reinterpret_cast<uint4*>(y + i * 8) = pack8(o);
     uint2 a;
     a.x = (uint32_t)idx[0] | ((uint32_t)idx[1] << 8) | ((uint32_t)idx[2] << 16) | ((uint32_t)idx[3] << 24);
@@ -547,41 +549,53 @@ __device__ __forceinline__ void pool_scatter_2x2(const uint16_t* __restrict__ dy
 }
 
 // bstat += (sum g, sum g*xhat) and dx = g (bn_bwd_apply_kernel then finishes in place);  g = scatter(dpool) * (bn(x) > 0),
-// bn(x) = gamma*(x-mean)*invstd + beta
-__global__ void __launch_bounds__(kThreads)
+// bn(x) = gamma*(x-mean)*invstd + beta.  One thread = the 2x2 input block (2a.., 2b..) x FOUR channels: with eight channels the
+// per-channel coefficients, the four window gradients and the 2x2 accumulators need 140 registers (one 256-thread CTA per SM, 126 us
+// for 270 MB); four channels fit in half of that.
+__global__ void __launch_bounds__(kThreads, 3)
 stem_bn_pool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__ dy2, const uint8_t* __restrict__ amax,
                         const uint16_t* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ gamma, const float* __restrict__ beta, double* __restrict__ bstat,
                         uint16_t* __restrict__ dx, int N, int H, int W, int C, int P, int Q) {
-  pdl_sync();  // programmatic dependent launch: wait for the previous kernel of the stream, then let the next one be scheduled
-  __shared__ float sh[kThreads][17];
-  const int c8 = C >> 3;
+  pdl_sync();
+  __shared__ float sh[kThreads][9];
+  const int c4 = C >> 2;
   const int HB = (H + 1) >> 1, WB = (W + 1) >> 1;
-  const long long total = (long long)N * HB * WB * c8;
+  const long long total = (long long)N * HB * WB * c4;
   const long long stride = (long long)gridDim.x * kThreads;
   long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
-  const int cg = (int)(i % c8);
-  const F8 mu = load8f(mean + cg * 8), is = load8f(invstd + cg * 8), ga = load8f(gamma + cg * 8), be = load8f(beta + cg * 8);
-  float sg[8], sgx[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) sg[j] = sgx[j] = 0.f;
+  const int cg = (int)(i % c4);
+  const float4 mu = *reinterpret_cast<const float4*>(mean + cg * 4), is = *reinterpret_cast<const float4*>(invstd + cg * 4);
+  const float4 ga = *reinterpret_cast<const float4*>(gamma + cg * 4), be = *reinterpret_cast<const float4*>(beta + cg * 4);
+  float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};
   for (; i < total; i += stride) {
-    long long t = i / c8;
+    long long t = i / c4;
     const int b = (int)(t % WB);
     t /= WB;
     const int a = (int)(t % HB);
     const int n = (int)(t / HB);
-    // the four raw-output loads do not depend on the scatter: issue them first
-    uint4 xu[2][2];
+    // gradients and argmax bytes of the (up to) four pooling windows p in {a, a+1}, q in {b, b+1} that cover this block
+    float gw[2][2][4];
+    uint32_t am[2][2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int dp = 0; dp < 2; ++dp)
 #pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        const int h = 2 * a + u, w = 2 * b + v;
-        xu[u][v] = (h < H && w < W) ? ldg16(x + ((((long long)n * H + h) * W + w) * c8 + cg) * 8) : make_uint4(0, 0, 0, 0);
+      for (int dq = 0; dq < 2; ++dq) {
+        const int p = a + dp, q = b + dq;
+        am[dp][dq] = 0xFFFFFFFFu;  // matches no window position
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gw[dp][dq][j] = 0.f;
+        if (p < P && q < Q) {
+          const long long o = (((long long)n * P + p) * Q + q) * C + cg * 4;
+          am[dp][dq] = __ldg(reinterpret_cast<const uint32_t*>(amax + o));
+          const uint2 g1 = __ldg(reinterpret_cast<const uint2*>(dy + o));
+          gw[dp][dq][0] = bf16_lo(g1.x), gw[dp][dq][1] = bf16_hi(g1.x), gw[dp][dq][2] = bf16_lo(g1.y), gw[dp][dq][3] = bf16_hi(g1.y);
+          if (dy2 != nullptr) {  // gradient arriving over two paths (conv branch + identity skip)
+            const uint2 g2 = __ldg(reinterpret_cast<const uint2*>(dy2 + o));
+            gw[dp][dq][0] += bf16_lo(g2.x), gw[dp][dq][1] += bf16_hi(g2.x), gw[dp][dq][2] += bf16_lo(g2.y), gw[dp][dq][3] += bf16_hi(g2.y);
+          }
+        }
       }
-    F8 acc[2][2];
-    pool_scatter_2x2(dy, dy2, amax, n, a, b, cg, c8, P, Q, acc);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int h = 2 * a + u;
@@ -590,27 +604,60 @@ stem_bn_pool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restr
       for (int v = 0; v < 2; ++v) {
         const int w = 2 * b + v;
         if (w >= W) continue;
-        const long long o = ((((long long)n * H + h) * W + w) * c8 + cg) * 8;
-        const F8 xv = unpack8(xu[u][v]);
-        F8 out;
+        const long long o = (((long long)n * H + h) * W + w) * C + cg * 4;
+        const uint2 xu = __ldg(reinterpret_cast<const uint2*>(x + o));
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        // window (p, q) covers rows 2p-1..2p+1: block row u (h = 2a+u) is window row r = u + 1 - 2*dp (valid: 0..2)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = (xv.v[j] - mu.v[j]) * is.v[j];
-          out.v[j] = fmaf(ga.v[j], xh, be.v[j]) > 0.f ? acc[u][v].v[j] : 0.f;  // ReLU mask recomputed
+        for (int dp = 0; dp < 2; ++dp) {
+          const int r = u + 1 - 2 * dp;
+          if (r < 0 || r > 2) continue;
+#pragma unroll
+          for (int dq = 0; dq < 2; ++dq) {
+            const int s2 = v + 1 - 2 * dq;
+            if (s2 < 0 || s2 > 2) continue;
+            const uint32_t want = (uint32_t)(r * 3 + s2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (((am[dp][dq] >> (8 * j)) & 0xFFu) == want) acc[j] += gw[dp][dq][j];
+          }
         }
-        const uint4 gp = pack8(out);
-        *reinterpret_cast<uint4*>(dx + o) = gp;  // materialised once: the apply pass is then a plain elementwise kernel
-        const F8 gr = unpack8(gp);               // sums of the ROUNDED g, which is what the apply pass reads
+        const float xv[4] = {bf16_lo(xu.x), bf16_hi(xu.x), bf16_lo(xu.y), bf16_hi(xu.y)};
+        const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
+        const float gav[4] = {ga.x, ga.y, ga.z, ga.w}, bev[4] = {be.x, be.y, be.z, be.w};
+        float xh[4], g[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = (xv.v[j] - mu.v[j]) * is.v[j];
-          sg[j] += gr.v[j];
-          sgx[j] = fmaf(gr.v[j], xh, sgx[j]);
+        for (int j = 0; j < 4; ++j) {
+          xh[j] = (xv[j] - muv[j]) * isv[j];
+          g[j] = fmaf(gav[j], xh[j], bev[j]) > 0.f ? acc[j] : 0.f;  // ReLU mask recomputed
+        }
+        const uint2 gp = make_uint2(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]));
+        *reinterpret_cast<uint2*>(dx + o) = gp;  // materialised once: the apply pass is then a plain elementwise kernel
+        const float gr[4] = {bf16_lo(gp.x), bf16_hi(gp.x), bf16_lo(gp.y), bf16_hi(gp.y)};  // sums of the ROUNDED g (what pass 2 reads)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sg[j] += gr[j];
+          sgx[j] = fmaf(gr[j], xh[j], sgx[j]);
         }
       }
     }
   }
-  bn_bwd_block_reduce(sg, sgx, sh, bstat, c8);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sh[threadIdx.x][j] = sg[j];
+    sh[threadIdx.x][4 + j] = sgx[j];
+  }
+  __syncthreads();
+  // threads t, t + c4, t + 2*c4, ... share a channel group (kThreads % c4 == 0)
+  for (int o = threadIdx.x; o < C; o += kThreads) {
+    const int gch = o >> 2, j = o & 3;
+    float aa = 0.f, bb = 0.f;
+    for (int t = gch; t < kThreads; t += c4) {
+      aa += sh[t][j];
+      bb += sh[t][4 + j];
+    }
+    stat_add(bstat, C, blockIdx.x, o, aa, bb);
+  }
 }
 
 // AdaptiveAvgPool2d((1,1)) + flatten: [N, HW, C] bf16 -> [N, C] fp32
@@ -845,11 +892,12 @@ int mml_stem_bn_pool_bwd(mml_ctx* ctx, const uint16_t* dy, const uint16_t* dy2, 
   int rc = check_rows_c(ctx, (int64_t)N * H * W, C);
   if (rc) return rc;
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
-  const long long items = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  MML_REQUIRE(ctx, kThreads % (C / 4) == 0, "stem_bn_pool_bwd: C/4 must divide %d", kThreads);
+  const long long items = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
   const float inv_count = 1.0f / (float)((int64_t)N * H * W);
   cudaStream_t st = (cudaStream_t)stream;
   int g0 = (int)mml_ceil_div(items, (long long)kThreads * 2);
-  if (g0 > ctx->sm_count * 4) g0 = ctx->sm_count * 4;
+  if (g0 > ctx->sm_count * 6) g0 = ctx->sm_count * 6;
   if (g0 < 1) g0 = 1;
   MML_LAUNCH(ctx, stem_bn_pool_bwd_kernel, g0, kThreads, 0, st, dy, dy2, argmax, x, mean, invstd, gamma, beta, bstat, dx, N, H, W, C, P, Q);
   // pass 2 in place over the buffer that now holds g: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))

@@ -73,28 +73,29 @@ __device__ __forceinline__ void patch_map_init(PatchMap& pm, const StemGeom& g) 
     pm.rr[i] = ok ? r : (1 << 28);
   }
 }
-__device__ __forceinline__ void patch_prefetch(float (&reg)[kPatchRegs], const PatchMap& pm, int tile, const float* __restrict__ x,
-                                               const float* __restrict__ mask, const StemGeom& g) {
+// Issues the 16 global loads of the NEXT tile's patch and nothing else: the values are only consumed by patch_store, after the
+// gather + epilogue of the current tile, so all 16 loads are in flight together.  (Round 1 applied the mask here; mask_mul's NaN
+// branch made every load's consumer follow it immediately -- 16 serialized DRAM round trips per tile, ~11 of the ~15 k cycles a
+// tile took.)
+__device__ __forceinline__ float patch_prefetch(float (&reg)[kPatchRegs], const PatchMap& pm, int tile, const float* __restrict__ x,
+                                                const float* __restrict__ mask, const StemGeom& g) {
   const int b = tile / g.tiles_per_img;
   const int p0 = (tile - b * g.tiles_per_img) * g.rpt;
-  const float mk = mask ? mask[b] : 1.0f;
   const int hbase = 2 * p0 - 3;
   const float* origin = x + (size_t)b * g.H * g.W + (long long)hbase * g.W;
 #pragma unroll
-  for (int i = 0; i < kPatchRegs; ++i) {
-    float v = 0.f;
-    if ((unsigned)(hbase + pm.rr[i]) < (unsigned)g.H) {
-      v = __ldg(origin + pm.off[i]);
-      if (mask) v = mask_mul(v, mk);  // sample = original * mask, data/base_dataset.py:71
-    }
-    reg[i] = v;
-  }
+  for (int i = 0; i < kPatchRegs; ++i) reg[i] = ((unsigned)(hbase + pm.rr[i]) < (unsigned)g.H) ? __ldg(origin + pm.off[i]) : 0.f;
+  return mask ? __ldg(mask + b) : 1.0f;
 }
-__device__ __forceinline__ void patch_store(const float (&reg)[kPatchRegs], uint16_t* patch, const StemGeom& g) {
+// sample = original * mask (data/base_dataset.py:71), rounded to bf16, into the shared-memory patch
+__device__ __forceinline__ void patch_store(const float (&reg)[kPatchRegs], float mk, bool masked, uint16_t* patch, const StemGeom& g) {
 #pragma unroll
   for (int i = 0; i < kPatchRegs; ++i) {
     const int e = (int)threadIdx.x + i * 128;
-    if (e < g.patch_halves) patch[e] = (uint16_t)(pack_bf16x2(reg[i], 0.f) & 0xFFFFu);
+    if (e < g.patch_halves) {
+      const float v = masked ? mask_mul(reg[i], mk) : reg[i];
+      patch[e] = (uint16_t)(pack_bf16x2(v, 0.f) & 0xFFFFu);
+    }
   }
 }
 // im2col row of tile pixel `row` -> 128-byte swizzled tile row (7 chunks of [7 taps, 0], last chunk zero)
@@ -245,20 +246,21 @@ stem_fprop_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
     float reg[kPatchRegs];
     PatchMap pm;
     patch_map_init(pm, g);
+    float mk = 1.0f;
     if (n_my > 0) {
-      patch_prefetch(reg, pm, (int)blockIdx.x, x, mask, g);
-      patch_store(reg, reinterpret_cast<uint16_t*>(smem_gen + kFOffPatch), g);
+      mk = patch_prefetch(reg, pm, (int)blockIdx.x, x, mask, g);
+      patch_store(reg, mk, mask != nullptr, reinterpret_cast<uint16_t*>(smem_gen + kFOffPatch), g);
     }
     named_bar_sync(1, 128);
     for (int i = 0; i < n_my; ++i) {
       const bool more = i + 1 < n_my;
-      if (more) patch_prefetch(reg, pm, (int)blockIdx.x + (i + 1) * (int)gridDim.x, x, mask, g);  // loads in flight during gather + epilogue
+      if (more) mk = patch_prefetch(reg, pm, (int)blockIdx.x + (i + 1) * (int)gridDim.x, x, mask, g);  // loads in flight during gather + epilogue
       if (live) gather_row(smem_base + (i & 1) * kTileBytes, row, reinterpret_cast<const uint32_t*>(smem_gen + kFOffPatch + (i & 1) * kPatchBytes), word0, g.PWW);
       fence_proxy_async_smem();
       tc_fence_before();  // orders this thread's earlier TMEM loads before the MMA that will overwrite that accumulator
       mbar_arrive(a_full(i & 1));
       if (i >= 1) epilogue(i - 1);
-      if (more) patch_store(reg, reinterpret_cast<uint16_t*>(smem_gen + kFOffPatch + ((i + 1) & 1) * kPatchBytes), g);
+      if (more) patch_store(reg, mk, mask != nullptr, reinterpret_cast<uint16_t*>(smem_gen + kFOffPatch + ((i + 1) & 1) * kPatchBytes), g);
       named_bar_sync(1, 128);
     }
     if (n_my >= 1) epilogue(n_my - 1);
@@ -350,16 +352,17 @@ stem_wgrad_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
     float reg[kPatchRegs];
     PatchMap pm;
     patch_map_init(pm, g);
+    float mk = 1.0f;
     if (n_my > 0) {
-      patch_prefetch(reg, pm, (int)blockIdx.x, x, mask, g);
-      patch_store(reg, reinterpret_cast<uint16_t*>(smem_gen + kWOffPatch), g);
+      mk = patch_prefetch(reg, pm, (int)blockIdx.x, x, mask, g);
+      patch_store(reg, mk, mask != nullptr, reinterpret_cast<uint16_t*>(smem_gen + kWOffPatch), g);
     }
     named_bar_sync(1, 128);
     for (int i = 0; i < n_my; ++i) {
       const int buf = i & 1;
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
       const bool more = i + 1 < n_my;
-      if (more) patch_prefetch(reg, pm, tile + (int)gridDim.x, x, mask, g);
+      if (more) mk = patch_prefetch(reg, pm, tile + (int)gridDim.x, x, mask, g);
       if (i >= 2) mbar_wait(freeb(buf), (uint32_t)((i >> 1) - 1) & 1u);
       if (threadIdx.x == 0) {
         const int b = tile / g.tiles_per_img;
@@ -370,7 +373,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
       if (live) gather_row(smem_base + buf * kTileBytes, row, reinterpret_cast<const uint32_t*>(smem_gen + kWOffPatch + buf * kPatchBytes), word0, g.PWW);
       fence_proxy_async_smem();
       mbar_arrive(full(buf));
-      if (more) patch_store(reg, reinterpret_cast<uint16_t*>(smem_gen + kWOffPatch + ((i + 1) & 1) * kPatchBytes), g);
+      if (more) patch_store(reg, mk, mask != nullptr, reinterpret_cast<uint16_t*>(smem_gen + kWOffPatch + ((i + 1) & 1) * kPatchBytes), g);
       named_bar_sync(1, 128);
     }
     // dW[k][r][s] lives in accumulator row k, column r*8+s

@@ -592,6 +592,8 @@ class _StepPlan:
                      "skip": _os.environ.get("MML_SKIP_ENCODER", ""), "side_prio": _os.environ.get("MML_SIDE_PRIO", "-1")}
         # the audio encoder's persistent conv kernels leave a few SMs to the image encoder's stream (measured: 16 -> -1.2 % step time)
         self.reserve_sms = int(_os.environ.get("MML_RESERVE_SMS", "16"))
+        self.pdl_mode = _os.environ.get("MML_PDL_MODE", "none")  # none | image | audio | all
+        ops.set_pdl(dev.index, self.pdl_mode != "none")
         if _os.environ.get("MML_WGRAD_STREAMS", "1") == "1":
             self.audio.wgrad_stream = torch.cuda.Stream(device=dev)
             self.image.wgrad_stream = torch.cuda.Stream(device=dev)
@@ -629,19 +631,25 @@ class _StepPlan:
         main = torch.cuda.current_stream(self.eng.device)
         side = self._side()
         side.wait_stream(main)
-        with torch.cuda.stream(side):
-            for op in image_ops:
-                op()
-            if after_image is not None:
-                after_image()
         idx = self.eng.device.index
-        if self.reserve_sms > 0 and image_ops:
-            ops.set_sm_budget(idx, ops._ctx_sm_count(idx) - self.reserve_sms)
+        # programmatic dependent launch per stream (measured on B200): it shortens the image encoder's chain of small
+        # dependent kernels (-7.5 % alone), but pre-launched CTAs of the audio encoder's large grids hold SMs the image stream needs
+        pdl_image, pdl_audio = self.pdl_mode in ("image", "all"), self.pdl_mode in ("audio", "all")
         try:
+            ops.set_pdl(idx, pdl_image)
+            with torch.cuda.stream(side):
+                for op in image_ops:
+                    op()
+                if after_image is not None:
+                    after_image()
+            ops.set_pdl(idx, pdl_audio)
+            if self.reserve_sms > 0 and image_ops:
+                ops.set_sm_budget(idx, ops._ctx_sm_count(idx) - self.reserve_sms)
             for op in audio_ops:
                 op()
         finally:
             ops.set_sm_budget(idx, 0)
+            ops.set_pdl(idx, self.pdl_mode != "none")
         main.wait_stream(side)
 
     def run_train(self, own_dropout: bool) -> None:

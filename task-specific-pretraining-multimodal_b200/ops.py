@@ -323,6 +323,12 @@ def set_sm_budget(device_index: int, sms: int) -> None:
     c.check(c.lib.mml_ctx_set_sm_budget(c.handle, int(sms)), "mml_ctx_set_sm_budget")
 
 
+def set_pdl(device_index: int, enable: bool) -> None:
+    """Programmatic dependent launch for the launches that follow (see mml_ctx_set_pdl)."""
+    c = Context.get(device_index)
+    c.check(c.lib.mml_ctx_set_pdl(c.handle, int(bool(enable))), "mml_ctx_set_pdl")
+
+
 def launch_count(device_index: int = 0) -> int:
     return Context.get(device_index).launches
 
