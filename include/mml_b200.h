@@ -292,6 +292,20 @@ int mml_adam_step(mml_ctx*, float* p, const float* g, float* m, float* v, uint16
                   int64_t* step, int advance_step, void* stream);
 /* fp32 -> bf16 copy (shadow refresh after load_state_dict) */
 int mml_cast_f32_bf16(mml_ctx*, const float* src, uint16_t* dst, int64_t n, void* stream);
+/* ---- e: data-parallel gradient all-reduce -- library-owned NCCL communicator (the reference has no distributed code) ------- */
+/* One communicator per ctx.  Rank 0 creates the id (mml_comm_unique_id) and hands the 128 bytes to the other ranks by any
+ * out-of-band channel (the Python binding uses torch.distributed's store); every rank then calls mml_comm_init.  max_ctas > 0
+ * caps the CTAs NCCL may use (ncclConfig_t::maxCTAs): the all-reduces run under the audio encoder's backward and every SM they
+ * take is one its persistent kernels lose; <= 0 leaves NCCL's default.  NCCL itself is dlopen'ed (the process's libnccl.so.2). */
+#define MML_COMM_ID_BYTES 128
+int mml_comm_unique_id(mml_ctx*, uint8_t* id_out /* [MML_COMM_ID_BYTES] */);
+int mml_comm_init(mml_ctx*, const uint8_t* id /* [MML_COMM_ID_BYTES] */, int rank, int world, int max_ctas);
+int mml_comm_world(const mml_ctx*); /* 0 until mml_comm_init */
+/* in-place fp32 sum all-reduce of buf[0, count) over the communicator, enqueued on `stream` (CUDA-graph capturable); the
+ * division by the world size happens in mml_adam_step (hyper[5]) */
+int mml_allreduce_bucket(mml_ctx*, float* buf, int64_t count, void* stream);
+int mml_comm_destroy(mml_ctx*);
+
 /* ---- a13: FedAvg weighted aggregation (no reference implementation exists; McMahan et al.) ---------------------- */
 /* out[i] = sum_k weights[k] * clients[k][i];  clients: DEVICE array of K device pointers; weights: device fp32[K] */
 int mml_fedavg(mml_ctx*, const float* const* clients, const float* weights, int K, float* out, int64_t n, void* stream);

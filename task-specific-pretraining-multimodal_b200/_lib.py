@@ -110,6 +110,11 @@ SIGNATURES = {
     "mml_clip_grad_scale": (I32, [P, P, I64, F32, F32, P, I32, P, P, P]),
     "mml_adam_step": (I32, [P, P, P, P, P, P, I64, P, P, I32, P]),
     "mml_cast_f32_bf16": (I32, [P, P, P, I64, P]),
+    "mml_comm_unique_id": (I32, [P, P]),
+    "mml_comm_init": (I32, [P, P, I32, I32, I32]),
+    "mml_comm_world": (I32, [P]),
+    "mml_allreduce_bucket": (I32, [P, P, I64, P]),
+    "mml_comm_destroy": (I32, [P]),
     "mml_fedavg": (I32, [P, P, P, I32, P, I64, P]),
     "mml_scale_inplace": (I32, [P, P, P, I32, I64, P]),
 }

@@ -29,6 +29,9 @@ struct mml_ctx {
   // previous one is still executing; every such kernel calls griddepcontrol.wait before it touches global memory.  MML_PDL=0
   // in the environment turns it off (A/B runs).
   int pdl;
+  // library-owned NCCL communicator of the data-parallel step (comm.cu); NULL until mml_comm_init
+  void* comm;
+  int comm_rank, comm_world;
   char err[512];
 };
 

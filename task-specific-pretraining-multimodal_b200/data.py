@@ -81,45 +81,32 @@ class DevicePrefetcher:
     ``DataLoader(pin_memory=True)``); non-tensor entries pass through.  The consumer's stream waits on the slot's copy event,
     and a slot is only overwritten after the consumer's stream has been waited on, so there is no allocator traffic and no race.
 
-    Which stream carries the copies is CALIBRATED, not assumed: CUDA multiplexes streams onto a limited number of hardware
-    queues, and a copy stream that happens to share a queue with one of the streams inside the step's CUDA graph serialises
-    with it (measured on B200: the 3.3 ms AVMNIST step became 4.4-4.9 ms with an unlucky stream, 3.45 ms with a lucky one).
-    The first ``len(candidates) * rounds`` batches rotate over a few candidate streams and over "inline" (copy on the
-    consumer's stream, no overlap); the candidate with the smallest median step time is kept for the device (class-level, so
-    later prefetchers on the same device reuse it).
+    The copies run on ONE dedicated high-priority stream per device (created once, shared by every prefetcher of that device).
+    Round 1 rotated over candidate streams and kept the fastest from three samples each; under data parallelism that calibration
+    picked a stream that serialised with the step about half of the time (prefetched 5.6 ms vs blocking 4.0 ms at N = 4).  The
+    aliasing it tried to dodge -- CUDA multiplexing streams onto 8 hardware queues -- is removed at the source instead:
+    ``CUDA_DEVICE_MAX_CONNECTIONS=32`` is set before CUDA initialises (mml_b200/__init__.py), and a high-priority stream keeps the
+    small H2D transfers from queueing behind the step's kernels.
     """
 
-    _streams: Dict[Any, list] = {}
-    _choice: Dict[Any, int] = {}
-    calibration: Dict[int, float] = {}
-    N_CANDIDATES, ROUNDS = 3, 3
+    _streams: Dict[Any, "torch.cuda.Stream"] = {}
 
-    def __init__(self, loader: Iterable[Dict[Any, Any]], device, depth: int = 1, calibrate: bool = True):
+    def __init__(self, loader: Iterable[Dict[Any, Any]], device, depth: int = 1):
         self.loader, self.device, self.depth = loader, torch.device(device), max(1, int(depth))
         if self.device.type != "cuda":
             raise RuntimeError("DevicePrefetcher stages batches onto a CUDA device")
-        key = (self.device.type, self.device.index if self.device.index is not None else torch.cuda.current_device())
+        key = self.device.index if self.device.index is not None else torch.cuda.current_device()
         if key not in DevicePrefetcher._streams:
-            DevicePrefetcher._streams[key] = [None] + [torch.cuda.Stream(device=self.device) for _ in range(self.N_CANDIDATES)]
-        self._key = key
-        self.candidates = DevicePrefetcher._streams[key]  # [inline, stream, stream, ...]
-        if not calibrate and key not in DevicePrefetcher._choice:
-            DevicePrefetcher._choice[key] = 1
+            DevicePrefetcher._streams[key] = torch.cuda.Stream(device=self.device, priority=-1)
+        self.stream = DevicePrefetcher._streams[key]
         self.slots = [dict() for _ in range(self.depth + 1)]
         self.h2d_bytes = 0
 
-    @property
-    def chosen(self) -> Optional[int]:
-        """Index into ``candidates`` picked by the calibration (0 = inline), or None while calibrating."""
-        return DevicePrefetcher._choice.get(self._key)
-
-    def _stage(self, batch: Dict[Any, Any], slot: Dict[Any, torch.Tensor], cand: int):
+    def _stage(self, batch: Dict[Any, Any], slot: Dict[Any, torch.Tensor]):
         main = torch.cuda.current_stream(self.device)
-        stream = self.candidates[cand] or main
-        if stream is not main:
-            stream.wait_stream(main)  # the slot's previous consumer is done before it is overwritten
+        self.stream.wait_stream(main)  # the slot's previous consumer is done before it is overwritten
         out = {}
-        with torch.cuda.stream(stream):
+        with torch.cuda.stream(self.stream):
             for k, v in batch.items():
                 if torch.is_tensor(v):
                     buf = slot.get(k)
@@ -131,45 +118,25 @@ class DevicePrefetcher:
                 else:
                     out[k] = v
         ev = torch.cuda.Event()
-        ev.record(stream)
+        ev.record(self.stream)
         return out, ev
 
     def __iter__(self) -> Iterator[Dict[Any, Any]]:
-        import time
-
         it = iter(self.loader)
         queue: deque = deque()
         n = 0
-        samples: Dict[int, list] = {c: [] for c in range(len(self.candidates))}
-
-        def next_candidate() -> int:
-            if self.chosen is not None:
-                return self.chosen
-            return n % len(self.candidates)
-
         for _ in range(self.depth):
             try:
-                queue.append(self._stage(next(it), self.slots[n % len(self.slots)], next_candidate()))
+                queue.append(self._stage(next(it), self.slots[n % len(self.slots)]))
                 n += 1
             except StopIteration:
                 break
         while queue:
             out, ev = queue.popleft()
-            staged_with = None
             try:
-                staged_with = next_candidate()
-                queue.append(self._stage(next(it), self.slots[n % len(self.slots)], staged_with))
+                queue.append(self._stage(next(it), self.slots[n % len(self.slots)]))
                 n += 1
             except StopIteration:
-                staged_with = None
+                pass
             torch.cuda.current_stream(self.device).wait_event(ev)
-            t0 = time.perf_counter()
             yield out
-            if self.chosen is None and staged_with is not None:
-                # the consumer's step on ``out`` ran while the copy staged with ``staged_with`` was in flight; consumers that
-                # return a loss synchronise, so the wall time of the step reflects how well that copy overlapped
-                samples[staged_with].append(time.perf_counter() - t0)
-                if all(len(v) >= self.ROUNDS for v in samples.values()):
-                    med = {c: sorted(v)[len(v) // 2] for c, v in samples.items()}
-                    DevicePrefetcher._choice[self._key] = min(med, key=med.get)
-                    DevicePrefetcher.calibration = med  # seconds per step by candidate (0 = inline), for inspection

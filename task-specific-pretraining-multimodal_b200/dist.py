@@ -9,8 +9,11 @@ the image encoder has 2/3 of the parameters but few FLOPs, so its backward runs 
 head, ~85 MB) is all-reduced on a side stream while the audio encoder's backward (87 % of the FLOPs) is still running;
 the audio encoder follows in two ranges: layer3..fc (94 % of its parameters, ~42 MB) as soon as layer3's backward is
 done -- under the backward of layer2 / layer1 / the stem -- and the small remainder (~3 MB) at the end of the step.  The wgrad kernels write straight into ``G``, so there is no pack/copy step.
-``torch.distributed`` (NCCL over NVLink/NVSwitch) is the plumbing; both the collectives and the cross-stream
-dependencies are captured into the step's CUDA graph.
+The data plane is the library's own NCCL communicator (``mml_comm_init`` / ``mml_allreduce_bucket``, csrc/comm.cu): NCCL over
+NVLink / NVSwitch with a capped CTA budget (``MML_NCCL_MAX_CTAS``, default 16: the all-reduces run under the audio encoder's
+backward and every SM NCCL takes is one its persistent kernels lose).  ``torch.distributed`` remains the CONTROL plane (rendezvous,
+hand-over of the communicator id, the initial broadcast, barriers); both the collectives and the cross-stream dependencies are
+captured into the step's CUDA graph.
 """
 from __future__ import annotations
 
@@ -40,11 +43,25 @@ class DataParallel:
         self.comm_stream: Optional[torch.cuda.Stream] = None
         self.buckets: List[Tuple[int, int]] = []
         self.engine = None
+        self.max_ctas = int(os.environ.get("MML_NCCL_MAX_CTAS", "16"))
+
+    def _ensure_comm(self, device: torch.device) -> None:
+        """Create the library-owned communicator of this device once: rank 0 draws the id, torch.distributed hands it over."""
+        from . import ops
+
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if ops.comm_world(idx) == self.world_size:
+            return
+        payload = [ops.comm_unique_id(idx) if self.rank == 0 else None]
+        dist.broadcast_object_list(payload, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        ops.comm_init(idx, payload[0], self.rank, self.world_size, self.max_ctas)
 
     def attach(self, engine) -> None:
         self.engine = engine
         self.buckets = bucket_ranges(engine.fs.offsets, engine.fs.total)
         self.comm_stream = torch.cuda.Stream(device=engine.device)
+        if self.world_size > 1:
+            self._ensure_comm(engine.device)
         engine.world = self.world_size
         engine.allreduce = self._allreduce if self.world_size > 1 else None
         if hasattr(engine, "allreduce_range"):
@@ -60,7 +77,7 @@ class DataParallel:
         producer = torch.cuda.current_stream(eng.device)  # the stream whose backward just finished this bucket
         self.comm_stream.wait_stream(producer)
         with torch.cuda.stream(self.comm_stream):
-            dist.all_reduce(eng.fs.G[a:b], op=dist.ReduceOp.SUM, group=self.group)
+            self._sum(eng.fs.G[a:b])
             if update is not None:
                 update()
         if idx == len(self.buckets) - 1:
@@ -74,11 +91,17 @@ class DataParallel:
         for st in producers:
             self.comm_stream.wait_stream(st)
         with torch.cuda.stream(self.comm_stream):
-            dist.all_reduce(eng.fs.G[a:b], op=dist.ReduceOp.SUM, group=self.group)
+            self._sum(eng.fs.G[a:b])
             if update is not None:
                 update()
         if join:
             torch.cuda.current_stream(eng.device).wait_stream(self.comm_stream)
+
+    @staticmethod
+    def _sum(buf: torch.Tensor) -> None:
+        from . import ops
+
+        ops.allreduce_bucket(buf)
 
     def broadcast_state(self, engine) -> None:
         """Make every rank start from rank 0's weights / Adam state / running statistics."""

@@ -307,6 +307,36 @@ def scale_inplace(x, weights, idx) -> None:
     ctx.check(ctx.lib.mml_scale_inplace(ctx.handle, _p(x, torch.float32), _p(weights, torch.float32), idx, x.numel(), _stream(x)), "scale_inplace")
 
 
+# ---- data-parallel gradient all-reduce (library-owned NCCL communicator) --------------------------------------------------
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id(device_index: int) -> bytes:
+    c = Context.get(device_index)
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    c.check(c.lib.mml_comm_unique_id(c.handle, buf), "mml_comm_unique_id")
+    return bytes(buf)
+
+
+def comm_init(device_index: int, comm_id: bytes, rank: int, world: int, max_ctas: int = 0) -> None:
+    if len(comm_id) != COMM_ID_BYTES:
+        raise MMLError("communicator id must be 128 bytes")
+    c = Context.get(device_index)
+    buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(comm_id)
+    c.check(c.lib.mml_comm_init(c.handle, buf, int(rank), int(world), int(max_ctas)), "mml_comm_init")
+
+
+def comm_world(device_index: int) -> int:
+    c = Context.get(device_index)
+    return int(c.lib.mml_comm_world(c.handle))
+
+
+def allreduce_bucket(buf) -> None:
+    """In-place fp32 sum all-reduce of ``buf`` over the context's communicator, on the current stream."""
+    ctx = _ctx(buf)
+    ctx.check(ctx.lib.mml_allreduce_bucket(ctx.handle, _p(buf, torch.float32), buf.numel(), _stream(buf)), "mml_allreduce_bucket")
+
+
 def debug_set(key: int, value: int) -> None:
     from ._lib import load_library
 

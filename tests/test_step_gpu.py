@@ -279,7 +279,6 @@ def test_device_prefetcher_batches_and_training_equivalence():
             else:
                 assert dev_b[k] == v
         n += 1
-    assert pf.chosen is None  # 5 batches are not enough to calibrate (4 candidates x 3 rounds)
     assert n == len(batches) and pf.h2d_bytes == sum(v.numel() * v.element_size() for b in batches for v in b.values() if torch.is_tensor(v))
     losses = []
     for use_pf in (False, True):
@@ -288,14 +287,8 @@ def test_device_prefetcher_batches_and_training_equivalence():
         it = DevicePrefetcher(iter(batches), DEV) if use_pf else iter(batches)
         losses.append([model.train_step(b, opt, LOSS, torch.device(DEV), None)["loss"] for b in it])
     assert np.allclose(losses[0], losses[1], rtol=2e-2, atol=2e-2), losses
-    # calibration: after candidates x rounds steps one copy stream (or "inline") is fixed for the device
-    model = build(dropout=0.0)
-    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
-    pf = DevicePrefetcher((batches[i % 5] for i in range(20)), DEV)
-    for b in pf:
-        model.train_step(b, opt, LOSS, torch.device(DEV), None)
-    assert pf.chosen in range(len(pf.candidates))
-    assert DevicePrefetcher(iter(batches), DEV).chosen == pf.chosen
+    # one dedicated high-priority copy stream per device, shared by every prefetcher
+    assert DevicePrefetcher(iter(batches), DEV).stream is pf.stream and pf.stream.priority < 0
 
 
 def test_adam_param_groups_follow_the_optimizer():
