@@ -451,18 +451,15 @@ stem_bn_pool_fwd_kernel(const uint16_t* __restrict__ x, BnTrain bn, const float*
     }
   }
   __syncthreads();
+  // One CTA walks output rows (n, p); its threads are (8-channel group) x (column q): no per-item 64-bit divisions (they cost more
+  // than the rest of the item: round 1 spent five long divisions per 16 output bytes here).
   const int c8 = C >> 3;
-  const long long total = (long long)N * P * Q * c8;
-  const long long stride = (long long)gridDim.x * kThreads;
-  long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
-  const int cg = (int)(i % c8);
+  const int cg = (int)threadIdx.x % c8, qs = (int)threadIdx.x / c8, nq = kThreads / c8;
   const F8 sc = load8f(s_coef + cg * 8), sh = load8f(s_coef + kMaxC + cg * 8);
-  for (; i < total; i += stride) {
-    long long t = i / c8;
-    const int q = (int)(t % Q);
-    t /= Q;
-    const int p = (int)(t % P);
-    const int n = (int)(t / P);
+  for (int row = blockIdx.x; row < N * P; row += gridDim.x) {
+    const int n = row / P, p = row - n * P;
+   for (int q = qs; q < Q; q += nq) {
+    const long long i = ((long long)row * Q + q) * c8 + cg;
     float best[8];
     int idx[8];
 #pragma unroll
@@ -500,6 +497,7 @@ stem_bn_pool_fwd_kernel(const uint16_t* __restrict__ x, BnTrain bn, const float*
     a.x = (uint32_t)idx[0] | ((uint32_t)idx[1] << 8) | ((uint32_t)idx[2] << 16) | ((uint32_t)idx[3] << 24);
     a.y = (uint32_t)idx[4] | ((uint32_t)idx[5] << 8) | ((uint32_t)idx[6] << 16) | ((uint32_t)idx[7] << 24);
     *reinterpret_cast<uint2*>(amax + i * 8) = a;
+   }
   }
 }
 
@@ -561,19 +559,14 @@ stem_bn_pool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restr
   __shared__ float sh[kThreads][9];
   const int c4 = C >> 2;
   const int HB = (H + 1) >> 1, WB = (W + 1) >> 1;
-  const long long total = (long long)N * HB * WB * c4;
-  const long long stride = (long long)gridDim.x * kThreads;
-  long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
-  const int cg = (int)(i % c4);
+  // One CTA walks block rows (n, a); its threads are (4-channel group) x (block column b): no per-item 64-bit divisions
+  const int cg = (int)threadIdx.x % c4, bs = (int)threadIdx.x / c4, nb = kThreads / c4;
   const float4 mu = *reinterpret_cast<const float4*>(mean + cg * 4), is = *reinterpret_cast<const float4*>(invstd + cg * 4);
   const float4 ga = *reinterpret_cast<const float4*>(gamma + cg * 4), be = *reinterpret_cast<const float4*>(beta + cg * 4);
   float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};
-  for (; i < total; i += stride) {
-    long long t = i / c4;
-    const int b = (int)(t % WB);
-    t /= WB;
-    const int a = (int)(t % HB);
-    const int n = (int)(t / HB);
+  for (int row = blockIdx.x; row < N * HB; row += gridDim.x) {
+    const int n = row / HB, a = row - n * HB;
+   for (int b = bs; b < WB; b += nb) {
     // gradients and argmax bytes of the (up to) four pooling windows p in {a, a+1}, q in {b, b+1} that cover this block
     float gw[2][2][4];
     uint32_t am[2][2];
@@ -641,6 +634,7 @@ stem_bn_pool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restr
         }
       }
     }
+   }
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -870,7 +864,7 @@ int mml_stem_bn_pool_fwd(mml_ctx* ctx, const uint16_t* x, const double* stats, c
   if (rc) return rc;
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
   const int64_t rows = (int64_t)N * H * W;
-  const int grid = ew_grid(ctx, (long long)N * P * Q * (C / 8));
+  int grid = N * P < ctx->sm_count * 8 ? N * P : ctx->sm_count * 8;  // CTAs walk output rows (n, p)
   BnTrain bn{stats, gamma, beta, running_mean, running_var, save_mean, save_invstd};
   cudaStream_t st = (cudaStream_t)stream;
   if (stats) {
@@ -893,12 +887,10 @@ int mml_stem_bn_pool_bwd(mml_ctx* ctx, const uint16_t* dy, const uint16_t* dy2, 
   if (rc) return rc;
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
   MML_REQUIRE(ctx, kThreads % (C / 4) == 0, "stem_bn_pool_bwd: C/4 must divide %d", kThreads);
-  const long long items = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
   const float inv_count = 1.0f / (float)((int64_t)N * H * W);
   cudaStream_t st = (cudaStream_t)stream;
-  int g0 = (int)mml_ceil_div(items, (long long)kThreads * 2);
-  if (g0 > ctx->sm_count * 6) g0 = ctx->sm_count * 6;
-  if (g0 < 1) g0 = 1;
+  const int brows = N * ((H + 1) / 2);  // CTAs walk block rows (n, a)
+  int g0 = brows < ctx->sm_count * 6 ? brows : ctx->sm_count * 6;
   MML_LAUNCH(ctx, stem_bn_pool_bwd_kernel, g0, kThreads, 0, st, dy, dy2, argmax, x, mean, invstd, gamma, beta, bstat, dx, N, H, W, C, P, Q);
   // pass 2 in place over the buffer that now holds g: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))
   const long long n8 = (long long)N * H * W * (C / 8);

@@ -277,7 +277,7 @@ stem_fprop_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
         stat_add(stats, 64, (int)blockIdx.x, c0 + 1, a.y + b2.y + c2.y + d2.y, a.w + b2.w + c2.w + d2.w);
       }
     }
-    if (threadIdx.x == 0) tma_store_wait_all<0>();
+    if (threadIdx.x == 0) tma_store_wait_read<0>();
   }
   tc_fence_before();
   __syncthreads();

@@ -53,7 +53,7 @@ def forced_from_plan(plan, state):
             forced[pre + name] = nchw(t)
         forced[pre + "avgpool"] = ep.pooled.detach().cpu().clone()
         act = torch.nn.functional.batch_norm(forced[pre + "conv1"], None, None, state[pre + "bn1.weight"], state[pre + "bn1.bias"], True, 0.1, 1e-5)
-        forced[pre + "relu1"] = torch.relu(act).to(torch.bfloat16).float()
+        forced[pre + "relu1"] = torch.relu(act)  # fp32: the fused stem tail pools the un-rounded BatchNorm outputs and rounds only the winner
     return forced
 
 

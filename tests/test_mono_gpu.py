@@ -44,7 +44,7 @@ def forced_from_plan(ep, state):
     forced = {"encoder." + name: nchw(t) for name, t in ep.taps.items()}
     forced["encoder.avgpool"] = ep.pooled.detach().cpu().clone()
     act = torch.nn.functional.batch_norm(forced["encoder.conv1"], None, None, state["encoder.bn1.weight"], state["encoder.bn1.bias"], True, 0.1, 1e-5)
-    forced["encoder.relu1"] = torch.relu(act).to(torch.bfloat16).float()
+    forced["encoder.relu1"] = torch.relu(act)  # fp32: the fused stem tail pools the un-rounded BatchNorm outputs and rounds only the winner
     return forced
 
 

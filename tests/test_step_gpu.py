@@ -55,14 +55,15 @@ def nchw(t):
 
 def forced_from_plan(plan, state):
     """Activations the GPU stored, in the oracle's tap names.  The post-ReLU stem activation is never materialised by the
-    fused stem tail; it is rebuilt here exactly as the kernel forms it: bf16(relu(bn_train(raw stem output)))."""
+    fused stem tail; it is rebuilt here exactly as the kernel forms it: relu(bn_train(raw stem output)) in fp32 (the kernel takes
+    the window maximum of the fp32 values and rounds only the winner to bf16)."""
     forced = {}
     for pre, ep in (("audio_encoder.", plan.audio), ("image_encoder.", plan.image)):
         for name, t in ep.taps.items():
             forced[pre + name] = nchw(t)
         forced[pre + "avgpool"] = ep.pooled.detach().cpu().clone()
         act = torch.nn.functional.batch_norm(forced[pre + "conv1"], None, None, state[pre + "bn1.weight"], state[pre + "bn1.bias"], True, 0.1, 1e-5)
-        forced[pre + "relu1"] = torch.relu(act).to(torch.bfloat16).float()
+        forced[pre + "relu1"] = torch.relu(act)  # fp32: the fused stem tail pools the un-rounded BatchNorm outputs and rounds only the winner
     return forced
 
 
