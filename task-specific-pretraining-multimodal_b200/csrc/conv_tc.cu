@@ -591,10 +591,11 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // The issue rate of this single thread bounds small-N tiles (a 128x64x16 MMA executes in ~32 cycles), so everything
-    // per MMA is kept to a couple of uniform integer adds: descriptors are (lo, hi) pairs, hi is a constant, the nine tap
-    // row-shifts are precomputed, all loops are fully unrolled (the halo kernel always has 9 taps).  elect.sync (not
-    // lane == 0) lets the compiler keep the descriptors in uniform registers without a per-MMA election loop.
+    // Measured on B200 (round 2): a 128 x N x 16 MMA with FRESH descriptors costs ~57 + 1.0 N cycles here (122 at N = 64, 187 at
+    // N = 128) although it executes in N / 2 (issuing every MMA twice with the same descriptors added exactly 32 cycles each at
+    // N = 64).  A second issuing warp (alternate tiles, own accumulator) changed nothing, an 8-row-aligned A window changed
+    // nothing: the cost is not in this thread's instruction stream and not in the row shift, it is the operand fetch of a new
+    // descriptor pair.  Only N = 256 tiles amortise it; the 64- and 128-channel layers cannot have them (N = output channels).
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, B_MN ? 1 : 0);
       constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
@@ -688,6 +689,14 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
         tmem_ld_32x32(taddr, r0);
         tmem_ld_32x32(taddr + 32, r1);
         tmem_ld_wait();
+        // The accumulator is in registers now: hand the TMEM buffer back BEFORE packing / storing / statistics, so the MMAs of
+        // iteration it + 2 run under the rest of this epilogue (round 1 released it at the end of the iteration, and the MMA
+        // warp spent ~500 cycles per tile waiting for it: profiles/r2_ncu_halo_l1_hot.txt).
+        if (L::kUnits == 1 || u == L::kUnits - 2 + gi) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(ab));
+        }
         if (eg == 0) tma_store_wait_read<0>();  // this group's previous TMA store has finished reading the staging buffer
         named_bar_sync(bar_id, 128);
         const uint32_t row_addr = stage + row * 128;
@@ -725,9 +734,6 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
           else st_acc1.x += s0, st_acc1.y += s1, st_acc1.z += q0, st_acc1.w += q1;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty(ab));
     }
     if (p.stats != nullptr) {  // one atomic per channel, group and CTA
       float4* sc = stat_scratch + gi * 128;
