@@ -134,6 +134,28 @@ int mml_stem_bn_pool_fwd(mml_ctx*, const uint16_t* x, const double* stats, const
 int mml_stem_bn_pool_bwd(mml_ctx*, const uint16_t* dy, const uint16_t* dy2, const uint8_t* argmax, const uint16_t* x, const float* mean,
                          const float* invstd, const float* gamma, const float* beta, double* bstat, float* dgamma, float* dbeta, uint16_t* dx,
                          int N, int H, int W, int C, void* stream);
+/* ---- ConvBlock encoders (MML_Suite/models/conv.py:16-59, models/avmnist.py:34-185: MNISTAudio / MNISTImage) ----
+ * First convolution of a ConvBlock encoder: Conv2d(1, K, 3, stride 1, padding 1) over (x * mask) (fp32 [B][H][W], mask [B] or NULL), weights
+ * fp32 [K][9], K in {8,16,32,64}; output NHWC bf16 with the channel dimension PADDED to 64 (channels >= K written as zeros) so that every later
+ * layer is a 64-channel tensor-core convolution; stats as mml_conv_fprop with C = 64.  The bias is not an argument: see mml_bn_conv_bias_fold. */
+int mml_conv3x3_c1_fprop(mml_ctx*, const float* x, const float* mask, const float* w, uint16_t* y, double* stats, int B, int H, int W, int K,
+                         void* stream);
+/* its weight gradient dw fp32 [K][9] (OVERWRITTEN; deterministic: per-CTA partials in `workspace`, added in a fixed order) */
+int mml_conv3x3_c1_wgrad(mml_ctx*, const float* x, const float* mask, const uint16_t* dy, float* dw, float* workspace, int64_t workspace_bytes,
+                         int B, int H, int W, int K, void* stream);
+int64_t mml_conv3x3_c1_wgrad_workspace(const mml_ctx*, int B, int H, int K);
+/* nn.MaxPool2d(kernel_size = k) (stride k, no padding, floor): x NHWC bf16 [B][H][W][C] -> y NHWC bf16 [B][H/k][W/k][C] and / or y_flat_nchw
+ * fp32 [B][C*(H/k)*(W/k)] in nn.Flatten order (either may be NULL); argmax uint8 = r*k+s of the first maximum.  Backward takes the gradient in
+ * exactly one of the two layouts and writes dx (zeros where the window maximum was elsewhere and in the rows / columns the floor drops). */
+int mml_maxpool_k_fwd(mml_ctx*, const uint16_t* x, uint16_t* y, float* y_flat_nchw, uint8_t* argmax, int B, int H, int W, int C, int k,
+                      void* stream);
+int mml_maxpool_k_bwd(mml_ctx*, const uint16_t* dy, const float* dy_flat_nchw, const uint8_t* argmax, uint16_t* dx, int B, int H, int W, int C,
+                      int k, void* stream);
+/* Conv2d bias in front of a BatchNorm2d (conv.py:24-45): running_mean += momentum * bias (train; pass scale = shift = NULL) or
+ * shift += bias * scale (eval coefficients of mml_bn_eval_coeffs; pass running_mean = NULL). */
+int mml_bn_conv_bias_fold(mml_ctx*, const float* conv_bias, int C, float momentum, float* running_mean, const float* scale, float* shift,
+                          void* stream);
+
 int mml_avgpool_fwd(mml_ctx*, const uint16_t* x, float* y, int N, int HW, int C, void* stream);
 int mml_avgpool_bwd(mml_ctx*, const float* dy, uint16_t* dx, int N, int HW, int C, void* stream);
 
@@ -271,11 +293,11 @@ int mml_relumax_fwd(mml_ctx*, const uint16_t* conv, const float* bias, const uin
 int mml_relumax_bwd(mml_ctx*, const float* dy, const int32_t* arg, const uint8_t* keep, float keep_scale, uint16_t* dconv, float* dbias, int B,
                     int P, int C, int ldy, int y_off, void* stream);
 /* small-batch dense layer (textcnn.py:25-28 embd, classifier.py:100-117): y = dropout(relu(x W^T + b)); x [B][ldx], y [B][ldy] (so the
- * concatenation of embeddings is a column offset), keep uint8 [B][N] or NULL.  Backward (dy [B][N] is overwritten by the gradient at the
+ * concatenation of embeddings is a column offset), keep uint8 [B][N] or NULL.  Backward (dy [B][lddy] is overwritten by the gradient at the
  * pre-activation): dx [B][lddx] (optional), dw [N][K], db [N] (stored). */
 int mml_dense_fwd(mml_ctx*, const float* x, int ldx, const float* w, const float* bias, const uint8_t* keep, float keep_scale, int relu,
                   float* y, int ldy, int B, int K, int N, void* stream);
-int mml_dense_bwd(mml_ctx*, float* dy, const float* y, int ldy, const uint8_t* keep, float keep_scale, int relu, const float* x, int ldx,
+int mml_dense_bwd(mml_ctx*, float* dy, int lddy, const float* y, int ldy, const uint8_t* keep, float keep_scale, int relu, const float* x, int ldx,
                   const float* w, float* dx, int lddx, float* dw, float* db, int B, int K, int N, void* stream);
 /* torch.nn.utils.clip_grad_norm_ (utt_fusion.py:181-182) folded into the optimizer: norm = ||g||_2 * base_scale over the flat gradient
  * buffer, hyper[row][5] = base_scale * min(1, clip / (norm + 1e-6)) for rows 0..groups-1 (the Adam kernel multiplies gradients by it);

@@ -6,6 +6,7 @@ Sub-modules (imported lazily so that ``import mml_b200`` works on a CPU-only box
   resnet    ResNetEncoder / ResNet18 / ResNet34 (same ctor, state_dict and forward contract as the reference)
   avmnist   AVMNIST late-fusion model: forward / train_step / validation_step / get_embeddings
   engine    the fused training / inference step (static buffers, kernel schedule, CUDA graph)
+  convblock ConvBlock / MNISTAudio / MNISTImage encoders (train_avmnist.yaml) and their fused step
   mmimdb    MMIMDb gated late-fusion model (config 3) + gated_engine, its fused step
   mono      MonomodalEncoder (encoder pre-training: one ResNet encoder + Linear + CE)
   data      missing-modality patterns and on-device mask application

@@ -80,6 +80,12 @@ SIGNATURES = {
     "mml_maxpool3x3s2_bwd": (I32, [P, P, P, P, P, I32, I32, I32, I32, P]),
     "mml_stem_bn_pool_fwd": (I32, [P] * 13 + [I32, I32, I32, I32, F32, F32, P]),
     "mml_stem_bn_pool_bwd": (I32, [P] * 13 + [I32, I32, I32, I32, P]),
+    "mml_conv3x3_c1_fprop": (I32, [P, P, P, P, P, P, I32, I32, I32, I32, P]),
+    "mml_conv3x3_c1_wgrad": (I32, [P, P, P, P, P, P, I64, I32, I32, I32, I32, P]),
+    "mml_conv3x3_c1_wgrad_workspace": (I64, [P, I32, I32, I32]),
+    "mml_maxpool_k_fwd": (I32, [P, P, P, P, P, I32, I32, I32, I32, I32, P]),
+    "mml_maxpool_k_bwd": (I32, [P, P, P, P, P, I32, I32, I32, I32, I32, P]),
+    "mml_bn_conv_bias_fold": (I32, [P, P, I32, F32, P, P, P, P]),
     "mml_avgpool_fwd": (I32, [P, P, P, I32, I32, I32, P]),
     "mml_avgpool_bwd": (I32, [P, P, P, I32, I32, I32, P]),
     "mml_head_scratch_per_sample": (I32, [C.POINTER(HeadParams)]),
@@ -106,7 +112,7 @@ SIGNATURES = {
     "mml_relumax_fwd": (I32, [P, P, P, P, F32, P, P, I32, I32, I32, I32, I32, P]),
     "mml_relumax_bwd": (I32, [P, P, P, P, F32, P, P, I32, I32, I32, I32, I32, P]),
     "mml_dense_fwd": (I32, [P, P, I32, P, P, P, F32, I32, P, I32, I32, I32, I32, P]),
-    "mml_dense_bwd": (I32, [P, P, P, I32, P, F32, I32, P, I32, P, P, I32, P, P, I32, I32, I32, P]),
+    "mml_dense_bwd": (I32, [P, P, I32, P, I32, P, F32, I32, P, I32, P, P, I32, P, P, I32, I32, I32, P]),
     "mml_clip_grad_scale": (I32, [P, P, I64, F32, F32, P, I32, P, P, P]),
     "mml_adam_step": (I32, [P, P, P, P, P, P, I64, P, P, I32, P]),
     "mml_cast_f32_bf16": (I32, [P, P, P, I64, P]),

@@ -89,9 +89,17 @@ class AVMNIST(nn.Module):
             device = torch.device("cuda", torch.cuda.current_device())
         eng = self._engine
         if eng is None or eng.device != device:
-            eng = self._engine = LateFusionEngine(self, device, self.dropout_p)
-            self.audio_encoder._mml_owner = (weakref.ref(eng), "audio_encoder.")
-            self.image_encoder._mml_owner = (weakref.ref(eng), "image_encoder.")
+            from .convblock import _ConvBlockEncoder, make_engine
+
+            kinds = {isinstance(e, _ConvBlockEncoder) for e in (self.audio_encoder, self.image_encoder)}
+            if kinds == {True}:  # AVMNIST(MNISTAudio, MNISTImage): configs/avmnist/centralised/train_avmnist.yaml
+                eng = self._engine = make_engine(self, device, self.dropout_p)
+            elif kinds == {False}:
+                eng = self._engine = LateFusionEngine(self, device, self.dropout_p)
+                self.audio_encoder._mml_owner = (weakref.ref(eng), "audio_encoder.")
+                self.image_encoder._mml_owner = (weakref.ref(eng), "image_encoder.")
+            else:
+                raise NotImplementedError("mixing a ResNet encoder with a ConvBlock encoder is not a configuration of the reference")
             if self._dp is not None:
                 self._dp.attach(eng)
         eng.fs.ensure_fresh()

@@ -222,36 +222,36 @@ __global__ void __launch_bounds__(256) dense_fwd_kernel(const float* __restrict_
 
 // backward of one dense layer: dpre = dy * (keep ? scale : 1) * (relu ? y > 0 : 1) in place in dy; then dx[b][k] = sum_o dpre[b][o] w[o][k],
 // dw[o][k] = sum_b dpre[b][o] x[b][k], db[o] = sum_b dpre[b][o]   (dw / db STORED).  Three small kernels.
-__global__ void dense_bwd_act_kernel(float* __restrict__ dy, const float* __restrict__ y, int ldy, const uint8_t* __restrict__ keep,
+__global__ void dense_bwd_act_kernel(float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, const uint8_t* __restrict__ keep,
                                      float keep_scale, int relu, int B, int N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * N) return;
   const int b = i / N, o = i - b * N;
-  float g = dy[i];
+  float g = dy[(size_t)b * lddy + o];
   if (keep) g = keep[i] ? g * keep_scale : 0.f;
   if (relu && !(y[(size_t)b * ldy + o] > 0.f)) g = 0.f;
-  dy[i] = g;
+  dy[(size_t)b * lddy + o] = g;
 }
 
-__global__ void dense_bwd_data_kernel(const float* __restrict__ dpre, const float* __restrict__ w, float* __restrict__ dx, int lddx, int B,
-                                      int K, int N) {
+__global__ void dense_bwd_data_kernel(const float* __restrict__ dpre, int ldd, const float* __restrict__ w, float* __restrict__ dx, int lddx,
+                                      int B, int K, int N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * K) return;
   const int b = i / K, k = i - b * K;
   float acc = 0.f;
 #pragma unroll 4
-  for (int o = 0; o < N; ++o) acc = fmaf(dpre[(size_t)b * N + o], w[(size_t)o * K + k], acc);
+  for (int o = 0; o < N; ++o) acc = fmaf(dpre[(size_t)b * ldd + o], w[(size_t)o * K + k], acc);
   dx[(size_t)b * lddx + k] = acc;
 }
 
-__global__ void dense_bwd_weight_kernel(const float* __restrict__ dpre, const float* __restrict__ x, int ldx, float* __restrict__ dw,
+__global__ void dense_bwd_weight_kernel(const float* __restrict__ dpre, int ldd, const float* __restrict__ x, int ldx, float* __restrict__ dw,
                                         float* __restrict__ db, int B, int K, int N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * K) return;
   const int o = i / K, k = i - o * K;
   float acc = 0.f, sb = 0.f;
   for (int b = 0; b < B; ++b) {
-    const float d = dpre[(size_t)b * N + o];
+    const float d = dpre[(size_t)b * ldd + o];
     acc = fmaf(d, x[(size_t)b * ldx + k], acc);
     sb += d;
   }
@@ -352,17 +352,17 @@ int mml_dense_fwd(mml_ctx* ctx, const float* x, int ldx, const float* w, const f
   return MML_OK;
 }
 
-int mml_dense_bwd(mml_ctx* ctx, float* dy, const float* y, int ldy, const uint8_t* keep, float keep_scale, int relu, const float* x, int ldx,
+int mml_dense_bwd(mml_ctx* ctx, float* dy, int lddy, const float* y, int ldy, const uint8_t* keep, float keep_scale, int relu, const float* x, int ldx,
                   const float* w, float* dx, int lddx, float* dw, float* db, int B, int K, int N, void* stream) {
-  MML_REQUIRE(ctx, ctx && dy && y && x && w && dw && db && B >= 1 && K >= 1 && N >= 1, "dense_bwd: bad arguments");
+  MML_REQUIRE(ctx, ctx && dy && y && x && w && dw && db && B >= 1 && K >= 1 && N >= 1 && lddy >= N, "dense_bwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  dense_bwd_act_kernel<<<(unsigned)mml_ceil_div((int64_t)B * N, 256), 256, 0, st>>>(dy, y, ldy, keep, keep_scale, relu, B, N);
+  dense_bwd_act_kernel<<<(unsigned)mml_ceil_div((int64_t)B * N, 256), 256, 0, st>>>(dy, lddy, y, ldy, keep, keep_scale, relu, B, N);
   MML_LAUNCHED(ctx);
   if (dx) {
-    dense_bwd_data_kernel<<<(unsigned)mml_ceil_div((int64_t)B * K, 256), 256, 0, st>>>(dy, w, dx, lddx, B, K, N);
+    dense_bwd_data_kernel<<<(unsigned)mml_ceil_div((int64_t)B * K, 256), 256, 0, st>>>(dy, lddy, w, dx, lddx, B, K, N);
     MML_LAUNCHED(ctx);
   }
-  dense_bwd_weight_kernel<<<(unsigned)mml_ceil_div((int64_t)N * K, 256), 256, 0, st>>>(dy, x, ldx, dw, db, B, K, N);
+  dense_bwd_weight_kernel<<<(unsigned)mml_ceil_div((int64_t)N * K, 256), 256, 0, st>>>(dy, lddy, x, ldx, dw, db, B, K, N);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }

@@ -39,11 +39,17 @@ def _round_up(n: int, a: int) -> int:
 # flat parameter / buffer storage
 # =====================================================================================================================
 class FlatState:
-    def __init__(self, module: nn.Module, device: torch.device, augment: Optional[Dict[str, str]] = None):
+    def __init__(self, module: nn.Module, device: torch.device, augment: Optional[Dict[str, str]] = None,
+                 pad: Optional[Dict[str, int]] = None):
         """``augment`` = {linear weight name: its bias name}: such a pair is stored as ONE [out][ld] matrix, ld = in + 1
         rounded up to 64, with the bias in column ``in`` (the tensor-core GEMM then adds the bias through a constant-1
-        activation column and its wgrad yields the bias gradient); ``weight`` / ``bias`` stay visible as strided views."""
+        activation column and its wgrad yields the bias gradient); ``weight`` / ``bias`` stay visible as strided views.
+
+        ``pad`` = {parameter or buffer name: channel count Cp}: a conv weight [K,C,R,S] is stored as [Cp,R,S,Cp] and a per-channel
+        vector [C] as [Cp], zero outside the logical part (narrow layers run as Cp-channel tensor-core convolutions; padded
+        weights, gradients and Adam moments are zero and stay zero); PyTorch sees the logical slice as a strided view."""
         self.module = module
+        self.pad: Dict[str, int] = dict(pad or {})
         self.aug: Dict[str, Tuple[int, int, int, int]] = {}  # weight or bias name -> (offset, out, in, ld)
         augment = augment or {}
         aug_bias = set(augment.values())
@@ -51,7 +57,6 @@ class FlatState:
         self.param_names: List[str] = []
         self.offsets: Dict[str, int] = {}
         self.numels: Dict[str, int] = {}
-        self.tc_convs: List[Tuple[str, int, int, int, int]] = []  # (name, offset, K, RS, C) of tensor-core conv weights
         off = 0
         for name, p in module.named_parameters():
             self.param_names.append(name)
@@ -66,11 +71,8 @@ class FlatState:
                 off = _round_up(off + n_out * ld, ALIGN)
                 continue
             self.offsets[name] = off
-            self.numels[name] = p.numel()
-            if p.dim() == 4 and p.shape[1] >= 64:
-                K, Cc, R, S = p.shape
-                self.tc_convs.append((name, off, K, R * S, Cc))
-            off = _round_up(off + p.numel(), ALIGN)
+            self.numels[name] = self._padded_numel(name, p)
+            off = _round_up(off + self.numels[name], ALIGN)
         self.total = off
         self.P = torch.zeros(off, device=device)
         self.G = torch.zeros(off, device=device)
@@ -85,7 +87,7 @@ class FlatState:
                 nbt.append(name)
             else:
                 self.buf_offsets[name] = soff
-                soff = _round_up(soff + b.numel(), 4)
+                soff = _round_up(soff + self._padded_numel(name, b), 4)
         self.S = torch.zeros(max(soff, 4), device=device)
         self.nbt_names = nbt
         self.NBT = torch.zeros(max(len(nbt), 1), device=device, dtype=torch.int64)
@@ -99,6 +101,18 @@ class FlatState:
         self._plist = list(module.parameters())
         self.bind(copy_in=True)
 
+    def _padded_numel(self, name: str, t: torch.Tensor) -> int:
+        cp = self.pad.get(name)
+        if cp is None:
+            return t.numel()
+        if t.dim() == 4:
+            if t.shape[0] > cp or t.shape[1] > cp:
+                raise ValueError(f"{name}: shape {tuple(t.shape)} exceeds the padded channel count {cp}")
+            return cp * cp * t.shape[2] * t.shape[3]
+        if t.dim() != 1 or t.numel() > cp:
+            raise ValueError(f"{name}: only conv weights and per-channel vectors can be padded")
+        return cp
+
     # -- views ------------------------------------------------------------------------------------------------
     def _view(self, flat: torch.Tensor, name: str, like: torch.Tensor) -> torch.Tensor:
         if name in self.aug:
@@ -107,9 +121,14 @@ class FlatState:
             return m[:, :n_in] if like.dim() == 2 else m[:, n_in]
         o, n = self.offsets[name], self.numels[name]
         v = flat[o:o + n]
+        cp = self.pad.get(name)
         if like.dim() == 4:
             K, Cc, R, S = like.shape
+            if cp is not None:
+                return v.view(cp, R, S, cp).permute(0, 3, 1, 2)[:K, :Cc]
             return v.view(K, R, S, Cc).permute(0, 3, 1, 2)  # OIHW view of K,R,S,C storage (channels_last)
+        if cp is not None:
+            return v[:like.numel()]
         return v.view(like.shape)
 
     def flat_slice(self, flat: torch.Tensor, name: str) -> torch.Tensor:
@@ -133,7 +152,7 @@ class FlatState:
             bufs = dict(self.module.named_buffers())
             for name, o in self.buf_offsets.items():
                 b = bufs[name]
-                v = self.S[o:o + b.numel()].view(b.shape)
+                v = self.S[o:o + b.numel()].view(b.shape)  # a padded buffer's tail (zeros) follows in S
                 if copy_in:
                     v.copy_(b.to(self.device, torch.float32))
                 self._set_buffer(name, v)

@@ -221,6 +221,49 @@ def stem_bn_pool_bwd(dy, dy2, argmax, x, bn: "BNBuffers", bstat, dgamma, dbeta, 
                                            _stream(dy)), "stem_bn_pool_bwd")
 
 
+# ---- ConvBlock encoders (MNISTAudio / MNISTImage, models/avmnist.py:34-185) -----------------------------------------------
+def conv3x3_c1_fprop(x, mask, w, y, stats, K: int) -> None:
+    """Conv2d(1, K, 3, padding=1) of (x * mask); y NHWC bf16 [B,H,W,64] (channels >= K zero)."""
+    B, H, W = x.shape
+    c = _ctx(x)
+    c.check(c.lib.mml_conv3x3_c1_fprop(c.handle, _p(x, torch.float32), _p(mask, torch.float32), _p(w, torch.float32), _p(y, torch.bfloat16),
+                                       _p(stats, torch.float64), B, H, W, int(K), _stream(x)), "mml_conv3x3_c1_fprop")
+
+
+def conv3x3_c1_wgrad_workspace(x, K: int) -> int:
+    c = _ctx(x)
+    return int(c.lib.mml_conv3x3_c1_wgrad_workspace(c.handle, x.shape[0], x.shape[1], int(K)))
+
+
+def conv3x3_c1_wgrad(x, mask, dy, dw, workspace, K: int) -> None:
+    B, H, W = x.shape
+    c = _ctx(x)
+    c.check(c.lib.mml_conv3x3_c1_wgrad(c.handle, _p(x, torch.float32), _p(mask, torch.float32), _p(dy, torch.bfloat16), _p(dw, torch.float32),
+                                       _p(workspace, torch.float32), workspace.numel() * 4, B, H, W, int(K), _stream(x)), "mml_conv3x3_c1_wgrad")
+
+
+def maxpool_k_fwd(x, y, y_flat, argmax, k: int) -> None:
+    """nn.MaxPool2d(k): x NHWC bf16 -> y NHWC bf16 and / or y_flat fp32 [B, C*P*Q] (nn.Flatten order)."""
+    B, H, W, Cn = x.shape
+    c = _ctx(x)
+    c.check(c.lib.mml_maxpool_k_fwd(c.handle, _p(x, torch.bfloat16), _p(y, torch.bfloat16), _p(y_flat, torch.float32), _p(argmax, torch.uint8),
+                                    B, H, W, Cn, int(k), _stream(x)), "mml_maxpool_k_fwd")
+
+
+def maxpool_k_bwd(dy, dy_flat, argmax, dx, k: int) -> None:
+    B, H, W, Cn = dx.shape
+    c = _ctx(dx)
+    c.check(c.lib.mml_maxpool_k_bwd(c.handle, _p(dy, torch.bfloat16), _p(dy_flat, torch.float32), _p(argmax, torch.uint8), _p(dx, torch.bfloat16),
+                                    B, H, W, Cn, int(k), _stream(dx)), "mml_maxpool_k_bwd")
+
+
+def bn_conv_bias_fold(conv_bias, momentum: float, running_mean=None, scale=None, shift=None) -> None:
+    c = _ctx(conv_bias)
+    f = torch.float32
+    c.check(c.lib.mml_bn_conv_bias_fold(c.handle, _p(conv_bias, f), conv_bias.numel(), float(momentum), _p(running_mean, f), _p(scale, f),
+                                        _p(shift, f), _stream(conv_bias)), "mml_bn_conv_bias_fold")
+
+
 def avgpool_fwd(x, y, N, HW, Cn) -> None:
     ctx = _ctx(x)
     ctx.check(ctx.lib.mml_avgpool_fwd(ctx.handle, _p(x, BF16), _p(y, torch.float32), N, HW, Cn, _stream(x)), "avgpool_fwd")
@@ -555,11 +598,11 @@ def dense_fwd(x, ldx: int, w, bias, keep, keep_scale: float, relu: bool, y, ldy:
                                 int(relu), C.c_void_p(y.data_ptr()), int(ldy), B, K, N, _stream(w)), "mml_dense_fwd")
 
 
-def dense_bwd(dy, y, ldy: int, keep, keep_scale: float, relu: bool, x, ldx: int, w, dx, lddx: int, dw, db, B: int) -> None:
+def dense_bwd(dy, y, ldy: int, keep, keep_scale: float, relu: bool, x, ldx: int, w, dx, lddx: int, dw, db, B: int, lddy: int = 0) -> None:
     N, K = w.shape
     c = _ctx(w)
     f = torch.float32
-    c.check(c.lib.mml_dense_bwd(c.handle, _p(dy, f), C.c_void_p(y.data_ptr()), int(ldy), _p(keep, torch.uint8), float(keep_scale), int(relu),
+    c.check(c.lib.mml_dense_bwd(c.handle, C.c_void_p(dy.data_ptr()), int(lddy) or N, C.c_void_p(y.data_ptr()), int(ldy), _p(keep, torch.uint8), float(keep_scale), int(relu),
                                 C.c_void_p(x.data_ptr()), int(ldx), _p(w, f), C.c_void_p(dx.data_ptr()) if dx is not None else C.c_void_p(0), int(lddx),
                                 _p(dw, f), _p(db, f), B, K, N, _stream(w)), "mml_dense_bwd")
 

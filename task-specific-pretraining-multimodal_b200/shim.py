@@ -5,6 +5,7 @@
 What it re-binds (reference file:line):
   * YAML tags ``!ResNet18`` / ``!ResNet34`` / ``!ResNetEncoder`` (MML_Suite/config/yaml_constructors.py:159-178) ->
     ``mml_b200.resnet`` factories (``yaml.SafeLoader.add_constructor`` replaces the earlier registration);
+  * YAML tags ``!MNISTAudio`` / ``!MNISTImage`` / ``!ConvBlockArgs`` / ``!ConvBlock`` (yaml_constructors.py:70-86) -> ``mml_b200.convblock``;
   * ``resolve_model_name("avmnist")`` (MML_Suite/config/resolvers.py:18-22 does ``from models.avmnist import AVMNIST``
     at call time) -> the attribute ``models.avmnist.AVMNIST`` is replaced by ``mml_b200.avmnist.AVMNIST``;
   * ``models.msa.networks.resnet.ResNet18/ResNet34/ResNetEncoder`` for scripts that import them directly
@@ -38,6 +39,11 @@ def install(patch_reference_modules: bool = True) -> Dict[str, object]:
     register("!ResNet18", ResNet18)
     register("!ResNet34", ResNet34)
     register("!ResNetEncoder", ResNetEncoder)
+    from . import convblock as _cb
+
+    # yaml_constructors.py:70-86 (train_avmnist.yaml builds AVMNIST from these four tags)
+    for cname in ("MNISTAudio", "MNISTImage", "ConvBlockArgs", "ConvBlock"):
+        register("!" + cname, getattr(_cb, cname))
     from . import mmimdb as _mm
 
     gated = {"MMIMDb": _mm.MMIMDb, "MMIMDbModalityEncoder": _mm.MMIMDbModalityEncoder, "GatedBiModalNetwork": _mm.GatedBiModalNetwork,
@@ -54,6 +60,10 @@ def install(patch_reference_modules: bool = True) -> Dict[str, object]:
         if ref_av is not None:
             _installed["reference.AVMNIST"] = getattr(ref_av, "AVMNIST", None)
             ref_av.AVMNIST = AVMNIST
+            ref_av.MNISTAudio, ref_av.MNISTImage = _cb.MNISTAudio, _cb.MNISTImage
+        ref_conv = sys.modules.get("models.conv")
+        if ref_conv is not None:
+            ref_conv.ConvBlock, ref_conv.ConvBlockArgs = _cb.ConvBlock, _cb.ConvBlockArgs
         ref_mm = sys.modules.get("models.mmimdb")
         if ref_mm is not None:
             _installed["reference.MMIMDb"] = getattr(ref_mm, "MMIMDb", None)

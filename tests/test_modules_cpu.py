@@ -270,6 +270,55 @@ def test_flat_state_layout_and_param_group_ranges(monkeypatch):
         fs.adopt_optimizer(torch.optim.SGD(net.parameters(), lr=0.1))
 
 
+def test_convblock_modules_match_reference_surface_and_padded_storage(monkeypatch):
+    """MNISTAudio / MNISTImage / ConvBlock (avmnist.py:34-185, conv.py:16-59): same constructor keywords, state_dict names, shapes and
+    initial values as the oracle's restatement of the reference; FlatState(pad=...) stores narrow layers as 64-channel tensors with a
+    zero tail and exposes the logical slice."""
+    from mml_b200 import engine, ops
+    from mml_b200.avmnist import AVMNIST
+    from mml_b200.convblock import CP, ConvBlock, ConvBlockArgs, MNISTAudio, MNISTImage, pad_map
+
+    monkeypatch.setattr(ops, "cast_f32_bf16", lambda src, dst: dst.copy_(src))
+    A = ConvBlockArgs
+    torch.manual_seed(0)
+    au = MNISTAudio(conv_block_one_one_args=A(1, 32), conv_block_one_two_args=A(32, 32), conv_block_two_one_args=A(32, 64),
+                    conv_block_two_two_args=A(64, 64), hidden_dim=64, conv_batch_norm=True)
+    im = MNISTImage(A(1, 32), A(32, 64), A(64, 64), A(64, 64), 128, max_pool_kernel_size=(2, 2))
+    model = AVMNIST(au, im, 128, dropout=0.5)
+    torch.manual_seed(0)
+    ref = O.init_convblock_avmnist_state()
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    assert all(sd[k].shape == ref[k].shape and torch.equal(sd[k], ref[k]) for k in ref)
+    assert au.get_embedding_size() == 64 and im.get_embedding_size() == 128 and au.pool_k == [2, 3] and im.pool_k == [2, 2]
+    with pytest.raises(NotImplementedError):
+        ConvBlock(A(1, 32, conv_one_kernel_size=5), A(32, 32))
+    with pytest.raises(NotImplementedError):
+        MNISTAudio(A(1, 32), A(32, 32), A(32, 64), A(64, 64), 64, conv_batch_norm=False)
+    with pytest.raises(RuntimeError):  # no CPU path
+        au(torch.zeros(2, 32, 94))
+    pad = {**pad_map(au, "audio_encoder."), **pad_map(im, "image_encoder.")}
+    assert "audio_encoder.net.0.conv_one.weight" not in pad and pad["audio_encoder.net.0.conv_two.weight"] == CP
+    fs = engine.FlatState(model, torch.device("cpu"), pad=pad)
+    for k, v in model.state_dict().items():
+        assert v.shape == ref[k].shape and torch.equal(v, ref[k]), k
+    w = fs.flat_slice(fs.P, "audio_encoder.net.0.conv_two.weight").view(CP, 3, 3, CP)
+    assert float(w[32:].abs().max()) == 0.0 and float(w[..., 32:].abs().max()) == 0.0
+    assert torch.equal(w[:32, :, :, :32].permute(0, 3, 1, 2), ref["audio_encoder.net.0.conv_two.weight"])
+    gm = fs.flat_slice(fs.P, "audio_encoder.net.0.batch_norm_one.weight")
+    assert gm.numel() == CP and float(gm[:32].min()) == 1.0 and float(gm[32:].abs().max()) == 0.0
+    o = fs.buf_offsets["audio_encoder.net.0.batch_norm_one.running_var"]
+    assert float(fs.S[o:o + 32].min()) == 1.0 and float(fs.S[o + 32:o + CP].abs().max()) == 0.0  # padded variance 0 -> eval scale 0
+    # load_state_dict goes through the strided views; the padding stays zero
+    model.load_state_dict({k: (torch.full_like(v, 0.25) if v.is_floating_point() else v) for k, v in ref.items()})
+    assert float(w[:32, :, :, :32].min()) == 0.25 and float(w[32:].abs().max()) == 0.0 and float(w[..., 32:].abs().max()) == 0.0
+    assert model.audio_encoder.net[0].conv_two.weight.grad.shape == (32, 32, 3, 3)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
+    fs.adopt_optimizer(opt)
+    assert fs.ranges == [(0, fs.total, 0)]
+    assert opt.state[model.audio_encoder.net[0].conv_two.weight]["exp_avg"].shape == (32, 32, 3, 3)
+
+
 def test_batch_unpacking_follows_the_reference_batch_contracts():
     """Batch dict handling of the four step methods (keys are ``modalities.Modality`` members in the reference, str() lower-case)."""
     import enum
