@@ -413,6 +413,156 @@ def run_mono_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# --workload convblock: AVMNIST with the ConvBlock encoders (configs/avmnist/centralised/train_avmnist.yaml)
+# ---------------------------------------------------------------------------------------------------------------------
+def convblock_bytes_per_sample():
+    """Algorithmic HBM bytes of one train step per sample: every stored bf16 tensor at its REAL channel count, written once and read
+    once per consumer (DESIGN.md "ConvBlock path").  Per encoder, full resolution: 8 tensor passes forward + 20 backward; after the
+    first pool: 9 forward + 23 backward (+ argmax bytes, + the fp32 input)."""
+    total = 0
+    for (h, w), k1, chans in (((32, 94), 2, (32, 32, 64, 64)), ((28, 28), 2, (32, 64, 64, 64))):
+        px0, px1 = h * w, (h // k1) * (w // k1)
+        c1, c2, c3, c4 = chans
+        t = lambda px, c: px * c * 2  # noqa: E731
+        fwd = t(px0, c1) * 3 + t(px0, c1) + t(px0, c2) * 3 + t(px0, c2) + t(px1, c2) * 1.5   # conv1 w, bn r/w, conv2 r/w, bn r/w, pool r/w
+        fwd += t(px1, c2) + t(px1, c3) * 3 + t(px1, c3) + t(px1, c4) * 3 + t(px1, c4)         # block two
+        bwd = t(px0, c2) * 12 + t(px0, c1) * 8 + t(px1, c4) * 12 + t(px1, c3) * 9 + t(px1, c2) * 2
+        total += fwd + bwd + 2 * px0 * 4
+    return float(total)
+
+
+def run_convblock_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from mml_b200 import dist as mdist
+    from mml_b200.avmnist import AVMNIST
+    from mml_b200.convblock import ConvBlockArgs as CA
+    from mml_b200.convblock import MNISTAudio, MNISTImage
+    from mml_b200.data import DevicePrefetcher
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import late_fusion_oracle as O
+
+    B = args.batch
+    metric = "avmnist_convblock_late_fusion_train_samples_per_s"
+    cfg = {"workload": "AVMNIST late-fusion train step with the ConvBlock encoders (train_avmnist.yaml): MNISTAudio 32x94 + MNISTImage 28x28, "
+                       "concat head, CE, Adam; audio missing_rate 0.2", "batch_per_gpu": B,
+           "l2_policy": "per-step working set (~3 GB of bf16 activations at batch 256) exceeds the 126 MB L2; no explicit flush",
+           "timing": "CUDA events around K CUDA-graph replays, barrier + synchronize on both sides, max over ranks"}
+
+    def cpu_run(budget):
+        torch.set_num_threads(os.cpu_count() or 1)
+        torch.manual_seed(0)
+        st = O.init_convblock_avmnist_state()
+        d = O.synthetic_batch(CPU_SAMPLE_BATCH, 0, (32, 94))
+        A, I = O.apply_missing_mask(d["audio"], d["audio_mask"]), O.apply_missing_mask(d["image"], d["image_mask"])
+        os_, ts = {}, []
+        O.convblock_train_step(st, os_, A, I, d["labels"], d["dropout_mask"], 0.5)
+        t_begin = time.perf_counter()
+        while len(ts) < 3 or (time.perf_counter() - t_begin < budget and len(ts) < 50):
+            t0 = time.perf_counter()
+            O.convblock_train_step(st, os_, A, I, d["labels"], d["dropout_mask"], 0.5)
+            ts.append(time.perf_counter() - t0)
+        per = statistics.median(ts)
+        return {"value": CPU_SAMPLE_BATCH / per, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                "sample": f"{len(ts)} train steps of the ConvBlock oracle port at batch {CPU_SAMPLE_BATCH}, fp32, torch CPU, median step {per * 1e3:.0f} ms",
+                "steps_timed": len(ts), "ms_per_step": per * 1e3}
+
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            r = cpu_run(60.0)
+            _emit(json.dumps({"impl": "reference", "metric": metric, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps_timed"],
+                              "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                              "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                              "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+    rank, local_rank, world = mdist.init_from_env("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(0)
+    model = AVMNIST(MNISTAudio(CA(1, 32), CA(32, 32), CA(32, 64), CA(64, 64), 64), MNISTImage(CA(1, 32), CA(32, 64), CA(64, 64), CA(64, 64), 128),
+                    128, dropout=0.5).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
+    loss_fns = {"cross_entropy": _Term(torch.nn.CrossEntropyLoss())}
+    if world > 1:
+        dp = mdist.DataParallel()
+        model.enable_data_parallel(dp)
+    eng = model._get_engine(dev)
+    if world > 1:
+        dp.broadcast_state(eng)
+
+    def pinned(seed):
+        d = O.synthetic_batch(B, seed, (32, 94))
+        b = {"audio_original": d["audio"], "audio_missing_index": d["audio_mask"], "image_original": d["image"],
+             "image_missing_index": d["image_mask"], "labels": d["labels"]}
+        b = {k: v.pin_memory() for k, v in b.items()}
+        b["pattern_name"] = ["ai"] * B
+        return b
+
+    host = [pinned(100 * rank + i) for i in range(3)]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values() if torch.is_tensor(v))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        model.train_step(host[i % 3], opt, loss_fns, dev, None)
+    plan = next(iter(eng.plans.values()))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(40):
+        plan.train_step(False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        barrier()
+        e0.record()
+        fn()
+        e1.record()
+        barrier()
+        dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item())
+
+    def dev_loop():
+        for _ in range(args.steps):
+            plan.train_step(False)
+
+    def e2e_loop():
+        for b in DevicePrefetcher((host[i % 3] for i in range(args.steps)), dev):
+            model.train_step(b, opt, loss_fns, dev, None)
+
+    t_dev = timed(dev_loop)
+    eng.fs._host_step += args.steps + 40
+    t_e2e = timed(e2e_loop)
+    clocks = sampler.stop()
+    if rank != 0:
+        return
+    pk = peaks()
+    bytes_step = convblock_bytes_per_sample() * B
+    gbs = bytes_step * args.steps / t_dev / 1e9
+    cpu = cpu_run(15.0)
+    cfg.update({"global_batch": B * world, "parallelism": f"dp{world}"})
+    _emit(json.dumps({
+        "metric": metric, "value": B * world * args.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": cfg, "e2e": {"value": B * world * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                               "ms_per_step": t_e2e / args.steps * 1e3,
+                               "path": "pinned host batches -> mml_b200.data.DevicePrefetcher -> AVMNIST.train_step -> loss float"},
+        "gpu_launches": plan.launches_per_step * args.steps, "launches_per_step": plan.launches_per_step, "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None,
+                     "algorithmic_bytes_per_step": bytes_step,
+                     "note": "whole step: narrow (32/64-channel) convolutions over 32x94 / 28x28 maps are HBM-bound; algorithmic bytes count every "
+                             f"stored bf16 tensor at its real channel count (the kernels move 64-channel padded tensors), vs {pk['src']} HBM copy bandwidth"},
+        "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}}))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # --workload mosi: BASELINE config 4 (MOSI / UttFusion; configs/mosi/centralised/utt_fusion_base_training.yaml)
 # ---------------------------------------------------------------------------------------------------------------------
 def run_mosi_arm(args):
@@ -968,7 +1118,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU (BASELINE.json configs[1])")
-    ap.add_argument("--workload", default="avmnist", choices=["avmnist", "mmimdb", "mono", "mosi"],
+    ap.add_argument("--workload", default="avmnist", choices=["avmnist", "mmimdb", "mono", "mosi", "convblock"],
                     help="avmnist = the headline line (configs[1]); mmimdb = configs[2]; mono = monomodal audio-encoder pre-training; mosi = configs[3]")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: library chatter (e.g. "NCCL version ...") is diverted to stderr
@@ -982,6 +1132,8 @@ def main():
         run_mono_arm(args)
     elif args.workload == "mosi":
         run_mosi_arm(args)
+    elif args.workload == "convblock":
+        run_convblock_arm(args)
     elif args.impl == "reference":
         run_reference_arm(args)
     else:

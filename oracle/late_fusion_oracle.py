@@ -467,7 +467,7 @@ def monomodal_train_step(state: "OrderedDict[str, Tensor]", opt_state: Dict, x: 
 
 # ----------------------------------------------------------------------------------------------
 # 8f rank 4 -- AVMNIST with the ConvBlock encoders (models/avmnist.py:34-185, models/conv.py:16-59; configs/avmnist/centralised/
-# train_avmnist.yaml).  ORACLE ONLY in round 1: the CUDA path for 32-channel biased convolutions is not built.
+# train_avmnist.yaml).  CUDA path: mml_b200/convblock.py, parity in tests/test_convblock_gpu.py.
 # ----------------------------------------------------------------------------------------------
 CONVBLOCK_CHANNELS = {"audio_encoder": ((1, 32), (32, 32), (32, 64), (64, 64)), "image_encoder": ((1, 32), (32, 64), (64, 64), (64, 64))}
 CONVBLOCK_POOLS = {"audio_encoder": (2, 3), "image_encoder": (2, 2)}   # MaxPool2d kernel sizes (stride = kernel)
@@ -499,29 +499,42 @@ def init_convblock_avmnist_state(audio_hidden: int = 64, image_hidden: int = 128
     return st
 
 
-def convblock_encoder_forward(state: Dict[str, Tensor], enc: str, x: Tensor, training: bool) -> Tensor:
-    """MNISTAudio.forward / MNISTImage.forward (avmnist.py:108-118, 177-184)."""
+def convblock_encoder_forward(state: Dict[str, Tensor], enc: str, x: Tensor, training: bool, taps: Optional[Dict[str, Tensor]] = None,
+                              emulate_bf16: bool = False, forced: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    """MNISTAudio.forward / MNISTImage.forward (avmnist.py:108-118, 177-184).  ``taps`` / ``emulate_bf16`` / ``forced``: the testing
+    aids of resnet_forward (tap names: net.<slot>.conv_one, .relu_one, .conv_two, net.<slot> = block output, net.<slot+1> = pooled)."""
+    eb = emulate_bf16
     if x.dim() == 3:
         x = x.unsqueeze(1)
+
+    def pt(name: str, t: Tensor) -> Tensor:
+        key = f"{enc}.{name}"
+        if forced is not None and key in forced:
+            t = t + (forced[key][:, :t.shape[1]].to(t.dtype) - t).detach()  # the CUDA path stores 64-channel padded tensors
+        if taps is not None:
+            taps[key] = t
+        return t
+
+    x = _q(x, eb)
     for slot, pool in zip((0, 2), CONVBLOCK_POOLS[enc]):
         p = f"{enc}.net.{slot}"
-        x = F.conv2d(x, state[p + ".conv_one.weight"], state[p + ".conv_one.bias"], stride=1, padding=1)
-        x = F.relu(_batch_norm(state, p + ".batch_norm_one", x, training, True))
-        x = F.conv2d(x, state[p + ".conv_two.weight"], state[p + ".conv_two.bias"], stride=1, padding=1)
-        x = F.relu(_batch_norm(state, p + ".batch_norm_two", x, training, True))
-        x = F.max_pool2d(x, kernel_size=pool)
+        x = pt(f"net.{slot}.conv_one", _q(F.conv2d(_qg(x, eb), _qw(state[p + ".conv_one.weight"], eb), state[p + ".conv_one.bias"], stride=1, padding=1), eb))
+        x = pt(f"net.{slot}.relu_one", _q(F.relu(_batch_norm(state, p + ".batch_norm_one", x, training, True)), eb))
+        x = pt(f"net.{slot}.conv_two", _q(F.conv2d(x, _qw(state[p + ".conv_two.weight"], eb), state[p + ".conv_two.bias"], stride=1, padding=1), eb))
+        x = pt(f"net.{slot}", _q(F.relu(_batch_norm(state, p + ".batch_norm_two", x, training, True)), eb))
+        x = pt(f"net.{slot + 1}", F.max_pool2d(x, kernel_size=pool))
     return F.linear(torch.flatten(x, 1), state[f"{enc}.net.5.weight"], state[f"{enc}.net.5.bias"])
 
 
 def convblock_train_step(state: "OrderedDict[str, Tensor]", opt_state: Dict, A: Tensor, I: Tensor, labels: Tensor,
                          dropout_mask: Optional[Tensor] = None, dropout_p: float = 0.5, lr: float = 5e-4, weight_decay: float = 1e-4,
-                         apply_update: bool = True) -> Dict[str, object]:
+                         apply_update: bool = True, emulate_bf16: bool = False, forced: Optional[Dict[str, Tensor]] = None) -> Dict[str, object]:
     params = {k: v for k, v in state.items() if is_parameter(k)}
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
     work = dict(state)
     work.update(leaves)
-    logits = head_forward(work, convblock_encoder_forward(work, "audio_encoder", A, True), convblock_encoder_forward(work, "image_encoder", I, True),
-                          dropout_mask, dropout_p)
+    logits = head_forward(work, convblock_encoder_forward(work, "audio_encoder", A, True, None, emulate_bf16, forced),
+                          convblock_encoder_forward(work, "image_encoder", I, True, None, emulate_bf16, forced), dropout_mask, dropout_p)
     loss = total_loss(logits, labels)
     gl = torch.autograd.grad(loss, list(leaves.values()))
     grads = dict(zip(leaves.keys(), gl))

@@ -335,8 +335,11 @@ class StandaloneConvBlockEncoder:
 class ConvBlockFusionEngine:
     """Same surface as engine.LateFusionEngine (``fs``, ``plan_for``, ``device``, data-parallel hooks)."""
 
-    def __init__(self, model: nn.Module, device: torch.device, dropout_p: float, seed: int = 0x5EED):
-        self.model, self.device, self.dropout_p, self.seed = model, device, float(dropout_p), seed
+    def __init__(self, model: nn.Module, device: torch.device, dropout_p: float, seed: Optional[int] = None):
+        self.model, self.device, self.dropout_p = model, device, float(dropout_p)
+        self.client_id = int(getattr(model, "_mml_client_id", 0))
+        self.seed = ops.engine_seed(self.client_id) if seed is None else seed
+        self.fwd_calls = 0
         pad = {}
         pad.update(pad_map(model.audio_encoder, "audio_encoder."))
         pad.update(pad_map(model.image_encoder, "image_encoder."))
@@ -450,7 +453,8 @@ class _ConvBlockStepPlan(_StepPlan):
         self.audio.stat_arena.zero_()
         self.image.stat_arena.zero_()
         if self._use_dropout():
-            ops.dropout_mask(self.drop_mask, eng.dropout_p, eng.seed, fs.step)
+            eng.fwd_calls += 1
+            ops.dropout_mask(self.drop_mask, eng.dropout_p, ops.engine_seed(eng.client_id, eng.fwd_calls) ^ eng.seed, fs.step)
         self._both_encoders(self.audio.fwd_train, self.image.fwd_train)
         dm, scale = self._drop()
         self._head_fwd(dm, scale)

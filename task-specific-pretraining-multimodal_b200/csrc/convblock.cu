@@ -164,13 +164,16 @@ conv3x3_c1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ m
   }
 }
 
-__global__ void partial_sum_kernel(const float* __restrict__ ws, int parts, int n, float* __restrict__ out) {
+// out[i] = sum_p ws[p][i] in a FIXED order: one warp per output, lane l adds parts l, l+32, ... then the lanes are combined by a butterfly
+__global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restrict__ ws, int parts, int n, float* __restrict__ out) {
   pdl_sync();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= n) return;
   float a = 0.f;
-  for (int p = 0; p < parts; ++p) a += ws[(size_t)p * n + i];
-  out[i] = a;
+  for (int p = lane; p < parts; p += 32) a += ws[(size_t)p * n + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[i] = a;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -293,7 +296,7 @@ int mml_conv3x3_c1_wgrad(mml_ctx* ctx, const float* x, const float* mask, const 
   const int ctas = B * H < ctx->sm_count * 4 ? B * H : ctx->sm_count * 4;
   cudaStream_t st = (cudaStream_t)stream;
   MML_LAUNCH(ctx, conv3x3_c1_wgrad_kernel, ctas, kT, 0, st, x, mask, dy, workspace, B, H, W, K);
-  MML_LAUNCH(ctx, partial_sum_kernel, (K * 9 + 255) / 256, 256, 0, st, (const float*)workspace, ctas, K * 9, dw);
+  MML_LAUNCH(ctx, partial_sum_kernel, (K * 9 + 7) / 8, 256, 0, st, (const float*)workspace, ctas, K * 9, dw);
   return MML_OK;
 }
 

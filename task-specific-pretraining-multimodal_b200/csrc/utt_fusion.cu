@@ -244,19 +244,49 @@ __global__ void dense_bwd_data_kernel(const float* __restrict__ dpre, int ldd, c
   dx[(size_t)b * lddx + k] = acc;
 }
 
-__global__ void dense_bwd_weight_kernel(const float* __restrict__ dpre, int ldd, const float* __restrict__ x, int ldx, float* __restrict__ dw,
-                                        float* __restrict__ db, int B, int K, int N) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * K) return;
-  const int o = i / K, k = i - o * K;
-  float acc = 0.f, sb = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const float d = dpre[(size_t)b * ldd + o];
-    acc = fmaf(d, x[(size_t)b * ldx + k], acc);
-    sb += d;
+// dw[o][k] = sum_b dpre[b][o] * x[b][k], db[o] = sum_b dpre[b][o]: one CTA per 32 (o) x 64 (k) tile, the batch walked in chunks of 32 rows
+// staged in shared memory, 2 x 4 outputs per thread; the sum over b runs in a fixed order (bit-reproducible).
+// (Was one thread per output looping over the batch: 256 dependent L2 round trips, ~100 us for any layer size.)
+constexpr int kDwTO = 32, kDwTK = 64, kDwTB = 32;
+__global__ void __launch_bounds__(256) dense_bwd_weight_kernel(const float* __restrict__ dpre, int ldd, const float* __restrict__ x, int ldx,
+                                                              float* __restrict__ dw, float* __restrict__ db, int B, int K, int N) {
+  __shared__ float ds[kDwTB][kDwTO + 1];
+  __shared__ __align__(16) float xs[kDwTB][kDwTK];
+  const int k0 = blockIdx.x * kDwTK, o0 = blockIdx.y * kDwTO;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float sb[2] = {0.f, 0.f};
+  for (int b0 = 0; b0 < B; b0 += kDwTB) {
+    for (int i = threadIdx.x; i < kDwTB * kDwTO; i += 256) {
+      const int bb = i / kDwTO, oo = i - bb * kDwTO;
+      ds[bb][oo] = (b0 + bb < B && o0 + oo < N) ? dpre[(size_t)(b0 + bb) * ldd + o0 + oo] : 0.f;
+    }
+    for (int i = threadIdx.x; i < kDwTB * kDwTK; i += 256) {
+      const int bb = i / kDwTK, kk = i - bb * kDwTK;
+      xs[bb][kk] = (b0 + bb < B && k0 + kk < K) ? x[(size_t)(b0 + bb) * ldx + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int bb = 0; bb < kDwTB; ++bb) {
+      const float d0 = ds[bb][ty * 2], d1 = ds[bb][ty * 2 + 1];
+      const float4 xv = *reinterpret_cast<const float4*>(&xs[bb][tx * 4]);
+      acc[0][0] = fmaf(d0, xv.x, acc[0][0]), acc[0][1] = fmaf(d0, xv.y, acc[0][1]), acc[0][2] = fmaf(d0, xv.z, acc[0][2]), acc[0][3] = fmaf(d0, xv.w, acc[0][3]);
+      acc[1][0] = fmaf(d1, xv.x, acc[1][0]), acc[1][1] = fmaf(d1, xv.y, acc[1][1]), acc[1][2] = fmaf(d1, xv.z, acc[1][2]), acc[1][3] = fmaf(d1, xv.w, acc[1][3]);
+      sb[0] += d0, sb[1] += d1;
+    }
+    __syncthreads();
   }
-  dw[i] = acc;
-  if (k == 0) db[o] = sb;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int o = o0 + ty * 2 + i;
+    if (o >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < K) dw[(size_t)o * K + k] = acc[i][j];
+    }
+    if (blockIdx.x == 0 && tx == 0) db[o] = sb[i];
+  }
 }
 
 // global gradient norm for clip_grad_norm_ (utt_fusion.py:182): two-stage sum of squares, then
@@ -362,7 +392,7 @@ int mml_dense_bwd(mml_ctx* ctx, float* dy, int lddy, const float* y, int ldy, co
     dense_bwd_data_kernel<<<(unsigned)mml_ceil_div((int64_t)B * K, 256), 256, 0, st>>>(dy, lddy, w, dx, lddx, B, K, N);
     MML_LAUNCHED(ctx);
   }
-  dense_bwd_weight_kernel<<<(unsigned)mml_ceil_div((int64_t)N * K, 256), 256, 0, st>>>(dy, lddy, x, ldx, dw, db, B, K, N);
+  dense_bwd_weight_kernel<<<dim3((unsigned)mml_ceil_div(K, kDwTK), (unsigned)mml_ceil_div(N, kDwTO)), 256, 0, st>>>(dy, lddy, x, ldx, dw, db, B, K, N);
   MML_LAUNCHED(ctx);
   return MML_OK;
 }

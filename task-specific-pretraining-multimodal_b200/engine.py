@@ -201,7 +201,7 @@ class FlatState:
         weight_decay -- the reference's pretrained-encoder runs use per-encoder groups, train_multimodal.py:213-300)."""
         groups = optimizer.param_groups
         sig = tuple(tuple(id(p) for p in g["params"]) for g in groups)
-        if getattr(self, "_adopted", None) is optimizer and sig == getattr(self, "_adopted_sig", None):
+        if getattr(self, "_adopted", None) is optimizer and sig == getattr(self, "_adopted_sig", None) and self._state_aliased(optimizer):
             return
         if type(optimizer) is not torch.optim.Adam:
             raise NotImplementedError(
@@ -243,22 +243,46 @@ class FlatState:
         if new_ranges != getattr(self, "ranges", None):
             self.ranges = new_ranges
             self.range_version = getattr(self, "range_version", 0) + 1  # captured graphs bake the launch ranges in
-        host_step = torch.tensor(float(self.step.item()))
+        # Whose moments are in M / V?  (1) this optimizer's own, already aliased -> keep; (2) tensors it brought along (a state restored
+        # by optimizer.load_state_dict, or an optimizer that stepped elsewhere) -> copy them in; (3) an optimizer without state (fresh
+        # torch.optim.Adam) -> start from zero moments and step 0 like torch does, NOT from a previous optimizer's buffers.
+        same_optimizer = getattr(self, "_adopted", None) is optimizer
+        host_step = torch.tensor(float(self.step.item())) if same_optimizer else torch.tensor(0.0)
+        fresh = [name for name, p in named if "exp_avg" not in optimizer.state.get(p, {})]
+        if len(fresh) == len(named) and not same_optimizer:
+            self.M.zero_()
+            self.V.zero_()
         for name, p in named:
             st = optimizer.state[p]
-            mv = self._view(self.M, name, p)
+            mv, vv = self._view(self.M, name, p), self._view(self.V, name, p)
             if "exp_avg" in st and st["exp_avg"].data_ptr() != mv.data_ptr():
                 mv.copy_(st["exp_avg"])
-                self._view(self.V, name, p).copy_(st["exp_avg_sq"])
-                host_step = torch.as_tensor(st["step"]).detach().float().cpu().reshape(())
+                vv.copy_(st["exp_avg_sq"])
+                host_step = torch.as_tensor(st["step"]).detach().float().cpu().reshape(()).clone()
+            elif "exp_avg" not in st and not same_optimizer and len(fresh) != len(named):
+                mv.zero_()  # a parameter this optimizer has not seen yet
+                vv.zero_()
             st["exp_avg"] = mv
-            st["exp_avg_sq"] = self._view(self.V, name, p)
+            st["exp_avg_sq"] = vv
             st["step"] = host_step  # one shared host scalar, advanced by the engine
         self.step.fill_(int(host_step.item()))
         self._host_step = host_step
         self._adopted = optimizer
         self._adopted_sig = sig
         self.hyper_host = [None] * self.MAX_GROUPS
+
+    def _state_aliased(self, optimizer: torch.optim.Optimizer) -> bool:
+        """Cheap per-step sentinel (first / last parameter): is ``optimizer.state`` still the M / V views?  ``load_state_dict`` replaces
+        the state tensors (the reference's CheckpointManager resume path), after which the fused Adam would keep updating buffers the
+        optimizer no longer owns."""
+        named = getattr(self, "_named_cache", None)
+        if named is None or len(named) != len(self._plist):
+            named = self._named_cache = list(self.module.named_parameters())
+        for name, p in (named[0], named[-1]):
+            st = optimizer.state.get(p)
+            if not st or "exp_avg" not in st or st["exp_avg"].data_ptr() != self._view(self.M, name, p).data_ptr() or st.get("step") is not self._host_step:
+                return False
+        return True
 
     def sync_hyper(self, optimizer: torch.optim.Optimizer, grad_scale: float) -> None:
         for gi, g in enumerate(optimizer.param_groups):
@@ -553,11 +577,13 @@ class StandaloneEncoder:
 class LateFusionEngine:
     """forward / train step / eval step of AVMNIST(audio_encoder, image_encoder, head) on one GPU."""
 
-    def __init__(self, model: nn.Module, device: torch.device, dropout_p: float, seed: int = 0x5EED):
+    def __init__(self, model: nn.Module, device: torch.device, dropout_p: float, seed: Optional[int] = None):
         self.model = model
         self.device = device
         self.dropout_p = float(dropout_p)
-        self.seed = seed
+        self.client_id = int(getattr(model, "_mml_client_id", 0))
+        self.seed = ops.engine_seed(self.client_id) if seed is None else seed
+        self.fwd_calls = 0  # forward() calls in train mode (they do not advance the optimizer step the kernel mixes into the seed)
         self.fs = FlatState(model, device)
         self.plans: Dict[Tuple, "_StepPlan"] = {}
         self.world = 1
@@ -764,7 +790,8 @@ class _StepPlan:
         self.audio.stat_arena.zero_()
         self.image.stat_arena.zero_()
         if self._use_dropout():
-            ops.dropout_mask(self.drop_mask, eng.dropout_p, eng.seed, fs.step)
+            eng.fwd_calls += 1
+            ops.dropout_mask(self.drop_mask, eng.dropout_p, ops.engine_seed(eng.client_id, eng.fwd_calls) ^ eng.seed, fs.step)
         self._both_encoders(self.audio.fwd_train, self.image.fwd_train)
         dm = self.drop_mask if self._use_dropout() else None
         scale = 1.0 / (1.0 - eng.dropout_p) if self._use_dropout() else 1.0

@@ -29,10 +29,12 @@ def aggregate_flat(buffers: List[torch.Tensor], num_samples: Sequence[float], ou
     if K == 0 or K != len(num_samples):
         raise ValueError("need one sample count per client")
     n = buffers[0].numel()
-    for b in buffers:
-        if b.numel() != n or b.dtype != torch.float32 or not b.is_cuda or not b.is_contiguous():
-            raise ValueError("client buffers must be contiguous fp32 CUDA tensors of equal length")
     dev = buffers[0].device
+    for b in buffers:
+        if b.numel() != n or b.dtype != torch.float32 or not b.is_cuda or not b.is_contiguous() or b.device != dev:
+            raise ValueError("client buffers must be contiguous fp32 CUDA tensors of equal length on one device")
+        if b.data_ptr() % 16 != 0:
+            raise ValueError("client buffers must be 16-byte aligned (the kernel reads float4; pass the flat buffer, not an odd-offset slice)")
     w = weights_from_counts(num_samples, dev)
     ptrs = torch.tensor([b.data_ptr() for b in buffers], dtype=torch.int64, device=dev)
     if out is None:
@@ -82,6 +84,8 @@ class FederatedSimulator:
     def __init__(self, model_factory, optimizer_factory, num_clients: int, device):
         self.device = torch.device(device)
         self.clients = [model_factory().to(self.device) for _ in range(num_clients)]
+        for k, m in enumerate(self.clients):
+            m._mml_client_id = k  # mixed into the dropout seed: clients with congruent weights still draw different masks
         self.optimizers = [optimizer_factory(m) for m in self.clients]
         for m in self.clients[1:]:
             m.load_state_dict(self.clients[0].state_dict())  # congruent start

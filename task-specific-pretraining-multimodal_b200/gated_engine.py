@@ -29,8 +29,10 @@ DROPOUT_P = 0.5  # MLPGenreClassifier hard-codes Dropout(p=0.5) (mmimdb.py:42,45
 
 
 class GatedFusionEngine:
-    def __init__(self, model: nn.Module, device: torch.device, seed: int = 0x5EED):
-        self.model, self.device, self.seed = model, device, seed
+    def __init__(self, model: nn.Module, device: torch.device, seed: Optional[int] = None):
+        self.model, self.device = model, device
+        self.client_id = int(getattr(model, "_mml_client_id", 0))
+        self.seed = ops.engine_seed(self.client_id) if seed is None else seed
         self.fs = FlatState(model, device, augment={"image_model.net.1.weight": "image_model.net.1.bias",
                                                     "text_model.net.1.weight": "text_model.net.1.bias"})
         self.plans: Dict[int, "_GatedPlan"] = {}

@@ -211,6 +211,7 @@ class MonomodalEncoder(nn.Module):
         _copy_in(plan.enc.x, x)
         plan.enc.mask.fill_(1.0)
         if labels is not None:
+            ops.check_class_labels(labels, plan.logits.shape[1])
             _copy_in(plan.labels, labels.reshape(-1))
         return plan
 

@@ -19,7 +19,23 @@ BF16 = torch.bfloat16
 def _ctx(t: torch.Tensor) -> Context:
     if not t.is_cuda:
         raise MMLError("mml_b200 ops need CUDA tensors (no CPU path)")
-    return Context.get(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    cur = torch.cuda.current_device()
+    idx = t.device.index if t.device.index is not None else cur
+    if idx != cur:  # kernels launch on the CURRENT device; a stream / pointer of another GPU fails obscurely (invalid resource handle)
+        raise MMLError(f"tensor lives on cuda:{idx} but the current device is cuda:{cur}: run the call under torch.cuda.device({idx})")
+    return Context.get(idx)
+
+
+def check_class_labels(labels, num_classes: int) -> None:
+    """CrossEntropyLoss contract of the fused heads: every label in [0, num_classes).  The kernels implement neither ``ignore_index``
+    rows (torch would drop them from the mean) nor torch's device-side assert for other out-of-range labels, so labels that arrive on
+    the host (the DataLoader case) are validated here; device-resident labels are the caller's responsibility."""
+    t = torch.as_tensor(labels)
+    if t.is_cuda or t.numel() == 0:
+        return
+    lo, hi = t.aminmax()
+    if int(lo) < 0 or int(hi) >= num_classes:
+        raise ValueError(f"labels must lie in [0, {num_classes}) (got min {int(lo)}, max {int(hi)}); ignore_index rows are not supported by the fused loss")
 
 
 def _stream(t: torch.Tensor) -> C.c_void_p:
@@ -64,6 +80,14 @@ def mask_apply(x: torch.Tensor, mask: torch.Tensor, want_reverse: bool = False):
     yr = torch.empty_like(x) if want_reverse else None
     ctx.check(ctx.lib.mml_mask_apply_f32(ctx.handle, _p(x, torch.float32), _p(mask, torch.float32), _p(y), _p(yr), B, per, _stream(x)), "mask_apply")
     return (y, yr) if want_reverse else y
+
+
+def mask_apply_into(x: torch.Tensor, mask: torch.Tensor, y: torch.Tensor) -> None:
+    """``mask_apply`` into a pre-allocated output (static buffers of a captured schedule)."""
+    ctx = _ctx(x)
+    B = x.shape[0]
+    ctx.check(ctx.lib.mml_mask_apply_f32(ctx.handle, _p(x, torch.float32), _p(mask, torch.float32), _p(y, torch.float32), _p(None), B,
+                                         x.numel() // max(B, 1), _stream(x)), "mask_apply")
 
 
 # ---- stem ----------------------------------------------------------------------------------------------------
@@ -318,6 +342,31 @@ def linear_fwd(x, w, bias, y) -> None:
     ctx = _ctx(x)
     ctx.check(ctx.lib.mml_linear_fwd(ctx.handle, _p(x, torch.float32), _p(w, torch.float32), _p(bias), _p(y, torch.float32), x.shape[0], x.shape[1],
                                      w.shape[0], _stream(x)), "linear_fwd")
+
+
+_M64 = (1 << 64) - 1
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def engine_seed(client_id: int = 0, salt: int = 0) -> int:
+    """Seed of one engine's dropout stream: ``torch.initial_seed()`` (so torch.manual_seed / the run's seed matter) mixed with the
+    data-parallel rank (each rank drops different units of its shard) and a client id (FedAvg clients draw different masks).  The
+    kernel mixes in the optimizer step counter, ``salt`` separates forward()-only calls in train mode from each other."""
+    import os
+
+    rank = int(os.environ.get("RANK", "0"))
+    x = _splitmix64(torch.initial_seed() & _M64)
+    x = _splitmix64(x ^ (rank + 1) * 0xD6E8FEB86659FD93 & _M64)
+    x = _splitmix64(x ^ (int(client_id) + 1) * 0xA0761D6478BD642F & _M64)
+    if salt:
+        x = _splitmix64(x ^ (int(salt) * 0xE7037ED1A0B428DB & _M64))
+    return x
 
 
 def dropout_mask(mask, p, seed, step_counter) -> None:

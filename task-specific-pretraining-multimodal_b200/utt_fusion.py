@@ -191,10 +191,11 @@ class _UttPlan:
 
     # ---- schedule --------------------------------------------------------------------------------------------------------
     def _mask_inputs(self) -> None:
-        torch.mul(self.xA, self.mA.view(-1, 1, 1), out=self.xmA)
-        torch.mul(self.xV, self.mV.view(-1, 1, 1), out=self.xmV)
-        torch.mul(self.xT, self.mT.view(-1, 1, 1), out=self.xmT)
-        self.xT16.copy_(self.xmT)
+        # sample[mod] = original * mask (data/base_dataset.py:70-72): the library's mask kernel, like the AVMNIST / MMIMDb paths
+        ops.mask_apply_into(self.xA, self.mA, self.xmA)
+        ops.mask_apply_into(self.xV, self.mV, self.xmV)
+        ops.mask_apply_into(self.xT, self.mT, self.xmT)
+        ops.cast_f32_bf16(self.xmT, self.xT16)
 
     def run_forward(self, train: bool, with_loss: bool, with_grad: bool) -> None:
         B, H = self.B, self.H
@@ -304,8 +305,10 @@ class _UttPlan:
 
 
 class UttEngine:
-    def __init__(self, model: nn.Module, device: torch.device, seed: int = 0x5EED):
-        self.model, self.device, self.seed = model, device, seed
+    def __init__(self, model: nn.Module, device: torch.device, seed: Optional[int] = None):
+        self.model, self.device = model, device
+        self.client_id = int(getattr(model, "_mml_client_id", 0))
+        self.seed = ops.engine_seed(self.client_id) if seed is None else seed
         self.fs = FlatState(model, device)
         self.plans: Dict[Tuple[int, int], _UttPlan] = {}
         self.world = 1
@@ -391,6 +394,7 @@ class UttFusionModel(nn.Module):
             else:
                 _copy_in(dst, torch.as_tensor(m).reshape(-1).float())
         if labels is not None:
+            ops.check_class_labels(labels, plan.logits.shape[1])
             _copy_in(plan.labels, torch.as_tensor(labels).reshape(-1))
         return plan
 

@@ -175,31 +175,61 @@ def test_reference_golden_fixture_convblock():
     assert abs(losses[1] - float(g["losses"][1])) < 5e-2
 
 
-@pytest.mark.parametrize("B", [8, 64])
+def forced_from_plan(plan):
+    """Activations the GPU stored, under the oracle's tap names (the conv bias is not part of the stored conv output: it cancels in
+    the BatchNorm that follows, so forcing the un-biased value leaves every later tensor and every gradient unchanged)."""
+    forced = {}
+    for pre, ep in (("audio_encoder.", plan.audio), ("image_encoder.", plan.image)):
+        for name, t in ep.taps.items():
+            forced[pre + name] = nchw(t).cpu()
+    return forced
+
+
+@pytest.mark.parametrize("B", [8, 64, 256])
 def test_convblock_step_against_oracle(B):
+    """B = 256 is the batch bench.py --workload convblock times."""
     model = build()
     torch.manual_seed(0)
     state = O.init_convblock_avmnist_state()
     d = O.synthetic_batch(B, 77, (32, 94))
     A, I = O.apply_missing_mask(d["audio"], d["audio_mask"]), O.apply_missing_mask(d["image"], d["image_mask"])
     opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
-    opt_state = {}
-    ref = O.convblock_train_step(state, opt_state, A, I, d["labels"], d["dropout_mask"], 0.5)
     out = model.train_step(make_batch(d, B), opt, LOSS, torch.device(DEV), None, dropout_mask=d["dropout_mask"])
     plan = next(iter(model._engine.plans.values()))
+    mine = grads_by_name(model)
+    # 1. teacher forced: the oracle's backward over the activations the GPU stored.  (a) rounding activation-gradients to bf16 where the
+    #    kernels store them -> only accumulation-order noise is left; (b) the plain fp32 backward -> the bf16 gradient storage itself
+    #    (grows with the number of positions a weight gradient sums over: the first convolution at batch 256 sums 770k pixels)
+    forced = forced_from_plan(plan)
+    rels = {}
+    for tag, eb in (("forced+bf16", True), ("forced", False)):
+        ref_f = O.convblock_train_step(copy.deepcopy(state), {}, A, I, d["labels"], d["dropout_mask"], 0.5, apply_update=False,
+                                       emulate_bf16=eb, forced=forced)
+        for k, gref in ref_f["grads"].items():
+            if k.endswith("conv_one.bias") or k.endswith("conv_two.bias"):
+                # cancels through BatchNorm: exactly zero here, fp32 rounding noise in the reference (bf16 rounding noise when emulated)
+                assert float(mine[k].abs().max()) == 0.0 and float(gref.abs().max()) < (1e-2 if eb else 1e-5)
+                continue
+            rels[(tag, k)] = float((mine[k] - gref).norm() / (gref.norm() + 1e-12))
+    for (tag, k), rel in sorted(rels.items(), key=lambda kv: -kv[1])[:6]:
+        print(f"B={B} {tag:12s} {k:45s} {rel:.4f}")
+    worst_f = max(v for (tag, _), v in rels.items() if tag == "forced")
+    worst_e = max(v for (tag, _), v in rels.items() if tag == "forced+bf16")
+    assert worst_e < 2e-2, worst_e
+    assert worst_f < 0.1, worst_f
+    # 2. un-forced against the fp32 oracle: loss, logits, and a looser gradient bound (ReLU / max-pool decisions flip on a few elements)
+    ref = O.convblock_train_step(state, {}, A, I, d["labels"], d["dropout_mask"], 0.5)
     assert abs(out["loss"] - ref["loss"]) < 2e-2
     span = float(ref["logits"].abs().max())
     assert float((plan.logits.cpu() - ref["logits"]).abs().max()) < 0.05 * span + 0.01
-    mine = grads_by_name(model)
     worst = 0.0
     for k, gref in ref["grads"].items():
         if k.endswith("conv_one.bias") or k.endswith("conv_two.bias"):
-            assert float(mine[k].abs().max()) == 0.0 and float(gref.abs().max()) < 1e-6
             continue
         rel = float((mine[k] - gref).norm() / (gref.norm() + 1e-12))
         worst = max(worst, rel)
-        assert rel < 0.12, (k, rel)  # un-forced: ReLU / max-pool decisions of bf16 activations differ from fp32 on a few elements
-    print("worst un-forced gradient rel L2", worst)
+        assert rel < 0.4, ("unforced", k, rel)
+    print(f"B={B}: worst gradient rel L2 forced+bf16 {worst_e:.4f} forced {worst_f:.4f} un-forced {worst:.4f}")
     # parameters after the Adam update (the oracle applied its own), BatchNorm running statistics incl. the folded conv bias
     sd = model.state_dict()
     for k, v in state.items():

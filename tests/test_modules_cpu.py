@@ -270,6 +270,47 @@ def test_flat_state_layout_and_param_group_ranges(monkeypatch):
         fs.adopt_optimizer(torch.optim.SGD(net.parameters(), lr=0.1))
 
 
+def test_optimizer_state_is_revalidated_after_load_state_dict(monkeypatch):
+    """CheckpointManager resume path: ``optimizer.load_state_dict`` replaces the state tensors; the next step must pick the restored
+    moments / step up (and alias them again) instead of continuing on the old buffers.  A brand-new Adam starts from zero moments."""
+    import copy
+
+    from mml_b200 import engine, ops
+
+    monkeypatch.setattr(ops, "cast_f32_bf16", lambda src, dst: dst.copy_(src))
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 4), torch.nn.Linear(4, 2))
+    fs = engine.FlatState(net, torch.device("cpu"))
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    fs.adopt_optimizer(opt)
+    assert float(fs.M.abs().max()) == 0.0 and int(fs.step) == 0
+    # pretend three fused steps happened
+    fs.M.copy_(torch.arange(fs.total, dtype=torch.float32) * 0.01)
+    fs.V.copy_(torch.arange(fs.total, dtype=torch.float32) * 0.02)
+    fs.step.fill_(3)
+    fs._host_step.fill_(3.0)
+    saved = copy.deepcopy(opt.state_dict())
+    assert float(saved["state"][0]["step"]) == 3.0 and torch.equal(saved["state"][0]["exp_avg"], fs.M[:32].view(4, 8))
+    # ... two more steps, then resume from the checkpoint
+    fs.M.add_(1.0)
+    fs.V.add_(1.0)
+    fs.step.fill_(5)
+    fs._host_step.fill_(5.0)
+    fs.adopt_optimizer(opt)  # unchanged optimizer: nothing to do
+    assert int(fs.step) == 5
+    opt.load_state_dict(saved)
+    assert opt.state[net[0].weight]["exp_avg"].data_ptr() != fs.M.data_ptr()  # torch replaced the tensors
+    fs.adopt_optimizer(opt)
+    assert int(fs.step) == 3 and float(fs._host_step) == 3.0
+    assert torch.equal(fs.M[:32], torch.arange(32, dtype=torch.float32) * 0.01) and torch.equal(fs.V[:32], torch.arange(32, dtype=torch.float32) * 0.02)
+    assert opt.state[net[0].weight]["exp_avg"].data_ptr() == fs.M.data_ptr() and opt.state[net[1].bias]["step"] is fs._host_step
+    # a brand-new optimizer starts like torch does: zero moments, step 0
+    opt2 = torch.optim.Adam(net.parameters(), lr=1e-3)
+    fs.adopt_optimizer(opt2)
+    assert float(fs.M.abs().max()) == 0.0 and float(fs.V.abs().max()) == 0.0 and int(fs.step) == 0
+    assert opt2.state[net[0].weight]["exp_avg"].data_ptr() == fs.M.data_ptr()
+
+
 def test_convblock_modules_match_reference_surface_and_padded_storage(monkeypatch):
     """MNISTAudio / MNISTImage / ConvBlock (avmnist.py:34-185, conv.py:16-59): same constructor keywords, state_dict names, shapes and
     initial values as the oracle's restatement of the reference; FlatState(pad=...) stores narrow layers as 64-channel tensors with a
