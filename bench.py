@@ -788,7 +788,7 @@ TENSOR_KERNELS = [
 
 
 def tensor_kernel_rooflines(torch, ops, B, pk, ms_per_step):
-    """Every tensor-core kernel above timed ALONE (CUDA events on the launching stream, L2 flushed between launches) on its real
+    """Every tensor-core kernel above timed ALONE (CUDA events on the launching stream, L2 flushed before every launch) on its real
     shape; `roofline` of the bench line = the one with the largest share (launches per step x time) of the step.  `traffic` = DRAM
     bytes of one launch from the ncu --set full capture of this build, if profiles/r2_kernel_traffic.json has it."""
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > L2
@@ -819,16 +819,16 @@ def tensor_kernel_rooflines(torch, ops, B, pk, ms_per_step):
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
-            times = []
-            for _ in range(7):
+            # [flush L2, event, kernel, event] x 9 enqueued WITHOUT a host sync in between: the 512 MB flush (~100 us) keeps the GPU behind
+            # the host, so the kernel is already queued when the first event fires and no launch latency is inside the bracket
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(9)]
+            for e0, e1 in evs:
                 flush.zero_()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 fn()
                 e1.record()
-                e1.synchronize()
-                times.append(e0.elapsed_time(e1) * 1e-3)
-            t = statistics.median(times)
+            torch.cuda.synchronize()
+            t = statistics.median([e0.elapsed_time(e1) * 1e-3 for e0, e1 in evs[1:]])
             flops = 2.0 * B * P * Q * K * C * R * R
             ach = flops / t / 1e12
             res[label] = {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
@@ -843,64 +843,73 @@ def tensor_kernel_rooflines(torch, ops, B, pk, ms_per_step):
 
 
 def hbm_kernel_rooflines(torch, ops, B, pk):
-    """Achieved HBM GB/s of the two memory-bound kernel families timed alone (L2 flushed): the fused BatchNorm-apply + ReLU +
-    residual forward on the ResNet18 layer1 tensor and the Adam update over the full parameter vector.  Never fatal."""
+    """Achieved HBM GB/s of the memory-bound kernel families timed alone: the fused BatchNorm-apply + ReLU + residual forward and the
+    two-pass BatchNorm backward on the ResNet18 layer1 tensor, and the Adam update over the full parameter vector.  Each kernel runs
+    back to back over ROTATING buffer sets whose total size exceeds the 126 MB L2 several times (every launch finds its inputs in
+    HBM, no flush kernel in between), CUDA events around the whole loop -> launch overhead does not inflate a 20 us kernel.  Never fatal."""
     out = {}
     try:
-        flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-
-        def timeit(fn):
-            for _ in range(2):
+        def timeit(fns, rounds=4):
+            for fn in fns:
                 fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ts = []
-            for _ in range(8):
-                flush.zero_()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(3):
                 e0.record()
-                fn()
+                for _ in range(rounds):
+                    for fn in fns:
+                        fn()
                 e1.record()
                 e1.synchronize()
-                ts.append(e0.elapsed_time(e1) * 1e-3)
+                ts.append(e0.elapsed_time(e1) * 1e-3 / (rounds * len(fns)))
             return statistics.median(ts)
 
         rows, Cn = B * 28 * 28, 64
-        x = torch.randn(rows, Cn, device="cuda").to(torch.bfloat16)
-        res = torch.randn(rows, Cn, device="cuda").to(torch.bfloat16)
-        y = torch.empty_like(x)
-        stats = ops.bn_stats_buffer(Cn, "cuda")
-        xf = x.float()
-        stats[0, :, 0] = xf.sum(0).double()
-        stats[0, :, 1] = (xf * xf).sum(0).double()
         f = lambda *sh: torch.zeros(*sh, device="cuda")
-        bn = ops.BNBuffers(stats, torch.ones(Cn, device="cuda"), f(Cn), f(Cn), torch.ones(Cn, device="cuda"), f(Cn), torch.ones(Cn, device="cuda"))
-        t = timeit(lambda: ops.bn_train_fwd(x, bn, res, None, y, rows, Cn, True))
+        sets = []
+        for _ in range(5):  # 5 x (x, res, y) = 385 MB of bf16 per rotation
+            x = torch.randn(rows, Cn, device="cuda").to(torch.bfloat16)
+            res = torch.randn(rows, Cn, device="cuda").to(torch.bfloat16)
+            y = torch.empty_like(x)
+            stats = ops.bn_stats_buffer(Cn, "cuda")
+            xf = x.float()
+            stats[0, :, 0] = xf.sum(0).double()
+            stats[0, :, 1] = (xf * xf).sum(0).double()
+            del xf
+            bn = ops.BNBuffers(stats, torch.ones(Cn, device="cuda"), f(Cn), f(Cn), torch.ones(Cn, device="cuda"), f(Cn), torch.ones(Cn, device="cuda"))
+            sets.append((x, res, y, bn))
+        t = timeit([lambda s_=s_: ops.bn_train_fwd(s_[0], s_[3], s_[1], None, s_[2], rows, Cn, True) for s_ in sets])
         bytes_bn = 3.0 * rows * Cn * 2  # read raw + residual, write output (bf16)
         out["bn_relu_residual_fwd"] = {"bound": "hbm", "achieved": bytes_bn / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                        "frac": bytes_bn / t / 1e9 / pk["hbm_gbs"], "us_per_launch": t * 1e6, "algorithmic_bytes_per_launch": bytes_bn}
         # BatchNorm backward of the same layer (two incoming gradients + ReLU mask): pass 1 reads dy1, dy2, y, x and stores g,
         # pass 2 reads g, x and stores dx -> 8 tensor passes of algorithmic traffic (round 1: 10)
-        dy1, dy2, gbuf, dxb = (torch.randn(rows, Cn, device="cuda").to(torch.bfloat16) for _ in range(4))
-        bstat = ops.bn_stats_buffer(Cn, "cuda")
-        dg, db = f(Cn), f(Cn)
+        bsets = []
+        for (x, res, y, bn) in sets[:3]:  # 3 x 7 tensors = 540 MB per rotation
+            dy1, dy2, gbuf, dxb = (torch.randn(rows, Cn, device="cuda").to(torch.bfloat16) for _ in range(4))
+            bsets.append((x, y, bn, dy1, dy2, gbuf, dxb, ops.bn_stats_buffer(Cn, "cuda"), f(Cn), f(Cn)))
 
-        def bn_bwd():
+        def bn_bwd(s_):
+            x, y, bn, dy1, dy2, gbuf, dxb, bstat, dg, db = s_
             ops.bn_bwd_reduce(dy1, dy2, y, x, bn.mean, bn.invstd, bstat, gbuf, rows, Cn, True)
             ops.bn_bwd_apply(gbuf, x, bn.mean, bn.invstd, bn.gamma, bstat, dg, db, dxb, rows, Cn)
 
-        t = timeit(bn_bwd)
+        t = timeit([lambda s_=s_: bn_bwd(s_) for s_ in bsets])
         bytes_bwd = 8.0 * rows * Cn * 2
         out["bn_relu_residual_bwd"] = {"bound": "hbm", "achieved": bytes_bwd / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                        "frac": bytes_bwd / t / 1e9 / pk["hbm_gbs"], "us_per_launch_pair": t * 1e6, "algorithmic_bytes_per_launch_pair": bytes_bwd}
-        n = 32_580_800
+        del sets, bsets
+        n = 32_580_800  # one launch touches 977 MB: far beyond L2, no rotation needed
         p_, g_, m_, v_ = (torch.randn(n, device="cuda") * 0.01 for _ in range(4))
         v_.abs_()
         wb = torch.empty(n, device="cuda", dtype=torch.bfloat16)
         hyper = torch.tensor([5e-4, 0.9, 0.999, 1e-8, 1e-4, 1.0, 0.0, 0.0], device="cuda")
         step = torch.zeros(1, device="cuda", dtype=torch.int64)
-        t = timeit(lambda: ops.adam_step(p_, g_, m_, v_, wb, hyper, step, True))
+        t = timeit([lambda: ops.adam_step(p_, g_, m_, v_, wb, hyper, step, True)], rounds=6)
         bytes_adam = 30.0 * n  # read p, g, m, v; write p, m, v (fp32) + the bf16 shadow
         out["adam"] = {"bound": "hbm", "achieved": bytes_adam / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": bytes_adam / t / 1e9 / pk["hbm_gbs"],
                        "us_per_launch": t * 1e6, "algorithmic_bytes_per_launch": bytes_adam}
+        out["method"] = "back-to-back launches over rotating buffer sets (> 3x L2 per rotation), CUDA events around the loop, median of 3"
     except Exception as exc:  # a diagnostic must never cost the bench line
         out["error"] = repr(exc)[:200]
     return out
@@ -1051,7 +1060,8 @@ def run_b200_arm(args):
         t_solo = float(dt.item())
         dp_info = {"dp_consistent": bool(flag.item() == 1), "exposed_comm_ms_per_step": (t_dev - t_solo) / args.steps * 1e3,
                    "no_comm_ms_per_step": t_solo / args.steps * 1e3, "allreduce_bytes_per_step": 4 * eng.fs.total,
-                   "nccl_max_ctas": dp.max_ctas, "ranges": 3,
+                   "nccl_max_ctas": dp.max_ctas, "ranges": 2 + int(plan.audio_mid > 0) + int(plan.image_mid > 0),
+                   "schedule": {k: os.environ.get(k, "default") for k in ("MML_IMAGE_MID", "MML_AUDIO_MID", "MML_IMAGE_AR_LATE", "MML_NCCL_MAX_CTAS")},
                    "note": "exposed = step time with the bucketed all-reduce minus the same step without data parallelism, timed in the same "
                            "processes on all ranks at once (max over ranks)"}
         del solo, solo_opt, solo_plan

@@ -209,12 +209,10 @@ class AVMNIST(nn.Module):
         given = kwargs.get("dropout_mask")
         if given is not None:
             plan.drop_mask.copy_(torch.as_tensor(given).reshape(plan.drop_mask.shape).to(torch.uint8), non_blocking=True)
+        plan.want_pred = metric_recorder is not None
         plan.train_step(given_dropout=given is not None)
         fs._host_step += 1
-        plan.h_loss.copy_(plan.loss, non_blocking=True)
-        if metric_recorder is not None:
-            plan.h_pred.copy_(plan.pred, non_blocking=True)
-        torch.cuda.current_stream(eng.device).synchronize()
+        plan.loss_ready.synchronize()  # loss / predictions are final after the forward half; the backward half keeps running (engine.publish)
         loss = float(plan.h_loss[0])
         if metric_recorder is not None:
             predictions = plan.h_pred.numpy().astype(np.int64)

@@ -100,7 +100,11 @@ class _ConvBlockEncoder(nn.Module):
     def _encode(self, x: torch.Tensor) -> torch.Tensor:
         """Encoder-only forward ([B, hidden_dim] fp32, no autograd graph): train() -> batch statistics + running-stat update."""
         if x.dim() == 4:
+            if x.shape[1] != 1:
+                raise ValueError("expected a 1-channel tensor")
             x = x[:, 0]
+        if x.dim() != 3:
+            raise ValueError(f"expected [B,H,W] or [B,1,H,W], got {tuple(x.shape)}")
         if not x.is_cuda:
             raise RuntimeError("mml_b200 ConvBlock encoders run on a B200 GPU only: there is no CPU / PyTorch fallback path")
         if self._standalone is None:
@@ -387,6 +391,8 @@ class _ConvBlockStepPlan(_StepPlan):
         self.h_loss = torch.zeros(1).pin_memory()
         self.h_pred = torch.zeros(B, dtype=torch.int32).pin_memory()
         self.graph_train = self.graph_train_nodrop = self.graph_eval = None
+        self.loss_ready = torch.cuda.Event()
+        self.want_pred = False
         self.eager_steps = 0
         self.launches_per_step = 0
         self.side_stream = None
@@ -422,7 +428,7 @@ class _ConvBlockStepPlan(_StepPlan):
         return (self.drop_mask, 1.0 / (1.0 - p)) if p > 0.0 else (None, 1.0)
 
     # -- schedules -------------------------------------------------------------------------------------------------
-    def run_train(self, own_dropout: bool) -> None:
+    def run_train_fwd(self, own_dropout: bool) -> None:
         eng, fs = self.eng, self.eng.fs
         self.audio.stat_arena.zero_()
         self.image.stat_arena.zero_()
@@ -432,9 +438,12 @@ class _ConvBlockStepPlan(_StepPlan):
         dm, scale = self._drop()
         self._head_fwd(dm, scale)
         ops.softmax_ce(self.logits, self.labels, self.dlogits, self.row_loss, self.loss, self.pred)
+
+    def run_train_bwd(self) -> None:
+        dm, scale = self._drop()
         self._head_bwd(dm, scale)
         self._both_encoders(self.audio.bwd, self.image.bwd)
-        fs.NBT += 1
+        self.eng.fs.NBT += 1
 
     def run_update(self) -> None:
         eng, fs = self.eng, self.eng.fs

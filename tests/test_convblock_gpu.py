@@ -266,7 +266,7 @@ def test_convblock_eval_and_standalone_encoder():
     span = float(ref.abs().max())
     assert float((logits - ref).abs().max()) < 0.03 * span + 5e-3
     got_a = model.audio_encoder(d["audio"].to(DEV)).cpu()
-    got_i = model.image_encoder(d["image"].to(DEV)[:, None]).cpu()
+    got_i = model.image_encoder(d["image"].to(DEV)).cpu()  # [B,1,28,28] as the dataset yields it
     assert float((got_a - ea).abs().max()) < 0.03 * float(ea.abs().max()) + 5e-3
     assert float((got_i - ei).abs().max()) < 0.03 * float(ei.abs().max()) + 5e-3
     out = model.validation_step(make_batch(d, B), LOSS, torch.device(DEV), None, return_test_info=True)
