@@ -62,13 +62,31 @@ int mml_ctx_set_sm_budget(mml_ctx* ctx, int sms);
 int mml_ctx_set_pdl(mml_ctx* ctx, int enable);
 
 /* A-B switches for experiments (not part of the reference surface): key 1 = use the halo conv kernel (default 1); key 2 = largest
- * thread-block cluster of the split-K convolution variant (1 = off (default), 2, 4, 8) */
+ * thread-block cluster of the split-K convolution variant (1 = off (default), 2, 4, 8); key 3 = BatchNorm grids capped at one
+ * resident wave (default 1) */
 int mml_debug_set(int key, int value);
 
 /* ---- a1: missing-modality mask -- data/base_dataset.py:70-72  sample[mod] = original * mask -------------------- */
 /* y[b, :] = x[b, :] * mask[b]   (true IEEE multiply, bit-exact with torch CPU); reverse: x * -1 * (mask - 1) */
 int mml_mask_apply_f32(mml_ctx*, const float* x, const float* mask, float* y, float* y_reverse, int64_t batch,
                        int64_t per_sample, void* stream);
+
+/* ---- f4: the input path in front of the encoders, on the device (staging.cu) --------------------------------------------------
+ * Mask draw: data/base_dataset.py:46-59 _initialise_missing_masks -> create_missing_mask(n_modalities, n, [P(present)]): one
+ * independent Bernoulli(P(present)) per (sample, modality), drawn once per pattern.  masks[m*ld + (i - first_sample)] for
+ * i in [first_sample, first_sample + count) = (u < p_present[m]) ? 1 : 0, u = (bits >> 8) * 2^-24 with bits = word (i % 4) of
+ * Philox4x32-10(counter = {lo32(i/4), hi32(i/4), m, stream_id}, key = {lo32(seed), hi32(seed)}): a pure function of
+ * (seed, stream_id, m, i), so any shard of the sample range (one rank's slice) reproduces the single-GPU draw bit for bit.
+ * p_present: device fp32 [n_modalities]; stream_id: the pattern's index. */
+int mml_missing_mask_draw(mml_ctx*, const float* p_present, float* masks, int n_modalities, int64_t first_sample, int64_t count, int64_t ld,
+                          uint64_t seed, uint32_t stream_id, void* stream);
+/* data/avmnist.py:193-224 __getitem__ looks the mask of sample idx up per item: out[m*batch + b] = masks[m*num_samples + sample_idx[b]];
+ * an index outside [0, num_samples) yields 0 and sets *bad_index_flag (device int, may be NULL) to 1 */
+int mml_missing_mask_gather(mml_ctx*, const float* masks, const int64_t* sample_idx, float* out, int n_modalities, int64_t num_samples,
+                            int64_t batch, int* bad_index_flag, void* stream);
+/* data/avmnist.py:188-191 _load_image for uint8 pixels: colormap -> uint8 RGBA -> PIL "L" -> float32 / 255 is a 256-entry table of the
+ * pixel value (host-built, mml_b200.data.luma_lut): dst[i] = lut256[src[i]].  src and dst 16-byte aligned, any n. */
+int mml_stage_u8_lut_f32(mml_ctx*, const uint8_t* src, const float* lut256, float* dst, int64_t n, void* stream);
 
 /* ---- a2/a3: ResNetEncoder stem -- models/msa/networks/resnet.py:137 conv1 (7x7, stride 2, pad 3, C_in = 1) ----- */
 /* x fp32 [B,H,W] (optionally multiplied by mask[b], same multiply as above), w fp32 [64][7][7] ->

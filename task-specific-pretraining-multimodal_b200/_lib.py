@@ -64,6 +64,9 @@ SIGNATURES = {
     "mml_ctx_set_pdl": (I32, [P, I32]),
     "mml_debug_set": (I32, [I32, I32]),
     "mml_mask_apply_f32": (I32, [P, P, P, P, P, I64, I64, P]),
+    "mml_missing_mask_draw": (I32, [P, P, P, I32, I64, I64, I64, U64, C.c_uint32, P]),
+    "mml_missing_mask_gather": (I32, [P, P, P, P, I32, I64, I64, P, P]),
+    "mml_stage_u8_lut_f32": (I32, [P, P, P, P, I64, P]),
     "mml_stem_fprop": (I32, [P, P, P, P, P, P, I32, I32, I32, P]),
     "mml_stem_wgrad": (I32, [P, P, P, P, P, P, I64, I32, I32, I32, P]),
     "mml_stem_wgrad_workspace": (I64, [P, I32, I32, I32]),

@@ -11,6 +11,9 @@
 
 using namespace mml;
 
+extern "C" int mml_g_bn_one_wave;
+int mml_g_bn_one_wave = 1;  // mml_debug_set key 3 (A/B switch): 1 = BatchNorm grids capped at one resident wave
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -714,6 +717,21 @@ int stream_grid(const mml_ctx* ctx, long long items, int U) {
   return (int)b;
 }
 
+// One resident wave: a grid capped at (CTAs that fit on an SM) x SMs, so every CTA runs its prologue (statistics -> coefficients,
+// two dependent loads) once and then streams ~3x more vectors, instead of 2-3 waves of short CTAs each paying that latency
+// (measured on the ResNet18 layer1 tensor, mml_debug_set key 3 switches it: see DESIGN.md section 4).
+template <typename K>
+int wave_cap(const mml_ctx* ctx, int grid, K kernel) {
+  if (!mml_g_bn_one_wave) return grid;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    return grid;
+  }
+  const int cap = occ * ctx->sm_count;
+  return grid < cap ? grid : cap;
+}
+
 int check_rows_c(mml_ctx* ctx, int64_t rows, int C) {
   MML_REQUIRE(ctx, rows >= 1, "rows must be >= 1");
   MML_REQUIRE(ctx, C >= 8 && C <= kMaxC && (C % 8) == 0 && (kThreads % (C / 8)) == 0,
@@ -751,7 +769,7 @@ int mml_bn_train_fwd(mml_ctx* ctx, const uint16_t* x, const double* stats, const
   const double unbias = rows > 1 ? (double)rows / (double)(rows - 1) : 1.0;
   cudaStream_t st = (cudaStream_t)stream;
 #define MML_TR(M, RL) \
-  MML_LAUNCH(ctx, (bn_fwd_kernel<M, RL, true>), grid, kThreads, 0, st, x, bn, nullptr, nullptr, res, rbn, nullptr, nullptr, y, n8, C / 8, inv_count, unbias, momentum, eps)
+  MML_LAUNCH(ctx, (bn_fwd_kernel<M, RL, true>), wave_cap(ctx, grid, bn_fwd_kernel<M, RL, true>), kThreads, 0, st, x, bn, nullptr, nullptr, res, rbn, nullptr, nullptr, y, n8, C / 8, inv_count, unbias, momentum, eps)
   switch (mode * 2 + (relu ? 1 : 0)) {
     case 0: MML_TR(0, false); break;
     case 1: MML_TR(0, true); break;
@@ -783,7 +801,7 @@ int mml_bn_act_fwd(mml_ctx* ctx, const uint16_t* x, const float* scale, const fl
   const BnTrain none{};
   cudaStream_t st = (cudaStream_t)stream;
 #define MML_FWD(M, RL) \
-  MML_LAUNCH(ctx, (bn_fwd_kernel<M, RL, false>), grid, kThreads, 0, st, x, none, scale, shift, res, none, rscale, rshift, y, n8, C / 8, 0.0, 0.0, 0.f, 0.f)
+  MML_LAUNCH(ctx, (bn_fwd_kernel<M, RL, false>), wave_cap(ctx, grid, bn_fwd_kernel<M, RL, false>), kThreads, 0, st, x, none, scale, shift, res, none, rscale, rshift, y, n8, C / 8, 0.0, 0.0, 0.f, 0.f)
   switch (mode * 2 + (relu ? 1 : 0)) {
     case 0: MML_FWD(0, false); break;
     case 1: MML_FWD(0, true); break;
@@ -812,7 +830,7 @@ int mml_bn_bwd_reduce(mml_ctx* ctx, const uint16_t* dy1, const uint16_t* dy2, co
   const long long n8 = rows * (C / 8);
   const int grid = bn_bwd_grid(ctx, rows, C);
   cudaStream_t st = (cudaStream_t)stream;
-#define MML_RED(TW, RL, GO) MML_LAUNCH(ctx, (bn_bwd_reduce_kernel<TW, RL, GO>), grid, kThreads, 0, st, dy1, dy2, y, x, mean, invstd, bstat, g_out, n8, C / 8)
+#define MML_RED(TW, RL, GO) MML_LAUNCH(ctx, (bn_bwd_reduce_kernel<TW, RL, GO>), wave_cap(ctx, grid, bn_bwd_reduce_kernel<TW, RL, GO>), kThreads, 0, st, dy1, dy2, y, x, mean, invstd, bstat, g_out, n8, C / 8)
   const int key = (dy2 ? 4 : 0) | (relu ? 2 : 0) | (g_out ? 1 : 0);
   switch (key) {
     case 0: MML_RED(false, false, false); break;
@@ -834,7 +852,7 @@ int mml_bn_bwd_apply(mml_ctx* ctx, const uint16_t* g, const uint16_t* x, const f
   int rc = check_rows_c(ctx, rows, C);
   if (rc) return rc;
   const long long n8 = rows * (C / 8);
-  MML_LAUNCH(ctx, bn_bwd_apply_kernel, stream_grid(ctx, n8, kU), kThreads, 0, (cudaStream_t)stream, g, x, mean, invstd, gamma, bstat, 1.0f / (float)rows, dgamma, dbeta,
+  MML_LAUNCH(ctx, bn_bwd_apply_kernel, wave_cap(ctx, stream_grid(ctx, n8, kU), bn_bwd_apply_kernel), kThreads, 0, (cudaStream_t)stream, g, x, mean, invstd, gamma, bstat, 1.0f / (float)rows, dgamma, dbeta,
                                                                                        dx, n8, C / 8);
   return MML_OK;
 }
@@ -894,7 +912,7 @@ int mml_stem_bn_pool_bwd(mml_ctx* ctx, const uint16_t* dy, const uint16_t* dy2, 
   MML_LAUNCH(ctx, stem_bn_pool_bwd_kernel, g0, kThreads, 0, st, dy, dy2, argmax, x, mean, invstd, gamma, beta, bstat, dx, N, H, W, C, P, Q);
   // pass 2 in place over the buffer that now holds g: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))
   const long long n8 = (long long)N * H * W * (C / 8);
-  MML_LAUNCH(ctx, bn_bwd_apply_kernel, stream_grid(ctx, n8, kU), kThreads, 0, st, dx, x, mean, invstd, gamma, bstat, inv_count, dgamma, dbeta, dx, n8, C / 8);
+  MML_LAUNCH(ctx, bn_bwd_apply_kernel, wave_cap(ctx, stream_grid(ctx, n8, kU), bn_bwd_apply_kernel), kThreads, 0, st, dx, x, mean, invstd, gamma, bstat, inv_count, dgamma, dbeta, dx, n8, C / 8);
   return MML_OK;
 }
 

@@ -36,10 +36,19 @@ constexpr int kMaxTaps = 9;
 constexpr int kMaxViews = 4;
 constexpr int kBoxBytes = 128 * 128;  // one 128-row x 64-channel bf16 box
 
+constexpr int kMaxPhases = 4;  // output phases one launch may cover (stride-2 dgrad: dx[h % 2][w % 2])
+
 struct alignas(64) IgemmMaps {
   CUtensorMap in[kMaxViews];
   CUtensorMap w;
   CUtensorMap out;
+  CUtensorMap out_extra[kMaxPhases - 1];  // output views of phases 1..3 (blockIdx.z)
+};
+
+// geometry + tap table of an additional output phase (phase 0 lives in the IgemmParams fields themselves)
+struct PhaseExtra {
+  int num_taps, tiles_h, Hb, Nb, valid_rows, m_tiles;
+  Tap taps[kMaxTaps];
 };
 
 struct IgemmParams {
@@ -57,6 +66,9 @@ struct IgemmParams {
   long long out_sw, out_sh, out_sn;  // byte strides of the output view along W, H, N
   int out_w, out_n;                  // view extents (Wb == out_w)
   Tap taps[kMaxTaps];
+  // multi-phase launches (grid.z = phases): pixel tiles of phase 0 (CTAs with blockIdx.x beyond their phase's count exit at once)
+  int m_tiles;
+  PhaseExtra ex[kMaxPhases - 1];
 };
 
 template <int BLOCK_N, int STAGES>
@@ -78,8 +90,20 @@ struct IgemmSmem {
 //               MN-major: 64-row x 64-element boxes, 8 KB each, one per 64 output channels.
 template <int BLOCK_N, int STAGES, int MIN_BLOCKS, bool B_MN>
 __global__ void __launch_bounds__(192, MIN_BLOCKS)
-conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
+conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ IgemmParams p) {
   using L = IgemmSmem<BLOCK_N, STAGES>;
+  // blockIdx.z = output phase: the four phase GEMMs of a stride-2 dgrad (different tap subsets, output views and -- for odd
+  // tensors -- tile shapes) run as ONE grid instead of four part-filled ones
+  int num_taps = p.num_taps, tiles_h = p.tiles_h, Hb = p.Hb, Nb = p.Nb, valid_rows = p.valid_rows, m_tiles = p.m_tiles;
+  const Tap* taps = p.taps;
+  const CUtensorMap* out_map = &maps.out;
+  if (blockIdx.z > 0) {
+    const PhaseExtra& e = p.ex[blockIdx.z - 1];
+    num_taps = e.num_taps, tiles_h = e.tiles_h, Hb = e.Hb, Nb = e.Nb, valid_rows = e.valid_rows, m_tiles = e.m_tiles;
+    taps = e.taps;
+    out_map = &maps.out_extra[blockIdx.z - 1];
+  }
+  if ((int)blockIdx.x >= m_tiles) return;  // whole CTA, before any barrier / TMEM allocation
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -97,15 +121,15 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
 
   const int m_tile = blockIdx.x;
   const int n_tile = blockIdx.y;
-  const int n_blk = m_tile / p.tiles_h;
-  const int h_blk = m_tile - n_blk * p.tiles_h;
-  const int a0 = h_blk * p.Hb;
-  const int n0 = n_blk * p.Nb;
-  const int iters = p.num_taps * p.c_chunks;
+  const int n_blk = m_tile / tiles_h;
+  const int h_blk = m_tile - n_blk * tiles_h;
+  const int a0 = h_blk * Hb;
+  const int n0 = n_blk * Nb;
+  const int iters = num_taps * p.c_chunks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.w);
-    tma_prefetch_desc(&maps.out);
+    tma_prefetch_desc(out_map);
     tma_prefetch_desc(&maps.in[0]);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
@@ -124,10 +148,10 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      const uint32_t tx_bytes = (uint32_t)p.valid_rows * 128u + (uint32_t)L::kB;
+      const uint32_t tx_bytes = (uint32_t)valid_rows * 128u + (uint32_t)L::kB;
       int it = 0;
-      for (int t = 0; t < p.num_taps; ++t) {
-        const Tap tap = p.taps[t];
+      for (int t = 0; t < num_taps; ++t) {
+        const Tap tap = taps[t];
         const CUtensorMap* in_map = &maps.in[tap.map];
         for (int cc = 0; cc < p.c_chunks; ++cc, ++it) {
           const int s = it % STAGES;
@@ -219,14 +243,14 @@ conv_igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy) store
       named_bar_sync(1, 128);
       if (et == 0) {
-        tma_store_4d(&maps.out, buf, n_tile * BLOCK_N + ch * 64, 0, a0, n0);
+        tma_store_4d(out_map, buf, n_tile * BLOCK_N + ch * 64, 0, a0, n0);
         tma_store_commit();
       }
       if (p.stats != nullptr) {
         // BatchNorm partials of the STORED (bf16-rounded) tile: thread = (channel pair wc, row quarter rq), one 32-bit shared load
         // per row, 8 loads in flight (round 1: one dependent 16-bit load per row and channel, ~1 us per tile)
         const int wc = et & 31, rq = et >> 5;
-        const int rend = min(p.valid_rows - rq * 32, 32);
+        const int rend = min(valid_rows - rq * 32, 32);
         const uint8_t* colp = buf_gen + (wc & 3) * 4;
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
@@ -1282,26 +1306,50 @@ int launch_igemm_splitk_t(mml_ctx* ctx, const IgemmMaps& maps, const IgemmParams
 
 int g_splitk_max = 1;  // largest cluster the split-K variant may use (mml_debug_set key 2; 1 = off, the default: see DESIGN.md)
 
-// One "shifted GEMM" launch: out view <- sum over taps of in views @ weights.
+// One "shifted GEMM" launch: out view <- sum over taps of in views @ weights, for 1..4 output phases (grid.z).
 //   b_mn = false: w is [cout rows][n_wtaps*cin inner] bf16;   b_mn = true: w is [cin rows][n_wtaps*cout inner] bf16
-int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, int n_wtaps, int cin, int cout, const View& out,
-              const Tap* taps, int num_taps, double* stats, bool b_mn, cudaStream_t st) {
+// Several phases (stride-2 dgrad): every phase reads the ONE input view through its own tensor map (in[i], boxed for that phase's
+// tile shape -- odd tensors have phases of different extents) and writes its own output view.
+struct PhaseDesc {
+  View out;
+  const Tap* taps;
+  int num_taps;
+};
+
+int run_igemm_phases(mml_ctx* ctx, const View* in_views, int n_views, const void* w, int n_wtaps, int cin, int cout, const PhaseDesc* ph,
+                     int n_ph, double* stats, bool b_mn, cudaStream_t st) {
   MML_REQUIRE(ctx, cin % 64 == 0 && cout % 64 == 0, "conv: channel counts must be multiples of 64 (got C=%d K=%d)", cin, cout);
-  MML_REQUIRE(ctx, num_taps >= 1 && num_taps <= kMaxTaps && n_views <= kMaxViews, "conv: bad tap table");
-  TileGeom tg;
-  MML_REQUIRE(ctx, choose_tile(out.Wv, out.Hv, out.N, &tg), "conv: output width %d not supported (max 128)", out.Wv);
+  MML_REQUIRE(ctx, n_ph >= 1 && n_ph <= kMaxPhases && n_views <= kMaxViews && (n_ph == 1 || (n_views == 1 && stats == nullptr)),
+              "conv: bad phase table");
+  TileGeom tgs[kMaxPhases];
+  int total_tiles = 0, max_tiles = 0;
+  for (int i = 0; i < n_ph; ++i) {
+    MML_REQUIRE(ctx, ph[i].num_taps >= 1 && ph[i].num_taps <= kMaxTaps, "conv: bad tap table");
+    MML_REQUIRE(ctx, choose_tile(ph[i].out.Wv, ph[i].out.Hv, ph[i].out.N, &tgs[i]), "conv: output width %d not supported (max 128)", ph[i].out.Wv);
+    const int t = tgs[i].tiles_h * tgs[i].tiles_n;
+    total_tiles += t;
+    if (t > max_tiles) max_tiles = t;
+  }
+  const TileGeom& tg = tgs[0];
+  const View& out = ph[0].out;
+  const int num_taps = ph[0].num_taps;
   IgemmMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc;
-  for (int i = 0; i < n_views; ++i)
-    if ((rc = encode_view(ctx, &maps.in[i], in_views[i], tg.Wb, tg.Hb, tg.Nb))) return rc;
+  if (n_ph == 1) {
+    for (int i = 0; i < n_views; ++i)
+      if ((rc = encode_view(ctx, &maps.in[i], in_views[i], tg.Wb, tg.Hb, tg.Nb))) return rc;
+  } else {
+    for (int i = 0; i < n_ph; ++i)
+      if ((rc = encode_view(ctx, &maps.in[i], in_views[0], tgs[i].Wb, tgs[i].Hb, tgs[i].Nb))) return rc;
+  }
   // 128x256 tiles have the best operand reuse, but a grid far below one wave (ResNet18 layer4: 32 pixel tiles) runs faster
   // with 128x128 tiles on twice as many SMs
   int block_n = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
-  if (block_n == 256 && tg.tiles_h * tg.tiles_n * (cout / 256) * 2 <= ctx->sm_count) block_n = 128;
+  if (block_n == 256 && total_tiles * (cout / 256) * 2 <= ctx->sm_count) block_n = 128;
   // a single pixel tile (the Linear layers of the MMIMDb step: M = batch <= 128): spread the output columns over as many SMs
   // as possible, every CTA streams the whole A operand from L2 anyway
-  if (tg.tiles_h * tg.tiles_n == 1) block_n = 64;
+  if (total_tiles == 1) block_n = 64;
   if (!b_mn) {
     if ((rc = encode_weights(ctx, &maps.w, w, (long long)n_wtaps * cin, cout, block_n))) return rc;
   } else {
@@ -1318,13 +1366,24 @@ int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, in
   p.Hb = tg.Hb;
   p.Nb = tg.Nb;
   p.valid_rows = tg.valid_rows;
+  p.m_tiles = tg.tiles_h * tg.tiles_n;
   p.cout = cout;
   p.stats = stats;
-  for (int i = 0; i < num_taps; ++i) p.taps[i] = taps[i];
+  for (int i = 0; i < num_taps; ++i) p.taps[i] = ph[0].taps[i];
+  for (int i = 1; i < n_ph; ++i) {
+    PhaseExtra& e = p.ex[i - 1];
+    e.num_taps = ph[i].num_taps, e.tiles_h = tgs[i].tiles_h, e.Hb = tgs[i].Hb, e.Nb = tgs[i].Nb, e.valid_rows = tgs[i].valid_rows;
+    e.m_tiles = tgs[i].tiles_h * tgs[i].tiles_n;
+    for (int t = 0; t < ph[i].num_taps; ++t) {
+      e.taps[t] = ph[i].taps[t];
+      e.taps[t].map = (int8_t)i;  // this phase's boxing of the input view
+    }
+    if ((rc = encode_view(ctx, &maps.out_extra[i - 1], ph[i].out, tgs[i].Wb, tgs[i].Hb, tgs[i].Nb))) return rc;
+  }
   // grids far below one wave: split the K loop over a cluster (see conv_igemm_splitk_kernel).  The cluster size is capped
   // (default 4) because a cluster needs that many free SMs in ONE GPC at the same time, which a concurrently running persistent
   // kernel of another stream (the audio encoder) makes unlikely for large clusters.
-  {
+  if (n_ph == 1) {
     const int tiles = tg.tiles_h * tg.tiles_n * (cout / block_n);
     int S = 1;
     for (int c = 2; c <= g_splitk_max && c <= 8; c *= 2)
@@ -1349,7 +1408,7 @@ int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, in
       }
     }
   }
-  dim3 grid(tg.tiles_h * tg.tiles_n, cout / block_n);
+  dim3 grid(max_tiles, cout / block_n, n_ph);
   if (!b_mn) {
     switch (block_n) {
       case 64: return launch_igemm_t<64, 3, 2, false>(ctx, maps, p, grid, st);
@@ -1363,7 +1422,14 @@ int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, in
       case 256: return launch_igemm_t<256, 3, 1, true>(ctx, maps, p, grid, st);
     }
   }
-  return mml_set_error(ctx, MML_ERR_INVALID, "conv: unsupported K=%d", cout);
+  return mml_set_error(ctx, MML_ERR_INVALID, "conv: unsupported tile width %d", block_n);
+}
+
+int run_igemm(mml_ctx* ctx, const View* in_views, int n_views, const void* w, int n_wtaps, int cin, int cout, const View& out,
+              const Tap* taps, int num_taps, double* stats, bool b_mn, cudaStream_t st) {
+  PhaseDesc ph;
+  ph.out = out, ph.taps = taps, ph.num_taps = num_taps;
+  return run_igemm_phases(ctx, in_views, n_views, w, n_wtaps, cin, cout, &ph, 1, stats, b_mn, st);
 }
 
 int check_geom(mml_ctx* ctx, const mml_conv_geom* g, int* P, int* Q) {
@@ -1505,9 +1571,12 @@ int launch_wgrad_t(mml_ctx* ctx, const WgradMaps& maps, const WgradParams& p, di
 extern "C" {
 
 /* experiment / A-B switches: key 1 = halo kernel enable (0/1), key 2 = largest split-K cluster (1 = off, 2, 4, 8) */
+extern int mml_g_bn_one_wave;  // bn_act.cu
+
 int mml_debug_set(int key, int value) {
   if (key == 1) g_halo_enable = value;
   else if (key == 2 && (value == 1 || value == 2 || value == 4 || value == 8)) g_splitk_max = value;
+  else if (key == 3 && (value == 0 || value == 1)) mml_g_bn_one_wave = value;
   else return MML_ERR_INVALID;
   return MML_OK;
 }
@@ -1582,12 +1651,12 @@ int mml_conv_dgrad(mml_ctx* ctx, const mml_conv_geom* g, const uint16_t* dy, con
   HaloGeom hg;
   if (g_halo_enable && g->R == 3 && s2 == 1 && g->pad == 1 && n_launch == 1 && launches[0].n == 9 && halo_geometry(g->W, g->H, g->N, g->K, g->C, &hg))
     return run_halo(ctx, in, w_krsc, 9, g->K, g->C, launches[0].out, launches[0].taps, 9, nullptr, true, hg, st);
-  for (int i = 0; i < n_launch; ++i) {
-    // GEMM-K = k (rows of the K,R,S,C weight matrix), GEMM-N = c: the fprop weights are read as an MN-major B operand
-    rc = run_igemm(ctx, &in, 1, w_krsc, g->R * g->S, g->K, g->C, launches[i].out, launches[i].taps, launches[i].n, nullptr, true, st);
-    if (rc) return rc;
-  }
-  return MML_OK;
+  // GEMM-K = k (rows of the K,R,S,C weight matrix), GEMM-N = c: the fprop weights are read as an MN-major B operand.  The output
+  // phases of a strided convolution (up to four part-filled grids in round 1) go out as ONE launch, grid.z = phase.
+  PhaseDesc ph[kMaxPhases];
+  for (int i = 0; i < n_launch; ++i) ph[i].out = launches[i].out, ph[i].taps = launches[i].taps, ph[i].num_taps = launches[i].n;
+  if (n_launch == 0) return MML_OK;
+  return run_igemm_phases(ctx, &in, 1, w_krsc, g->R * g->S, g->K, g->C, ph, n_launch, nullptr, true, st);
 }
 
 // how mml_conv_wgrad will run a geometry: kernel family, grid, splits and the workspace it needs for the per-CTA / per-split partials

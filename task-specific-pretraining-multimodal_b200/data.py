@@ -10,6 +10,11 @@ the host only has to produce the masks -- and to get the batch onto the device w
 
 ``create_missing_mask`` itself lives in the external ``modalities`` package that is not part of the reference tree; the
 draw below is its documented behaviour (independent Bernoulli(P(present)) per sample and modality).
+
+Device side (csrc/staging.cu): ``DeviceMaskTable`` draws the whole table on the GPU (counter-based Philox4x32-10: the bits depend
+on (seed, pattern, modality, sample) only, so every data-parallel rank and the CPU oracle agree) and gathers a batch's masks by
+sample index; ``luma_lut`` + ``DevicePrefetcher(luts=...)`` turn the reference's per-item ``uint8 -> gist_earth -> "L" -> float32``
+image conversion (data/avmnist.py:188-191) into one byte per pixel over PCIe and a 256-entry table lookup on the device.
 """
 from __future__ import annotations
 
@@ -17,6 +22,7 @@ from collections import OrderedDict, deque
 from itertools import chain, combinations
 from typing import Any, Dict, Iterable, Iterator, Mapping, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 
@@ -74,6 +80,64 @@ def attach_masks(batch: Dict[Any, Any], masks: Mapping[str, torch.Tensor], modal
     return out
 
 
+class DeviceMaskTable:
+    """pattern -> fp32 [n_modalities, num_samples] masks resident on the device, drawn there (``mml_missing_mask_draw``).
+
+    ``masks[pattern]`` plays the role of ``MultimodalBaseDataset.masks[pattern]`` (base_dataset.py:46-59); ``batch(pattern, idx)``
+    is the per-item lookup of ``__getitem__`` for a whole batch: {modality: fp32 [B]} views of one gathered [n_modalities, B] buffer.
+    The draw is a pure function of (seed, pattern index, modality index, sample index)."""
+
+    def __init__(self, patterns: "Mapping[str, Mapping[str, float]]", num_samples: int, seed: int, device):
+        from . import ops
+
+        self.device = torch.device(device)
+        self.num_samples, self.seed = int(num_samples), int(seed)
+        self.patterns = list(patterns)
+        self.modalities = {pat: list(probs) for pat, probs in patterns.items()}
+        self.masks: Dict[str, torch.Tensor] = {}
+        self.bad = torch.zeros(1, dtype=torch.int32, device=self.device)
+        for k, (pat, probs) in enumerate(patterns.items()):
+            p = torch.tensor([float(v) for v in probs.values()], dtype=torch.float32).to(self.device)
+            self.masks[pat] = ops.missing_mask_draw(p, self.num_samples, self.seed, stream_id=k)
+
+    def as_dict(self, pattern: str) -> Dict[str, torch.Tensor]:
+        return {m: self.masks[pattern][j] for j, m in enumerate(self.modalities[pattern])}
+
+    def batch(self, pattern: str, sample_idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        from . import ops
+
+        idx = sample_idx.to(self.device, dtype=torch.int64, non_blocking=True).contiguous()
+        g = ops.missing_mask_gather(self.masks[pattern], idx, out, self.bad)
+        return {m: g[j] for j, m in enumerate(self.modalities[pattern])}
+
+    def check_indices(self) -> None:
+        """Raises if any ``batch`` call so far carried a sample index outside [0, num_samples) (one host sync; call it per epoch)."""
+        if int(self.bad.item()):
+            raise IndexError("DeviceMaskTable.batch: a sample index was outside [0, num_samples)")
+
+
+def luma_lut(cmap_table, scale: str = "mul") -> torch.Tensor:
+    """fp32 [256] table of ``AVMNIST._load_image`` (data/avmnist.py:188-191) for uint8 pixels.
+
+    ``cmap_table``: the colormap's 256 colours as floats in [0, 1], shape [256, 3 or 4] -- for the reference:
+    ``matplotlib.cm.gist_earth(np.arange(256))`` (matplotlib indexes the table directly for integer pixels).  Each entry goes through
+    the same arithmetic as the reference: ``np.uint8(colour * 255)`` (truncation), PIL's "L" conversion
+    ``(19595 R + 38470 G + 7471 B + 0x8000) >> 16`` (alpha ignored), then fp32 scaling -- ``scale="mul"``: torchvision's
+    ``ToDtype(float32, scale=True)`` = ``x * (1/255)``; ``scale="div"``: ``x.float() / 255.0`` (train_monomodal.py:55-62)."""
+    t = np.asarray(cmap_table, dtype=np.float64)
+    if t.ndim != 2 or t.shape[0] != 256 or t.shape[1] not in (3, 4):
+        raise ValueError(f"expected a [256, 3|4] colour table, got {t.shape}")
+    rgb = np.uint8(t[:, :3] * 255).astype(np.uint32)
+    lum = ((rgb[:, 0] * 19595 + rgb[:, 1] * 38470 + rgb[:, 2] * 7471 + 0x8000) >> 16).astype(np.float32)
+    if scale == "mul":
+        lut = lum * np.float32(1.0 / 255.0)
+    elif scale == "div":
+        lut = lum / np.float32(255.0)
+    else:
+        raise ValueError("scale must be 'mul' (torchvision ToDtype) or 'div' (x / 255.0)")
+    return torch.from_numpy(lut.astype(np.float32))
+
+
 class DevicePrefetcher:
     """Iterate a loader of batch dicts with the host->device copies of batch n+1 running under step n.
 
@@ -91,10 +155,13 @@ class DevicePrefetcher:
 
     _streams: Dict[Any, "torch.cuda.Stream"] = {}
 
-    def __init__(self, loader: Iterable[Dict[Any, Any]], device, depth: int = 1):
+    def __init__(self, loader: Iterable[Dict[Any, Any]], device, depth: int = 1, luts: Optional[Mapping[Any, torch.Tensor]] = None):
+        """``luts``: {batch key: fp32 [256] table}: a uint8 tensor under that key crosses PCIe as bytes and is expanded to fp32 on the
+        device by ``mml_stage_u8_lut_f32`` on the copy stream (``luma_lut``: the AVMNIST image conversion)."""
         self.loader, self.device, self.depth = loader, torch.device(device), max(1, int(depth))
         if self.device.type != "cuda":
             raise RuntimeError("DevicePrefetcher stages batches onto a CUDA device")
+        self.luts = {k: v.to(self.device, dtype=torch.float32).contiguous() for k, v in (luts or {}).items()}
         key = self.device.index if self.device.index is not None else torch.cuda.current_device()
         if key not in DevicePrefetcher._streams:
             DevicePrefetcher._streams[key] = torch.cuda.Stream(device=self.device, priority=-1)
@@ -114,6 +181,14 @@ class DevicePrefetcher:
                         buf = slot[k] = torch.empty(v.shape, dtype=v.dtype, device=self.device)
                     buf.copy_(v, non_blocking=True)
                     self.h2d_bytes += v.numel() * v.element_size()
+                    if k in self.luts and v.dtype == torch.uint8:
+                        from . import ops
+
+                        f = slot.get((k, "f32"))
+                        if f is None or f.shape != v.shape:
+                            f = slot[(k, "f32")] = torch.empty(v.shape, dtype=torch.float32, device=self.device)
+                        ops.u8_lut(buf, self.luts[k], f)
+                        buf = f
                     out[k] = buf
                 else:
                     out[k] = v

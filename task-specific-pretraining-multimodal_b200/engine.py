@@ -682,7 +682,7 @@ class _StepPlan:
         """
         skip = self.tune.get("skip", "")  # timing experiments only (results are then meaningless)
         if skip == "image":
-            image_ops = []
+            image_ops = [self.image.join_offload]  # the head's weight gradients were offloaded to that encoder's wgrad stream
         elif skip == "audio":
             audio_ops = []
         main = torch.cuda.current_stream(self.eng.device)

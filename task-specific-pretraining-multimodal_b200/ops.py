@@ -90,6 +90,50 @@ def mask_apply_into(x: torch.Tensor, mask: torch.Tensor, y: torch.Tensor) -> Non
                                          x.numel() // max(B, 1), _stream(x)), "mask_apply")
 
 
+# ---- f4: input staging (staging.cu) --------------------------------------------------------------------------
+def missing_mask_draw(p_present: torch.Tensor, num_samples: int, seed: int, stream_id: int = 0, first_sample: int = 0,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [n_modalities, num_samples] of 0/1: sample ``first_sample + j`` of modality m is present iff its Philox4x32-10 uniform
+    is below ``p_present[m]`` (base_dataset.py:46-59; bit pattern fixed by (seed, stream_id, m, sample) -- include/mml_b200.h)."""
+    ctx = _ctx(p_present)
+    n_mod = p_present.numel()
+    if out is None:
+        out = torch.empty(n_mod, num_samples, device=p_present.device)
+    if out.shape != (n_mod, num_samples):
+        raise MMLError(f"missing_mask_draw: out must be [{n_mod}, {num_samples}]")
+    ctx.check(ctx.lib.mml_missing_mask_draw(ctx.handle, _p(p_present, torch.float32), _p(out, torch.float32), n_mod, int(first_sample),
+                                            int(num_samples), int(num_samples), int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_id) & 0xFFFFFFFF,
+                                            _stream(p_present)), "missing_mask_draw")
+    return out
+
+
+def missing_mask_gather(masks: torch.Tensor, sample_idx: torch.Tensor, out: Optional[torch.Tensor] = None,
+                        bad_flag: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[m, b] = masks[m, sample_idx[b]] (the per-item mask lookup of data/avmnist.py:193-224, for a whole batch)."""
+    ctx = _ctx(masks)
+    n_mod, n = masks.shape
+    B = sample_idx.numel()
+    if out is None:
+        out = torch.empty(n_mod, B, device=masks.device)
+    ctx.check(ctx.lib.mml_missing_mask_gather(ctx.handle, _p(masks, torch.float32), _p(sample_idx, torch.int64), _p(out, torch.float32), n_mod, n, B,
+                                              _p(bad_flag, torch.int32), _stream(masks)), "missing_mask_gather")
+    return out
+
+
+def u8_lut(src: torch.Tensor, lut: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 ``lut[src]`` for a uint8 tensor and a 256-entry fp32 table (data/avmnist.py:188-191 for uint8 pixels, see data.luma_lut)."""
+    ctx = _ctx(src)
+    if lut.numel() != 256:
+        raise MMLError("u8_lut: the table must have 256 entries")
+    if out is None:
+        out = torch.empty(src.shape, device=src.device)
+    if out.numel() != src.numel():
+        raise MMLError("u8_lut: out must have as many elements as src")
+    ctx.check(ctx.lib.mml_stage_u8_lut_f32(ctx.handle, _p(src, torch.uint8), _p(lut, torch.float32), _p(out, torch.float32), src.numel(),
+                                           _stream(src)), "stage_u8_lut")
+    return out
+
+
 # ---- stem ----------------------------------------------------------------------------------------------------
 def stem_fprop(x, mask, w, y, stats) -> None:
     """stats: ``bn_stats_buffer(64)`` accumulator (zeroed by the caller) or None."""

@@ -49,6 +49,14 @@ SHAPES = [
     (256, 2, 2, 256, 256, 3, 1, 1),   # R34 layer3
     (256, 1, 1, 512, 512, 3, 1, 1),   # R34 layer4
     (250, 28, 28, 64, 64, 3, 1, 1),   # ragged batch on the persistent path (tile count not a multiple of the grid)
+    # stride-2 dgrad = ONE launch over the four output phases (grid.z): equal phases (14x14 -> 7x7 each), unequal phases of an odd
+    # tensor (7x7 -> 4x4, 4x3, 3x4, 3x3: different tile shapes and tile counts per phase), ragged batch
+    (256, 7, 7, 256, 512, 3, 2, 1),   # R18 layer4.0.conv1
+    (256, 7, 7, 64, 128, 3, 2, 1),    # R34 layer2.0.conv1
+    (256, 4, 4, 128, 256, 3, 2, 1),   # R34 layer3.0.conv1
+    (250, 2, 2, 256, 512, 3, 2, 1),   # R34 layer4.0.conv1 (2x2 -> phases of 1x1)
+    (37, 7, 5, 64, 64, 3, 2, 1),      # odd x odd, ragged
+    (256, 7, 7, 256, 512, 1, 2, 0),   # 1x1 stride 2: three of the four phases receive no tap (zero-filled)
 ]
 
 

@@ -60,6 +60,30 @@ def conv(N, H, W, C, K, R, st, pad, tag=""):
     print(f"conv {tag:10s} N={N} {H}x{W} C={C} K={K} R={R} s={st}: fprop {tf:6.1f} us ({fl / tf / 1e6:6.0f} TF)  dgrad {td:6.1f} us ({fl / td / 1e6:6.0f} TF)  wgrad {tw:6.1f} us ({fl / tw / 1e6:6.0f} TF)")
 
 
+def bn(rows, Cn, tag=""):
+    """Fused BatchNorm kernels on a [rows, C] bf16 tensor: GB/s = algorithmic bytes (tensors read + written once) / time."""
+    x, res, dy, dy2 = (torch.randn(rows, Cn, device="cuda").to(BF) for _ in range(4))
+    y, gs, dx = (torch.empty_like(x) for _ in range(3))
+    stats = ops.bn_stats_buffer(Cn, "cuda")
+    xf = x.float()
+    stats[0, :, 0] = xf.sum(0).double()
+    stats[0, :, 1] = (xf * xf).sum(0).double()
+    bstat = ops.bn_stats_buffer(Cn, "cuda")
+    f = lambda *sh: torch.zeros(*sh, device="cuda")
+    b = ops.BNBuffers(stats, torch.ones(Cn, device="cuda"), f(Cn), f(Cn), torch.ones(Cn, device="cuda"), f(Cn), torch.ones(Cn, device="cuda"))
+    dg, db = f(Cn), f(Cn)
+    ops.bn_train_fwd(x, b, res, None, y, rows, Cn, True)
+    nb = rows * Cn * 2
+    out = []
+    for mode in (0, 1):
+        ops.debug_set(3, mode)
+        tf = timeit(lambda: ops.bn_train_fwd(x, b, res, None, y, rows, Cn, True))
+        tr = timeit(lambda: (bstat.zero_(), ops.bn_bwd_reduce(dy, dy2, y, x, b.mean, b.invstd, bstat, gs, rows, Cn, True)))
+        ta = timeit(lambda: ops.bn_bwd_apply(gs, x, b.mean, b.invstd, b.gamma, bstat, dg, db, dx, rows, Cn))
+        out.append(f"wave={mode}: fwd {tf:5.1f} us ({3 * nb / tf / 1e3:5.0f} GB/s)  reduce {tr:5.1f} us ({5 * nb / tr / 1e3:5.0f})  apply {ta:5.1f} us ({3 * nb / ta / 1e3:5.0f})")
+    print(f"bn {tag:6s} rows={rows} C={Cn}: " + " | ".join(out))
+
+
 def head(B):
     g = torch.Generator(device="cuda").manual_seed(0)
     r = lambda *sh: torch.randn(*sh, device="cuda", generator=g) * 0.05
@@ -97,6 +121,20 @@ if __name__ == "__main__":
         conv(B, 1, 1, 512, 512, 3, 1, 1, "i.l4")
     if what in ("all", "head"):
         head(B)
+    if what in ("all", "bn"):
+        bn(B * 28 * 28, 64, "a.l1")
+        bn(B * 14 * 14, 128, "a.l2")
+        bn(B * 7 * 7, 256, "a.l3")
+        bn(B * 4 * 4, 512, "a.l4")
+        bn(B * 7 * 7, 64, "i.l1")
+        bn(B * 2 * 2, 256, "i.l3")
+    if what == "s2":
+        conv(B, 28, 28, 64, 128, 3, 2, 1, "a.l2.0c1")
+        conv(B, 14, 14, 128, 256, 3, 2, 1, "a.l3.0c1")
+        conv(B, 7, 7, 256, 512, 3, 2, 1, "a.l4.0c1")
+        conv(B, 7, 7, 64, 128, 3, 2, 1, "i.l2.0c1")
+        conv(B, 4, 4, 128, 256, 3, 2, 1, "i.l3.0c1")
+        conv(B, 2, 2, 256, 512, 3, 2, 1, "i.l4.0c1")
     if what == "l1":
         conv(B, 28, 28, 64, 64, 3, 1, 1, "a.l1")
     if what == "l3":

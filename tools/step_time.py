@@ -7,6 +7,9 @@ import late_fusion_oracle as O
 from mml_b200.avmnist import AVMNIST
 from mml_b200.resnet import ResNet18, ResNet34
 dev = torch.device("cuda:0"); B = 256
+if os.environ.get('MML_SPLITK'):
+    from mml_b200 import ops as _ops
+    _ops.debug_set(2, int(os.environ['MML_SPLITK']))
 torch.manual_seed(0)
 model = AVMNIST(ResNet18(1, 64), ResNet34(1, 128), 128, dropout=0.5).to(dev)
 opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
