@@ -63,7 +63,7 @@ int mml_ctx_set_pdl(mml_ctx* ctx, int enable);
 
 /* A-B switches for experiments (not part of the reference surface): key 1 = use the halo conv kernel (default 1); key 2 = largest
  * thread-block cluster of the split-K convolution variant (1 = off (default), 2, 4, 8); key 3 = BatchNorm grids capped at one
- * resident wave (default 1) */
+ * resident wave (default 1); key 4 = fewest 128-pixel tiles per weight-gradient split (default 48) */
 int mml_debug_set(int key, int value);
 
 /* ---- a1: missing-modality mask -- data/base_dataset.py:70-72  sample[mod] = original * mask -------------------- */
@@ -332,6 +332,8 @@ int mml_adam_step(mml_ctx*, float* p, const float* g, float* m, float* v, uint16
                   int64_t* step, int advance_step, void* stream);
 /* fp32 -> bf16 copy (shadow refresh after load_state_dict) */
 int mml_cast_f32_bf16(mml_ctx*, const float* src, uint16_t* dst, int64_t n, void* stream);
+/* exact widening of a bf16 GEMM output for an fp32 consumer (MonomodalEncoder around the MMIMDb encoders: encoder -> fp32 classifier) */
+int mml_cast_bf16_f32(mml_ctx*, const uint16_t* src, float* dst, int64_t n, void* stream);
 /* ---- e: data-parallel gradient all-reduce -- library-owned NCCL communicator (the reference has no distributed code) ------- */
 /* One communicator per ctx.  Rank 0 creates the id (mml_comm_unique_id) and hands the 128 bytes to the other ranks by any
  * out-of-band channel (the Python binding uses torch.distributed's store); every rank then calls mml_comm_init.  max_ctas > 0

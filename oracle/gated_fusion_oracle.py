@@ -217,6 +217,54 @@ def validation_step(st: Dict[str, Tensor], I: Tensor, T: Tensor, labels: Tensor,
 
 
 # ----------------------------------------------------------------------------------------------
+# monomodal pre-training of ONE MMIMDb encoder (train_monomodal.py:64-92,224-232 with configs/mmimdb/mono/*.yaml):
+#   MonomodalEncoder(MMIMDbModalityEncoder(in, 512), 512, 23) = BatchNorm1d -> Linear -> Linear(512, 23), BCEWithLogitsLoss on the
+#   multi-hot genre vector, Adam(lr 1e-5, weight_decay 1e-3), predictions = sigmoid > 0.5 (:243).  CUDA path: mml_b200/mono.py.
+# ----------------------------------------------------------------------------------------------
+def init_mono_vector_state(in_dim: int, embed: int = 512, classes: int = 23) -> "OrderedDict[str, Tensor]":
+    """Same RNG draws, in the same order, as ``MonomodalEncoder(MMIMDbModalityEncoder(in_dim, embed), embed, classes)``."""
+    st: "OrderedDict[str, Tensor]" = OrderedDict()
+    _bn_entries(st, "encoder.net.0", in_dim)
+    st["encoder.net.1.weight"], st["encoder.net.1.bias"] = _linear_params(embed, in_dim)
+    st["classifier.weight"], st["classifier.bias"] = _linear_params(classes, embed)
+    return st
+
+
+def mono_vector_forward(st: Dict[str, Tensor], x: Tensor, training: bool, emulate_bf16: bool = False) -> Tensor:
+    q = emulate_bf16
+    xn = _q(_bn1d(st, "encoder.net.0", x, training), q)
+    emb = _qg(_q(F.linear(xn, _qw(st["encoder.net.1.weight"], q), _qw(st["encoder.net.1.bias"], q)), q), q)
+    return F.linear(emb.reshape(emb.shape[0], -1), st["classifier.weight"], st["classifier.bias"])
+
+
+def mono_vector_train_step(st: "OrderedDict[str, Tensor]", opt_state: Dict, x: Tensor, labels: Tensor, lr: float = 1e-5,
+                           weight_decay: float = 1e-3, apply_update: bool = True, emulate_bf16: bool = False,
+                           threshold: float = 0.5) -> Dict[str, object]:
+    params = {k: v for k, v in st.items() if is_parameter(k)}
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    work = dict(st)
+    work.update(leaves)
+    logits = mono_vector_forward(work, x, True, emulate_bf16)
+    loss = total_loss(logits, labels)
+    gl = torch.autograd.grad(loss, list(leaves.values()))
+    grads = dict(zip(leaves.keys(), gl))
+    for k in st:
+        if k.endswith("num_batches_tracked"):
+            st[k] = work[k]
+    if apply_update:
+        with torch.no_grad():
+            adam_step(params, grads, opt_state, lr=lr, weight_decay=weight_decay)
+    preds = (torch.sigmoid(logits.detach()) > threshold).to(torch.int64)
+    return {"loss": float(loss.item()), "logits": logits.detach(), "predictions": preds, "grads": grads}
+
+
+@torch.no_grad()
+def mono_vector_validation_step(st: Dict[str, Tensor], x: Tensor, labels: Tensor, threshold: float = 0.5) -> Dict[str, object]:
+    logits = mono_vector_forward(dict(st), x, False)
+    return {"loss": float(total_loss(logits, labels).item()), "logits": logits, "predictions": (torch.sigmoid(logits) > threshold).to(torch.int64)}
+
+
+# ----------------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md section 8d, config 3)
 # ----------------------------------------------------------------------------------------------
 def synthetic_batch(batch: int, seed: int, image_dim: int = 4096, text_dim: int = 300, hidden: int = 512, classes: int = 23,

@@ -119,6 +119,7 @@ SIGNATURES = {
     "mml_clip_grad_scale": (I32, [P, P, I64, F32, F32, P, I32, P, P, P]),
     "mml_adam_step": (I32, [P, P, P, P, P, P, I64, P, P, I32, P]),
     "mml_cast_f32_bf16": (I32, [P, P, P, I64, P]),
+    "mml_cast_bf16_f32": (I32, [P, P, P, I64, P]),
     "mml_comm_unique_id": (I32, [P, P]),
     "mml_comm_init": (I32, [P, P, I32, I32, I32]),
     "mml_comm_world": (I32, [P]),

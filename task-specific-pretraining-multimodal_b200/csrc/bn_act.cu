@@ -6,6 +6,9 @@
 // Activations are NHWC bf16 viewed as a [rows, C] matrix; every thread owns 8 consecutive channels (one 16-byte
 // access) and, because 256-thread blocks stride by a multiple of C/8, the SAME 8 channels for its whole life, so the
 // per-channel coefficients live in registers.
+#include <mutex>
+#include <unordered_map>
+
 #include "mml_common.cuh"
 #include "mml_ctx.h"
 
@@ -721,12 +724,27 @@ int stream_grid(const mml_ctx* ctx, long long items, int U) {
 // two dependent loads) once and then streams ~3x more vectors, instead of 2-3 waves of short CTAs each paying that latency
 // (measured on the ResNet18 layer1 tensor, mml_debug_set key 3 switches it: see DESIGN.md section 4).
 template <typename K>
-int wave_cap(const mml_ctx* ctx, int grid, K kernel) {
+int wave_cap(const mml_ctx* ctx, int grid, K kernel, cudaStream_t st) {
   if (!mml_g_bn_one_wave) return grid;
+  // The occupancy of each kernel is queried ONCE and outside stream capture (a query during capture invalidated a CUDA-graph capture
+  // on the GPU box; every schedule runs two eager steps before it is captured, so the cache is warm by then), kept per kernel address.
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> cache;
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ < 1) {
-    cudaGetLastError();
-    return grid;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find((const void*)kernel);
+    if (it != cache.end()) occ = it->second;
+  }
+  if (occ == 0) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return grid;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ < 1) {
+      cudaGetLastError();
+      return grid;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    cache[(const void*)kernel] = occ;
   }
   const int cap = occ * ctx->sm_count;
   return grid < cap ? grid : cap;
@@ -769,7 +787,7 @@ int mml_bn_train_fwd(mml_ctx* ctx, const uint16_t* x, const double* stats, const
   const double unbias = rows > 1 ? (double)rows / (double)(rows - 1) : 1.0;
   cudaStream_t st = (cudaStream_t)stream;
 #define MML_TR(M, RL) \
-  MML_LAUNCH(ctx, (bn_fwd_kernel<M, RL, true>), wave_cap(ctx, grid, bn_fwd_kernel<M, RL, true>), kThreads, 0, st, x, bn, nullptr, nullptr, res, rbn, nullptr, nullptr, y, n8, C / 8, inv_count, unbias, momentum, eps)
+  MML_LAUNCH(ctx, (bn_fwd_kernel<M, RL, true>), wave_cap(ctx, grid, bn_fwd_kernel<M, RL, true>, st), kThreads, 0, st, x, bn, nullptr, nullptr, res, rbn, nullptr, nullptr, y, n8, C / 8, inv_count, unbias, momentum, eps)
   switch (mode * 2 + (relu ? 1 : 0)) {
     case 0: MML_TR(0, false); break;
     case 1: MML_TR(0, true); break;
@@ -801,7 +819,7 @@ int mml_bn_act_fwd(mml_ctx* ctx, const uint16_t* x, const float* scale, const fl
   const BnTrain none{};
   cudaStream_t st = (cudaStream_t)stream;
 #define MML_FWD(M, RL) \
-  MML_LAUNCH(ctx, (bn_fwd_kernel<M, RL, false>), wave_cap(ctx, grid, bn_fwd_kernel<M, RL, false>), kThreads, 0, st, x, none, scale, shift, res, none, rscale, rshift, y, n8, C / 8, 0.0, 0.0, 0.f, 0.f)
+  MML_LAUNCH(ctx, (bn_fwd_kernel<M, RL, false>), wave_cap(ctx, grid, bn_fwd_kernel<M, RL, false>, st), kThreads, 0, st, x, none, scale, shift, res, none, rscale, rshift, y, n8, C / 8, 0.0, 0.0, 0.f, 0.f)
   switch (mode * 2 + (relu ? 1 : 0)) {
     case 0: MML_FWD(0, false); break;
     case 1: MML_FWD(0, true); break;
@@ -830,7 +848,7 @@ int mml_bn_bwd_reduce(mml_ctx* ctx, const uint16_t* dy1, const uint16_t* dy2, co
   const long long n8 = rows * (C / 8);
   const int grid = bn_bwd_grid(ctx, rows, C);
   cudaStream_t st = (cudaStream_t)stream;
-#define MML_RED(TW, RL, GO) MML_LAUNCH(ctx, (bn_bwd_reduce_kernel<TW, RL, GO>), wave_cap(ctx, grid, bn_bwd_reduce_kernel<TW, RL, GO>), kThreads, 0, st, dy1, dy2, y, x, mean, invstd, bstat, g_out, n8, C / 8)
+#define MML_RED(TW, RL, GO) MML_LAUNCH(ctx, (bn_bwd_reduce_kernel<TW, RL, GO>), wave_cap(ctx, grid, bn_bwd_reduce_kernel<TW, RL, GO>, st), kThreads, 0, st, dy1, dy2, y, x, mean, invstd, bstat, g_out, n8, C / 8)
   const int key = (dy2 ? 4 : 0) | (relu ? 2 : 0) | (g_out ? 1 : 0);
   switch (key) {
     case 0: MML_RED(false, false, false); break;
@@ -852,7 +870,7 @@ int mml_bn_bwd_apply(mml_ctx* ctx, const uint16_t* g, const uint16_t* x, const f
   int rc = check_rows_c(ctx, rows, C);
   if (rc) return rc;
   const long long n8 = rows * (C / 8);
-  MML_LAUNCH(ctx, bn_bwd_apply_kernel, wave_cap(ctx, stream_grid(ctx, n8, kU), bn_bwd_apply_kernel), kThreads, 0, (cudaStream_t)stream, g, x, mean, invstd, gamma, bstat, 1.0f / (float)rows, dgamma, dbeta,
+  MML_LAUNCH(ctx, bn_bwd_apply_kernel, wave_cap(ctx, stream_grid(ctx, n8, kU), bn_bwd_apply_kernel, (cudaStream_t)stream), kThreads, 0, (cudaStream_t)stream, g, x, mean, invstd, gamma, bstat, 1.0f / (float)rows, dgamma, dbeta,
                                                                                        dx, n8, C / 8);
   return MML_OK;
 }
@@ -912,7 +930,7 @@ int mml_stem_bn_pool_bwd(mml_ctx* ctx, const uint16_t* dy, const uint16_t* dy2, 
   MML_LAUNCH(ctx, stem_bn_pool_bwd_kernel, g0, kThreads, 0, st, dy, dy2, argmax, x, mean, invstd, gamma, beta, bstat, dx, N, H, W, C, P, Q);
   // pass 2 in place over the buffer that now holds g: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))
   const long long n8 = (long long)N * H * W * (C / 8);
-  MML_LAUNCH(ctx, bn_bwd_apply_kernel, wave_cap(ctx, stream_grid(ctx, n8, kU), bn_bwd_apply_kernel), kThreads, 0, st, dx, x, mean, invstd, gamma, bstat, inv_count, dgamma, dbeta, dx, n8, C / 8);
+  MML_LAUNCH(ctx, bn_bwd_apply_kernel, wave_cap(ctx, stream_grid(ctx, n8, kU), bn_bwd_apply_kernel, st), kThreads, 0, st, dx, x, mean, invstd, gamma, bstat, inv_count, dgamma, dbeta, dx, n8, C / 8);
   return MML_OK;
 }
 

@@ -1304,6 +1304,7 @@ int launch_igemm_splitk_t(mml_ctx* ctx, const IgemmMaps& maps, const IgemmParams
   return MML_OK;
 }
 
+int g_wgrad_min_tiles = 48;  // fewest pixel tiles (128 pixels each) per weight-gradient split (mml_debug_set key 4; swept on B200: DESIGN.md section 5)
 int g_splitk_max = 1;  // largest cluster the split-K variant may use (mml_debug_set key 2; 1 = off, the default: see DESIGN.md)
 
 // One "shifted GEMM" launch: out view <- sum over taps of in views @ weights, for 1..4 output phases (grid.z).
@@ -1577,6 +1578,7 @@ int mml_debug_set(int key, int value) {
   if (key == 1) g_halo_enable = value;
   else if (key == 2 && (value == 1 || value == 2 || value == 4 || value == 8)) g_splitk_max = value;
   else if (key == 3 && (value == 0 || value == 1)) mml_g_bn_one_wave = value;
+  else if (key == 4 && value >= 1 && value <= 64) g_wgrad_min_tiles = value;
   else return MML_ERR_INVALID;
   return MML_OK;
 }
@@ -1692,6 +1694,11 @@ static int plan_wgrad(const mml_ctx* ctx, const mml_conv_geom* g, int P, int Q, 
   const int m_tiles = wp->tg.tiles_h * wp->tg.tiles_n;
   // one wave: every split's partial tile is written to and read back from the workspace, so more CTAs than SMs only add traffic
   int splits = ctx->sm_count / wp->out_tiles;
+  // ... and every split should own a few pixel tiles: a split of ONE 128-pixel tile runs 8 MMAs and then writes (and the reduce launch
+  // re-reads) a whole fp32 partial tile -- on the ResNet34 2x2 / 1x1 maps the partials were 8x the useful traffic (18.9 MB for a
+  // 2.4 MB gradient), and a single split needs no reduce launch at all
+  const int by_depth = (m_tiles + g_wgrad_min_tiles - 1) / g_wgrad_min_tiles;
+  if (splits > by_depth) splits = by_depth;
   if (splits > m_tiles) splits = m_tiles;
   if (splits < 1) splits = 1;
   wp->splits = splits;

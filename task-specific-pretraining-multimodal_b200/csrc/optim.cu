@@ -79,6 +79,19 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src
     dst[i] = (uint16_t)(pack_bf16x2(src[i], 0.f) & 0xFFFFu);
 }
 
+// bf16 -> fp32 (exact): a GEMM output row handed to an fp32 head (MonomodalEncoder around the MMIMDb encoders)
+__global__ void __launch_bounds__(256) widen_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, long long n) {
+  pdl_sync();
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(src) + i);
+    reinterpret_cast<float4*>(dst)[i] = make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __uint_as_float((uint32_t)src[i] << 16);
+}
+
 constexpr int kMaxClients = 64;
 
 __global__ void __launch_bounds__(256)
@@ -152,6 +165,13 @@ int mml_cast_f32_bf16(mml_ctx* ctx, const float* src, uint16_t* dst, int64_t n, 
   MML_REQUIRE(ctx, ctx && src && dst && n >= 1, "cast: bad arguments");
   MML_REQUIRE(ctx, aligned16(src) && ((uintptr_t)dst & 7u) == 0, "cast: buffers must be aligned");
   MML_LAUNCH(ctx, cast_kernel, flat_grid(ctx, n), 256, 0, (cudaStream_t)stream, src, dst, n);
+  return MML_OK;
+}
+
+int mml_cast_bf16_f32(mml_ctx* ctx, const uint16_t* src, float* dst, int64_t n, void* stream) {
+  MML_REQUIRE(ctx, ctx && src && dst && n >= 1, "cast: bad arguments");
+  MML_REQUIRE(ctx, aligned16(dst) && ((uintptr_t)src & 7u) == 0, "cast: buffers must be aligned");
+  MML_LAUNCH(ctx, widen_kernel, flat_grid(ctx, n), 256, 0, (cudaStream_t)stream, src, dst, n);
   return MML_OK;
 }
 

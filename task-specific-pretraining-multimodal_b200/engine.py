@@ -682,7 +682,7 @@ class _StepPlan:
         """
         skip = self.tune.get("skip", "")  # timing experiments only (results are then meaningless)
         if skip == "image":
-            image_ops = [self.image.join_offload]  # the head's weight gradients were offloaded to that encoder's wgrad stream
+            image_ops = []
         elif skip == "audio":
             audio_ops = []
         main = torch.cuda.current_stream(self.eng.device)
@@ -799,7 +799,10 @@ class _StepPlan:
         else:
             # the head's weight gradients are off the chain too: they share the image encoder's wgrad stream, which is joined
             # before that range's all-reduce / Adam
-            self.image._offload(head_weight_grads)
+            if self.tune.get("skip", "") == "image":
+                head_weight_grads()  # timing experiment without the image encoder: nothing would join its wgrad stream
+            else:
+                self.image._offload(head_weight_grads)
             late = eng.allreduce_range is not None and _late_image_allreduce()
             self._both_encoders(audio_bwd, image_bwd, after_image=finish_image_range if self.tune["adam_split"] and not late else None,
                                 after_image_late=finish_image_range if self.tune["adam_split"] and late else None)

@@ -106,8 +106,8 @@ class MMIMDbModalityEncoder(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         owner = self._mml_owner[0]() if self._mml_owner is not None else None
         if owner is None:
-            raise NotImplementedError("mml_b200.MMIMDbModalityEncoder runs as part of an MMIMDb model (stand-alone use is the "
-                                      "monomodal pre-training path, not built yet)")
+            raise NotImplementedError("mml_b200.MMIMDbModalityEncoder runs as part of an MMIMDb model or inside mml_b200.mono.MonomodalEncoder "
+                                      "(monomodal pre-training)")
         return owner.encode(self._mml_owner[1], x)
 
 

@@ -7,8 +7,12 @@ schedule of ``engine.EncoderPlan`` plus a small tail (encoder fc, classifier, so
 CUDA graph per (batch, input size).  ``get_encoder().state_dict()`` is what ``train_monomodal.py:790-801`` saves and
 ``train_multimodal.py:186-187`` loads into the fusion model -- same names, shapes and dtypes as the reference.
 
-Only ResNet encoders (``mml_b200.resnet``) are built; anything else raises.  File-path batches (the reference loads
-``.pt`` paths inside ``train_step``, :138-160) are host I/O and are not accepted -- pass tensors.
+Two encoder families are built: the ResNet encoders of ``mml_b200.resnet`` (AVMNIST; single-label CrossEntropy) and the
+``MMIMDbModalityEncoder`` of ``mml_b200.mmimdb`` (``configs/mmimdb/mono/*.yaml``: BatchNorm1d -> Linear on a feature vector,
+multi-hot genre targets, ``bce_with_logits``, predictions ``sigmoid > 0.5``, train_monomodal.py:243) -- the latter reuses the
+MMIMDb step's kernels (fused BatchNorm1d, the tcgen05 GEMM with the bias as an extra input column, the BCE head).  Anything else
+(the MOSI LSTM / TextCNN encoders) raises.  File-path batches (the reference loads ``.pt`` paths inside ``train_step``,
+:138-160) are host I/O and are not accepted -- pass tensors.
 """
 from __future__ import annotations
 
@@ -20,7 +24,7 @@ import torch.nn as nn
 
 from . import ops
 from .avmnist import _copy_in
-from .engine import EncoderPlan, FlatState
+from .engine import ALIGN, BF16, BN_EPS, BN_MOMENTUM, EncoderPlan, FlatState, _round_up
 
 _SKIP = ("labels", "label", "genres", "imdb_ids", "pattern_name", "missing_masks", "sample_idx")
 
@@ -121,13 +125,109 @@ class MonoEngine:
         return plan
 
 
+class _VecMonoPlan:
+    """MonomodalEncoder(MMIMDbModalityEncoder(D, E), E, NC) for a fixed batch size: BatchNorm1d -> Linear -> Linear -> BCE.
+
+    Layout as in ``gated_engine``: the encoder Linear is stored augmented ([E][ld], ld = D + 1 rounded up to 64, bias in column D)
+    and its input rows carry a constant 1 there, so the tensor-core GEMM adds the bias and its wgrad yields the bias gradient."""
+
+    def __init__(self, eng: "VecMonoEngine", B: int):
+        self.eng, self.B = eng, B
+        fs, dev, model = eng.fs, eng.device, eng.model
+        params = dict(model.named_parameters())
+        D, E, NC = params["encoder.net.0.weight"].numel(), params["encoder.net.1.weight"].shape[0], params["classifier.weight"].shape[0]
+        if E % 64:
+            raise NotImplementedError("the encoder's output width must be a multiple of 64 for the tensor-core GEMM")
+        if params["classifier.weight"].shape[1] != E:
+            raise ValueError(f"classifier expects {params['classifier.weight'].shape[1]} features but the encoder produces {E}")
+        self.D, self.E, self.NC = D, E, NC
+        L = _round_up(D + 1, ALIGN)
+
+        def f32(*shape):
+            return torch.zeros(*shape, device=dev)
+
+        def b16(*shape):
+            return torch.zeros(*shape, device=dev, dtype=BF16)
+
+        def par(flat, name):
+            return fs.flat_slice(flat, name).view(params[name].shape)
+
+        self.x, self.labels = f32(B, D), f32(B, NC)
+        self.xn, self.xh, self.inv = b16(B, L), f32(B, D), f32(D)
+        self.xn[:, D] = 1.0  # the bias column
+        self.e, self.ef = b16(B, E), f32(B, E)
+        self.logits, self.dlogits, self.loss = f32(B, NC), f32(B, NC), f32(1)
+        self.pred = torch.zeros(B, NC, device=dev, dtype=torch.uint8)
+        self.scratch = f32(ops.bce_head_scratch_floats(B))
+        self.de, self.dxn = b16(B, E), b16(B, L)
+        self.h_loss = torch.zeros(1).pin_memory()
+        self.h_pred = torch.zeros(B, NC, dtype=torch.uint8).pin_memory()
+        om, ov = fs.buf_offsets["encoder.net.0.running_mean"], fs.buf_offsets["encoder.net.0.running_var"]
+        gamma, beta = par(fs.P, "encoder.net.0.weight"), par(fs.P, "encoder.net.0.bias")
+        self.f_bn = ops.bn1d_fwd_desc(ops.BN1D_INPUT, B, D, gamma, beta, fs.S[om:om + D], fs.S[ov:ov + D], x=self.x, xhat=self.xh, invstd=self.inv,
+                                      y_bf16=self.xn, momentum=BN_MOMENTUM, eps=BN_EPS)
+        self.b_bn = ops.bn1d_bwd_desc(ops.BN1D_INPUT, B, D, self.dxn, self.xh, gamma, self.inv, par(fs.G, "encoder.net.0.weight"),
+                                      par(fs.G, "encoder.net.0.bias"))
+        self.gem = (ops.make_geom(B, 1, 1, L, E, 1, 1, 1, 0), fs.aug_matrix(fs.Wb, "encoder.net.1.weight"), fs.aug_matrix(fs.G, "encoder.net.1.weight"))
+        self.cls_w, self.cls_b = par(fs.P, "classifier.weight"), par(fs.P, "classifier.bias")
+        self.d_cls_w, self.d_cls_b = par(fs.G, "classifier.weight"), par(fs.G, "classifier.bias")
+        self.wgrad_ws = ops.WgradScratch(dev)
+        self.threshold = 0.5  # train_monomodal.py:243
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.eager_steps = 0
+        self.launches_per_step = 0
+
+    def run_forward(self, training: bool, with_loss: bool, with_grad: bool = False) -> None:
+        ops.bn1d_fwd(self.f_bn, training)
+        ops.conv_fprop(self.gem[0], self.xn, self.gem[1], self.e, None)
+        ops.cast_bf16_f32(self.e, self.ef)
+        ops.bce_head_fwd(self.ef, self.cls_w, self.cls_b, self.labels if with_loss else None, self.logits, self.loss if with_loss else None,
+                         self.dlogits if with_grad else None, self.pred, self.scratch, self.threshold, 1.0)
+        if training:
+            self.eng.fs.NBT += 1
+
+    def run_train(self) -> None:
+        fs = self.eng.fs
+        fs.G.zero_()
+        self.run_forward(True, True, True)
+        ops.bce_head_bwd(self.dlogits, self.ef, self.cls_w, self.d_cls_w, self.d_cls_b, self.de)
+        ops.conv_wgrad(self.gem[0], self.xn, self.de, self.gem[2], self.wgrad_ws)
+        ops.conv_dgrad(self.gem[0], self.de, self.gem[1], self.dxn)
+        ops.bn1d_bwd(self.b_bn)
+        if self.eng.allreduce is not None:
+            self.eng.allreduce(self, 0, update=lambda: fs.adam(0, fs.total, True))
+        else:
+            fs.adam(0, fs.total, True)
+
+    train_step = _MonoPlan.train_step  # same eager-twice-then-graph protocol
+
+
+class VecMonoEngine:
+    def __init__(self, model: nn.Module, device: torch.device):
+        self.model, self.device = model, device
+        self.fs = FlatState(model, device, augment={"encoder.net.1.weight": "encoder.net.1.bias"})
+        self.plans: Dict[int, _VecMonoPlan] = {}
+        self.world = 1
+        self.allreduce = None
+        self.use_graphs = True
+
+    def plan_for(self, B: int) -> _VecMonoPlan:
+        plan = self.plans.get(B)
+        if plan is None:
+            plan = self.plans[B] = _VecMonoPlan(self, B)
+        return plan
+
+
 class MonomodalEncoder(nn.Module):
     def __init__(self, encoder: nn.Module, output_dim: int, num_classes: int):
         super().__init__()
+        from .mmimdb import MMIMDbModalityEncoder
         from .resnet import ResNetEncoder
 
-        if not isinstance(encoder, ResNetEncoder):
-            raise NotImplementedError(f"mml_b200.MonomodalEncoder wraps the ResNet encoders of mml_b200.resnet; got {type(encoder).__name__}")
+        if not isinstance(encoder, (ResNetEncoder, MMIMDbModalityEncoder)):
+            raise NotImplementedError("mml_b200.MonomodalEncoder wraps the ResNet encoders of mml_b200.resnet and the MMIMDbModalityEncoder "
+                                      f"of mml_b200.mmimdb; got {type(encoder).__name__}")
+        self._vector = isinstance(encoder, MMIMDbModalityEncoder)  # feature-vector encoder, multi-label targets
         self.encoder = encoder
         self.classifier = nn.Linear(output_dim, num_classes)
         self._engine: Optional[MonoEngine] = None
@@ -152,9 +252,13 @@ class MonomodalEncoder(nn.Module):
             device = torch.device("cuda", torch.cuda.current_device())
         eng = self._engine
         if eng is None or eng.device != device:
-            eng = self._engine = MonoEngine(self, device)
             import weakref
-            self.encoder._mml_owner = (weakref.ref(eng), "encoder.")  # stand-alone encoder calls share this flat storage
+            if self._vector:
+                eng = self._engine = VecMonoEngine(self, device)
+                self.encoder._mml_owner = (weakref.ref(self), "mono")  # encoder(x) outside the step -> self.encode
+            else:
+                eng = self._engine = MonoEngine(self, device)
+                self.encoder._mml_owner = (weakref.ref(eng), "encoder.")  # stand-alone encoder calls share this flat storage
             if self._dp is not None:
                 self._dp.attach(eng)
         eng.fs.ensure_fresh()
@@ -196,8 +300,6 @@ class MonomodalEncoder(nn.Module):
         if labels is None:
             raise ValueError(f"No labels found in batch. Available keys: {list(batch.keys())}")
         labels = torch.as_tensor(labels)
-        if labels.dim() != 1:
-            raise NotImplementedError("multi-label monomodal targets (MMIMDb encoders) are not built yet")
         return key, data, labels
 
     def _stage(self, eng: MonoEngine, x: torch.Tensor, labels: Optional[torch.Tensor]) -> _MonoPlan:
@@ -216,10 +318,33 @@ class MonomodalEncoder(nn.Module):
         return plan
 
     # ---- forward / steps --------------------------------------------------------------------------------------------------
+    def _stage_vec(self, eng: "VecMonoEngine", x: torch.Tensor, labels: Optional[torch.Tensor]) -> _VecMonoPlan:
+        x = x.reshape(x.shape[0], -1)
+        plan = eng.plan_for(x.shape[0])
+        if x.shape[1] != plan.D:
+            raise ValueError(f"expected [B, {plan.D}] features, got {tuple(x.shape)}")
+        _copy_in(plan.x, x)
+        if labels is not None:
+            if labels.dim() != 2 or labels.shape[1] != plan.NC:
+                raise ValueError(f"multi-label targets must be [B, {plan.NC}] (bce_with_logits), got {tuple(labels.shape)}")
+            _copy_in(plan.labels, labels.to(torch.float32))
+        return plan
+
+    def encode(self, which: str, x: torch.Tensor) -> torch.Tensor:
+        """``self.encoder(x)`` outside the step (vector encoders): BatchNorm1d -> Linear, fp32 [B, E]."""
+        eng = self._get_engine(x.device if x.is_cuda else next(self.parameters()).device)
+        plan = self._stage_vec(eng, x, None)
+        plan.run_forward(self.training, with_loss=False)
+        return plan.ef.clone()
+
     def forward(self, x) -> torch.Tensor:
         if isinstance(x, list):
             x = torch.stack(x)
         eng = self._get_engine(x.device if x.is_cuda else next(self.parameters()).device)
+        if self._vector:
+            plan = self._stage_vec(eng, x, None)
+            plan.run_forward(self.training, with_loss=False)
+            return plan.logits.clone()
         plan = self._stage(eng, x, None)
         plan.run_forward(self.training, with_loss=False)
         return plan.logits.clone()
@@ -228,13 +353,13 @@ class MonomodalEncoder(nn.Module):
         from .avmnist import AVMNIST
 
         eng = self._get_engine(device)
-        AVMNIST._check_loss(loss_functions)
+        self._check_loss(loss_functions)
         key, x, labels = self._unpack(batch, config)
         self._set_mode(True)
         fs = eng.fs
         fs.adopt_optimizer(optimizer)
         fs.sync_hyper(optimizer, 1.0 / self.world_size)
-        plan = self._stage(eng, x, labels)
+        plan = self._stage_vec(eng, x, labels) if self._vector else self._stage(eng, x, labels)
         plan.train_step()
         fs._host_step += 1
         return self._finish(eng, plan, key, labels, metric_recorder)
@@ -243,18 +368,34 @@ class MonomodalEncoder(nn.Module):
         from .avmnist import AVMNIST
 
         eng = self._get_engine(device)
-        AVMNIST._check_loss(loss_functions)
+        self._check_loss(loss_functions)
         key, x, labels = self._unpack(batch, config)
         self._set_mode(False)
-        plan = self._stage(eng, x, labels)
+        plan = self._stage_vec(eng, x, labels) if self._vector else self._stage(eng, x, labels)
         plan.run_forward(False, with_loss=True)
         return self._finish(eng, plan, key, labels, metric_recorder)
+
+    def _check_loss(self, loss_functions) -> None:
+        """ResNet encoders: one cross_entropy term; MMIMDb encoders: one bce_with_logits term (configs/mmimdb/mono/*.yaml)."""
+        if self._vector:
+            from .mmimdb import MMIMDb
+            MMIMDb._check_loss(loss_functions)
+        else:
+            from .avmnist import AVMNIST
+            AVMNIST._check_loss(loss_functions)
 
     def _finish(self, eng, plan, key, labels, metric_recorder) -> Dict[str, Any]:
         plan.h_loss.copy_(plan.loss, non_blocking=True)
         plan.h_pred.copy_(plan.pred, non_blocking=True)
         torch.cuda.current_stream(eng.device).synchronize()
         loss = float(plan.h_loss[0])
+        if self._vector:  # multi-label: predictions = sigmoid(logits) > 0.5, no accuracy entry (train_monomodal.py:240-258)
+            preds = plan.h_pred.to(torch.bool)
+            targets = labels.detach().cpu()
+            if metric_recorder is not None:
+                for group_name in metric_recorder.config.groups:
+                    metric_recorder.update_group(group_name=group_name, predictions=preds, targets=targets, modality=str(key))
+            return {"loss": loss, "metrics": {"loss": loss}}
         preds = plan.h_pred.to(torch.int64)
         targets = labels.detach().cpu().reshape(-1)
         acc = float((preds == targets).float().mean())

@@ -426,6 +426,11 @@ def adam_step(p, g, m, v, p_bf16, hyper, step, advance_step: bool = True) -> Non
                                     p.numel(), _p(hyper, torch.float32), _p(step, torch.int64), int(advance_step), _stream(p)), "adam_step")
 
 
+def cast_bf16_f32(src, dst) -> None:
+    ctx = _ctx(src)
+    ctx.check(ctx.lib.mml_cast_bf16_f32(ctx.handle, _p(src, BF16), _p(dst, torch.float32), src.numel(), _stream(src)), "cast_bf16_f32")
+
+
 def cast_f32_bf16(src, dst) -> None:
     ctx = _ctx(src)
     ctx.check(ctx.lib.mml_cast_f32_bf16(ctx.handle, _p(src, torch.float32), _p(dst, BF16), src.numel(), _stream(src)), "cast_f32_bf16")

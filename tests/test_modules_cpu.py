@@ -213,6 +213,18 @@ def test_shim_builds_the_other_configs_from_the_reference_yaml_tags():
     rm = O.init_monomodal_state("resnet18", 1, 64, 10)
     sm = mm.state_dict()
     assert list(sm.keys()) == list(rm.keys()) and all(torch.equal(sm[k], rm[k]) for k in rm)
+    # ... and around an MMIMDb encoder (configs/mmimdb/mono/*.yaml)
+    import gated_fusion_oracle as G
+    torch.manual_seed(0)
+    mv = mono.MonomodalEncoder(mmimdb.MMIMDbModalityEncoder(300, 512), 512, 23)
+    torch.manual_seed(0)
+    rv = G.init_mono_vector_state(300, 512, 23)
+    sv = mv.state_dict()
+    assert list(sv.keys()) == list(rv.keys()) and all(torch.equal(sv[k], rv[k]) for k in rv)
+    with pytest.raises(NotImplementedError):
+        mono.MonomodalEncoder(torch.nn.Linear(4, 4), 4, 3)
+    with pytest.raises(RuntimeError):
+        mv.train_step({"text": torch.zeros(2, 300), "label": torch.zeros(2, 23)}, torch.optim.Adam(mv.parameters()), None, torch.device("cpu"), None)
     # no CPU execution path anywhere
     with pytest.raises(RuntimeError):
         model.train_step({"image": torch.zeros(2, 4096), "text": torch.zeros(2, 300), "label": torch.zeros(2, 23), "pattern_name": ["it"] * 2},

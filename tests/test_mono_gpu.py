@@ -130,3 +130,145 @@ def test_monomodal_unsupported_requests_raise():
                          torch.device(DEV), None)
     with pytest.raises(NotImplementedError):
         model.train_step({"audio": torch.rand(2, 28, 28), "labels": torch.zeros(2, 3)}, torch.optim.Adam(model.parameters()), LOSS, torch.device(DEV), None)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# MonomodalEncoder around an MMIMDb encoder (configs/mmimdb/mono/*.yaml): BatchNorm1d -> Linear -> Linear(512, 23), bce_with_logits
+# ---------------------------------------------------------------------------------------------------------------------
+class BceTerm:
+    def __init__(self):
+        self.loss_fn, self.weight = torch.nn.BCEWithLogitsLoss(), 1.0
+
+
+BCE = {"bce": BceTerm()}
+
+
+def build_vec(in_dim, graphs=True):
+    from mml_b200.mmimdb import MMIMDbModalityEncoder
+    from mml_b200.mono import MonomodalEncoder
+
+    torch.manual_seed(0)
+    model = MonomodalEncoder(MMIMDbModalityEncoder(in_dim, 512), 512, 23).to(DEV)
+    model._get_engine(torch.device(DEV)).use_graphs = graphs
+    return model
+
+
+def vec_batch(B, in_dim, seed):
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, in_dim, generator=gen) * 1.5 + 0.3
+    y = (torch.rand(B, 23, generator=gen) < 0.15).float()
+    return x, y
+
+
+@pytest.mark.parametrize("in_dim,B", [(300, 16), (4096, 128), (300, 128), (4096, 37)])
+def test_monomodal_mmimdb_step_matches_oracle(in_dim, B):
+    """Loss / logits / predictions vs the fp32 oracle; gradients vs the oracle rounded to bf16 where the kernels round (GEMM operands and
+    output) at 2 %, vs the fp32 oracle at the bound that rounding itself causes; Adam update exact for the GPU's own gradients."""
+    import gated_fusion_oracle as G
+
+    model = build_vec(in_dim, graphs=False)
+    torch.manual_seed(0)
+    state = G.init_mono_vector_state(in_dim, 512, 23)
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(state.keys())
+    for k in state:
+        assert torch.equal(sd[k].cpu(), state[k]), k
+    x, y = vec_batch(B, in_dim, 31)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5, weight_decay=1e-3)
+    before = {k: v.detach().cpu().clone() for k, v in model.named_parameters()}
+    out = model.train_step({"text": x, "label": y}, opt, BCE, torch.device(DEV), None)
+    ref = G.mono_vector_train_step(copy.deepcopy(state), {}, x, y, apply_update=False)
+    emu = G.mono_vector_train_step(copy.deepcopy(state), {}, x, y, apply_update=False, emulate_bf16=True)
+    plan = next(iter(model._engine.plans.values()))
+    assert abs(out["loss"] - ref["loss"]) < 2e-3 and "accuracy" not in out["metrics"]
+    logits = plan.logits.cpu()
+    span = float(ref["logits"].max() - ref["logits"].min())
+    assert float((logits - ref["logits"]).abs().max()) < 1e-2 * span
+    assert float((logits - emu["logits"]).abs().max()) < 2e-3 * span
+    agree = float(((torch.sigmoid(logits) > 0.5) == ref["predictions"].bool()).float().mean())
+    assert agree > 0.98
+    g = torch.cat([p.grad.detach().cpu().float().reshape(-1) for _, p in model.named_parameters()])
+    r_emu = torch.cat([emu["grads"][n].reshape(-1) for n, _ in model.named_parameters()])
+    r_fp = torch.cat([ref["grads"][n].reshape(-1) for n, _ in model.named_parameters()])
+    rel_emu, rel_fp, self_gap = float((g - r_emu).norm() / r_emu.norm()), float((g - r_fp).norm() / r_fp.norm()), float((r_emu - r_fp).norm() / r_fp.norm())
+    print(f"in={in_dim} B={B}: grad rel L2 vs same-rounding oracle {rel_emu:.4f}, vs fp32 oracle {rel_fp:.4f} (oracle bf16-vs-fp32 {self_gap:.4f})")
+    assert rel_emu < 2e-2 and rel_fp < max(3e-2, 2.5 * self_gap)
+    # Adam (coupled weight decay, lr 1e-5): exact for the gradients the GPU produced; BN running statistics as torch updates them
+    for n, p in model.named_parameters():
+        gg = p.grad.detach().cpu().float() + 1e-3 * before[n]
+        m, v = 0.1 * gg, 0.001 * gg * gg
+        want = before[n] - 1e-5 * (m / 0.1) / ((v / 0.001).sqrt() + 1e-8)
+        assert torch.allclose(p.detach().cpu(), want, rtol=1e-5, atol=1e-7), n
+    sd = model.state_dict()
+    assert int(sd["encoder.net.0.num_batches_tracked"]) == 1
+    assert torch.allclose(sd["encoder.net.0.running_mean"].cpu(), 0.1 * x.mean(0), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(sd["encoder.net.0.running_var"].cpu(), 0.9 + 0.1 * x.var(0, unbiased=True), rtol=1e-4, atol=1e-5)
+
+
+def test_monomodal_mmimdb_reference_fixture_curve_eval_and_handoff():
+    import gated_fusion_oracle as G
+    from mml_b200.mmimdb import MMIMDb, MMIMDbModalityEncoder, GatedBiModalNetwork, MLPGenreClassifier
+
+    gld = np.load(os.path.join(GOLD, "mono_mmimdb_text_b16.npz"))
+    batch, in_dim, seed, steps = (int(v) for v in gld["meta"])
+    model = build_vec(in_dim)
+    x, y = vec_batch(batch, in_dim, seed)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5, weight_decay=1e-3)
+    for step in range(steps):  # the recorded run of the reference class (eager, eager, graph replay)
+        out = model.train_step({"text": x, "label": y}, opt, BCE, torch.device(DEV), None)
+        assert abs(out["loss"] - float(gld["losses"][step])) < 2e-3, (step, out["loss"], float(gld["losses"][step]))
+    # a longer run at a useful learning rate: the loss curve follows the oracle's, CUDA-graph replays included
+    model = build_vec(in_dim)
+    torch.manual_seed(0)
+    state, opt_state = G.init_mono_vector_state(in_dim, 512, 23), {}
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3)
+    x, y = vec_batch(64, in_dim, 5)
+    got, want = [], []
+    for step in range(30):
+        got.append(model.train_step({"text_original": x, "text": x * 0, "genres": y}, opt, BCE, torch.device(DEV), None)["loss"])
+        want.append(G.mono_vector_train_step(state, opt_state, x, y, lr=1e-3)["loss"])
+    assert want[-1] < 0.5 * want[0]
+    assert max(abs(a - b) for a, b in zip(got, want)) < 0.02 * want[0], (got[-3:], want[-3:])
+    # eval mode (running statistics) and the recorder contract for multi-label predictions
+    class Rec:
+        class config:
+            groups = ["classification"]
+        calls = []
+        def update_group(self, **kw):
+            self.calls.append(kw)
+    rec = Rec()
+    ev = model.validation_step({"text": x, "label": y}, BCE, torch.device(DEV), rec)
+    sd_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    rv = G.mono_vector_validation_step(sd_cpu, x, y)
+    assert abs(ev["loss"] - rv["loss"]) < 5e-3
+    assert rec.calls and rec.calls[0]["predictions"].dtype == torch.bool and rec.calls[0]["predictions"].shape == (64, 23)
+    assert float((rec.calls[0]["predictions"] == rv["predictions"].bool()).float().mean()) > 0.97
+    # stand-alone encoder call and the pretrain -> fusion hand-off (train_monomodal.py:790-801 saves get_encoder().state_dict(),
+    # train_multimodal.py:186-187 loads it into the fusion model's encoder)
+    model.eval()
+    emb = model.get_encoder()(x.to(DEV))
+    assert emb.shape == (64, 512)
+    enc_sd = {k: v.detach().cpu().clone() for k, v in model.get_encoder().state_dict().items()}
+    torch.manual_seed(1)
+    fusion = MMIMDb(MMIMDbModalityEncoder(4096, 512), MMIMDbModalityEncoder(in_dim, 512), GatedBiModalNetwork(512, 512, 512, 512),
+                    classifier=MLPGenreClassifier(512, 23, 512)).to(DEV)
+    fusion.text_model.load_state_dict(enc_sd)
+    fusion.eval()
+    emb2 = fusion.text_model(x.to(DEV))
+    assert torch.equal(emb.cpu(), emb2.cpu())
+
+
+def test_monomodal_unsupported_requests_raise():
+    from mml_b200.mono import MonomodalEncoder
+
+    model = build_vec(300)
+    x, y = vec_batch(8, 300, 1)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5)
+    with pytest.raises(ValueError):
+        model.train_step({"text": x, "label": torch.zeros(8, dtype=torch.long)}, opt, BCE, torch.device(DEV), None)  # single-label targets
+    with pytest.raises(NotImplementedError):
+        model.train_step({"text": x, "label": y}, opt, LOSS, torch.device(DEV), None)  # cross-entropy on a multi-label head
+    with pytest.raises(ValueError):
+        model.train_step({"text": x[:, :299], "label": y}, opt, BCE, torch.device(DEV), None)
+    with pytest.raises(NotImplementedError):
+        MonomodalEncoder(torch.nn.LSTM(5, 64), 64, 3)

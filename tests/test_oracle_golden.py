@@ -155,6 +155,33 @@ def test_monomodal_oracle_matches_reference():
             assert np.abs(out["grads"]["classifier.weight"].numpy() - g["grad::classifier.weight"]).max() < 1e-6
 
 
+def test_monomodal_mmimdb_encoder_oracle_matches_reference():
+    """Monomodal pre-training of an MMIMDb encoder (configs/mmimdb/mono/*.yaml): BatchNorm1d -> Linear -> Linear(512, 23), BCE on
+    multi-hot labels, Adam(1e-5, wd 1e-3) -- the oracle against the recorded run of the reference MonomodalEncoder."""
+    import gated_fusion_oracle as G
+
+    g = np.load(os.path.join(GOLD, "mono_mmimdb_text_b16.npz"))
+    batch, in_dim, seed, steps = (int(v) for v in g["meta"])
+    torch.manual_seed(0)
+    state = G.init_mono_vector_state(in_dim, 512, 23)
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, in_dim, generator=gen) * 1.5 + 0.3
+    y = (torch.rand(batch, 23, generator=gen) < 0.15).float()
+    opt_state = {}
+    for step in range(steps):
+        out = G.mono_vector_train_step(state, opt_state, x, y)
+        assert abs(out["loss"] - float(g["losses"][step])) < 1e-6
+        if step == 0:
+            assert np.allclose(out["logits"].numpy(), g["logits"], rtol=1e-5, atol=1e-6)
+            l2 = np.array([float(out["grads"][k].double().norm()) for k in g["grad_keys"]])
+            assert np.allclose(l2, g["grad_l2"], rtol=1e-4, atol=1e-9)
+            for k in ("classifier.weight", "encoder.net.0.weight", "encoder.net.1.bias"):
+                ref = g["grad::" + k]
+                assert np.abs(out["grads"][k].numpy() - ref).max() <= 1e-5 * np.abs(ref).max() + 1e-9, k
+    assert np.allclose(state["classifier.bias"].numpy(), g["final::classifier.bias"], rtol=1e-5, atol=1e-7)
+    assert np.allclose(state["encoder.net.0.running_mean"].numpy(), g["final::encoder.net.0.running_mean"], rtol=1e-5, atol=1e-7)
+
+
 def test_mosi_utt_fusion_oracle_matches_reference():
     """config 4: the oracle for the MOSI / UttFusion step against the recorded reference run -- LSTM x2, TextCNN,
     FcClassifier, CE, clip_grad_norm_(1.0), Adam; zero-padded variable-length sequences and all seven missing patterns."""

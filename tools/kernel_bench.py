@@ -60,6 +60,18 @@ def conv(N, H, W, C, K, R, st, pad, tag=""):
     print(f"conv {tag:10s} N={N} {H}x{W} C={C} K={K} R={R} s={st}: fprop {tf:6.1f} us ({fl / tf / 1e6:6.0f} TF)  dgrad {td:6.1f} us ({fl / td / 1e6:6.0f} TF)  wgrad {tw:6.1f} us ({fl / tw / 1e6:6.0f} TF)")
 
 
+def wgrad_only(N, H, W, C, K, R, st, pad, tag=""):
+    g = ops.make_geom(N, H, W, C, K, R, R, st, pad)
+    P, Q = ops.conv_out_hw(H, W, R, R, st, pad)
+    x = torch.randn(N, H, W, C, device="cuda").to(BF)
+    dy = torch.randn(N, P, Q, K, device="cuda").to(BF)
+    dw = torch.zeros(K, R, R, C, device="cuda")
+    ws = ops.WgradScratch("cuda")
+    fl = 2.0 * N * P * Q * K * C * R * R
+    tw = timeit(lambda: ops.conv_wgrad(g, x, dy, dw, ws), n=9)
+    print(f"wgrad {tag:9s} N={N} {H}x{W} C={C} K={K} s={st}: {tw:6.1f} us ({fl / tw / 1e6:6.0f} TF)")
+
+
 def bn(rows, Cn, tag=""):
     """Fused BatchNorm kernels on a [rows, C] bf16 tensor: GB/s = algorithmic bytes (tensors read + written once) / time."""
     x, res, dy, dy2 = (torch.randn(rows, Cn, device="cuda").to(BF) for _ in range(4))
@@ -128,6 +140,14 @@ if __name__ == "__main__":
         bn(B * 4 * 4, 512, "a.l4")
         bn(B * 7 * 7, 64, "i.l1")
         bn(B * 2 * 2, 256, "i.l3")
+    if what == "wg":
+        for mt in (1, 2, 4, 8, 16):
+            ops.debug_set(4, mt)
+            print(f"--- min pixel tiles per wgrad split = {mt}")
+            for shp, tag in (((B, 7, 7, 64, 64, 3, 1, 1), "i.l1"), ((B, 4, 4, 128, 128, 3, 1, 1), "i.l2"), ((B, 2, 2, 256, 256, 3, 1, 1), "i.l3"),
+                             ((B, 1, 1, 512, 512, 3, 1, 1), "i.l4"), ((B, 2, 2, 256, 512, 3, 2, 1), "i.l4.0c1"), ((B, 7, 7, 256, 256, 3, 1, 1), "a.l3"),
+                             ((B, 4, 4, 512, 512, 3, 1, 1), "a.l4")):
+                wgrad_only(*shp, tag)
     if what == "s2":
         conv(B, 28, 28, 64, 128, 3, 2, 1, "a.l2.0c1")
         conv(B, 14, 14, 128, 256, 3, 2, 1, "a.l3.0c1")

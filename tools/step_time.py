@@ -7,6 +7,12 @@ import late_fusion_oracle as O
 from mml_b200.avmnist import AVMNIST
 from mml_b200.resnet import ResNet18, ResNet34
 dev = torch.device("cuda:0"); B = 256
+if os.environ.get('MML_BN_WAVE'):
+    from mml_b200 import ops as _ops
+    _ops.debug_set(3, int(os.environ['MML_BN_WAVE']))
+if os.environ.get('MML_WGRAD_MIN_TILES'):
+    from mml_b200 import ops as _ops
+    _ops.debug_set(4, int(os.environ['MML_WGRAD_MIN_TILES']))
 if os.environ.get('MML_SPLITK'):
     from mml_b200 import ops as _ops
     _ops.debug_set(2, int(os.environ['MML_SPLITK']))
