@@ -96,6 +96,15 @@ int mml_stem_fprop(mml_ctx*, const float* x, const float* mask, const float* w, 
 /* dw fp32 [64][49] = sum_{b,p,q} dy[b,p,q,k] * (x*mask)[b, 2p+r-3, 2q+s-3]  (overwrites dw) */
 int mml_stem_wgrad(mml_ctx*, const float* x, const float* mask, const uint16_t* dy, float* dw, float* workspace,
                    int64_t workspace_bytes, int B, int H, int W, void* stream);
+/* The same weight gradient with the stem BatchNorm's backward pass 2 folded in (resnet.py:137-138 conv1 -> bn1 and their autograd): g =
+ * gradient w.r.t. the BatchNorm OUTPUT after the ReLU mask (what mml_stem_bn_pool_bwd(apply = 0) leaves in dx), bstat = its (sum g,
+ * sum g*xhat).  Because the stem output is linear in the input patches, dx never has to exist:
+ *   dw[k][t] = gamma_k invstd_k ( sum_p g x_t - mean(g)_k sum_p x_t - mean(g xhat)_k invstd_k ( sum_t' w[k][t'] sum_p x_t' x_t - mu_k sum_p x_t ) )
+ * with the patch Gram matrix and the tap sums produced by the same tensor-core pass that forms sum_p g x_t.  w: the fp32 stem weights the
+ * forward used; also stores dgamma = sum g*xhat and dbeta = sum g.  workspace: mml_stem_wgrad_workspace bytes, 8-byte aligned. */
+int mml_stem_wgrad_bn(mml_ctx*, const float* x, const float* mask, const uint16_t* g, const float* w, const double* bstat, const float* mean,
+                      const float* invstd, const float* gamma, float* dgamma, float* dbeta, float* dw, float* workspace,
+                      int64_t workspace_bytes, int B, int H, int W, void* stream);
 int64_t mml_stem_wgrad_workspace(const mml_ctx*, int B, int H, int W);
 
 /* ---- a2-a4: 3x3 / 1x1 convolutions -- resnet.py:25,30,176 (nn.Conv2d fwd) and their autograd -------------------- */
@@ -148,10 +157,11 @@ int mml_stem_bn_pool_fwd(mml_ctx*, const uint16_t* x, const double* stats, const
                          float* running_var, float* save_mean, float* save_invstd, const float* scale, const float* shift, uint16_t* y,
                          uint8_t* argmax, int N, int H, int W, int C, float momentum, float eps, void* stream);
 /* its backward: dx (grad of the raw stem output) from the pooled gradient(s); ReLU mask recomputed from x; two passes
- * (scatter + statistics, then the in-place apply) */
+ * (scatter + statistics, then the in-place apply).  apply == 0 stops after pass 1: dx holds g = scatter(dpool) * [bn(x) > 0] and bstat
+ * the sums (sum g, sum g*xhat); dgamma / dbeta are then written by mml_stem_wgrad_bn, which folds pass 2 into the weight gradient */
 int mml_stem_bn_pool_bwd(mml_ctx*, const uint16_t* dy, const uint16_t* dy2, const uint8_t* argmax, const uint16_t* x, const float* mean,
                          const float* invstd, const float* gamma, const float* beta, double* bstat, float* dgamma, float* dbeta, uint16_t* dx,
-                         int N, int H, int W, int C, void* stream);
+                         int N, int H, int W, int C, int apply, void* stream);
 /* ---- ConvBlock encoders (MML_Suite/models/conv.py:16-59, models/avmnist.py:34-185: MNISTAudio / MNISTImage) ----
  * First convolution of a ConvBlock encoder: Conv2d(1, K, 3, stride 1, padding 1) over (x * mask) (fp32 [B][H][W], mask [B] or NULL), weights
  * fp32 [K][9], K in {8,16,32,64}; output NHWC bf16 with the channel dimension PADDED to 64 (channels >= K written as zeros) so that every later

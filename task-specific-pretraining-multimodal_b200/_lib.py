@@ -70,6 +70,7 @@ SIGNATURES = {
     "mml_stem_fprop": (I32, [P, P, P, P, P, P, I32, I32, I32, P]),
     "mml_stem_wgrad": (I32, [P, P, P, P, P, P, I64, I32, I32, I32, P]),
     "mml_stem_wgrad_workspace": (I64, [P, I32, I32, I32]),
+    "mml_stem_wgrad_bn": (I32, [P] * 13 + [I64, I32, I32, I32, P]),
     "mml_conv_fprop": (I32, [P, C.POINTER(ConvGeom), P, P, P, P, P]),
     "mml_conv_dgrad": (I32, [P, C.POINTER(ConvGeom), P, P, P, P]),
     "mml_conv_wgrad": (I32, [P, C.POINTER(ConvGeom), P, P, P, P, I64, P]),
@@ -82,7 +83,7 @@ SIGNATURES = {
     "mml_maxpool3x3s2_fwd": (I32, [P, P, P, P, I32, I32, I32, I32, P]),
     "mml_maxpool3x3s2_bwd": (I32, [P, P, P, P, P, I32, I32, I32, I32, P]),
     "mml_stem_bn_pool_fwd": (I32, [P] * 13 + [I32, I32, I32, I32, F32, F32, P]),
-    "mml_stem_bn_pool_bwd": (I32, [P] * 13 + [I32, I32, I32, I32, P]),
+    "mml_stem_bn_pool_bwd": (I32, [P] * 13 + [I32, I32, I32, I32, I32, P]),
     "mml_conv3x3_c1_fprop": (I32, [P, P, P, P, P, P, I32, I32, I32, I32, P]),
     "mml_conv3x3_c1_wgrad": (I32, [P, P, P, P, P, P, I64, I32, I32, I32, I32, P]),
     "mml_conv3x3_c1_wgrad_workspace": (I64, [P, I32, I32, I32]),

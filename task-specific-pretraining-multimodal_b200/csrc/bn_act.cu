@@ -916,7 +916,7 @@ int mml_stem_bn_pool_fwd(mml_ctx* ctx, const uint16_t* x, const double* stats, c
 
 int mml_stem_bn_pool_bwd(mml_ctx* ctx, const uint16_t* dy, const uint16_t* dy2, const uint8_t* argmax, const uint16_t* x, const float* mean,
                          const float* invstd, const float* gamma, const float* beta, double* bstat, float* dgamma, float* dbeta, uint16_t* dx,
-                         int N, int H, int W, int C, void* stream) {
+                         int N, int H, int W, int C, int apply, void* stream) {
   MML_REQUIRE(ctx, ctx && dy && argmax && x && mean && invstd && gamma && beta && bstat && dx && N >= 1 && H >= 1 && W >= 1,
               "stem_bn_pool_bwd: bad arguments");
   int rc = check_rows_c(ctx, (int64_t)N * H * W, C);
@@ -928,6 +928,9 @@ int mml_stem_bn_pool_bwd(mml_ctx* ctx, const uint16_t* dy, const uint16_t* dy2, 
   const int brows = N * ((H + 1) / 2);  // CTAs walk block rows (n, a)
   int g0 = brows < ctx->sm_count * 6 ? brows : ctx->sm_count * 6;
   MML_LAUNCH(ctx, stem_bn_pool_bwd_kernel, g0, kThreads, 0, st, dy, dy2, argmax, x, mean, invstd, gamma, beta, bstat, dx, N, H, W, C, P, Q);
+  // apply == 0: dx keeps g and bstat the two sums -- the caller folds pass 2 into the stem weight gradient (mml_stem_wgrad_bn), the only
+  // consumer of this layer's dx
+  if (!apply) return MML_OK;
   // pass 2 in place over the buffer that now holds g: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))
   const long long n8 = (long long)N * H * W * (C / 8);
   MML_LAUNCH(ctx, bn_bwd_apply_kernel, wave_cap(ctx, stream_grid(ctx, n8, kU), bn_bwd_apply_kernel, st), kThreads, 0, st, dx, x, mean, invstd, gamma, bstat, inv_count, dgamma, dbeta, dx, n8, C / 8);

@@ -284,15 +284,27 @@ stem_fprop_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
   if (warp == 4) tmem_dealloc<128>(tmem_base);
 }
 
-// wgrad smem: [X0 | X1 | DY0 (2 boxes) | DY1 (2 boxes) | patch0 | patch1 | barriers]
-constexpr int kWOffDy = 2 * kTileBytes;
-constexpr int kWOffPatch = kWOffDy + 2 * 2 * kTileBytes;
+// wgrad smem: [DY0 | DY1 | X0 | X1 | patch0 | patch1 | barriers]
+//
+// The MMA is 128 x 64 x 16 with an MN-major A operand whose two 64-row halves sit LBO bytes apart: rows 0..63 = the 64 channels of the
+// dy tile, rows 64..127 = the im2col tile ITSELF (LBO = X - DY), whose otherwise unused last column holds a constant 1.  One pass over
+// dy therefore yields, per CTA,
+//     acc[k][t]       = sum_p dy[p][k] * xcol[p][t]            (the weight gradient w.r.t. whatever dy is)
+//     acc[64 + t'][t] = sum_p xcol[p][t'] * xcol[p][t]         (Gram matrix of the input patches)
+//     acc[127][t]     = sum_p xcol[p][t]                        (tap sums)
+// which is what folds the BatchNorm backward's second pass into this kernel (mml_stem_wgrad_bn below): with dy = g, the gradient after
+// ReLU / pooling but BEFORE the BatchNorm correction,
+//     dW[k][t] = gamma_k*invstd_k * ( acc[k][t] - mean(g)_k * S[t] - mean(g*xhat)_k * invstd_k * ( sum_t' W[k][t'] X2[t'][t] - mu_k * S[t] ) )
+// because the stem output is linear in the patches (raw[p][k] = sum_t' W[k][t'] xcol[p][t']).  The 102 MB dx tensor is never formed.
+constexpr int kWOffX = 2 * kTileBytes;
+constexpr int kWOffPatch = 4 * kTileBytes;
 constexpr int kWOffBars = kWOffPatch + 2 * kPatchBytes;
 constexpr int kWBytes = kWOffBars + 1024 + 1024;
+constexpr int kOnesCol = 63;  // column of the im2col tile that carries the constant 1 (columns r*8+7 and 56..63 are padding)
 
 __global__ void __launch_bounds__(kThreadsStem, 2)
 stem_wgrad_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restrict__ x, const float* __restrict__ mask,
-                     float* __restrict__ ws, StemGeom g) {
+                     float* __restrict__ ws, StemGeom g, int rows_out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -304,10 +316,18 @@ stem_wgrad_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
   const uint32_t tmem_slot = bars + 8u * 5;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kWOffBars + 8 * 5);
 
-  {  // rows >= valid of every tile and the k = 64..127 box of each dy stage are never written: zero everything once
+  {  // rows >= valid of every tile and the padding columns of the im2col tiles are never written: zero everything once ...
     uint4 z = make_uint4(0, 0, 0, 0);
     uint4* base = reinterpret_cast<uint4*>(smem_gen);
     for (int i = threadIdx.x; i < kWOffPatch / 16; i += blockDim.x) base[i] = z;
+    __syncthreads();
+    // ... and put the constant 1 (bf16 0x3F80) into column kOnesCol of every live row of both im2col tiles (gather_row never touches
+    // the last 16-byte chunk of a row, so it stays)
+    for (int i = threadIdx.x; i < 2 * g.valid; i += blockDim.x) {
+      const int b = i / g.valid, row = i - b * g.valid;
+      uint8_t* rowp = smem_gen + kWOffX + b * kTileBytes + row * 128;
+      *reinterpret_cast<uint16_t*>(rowp + (((kOnesCol >> 3) ^ (row & 7)) << 4) + (kOnesCol & 7) * 2) = 0x3F80;
+    }
     fence_proxy_async_smem();
   }
   if (threadIdx.x == 0) {
@@ -335,10 +355,10 @@ stem_wgrad_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
         const int buf = i & 1;
         mbar_wait(full(buf), (uint32_t)(i >> 1) & 1u);
         tc_fence_after();
-        const uint32_t a_addr = smem_base + kWOffDy + buf * 2 * kTileBytes;  // dy^T, MN-major, M = k (64 valid rows)
-        const uint32_t b_addr = smem_base + buf * kTileBytes;                // xcol, MN-major, N = 64 (r*8+s)
+        const uint32_t a_addr = smem_base + buf * kTileBytes;           // [dy^T ; xcol^T], MN-major: M rows 64..127 start kWOffX further
+        const uint32_t b_addr = smem_base + kWOffX + buf * kTileBytes;  // xcol, MN-major, N = 64 (r*8+s)
         for (int ks = 0; ks < ksteps; ++ks)
-          umma_bf16(tmem_base, umma_desc_sw128(a_addr + ks * 2048, kTileBytes, 1024), umma_desc_sw128(b_addr + ks * 2048, kTileBytes, 1024), idesc,
+          umma_bf16(tmem_base, umma_desc_sw128(a_addr + ks * 2048, kWOffX, 1024), umma_desc_sw128(b_addr + ks * 2048, kTileBytes, 1024), idesc,
                     (i | ks) != 0);
         umma_commit(freeb(buf));
       }
@@ -368,16 +388,16 @@ stem_wgrad_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
         const int b = tile / g.tiles_per_img;
         const int p0 = (tile - b * g.tiles_per_img) * g.rpt;
         mbar_arrive_expect_tx(full(buf), (uint32_t)g.valid * 128u);
-        tma_load_4d(&maps.io, full(buf), smem_base + kWOffDy + buf * 2 * kTileBytes, 0, 0, p0, b);
+        tma_load_4d(&maps.io, full(buf), smem_base + buf * kTileBytes, 0, 0, p0, b);
       }
-      if (live) gather_row(smem_base + buf * kTileBytes, row, reinterpret_cast<const uint32_t*>(smem_gen + kWOffPatch + buf * kPatchBytes), word0, g.PWW);
+      if (live) gather_row(smem_base + kWOffX + buf * kTileBytes, row, reinterpret_cast<const uint32_t*>(smem_gen + kWOffPatch + buf * kPatchBytes), word0, g.PWW);
       fence_proxy_async_smem();
       mbar_arrive(full(buf));
       if (more) patch_store(reg, mk, mask != nullptr, reinterpret_cast<uint16_t*>(smem_gen + kWOffPatch + ((i + 1) & 1) * kPatchBytes), g);
       named_bar_sync(1, 128);
     }
-    // dW[k][r][s] lives in accumulator row k, column r*8+s
-    float* out = ws + ((size_t)blockIdx.x * 64 + row) * 49;
+    // dW[k][r][s] lives in accumulator row k, column r*8+s; rows 64..127 (rows_out == 128) = Gram matrix / tap sums, same columns
+    float* out = ws + ((size_t)blockIdx.x * rows_out + row) * 49;
     if (n_my >= 1) {
       mbar_wait(all_done, 0);
       tc_fence_after();
@@ -386,7 +406,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
       tmem_ld_32x32(taddr, r0);
       tmem_ld_32x32(taddr + 32, r1);
       tmem_ld_wait();
-      if (row < 64) {
+      if (row < rows_out) {
 #pragma unroll
         for (int r = 0; r < 7; ++r)
 #pragma unroll
@@ -395,7 +415,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ StemMaps maps, const float* __restr
             out[r * 7 + s2] = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]);
           }
       }
-    } else if (row < 64) {
+    } else if (row < rows_out) {
       for (int t = 0; t < 49; ++t) out[t] = 0.f;
     }
   }
@@ -411,6 +431,49 @@ __global__ void stem_wgrad_reduce_kernel(const float* __restrict__ ws, int parts
   float a = 0.f;
   for (int p = 0; p < parts; ++p) a += ws[(size_t)p * (64 * 49) + i];
   dw[i] = a;
+}
+
+// Fixed-order fp64 sums of the per-CTA [128][49] partials (rows 0..63: sum g (x) xcol; rows 64..127: Gram matrix, row 127 = tap sums)
+__global__ void stem_wgrad_bn_sum_kernel(const float* __restrict__ ws, int parts, double* __restrict__ red) {
+  pdl_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128 * 49) return;
+  double a = 0.0;
+  for (int p = 0; p < parts; ++p) a += (double)ws[(size_t)p * (128 * 49) + i];
+  red[i] = a;
+}
+
+// dW = gamma*invstd*( G - mean(g)*S - mean(g*xhat)*invstd*( W X2 - mu*S ) ), plus dgamma / dbeta (what bn_bwd_apply's block 0 stores).
+// One CTA: the 49 x 49 Gram matrix and the 64 x 49 bf16-rounded weights (the operand the forward multiplied with) sit in shared memory.
+__global__ void __launch_bounds__(256)
+stem_wgrad_bn_combine_kernel(const double* __restrict__ red, const float* __restrict__ w, const double* __restrict__ bstat,
+                             const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma, double inv_count,
+                             float* __restrict__ dw, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_sync();
+  __shared__ double x2[49][49], S[49], k1[64], k2[64];
+  __shared__ float wb[64][49];
+  for (int i = threadIdx.x; i < 49 * 49; i += blockDim.x) {
+    const int tp = i / 49, t = i - tp * 49;
+    x2[tp][t] = red[(64 + (tp / 7) * 8 + tp % 7) * 49 + t];
+  }
+  for (int t = threadIdx.x; t < 49; t += blockDim.x) S[t] = red[(64 + kOnesCol) * 49 + t];
+  for (int i = threadIdx.x; i < 64 * 49; i += blockDim.x) wb[i / 49][i % 49] = bf16_lo(pack_bf16x2(w[i], 0.f));
+  for (int k = threadIdx.x; k < 64; k += blockDim.x) {
+    double sg, sgx;
+    stat_load(bstat, 64, k, sg, sgx);
+    k1[k] = sg * inv_count, k2[k] = sgx * inv_count;
+    if (dbeta) dbeta[k] = (float)sg;
+    if (dgamma) dgamma[k] = (float)sgx;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 49; i += blockDim.x) {
+    const int k = i / 49, t = i - k * 49;
+    double r = 0.0;
+#pragma unroll 7
+    for (int tp = 0; tp < 49; ++tp) r += (double)wb[k][tp] * x2[tp][t];
+    const double is = (double)invstd[k];
+    dw[i] = (float)((double)gamma[k] * is * (red[k * 49 + t] - k1[k] * S[t] - k2[k] * is * (r - (double)mean[k] * S[t])));
+  }
 }
 
 // several CTAs per SM: each has only 4 builder warps, latency is hidden across CTAs (fprop 66 KB smem -> 3, wgrad 106 KB -> 2)
@@ -458,7 +521,8 @@ int mml_stem_fprop(mml_ctx* ctx, const float* x, const float* mask, const float*
 int64_t mml_stem_wgrad_workspace(const mml_ctx* ctx, int B, int H, int W) {
   StemGeom g;
   if (!ctx || !stem_geom(B, H, W, &g)) return 0;
-  return (int64_t)stem_ctas(ctx, g.tiles, 2) * 64 * 49 * sizeof(float);
+  // [ctas][128][49] fp32 partials (the BatchNorm-folding variant stores all 128 accumulator rows) + [128][49] fp64 sums
+  return (int64_t)stem_ctas(ctx, g.tiles, 2) * 128 * 49 * sizeof(float) + 128 * 49 * sizeof(double);
 }
 
 int mml_stem_wgrad(mml_ctx* ctx, const float* x, const float* mask, const uint16_t* dy, float* dw, float* workspace,
@@ -479,8 +543,35 @@ int mml_stem_wgrad(mml_ctx* ctx, const float* x, const float* mask, const uint16
   }
   const int ctas = stem_ctas(ctx, g.tiles, 2);
   cudaStream_t st = (cudaStream_t)stream;
-  MML_LAUNCH(ctx, stem_wgrad_tc_kernel, ctas, kThreadsStem, kWBytes, st, maps, x, mask, workspace, g);
+  MML_LAUNCH(ctx, stem_wgrad_tc_kernel, ctas, kThreadsStem, kWBytes, st, maps, x, mask, workspace, g, 64);
   MML_LAUNCH(ctx, stem_wgrad_reduce_kernel, (64 * 49 + 255) / 256, 256, 0, st, workspace, ctas, dw);
+  return MML_OK;
+}
+
+int mml_stem_wgrad_bn(mml_ctx* ctx, const float* x, const float* mask, const uint16_t* g_bf16, const float* w, const double* bstat,
+                      const float* mean, const float* invstd, const float* gamma, float* dgamma, float* dbeta, float* dw, float* workspace,
+                      int64_t workspace_bytes, int B, int H, int W, void* stream) {
+  MML_REQUIRE(ctx, ctx && x && g_bf16 && w && bstat && mean && invstd && gamma && dw && workspace, "stem_wgrad_bn: null pointer");
+  MML_REQUIRE(ctx, B >= 1 && H >= 1 && W >= 1, "stem_wgrad_bn: bad dims");
+  MML_REQUIRE(ctx, workspace_bytes >= mml_stem_wgrad_workspace(ctx, B, H, W) && ((uintptr_t)workspace & 7) == 0, "stem_wgrad_bn: workspace too small / misaligned");
+  StemGeom g;
+  MML_REQUIRE(ctx, stem_geom(B, H, W, &g), "stem: output width %d not supported (max 128)", (W - 1) / 2 + 1);
+  StemMaps maps;
+  int rc = encode_px_map(ctx, &maps.io, g_bf16, g);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    MML_CHECK_CUDA(ctx, cudaFuncSetAttribute(stem_fprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFBytes));
+    MML_CHECK_CUDA(ctx, cudaFuncSetAttribute(stem_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWBytes));
+    configured = true;
+  }
+  const int ctas = stem_ctas(ctx, g.tiles, 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* red = reinterpret_cast<double*>(workspace + (size_t)ctas * 128 * 49);  // ctas * 128 * 49 floats: a multiple of 8 bytes
+  MML_LAUNCH(ctx, stem_wgrad_tc_kernel, ctas, kThreadsStem, kWBytes, st, maps, x, mask, workspace, g, 128);
+  MML_LAUNCH(ctx, stem_wgrad_bn_sum_kernel, (128 * 49 + 255) / 256, 256, 0, st, (const float*)workspace, ctas, red);
+  const double inv_count = 1.0 / ((double)B * g.P * g.Q);
+  MML_LAUNCH(ctx, stem_wgrad_bn_combine_kernel, 1, 256, 0, st, (const double*)red, w, bstat, mean, invstd, gamma, inv_count, dw, dgamma, dbeta);
   return MML_OK;
 }
 

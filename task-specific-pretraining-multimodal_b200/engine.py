@@ -516,9 +516,19 @@ class EncoderPlan:
             d_raw0 = self._act(B, P0, Q0, 64)
             ws = torch.zeros(max(ops.stem_wgrad_workspace(x) // 4, 4), device=dev)
 
+            import os as _os
+            fold = _os.environ.get("MML_STEM_FOLD", "1") == "1"
+
             def bwd_stem():
-                ops.stem_bn_pool_bwd(stem_grad_slots[0], stem_grad_slots[1], amax, raw0, bn0, bn0.bstat, bn0.dgamma, bn0.dbeta, d_raw0, B, P0, Q0, 64)
-                ops.stem_wgrad(x, mask, d_raw0, dw_stem, ws)
+                # The stem's dx has ONE consumer, its own weight gradient, and the stem output is linear in the input patches: pass 2 of the
+                # BatchNorm backward (read g + raw, write dx: 306 MB at B = 256 / 112x112) is folded into the wgrad algebraically
+                # (csrc/stem.cu); MML_STEM_FOLD=0 keeps the two-pass form for A/B runs
+                ops.stem_bn_pool_bwd(stem_grad_slots[0], stem_grad_slots[1], amax, raw0, bn0, bn0.bstat, bn0.dgamma, bn0.dbeta, d_raw0, B, P0, Q0, 64,
+                                     apply=not fold)
+                if fold:
+                    ops.stem_wgrad_bn(x, mask, d_raw0, w_stem, bn0, bn0.bstat, bn0.dgamma, bn0.dbeta, dw_stem, ws)
+                else:
+                    ops.stem_wgrad(x, mask, d_raw0, dw_stem, ws)
                 self.join_offload()
 
             Bk.append(bwd_stem)
@@ -644,8 +654,9 @@ class _StepPlan:
         # schedule variants (A/B-tested on B200): defaults are the measured best
         self.tune = {"adam_split": _os.environ.get("MML_ADAM_SPLIT", "1") == "1", "head_side": _os.environ.get("MML_HEAD_SIDE", "0") == "1",
                      "skip": _os.environ.get("MML_SKIP_ENCODER", ""), "side_prio": _os.environ.get("MML_SIDE_PRIO", "-1")}
-        # the audio encoder's persistent conv kernels leave a few SMs to the image encoder's stream (measured: 16 -> -1.2 % step time)
-        self.reserve_sms = int(_os.environ.get("MML_RESERVE_SMS", "16"))
+        # the audio encoder's persistent conv kernels leave a few SMs to the image encoder's stream (measured on the round-2 build: 0 -> 2.64 ms,
+        # 16 -> 2.57, 32 -> 2.53, 40 / 48 -> 2.53)
+        self.reserve_sms = int(_os.environ.get("MML_RESERVE_SMS", "32"))
         self.pdl_mode = _os.environ.get("MML_PDL_MODE", "none")  # none | image | audio | all
         ops.set_pdl(dev.index, self.pdl_mode != "none")
         if _os.environ.get("MML_WGRAD_STREAMS", "1") == "1":

@@ -156,6 +156,15 @@ def stem_wgrad(x, mask, dy, dw, workspace) -> None:
                                      _p(workspace, torch.float32), workspace.numel() * 4, B, H, W, _stream(x)), "stem_wgrad")
 
 
+def stem_wgrad_bn(x, mask, g, w, bn: "BNBuffers", bstat, dgamma, dbeta, dw, workspace) -> None:
+    """Stem weight gradient with the stem BatchNorm's backward pass 2 folded in: ``g`` = what ``stem_bn_pool_bwd(apply=False)`` left in dx."""
+    ctx = _ctx(x)
+    B, H, W = x.shape
+    ctx.check(ctx.lib.mml_stem_wgrad_bn(ctx.handle, _p(x, torch.float32), _p(mask, torch.float32), _p(g, BF16), _p(w, torch.float32),
+                                        _p(bstat, torch.float64), _p(bn.mean), _p(bn.invstd), _p(bn.gamma), _p(dgamma), _p(dbeta), _p(dw, torch.float32),
+                                        _p(workspace, torch.float32), workspace.numel() * 4, B, H, W, _stream(x)), "stem_wgrad_bn")
+
+
 # ---- conv ----------------------------------------------------------------------------------------------------
 def conv_fprop(g: ConvGeom, x, w_krsc, y, stats=None) -> None:
     """stats: ``bn_stats_buffer(K)`` accumulator of (sum, sum of squares) of y (zeroed by the caller) or None."""
@@ -282,11 +291,12 @@ def stem_bn_pool_fwd(x, bn: "BNBuffers", scale, shift, y, argmax, N, H, W, Cn, t
                                            _stream(x)), "stem_bn_pool_fwd")
 
 
-def stem_bn_pool_bwd(dy, dy2, argmax, x, bn: "BNBuffers", bstat, dgamma, dbeta, dx, N, H, W, Cn) -> None:
+def stem_bn_pool_bwd(dy, dy2, argmax, x, bn: "BNBuffers", bstat, dgamma, dbeta, dx, N, H, W, Cn, apply: bool = True) -> None:
+    """apply=False: stop after pass 1 (dx holds g, bstat the sums); ``stem_wgrad_bn`` then finishes the BatchNorm backward inside the wgrad."""
     ctx = _ctx(dy)
     ctx.check(ctx.lib.mml_stem_bn_pool_bwd(ctx.handle, _p(dy, BF16), _p(dy2), _p(argmax, torch.uint8), _p(x, BF16), _p(bn.mean), _p(bn.invstd),
                                            _p(bn.gamma), _p(bn.beta), _p(bstat, torch.float64), _p(dgamma), _p(dbeta), _p(dx, BF16), N, H, W, Cn,
-                                           _stream(dy)), "stem_bn_pool_bwd")
+                                           1 if apply else 0, _stream(dy)), "stem_bn_pool_bwd")
 
 
 # ---- ConvBlock encoders (MNISTAudio / MNISTImage, models/avmnist.py:34-185) -----------------------------------------------

@@ -72,6 +72,62 @@ def test_stem_fprop_wgrad(B, H, W):
     assert (dw - refw).abs().max().item() <= 1e-3 * refw.abs().max().item() + 1e-4  # fp32 sums over up to 10^6 pixels, other order
 
 
+@pytest.mark.parametrize("B,H,W", [(4, 112, 112), (5, 28, 28), (3, 32, 94), (2, 9, 13), (256, 28, 28), (64, 112, 112)])
+def test_stem_wgrad_with_batchnorm_backward_folded_in(B, H, W):
+    """conv1 -> bn1 (train) and their autograd (resnet.py:137-138): the stem's weight / gamma / beta gradients from g, the gradient w.r.t.
+    the BatchNorm OUTPUT, without ever forming dx -- against torch autograd through conv + batch_norm on the same bf16 operands, and against
+    the two-pass path (BatchNorm backward apply, then the plain weight gradient)."""
+    from mml_b200 import ops
+
+    x = torch.rand(B, H, W, device="cuda", generator=gen(11))
+    m = (torch.rand(B, device="cuda", generator=gen(12)) > 0.3).float()
+    m[0] = 1.0
+    w = torch.randn(64, 1, 7, 7, device="cuda", generator=gen(13)) * 0.2
+    gamma = torch.rand(64, device="cuda", generator=gen(14)) + 0.5
+    beta = torch.randn(64, device="cuda", generator=gen(15)) * 0.2
+    P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    rows = B * P * Q
+    raw = torch.empty(B, P, Q, 64, device="cuda", dtype=BF)
+    stats = ops.bn_stats_buffer(64, "cuda")
+    ops.stem_fprop(x, m, w.view(64, 49).contiguous(), raw, stats)
+    # batch statistics of the STORED (bf16) stem output, as the forward's BatchNorm kernels derive them
+    rd = raw.double().reshape(-1, 64)
+    mean = rd.mean(0)
+    var = (rd * rd).mean(0) - mean * mean
+    bn = ops.BNBuffers(stats, gamma, beta, torch.zeros(64, device="cuda"), torch.ones(64, device="cuda"), mean.float(), (1.0 / torch.sqrt(var + 1e-5)).float())
+    g = (torch.randn(B, P, Q, 64, device="cuda", generator=gen(16)) * (torch.rand(B, P, Q, 64, device="cuda", generator=gen(17)) > 0.4)).to(BF)  # ReLU-masked
+    gd = g.double().reshape(-1, 64)
+    xhat = (rd - mean) * bn.invstd.double()
+    bstat = ops.bn_stats_buffer(64, "cuda")
+    bstat[0] = torch.stack([gd.sum(0), (gd * xhat).sum(0)], 1)
+    # reference: autograd through conv (bf16 operands, fp32 accumulate) + batch_norm, seeded with g at the BatchNorm output
+    xm = (x * m.view(-1, 1, 1)).to(BF).float()
+    wr = w.to(BF).float().clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    out = F.batch_norm(F.conv2d(xm.unsqueeze(1), wr, stride=2, padding=3), None, None, gr, br, True, 0.1, 1e-5)
+    out.backward(g.float().permute(0, 3, 1, 2))
+    refw = wr.grad.view(64, 49)
+    ws = torch.empty(ops.stem_wgrad_workspace(x) // 4, device="cuda")
+    dw, dgamma, dbeta = torch.empty(64, 49, device="cuda"), torch.empty(64, device="cuda"), torch.empty(64, device="cuda")
+    ops.stem_wgrad_bn(x, m, g, w.view(64, 49).contiguous(), bn, bstat, dgamma, dbeta, dw, ws)
+    scale = refw.abs().max().item()
+    err = (dw - refw).abs().max().item()
+    # two-pass path on the same inputs: dx rounded to bf16, then the plain weight gradient
+    dx = torch.empty_like(raw)
+    dg2, db2 = torch.empty(64, device="cuda"), torch.empty(64, device="cuda")
+    ops.bn_bwd_apply(g, raw, bn.mean, bn.invstd, gamma, bstat, dg2, db2, dx, rows, 64)
+    dw2 = torch.empty(64, 49, device="cuda")
+    ops.stem_wgrad(x, m, dx, dw2, ws)
+    err2 = (dw2 - refw).abs().max().item()
+    print(f"stem wgrad+BN B={B} {H}x{W}: folded max err {err / scale:.2e}, two-pass {err2 / scale:.2e} (of max |dW| = {scale:.3g})")
+    # the reference keeps the conv output in fp32 while the kernels' BatchNorm sees the bf16-rounded one: 2^-9 relative noise on xhat
+    assert err <= 1e-2 * scale + 1e-4, (err, scale)
+    assert err <= 2.0 * err2 + 2e-3 * scale   # at least as close to autograd as the two-pass path it replaces
+    assert torch.equal(dgamma, dg2) and torch.equal(dbeta, db2)
+    assert (dgamma - gr.grad).abs().max().item() <= 2e-2 * gr.grad.abs().max().item() + 1e-2
+    assert (dbeta - br.grad).abs().max().item() <= 1e-3 * br.grad.abs().max().item() + 1e-2
+
+
 @pytest.mark.parametrize("rows,C", [(256 * 49, 64), (1000, 128), (98, 256), (4096, 512), (7, 512)])
 def test_bn_forward_backward(rows, C):
     from mml_b200 import ops

@@ -54,7 +54,26 @@ def stem_case(H, W):
     dy = torch.randn(B, P, Q, 64, device="cuda").to(BF)
     ws = torch.empty(ops.stem_wgrad_workspace(x) // 4, device="cuda")
     dw = torch.empty(64, 49, device="cuda")
-    return dict(fprop=lambda: ops.stem_fprop(x, m, w, y, st), wgrad=lambda: ops.stem_wgrad(x, m, dy, dw, ws))
+    # fused BN + ReLU + maxpool tail and its backward on the stem output
+    Cn = 64
+    P1, Q1 = (P - 1) // 2 + 1, (Q - 1) // 2 + 1
+    raw = torch.randn(B, P, Q, Cn, device="cuda").to(BF)
+    rd = raw.double().reshape(-1, Cn)
+    stb = ops.bn_stats_buffer(Cn, "cuda")
+    stb[0] = torch.stack([rd.sum(0), (rd * rd).sum(0)], 1)
+    f = lambda *sh: torch.zeros(*sh, device="cuda")
+    bn = ops.BNBuffers(stb, torch.ones(Cn, device="cuda"), f(Cn), f(Cn), torch.ones(Cn, device="cuda"), f(Cn), torch.ones(Cn, device="cuda"))
+    pool = torch.empty(B, P1, Q1, Cn, device="cuda", dtype=BF)
+    am = torch.empty(B, P1, Q1, Cn, device="cuda", dtype=torch.uint8)
+    dp1, dp2 = (torch.randn(B, P1, Q1, Cn, device="cuda").to(BF) for _ in range(2))
+    bstat = ops.bn_stats_buffer(Cn, "cuda")
+    dg, db = f(Cn), f(Cn)
+    dx = torch.empty_like(raw)
+    ws2 = torch.empty(ops.stem_wgrad_workspace(x) // 4, device="cuda")
+    return dict(fprop=lambda: ops.stem_fprop(x, m, w, y, st), wgrad=lambda: ops.stem_wgrad(x, m, dy, dw, ws),
+                pool_fwd=lambda: ops.stem_bn_pool_fwd(raw, bn, None, None, pool, am, B, P, Q, Cn, True),
+                pool_bwd=lambda: ops.stem_bn_pool_bwd(dp1, dp2, am, raw, bn, bstat, dg, db, dx, B, P, Q, Cn, apply=False),
+                wgrad_bn=lambda: ops.stem_wgrad_bn(x, m, dx, w, bn, bstat, dg, db, dw, ws2))
 
 
 TARGETS = {
