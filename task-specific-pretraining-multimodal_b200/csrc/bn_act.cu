@@ -473,15 +473,27 @@ stem_bn_pool_fwd_kernel(const uint16_t* __restrict__ x, BnTrain bn, const float*
       best[j] = -INFINITY;
       idx[j] = -1;
     }
+    // all nine window loads are issued before the first one is consumed (ncu: with the load inside the compare loop every window
+    // element cost a full memory round trip -- nine serialized long-scoreboard stalls per output vector, 80 us for 140 MB)
+    uint4 win[9];
+    uint32_t live = 0;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int h = 2 * p - 1 + r;
-      if (h < 0 || h >= H) continue;
 #pragma unroll
       for (int s2 = 0; s2 < 3; ++s2) {
         const int w = 2 * q - 1 + s2;
-        if (w < 0 || w >= W) continue;
-        const F8 v = unpack8(ldg16(x + (((long long)n * H + h) * W + w) * C + cg * 8));
+        const bool ok = (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W;
+        live |= (ok ? 1u : 0u) << (r * 3 + s2);
+        win[r * 3 + s2] = ok ? ldg16(x + (((long long)n * H + h) * W + w) * C + cg * 8) : make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        if (!((live >> (r * 3 + s2)) & 1u)) continue;
+        const F8 v = unpack8(win[r * 3 + s2]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           // ReLU and the bf16 rounding of the (never stored) activation are monotone, so they commute with the max: compare the
@@ -574,26 +586,36 @@ stem_bn_pool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restr
     const int n = row / HB, a = row - n * HB;
    for (int b = bs; b < WB; b += nb) {
     // gradients and argmax bytes of the (up to) four pooling windows p in {a, a+1}, q in {b, b+1} that cover this block
-    float gw[2][2][4];
+    // Every global load of this block -- argmax bytes and gradient(s) of its four windows, the four raw values -- is issued before any
+    // of them is consumed (ncu: loaded at their first use they cost five to eight serialized memory round trips per block, 141 us for
+    // 240 MB; the loads are predicated, so out-of-range windows cost nothing).
     uint32_t am[2][2];
+    uint2 g1[2][2], g2[2][2], xblk[2][2];
 #pragma unroll
     for (int dp = 0; dp < 2; ++dp)
 #pragma unroll
       for (int dq = 0; dq < 2; ++dq) {
         const int p = a + dp, q = b + dq;
-        am[dp][dq] = 0xFFFFFFFFu;  // matches no window position
+        const bool ok = p < P && q < Q;
+        const long long o = (((long long)n * P + p) * Q + q) * C + cg * 4;
+        am[dp][dq] = ok ? __ldg(reinterpret_cast<const uint32_t*>(amax + o)) : 0xFFFFFFFFu;  // 0xFF matches no window position
+        g1[dp][dq] = ok ? __ldg(reinterpret_cast<const uint2*>(dy + o)) : make_uint2(0, 0);
+        g2[dp][dq] = (ok && dy2 != nullptr) ? __ldg(reinterpret_cast<const uint2*>(dy2 + o)) : make_uint2(0, 0);  // second gradient path
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) gw[dp][dq][j] = 0.f;
-        if (p < P && q < Q) {
-          const long long o = (((long long)n * P + p) * Q + q) * C + cg * 4;
-          am[dp][dq] = __ldg(reinterpret_cast<const uint32_t*>(amax + o));
-          const uint2 g1 = __ldg(reinterpret_cast<const uint2*>(dy + o));
-          gw[dp][dq][0] = bf16_lo(g1.x), gw[dp][dq][1] = bf16_hi(g1.x), gw[dp][dq][2] = bf16_lo(g1.y), gw[dp][dq][3] = bf16_hi(g1.y);
-          if (dy2 != nullptr) {  // gradient arriving over two paths (conv branch + identity skip)
-            const uint2 g2 = __ldg(reinterpret_cast<const uint2*>(dy2 + o));
-            gw[dp][dq][0] += bf16_lo(g2.x), gw[dp][dq][1] += bf16_hi(g2.x), gw[dp][dq][2] += bf16_lo(g2.y), gw[dp][dq][3] += bf16_hi(g2.y);
-          }
-        }
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int h = 2 * a + u, w = 2 * b + v;
+        xblk[u][v] = (h < H && w < W) ? __ldg(reinterpret_cast<const uint2*>(x + (((long long)n * H + h) * W + w) * C + cg * 4)) : make_uint2(0, 0);
+      }
+    float gw[2][2][4];
+#pragma unroll
+    for (int dp = 0; dp < 2; ++dp)
+#pragma unroll
+      for (int dq = 0; dq < 2; ++dq) {
+        gw[dp][dq][0] = bf16_lo(g1[dp][dq].x) + bf16_lo(g2[dp][dq].x), gw[dp][dq][1] = bf16_hi(g1[dp][dq].x) + bf16_hi(g2[dp][dq].x);
+        gw[dp][dq][2] = bf16_lo(g1[dp][dq].y) + bf16_lo(g2[dp][dq].y), gw[dp][dq][3] = bf16_hi(g1[dp][dq].y) + bf16_hi(g2[dp][dq].y);
       }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -604,7 +626,7 @@ stem_bn_pool_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restr
         const int w = 2 * b + v;
         if (w >= W) continue;
         const long long o = (((long long)n * H + h) * W + w) * C + cg * 4;
-        const uint2 xu = __ldg(reinterpret_cast<const uint2*>(x + o));
+        const uint2 xu = xblk[u][v];
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         // window (p, q) covers rows 2p-1..2p+1: block row u (h = 2a+u) is window row r = u + 1 - 2*dp (valid: 0..2)
 #pragma unroll

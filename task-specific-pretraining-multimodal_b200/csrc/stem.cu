@@ -433,46 +433,67 @@ __global__ void stem_wgrad_reduce_kernel(const float* __restrict__ ws, int parts
   dw[i] = a;
 }
 
-// Fixed-order fp64 sums of the per-CTA [128][49] partials (rows 0..63: sum g (x) xcol; rows 64..127: Gram matrix, row 127 = tap sums)
-__global__ void stem_wgrad_bn_sum_kernel(const float* __restrict__ ws, int parts, double* __restrict__ red) {
+// Fixed-order fp64 sums of the per-CTA [128][49] partials (rows 0..63: sum g (x) xcol; rows 64..127: Gram matrix, row 127 = tap sums).
+// Eight lanes per output: lane l sums partials l, l+8, ... (four independent loads in flight), then a fixed shuffle tree -- the order
+// of the additions never depends on timing.  (One thread per output walking ~300 partials took 17 us of exposed latency at the very
+// end of the step.)
+__global__ void __launch_bounds__(256) stem_wgrad_bn_sum_kernel(const float* __restrict__ ws, int parts, double* __restrict__ red) {
   pdl_sync();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 128 * 49) return;
-  double a = 0.0;
-  for (int p = 0; p < parts; ++p) a += (double)ws[(size_t)p * (128 * 49) + i];
-  red[i] = a;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = t >> 3, l = t & 7;
+  const bool live = i < 128 * 49;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (live) {
+    const float* src = ws + i;
+    int p = l;
+    for (; p + 24 < parts; p += 32) {
+      const float v0 = __ldcg(src + (size_t)p * (128 * 49)), v1 = __ldcg(src + (size_t)(p + 8) * (128 * 49));
+      const float v2 = __ldcg(src + (size_t)(p + 16) * (128 * 49)), v3 = __ldcg(src + (size_t)(p + 24) * (128 * 49));
+      a0 += (double)v0, a1 += (double)v1, a2 += (double)v2, a3 += (double)v3;
+    }
+    for (; p < parts; p += 8) a0 += (double)__ldcg(src + (size_t)p * (128 * 49));
+  }
+  double a = (a0 + a1) + (a2 + a3);
+  a += __shfl_xor_sync(0xffffffffu, a, 1);
+  a += __shfl_xor_sync(0xffffffffu, a, 2);
+  a += __shfl_xor_sync(0xffffffffu, a, 4);
+  if (live && l == 0) red[i] = a;
 }
 
 // dW = gamma*invstd*( G - mean(g)*S - mean(g*xhat)*invstd*( W X2 - mu*S ) ), plus dgamma / dbeta (what bn_bwd_apply's block 0 stores).
-// One CTA: the 49 x 49 Gram matrix and the 64 x 49 bf16-rounded weights (the operand the forward multiplied with) sit in shared memory.
+// One output per thread; every CTA stages the 49 x 49 Gram matrix and the tap sums in shared memory, and everything an output needs
+// from global memory is requested before the first use (two round trips per CTA in total).
 __global__ void __launch_bounds__(256)
 stem_wgrad_bn_combine_kernel(const double* __restrict__ red, const float* __restrict__ w, const double* __restrict__ bstat,
                              const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma, double inv_count,
                              float* __restrict__ dw, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   pdl_sync();
-  __shared__ double x2[49][49], S[49], k1[64], k2[64];
-  __shared__ float wb[64][49];
-  for (int i = threadIdx.x; i < 49 * 49; i += blockDim.x) {
-    const int tp = i / 49, t = i - tp * 49;
-    x2[tp][t] = red[(64 + (tp / 7) * 8 + tp % 7) * 49 + t];
+  __shared__ double x2[49][49], S[49];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < 64 * 49;
+  const int k = live ? i / 49 : 0, t = live ? i - k * 49 : 0;
+  for (int j = threadIdx.x; j < 49 * 49; j += blockDim.x) {
+    const int tp = j / 49, tt = j - tp * 49;
+    x2[tp][tt] = __ldcg(red + (64 + (tp / 7) * 8 + tp % 7) * 49 + tt);
   }
-  for (int t = threadIdx.x; t < 49; t += blockDim.x) S[t] = red[(64 + kOnesCol) * 49 + t];
-  for (int i = threadIdx.x; i < 64 * 49; i += blockDim.x) wb[i / 49][i % 49] = bf16_lo(pack_bf16x2(w[i], 0.f));
-  for (int k = threadIdx.x; k < 64; k += blockDim.x) {
-    double sg, sgx;
-    stat_load(bstat, 64, k, sg, sgx);
-    k1[k] = sg * inv_count, k2[k] = sgx * inv_count;
+  for (int tt = threadIdx.x; tt < 49; tt += blockDim.x) S[tt] = __ldcg(red + (64 + kOnesCol) * 49 + tt);
+  double sg, sgx;
+  stat_load(bstat, 64, k, sg, sgx);
+  const double G = __ldcg(red + k * 49 + t);
+  const double is = (double)invstd[k], mu = (double)mean[k], ga = (double)gamma[k];
+  float wk[49];
+#pragma unroll
+  for (int tp = 0; tp < 49; ++tp) wk[tp] = __ldg(w + k * 49 + tp);
+  __syncthreads();
+  if (!live) return;
+  double r = 0.0;
+#pragma unroll
+  for (int tp = 0; tp < 49; ++tp) r += (double)bf16_lo(pack_bf16x2(wk[tp], 0.f)) * x2[tp][t];  // the bf16 operand the forward multiplied with
+  const double k1 = sg * inv_count, k2 = sgx * inv_count;
+  dw[i] = (float)(ga * is * (G - k1 * S[t] - k2 * is * (r - mu * S[t])));
+  if (t == 0) {
     if (dbeta) dbeta[k] = (float)sg;
     if (dgamma) dgamma[k] = (float)sgx;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 64 * 49; i += blockDim.x) {
-    const int k = i / 49, t = i - k * 49;
-    double r = 0.0;
-#pragma unroll 7
-    for (int tp = 0; tp < 49; ++tp) r += (double)wb[k][tp] * x2[tp][t];
-    const double is = (double)invstd[k];
-    dw[i] = (float)((double)gamma[k] * is * (red[k * 49 + t] - k1[k] * S[t] - k2[k] * is * (r - (double)mean[k] * S[t])));
   }
 }
 
@@ -569,9 +590,9 @@ int mml_stem_wgrad_bn(mml_ctx* ctx, const float* x, const float* mask, const uin
   cudaStream_t st = (cudaStream_t)stream;
   double* red = reinterpret_cast<double*>(workspace + (size_t)ctas * 128 * 49);  // ctas * 128 * 49 floats: a multiple of 8 bytes
   MML_LAUNCH(ctx, stem_wgrad_tc_kernel, ctas, kThreadsStem, kWBytes, st, maps, x, mask, workspace, g, 128);
-  MML_LAUNCH(ctx, stem_wgrad_bn_sum_kernel, (128 * 49 + 255) / 256, 256, 0, st, (const float*)workspace, ctas, red);
+  MML_LAUNCH(ctx, stem_wgrad_bn_sum_kernel, (128 * 49 * 8 + 255) / 256, 256, 0, st, (const float*)workspace, ctas, red);
   const double inv_count = 1.0 / ((double)B * g.P * g.Q);
-  MML_LAUNCH(ctx, stem_wgrad_bn_combine_kernel, 1, 256, 0, st, (const double*)red, w, bstat, mean, invstd, gamma, inv_count, dw, dgamma, dbeta);
+  MML_LAUNCH(ctx, stem_wgrad_bn_combine_kernel, (64 * 49 + 255) / 256, 256, 0, st, (const double*)red, w, bstat, mean, invstd, gamma, inv_count, dw, dgamma, dbeta);
   return MML_OK;
 }
 
