@@ -81,7 +81,7 @@ def lstm_last(st: Dict[str, Tensor], prefix: str, x: Tensor) -> Tensor:
     return h
 
 
-def textcnn(st: Dict[str, Tensor], x: Tensor, keep: Optional[Tensor], p: float, emulate_bf16: bool = False) -> Tensor:
+def textcnn(st: Dict[str, Tensor], x: Tensor, keep: Optional[Tensor], p: float, emulate_bf16: bool = False, prefix: str = "netT") -> Tensor:
     """``emulate_bf16`` (debugging aid for the CUDA path, not part of the reference): round where the B200 path stores bf16 -- the
     text input, the convolution weights, the convolution output (bias is added afterwards in fp32) and its gradient."""
     B, T, D = x.shape
@@ -89,12 +89,12 @@ def textcnn(st: Dict[str, Tensor], x: Tensor, keep: Optional[Tensor], p: float, 
     frame = _q(x, q).view(B, 1, T, D)
     outs = []
     for i in range(len(KERNEL_HEIGHTS)):
-        conv = _qg(_q(F.conv2d(frame, _qw(st[f"netT.conv{i + 1}.weight"], q), None), q), q) + st[f"netT.conv{i + 1}.bias"].view(1, -1, 1, 1)
+        conv = _qg(_q(F.conv2d(frame, _qw(st[f"{prefix}.conv{i + 1}.weight"], q), None), q), q) + st[f"{prefix}.conv{i + 1}.bias"].view(1, -1, 1, 1)
         outs.append(F.relu(conv.squeeze(3)).max(dim=2).values)
     allo = torch.cat(outs, 1)
     if keep is not None:
         allo = allo * keep / (1.0 - p)
-    return F.relu(F.linear(allo, st["netT.embd.0.weight"], st["netT.embd.0.bias"]))
+    return F.relu(F.linear(allo, st[f"{prefix}.embd.0.weight"], st[f"{prefix}.embd.0.bias"]))
 
 
 def utt_forward(st: Dict[str, Tensor], A: Tensor, V: Tensor, T: Tensor, keeps: Optional[Sequence[Tensor]] = None, p: float = 0.5,
@@ -156,3 +156,53 @@ def synthetic_batch(batch: int, seed: int, seq_len: int = 50, audio_dim: int = 5
     return {"audio": A, "video": V, "text": T, "lengths": lengths, "pattern_name": pat, "audio_mask": ma, "text_mask": mt, "video_mask": mv,
             "labels": y, "keeps": keeps, "audio_masked": apply_missing_mask(A, ma), "video_masked": apply_missing_mask(V, mv),
             "text_masked": apply_missing_mask(T, mt)}
+
+
+# ----------------------------------------------------------------------------------------------
+# monomodal pre-training of ONE MOSI encoder (train_monomodal.py:64-92,224-260 with configs/mosi/mono/*.yaml):
+#   MonomodalEncoder(LSTMEncoder(5 | 20, 64, "last"), 64, 3)  or  MonomodalEncoder(TextCNN(768, 64, dropout .5), 64, 3),
+#   cross_entropy, Adam(lr 1e-3, weight_decay 1e-3), no gradient clip.  CUDA path: mml_b200/mono.py (_SeqMonoPlan).
+# ----------------------------------------------------------------------------------------------
+def init_mono_seq_state(kind: str, input_size: int, hidden: int = 64, classes: int = 3, channels: int = 128) -> "OrderedDict[str, Tensor]":
+    """Same RNG draws, in the same order, as ``MonomodalEncoder(encoder, hidden, classes)`` with encoder = LSTMEncoder(input_size, hidden)
+    (kind "lstm") or TextCNN(input_size, hidden, out_channels=channels) (kind "textcnn")."""
+    st: "OrderedDict[str, Tensor]" = OrderedDict()
+    if kind == "lstm":
+        _lstm_params(st, "encoder", input_size, hidden)
+    elif kind == "textcnn":
+        for i, k in enumerate(KERNEL_HEIGHTS):
+            st[f"encoder.conv{i + 1}.weight"], st[f"encoder.conv{i + 1}.bias"] = _conv_params(channels, 1, k, input_size)
+        st["encoder.embd.0.weight"], st["encoder.embd.0.bias"] = _linear_params(hidden, len(KERNEL_HEIGHTS) * channels)
+    else:
+        raise ValueError(kind)
+    st["classifier.weight"], st["classifier.bias"] = _linear_params(classes, hidden)
+    return st
+
+
+def mono_seq_forward(st: Dict[str, Tensor], x: Tensor, keep: Optional[Tensor] = None, p: float = 0.5, emulate_bf16: bool = False) -> Tensor:
+    if "encoder.rnn.weight_ih_l0" in st:
+        emb = lstm_last(st, "encoder", x)
+    else:
+        emb = textcnn(st, x, keep, p, emulate_bf16, prefix="encoder")
+    return F.linear(emb.reshape(emb.shape[0], -1), st["classifier.weight"], st["classifier.bias"])
+
+
+def mono_seq_train_step(st: "OrderedDict[str, Tensor]", opt_state: Dict, x: Tensor, labels: Tensor, keep: Optional[Tensor] = None, p: float = 0.5,
+                        lr: float = 1e-3, weight_decay: float = 1e-3, apply_update: bool = True, emulate_bf16: bool = False) -> Dict[str, object]:
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in st.items()}
+    logits = mono_seq_forward(leaves, x, keep, p, emulate_bf16)
+    loss = F.cross_entropy(logits, labels) * 1.0
+    gl = torch.autograd.grad(loss, list(leaves.values()))
+    grads = dict(zip(leaves.keys(), gl))
+    if apply_update:
+        with torch.no_grad():
+            adam_step(st, grads, opt_state, lr=lr, weight_decay=weight_decay)
+    preds = torch.argmax(logits.detach(), dim=1)  # train_monomodal.py:239
+    return {"loss": float(loss.item()), "logits": logits.detach(), "predictions": preds, "grads": grads,
+            "accuracy": float((preds == labels).float().mean())}
+
+
+@torch.no_grad()
+def mono_seq_validation_step(st: Dict[str, Tensor], x: Tensor, labels: Tensor) -> Dict[str, object]:
+    logits = mono_seq_forward(st, x, None)
+    return {"loss": float(F.cross_entropy(logits, labels).item()), "logits": logits, "predictions": logits.argmax(-1)}

@@ -11,7 +11,9 @@ Two encoder families are built: the ResNet encoders of ``mml_b200.resnet`` (AVMN
 ``MMIMDbModalityEncoder`` of ``mml_b200.mmimdb`` (``configs/mmimdb/mono/*.yaml``: BatchNorm1d -> Linear on a feature vector,
 multi-hot genre targets, ``bce_with_logits``, predictions ``sigmoid > 0.5``, train_monomodal.py:243) -- the latter reuses the
 MMIMDb step's kernels (fused BatchNorm1d, the tcgen05 GEMM with the bias as an extra input column, the BCE head).  Anything else
-(the MOSI LSTM / TextCNN encoders) raises.  File-path batches (the reference loads ``.pt`` paths inside ``train_step``,
+raises.  The MOSI encoders of ``mml_b200.utt_fusion`` (``configs/mosi/mono/*.yaml``: ``LSTMEncoder`` on [B, T, 5 | 20] sequences,
+``TextCNN`` on [B, T, 768]; cross entropy over 3 classes, no gradient clip) run on the UttFusion step's kernels (LSTM forward / BPTT,
+tcgen05 convolutions over time, fused ReLU + max-over-time + dropout, dense layers).  File-path batches (the reference loads ``.pt`` paths inside ``train_step``,
 :138-160) are host I/O and are not accepted -- pass tensors.
 """
 from __future__ import annotations
@@ -202,6 +204,145 @@ class _VecMonoPlan:
     train_step = _MonoPlan.train_step  # same eager-twice-then-graph protocol
 
 
+class _SeqMonoPlan:
+    """MonomodalEncoder(LSTMEncoder | TextCNN, 64, NC) for a fixed (batch, sequence length): encoder -> Linear -> cross entropy.
+
+    The schedule is the matching slice of the UttFusion step (utt_fusion._UttPlan): ``mml_lstm_fwd / mml_lstm_bwd`` with h_T as the
+    embedding, or three ``Conv2d(1, C, (k, 768))`` on the tcgen05 conv path + fused ReLU / max-over-time / dropout + the embd Linear."""
+
+    def __init__(self, eng: "SeqMonoEngine", B: int, T: int):
+        self.eng, self.B, self.T = eng, B, T
+        fs, dev, enc = eng.fs, eng.device, eng.model.encoder
+        params = dict(eng.model.named_parameters())
+
+        def par(flat, name):
+            return fs.flat_slice(flat, name).view(params[name].shape)
+
+        f32 = lambda *sh: torch.zeros(*sh, device=dev)
+        self.kind = eng.kind
+        self.D = enc.input_size
+        E = enc.hidden_size
+        self.E = E
+        self.NC = params["classifier.weight"].shape[0]
+        if params["classifier.weight"].shape[1] != E:
+            raise ValueError(f"classifier expects {params['classifier.weight'].shape[1]} features but the encoder produces {E}")
+        self.x = f32(B, T, self.D)
+        self.labels = torch.zeros(B, device=dev, dtype=torch.int64)
+        self.emb, self.demb = f32(B, E), f32(B, E)
+        self.logits, self.dlogits = f32(B, self.NC), f32(B, self.NC)
+        self.row_loss, self.loss = f32(B), f32(1)
+        self.pred = torch.zeros(B, device=dev, dtype=torch.int32)
+        self.h_loss = torch.zeros(1).pin_memory()
+        self.h_pred = torch.zeros(B, dtype=torch.int32).pin_memory()
+        self.cls = dict(w=par(fs.P, "classifier.weight"), b=par(fs.P, "classifier.bias"), dw=par(fs.G, "classifier.weight"), db=par(fs.G, "classifier.bias"))
+        if self.kind == "lstm":
+            names = [f"encoder.rnn.{n}" for n in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")]
+            self.w, self.dw = [par(fs.P, n) for n in names], [par(fs.G, n) for n in names]
+            self.gates, self.cs, self.hs = f32(B, T, 4 * E), f32(B, T, E), f32(B, T, E)
+            self.p_drop = 0.0
+        else:
+            C_ = enc.out_channels
+            self.C = C_
+            self.x16 = torch.zeros(B, T, self.D, device=dev, dtype=BF16)  # bf16 NHWC [B][T][1][768]
+            self.convs = []
+            self.wgrad_ws = ops.WgradScratch(dev)
+            for i, k in enumerate(enc.kernel_heights):
+                name = f"encoder.conv{i + 1}"
+                P_ = T - k + 1
+                if P_ < 1:
+                    raise ValueError(f"sequence length {T} shorter than the TextCNN kernel height {k}")
+                self.convs.append(dict(geom=ops.make_geom(B, T, 1, self.D, C_, k, 1, 1, 0), w16=fs.flat_slice(fs.Wb, name + ".weight").view(C_, k, 1, self.D),
+                                       dw=fs.flat_slice(fs.G, name + ".weight").view(C_, k, 1, self.D), bias=par(fs.P, name + ".bias"),
+                                       dbias=par(fs.G, name + ".bias"), out=torch.zeros(B, P_, C_, device=dev, dtype=BF16),
+                                       dout=torch.zeros(B, P_, C_, device=dev, dtype=BF16)))
+            NP = len(self.convs) * C_
+            self.pooled, self.dpooled = f32(B, NP), f32(B, NP)
+            self.arg = torch.zeros(B, NP, device=dev, dtype=torch.int32)
+            self.keep = torch.ones(B, NP, device=dev, dtype=torch.uint8)
+            self.p_drop = float(enc.dropout.p)
+            self.embd = dict(w=par(fs.P, "encoder.embd.0.weight"), b=par(fs.P, "encoder.embd.0.bias"), dw=par(fs.G, "encoder.embd.0.weight"),
+                             db=par(fs.G, "encoder.embd.0.bias"))
+        self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
+        self.eager_steps = 0
+        self.launches_per_step = 0
+
+    def run_forward(self, training: bool, with_loss: bool, with_grad: bool = False) -> None:
+        B, E = self.B, self.E
+        if self.kind == "lstm":
+            ops.lstm_fwd(self.x, *self.w, self.gates, self.cs, self.hs, self.emb)
+        else:
+            drop = training and self.p_drop > 0
+            ops.cast_f32_bf16(self.x, self.x16)
+            for i, cv in enumerate(self.convs):
+                ops.conv_fprop(cv["geom"], self.x16, cv["w16"], cv["out"], None)
+                ops.relumax_fwd(cv["out"], cv["bias"], self.keep if drop else None, 1.0 / (1.0 - self.p_drop) if drop else 1.0, self.pooled, self.arg, i * self.C)
+            ops.dense_fwd(self.pooled, self.pooled.shape[1], self.embd["w"], self.embd["b"], None, 1.0, True, self.emb, E, B)
+        ops.dense_fwd(self.emb, E, self.cls["w"], self.cls["b"], None, 1.0, False, self.logits, self.NC, B)
+        ops.softmax_ce(self.logits, self.labels if with_loss else None, self.dlogits if with_grad else None, self.row_loss if with_loss else None,
+                       self.loss if with_loss else None, self.pred, 1.0)
+
+    def run_train(self, own_dropout: bool = True) -> None:
+        eng, fs, B, E = self.eng, self.eng.fs, self.B, self.E
+        fs.G.zero_()  # the BPTT kernel accumulates its weight gradients with atomics
+        if self.p_drop > 0 and own_dropout:
+            ops.dropout_mask(self.keep, self.p_drop, eng.seed, fs.step)
+        self.run_forward(True, True, True)
+        ops.dense_bwd(self.dlogits, self.logits, self.NC, None, 1.0, False, self.emb, E, self.cls["w"], self.demb, E, self.cls["dw"], self.cls["db"], B)
+        if self.kind == "lstm":
+            ops.lstm_bwd(self.x, self.w[1], self.gates, self.cs, self.hs, self.demb, *self.dw)
+        else:
+            drop = self.p_drop > 0
+            e = self.embd
+            ops.dense_bwd(self.demb, self.emb, E, None, 1.0, True, self.pooled, self.pooled.shape[1], e["w"], self.dpooled, self.dpooled.shape[1], e["dw"], e["db"], B)
+            for i, cv in enumerate(self.convs):
+                ops.relumax_bwd(self.dpooled, self.arg, self.keep if drop else None, 1.0 / (1.0 - self.p_drop) if drop else 1.0, cv["dout"], cv["dbias"], i * self.C)
+                ops.conv_wgrad(cv["geom"], self.x16, cv["dout"], cv["dw"], self.wgrad_ws)
+        if eng.allreduce is not None:
+            eng.allreduce(self, 0, update=lambda: fs.adam(0, fs.total, True))
+        else:
+            fs.adam(0, fs.total, True)
+
+    def train_step(self, given_dropout: bool = False) -> None:
+        eng = self.eng
+        key = "train_given" if given_dropout else "train"
+        if getattr(self, "_range_version", None) != eng.fs.range_version:
+            self.graphs.clear()
+            self._range_version = eng.fs.range_version
+        if not eng.use_graphs:
+            return self.run_train(not given_dropout)
+        g = self.graphs.get(key)
+        if g is None:
+            if self.eager_steps < 2:
+                before = ops.launch_count(eng.device.index)
+                self.run_train(not given_dropout)
+                self.launches_per_step = ops.launch_count(eng.device.index) - before
+                self.eager_steps += 1
+                return
+            torch.cuda.synchronize(eng.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.run_train(not given_dropout)
+            self.graphs[key] = g
+        g.replay()
+
+
+class SeqMonoEngine:
+    def __init__(self, model: nn.Module, device: torch.device, kind: str):
+        self.model, self.device, self.kind = model, device, kind
+        self.seed = ops.engine_seed(int(getattr(model, "_mml_client_id", 0)))
+        self.fs = FlatState(model, device)
+        self.plans: Dict[Tuple[int, int], _SeqMonoPlan] = {}
+        self.world = 1
+        self.allreduce = None
+        self.use_graphs = True
+
+    def plan_for(self, B: int, T: int) -> _SeqMonoPlan:
+        plan = self.plans.get((B, T))
+        if plan is None:
+            plan = self.plans[(B, T)] = _SeqMonoPlan(self, B, T)
+        return plan
+
+
 class VecMonoEngine:
     def __init__(self, model: nn.Module, device: torch.device):
         self.model, self.device = model, device
@@ -223,11 +364,13 @@ class MonomodalEncoder(nn.Module):
         super().__init__()
         from .mmimdb import MMIMDbModalityEncoder
         from .resnet import ResNetEncoder
+        from .utt_fusion import LSTMEncoder, TextCNN
 
-        if not isinstance(encoder, (ResNetEncoder, MMIMDbModalityEncoder)):
-            raise NotImplementedError("mml_b200.MonomodalEncoder wraps the ResNet encoders of mml_b200.resnet and the MMIMDbModalityEncoder "
-                                      f"of mml_b200.mmimdb; got {type(encoder).__name__}")
+        if not isinstance(encoder, (ResNetEncoder, MMIMDbModalityEncoder, LSTMEncoder, TextCNN)):
+            raise NotImplementedError("mml_b200.MonomodalEncoder wraps the ResNet encoders of mml_b200.resnet, the MMIMDbModalityEncoder of "
+                                      f"mml_b200.mmimdb and the LSTMEncoder / TextCNN of mml_b200.utt_fusion; got {type(encoder).__name__}")
         self._vector = isinstance(encoder, MMIMDbModalityEncoder)  # feature-vector encoder, multi-label targets
+        self._seq = "lstm" if isinstance(encoder, LSTMEncoder) else ("textcnn" if isinstance(encoder, TextCNN) else None)  # [B, T, D] sequences
         self.encoder = encoder
         self.classifier = nn.Linear(output_dim, num_classes)
         self._engine: Optional[MonoEngine] = None
@@ -253,7 +396,9 @@ class MonomodalEncoder(nn.Module):
         eng = self._engine
         if eng is None or eng.device != device:
             import weakref
-            if self._vector:
+            if self._seq is not None:
+                eng = self._engine = SeqMonoEngine(self, device, self._seq)
+            elif self._vector:
                 eng = self._engine = VecMonoEngine(self, device)
                 self.encoder._mml_owner = (weakref.ref(self), "mono")  # encoder(x) outside the step -> self.encode
             else:
@@ -330,6 +475,24 @@ class MonomodalEncoder(nn.Module):
             _copy_in(plan.labels, labels.to(torch.float32))
         return plan
 
+    def _stage_seq(self, eng: "SeqMonoEngine", x: torch.Tensor, labels: Optional[torch.Tensor]) -> _SeqMonoPlan:
+        if x.dim() != 3:
+            raise ValueError(f"expected a [B, T, D] sequence batch, got {tuple(x.shape)}")
+        plan = eng.plan_for(x.shape[0], x.shape[1])
+        if x.shape[2] != plan.D:
+            raise ValueError(f"expected {plan.D} features per step, got {x.shape[2]}")
+        _copy_in(plan.x, x)
+        if labels is not None:
+            labels = labels.reshape(-1)
+            ops.check_class_labels(labels, plan.NC)
+            _copy_in(plan.labels, labels)
+        return plan
+
+    def _plan(self, eng, x, labels):
+        if self._seq is not None:
+            return self._stage_seq(eng, x, labels)
+        return self._stage_vec(eng, x, labels) if self._vector else self._stage(eng, x, labels)
+
     def encode(self, which: str, x: torch.Tensor) -> torch.Tensor:
         """``self.encoder(x)`` outside the step (vector encoders): BatchNorm1d -> Linear, fp32 [B, E]."""
         eng = self._get_engine(x.device if x.is_cuda else next(self.parameters()).device)
@@ -341,8 +504,8 @@ class MonomodalEncoder(nn.Module):
         if isinstance(x, list):
             x = torch.stack(x)
         eng = self._get_engine(x.device if x.is_cuda else next(self.parameters()).device)
-        if self._vector:
-            plan = self._stage_vec(eng, x, None)
+        if self._vector or self._seq is not None:
+            plan = self._plan(eng, x, None)
             plan.run_forward(self.training, with_loss=False)
             return plan.logits.clone()
         plan = self._stage(eng, x, None)
@@ -359,8 +522,13 @@ class MonomodalEncoder(nn.Module):
         fs = eng.fs
         fs.adopt_optimizer(optimizer)
         fs.sync_hyper(optimizer, 1.0 / self.world_size)
-        plan = self._stage_vec(eng, x, labels) if self._vector else self._stage(eng, x, labels)
-        plan.train_step()
+        plan = self._plan(eng, x, labels)
+        given = kwargs.get("dropout_mask") if self._seq == "textcnn" else None
+        if given is not None:  # tests: replay a given TextCNN dropout mask
+            plan.keep.copy_(torch.as_tensor(given).reshape(plan.keep.shape).to(torch.uint8), non_blocking=True)
+            plan.train_step(given_dropout=True)
+        else:
+            plan.train_step()
         fs._host_step += 1
         return self._finish(eng, plan, key, labels, metric_recorder)
 
@@ -371,7 +539,7 @@ class MonomodalEncoder(nn.Module):
         self._check_loss(loss_functions)
         key, x, labels = self._unpack(batch, config)
         self._set_mode(False)
-        plan = self._stage_vec(eng, x, labels) if self._vector else self._stage(eng, x, labels)
+        plan = self._plan(eng, x, labels)
         plan.run_forward(False, with_loss=True)
         return self._finish(eng, plan, key, labels, metric_recorder)
 

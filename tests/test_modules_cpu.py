@@ -221,6 +221,14 @@ def test_shim_builds_the_other_configs_from_the_reference_yaml_tags():
     rv = G.init_mono_vector_state(300, 512, 23)
     sv = mv.state_dict()
     assert list(sv.keys()) == list(rv.keys()) and all(torch.equal(sv[k], rv[k]) for k in rv)
+    # ... and around the MOSI encoders (configs/mosi/mono/*.yaml)
+    for kind, make, d in (("lstm", lambda: utt_fusion.LSTMEncoder(20, 64, "last"), 20), ("textcnn", lambda: utt_fusion.TextCNN(768, 64, 1, 128, [3, 4, 5], 0.5), 768)):
+        torch.manual_seed(0)
+        ms = mono.MonomodalEncoder(make(), 64, 3)
+        torch.manual_seed(0)
+        rs = U.init_mono_seq_state(kind, d)
+        ss = ms.state_dict()
+        assert list(ss.keys()) == list(rs.keys()) and all(torch.equal(ss[k], rs[k]) for k in rs)
     with pytest.raises(NotImplementedError):
         mono.MonomodalEncoder(torch.nn.Linear(4, 4), 4, 3)
     with pytest.raises(RuntimeError):

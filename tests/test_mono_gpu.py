@@ -272,3 +272,96 @@ def test_monomodal_unsupported_requests_raise():
         model.train_step({"text": x[:, :299], "label": y}, opt, BCE, torch.device(DEV), None)
     with pytest.raises(NotImplementedError):
         MonomodalEncoder(torch.nn.LSTM(5, 64), 64, 3)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# MonomodalEncoder around a MOSI encoder (configs/mosi/mono/*.yaml): LSTMEncoder / TextCNN -> Linear(64, 3), cross entropy
+# ---------------------------------------------------------------------------------------------------------------------
+def build_seq(kind, input_size, graphs=True):
+    from mml_b200.mono import MonomodalEncoder
+    from mml_b200.utt_fusion import LSTMEncoder, TextCNN
+
+    torch.manual_seed(0)
+    enc = LSTMEncoder(input_size, 64, "last") if kind == "lstm" else TextCNN(input_size, 64, 1, 128, [3, 4, 5], 0.5)
+    model = MonomodalEncoder(enc, 64, 3).to(DEV)
+    model._get_engine(torch.device(DEV)).use_graphs = graphs
+    return model
+
+
+@pytest.mark.parametrize("kind,input_size,B", [("lstm", 5, 8), ("lstm", 20, 32), ("textcnn", 768, 8), ("textcnn", 768, 32)])
+def test_monomodal_mosi_step_matches_oracle(kind, input_size, B):
+    """Loss / logits vs the fp32 oracle, gradients vs the oracle that rounds where the kernels round (TextCNN: text input, conv weights,
+    conv output and its gradient in bf16; the LSTM path is fp32 throughout), Adam exact for the GPU's own gradients."""
+    import utt_fusion_oracle as U
+    from test_oracle_golden import mono_seq_batch
+
+    model = build_seq(kind, input_size, graphs=False)
+    torch.manual_seed(0)
+    state = U.init_mono_seq_state(kind, input_size)
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(state.keys()) and all(torch.equal(sd[k].cpu(), state[k]) for k in state)
+    x, y, keep = mono_seq_batch(kind, B, input_size, 41)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3)
+    before = {k: v.detach().cpu().clone() for k, v in model.named_parameters()}
+    out = model.train_step({"audio": x, "label": y}, opt, LOSS, torch.device(DEV), None, dropout_mask=keep)
+    ref = U.mono_seq_train_step(copy.deepcopy(state), {}, x, y, keep, apply_update=False)
+    emu = U.mono_seq_train_step(copy.deepcopy(state), {}, x, y, keep, apply_update=False, emulate_bf16=True)
+    plan = next(iter(model._engine.plans.values()))
+    logits = plan.logits.cpu()
+    span = float(ref["logits"].max() - ref["logits"].min()) + 1e-6
+    tol = 1e-4 if kind == "lstm" else 2e-2
+    assert abs(out["loss"] - ref["loss"]) < (1e-4 if kind == "lstm" else 1e-2)
+    assert float((logits - ref["logits"]).abs().max()) < tol * span
+    assert abs(out["metrics"]["accuracy"] - float((logits.argmax(1) == y).float().mean())) < 1e-6
+    g = torch.cat([p.grad.detach().cpu().float().reshape(-1) for _, p in model.named_parameters()])
+    r_emu = torch.cat([emu["grads"][n].reshape(-1) for n, _ in model.named_parameters()])
+    r_fp = torch.cat([ref["grads"][n].reshape(-1) for n, _ in model.named_parameters()])
+    rel_emu, rel_fp = float((g - r_emu).norm() / r_emu.norm()), float((g - r_fp).norm() / r_fp.norm())
+    print(f"{kind} in={input_size} B={B}: grad rel L2 vs same-rounding oracle {rel_emu:.2e}, vs fp32 oracle {rel_fp:.2e}")
+    assert rel_emu < (1e-4 if kind == "lstm" else 2e-3)
+    assert rel_fp < (1e-4 if kind == "lstm" else 0.15)   # bf16 rounding moves max-over-time winners (same bound as tests/test_utt_gpu.py)
+    for n, p in model.named_parameters():
+        gg = p.grad.detach().cpu().float() + 1e-3 * before[n]
+        m, v = 0.1 * gg, 0.001 * gg * gg
+        want = before[n] - 1e-3 * (m / 0.1) / ((v / 0.001).sqrt() + 1e-8)
+        assert torch.allclose(p.detach().cpu(), want, rtol=1e-4, atol=1e-6), n
+
+
+@pytest.mark.parametrize("name,kind", [("mono_mosi_audio_b8", "lstm"), ("mono_mosi_text_b8", "textcnn")])
+def test_monomodal_mosi_reference_fixture_curve_and_handoff(name, kind):
+    import utt_fusion_oracle as U
+    from test_oracle_golden import mono_seq_batch
+    from mml_b200.utt_fusion import FcClassifier, LSTMEncoder, TextCNN, UttFusionModel
+
+    gld = np.load(os.path.join(GOLD, name + ".npz"))
+    batch, input_size, seed, steps, T = (int(v) for v in gld["meta"])
+    model = build_seq(kind, input_size)
+    x, y, keep = mono_seq_batch(kind, batch, input_size, seed, T)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3)
+    for step in range(steps):  # the recorded run of the reference class (eager, eager, graph replay)
+        out = model.train_step({"text": x, "label": y}, opt, LOSS, torch.device(DEV), None, dropout_mask=keep)
+        assert abs(out["loss"] - float(gld["losses"][step])) < (1e-4 if kind == "lstm" else 2e-2), (step, out["loss"], float(gld["losses"][step]))
+    # longer run without a given mask (the kernel's own dropout stream for TextCNN): the loss falls like the oracle's
+    model = build_seq(kind, input_size)
+    torch.manual_seed(0)
+    state, opt_state = U.init_mono_seq_state(kind, input_size), {}
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3)
+    x, y, _ = mono_seq_batch(kind, 32, input_size, 7, T)
+    got, want = [], []
+    for step in range(25):
+        got.append(model.train_step({"video": x, "labels": y}, opt, LOSS, torch.device(DEV), None)["loss"])
+        want.append(U.mono_seq_train_step(state, opt_state, x, y, None)["loss"])  # oracle without dropout
+    assert got[-1] < (0.99 if kind == "lstm" else 0.9) * got[0]  # 25 Adam steps at lr 1e-3: the LSTM moves slowly (oracle: same curve)
+    if kind == "lstm":
+        assert max(abs(a - b) for a, b in zip(got, want)) < 2e-3, (got[-3:], want[-3:])
+    ev = model.validation_step({"video": x, "labels": y}, LOSS, torch.device(DEV), None)
+    rv = U.mono_seq_validation_step({k: v.detach().cpu().clone() for k, v in model.state_dict().items()}, x, y)
+    assert abs(ev["loss"] - rv["loss"]) < (1e-4 if kind == "lstm" else 2e-2)
+    # hand-off: the pre-trained encoder's state_dict loads into the fusion model's encoder slot (train_multimodal.py:186-187)
+    enc_sd = {k: v.detach().cpu().clone() for k, v in model.get_encoder().state_dict().items()}
+    torch.manual_seed(3)
+    fusion = UttFusionModel(LSTMEncoder(5 if kind != "lstm" else input_size, 64), LSTMEncoder(20, 64), TextCNN(768, 64, 1, 128, [3, 4, 5], 0.5),
+                            FcClassifier(192, [192, 64, 32], 3, dropout=0.5), clip=1.0)
+    (fusion.netA if kind == "lstm" else fusion.netT).load_state_dict(enc_sd)
+    got_sd = (fusion.netA if kind == "lstm" else fusion.netT).state_dict()
+    assert all(torch.equal(got_sd[k].cpu(), enc_sd[k]) for k in enc_sd)

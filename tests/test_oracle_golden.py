@@ -182,6 +182,42 @@ def test_monomodal_mmimdb_encoder_oracle_matches_reference():
     assert np.allclose(state["encoder.net.0.running_mean"].numpy(), g["final::encoder.net.0.running_mean"], rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("name,kind", [("mono_mosi_audio_b8", "lstm"), ("mono_mosi_text_b8", "textcnn")])
+def test_monomodal_mosi_encoder_oracle_matches_reference(name, kind):
+    """Monomodal pre-training of a MOSI encoder (configs/mosi/mono/*.yaml): LSTMEncoder / TextCNN -> Linear(64, 3), cross entropy,
+    Adam(1e-3, wd 1e-3) -- the oracle against the recorded run of the reference MonomodalEncoder."""
+    import utt_fusion_oracle as U
+
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    batch, input_size, seed, steps, T = (int(v) for v in g["meta"])
+    torch.manual_seed(0)
+    state = U.init_mono_seq_state(kind, input_size)
+    x, y, keep = mono_seq_batch(kind, batch, input_size, seed, T)
+    opt_state = {}
+    for step in range(steps):
+        out = U.mono_seq_train_step(state, opt_state, x, y, keep)
+        assert abs(out["loss"] - float(g["losses"][step])) < 2e-6
+        if step == 0:
+            assert np.allclose(out["logits"].numpy(), g["logits"], rtol=1e-5, atol=2e-6)
+            l2 = np.array([float(out["grads"][k].double().norm()) for k in g["grad_keys"]])
+            assert np.allclose(l2, g["grad_l2"], rtol=1e-4, atol=1e-9)
+            ref = g["grad::classifier.weight"]
+            assert np.abs(out["grads"]["classifier.weight"].numpy() - ref).max() <= 1e-5 * np.abs(ref).max() + 1e-9
+    assert np.allclose(state["classifier.bias"].numpy(), g["final::classifier.bias"], rtol=1e-4, atol=1e-7)
+
+
+def mono_seq_batch(kind, batch, input_size, seed, T=50):
+    """The inputs oracle/make_golden.py::mono_seq_case drew (zero-padded sequences, labels, TextCNN dropout mask)."""
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, T, input_size, generator=gen)
+    lens = torch.randint(20, T + 1, (batch,), generator=gen)
+    for b in range(batch):
+        x[b, int(lens[b]):] = 0.0
+    y = torch.randint(0, 3, (batch,), generator=gen)
+    keep = (torch.rand(batch, 384, generator=gen) >= 0.5).float() if kind == "textcnn" else None
+    return x, y, keep
+
+
 def test_mosi_utt_fusion_oracle_matches_reference():
     """config 4: the oracle for the MOSI / UttFusion step against the recorded reference run -- LSTM x2, TextCNN,
     FcClassifier, CE, clip_grad_norm_(1.0), Adam; zero-padded variable-length sequences and all seven missing patterns."""
