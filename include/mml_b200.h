@@ -62,8 +62,8 @@ int mml_ctx_set_sm_budget(mml_ctx* ctx, int sms);
 int mml_ctx_set_pdl(mml_ctx* ctx, int enable);
 
 /* A-B switches for experiments (not part of the reference surface): key 1 = use the halo conv kernel (default 1); key 2 = largest
- * thread-block cluster of the split-K convolution variant (1 = off (default), 2, 4, 8); key 3 = BatchNorm grids capped at one
- * resident wave (default 1); key 4 = fewest 128-pixel tiles per weight-gradient split (default 48) */
+ * thread-block cluster of the split-K convolution variant (1 = off (default), 2, 4, 8); key 3 = BatchNorm grids: 0 = fixed caps,
+ * 1 = one resident wave, 2 = one resident wave of the SM budget (default); key 4 = fewest 128-pixel tiles per weight-gradient split (default 48) */
 int mml_debug_set(int key, int value);
 
 /* ---- a1: missing-modality mask -- data/base_dataset.py:70-72  sample[mod] = original * mask -------------------- */

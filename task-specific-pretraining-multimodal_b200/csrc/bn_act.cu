@@ -15,7 +15,7 @@
 using namespace mml;
 
 extern "C" int mml_g_bn_one_wave;
-int mml_g_bn_one_wave = 1;  // mml_debug_set key 3 (A/B switch): 1 = BatchNorm grids capped at one resident wave
+int mml_g_bn_one_wave = 2;  // mml_debug_set key 3 (A/B switch): 0 = old grid caps, 1 = BatchNorm grids capped at one resident wave, 2 = ... of the SM budget
 
 namespace {
 
@@ -768,7 +768,10 @@ int wave_cap(const mml_ctx* ctx, int grid, K kernel, cudaStream_t st) {
     std::lock_guard<std::mutex> lock(mu);
     cache[(const void*)kernel] = occ;
   }
-  const int cap = occ * ctx->sm_count;
+  // mode 2: one wave of the SM BUDGET (mml_ctx_set_sm_budget) -- the audio encoder's BatchNorm kernels then fill 116 SMs' worth of
+  // register file instead of all 148, which leaves room on every SM for the image stream's GEMM CTAs to co-reside
+  const int sms = (mml_g_bn_one_wave == 2 && ctx->sm_budget > 0) ? ctx->sm_budget : ctx->sm_count;
+  const int cap = occ * sms;
   return grid < cap ? grid : cap;
 }
 
@@ -922,7 +925,7 @@ int mml_stem_bn_pool_fwd(mml_ctx* ctx, const uint16_t* x, const double* stats, c
   if (rc) return rc;
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
   const int64_t rows = (int64_t)N * H * W;
-  int grid = N * P < ctx->sm_count * 8 ? N * P : ctx->sm_count * 8;  // CTAs walk output rows (n, p)
+  int grid = N * P < ctx->sm_count * 8 ? N * P : ctx->sm_count * 8;  // CTAs walk output rows (n, p) (a one-wave cap was measured here: slower)
   BnTrain bn{stats, gamma, beta, running_mean, running_var, save_mean, save_invstd};
   cudaStream_t st = (cudaStream_t)stream;
   if (stats) {

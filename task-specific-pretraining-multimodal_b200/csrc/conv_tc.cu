@@ -1577,7 +1577,7 @@ extern int mml_g_bn_one_wave;  // bn_act.cu
 int mml_debug_set(int key, int value) {
   if (key == 1) g_halo_enable = value;
   else if (key == 2 && (value == 1 || value == 2 || value == 4 || value == 8)) g_splitk_max = value;
-  else if (key == 3 && (value == 0 || value == 1)) mml_g_bn_one_wave = value;
+  else if (key == 3 && value >= 0 && value <= 2) mml_g_bn_one_wave = value;
   else if (key == 4 && value >= 1 && value <= 64) g_wgrad_min_tiles = value;
   else return MML_ERR_INVALID;
   return MML_OK;

@@ -499,7 +499,7 @@ stem_wgrad_bn_combine_kernel(const double* __restrict__ red, const float* __rest
 
 // several CTAs per SM: each has only 4 builder warps, latency is hidden across CTAs (fprop 66 KB smem -> 3, wgrad 106 KB -> 2)
 int stem_ctas(const mml_ctx* ctx, int tiles, int per_sm) {
-  int n = ctx->sm_count * per_sm;
+  int n = ctx->sm_count * per_sm;  // (applying the SM budget here was measured and costs more than it frees: these kernels are issue-bound)
   if (n > tiles) n = tiles;
   return n < 1 ? 1 : n;
 }
