@@ -58,6 +58,10 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        if os.environ.get("MML_BENCH_SAMPLER", "nvml") == "off":
+            return
+        if os.environ.get("MML_BENCH_SAMPLER", "nvml") == "nvml" and self._start_nvml():
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -70,14 +74,70 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    # In-process NVML polling (nvidia_ml_py): the same counters as the nvidia-smi query, without a second process taking the driver's
+    # locks every 100 ms next to loops that issue a dozen CUDA calls per step (the end-to-end loops at N > 1 were perturbed by it).
+    def _start_nvml(self) -> bool:
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            except Exception:
+                pass
+            h = None
+            if uuid:
+                for cand in (uuid, "GPU-" + uuid):
+                    try:
+                        h = nv.nvmlDeviceGetHandleByUUID(cand.encode() if hasattr(cand, "encode") else cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+                h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.nv, self.h, self.stop_flag = nv, h, False
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+
+            def poll():
+                R = nv
+                bits = (("hw_slowdown", getattr(R, "nvmlClocksEventReasonHwSlowdown", 0x8)), ("hw_thermal_slowdown", getattr(R, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                        ("sw_thermal_slowdown", getattr(R, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)), ("sw_power_cap", getattr(R, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+                while not self.stop_flag:
+                    try:
+                        clk = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                        util = float(nv.nvmlDeviceGetUtilizationRates(h).gpu)
+                        try:
+                            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        except Exception:
+                            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        flags = ["Active" if mask & b else "Not Active" for _, b in bits]
+                        self.lines.append(",".join([str(clk), str(self.mx), "0"] + flags + [str(util)]))
+                    except Exception:
+                        pass
+                    time.sleep(0.05)
+
+            self.t = threading.Thread(target=poll, daemon=True)
+            self.t.start()
+            self.proc = "nvml"
+            return True
+        except Exception:
+            return False
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        if self.proc == "nvml":
+            self.stop_flag = True
+            self.t.join(timeout=1)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         sm, sm_all, mx, reasons = [], [], None, set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]

@@ -155,6 +155,8 @@ class AVMNIST(nn.Module):
 
             ops.check_class_labels(labels, NUM_CLASSES)
             _copy_in(plan.labels, torch.as_tensor(labels).reshape(B))
+        from .data import note_inputs_consumed
+        note_inputs_consumed(eng.device)  # a prefetcher may overwrite the batch's device buffers from here on
         return plan
 
     # ---- forward ---------------------------------------------------------------------------------------------------

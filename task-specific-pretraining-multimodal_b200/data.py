@@ -138,6 +138,21 @@ def luma_lut(cmap_table, scale: str = "mul") -> torch.Tensor:
     return torch.from_numpy(lut.astype(np.float32))
 
 
+# The consumer of a prefetched batch (every fused ``train_step`` / ``validation_step``) copies it into its static input buffers first thing;
+# right after those copies it records an event here.  The prefetcher waits for THAT event before it overwrites the slot, instead of for
+# everything queued on the consumer's stream (= the whole previous step, collectives included).
+_inputs_consumed: Dict[int, "torch.cuda.Event"] = {}
+
+
+def note_inputs_consumed(device) -> None:
+    """Called by the step methods once the batch has been copied into the plan's static buffers (stream-ordered on the current stream)."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))
+    _inputs_consumed[idx] = ev
+
+
 class DevicePrefetcher:
     """Iterate a loader of batch dicts with the host->device copies of batch n+1 running under step n.
 
@@ -162,6 +177,8 @@ class DevicePrefetcher:
         if self.device.type != "cuda":
             raise RuntimeError("DevicePrefetcher stages batches onto a CUDA device")
         self.luts = {k: v.to(self.device, dtype=torch.float32).contiguous() for k, v in (luts or {}).items()}
+        import os as _os
+        self.sync = _os.environ.get("MML_PREFETCH_SYNC", "event")  # "stream": wait for the consumer's whole stream (round-1 behaviour)
         key = self.device.index if self.device.index is not None else torch.cuda.current_device()
         if key not in DevicePrefetcher._streams:
             DevicePrefetcher._streams[key] = torch.cuda.Stream(device=self.device, priority=-1)
@@ -171,7 +188,14 @@ class DevicePrefetcher:
 
     def _stage(self, batch: Dict[Any, Any], slot: Dict[Any, torch.Tensor]):
         main = torch.cuda.current_stream(self.device)
-        self.stream.wait_stream(main)  # the slot's previous consumer is done before it is overwritten
+        # the slot's previous consumer must be done with it before it is overwritten: its "inputs consumed" event when the step method
+        # recorded one (consumed here, so a consumer that records nothing falls back to waiting for its whole stream)
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        ev = _inputs_consumed.pop(idx, None) if self.sync == "event" else None
+        if ev is not None:
+            self.stream.wait_event(ev)
+        else:
+            self.stream.wait_stream(main)
         out = {}
         with torch.cuda.stream(self.stream):
             for k, v in batch.items():
