@@ -843,7 +843,7 @@ TENSOR_KERNELS = [
     ("fprop_audio_l2", "conv_halo_kernel<2,128,2,0,0> C=K=128 14x14 (ResNet18 layer2 fprop)", (14, 14, 128, 128, 3, 1, 1), "fprop", 3),
     ("fprop_image_l3", "conv_igemm_kernel<128,4,1,0> C=K=256 2x2 (ResNet34 layer3 fprop, 11 of its 12 convolutions)", (2, 2, 256, 256, 3, 1, 1), "fprop", 11),
     ("dgrad_image_l3", "conv_igemm_kernel<128,4,1,1> C=K=256 2x2 (ResNet34 layer3 dgrad)", (2, 2, 256, 256, 3, 1, 1), "dgrad", 11),
-    ("wgrad_image_l3", "conv_wgrad_kernel<256,2> (one split, no reduce launch), C=K=256 2x2 (ResNet34 layer3 wgrad)", (2, 2, 256, 256, 3, 1, 1), "wgrad", 11),
+    ("wgrad_image_l3", "conv_wgrad_kernel<128,3> (one split, no reduce launch; 128-wide tiles on <= 8 pixel tiles), C=K=256 2x2 (ResNet34 layer3 wgrad)", (2, 2, 256, 256, 3, 1, 1), "wgrad", 11),
 ]
 
 

@@ -1305,6 +1305,8 @@ int launch_igemm_splitk_t(mml_ctx* ctx, const IgemmMaps& maps, const IgemmParams
 }
 
 int g_wgrad_min_tiles = 48;  // fewest pixel tiles (128 pixels each) per weight-gradient split (mml_debug_set key 4; swept on B200: DESIGN.md section 5)
+int g_wgrad_narrow = 8;  // weight gradients of layers with at most this many pixel tiles use 128-wide output tiles (0 = off; key 5)
+int g_igemm_narrow = 0;  // fprop / dgrad of layers with at most this many pixel tiles use 64-wide output tiles (0 = off; key 6)
 int g_splitk_max = 1;  // largest cluster the split-K variant may use (mml_debug_set key 2; 1 = off, the default: see DESIGN.md)
 
 // One "shifted GEMM" launch: out view <- sum over taps of in views @ weights, for 1..4 output phases (grid.z).
@@ -1351,6 +1353,8 @@ int run_igemm_phases(mml_ctx* ctx, const View* in_views, int n_views, const void
   // a single pixel tile (the Linear layers of the MMIMDb step: M = batch <= 128): spread the output columns over as many SMs
   // as possible, every CTA streams the whole A operand from L2 anyway
   if (total_tiles == 1) block_n = 64;
+  // a handful of pixel tiles (the ResNet34 4x4 / 2x2 / 1x1 maps): 64-wide tiles double the CTA count again (mml_debug_set key 6)
+  if (g_igemm_narrow && block_n == 128 && total_tiles <= g_igemm_narrow && total_tiles * (cout / 64) * 2 <= ctx->sm_count) block_n = 64;
   if (!b_mn) {
     if ((rc = encode_weights(ctx, &maps.w, w, (long long)n_wtaps * cin, cout, block_n))) return rc;
   } else {
@@ -1579,6 +1583,8 @@ int mml_debug_set(int key, int value) {
   else if (key == 2 && (value == 1 || value == 2 || value == 4 || value == 8)) g_splitk_max = value;
   else if (key == 3 && value >= 0 && value <= 2) mml_g_bn_one_wave = value;
   else if (key == 4 && value >= 1 && value <= 64) g_wgrad_min_tiles = value;
+  else if (key == 5 && value >= 0 && value <= 1024) g_wgrad_narrow = value;
+  else if (key == 6 && value >= 0 && value <= 1024) g_igemm_narrow = value;
   else return MML_ERR_INVALID;
   return MML_OK;
 }
@@ -1692,6 +1698,12 @@ static int plan_wgrad(const mml_ctx* ctx, const mml_conv_geom* g, int P, int Q, 
   wp->block_c = g->C % 256 == 0 ? 256 : (g->C % 128 == 0 ? 128 : 64);
   wp->out_tiles = (int)mml_ceil_div(g->K, 128) * n_taps * (g->C / wp->block_c);
   const int m_tiles = wp->tg.tiles_h * wp->tg.tiles_n;
+  // few pixel tiles (the ResNet34 2x2 / 1x1 maps): 128-wide output tiles give twice the CTAs and a three-stage instead of a two-stage
+  // operand pipeline (64 KB instead of 96 KB per stage) for a loop that is all load latency (mml_debug_set key 5)
+  if (g_wgrad_narrow && wp->block_c == 256 && m_tiles <= g_wgrad_narrow && wp->out_tiles * 2 <= ctx->sm_count) {
+    wp->block_c = 128;
+    wp->out_tiles *= 2;
+  }
   // one wave: every split's partial tile is written to and read back from the workspace, so more CTAs than SMs only add traffic
   int splits = ctx->sm_count / wp->out_tiles;
   // ... and every split should own a few pixel tiles: a split of ONE 128-pixel tile runs 8 MMAs and then writes (and the reduce launch

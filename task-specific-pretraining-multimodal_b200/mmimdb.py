@@ -209,6 +209,8 @@ class MMIMDb(nn.Module):
                 _copy_in(dst, torch.as_tensor(m).reshape(B))
         if labels is not None:
             _copy_in(plan.labels, labels.reshape(B, plan.NC))
+        from .data import note_inputs_consumed
+        note_inputs_consumed(eng.device)  # a prefetcher may overwrite the batch's device buffers from here on
         return plan
 
     def forward(self, I: torch.Tensor, T: torch.Tensor, *, is_embd_I: bool = False, is_embd_T: bool = False) -> torch.Tensor:

@@ -489,9 +489,14 @@ class MonomodalEncoder(nn.Module):
         return plan
 
     def _plan(self, eng, x, labels):
+        from .data import note_inputs_consumed
+
         if self._seq is not None:
-            return self._stage_seq(eng, x, labels)
-        return self._stage_vec(eng, x, labels) if self._vector else self._stage(eng, x, labels)
+            plan = self._stage_seq(eng, x, labels)
+        else:
+            plan = self._stage_vec(eng, x, labels) if self._vector else self._stage(eng, x, labels)
+        note_inputs_consumed(eng.device)  # a prefetcher may overwrite the batch's device buffers from here on
+        return plan
 
     def encode(self, which: str, x: torch.Tensor) -> torch.Tensor:
         """``self.encoder(x)`` outside the step (vector encoders): BatchNorm1d -> Linear, fp32 [B, E]."""

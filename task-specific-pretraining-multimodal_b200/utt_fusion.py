@@ -396,6 +396,8 @@ class UttFusionModel(nn.Module):
         if labels is not None:
             ops.check_class_labels(labels, plan.logits.shape[1])
             _copy_in(plan.labels, torch.as_tensor(labels).reshape(-1))
+        from .data import note_inputs_consumed
+        note_inputs_consumed(eng.device)  # a prefetcher may overwrite the batch's device buffers from here on
         return plan
 
     def _unpack(self, batch: Dict[Any, Any]):

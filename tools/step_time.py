@@ -13,6 +13,12 @@ if os.environ.get('MML_BN_WAVE'):
 if os.environ.get('MML_WGRAD_MIN_TILES'):
     from mml_b200 import ops as _ops
     _ops.debug_set(4, int(os.environ['MML_WGRAD_MIN_TILES']))
+if os.environ.get('MML_WGRAD_NARROW'):
+    from mml_b200 import ops as _ops
+    _ops.debug_set(5, int(os.environ['MML_WGRAD_NARROW']))
+if os.environ.get('MML_IGEMM_NARROW'):
+    from mml_b200 import ops as _ops
+    _ops.debug_set(6, int(os.environ['MML_IGEMM_NARROW']))
 if os.environ.get('MML_SPLITK'):
     from mml_b200 import ops as _ops
     _ops.debug_set(2, int(os.environ['MML_SPLITK']))
