@@ -832,7 +832,7 @@ class _Term:
 # of that kernel AND shape per step).  The launch counts are those of the step's launch list (profiles/r2_step_launches_*.csv).
 TENSOR_KERNELS = [
     ("wgrad_audio_l3", "conv_wgrad_kernel<256,2> (3 pixel splits) + fixed-order partial reduce, C=K=256 7x7 (ResNet18 layer3)", (7, 7, 256, 256, 3, 1, 1), "wgrad", 4),
-    ("wgrad_audio_l4", "conv_wgrad_kernel<256,2> (one split, no reduce launch), C=K=512 4x4 (ResNet18 layer4)", (4, 4, 512, 512, 3, 1, 1), "wgrad", 3),
+    ("wgrad_audio_l4", "conv_wgrad_kernel<128,3> (one split, no reduce launch; 128-wide tiles), C=K=512 4x4 (ResNet18 layer4)", (4, 4, 512, 512, 3, 1, 1), "wgrad", 3),
     ("fprop_audio_l4", "conv_igemm_kernel<128,4,1,0> C=K=512 4x4 (ResNet18 layer4 fprop)", (4, 4, 512, 512, 3, 1, 1), "fprop", 3),
     ("dgrad_audio_l4", "conv_igemm_kernel<128,4,1,1> C=K=512 4x4 (ResNet18 layer4 dgrad)", (4, 4, 512, 512, 3, 1, 1), "dgrad", 3),
     ("fprop_audio_l3", "conv_igemm_kernel<256,3,1,0> C=K=256 7x7 (ResNet18 layer3 fprop)", (7, 7, 256, 256, 3, 1, 1), "fprop", 3),
@@ -843,7 +843,7 @@ TENSOR_KERNELS = [
     ("fprop_audio_l2", "conv_halo_kernel<2,128,2,0,0> C=K=128 14x14 (ResNet18 layer2 fprop)", (14, 14, 128, 128, 3, 1, 1), "fprop", 3),
     ("fprop_image_l3", "conv_igemm_kernel<128,4,1,0> C=K=256 2x2 (ResNet34 layer3 fprop, 11 of its 12 convolutions)", (2, 2, 256, 256, 3, 1, 1), "fprop", 11),
     ("dgrad_image_l3", "conv_igemm_kernel<128,4,1,1> C=K=256 2x2 (ResNet34 layer3 dgrad)", (2, 2, 256, 256, 3, 1, 1), "dgrad", 11),
-    ("wgrad_image_l3", "conv_wgrad_kernel<128,3> (one split, no reduce launch; 128-wide tiles on <= 8 pixel tiles), C=K=256 2x2 (ResNet34 layer3 wgrad)", (2, 2, 256, 256, 3, 1, 1), "wgrad", 11),
+    ("wgrad_image_l3", "conv_wgrad_kernel<128,3> (one split, no reduce launch; 128-wide tiles), C=K=256 2x2 (ResNet34 layer3 wgrad)", (2, 2, 256, 256, 3, 1, 1), "wgrad", 11),
 ]
 
 

@@ -64,7 +64,7 @@ int mml_ctx_set_pdl(mml_ctx* ctx, int enable);
 /* A-B switches for experiments (not part of the reference surface): key 1 = use the halo conv kernel (default 1); key 2 = largest
  * thread-block cluster of the split-K convolution variant (1 = off (default), 2, 4, 8); key 3 = BatchNorm grids: 0 = fixed caps,
  * 1 = one resident wave, 2 = one resident wave of the SM budget (default); key 4 = fewest 128-pixel tiles per weight-gradient split (default 48);
- * key 5 = weight gradients of layers with at most this many pixel tiles use 128-wide output tiles (default 8, 0 = off); key 6 = the same
+ * key 5 = weight gradients of layers with at most this many pixel tiles use 128-wide output tiles (default 32, 0 = off); key 6 = the same
  * for fprop / dgrad with 64-wide tiles (default 0 = off) */
 int mml_debug_set(int key, int value);
 

@@ -1305,7 +1305,7 @@ int launch_igemm_splitk_t(mml_ctx* ctx, const IgemmMaps& maps, const IgemmParams
 }
 
 int g_wgrad_min_tiles = 48;  // fewest pixel tiles (128 pixels each) per weight-gradient split (mml_debug_set key 4; swept on B200: DESIGN.md section 5)
-int g_wgrad_narrow = 8;  // weight gradients of layers with at most this many pixel tiles use 128-wide output tiles (0 = off; key 5)
+int g_wgrad_narrow = 32;  // weight gradients of layers with at most this many pixel tiles use 128-wide output tiles (0 = off; key 5)
 int g_igemm_narrow = 0;  // fprop / dgrad of layers with at most this many pixel tiles use 64-wide output tiles (0 = off; key 6)
 int g_splitk_max = 1;  // largest cluster the split-K variant may use (mml_debug_set key 2; 1 = off, the default: see DESIGN.md)
 
