@@ -462,17 +462,13 @@ stem_bn_pool_fwd_kernel(const uint16_t* __restrict__ x, BnTrain bn, const float*
   const int c8 = C >> 3;
   const int cg = (int)threadIdx.x % c8, qs = (int)threadIdx.x / c8, nq = kThreads / c8;
   const F8 sc = load8f(s_coef + cg * 8), sh = load8f(s_coef + kMaxC + cg * 8);
+  uint32_t flip[4];  // sign-bit mask per packed channel pair: set where scale < 0 (max of bn(x) = bn(min x))
+#pragma unroll
+  for (int c2 = 0; c2 < 4; ++c2) flip[c2] = (sc.v[2 * c2] < 0.f ? 0x00008000u : 0u) | (sc.v[2 * c2 + 1] < 0.f ? 0x80000000u : 0u);
   for (int row = blockIdx.x; row < N * P; row += gridDim.x) {
     const int n = row / P, p = row - n * P;
    for (int q = qs; q < Q; q += nq) {
     const long long i = ((long long)row * Q + q) * c8 + cg;
-    float best[8];
-    int idx[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      best[j] = -INFINITY;
-      idx[j] = -1;
-    }
     // all nine window loads are issued before the first one is consumed (ncu: with the load inside the compare loop every window
     // element cost a full memory round trip -- nine serialized long-scoreboard stalls per output vector, 80 us for 140 MB)
     uint4 win[9];
@@ -488,32 +484,46 @@ stem_bn_pool_fwd_kernel(const uint16_t* __restrict__ x, BnTrain bn, const float*
         win[r * 3 + s2] = ok ? ldg16(x + (((long long)n * H + h) * W + w) * C + cg * 8) : make_uint4(0, 0, 0, 0);
       }
     }
+    // The window maximum is taken on the RAW bf16 values, two channels per instruction: x -> fma(x, scale, shift) is monotone
+    // (non-decreasing for scale >= 0; for scale < 0 the sign bit of the key is flipped, which turns the max into the min of x), so the
+    // maximum of the fp32 BatchNorm outputs IS the BatchNorm output of the extreme raw value -- same y bit for bit, at a quarter of
+    // the instructions of comparing nine fp32 fma results per channel (ncu: the kernel was instruction-issue bound, 80 us for 140 MB).
+    // ReLU and the bf16 rounding are applied once, to the winner.  argmax = first position (h, w scan order) holding the extreme value.
+    uint32_t key[9][4];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
+    for (int t = 0; t < 9; ++t) {
+      const bool ok = (live >> t) & 1u;
+      const uint32_t raw[4] = {win[t].x, win[t].y, win[t].z, win[t].w};
 #pragma unroll
-      for (int s2 = 0; s2 < 3; ++s2) {
-        if (!((live >> (r * 3 + s2)) & 1u)) continue;
-        const F8 v = unpack8(win[r * 3 + s2]);
+      for (int c2 = 0; c2 < 4; ++c2) key[t][c2] = ok ? (raw[c2] ^ flip[c2]) : 0xFF80FF80u;  // outside the image: -inf, never wins
+    }
+    uint32_t best2[4], idx2[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          // ReLU and the bf16 rounding of the (never stored) activation are monotone, so they commute with the max: compare the
-          // fp32 BatchNorm outputs and apply both once to the winner (a window whose maximum is <= 0 yields 0; its argmax is
-          // irrelevant because backward recomputes the ReLU mask)
-          const float a = fmaf(v.v[j], sc.v[j], sh.v[j]);
-          if (idx[j] < 0 || a > best[j] || a != a) {  // torch: (val > maxval) || isnan(val)
-            best[j] = a;
-            idx[j] = r * 3 + s2;
-          }
-        }
+    for (int c2 = 0; c2 < 4; ++c2) {
+      __nv_bfloat162 m = *reinterpret_cast<const __nv_bfloat162*>(&key[0][c2]);
+#pragma unroll
+      for (int t = 1; t < 9; ++t) m = __hmax2_nan(m, *reinterpret_cast<const __nv_bfloat162*>(&key[t][c2]));  // NaN wins, like torch
+      uint32_t id = 4u * 0x00010001u;  // the centre of the window is always inside the image
+#pragma unroll
+      for (int t = 8; t >= 0; --t) {
+        uint32_t eq = __hequ2_mask(*reinterpret_cast<const __nv_bfloat162*>(&key[t][c2]), m);  // 0xFFFF per half where equal (or NaN)
+        eq = ((live >> t) & 1u) ? eq : 0u;
+        id = (eq & ((uint32_t)t * 0x00010001u)) | (~eq & id);
       }
+      best2[c2] = *reinterpret_cast<const uint32_t*>(&m) ^ flip[c2];
+      idx2[c2] = id;
     }
     F8 o;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o.v[j] = best[j] != best[j] ? best[j] : fmaxf(best[j], 0.f);  // relu(NaN) = NaN like torch
+    for (int c2 = 0; c2 < 4; ++c2) {
+      const float a0 = fmaf(bf16_lo(best2[c2]), sc.v[2 * c2], sh.v[2 * c2]), a1 = fmaf(bf16_hi(best2[c2]), sc.v[2 * c2 + 1], sh.v[2 * c2 + 1]);
+      o.v[2 * c2] = a0 != a0 ? a0 : fmaxf(a0, 0.f);  // relu(NaN) = NaN like torch
+      o.v[2 * c2 + 1] = a1 != a1 ? a1 : fmaxf(a1, 0.f);
+    }
     *reinterpret_cast<uint4*>(y + i * 8) = pack8(o);
     uint2 a;
-    a.x = (uint32_t)idx[0] | ((uint32_t)idx[1] << 8) | ((uint32_t)idx[2] << 16) | ((uint32_t)idx[3] << 24);
-    a.y = (uint32_t)idx[4] | ((uint32_t)idx[5] << 8) | ((uint32_t)idx[6] << 16) | ((uint32_t)idx[7] << 24);
+    a.x = (idx2[0] & 0xFFu) | ((idx2[0] >> 8) & 0xFF00u) | ((idx2[1] & 0xFFu) << 16) | ((idx2[1] & 0xFF0000u) << 8);
+    a.y = (idx2[2] & 0xFFu) | ((idx2[2] >> 8) & 0xFF00u) | ((idx2[3] & 0xFFu) << 16) | ((idx2[3] & 0xFF0000u) << 8);
     *reinterpret_cast<uint2*>(amax + i * 8) = a;
    }
   }
