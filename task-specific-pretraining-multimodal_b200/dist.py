@@ -10,8 +10,9 @@ head, ~85 MB) is all-reduced on a side stream while the audio encoder's backward
 the audio encoder follows in two ranges: layer3..fc (94 % of its parameters, ~42 MB) as soon as layer3's backward is
 done -- under the backward of layer2 / layer1 / the stem -- and the small remainder (~3 MB) at the end of the step.  The wgrad kernels write straight into ``G``, so there is no pack/copy step.
 The data plane is the library's own NCCL communicator (``mml_comm_init`` / ``mml_allreduce_bucket``, csrc/comm.cu): NCCL over
-NVLink / NVSwitch with a capped CTA budget (``MML_NCCL_MAX_CTAS``, default 16: the all-reduces run under the audio encoder's
-backward and every SM NCCL takes is one its persistent kernels lose).  ``torch.distributed`` remains the CONTROL plane (rendezvous,
+NVLink / NVSwitch with a capped CTA budget (``MML_NCCL_MAX_CTAS``, default 32: the all-reduces run under the audio encoder's
+backward and every SM NCCL takes is one its persistent kernels lose -- measured at N = 2 on the final round-2 build: 8 CTAs 2.89 ms/step
+end to end, 16 2.65, 32 2.59).  ``torch.distributed`` remains the CONTROL plane (rendezvous,
 hand-over of the communicator id, the initial broadcast, barriers); both the collectives and the cross-stream dependencies are
 captured into the step's CUDA graph.
 """
@@ -43,7 +44,7 @@ class DataParallel:
         self.comm_stream: Optional[torch.cuda.Stream] = None
         self.buckets: List[Tuple[int, int]] = []
         self.engine = None
-        self.max_ctas = int(os.environ.get("MML_NCCL_MAX_CTAS", "16"))
+        self.max_ctas = int(os.environ.get("MML_NCCL_MAX_CTAS", "32"))
 
     def _ensure_comm(self, device: torch.device) -> None:
         """Create the library-owned communicator of this device once: rank 0 draws the id, torch.distributed hands it over."""
