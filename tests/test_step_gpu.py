@@ -164,8 +164,10 @@ def test_graph_replay_equals_eager_and_eval_roundtrip():
         opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
         ls = [model.train_step(make_batch(d, B), opt, LOSS, torch.device(DEV), None, dropout_mask=d["dropout_mask"])["loss"] for _ in range(5)]
         losses[graphs] = ls
-    # steps 3-4 of the graph run are replays; split-K wgrad uses fp32 atomics => tiny run-to-run differences allowed
-    assert np.allclose(losses[False], losses[True], rtol=0, atol=3e-2), losses  # chaotic amplification of atomic-order noise, see module docstring
+    # steps 3-4 of the graph run are replays.  Every weight gradient is a fixed-order sum (no fp32 atomics since round 2) and the BatchNorm
+    # statistics are fp64 atomics rounded to fp32, so the two runs agree bit for bit in practice (measured |diff| = 0.0, eager vs graph, graph
+    # vs graph and eager vs eager: tools/replay_determinism.py); 1e-5 leaves room for a one-ulp flip of a rounded fp64 sum
+    assert np.allclose(losses[False], losses[True], rtol=0, atol=1e-5), losses
     # eval forward == validation_step, and a state_dict round trip reproduces it bit for bit
     A = O.apply_missing_mask(d["audio"], d["audio_mask"]).to(DEV)
     I = d["image"].to(DEV)
