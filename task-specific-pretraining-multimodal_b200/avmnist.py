@@ -138,6 +138,10 @@ class AVMNIST(nn.Module):
         return t
 
     def _stage(self, eng, A, I, mask_a=None, mask_i=None, labels=None):
+        for name, t in (("audio", A), ("image", I)):
+            if t.dtype == torch.uint8:  # a plain cast would feed 0..255 instead of the reference's colormap -> "L" -> [0, 1] chain
+                raise TypeError(f"{name}: uint8 pixels must go through the luminance table first (DevicePrefetcher(luts=...) / "
+                                "datasets.AVMNIST.fused_loader, or datasets.AVMNIST.batches(image_form='f32'))")
         A, I = self._as_bhw(A), self._as_bhw(I)
         B = A.shape[0]
         if I.shape[0] != B:

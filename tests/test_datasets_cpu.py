@@ -1,0 +1,199 @@
+"""``mml_b200.datasets.AVMNIST`` against the reference's own dataset class ("the real AVMNIST loader").
+
+``tests/golden/avmnist_loader.npz`` was written by ``oracle/make_golden_loader.py`` from the UNMODIFIED ``data.avmnist.AVMNIST``
+(MML_Suite/data/avmnist.py:21-277) over a tiny CSV + ``torch.save`` dataset; the raw inputs are stored with it, the files are rebuilt
+here, and every item / batch the reference produced must come back bit for bit (the comparison is on int32 views: -0.0, inf * 0 = nan).
+The batch-granular path (``batches()``) has no reference counterpart; it is checked against the item path.
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from mml_b200.datasets import AVMNIST, PatternSpecificDataset
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "avmnist_loader.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+@pytest.fixture(scope="module")
+def csv(gold, tmp_path_factory):
+    import pandas as pd
+
+    root = tmp_path_factory.mktemp("avmnist_files")
+    audio = torch.from_numpy(gold["audio"]).view(torch.float32)
+    rows = []
+    for i, lab in enumerate(gold["labels"]):
+        pa, pi = str(root / f"a{i}.pt"), str(root / f"i{i}.pt")
+        torch.save(audio[i].clone(), pa)
+        torch.save(gold["image"][i].copy(), pi)
+        rows.append({"audio": pa, "image": pi, "label": int(lab)})
+    path = str(root / "data.csv")
+    pd.DataFrame(rows).to_csv(path, index=False)
+    return path
+
+
+def _masks(gold, prefix):
+    out = {}
+    for k in gold.files:
+        if k.startswith(prefix + "_masks_"):
+            pat, mod = k[len(prefix) + 7:].split("_")
+            out.setdefault(pat, {})[mod] = torch.from_numpy(gold[k])
+    return out
+
+
+def _bits(t: torch.Tensor) -> np.ndarray:
+    return t.contiguous().view(torch.int32).numpy()
+
+
+def _check_items(gold, prefix, items, ds):
+    """Modality entries are keyed by ``modalities.Modality`` members when that package is importable, else by name: ``ds.keys``."""
+    assert [str(k) for k in items[0].keys()] == list(gold[f"{prefix}_keys"])
+    assert [int(it["labels"]) for it in items] == list(gold[f"{prefix}_labels"])
+    assert [it["sample_idx"] for it in items] == list(gold[f"{prefix}_sample_idx"])
+    assert [it["pattern_name"] for it in items] == list(gold[f"{prefix}_pattern"])
+    for it in items:
+        assert it["labels"].dtype == torch.long and it["labels"].dim() == 0 and it["missing_mask"] == {}
+    for mod in ("audio", "image"):
+        assert [float(it[f"{mod}_missing_index"]) for it in items] == list(gold[f"{prefix}_{mod}_missing_index"])
+        if f"{prefix}_{mod}" not in gold.files:
+            assert ds.keys[mod] not in items[0] and f"{mod}_original" not in items[0]
+            continue
+        for suffix, key in (("", ds.keys[mod]), ("_original", f"{mod}_original"), ("_reverse", f"{mod}_reverse")):
+            got = torch.stack([it[key] for it in items])
+            assert got.dtype == torch.float32
+            want = gold[f"{prefix}_{mod}{suffix}"]
+            assert got.shape == want.shape, (mod, suffix, got.shape, want.shape)
+            assert np.array_equal(_bits(got), want), (prefix, mod, suffix)
+
+
+def test_validation_items_collate_and_pattern_batches(gold, csv):
+    ds = AVMNIST(csv, "valid", cmap=gold["table"], masks=_masks(gold, "valid"))
+    assert len(ds) == 15 and ds.selected_patterns == ["a", "ai", "i"] and ds.get_full_modality() == "ai" and ds.num_samples == 5
+    items = [ds[i] for i in range(len(ds))]
+    _check_items(gold, "valid", items, ds)
+    with pytest.raises(IndexError):
+        ds[15]
+    for k, lo in enumerate((0, 7)):
+        c = ds.collate_fn(items[lo:lo + 7])
+        assert [str(x) for x in c.keys()] == list(gold[f"valid_collate{k}_keys"]) and c["missing_masks"] == {}
+        assert np.array_equal(c["labels"].numpy(), gold[f"valid_collate{k}_labels"])
+        assert c["pattern_name"] == list(gold[f"valid_collate{k}_pattern"])
+        assert np.array_equal(_bits(c[ds.keys["audio"]]), gold[f"valid_collate{k}_audio"])
+        assert np.array_equal(_bits(c[ds.keys["image"]]), gold[f"valid_collate{k}_image"])
+    loaders = ds.get_pattern_batches(2)
+    assert list(loaders) == ["a", "ai", "i"]
+    for pat, loader in loaders.items():
+        assert isinstance(loader.dataset, PatternSpecificDataset) and len(loader.dataset) == 5
+        bs = list(loader)
+        assert [len(b["labels"]) for b in bs] == list(gold[f"valid_pb_{pat}_sizes"])
+        assert np.array_equal(torch.cat([b["labels"] for b in bs]).numpy(), gold[f"valid_pb_{pat}_labels"])
+        assert np.array_equal(_bits(torch.cat([b[ds.keys["audio"]] for b in bs])), gold[f"valid_pb_{pat}_audio"])
+        assert np.array_equal(_bits(torch.cat([b[ds.keys["image"]] for b in bs])), gold[f"valid_pb_{pat}_image"])
+        assert sum((b["pattern_name"] for b in bs), []) == list(gold[f"valid_pb_{pat}_pattern"])
+
+
+def test_training_items_pick_the_pattern_like_the_reference(gold, csv):
+    mp = {"ai": {"audio": 0.6, "image": 1.0}, "i": {"audio": 0.0, "image": 1.0}}
+    ds = AVMNIST(csv, "train", missing_patterns=mp, selected_patterns=["ai", "i"], cmap=gold["table"], masks=_masks(gold, "train"))
+    assert len(ds) == 5
+    random.seed(3)  # base_dataset.py:87-89 draws from Python's global generator
+    _check_items(gold, "train", [ds[i] for i in (4, 0, 2, 2, 1, 3)], ds)
+    with pytest.raises(ValueError):
+        ds.get_pattern_batches(2)
+
+
+def test_monomodal_split_and_split_indices(gold, csv):
+    ds = AVMNIST(csv, "test", "audio", selected_patterns=["ai"], masks=_masks(gold, "testa"))  # no colour table needed without images
+    assert len(ds) == 5 and ds.image_u8 is None
+    items = [ds[i] for i in range(len(ds))]
+    _check_items(gold, "testa", items, ds)
+    c = ds.collate_fn(items)
+    assert [str(x) for x in c.keys()] == list(gold["testa_collate_keys"])
+    assert np.array_equal(_bits(c[ds.keys["audio"]]), gold["testa_collate_audio"])
+    sub = AVMNIST(csv, "valid", selected_patterns=["i"], split_indices=[4, 1, 2], cmap=gold["table"], masks=_masks(gold, "sub"))
+    assert len(sub) == 3
+    _check_items(gold, "sub", [sub[i] for i in range(3)], sub)
+
+
+def test_constructor_errors(gold, csv, tmp_path):
+    with pytest.raises(FileNotFoundError):
+        AVMNIST(str(tmp_path / "nope.csv"), "train", cmap=gold["table"])
+    with pytest.raises(AssertionError):
+        AVMNIST(csv, "validation", cmap=gold["table"])
+    with pytest.raises(ValueError, match="Invalid patterns"):
+        AVMNIST(csv, "valid", selected_patterns=["x"], cmap=gold["table"])
+    with pytest.raises(ValueError, match="Missing required columns"):
+        AVMNIST(csv, "valid", labels_column="digit", cmap=gold["table"])
+    with pytest.raises(ValueError, match="colour table"):
+        AVMNIST(csv, "valid", cmap=np.zeros((16, 3)))
+    bad = tmp_path / "f.pt"
+    torch.save(np.zeros((3, 3), dtype=np.float32), str(bad))
+    import pandas as pd
+
+    df = pd.read_csv(csv)
+    df.loc[1, "image"] = str(bad)
+    p = str(tmp_path / "bad.csv")
+    df.to_csv(p, index=False)
+    with pytest.raises(TypeError, match="uint8"):
+        AVMNIST(p, "valid", cmap=gold["table"])
+
+
+@pytest.mark.parametrize("image_form", ["u8", "f32"])
+def test_batches_equal_the_item_path(gold, csv, image_form):
+    """Evaluation order = dataset index order; tensors = the items' ORIGINAL tensors + masks (the multiply runs on the device)."""
+    ds = AVMNIST(csv, "valid", cmap=gold["table"], masks=_masks(gold, "valid"), pin=False)
+    items = [ds[i] for i in range(len(ds))]
+    got = []
+    for b in ds.batches(4, image_form=image_form, rotate=1):
+        got.append({k: (v.clone() if torch.is_tensor(v) else v) for k, v in b.items()})
+    assert [len(b["labels"]) for b in got] == [4, 4, 4, 3]
+    assert sum((b["pattern_name"] for b in got), []) == [it["pattern_name"] for it in items]
+    cat = {k: torch.cat([b[k] for b in got]) for k in got[0] if k != "pattern_name"}
+    assert cat["labels"].tolist() == [int(it["labels"]) for it in items] and cat["labels"].dtype == torch.long
+    assert cat["sample_idx"].tolist() == [it["sample_idx"] for it in items]
+    assert np.array_equal(_bits(cat["audio_original"]), _bits(torch.stack([it["audio_original"] for it in items])))
+    for mod in ("audio", "image"):
+        assert cat[f"{mod}_missing_index"].dtype == torch.float32
+        assert cat[f"{mod}_missing_index"].tolist() == [float(it[f"{mod}_missing_index"]) for it in items]
+    want_img = torch.stack([it["image_original"] for it in items])
+    if image_form == "u8":
+        assert cat["image_original"].dtype == torch.uint8 and cat["image_original"].shape == want_img.shape
+        assert torch.equal(ds.lut[cat["image_original"].long()], want_img)  # what mml_stage_u8_lut_f32 computes on the device
+    else:
+        assert torch.equal(cat["image_original"], want_img)
+    # x * mask of the reference == ORIGINAL * missing_index of the batch path
+    masked = cat["audio_original"] * cat["audio_missing_index"].reshape(-1, 1, 1)
+    assert np.array_equal(_bits(masked), _bits(torch.stack([it[ds.keys["audio"]] for it in items])))
+    one = list(ds.batches(8, pattern="ai", drop_last=True))
+    assert len(one) == 0 and [b["pattern_name"] for b in ds.batches(5, pattern="ai")] == [["ai"] * 5]
+
+
+def test_training_batches_visit_every_sample_once(gold, csv):
+    mp = {"ai": {"audio": 0.6, "image": 1.0}, "i": {"audio": 0.0, "image": 1.0}}
+    g = torch.Generator().manual_seed(5)
+    ds = AVMNIST(csv, "train", missing_patterns=mp, selected_patterns=["ai", "i"], cmap=gold["table"], generator=g, pin=False)
+    assert set(ds.masks) == {"ai", "i"} and all(v.shape == (5,) for t in ds.masks.values() for v in t.values())
+    assert not ds.masks["i"]["audio"].any() and ds.masks["ai"]["image"].all()
+    seen, n_batches = [], 0
+    for b in ds.batches(2, drop_last=False):
+        n_batches += 1
+        for j, (i, pat) in enumerate(zip(b["sample_idx"].tolist(), b["pattern_name"])):
+            seen.append(i)
+            assert b["audio_missing_index"][j] == ds.masks[pat]["audio"][i] and b["image_missing_index"][j] == ds.masks[pat]["image"][i]
+            assert torch.equal(b["audio_original"][j], ds.audio[i]) and torch.equal(b["image_original"][j, 0], ds.image_u8[i])
+            assert int(b["labels"][j]) == int(gold["labels"][i])
+    assert n_batches == 3 and sorted(seen) == [0, 1, 2, 3, 4]
+    assert [len(b["labels"]) for b in ds.batches(2, drop_last=True)] == [2, 2]
+    assert [b["sample_idx"].tolist() for b in ds.batches(5, shuffle=False, pattern="i")] == [[0, 1, 2, 3, 4]]
+    # staging buffers rotate: with rotate=2 the third batch reuses the first batch's storage
+    bs = []
+    for b in ds.batches(2, shuffle=False, rotate=2):
+        bs.append(b["audio_original"])
+    assert bs[0].data_ptr() != bs[1].data_ptr() and bs[0][:1].data_ptr() == bs[2].data_ptr()
