@@ -1,4 +1,4 @@
-"""Generate tests/golden/avmnist_loader.npz from the UNMODIFIED reference dataset class.  Run in the build container only.
+"""Generate tests/golden/avmnist_loader.npz and mosi_loader.npz from the UNMODIFIED reference dataset classes.  Run in the build container only.
 
     python oracle/make_golden_loader.py
 
@@ -149,6 +149,96 @@ def main() -> None:
 
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     path = os.path.join(GOLDEN_DIR, "avmnist_loader.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays,", len(drawn), "mask draws")
+    mosi_case(ns, RB)
+
+
+MOSI_N, MOSI_T, MOSI_F = 4, 6, {"audio": 3, "vision": 4, "text": 8}
+
+
+def mosi_raw():
+    """{split: {...}} in the pickle layout data/mosi.py:118-158 reads: zero-padded [N, T, F] float arrays, labels, lengths."""
+    rng = np.random.default_rng(99)
+    raw = {}
+    for split, n in (("train", MOSI_N), ("valid", MOSI_N - 1), ("test", 2)):
+        d = {}
+        lengths = rng.integers(2, MOSI_T + 1, size=n)
+        for k, f in MOSI_F.items():
+            x = rng.normal(size=(n, MOSI_T, f)).astype(np.float32)
+            for i, ln in enumerate(lengths):
+                x[i, ln:] = 0.0
+            d[k] = x
+        d["classification_labels"] = rng.integers(0, 3, size=n)
+        d["regression_labels"] = rng.normal(size=n).astype(np.float32)
+        d["audio_lengths"], d["vision_lengths"] = lengths.copy(), lengths.copy()
+        raw[split] = d
+    return raw
+
+
+def mosi_items(prefix: str, items, M, out: dict) -> None:
+    out[f"{prefix}_label"] = torch.stack([it["label"] for it in items]).numpy()
+    out[f"{prefix}_sample_idx"] = np.array([int(it["sample_idx"]) for it in items], dtype=np.int64)
+    out[f"{prefix}_pattern"] = np.array([it["pattern_name"] for it in items])
+    out[f"{prefix}_keys"] = np.array([str(k) for k in items[0].keys()])
+    if "audio_length" in items[0]:
+        out[f"{prefix}_audio_length"] = np.array([float(it["audio_length"]) for it in items], dtype=np.float32)
+        out[f"{prefix}_video_length"] = np.array([float(it["video_length"]) for it in items], dtype=np.float32)
+    for mod, m in (("audio", M.AUDIO), ("video", M.VIDEO), ("text", M.TEXT)):
+        out[f"{prefix}_{mod}_missing_index"] = np.array([float(it[f"{mod}_missing_index"]) for it in items], dtype=np.float32)
+        if m in items[0]:
+            for suffix, key in (("", m), ("_original", f"{mod}_original"), ("_reverse", f"{mod}_reverse")):
+                out[f"{prefix}_{mod}{suffix}"] = torch.stack([it[key] for it in items]).contiguous().view(torch.int32).numpy()
+
+
+def mosi_case(ns, RB) -> None:
+    """tests/golden/mosi_loader.npz from the unmodified ``data.mosi.MOSI`` (MML_Suite/data/mosi.py:17-301)."""
+    import pickle
+
+    import data.mosi as RM
+
+    M = ns.Modality
+    raw = mosi_raw()
+    drawn = []
+
+    def create_missing_mask(n_modalities, batch_size, missing_rates):
+        g = torch.Generator().manual_seed(2000 + len(drawn))
+        keep = 1.0 - torch.tensor(list(missing_rates), dtype=torch.float32)
+        m = torch.bernoulli(keep.expand(batch_size, n_modalities).contiguous(), generator=g)
+        drawn.append(m)
+        return m
+
+    RB.create_missing_mask = create_missing_mask
+    out = {}
+    for split, d in raw.items():
+        for k, v in d.items():
+            out[f"raw_{split}_{k}"] = np.asarray(v)
+
+    def masks_of(ds, prefix):
+        for pat, tab in ds.masks.items():
+            for m, v in tab.items():
+                out[f"{prefix}_masks_{pat}_{m}"] = v.numpy().astype(np.float32)
+
+    with tempfile.TemporaryDirectory() as root:
+        fp = os.path.join(root, "mosi.pkl")
+        with open(fp, "wb") as f:
+            pickle.dump(raw, f)
+        # (1) validation split, all seven patterns, unaligned (lengths in the items)
+        ds = RM.MOSI(fp, "valid")
+        assert len(ds) == 7 * (MOSI_N - 1) and ds.selected_patterns == ["a", "at", "atv", "av", "t", "tv", "v"]
+        masks_of(ds, "valid")
+        mosi_items("valid", [ds[i] for i in range(len(ds))], M, out)
+        # (2) training split: audio present with P = 0.8 in the full pattern (the MOSI YAMLs' audio rate 0.2), pattern per item from ``random``
+        mp = {"atv": {M.AUDIO: 0.8, M.TEXT: 1.0, M.VIDEO: 1.0}, "t": {M.AUDIO: 0.0, M.TEXT: 1.0, M.VIDEO: 0.0}}
+        ds = RM.MOSI(fp, "train", missing_patterns=mp, selected_patterns=["atv", "t"], aligned=True, length=MOSI_T)
+        masks_of(ds, "train")
+        random.seed(5)
+        mosi_items("train", [ds[i] for i in (3, 0, 1, 1, 2)], M, out)
+        # (3) monomodal test split with regression labels
+        ds = RM.MOSI(fp, "test", M.TEXT, selected_patterns=["atv"], labels_key="regression_labels")
+        masks_of(ds, "testt")
+        mosi_items("testt", [ds[i] for i in range(len(ds))], M, out)
+    path = os.path.join(GOLDEN_DIR, "mosi_loader.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays,", len(drawn), "mask draws")
 

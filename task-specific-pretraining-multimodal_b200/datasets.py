@@ -19,6 +19,10 @@ labels int64 ``[N]`` -- plus the mask table ``[pattern][modality][len(self)]``. 
   and ``fused_loader()`` = ``DevicePrefetcher(batches(), luts={"image_original": lut})``: 1 byte per image pixel over PCIe, table
   lookup on the copy stream (``mml_stage_u8_lut_f32``).
 
+``MOSI`` / ``MOSEI`` (``MML_Suite/data/mosi.py:17-301``, one pickle of padded ``[N, T, F]`` arrays per split) get the same two views.  The
+MMIMDb loader reads HDF5 through ``h5py``, which this image does not have: not built (its batches are plain ``[B, 4096]`` / ``[B, 300]``
+tensors; ``DevicePrefetcher`` takes them as they are).
+
 Mask *sampling* follows ``data.draw_missing_masks`` (independent Bernoulli(P(present)); the reference's generator lives in the
 un-vendored ``modalities`` package) or is handed in (``masks=``: e.g. ``DeviceMaskTable(...).masks`` copied back, or
 the table of a reference run).
@@ -39,15 +43,15 @@ from .data import draw_missing_masks, luma_lut
 NAMES = ("audio", "image")
 
 
-def _modality_keys() -> Dict[str, Any]:
+def _modality_keys(names: Sequence[str] = ("audio", "image")) -> Dict[str, Any]:
     """``modalities.Modality`` members when the package is importable (the reference's batch keys), else the lower-case names
     (``str(Modality.AUDIO) == "audio"``, so the ``<mod>_original`` / ``<mod>_missing_index`` keys are the same either way)."""
     try:
         from modalities import Modality  # type: ignore
 
-        return {"audio": Modality.AUDIO, "image": Modality.IMAGE, "multimodal": Modality.MULTIMODAL}
+        return {n: Modality.from_str(n) for n in tuple(names) + ("multimodal",)}
     except Exception:
-        return {"audio": "audio", "image": "image", "multimodal": "multimodal"}
+        return {n: n for n in tuple(names) + ("multimodal",)}
 
 
 def _name(modality: Any) -> str:
@@ -76,21 +80,23 @@ def _maybe_pin(t: torch.Tensor, pin: bool) -> torch.Tensor:
     return t.pin_memory() if pin else t
 
 
-class AVMNIST(Dataset):
-    """Same constructor and item / batch contract as ``data.avmnist.AVMNIST`` (data/avmnist.py:45-59), plus ``cmap`` (colour table),
-    ``masks`` (explicit mask table), ``generator`` (mask draw / batch shuffling) and ``pin`` (default: pinned iff CUDA is available)."""
+class _PatternDataset(Dataset):
+    """What the reference keeps in ``MultimodalBaseDataset`` (data/base_dataset.py:16-154) -- splits, pattern names, the mask table, the
+    index -> (pattern, sample) rule -- plus the staging machinery of the batch-granular path.  Subclasses set ``MODS`` (modality names
+    in ``AVAILABLE_MODALITIES`` order), ``DEFAULT_PATTERNS`` and store their arrays."""
 
-    NUM_CLASSES: int = 10
     VALID_SPLITS: List[str] = ["train", "valid", "test"]
-    AVAILABLE_MODALITIES: Dict[str, Any] = {"audio": "audio", "image": "image"}
+    MODS: tuple = ()
+    DEFAULT_PATTERNS: Dict[str, Dict[str, float]] = {}
+    AVAILABLE_MODALITIES: Dict[str, Any] = {}
 
-    @staticmethod
-    def get_full_modality() -> str:
-        return "".join(sorted(k[0] for k in AVMNIST.AVAILABLE_MODALITIES))
+    @classmethod
+    def get_full_modality(cls) -> str:
+        return "".join(sorted(k[0] for k in cls.MODS))
 
     @classmethod
     def get_all_possible_patterns(cls) -> List[str]:
-        mods = list(cls.AVAILABLE_MODALITIES.keys())
+        mods = list(cls.MODS)
         return sorted("".join(m[0] for m in sorted(c)) for r in range(1, len(mods) + 1) for c in combinations(mods, r))
 
     def validate_patterns(self, patterns: Sequence[str]) -> List[str]:
@@ -98,6 +104,211 @@ class AVMNIST(Dataset):
         if bad:
             raise ValueError(f"Invalid patterns: {bad}\nValid patterns are: {self.get_all_possible_patterns()}")
         return list(patterns)
+
+    def _configure(self, split, target_modality, missing_patterns, selected_patterns, _id=1) -> None:
+        self.split = str(split).lower()
+        assert split in self.VALID_SPLITS, f"Invalid split provided, must be one of {self.VALID_SPLITS}"
+        assert isinstance(_id, int), "ID must be an integer."
+        self._id = _id
+        self.keys = _modality_keys(self.MODS)
+        self.AVAILABLE_MODALITIES = {n: self.keys[n] for n in self.MODS}
+        # pattern -> {modality name: P(present)}
+        mp = missing_patterns or self.DEFAULT_PATTERNS
+        self.missing_patterns = {pat: {_name(m): float(p) for m, p in probs.items()} for pat, probs in mp.items()}
+        self.selected_patterns = self.validate_patterns(selected_patterns) if selected_patterns is not None else self.get_all_possible_patterns()
+        for pat in self.selected_patterns:
+            if pat not in self.missing_patterns:
+                raise ValueError(f"selected pattern {pat!r} has no entry in missing_patterns {list(self.missing_patterns)}")
+        self.current_pattern = None
+        tm = _name(target_modality)
+        assert tm in self.MODS + ("multimodal",), f"Invalid modality provided, must be one of {list(self.MODS) + ['multimodal']}"
+        self.target_modality = self.keys[tm]
+        self._target = tm
+
+    def _loads(self, m: str) -> bool:
+        return self._target in ("multimodal", m)
+
+    def _finish(self, num_samples: int, masks, generator, pin) -> None:
+        """Mask table (given or drawn) once ``num_samples`` is known."""
+        self.num_samples = int(num_samples)
+        self.pattern_indices = {pattern: list(range(self.num_samples)) for pattern in self.selected_patterns}
+        self._pin = torch.cuda.is_available() if pin is None else bool(pin)
+        if masks is not None:
+            self.masks = {pat: {_name(m): torch.as_tensor(v, dtype=torch.float32).reshape(-1) for m, v in tab.items()} for pat, tab in masks.items()}
+            for pat in self.missing_patterns:
+                for m in self.MODS:
+                    if pat not in self.masks or m not in self.masks[pat] or self.masks[pat][m].numel() < self.num_samples:
+                        raise ValueError(f"masks[{pat!r}][{m!r}] must hold at least {self.num_samples} entries")
+        else:
+            # one draw per (pattern, modality, dataset index) at construction, length len(self) like base_dataset.py:46-59
+            self.masks = draw_missing_masks(self.missing_patterns, len(self), generator)
+        self.generator = generator
+        # [pattern][modality][sample] as one tensor for the vectorised batch path
+        self._pat_index = {pat: i for i, pat in enumerate(self.missing_patterns)}
+        self._mask_table = torch.stack([torch.stack([self.masks[pat][m][: self.num_samples] for m in self.MODS]) for pat in self.missing_patterns])
+
+    def __len__(self) -> int:
+        return self.num_samples if self.split == "train" else self.num_samples * len(self.selected_patterns)
+
+    def _get_pattern_and_sample_idx(self, idx: int):
+        if self.split == "train" or self.split == "trn":
+            return random.choice(self.selected_patterns), idx  # base_dataset.py:87-89: Python's global ``random``
+        return self.selected_patterns[idx // self.num_samples], idx % self.num_samples
+
+    def _item_head(self, idx: int):
+        pattern, i = self._get_pattern_and_sample_idx(int(idx))
+        if not 0 <= i < self.num_samples:
+            raise IndexError(idx)
+        self.current_pattern = pattern
+        return pattern, i
+
+    @staticmethod
+    def _masked(sample: Dict[Any, Any], key: Any, m: str, original: torch.Tensor) -> None:
+        """``get_samples`` (base_dataset.py:61-74): original, original * mask and the complementary ``_reverse`` tensor."""
+        mask = sample[f"{m}_missing_index"]
+        sample[f"{m}_original"] = original
+        sample[key] = original * mask
+        sample[f"{m}_reverse"] = original * -1 * (mask - 1)
+
+    def get_split(self) -> str:
+        return self.split
+
+    def get_selected_patterns(self) -> List[str]:
+        return self.selected_patterns
+
+    def get_missing_patterns(self):
+        return self.missing_patterns
+
+    # ---- batch-granular machinery ------------------------------------------------------------------------------------------
+    def _epoch(self, batch_size: int, shuffle: Optional[bool], drop_last: bool, pattern: Optional[str], generator, rotate: int):
+        """(staging set, rows int64 [B], pattern names, masks fp32 [B, n_modalities]) per batch.
+
+        Order: the training split visits every sample once (shuffled unless ``shuffle=False``) with an independent uniformly drawn
+        pattern per sample (the vectorised form of ``random.choice``, base_dataset.py:87-89; drawn from ``generator``, not from
+        Python's ``random``); the other splits walk ``selected_patterns`` in order, all samples of one pattern after the other --
+        dataset index order, base_dataset.py:90-93 -- or only ``pattern``."""
+        if batch_size < 1 or rotate < 1:
+            raise ValueError("batch_size and rotate must be positive")
+        gen = generator if generator is not None else self.generator
+        train = self.split == "train"
+        if shuffle is None:
+            shuffle = train
+        N = self.num_samples
+        if train:
+            if pattern is not None:
+                pats = torch.full((N,), self.selected_patterns.index(pattern), dtype=torch.long)
+            else:
+                pats = torch.randint(len(self.selected_patterns), (N,), generator=gen)
+            rows = torch.randperm(N, generator=gen) if shuffle else torch.arange(N)
+            pats = pats[rows] if shuffle else pats
+        else:
+            which = [self.selected_patterns.index(pattern)] if pattern is not None else range(len(self.selected_patterns))
+            rows = torch.cat([torch.arange(N) for _ in which]) if len(which) else torch.empty(0, dtype=torch.long)
+            pats = torch.cat([torch.full((N,), k, dtype=torch.long) for k in which]) if len(which) else rows
+            if shuffle:
+                perm = torch.randperm(rows.numel(), generator=gen)
+                rows, pats = rows[perm], pats[perm]
+        table_row = torch.tensor([self._pat_index[p] for p in self.selected_patterns], dtype=torch.long)
+        bufs: List[Dict[str, torch.Tensor]] = [dict() for _ in range(rotate)]
+        total = rows.numel()
+        stop = total - (total % batch_size) if drop_last else total
+        for n, lo in enumerate(range(0, stop, batch_size)):
+            r, p = rows[lo:lo + batch_size], pats[lo:lo + batch_size]
+            yield bufs[n % rotate], r, [self.selected_patterns[k] for k in p.tolist()], self._mask_table[table_row[p], :, r]
+
+    def _staging(self, buf: Dict[str, torch.Tensor], key: str, shape, dtype) -> torch.Tensor:
+        """View of ``shape`` on the pinned buffer ``buf[key]`` (allocated once at the largest leading dimension seen: the ragged last
+        batch of an epoch reuses the full-size buffer)."""
+        shape = tuple(shape)
+        t = buf.get(key)
+        if t is None or t.shape[1:] != torch.Size(shape[1:]) or t.dtype != dtype or t.shape[0] < shape[0]:
+            t = buf[key] = _maybe_pin(torch.empty(shape, dtype=dtype), self._pin)
+        return t[: shape[0]]
+
+    def _gather(self, buf: Dict[str, torch.Tensor], key: str, src: Optional[torch.Tensor], rows: torch.Tensor) -> torch.Tensor:
+        """rows of ``src`` (or ``rows`` itself when ``src`` is None) into the pinned staging tensor ``buf[key]``."""
+        if src is None:
+            t = self._staging(buf, key, rows.shape, rows.dtype)
+            t.copy_(rows)
+            return t
+        t = self._staging(buf, key, (rows.numel(),) + tuple(src.shape[1:]), src.dtype)
+        torch.index_select(src, 0, rows, out=t)
+        return t
+
+    def batches(self, batch_size: int, **kwargs) -> Iterator[Dict[Any, Any]]:  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def _luts(self, kwargs) -> Optional[Dict[Any, torch.Tensor]]:
+        return None
+
+    def background_batches(self, batch_size: int, ahead: int = 2, **kwargs) -> Iterator[Dict[Any, Any]]:
+        """``batches()`` produced by a worker thread, ``ahead`` batches in front of the consumer (the row gathers are ``index_select``
+        calls that release the GIL, so they overlap the step's host code instead of adding 1.4-3.3 ms per 256-sample AVMNIST batch to
+        it).  ``rotate`` defaults to ``ahead + 3`` staging sets: ``ahead`` queued, one being filled, one with the consumer, one spare."""
+        import queue
+        import threading
+
+        kwargs.setdefault("rotate", ahead + 3)
+        if kwargs["rotate"] < ahead + 2:
+            raise ValueError("rotate must be at least ahead + 2 (queued batches + the one being filled + the one in use)")
+        q: "queue.Queue" = queue.Queue(maxsize=max(1, int(ahead)))
+        stop = threading.Event()
+        done = object()
+
+        def put(item) -> bool:
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
+
+        def work():
+            try:
+                for b in self.batches(batch_size, **kwargs):
+                    if not put(b):
+                        return
+                put(done)
+            except BaseException as e:  # surfaced in the consumer
+                put(e)
+
+        t = threading.Thread(target=work, name="mml-batches", daemon=True)
+        t.start()
+        try:
+            while True:
+                b = q.get()
+                if b is done:
+                    return
+                if isinstance(b, BaseException):
+                    raise b
+                yield b
+        finally:
+            stop.set()
+            t.join(timeout=5.0)
+
+    def fused_loader(self, device, batch_size: int, depth: int = 1, ahead: int = 2, **kwargs):
+        """``batches()`` (on a worker thread when ``ahead`` > 0) behind the device prefetcher; the result feeds the fused
+        ``train_step / validation_step`` of the matching model directly.  AVMNIST: uint8 images cross PCIe as bytes and are expanded
+        through the luminance table on the copy stream.  Staging sets: ``ahead`` + ``depth`` + 3 (queued + staged on the copy stream +
+        filling / in use / spare)."""
+        from .data import DevicePrefetcher
+
+        kwargs.setdefault("rotate", ahead + depth + 3)
+        luts = self._luts(kwargs)
+        it = self.background_batches(batch_size, ahead=ahead, **kwargs) if ahead > 0 else self.batches(batch_size, **kwargs)
+        return DevicePrefetcher(it, device, depth=depth, luts=luts)
+
+
+class AVMNIST(_PatternDataset):
+    """Same constructor and item / batch contract as ``data.avmnist.AVMNIST`` (data/avmnist.py:45-59), plus ``cmap`` (colour table),
+    ``masks`` (explicit mask table), ``generator`` (mask draw / batch shuffling) and ``pin`` (default: pinned iff CUDA is available)."""
+
+    NUM_CLASSES: int = 10
+    MODS = NAMES
+    AVAILABLE_MODALITIES: Dict[str, Any] = {"audio": "audio", "image": "image"}
+    # the reference's default (data/avmnist.py:73-77)
+    DEFAULT_PATTERNS = {"ai": {"audio": 1.0, "image": 1.0}, "a": {"audio": 1.0, "image": 0.0}, "i": {"audio": 0.0, "image": 1.0}}
 
     def __init__(self, data_fp: Union[str, Path], split: str, target_modality: Any = "multimodal", *,
                  missing_patterns: Optional[Mapping[str, Mapping[Any, float]]] = None, selected_patterns: Optional[Sequence[str]] = None,
@@ -118,10 +329,9 @@ class AVMNIST(Dataset):
         missing_columns = [c for c in (audio_column, image_column, labels_column) if c not in self.data.columns]
         if missing_columns:
             raise ValueError(f"Missing required columns: {missing_columns}")
-        tm = self._target
         labels = torch.from_numpy(np.array(self.data[labels_column].to_numpy(), dtype=np.int64))
-        audio = self._read_audio(self.data[audio_column]) if tm in ("audio", "multimodal") else None
-        image = self._read_images(self.data[image_column]) if tm in ("image", "multimodal") else None
+        audio = self._read_audio(self.data[audio_column]) if self._loads("audio") else None
+        image = self._read_images(self.data[image_column]) if self._loads("image") else None
         self._store(labels, audio, image, cmap, masks, generator, pin)
 
     @classmethod
@@ -134,13 +344,12 @@ class AVMNIST(Dataset):
         self._configure(split, target_modality, missing_patterns, selected_patterns, _id)
         self.data_fp = self.data = None
         labels = torch.as_tensor(labels, dtype=torch.long).reshape(-1).clone()
-        tm = self._target
         a = i = None
-        if tm in ("audio", "multimodal"):
+        if self._loads("audio"):
             a = torch.as_tensor(audio, dtype=torch.float32).contiguous()
             if a.dim() != 3 or a.shape[0] != labels.numel():
                 raise ValueError(f"audio must be [N, H, W] with N = {labels.numel()}, got {tuple(a.shape)}")
-        if tm in ("image", "multimodal"):
+        if self._loads("image"):
             i = torch.as_tensor(image_u8)
             if i.dtype != torch.uint8 or i.dim() != 3 or i.shape[0] != labels.numel():
                 raise TypeError(f"image_u8 must be uint8 [N, h, w] with N = {labels.numel()}, got {i.dtype} {tuple(i.shape)}")
@@ -148,50 +357,14 @@ class AVMNIST(Dataset):
         self._store(labels, a, i, cmap, masks, generator, pin)
         return self
 
-    def _configure(self, split, target_modality, missing_patterns, selected_patterns, _id) -> None:
-        self.split = str(split).lower()
-        assert split in self.VALID_SPLITS, f"Invalid split provided, must be one of {self.VALID_SPLITS}"
-        assert isinstance(_id, int), "ID must be an integer."
-        self._id = _id
-        self.keys = _modality_keys()
-        self.AVAILABLE_MODALITIES = {n: self.keys[n] for n in NAMES}
-        # pattern -> {modality name: P(present)}; the default is the reference's (data/avmnist.py:73-77)
-        mp = missing_patterns or {"ai": {"audio": 1.0, "image": 1.0}, "a": {"audio": 1.0, "image": 0.0}, "i": {"audio": 0.0, "image": 1.0}}
-        self.missing_patterns = {pat: {_name(m): float(p) for m, p in probs.items()} for pat, probs in mp.items()}
-        self.selected_patterns = self.validate_patterns(selected_patterns) if selected_patterns is not None else self.get_all_possible_patterns()
-        for pat in self.selected_patterns:
-            if pat not in self.missing_patterns:
-                raise ValueError(f"selected pattern {pat!r} has no entry in missing_patterns {list(self.missing_patterns)}")
-        self.current_pattern = None
-        tm = _name(target_modality)
-        assert tm in ("audio", "image", "multimodal"), "Invalid modality provided, must be one of [audio, image, multimodal]"
-        self.target_modality = self.keys[tm]
-        self._target = tm
-
     def _store(self, labels, audio, image_u8, cmap, masks, generator, pin) -> None:
-        self.num_samples = int(labels.numel())
-        self.pattern_indices = {pattern: list(range(self.num_samples)) for pattern in self.selected_patterns}
-        pin = torch.cuda.is_available() if pin is None else bool(pin)
-        self._pin = pin
-        self.labels = _maybe_pin(labels, pin)
-        self.audio = _maybe_pin(audio, pin) if audio is not None else None
+        self._finish(labels.numel(), masks, generator, pin)
+        self.labels = _maybe_pin(labels, self._pin)
+        self.audio = _maybe_pin(audio, self._pin) if audio is not None else None
         self.image_u8 = self.lut = None
         if image_u8 is not None:
             self.lut = luma_lut(_colour_table(cmap))  # fp32 [256]: the reference's image chain as a function of the pixel value
-            self.image_u8 = _maybe_pin(image_u8, pin)
-        if masks is not None:
-            self.masks = {pat: {_name(m): torch.as_tensor(v, dtype=torch.float32).reshape(-1) for m, v in tab.items()} for pat, tab in masks.items()}
-            for pat in self.missing_patterns:
-                for m in NAMES:
-                    if pat not in self.masks or m not in self.masks[pat] or self.masks[pat][m].numel() < self.num_samples:
-                        raise ValueError(f"masks[{pat!r}][{m!r}] must hold at least {self.num_samples} entries")
-        else:
-            # one draw per (pattern, modality, dataset index) at construction, length len(self) like base_dataset.py:46-59
-            self.masks = draw_missing_masks(self.missing_patterns, len(self), generator)
-        self.generator = generator
-        # [pattern][modality][sample] as one tensor for the vectorised batch path
-        self._pat_index = {pat: i for i, pat in enumerate(self.missing_patterns)}
-        self._mask_table = torch.stack([torch.stack([self.masks[pat][m][: self.num_samples] for m in NAMES]) for pat in self.missing_patterns])
+            self.image_u8 = _maybe_pin(image_u8, self._pin)
 
     # ---- file reading (once) ------------------------------------------------------------------------------------------
     @staticmethod
@@ -221,33 +394,18 @@ class AVMNIST(Dataset):
         return torch.from_numpy(np.stack(items)).contiguous()
 
     # ---- reference item / batch contract ----------------------------------------------------------------------------------
-    def __len__(self) -> int:
-        return self.num_samples if self.split == "train" else self.num_samples * len(self.selected_patterns)
-
-    def _get_pattern_and_sample_idx(self, idx: int):
-        if self.split == "train" or self.split == "trn":
-            return random.choice(self.selected_patterns), idx  # base_dataset.py:87-89: Python's global ``random``
-        return self.selected_patterns[idx // self.num_samples], idx % self.num_samples
-
     def image_float(self, rows) -> torch.Tensor:
         """fp32 [n, 1, h, w] images of ``rows`` = ``_load_image`` of the reference for each of them (table lookup on the host)."""
         return self.lut[self.image_u8[rows].long()].unsqueeze(-3)
 
     def __getitem__(self, idx: int) -> Dict[Any, Any]:
-        pattern, i = self._get_pattern_and_sample_idx(int(idx))
-        if not 0 <= i < self.num_samples:
-            raise IndexError(idx)
-        self.current_pattern = pattern
+        pattern, i = self._item_head(idx)
         sample: Dict[Any, Any] = {"labels": self.labels[i].clone(), "pattern_name": pattern, "missing_mask": {}, "sample_idx": i}
         for m in NAMES:
             sample[f"{m}_missing_index"] = self.masks[pattern][m][i]
         for m in NAMES:
-            if self._target in ("multimodal", m):
-                original = self.audio[i].clone() if m == "audio" else self.image_float(i)
-                mask = sample[f"{m}_missing_index"]
-                sample[f"{m}_original"] = original
-                sample[self.keys[m]] = original * mask
-                sample[f"{m}_reverse"] = original * -1 * (mask - 1)
+            if self._loads(m):
+                self._masked(sample, self.keys[m], m, self.audio[i].clone() if m == "audio" else self.image_float(i))
         return sample
 
     def collate_fn(self, batch: List[Dict[Any, Any]]) -> Dict[Any, Any]:
@@ -275,62 +433,20 @@ class AVMNIST(Dataset):
         return {pattern: DataLoader(PatternSpecificDataset(self, pattern), batch_size=batch_size, shuffle=False, collate_fn=self.collate_fn,
                                     **dataloader_kwargs) for pattern in self.selected_patterns}
 
-    def get_split(self) -> str:
-        return self.split
-
-    def get_selected_patterns(self) -> List[str]:
-        return self.selected_patterns
-
-    def get_missing_patterns(self):
-        return self.missing_patterns
-
     # ---- batch-granular path ------------------------------------------------------------------------------------------------
     def batches(self, batch_size: int, shuffle: Optional[bool] = None, drop_last: bool = False, pattern: Optional[str] = None,
                 image_form: str = "u8", rotate: int = 4, generator: Optional[torch.Generator] = None) -> Iterator[Dict[Any, Any]]:
         """Whole batches in the fused step's input form: ``labels`` int64 [B], ``pattern_name`` list, ``sample_idx`` int64 [B],
         ``audio_original`` fp32 [B, H, W], ``image_original`` uint8 [B, 1, h, w] (``image_form="u8"``: expand on the device with
         ``DevicePrefetcher(luts={"image_original": ds.lut})``) or fp32 (``"f32"``: table lookup on the host), ``<mod>_missing_index`` fp32 [B].
-
-        Order: the training split visits every sample once (shuffled unless ``shuffle=False``) with an independent uniformly drawn
-        pattern per sample (the vectorised form of ``random.choice``, base_dataset.py:87-89; drawn from ``generator``, not from
-        Python's ``random``); the other splits walk ``selected_patterns`` in order, all samples of one pattern after the other --
-        dataset index order, data/base_dataset.py:90-93 -- or only ``pattern``.  A yielded batch's tensors live in one of ``rotate``
-        pinned staging buffer sets and stay valid until ``rotate - 1`` further batches have been drawn (enough for a copy stream
-        one batch ahead of the step)."""
+        Order: ``_PatternDataset._epoch``.  A yielded batch's tensors live in one of ``rotate`` pinned staging buffer sets and stay valid
+        until ``rotate - 1`` further batches have been drawn (enough for a copy stream one batch ahead of the step)."""
         if image_form not in ("u8", "f32"):
             raise ValueError("image_form must be 'u8' or 'f32'")
-        if batch_size < 1 or rotate < 1:
-            raise ValueError("batch_size and rotate must be positive")
-        gen = generator if generator is not None else self.generator
-        train = self.split == "train"
-        if shuffle is None:
-            shuffle = train
-        N = self.num_samples
-        if train:
-            if pattern is not None:
-                pats = torch.full((N,), self.selected_patterns.index(pattern), dtype=torch.long)
-            else:
-                pats = torch.randint(len(self.selected_patterns), (N,), generator=gen)
-            rows = torch.randperm(N, generator=gen) if shuffle else torch.arange(N)
-            pats = pats[rows] if shuffle else pats
-        else:
-            which = [self.selected_patterns.index(pattern)] if pattern is not None else range(len(self.selected_patterns))
-            rows = torch.cat([torch.arange(N) for _ in which]) if len(which) else torch.empty(0, dtype=torch.long)
-            pats = torch.cat([torch.full((N,), k, dtype=torch.long) for k in which]) if len(which) else rows
-            if shuffle:
-                perm = torch.randperm(rows.numel(), generator=gen)
-                rows, pats = rows[perm], pats[perm]
-        table_row = torch.tensor([self._pat_index[p] for p in self.selected_patterns], dtype=torch.long)
-        bufs: List[Dict[str, torch.Tensor]] = [dict() for _ in range(rotate)]
-        total = rows.numel()
-        stop = total - (total % batch_size) if drop_last else total
-        for n, lo in enumerate(range(0, stop, batch_size)):
-            r, p = rows[lo:lo + batch_size], pats[lo:lo + batch_size]
-            buf = bufs[n % rotate]
-            out: Dict[Any, Any] = {"pattern_name": [self.selected_patterns[k] for k in p.tolist()]}
+        for buf, r, names, m in self._epoch(batch_size, shuffle, drop_last, pattern, generator, rotate):
+            out: Dict[Any, Any] = {"pattern_name": names}
             out["labels"] = self._gather(buf, "labels", self.labels, r)
             out["sample_idx"] = self._gather(buf, "sample_idx", None, r)
-            m = self._mask_table[table_row[p], :, r]  # [B, n_modalities]
             if self.audio is not None:
                 out["audio_original"] = self._gather(buf, "audio", self.audio, r)
                 out["audio_missing_index"] = self._gather(buf, "audio_mask", None, m[:, 0])
@@ -344,90 +460,117 @@ class AVMNIST(Dataset):
                 out["image_missing_index"] = self._gather(buf, "image_mask", None, m[:, 1])
             yield out
 
-    def _staging(self, buf: Dict[str, torch.Tensor], key: str, shape, dtype) -> torch.Tensor:
-        """View of ``shape`` on the pinned buffer ``buf[key]`` (allocated once at the largest leading dimension seen: the ragged last
-        batch of an epoch reuses the full-size buffer)."""
-        shape = tuple(shape)
-        t = buf.get(key)
-        if t is None or t.shape[1:] != torch.Size(shape[1:]) or t.dtype != dtype or t.shape[0] < shape[0]:
-            t = buf[key] = _maybe_pin(torch.empty(shape, dtype=dtype), self._pin)
-        return t[: shape[0]]
+    def _luts(self, kwargs):
+        return {"image_original": self.lut} if self.image_u8 is not None and kwargs.get("image_form", "u8") == "u8" else None
 
-    def _gather(self, buf: Dict[str, torch.Tensor], key: str, src: Optional[torch.Tensor], rows: torch.Tensor) -> torch.Tensor:
-        """rows of ``src`` (or ``rows`` itself when ``src`` is None) into the pinned staging tensor ``buf[key]``."""
-        if src is None:
-            t = self._staging(buf, key, rows.shape, rows.dtype)
-            t.copy_(rows)
-            return t
-        t = self._staging(buf, key, (rows.numel(),) + tuple(src.shape[1:]), src.dtype)
-        torch.index_select(src, 0, rows, out=t)
-        return t
 
-    def background_batches(self, batch_size: int, ahead: int = 2, **kwargs) -> Iterator[Dict[Any, Any]]:
-        """``batches()`` produced by a worker thread, ``ahead`` batches in front of the consumer (the row gathers are ``index_select``
-        calls that release the GIL, so they overlap the step's host code instead of adding 1.4-3.3 ms per 256-sample batch to it).
-        ``rotate`` defaults to ``ahead + 3`` staging sets: ``ahead`` queued, one being filled, one with the consumer, one spare."""
-        import queue
-        import threading
+class MultimodalSentimentDataset(_PatternDataset):
+    """CMU-MOSI / CMU-MOSEI: same constructor and item contract as ``data.mosi.MultimodalSentimentDataset`` (data/mosi.py:17-202) -- one
+    pickle ``{split: {"audio", "vision", "text", <labels_key>, "audio_lengths", "vision_lengths"}}`` of zero-padded ``[N, T, F]`` arrays.
+    The reference's own ``collate_fn`` cannot run (``_collate_train_batch`` indexes ``b[""]``, data/mosi.py:231; its loaders use torch's
+    default collation, ``DataConfig.use_collate_fn = False``), so none is mirrored: ``DataLoader(ds)`` with the default collation gives the
+    reference's batches, ``batches()`` / ``fused_loader()`` give the fused step's form (``<mod>_original`` + ``<mod>_missing_index``)."""
 
-        kwargs.setdefault("rotate", ahead + 3)
-        if kwargs["rotate"] < ahead + 2:
-            raise ValueError("rotate must be at least ahead + 2 (queued batches + the one being filled + the one in use)")
-        q: "queue.Queue" = queue.Queue(maxsize=max(1, int(ahead)))
-        stop = threading.Event()
-        done = object()
+    NUM_CLASSES: int = 3
+    MODS = ("audio", "video", "text")
+    AVAILABLE_MODALITIES: Dict[str, Any] = {"audio": "audio", "video": "video", "text": "text"}
+    RAW_KEYS = {"audio": "audio", "video": "vision", "text": "text"}
+    # the reference's default (data/mosi.py:62-70)
+    DEFAULT_PATTERNS = {
+        "atv": {"audio": 1.0, "text": 1.0, "video": 1.0}, "at": {"audio": 1.0, "text": 1.0, "video": 0.0},
+        "av": {"audio": 1.0, "text": 0.0, "video": 1.0}, "tv": {"audio": 0.0, "text": 1.0, "video": 1.0},
+        "a": {"audio": 1.0, "text": 0.0, "video": 0.0}, "t": {"audio": 0.0, "text": 1.0, "video": 0.0},
+        "v": {"audio": 0.0, "text": 0.0, "video": 1.0},
+    }
 
-        def work():
-            try:
-                for b in self.batches(batch_size, **kwargs):
-                    while not stop.is_set():
-                        try:
-                            q.put(b, timeout=0.1)
-                            break
-                        except queue.Full:
-                            continue
-                    if stop.is_set():
-                        return
-                item: Any = done
-            except BaseException as e:  # surfaced in the consumer
-                item = e
-            while not stop.is_set():
-                try:
-                    q.put(item, timeout=0.1)
-                    return
-                except queue.Full:
-                    continue
+    def __init__(self, data_fp: Union[str, Path], split: str, target_modality: Any = "multimodal", *,
+                 missing_patterns: Optional[Mapping[str, Mapping[Any, float]]] = None, selected_patterns: Optional[Sequence[str]] = None,
+                 labels_key: str = "classification_labels", aligned: bool = False, length: Optional[int] = None,
+                 num_classes: Optional[int] = None, batch_size: int = 1, masks=None, generator: Optional[torch.Generator] = None,
+                 pin: Optional[bool] = None) -> None:
+        import pickle
 
-        t = threading.Thread(target=work, name="avmnist-batches", daemon=True)
-        t.start()
-        try:
-            while True:
-                b = q.get()
-                if b is done:
-                    return
-                if isinstance(b, BaseException):
-                    raise b
-                yield b
-        finally:
-            stop.set()
-            t.join(timeout=5.0)
+        if num_classes is not None:
+            self.NUM_CLASSES = num_classes
+        self._configure(split, target_modality, missing_patterns, selected_patterns)
+        self._batch_size = batch_size
+        self.data_fp = Path(data_fp)
+        self.aligned = aligned
+        self.length = length if aligned else None
+        self.labels_key = labels_key
+        if not self.data_fp.exists():
+            raise FileNotFoundError(f"Data file not found: {self.data_fp}")
+        with open(self.data_fp, "rb") as f:
+            raw_data = pickle.load(f)
+        if self.split not in raw_data:
+            raise KeyError(f"Split '{self.split}' not found in data")
+        split_data = raw_data[self.split]
+        if labels_key not in split_data:
+            raise KeyError(f"Labels key '{labels_key}' not found in data")
+        label = torch.tensor(split_data[labels_key], dtype=torch.float32 if "regression" in labels_key else torch.long)
+        self.original_label_size = label.size(0)
+        self._finish(len(label), masks, generator, pin)
+        self.data: Dict[Any, torch.Tensor] = {"label": _maybe_pin(label, self._pin)}
+        for m in self.MODS:  # the reference converts all three whatever the target modality (data/mosi.py:137-145)
+            self.data[self.keys[m]] = _maybe_pin(torch.tensor(split_data[self.RAW_KEYS[m]]).float().contiguous(), self._pin)
+        if not aligned:
+            self.data["audio_lengths"] = _maybe_pin(torch.tensor(split_data["audio_lengths"]).float(), self._pin)
+            self.data["video_lengths"] = _maybe_pin(torch.tensor(split_data["vision_lengths"]).float(), self._pin)
 
-    def fused_loader(self, device, batch_size: int, depth: int = 1, ahead: int = 2, **kwargs):
-        """``batches()`` (on a worker thread when ``ahead`` > 0) behind the device prefetcher: uint8 images cross PCIe as bytes and are
-        expanded through the luminance table on the copy stream; the result feeds ``mml_b200.avmnist.AVMNIST.train_step /
-        validation_step`` directly.  Staging sets: ``ahead`` + ``depth`` + 3 (queued + staged on the copy stream + filling / in use / spare)."""
-        from .data import DevicePrefetcher
+    def __getitem__(self, idx: int) -> Dict[Any, Any]:
+        pattern, i = self._item_head(idx)
+        sample: Dict[Any, Any] = {"label": self.data["label"][i], "pattern_name": pattern, "missing_index": {}, "sample_idx": i}
+        for m in self.MODS:
+            sample[f"{m}_missing_index"] = self.masks[pattern][m][i]
+        if not self.aligned:
+            sample["audio_length"] = self.data["audio_lengths"][i]
+            sample["video_length"] = self.data["video_lengths"][i]
+        for m in self.MODS:
+            if self._loads(m):
+                self._masked(sample, self.keys[m], m, self.data[self.keys[m]][i])
+        return sample
 
-        kwargs.setdefault("rotate", ahead + depth + 3)
-        luts = {"image_original": self.lut} if self.image_u8 is not None and kwargs.get("image_form", "u8") == "u8" else None
-        it = self.background_batches(batch_size, ahead=ahead, **kwargs) if ahead > 0 else self.batches(batch_size, **kwargs)
-        return DevicePrefetcher(it, device, depth=depth, luts=luts)
+    def batches(self, batch_size: int, shuffle: Optional[bool] = None, drop_last: bool = False, pattern: Optional[str] = None,
+                rotate: int = 4, generator: Optional[torch.Generator] = None) -> Iterator[Dict[Any, Any]]:
+        """``label`` [B], ``pattern_name``, ``sample_idx``, ``<mod>_original`` fp32 [B, T, F] + ``<mod>_missing_index`` fp32 [B] for the
+        loaded modalities and, for unaligned data, ``audio_length`` / ``video_length`` [B]; order and staging as in ``AVMNIST.batches``."""
+        for buf, r, names, msk in self._epoch(batch_size, shuffle, drop_last, pattern, generator, rotate):
+            out: Dict[Any, Any] = {"pattern_name": names}
+            out["label"] = self._gather(buf, "label", self.data["label"], r)
+            out["sample_idx"] = self._gather(buf, "sample_idx", None, r)
+            if not self.aligned:
+                out["audio_length"] = self._gather(buf, "audio_length", self.data["audio_lengths"], r)
+                out["video_length"] = self._gather(buf, "video_length", self.data["video_lengths"], r)
+            for j, m in enumerate(self.MODS):
+                if self._loads(m):
+                    out[f"{m}_original"] = self._gather(buf, m, self.data[self.keys[m]], r)
+                    out[f"{m}_missing_index"] = self._gather(buf, m + "_mask", None, msk[:, j])
+            yield out
+
+    @staticmethod
+    def normalize_features(features: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+        """Zero mean / unit std along the time dimension (data/mosi.py:258-271)."""
+        mean = torch.mean(features, dim=0, keepdim=True)
+        std = torch.std(features, dim=0, keepdim=True).clamp(min=eps)
+        return (features - mean) / std
+
+    @staticmethod
+    def get_num_classes(is_classification: bool = True) -> int:
+        return 3 if is_classification else 1
+
+
+class MOSI(MultimodalSentimentDataset):
+    """CMU-MOSI (data/mosi.py:288-301)."""
+
+
+class MOSEI(MultimodalSentimentDataset):
+    """CMU-MOSEI (data/mosi.py:274-286)."""
 
 
 class PatternSpecificDataset(Dataset):
     """The samples of one pattern of a validation / test split (data/pattern.py:6-19)."""
 
-    def __init__(self, parent_dataset: AVMNIST, pattern: str):
+    def __init__(self, parent_dataset: _PatternDataset, pattern: str):
         self.parent, self.pattern = parent_dataset, pattern
         self.sample_indices = parent_dataset.pattern_indices[pattern]
 

@@ -197,3 +197,111 @@ def test_training_batches_visit_every_sample_once(gold, csv):
     for b in ds.batches(2, shuffle=False, rotate=2):
         bs.append(b["audio_original"])
     assert bs[0].data_ptr() != bs[1].data_ptr() and bs[0][:1].data_ptr() == bs[2].data_ptr()
+
+
+# ---- MOSI / MOSEI (MML_Suite/data/mosi.py) -----------------------------------------------------------------------------------------
+MOSI_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mosi_loader.npz")
+
+
+@pytest.fixture(scope="module")
+def mgold():
+    return np.load(MOSI_GOLD)
+
+
+@pytest.fixture(scope="module")
+def pkl(mgold, tmp_path_factory):
+    import pickle
+
+    raw = {}
+    for k in mgold.files:
+        if k.startswith("raw_"):
+            _, split, name = k.split("_", 2)
+            raw.setdefault(split, {})[name] = mgold[k]
+    path = str(tmp_path_factory.mktemp("mosi_files") / "mosi.pkl")
+    with open(path, "wb") as f:
+        pickle.dump(raw, f)
+    return path
+
+
+def _check_mosi_items(gold, prefix, items, ds):
+    assert [str(k) for k in items[0].keys()] == list(gold[f"{prefix}_keys"])
+    lab = torch.stack([it["label"] for it in items])
+    assert lab.numpy().dtype == gold[f"{prefix}_label"].dtype and np.array_equal(lab.numpy(), gold[f"{prefix}_label"])
+    assert [it["sample_idx"] for it in items] == list(gold[f"{prefix}_sample_idx"])
+    assert [it["pattern_name"] for it in items] == list(gold[f"{prefix}_pattern"])
+    if f"{prefix}_audio_length" in gold.files:
+        assert [float(it["audio_length"]) for it in items] == list(gold[f"{prefix}_audio_length"])
+        assert [float(it["video_length"]) for it in items] == list(gold[f"{prefix}_video_length"])
+    else:
+        assert "audio_length" not in items[0]
+    for mod in ("audio", "video", "text"):
+        assert [float(it[f"{mod}_missing_index"]) for it in items] == list(gold[f"{prefix}_{mod}_missing_index"])
+        if f"{prefix}_{mod}" not in gold.files:
+            assert ds.keys[mod] not in items[0] and f"{mod}_original" not in items[0]
+            continue
+        for suffix, key in (("", ds.keys[mod]), ("_original", f"{mod}_original"), ("_reverse", f"{mod}_reverse")):
+            got = torch.stack([it[key] for it in items])
+            assert got.dtype == torch.float32 and np.array_equal(_bits(got), gold[f"{prefix}_{mod}{suffix}"]), (prefix, mod, suffix)
+
+
+def test_mosi_items_equal_the_reference(mgold, pkl):
+    from mml_b200.datasets import MOSEI, MOSI
+
+    ds = MOSI(pkl, "valid", masks=_masks(mgold, "valid"))
+    assert len(ds) == 21 and ds.selected_patterns == ["a", "at", "atv", "av", "t", "tv", "v"] and ds.get_full_modality() == "atv"
+    assert MOSI.get_num_classes() == 3 and MOSEI.get_num_classes(False) == 1 and ds.NUM_CLASSES == 3
+    _check_mosi_items(mgold, "valid", [ds[i] for i in range(len(ds))], ds)
+    mp = {"atv": {"audio": 0.8, "text": 1.0, "video": 1.0}, "t": {"audio": 0.0, "text": 1.0, "video": 0.0}}
+    tr = MOSI(pkl, "train", missing_patterns=mp, selected_patterns=["atv", "t"], aligned=True, length=6, masks=_masks(mgold, "train"))
+    assert len(tr) == 4 and tr.length == 6
+    random.seed(5)
+    _check_mosi_items(mgold, "train", [tr[i] for i in (3, 0, 1, 1, 2)], tr)
+    te = MOSI(pkl, "test", "text", selected_patterns=["atv"], labels_key="regression_labels", masks=_masks(mgold, "testt"))
+    _check_mosi_items(mgold, "testt", [te[i] for i in range(len(te))], te)
+    with pytest.raises(KeyError):
+        MOSI(pkl, "valid", labels_key="nope")
+    # torch's default collation (what the reference's loaders use: its own collate_fn indexes b[""], data/mosi.py:231)
+    from torch.utils.data import DataLoader
+
+    b = next(iter(DataLoader(ds, batch_size=5)))
+    assert b["label"].shape == (5,) and b["audio_original"].shape == (5, 6, 3) and b[ds.keys["text"]].shape == (5, 6, 8) and b["pattern_name"] == ["a"] * 3 + ["at"] * 2
+
+
+def test_mosi_batches_equal_the_item_path(mgold, pkl):
+    from mml_b200.datasets import MOSI
+
+    ds = MOSI(pkl, "valid", masks=_masks(mgold, "valid"), pin=False)
+    items = [ds[i] for i in range(len(ds))]
+    got = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in b.items()} for b in ds.batches(8, rotate=1)]
+    assert [len(b["label"]) for b in got] == [8, 8, 5]
+    assert sum((b["pattern_name"] for b in got), []) == [it["pattern_name"] for it in items]
+    cat = {k: torch.cat([b[k] for b in got]) for k in got[0] if k != "pattern_name"}
+    assert torch.equal(cat["label"], torch.stack([it["label"] for it in items])) and cat["sample_idx"].tolist() == [it["sample_idx"] for it in items]
+    assert torch.equal(cat["audio_length"], torch.stack([it["audio_length"] for it in items]))
+    for mod in ("audio", "video", "text"):
+        assert np.array_equal(_bits(cat[f"{mod}_original"]), _bits(torch.stack([it[f"{mod}_original"] for it in items])))
+        assert cat[f"{mod}_missing_index"].tolist() == [float(it[f"{mod}_missing_index"]) for it in items]
+        masked = cat[f"{mod}_original"] * cat[f"{mod}_missing_index"].reshape(-1, 1, 1)
+        assert np.array_equal(_bits(masked), _bits(torch.stack([it[ds.keys[mod]] for it in items])))
+    mono = MOSI(pkl, "test", "text", selected_patterns=["atv"], pin=False)
+    b = next(iter(mono.batches(2)))
+    assert "text_original" in b and "audio_original" not in b and b["label"].dtype == torch.long
+
+
+def test_background_batches_equal_inline_batches(gold, csv):
+    ds = AVMNIST(csv, "train", cmap=gold["table"], selected_patterns=["ai", "i"], pin=False)
+    inline = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in b.items()} for b in ds.batches(2, generator=torch.Generator().manual_seed(4))]
+    for ahead in (1, 3):
+        n = 0
+        for want, got in zip(inline, ds.background_batches(2, ahead=ahead, generator=torch.Generator().manual_seed(4))):
+            assert set(want) == set(got) and want["pattern_name"] == got["pattern_name"]
+            assert all(torch.equal(want[k], got[k]) for k in want if k != "pattern_name")
+            n += 1
+        assert n == len(inline) == 3
+    with pytest.raises(ValueError, match="rotate"):
+        next(ds.background_batches(2, ahead=3, rotate=4))
+    with pytest.raises(ValueError, match="image_form"):  # an error on the worker thread surfaces in the consumer
+        next(ds.background_batches(2, image_form="png"))
+    it = ds.background_batches(1)  # abandoning the iterator stops the worker
+    next(it)
+    it.close()

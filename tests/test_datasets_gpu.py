@@ -94,3 +94,55 @@ def test_validation_split_through_the_fused_loader():
         if seen[-1] == ["i"]:
             assert not b["audio_missing_index"].any()  # pattern "i": the audio modality is masked out on the device
     assert seen == [["ai"], ["i"]]
+
+
+def test_mosi_fused_loader_trains_like_the_host_path(tmp_path):
+    """``datasets.MOSI`` -> worker thread -> DevicePrefetcher -> ``UttFusionModel.train_step`` (config 4), against the same batches fed from
+    the host; the dropout keep-masks are given so that both runs draw the same ones."""
+    import pickle
+
+    from mml_b200.datasets import MOSI
+    from mml_b200.utt_fusion import FcClassifier, LSTMEncoder, TextCNN, UttFusionModel
+
+    rng = np.random.default_rng(0)
+    n, T, B = 70, 50, 32
+    raw = {"audio": rng.normal(size=(n, T, 5)).astype(np.float32), "vision": rng.normal(size=(n, T, 20)).astype(np.float32),
+           "text": rng.normal(size=(n, T, 768)).astype(np.float32), "classification_labels": rng.integers(0, 3, size=n),
+           "audio_lengths": np.full(n, T), "vision_lengths": np.full(n, T)}
+    fp = str(tmp_path / "mosi.pkl")
+    with open(fp, "wb") as f:
+        pickle.dump({"train": raw}, f)
+    mp = {"atv": {"audio": 0.8, "text": 1.0, "video": 1.0}, "t": {"audio": 0.0, "text": 1.0, "video": 0.0}, "av": {"audio": 1.0, "text": 0.0, "video": 1.0}}
+    ds = MOSI(fp, "train", missing_patterns=mp, selected_patterns=["atv", "t", "av"], generator=torch.Generator().manual_seed(3))
+    host = [_snapshot(b) for b in ds.batches(B, generator=torch.Generator().manual_seed(1))]
+    assert [len(b["label"]) for b in host] == [32, 32, 6] and {p for b in host for p in b["pattern_name"]} == {"atv", "t", "av"}
+    n_batches = 0
+    for h, d in zip(host, ds.fused_loader(DEV, B, generator=torch.Generator().manual_seed(1))):
+        assert set(d) == set(h)
+        for k, v in h.items():
+            if torch.is_tensor(v):
+                assert d[k].is_cuda and d[k].dtype == v.dtype and torch.equal(d[k].cpu(), v), k
+            else:
+                assert d[k] == v, k
+        n_batches += 1
+    assert n_batches == 3
+
+    g = torch.Generator().manual_seed(9)
+    keeps = [(torch.rand(B, k, generator=g) >= 0.5).float() for k in (384, 192, 64, 32)]
+
+    def run(fused):
+        torch.manual_seed(0)
+        model = UttFusionModel(LSTMEncoder(5, 64, "last"), LSTMEncoder(20, 64, "last"),
+                               TextCNN(768, embd_size=64, dropout=0.5, in_channels=1, out_channels=128, kernel_heights=[3, 4, 5]),
+                               FcClassifier(192, [192, 64, 32], 3, dropout=0.5), clip=1.0).to(DEV)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3)
+        out = []
+        for epoch in range(2):
+            kw = dict(drop_last=True, generator=torch.Generator().manual_seed(2 + epoch))
+            it = ds.fused_loader(DEV, B, **kw) if fused else ds.batches(B, **kw)
+            out += [model.train_step(b, opt, LOSS, torch.device(DEV), None, dropout_masks=keeps)["loss"] for b in it]
+        return out
+
+    from_host, from_loader = run(False), run(True)
+    assert len(from_host) == len(from_loader) == 4 and all(np.isfinite(from_host))
+    assert np.allclose(from_host, from_loader, rtol=2e-2, atol=2e-2), (from_host, from_loader)
