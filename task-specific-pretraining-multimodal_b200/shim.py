@@ -13,6 +13,9 @@ What it re-binds (reference file:line):
   * config 3: YAML tags ``!MMIMDb`` / ``!MMIMDbModalityEncoder`` / ``!GatedBiModalNetwork`` / ``!MLPGenreClassifier``
     (yaml_constructors.py:126-142) and the attributes ``models.mmimdb.MMIMDb`` (+ the three part classes) ->
     ``mml_b200.mmimdb``.
+  * ``install(datasets=True)`` (opt-in): ``config.resolvers.AVMNIST / MOSI / MOSEI`` -- the names ``resolve_dataset_name`` looks up at call
+    time (config/resolvers.py:192-221) -- and ``data.AVMNIST / MOSI / MOSEI`` -> ``mml_b200.datasets``: ``dataset: "AVMNIST"`` in a YAML
+    then builds the pinned in-memory dataset (same items through a DataLoader, plus ``fused_loader()`` for the fused step).
 Works without the reference on the path too (then only the YAML tags are registered).
 """
 from __future__ import annotations
@@ -23,7 +26,7 @@ from typing import Dict
 _installed: Dict[str, object] = {}
 
 
-def install(patch_reference_modules: bool = True) -> Dict[str, object]:
+def install(patch_reference_modules: bool = True, datasets: bool = False) -> Dict[str, object]:
     import yaml
 
     from .avmnist import AVMNIST
@@ -94,4 +97,14 @@ def install(patch_reference_modules: bool = True) -> Dict[str, object]:
         _installed["reference.MonomodalEncoder"] = getattr(ref_tm, "MonomodalEncoder", None)
         ref_tm.MonomodalEncoder = MonomodalEncoder
     _installed["MonomodalEncoder"] = MonomodalEncoder
+    if datasets:
+        from . import datasets as _ds
+
+        for modname in ("config.resolvers", "data"):
+            mod = sys.modules.get(modname)
+            if patch_reference_modules and mod is not None:
+                for n in ("AVMNIST", "MOSI", "MOSEI"):
+                    _installed.setdefault(f"reference.{modname}.{n}", getattr(mod, n, None))
+                    setattr(mod, n, getattr(_ds, n))
+        _installed["datasets"] = (_ds.AVMNIST, _ds.MOSI, _ds.MOSEI)
     return dict(_installed)

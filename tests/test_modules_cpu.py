@@ -115,6 +115,35 @@ def test_shim_registers_yaml_tags_and_swaps_reference_model():
         assert resolve_model_name("avmnist") is AVMNIST
         cfg = yaml.safe_load("a: !ResNet18\n  in_channels: 1\n  hidden_dim: 64\n")
         assert isinstance(cfg["a"], ResNetEncoder)
+        # opt-in dataset swap: ``dataset: "AVMNIST"`` / "mosi" of a YAML resolve to the pinned in-memory classes, and the reference's own
+        # MissingPatternConfig output (Modality-keyed probabilities) is a valid ``missing_patterns`` argument for them
+        from collections import OrderedDict
+
+        from config.resolvers import resolve_dataset_name
+        from mml_b200 import datasets as D
+
+        ref_cls = resolve_dataset_name("avmnist")
+        got = shim.install(datasets=True)
+        assert resolve_dataset_name("avmnist") is D.AVMNIST and resolve_dataset_name("MOSI") is D.MOSI and resolve_dataset_name("mosei") is D.MOSEI
+        assert got["reference.config.resolvers.AVMNIST"] is ref_cls and ref_cls is not D.AVMNIST
+        ns = ref_import.import_reference()
+        M = ns.Modality
+        pats = ns.MissingPatternConfig(modalities=OrderedDict([(M.AUDIO, ns.ModalityConfig(missing_rate=0.2, apply_to=None)),
+                                                               (M.IMAGE, ns.ModalityConfig(missing_rate=0.0, apply_to=None))]),
+                                       selected_patterns=["ai"]).generate_patterns()
+        import numpy as np
+        import torch
+
+        ds = D.AVMNIST.from_arrays(torch.arange(6) % 10, torch.rand(6, 4, 5), torch.zeros(6, 3, 3, dtype=torch.uint8), "train",
+                                   missing_patterns=pats, selected_patterns=["ai"], cmap=np.zeros((256, 3)), pin=False)
+        assert ds.missing_patterns == {"ai": {"audio": 0.8, "image": 1.0}} and ds.masks["ai"]["image"].all()
+        assert M.AUDIO in ds[0] and ds[0]["pattern_name"] == "ai"  # Modality-keyed items once the ``modalities`` package is importable
+        import config.resolvers as R
+        import data as RDATA
+
+        for n in ("AVMNIST", "MOSI", "MOSEI"):  # leave the reference modules as they were for the other tests
+            setattr(R, n, got[f"reference.config.resolvers.{n}"])
+            setattr(RDATA, n, got[f"reference.data.{n}"])
 
 
 def test_ctypes_signatures_match_header_arity():
