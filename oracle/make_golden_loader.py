@@ -152,6 +152,7 @@ def main() -> None:
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays,", len(drawn), "mask draws")
     mosi_case(ns, RB)
+    mmimdb_case(ns, RB)
 
 
 MOSI_N, MOSI_T, MOSI_F = 4, 6, {"audio": 3, "vision": 4, "text": 8}
@@ -239,6 +240,73 @@ def mosi_case(ns, RB) -> None:
         masks_of(ds, "testt")
         mosi_items("testt", [ds[i] for i in range(len(ds))], M, out)
     path = os.path.join(GOLDEN_DIR, "mosi_loader.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays,", len(drawn), "mask draws")
+
+
+
+
+class FakeH5(dict):
+    """Dict-backed stand-in for ``h5py.File`` (h5py is not installed here): ``keys()``, ``[key]`` -> array with ``[idx]`` / ``[...]`` / ``len``."""
+
+    def close(self):
+        pass
+
+
+def mmimdb_raw(n: int = 5):
+    rng = np.random.default_rng(123)
+    return {"imdb_ids": np.array([f"tt{1000 + i:07d}".encode() for i in range(n)]), "vgg_features": np.abs(rng.normal(size=(n, 12))).astype(np.float32),
+            "features": rng.normal(0, 0.3, size=(n, 7)).astype(np.float64), "genres": (rng.random((n, 23)) < 0.2).astype(np.int64)}
+
+
+def mmimdb_case(ns, RB) -> None:
+    """tests/golden/mmimdb_loader.npz from the unmodified ``data.mmimdb.MMIMDb`` (MML_Suite/data/mmimdb.py:14-207) over a dict-backed HDF5."""
+    import data.mmimdb as RMM
+
+    M = ns.Modality
+    raw = mmimdb_raw()
+    drawn = []
+
+    def create_missing_mask(n_modalities, batch_size, missing_rates):
+        g = torch.Generator().manual_seed(3000 + len(drawn))
+        keep = 1.0 - torch.tensor(list(missing_rates), dtype=torch.float32)
+        m = torch.bernoulli(keep.expand(batch_size, n_modalities).contiguous(), generator=g)
+        drawn.append(m)
+        return m
+
+    RB.create_missing_mask = create_missing_mask
+    RMM.h5.File = lambda path, mode="r": FakeH5(raw)
+    out = {f"raw_{k}": v for k, v in raw.items()}
+
+    def store(prefix, ds, idxs):
+        for pat, tab in ds.masks.items():
+            for m, v in tab.items():
+                out[f"{prefix}_masks_{pat}_{m}"] = v.numpy().astype(np.float32)
+        items = [ds[i] for i in idxs]
+        out[f"{prefix}_label"] = torch.stack([it["label"] for it in items]).numpy()
+        out[f"{prefix}_sample_idx"] = np.array([int(it["sample_idx"]) for it in items], dtype=np.int64)
+        out[f"{prefix}_pattern"] = np.array([it["pattern_name"] for it in items])
+        out[f"{prefix}_keys"] = np.array([str(k) for k in items[0].keys()])
+        out[f"{prefix}_ids"] = np.array([ds._load_id(int(it["sample_idx"])) for it in items])
+        for mod, m in (("image", M.IMAGE), ("text", M.TEXT)):
+            out[f"{prefix}_{mod}_missing_index"] = np.array([float(it[f"{mod}_missing_index"]) for it in items], dtype=np.float32)
+            if m in items[0]:
+                for suffix, key in (("", m), ("_original", f"{mod}_original"), ("_reverse", f"{mod}_reverse")):
+                    out[f"{prefix}_{mod}{suffix}"] = torch.stack([it[key] for it in items]).contiguous().view(torch.int32).numpy()
+
+    with tempfile.TemporaryDirectory() as root:
+        fp = os.path.join(root, "val.h5")
+        open(fp, "wb").close()  # the class only checks that the path exists before h5py opens it
+        ds = RMM.MMIMDb(fp, "val")
+        assert len(ds) == 15 and ds.selected_patterns == ["i", "it", "t"]
+        store("val", ds, range(len(ds)))
+        mp = {"it": {M.IMAGE: 0.3, M.TEXT: 0.7}, "t": {M.IMAGE: 0.0, M.TEXT: 1.0}}  # missing_exp/baseline_30_70.yaml: text 0.3, image 0.7 missing
+        ds = RMM.MMIMDb(fp, "train", missing_patterns=mp, selected_patterns=["it", "t"])
+        random.seed(8)
+        store("train", ds, (1, 4, 4, 0, 2))
+        ds = RMM.MMIMDb(fp, "test", M.TEXT, selected_patterns=["it"])
+        store("testt", ds, range(len(ds)))
+    path = os.path.join(GOLDEN_DIR, "mmimdb_loader.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays,", len(drawn), "mask draws")
 

@@ -10,7 +10,7 @@ Sub-modules (imported lazily so that ``import mml_b200`` works on a CPU-only box
   mmimdb    MMIMDb gated late-fusion model (config 3) + gated_engine, its fused step
   mono      MonomodalEncoder (encoder pre-training: one ResNet encoder + Linear + CE)
   data      missing-modality patterns, device mask table, luminance table, device prefetcher
-  datasets  AVMNIST / MOSI dataset classes (the reference's item contract + whole pinned batches for the fused steps)
+  datasets  AVMNIST / MMIMDb / MOSI dataset classes (the reference's item contract + whole pinned batches for the fused steps)
   dist      one-process-per-GPU data parallelism (NCCL) with bucketed gradient allreduce
   fedavg    FedAvg weighted aggregation
   shim      registration under the reference's YAML tags / model resolver

@@ -19,9 +19,9 @@ labels int64 ``[N]`` -- plus the mask table ``[pattern][modality][len(self)]``. 
   and ``fused_loader()`` = ``DevicePrefetcher(batches(), luts={"image_original": lut})``: 1 byte per image pixel over PCIe, table
   lookup on the copy stream (``mml_stage_u8_lut_f32``).
 
-``MOSI`` / ``MOSEI`` (``MML_Suite/data/mosi.py:17-301``, one pickle of padded ``[N, T, F]`` arrays per split) get the same two views.  The
-MMIMDb loader reads HDF5 through ``h5py``, which this image does not have: not built (its batches are plain ``[B, 4096]`` / ``[B, 300]``
-tensors; ``DevicePrefetcher`` takes them as they are).
+``MOSI`` / ``MOSEI`` (``MML_Suite/data/mosi.py:17-301``, one pickle of padded ``[N, T, F]`` arrays per split) get the same two views.  ``MMIMDb``
+(``MML_Suite/data/mmimdb.py:14-207``, one HDF5 file per split) too: its items are pinned against the reference class with a dict-backed
+stand-in for ``h5py`` (not installed in this image; the one ``h5py.File`` call is the only unexercised line).
 
 Mask *sampling* follows ``data.draw_missing_masks`` (independent Bernoulli(P(present)); the reference's generator lives in the
 un-vendored ``modalities`` package) or is handed in (``masks=``: e.g. ``DeviceMaskTable(...).masks`` copied back, or
@@ -565,6 +565,98 @@ class MOSI(MultimodalSentimentDataset):
 
 class MOSEI(MultimodalSentimentDataset):
     """CMU-MOSEI (data/mosi.py:274-286)."""
+
+
+def _open_h5(path):
+    """``h5py.File(path, "r")`` (data/mmimdb.py:88); h5py is imported here so that the module loads without it."""
+    try:
+        import h5py  # type: ignore
+    except Exception as e:
+        raise ImportError("MMIMDb reads an HDF5 file: install h5py, or build the dataset with MMIMDb.from_arrays(...)") from e
+    return h5py.File(Path(path), "r")
+
+
+class MMIMDb(_PatternDataset):
+    """MM-IMDb features: same constructor and item contract as ``data.mmimdb.MMIMDb`` (data/mmimdb.py:14-207) -- one HDF5 file per split
+    with ``vgg_features`` [N, 4096], ``features`` [N, 300], multi-hot ``genres`` [N, 23] and ``imdb_ids``.  The reference indexes the open
+    file per item; here the four datasets are read once into (pinned) arrays.  Batches feed ``mml_b200.mmimdb.MMIMDb.train_step``."""
+
+    VALID_SPLITS: List[str] = ["train", "val", "test"]
+    NUM_CLASSES: int = 23
+    MODS = ("image", "text")
+    AVAILABLE_MODALITIES: Dict[str, Any] = {"image": "image", "text": "text"}
+    # the reference's default (data/mmimdb.py:73-77)
+    DEFAULT_PATTERNS = {"it": {"image": 1.0, "text": 1.0}, "i": {"image": 1.0, "text": 0.0}, "t": {"image": 0.0, "text": 1.0}}
+
+    def __init__(self, data_fp: Union[str, Path], split: str, target_modality: Any = "multimodal", *,
+                 missing_patterns: Optional[Mapping[str, Mapping[Any, float]]] = None, selected_patterns: Optional[Sequence[str]] = None,
+                 image_key: str = "vgg_features", text_key: str = "features", labels_key: str = "genres", imdb_ids_key: str = "imdb_ids",
+                 split_indices: Optional[Sequence[int]] = None, _id: int = 1, masks=None, generator: Optional[torch.Generator] = None,
+                 pin: Optional[bool] = None) -> None:
+        self._configure(split, target_modality, missing_patterns, selected_patterns, _id)
+        data_fp = Path(data_fp)
+        if not data_fp.exists():
+            raise FileNotFoundError(f"Dataset file not found: {data_fp}")
+        f = _open_h5(data_fp)
+        try:
+            keys = list(f.keys())
+            assert imdb_ids_key in keys, f"IMDb IDs key {imdb_ids_key} not found in the dataset"
+            assert image_key in keys, f"Image key {image_key} not found in the dataset"
+            assert text_key in keys, f"Text key {text_key} not found in the dataset"
+            assert labels_key in keys, f"Labels key {labels_key} not found in the dataset"
+            ids = [x.decode("utf-8") if isinstance(x, bytes) else str(x) for x in np.asarray(f[imdb_ids_key][...]).tolist()]
+            self._store(np.asarray(f[labels_key][...]), np.asarray(f[image_key][...]), np.asarray(f[text_key][...]), ids, masks, generator, pin)
+        finally:
+            close = getattr(f, "close", None)
+            if close is not None:
+                close()
+
+    @classmethod
+    def from_arrays(cls, labels, image, text, imdb_ids: Optional[Sequence[str]] = None, split: str = "train", target_modality: Any = "multimodal", *,
+                    missing_patterns=None, selected_patterns=None, _id: int = 1, masks=None, generator: Optional[torch.Generator] = None,
+                    pin: Optional[bool] = None) -> "MMIMDb":
+        """The same dataset over arrays in memory: ``labels`` [N, 23], ``image`` [N, 4096], ``text`` [N, 300] (any float / integer dtype)."""
+        self = cls.__new__(cls)
+        self._configure(split, target_modality, missing_patterns, selected_patterns, _id)
+        self._store(labels, image, text, imdb_ids, masks, generator, pin)
+        return self
+
+    def _store(self, labels, image, text, ids, masks, generator, pin) -> None:
+        lab = torch.as_tensor(np.asarray(labels)).float().contiguous()  # ``torch.as_tensor(...).float()`` per item in the reference (:125-155)
+        self._finish(lab.shape[0], masks, generator, pin)
+        img, txt = torch.as_tensor(np.asarray(image)).float().contiguous(), torch.as_tensor(np.asarray(text)).float().contiguous()
+        if img.shape[0] != self.num_samples or txt.shape[0] != self.num_samples:
+            raise ValueError(f"labels / image / text disagree on the number of samples: {lab.shape[0]} / {img.shape[0]} / {txt.shape[0]}")
+        self.label = _maybe_pin(lab, self._pin)
+        self.data = {"image": _maybe_pin(img, self._pin), "text": _maybe_pin(txt, self._pin)}
+        self.imdb_ids = list(ids) if ids is not None else [str(i) for i in range(self.num_samples)]
+
+    def _load_id(self, idx: int) -> str:
+        return self.imdb_ids[idx]
+
+    def __getitem__(self, idx: int) -> Dict[Any, Any]:
+        pattern, i = self._item_head(idx)
+        sample: Dict[Any, Any] = {"label": self.label[i].clone(), "pattern_name": pattern, "missing_mask": {}, "sample_idx": i}
+        for m in self.MODS:
+            sample[f"{m}_missing_index"] = self.masks[pattern][m][i]
+        for m in self.MODS:
+            if self._loads(m):
+                self._masked(sample, self.keys[m], m, self.data[m][i].clone())
+        return sample
+
+    def batches(self, batch_size: int, shuffle: Optional[bool] = None, drop_last: bool = False, pattern: Optional[str] = None,
+                rotate: int = 4, generator: Optional[torch.Generator] = None) -> Iterator[Dict[Any, Any]]:
+        """``label`` fp32 [B, 23], ``pattern_name``, ``sample_idx``, ``<mod>_original`` fp32 [B, D] + ``<mod>_missing_index`` fp32 [B] for the
+        loaded modalities; order and staging as in ``AVMNIST.batches``."""
+        for buf, r, names, msk in self._epoch(batch_size, shuffle, drop_last, pattern, generator, rotate):
+            out: Dict[Any, Any] = {"pattern_name": names}
+            out["label"] = self._gather(buf, "label", self.label, r)
+            out["sample_idx"] = self._gather(buf, "sample_idx", None, r)
+            for j, m in enumerate(self.MODS):
+                if self._loads(m):
+                    out[f"{m}_original"] = self._gather(buf, m, self.data[m], r)
+                    out[f"{m}_missing_index"] = self._gather(buf, m + "_mask", None, msk[:, j])
+            yield out
 
 
 class PatternSpecificDataset(Dataset):

@@ -13,8 +13,8 @@ What it re-binds (reference file:line):
   * config 3: YAML tags ``!MMIMDb`` / ``!MMIMDbModalityEncoder`` / ``!GatedBiModalNetwork`` / ``!MLPGenreClassifier``
     (yaml_constructors.py:126-142) and the attributes ``models.mmimdb.MMIMDb`` (+ the three part classes) ->
     ``mml_b200.mmimdb``.
-  * ``install(datasets=True)`` (opt-in): ``config.resolvers.AVMNIST / MOSI / MOSEI`` -- the names ``resolve_dataset_name`` looks up at call
-    time (config/resolvers.py:192-221) -- and ``data.AVMNIST / MOSI / MOSEI`` -> ``mml_b200.datasets``: ``dataset: "AVMNIST"`` in a YAML
+  * ``install(datasets=True)`` (opt-in): ``config.resolvers.AVMNIST / MOSI / MOSEI / MMIMDb`` -- the names ``resolve_dataset_name`` looks up at call
+    time (config/resolvers.py:192-221) -- and ``data.AVMNIST / MOSI / MOSEI / MMIMDb`` -> ``mml_b200.datasets``: ``dataset: "AVMNIST"`` in a YAML
     then builds the pinned in-memory dataset (same items through a DataLoader, plus ``fused_loader()`` for the fused step).
 Works without the reference on the path too (then only the YAML tags are registered).
 """
@@ -103,8 +103,8 @@ def install(patch_reference_modules: bool = True, datasets: bool = False) -> Dic
         for modname in ("config.resolvers", "data"):
             mod = sys.modules.get(modname)
             if patch_reference_modules and mod is not None:
-                for n in ("AVMNIST", "MOSI", "MOSEI"):
+                for n in ("AVMNIST", "MOSI", "MOSEI", "MMIMDb"):  # module-level names of the DATASET classes (models are imported locally)
                     _installed.setdefault(f"reference.{modname}.{n}", getattr(mod, n, None))
                     setattr(mod, n, getattr(_ds, n))
-        _installed["datasets"] = (_ds.AVMNIST, _ds.MOSI, _ds.MOSEI)
+        _installed["datasets"] = (_ds.AVMNIST, _ds.MOSI, _ds.MOSEI, _ds.MMIMDb)
     return dict(_installed)

@@ -305,3 +305,84 @@ def test_background_batches_equal_inline_batches(gold, csv):
     it = ds.background_batches(1)  # abandoning the iterator stops the worker
     next(it)
     it.close()
+
+
+# ---- MMIMDb (MML_Suite/data/mmimdb.py) ----------------------------------------------------------------------------------------------
+MMIMDB_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mmimdb_loader.npz")
+
+
+class _DictH5(dict):
+    """What ``h5py.File`` is to the dataset class: keys(), [key] -> array, close() (h5py is not installed in this image)."""
+
+    def close(self):
+        self.closed = True
+
+
+def _check_mmimdb_items(gold, prefix, items, ds):
+    assert [str(k) for k in items[0].keys()] == list(gold[f"{prefix}_keys"])
+    lab = torch.stack([it["label"] for it in items])
+    assert lab.dtype == torch.float32 and np.array_equal(lab.numpy(), gold[f"{prefix}_label"])
+    assert [it["sample_idx"] for it in items] == list(gold[f"{prefix}_sample_idx"])
+    assert [it["pattern_name"] for it in items] == list(gold[f"{prefix}_pattern"])
+    assert [ds._load_id(it["sample_idx"]) for it in items] == list(gold[f"{prefix}_ids"])
+    for mod in ("image", "text"):
+        assert [float(it[f"{mod}_missing_index"]) for it in items] == list(gold[f"{prefix}_{mod}_missing_index"])
+        if f"{prefix}_{mod}" not in gold.files:
+            assert ds.keys[mod] not in items[0] and f"{mod}_original" not in items[0]
+            continue
+        for suffix, key in (("", ds.keys[mod]), ("_original", f"{mod}_original"), ("_reverse", f"{mod}_reverse")):
+            got = torch.stack([it[key] for it in items])
+            assert got.dtype == torch.float32 and np.array_equal(_bits(got), gold[f"{prefix}_{mod}{suffix}"]), (prefix, mod, suffix)
+
+
+def test_mmimdb_items_and_batches(monkeypatch, tmp_path):
+    import mml_b200.datasets as D
+
+    gold = np.load(MMIMDB_GOLD)
+    raw = _DictH5({k[4:]: gold[k] for k in gold.files if k.startswith("raw_")})
+    opened = []
+    monkeypatch.setattr(D, "_open_h5", lambda path: (opened.append(str(path)), raw)[1])
+    fp = tmp_path / "val.h5"
+    fp.write_bytes(b"")
+    ds = D.MMIMDb(str(fp), "val", masks=_masks(gold, "val"), pin=False)
+    assert opened == [str(fp)] and raw.closed and len(ds) == 15 and ds.selected_patterns == ["i", "it", "t"] and ds.get_full_modality() == "it"
+    items = [ds[i] for i in range(len(ds))]
+    _check_mmimdb_items(gold, "val", items, ds)
+    mp = {"it": {"image": 0.3, "text": 0.7}, "t": {"image": 0.0, "text": 1.0}}
+    tr = D.MMIMDb(str(fp), "train", missing_patterns=mp, selected_patterns=["it", "t"], masks=_masks(gold, "train"), pin=False)
+    random.seed(8)
+    _check_mmimdb_items(gold, "train", [tr[i] for i in (1, 4, 4, 0, 2)], tr)
+    te = D.MMIMDb(str(fp), "test", "text", selected_patterns=["it"], masks=_masks(gold, "testt"), pin=False)
+    _check_mmimdb_items(gold, "testt", [te[i] for i in range(len(te))], te)
+    with pytest.raises(AssertionError, match="Labels key"):
+        D.MMIMDb(str(fp), "val", labels_key="nope")
+    with pytest.raises(FileNotFoundError):
+        D.MMIMDb(str(tmp_path / "missing.h5"), "val")
+    with pytest.raises(AssertionError):
+        D.MMIMDb(str(fp), "valid")  # this dataset's evaluation split is called "val" (data/mmimdb.py:26)
+    # batch path == item path; from_arrays == the file path
+    same = D.MMIMDb.from_arrays(gold["raw_genres"], gold["raw_vgg_features"], gold["raw_features"], None, "val", masks=_masks(gold, "val"), pin=False)
+    for dset in (ds, same):
+        got = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in b.items()} for b in dset.batches(4, rotate=1)]
+        assert [len(b["label"]) for b in got] == [4, 4, 4, 3] and sum((b["pattern_name"] for b in got), []) == [it["pattern_name"] for it in items]
+        cat = {k: torch.cat([b[k] for b in got]) for k in got[0] if k != "pattern_name"}
+        assert torch.equal(cat["label"], torch.stack([it["label"] for it in items])) and cat["label"].shape == (15, 23)
+        for mod in ("image", "text"):
+            assert np.array_equal(_bits(cat[f"{mod}_original"]), _bits(torch.stack([it[f"{mod}_original"] for it in items])))
+            masked = cat[f"{mod}_original"] * cat[f"{mod}_missing_index"].reshape(-1, 1)
+            assert np.array_equal(_bits(masked), _bits(torch.stack([it[ds.keys[mod]] for it in items])))
+
+
+def test_mmimdb_without_h5py_says_so(tmp_path):
+    import importlib.util
+
+    import mml_b200.datasets as D
+
+    import sys
+
+    if "h5py" in sys.modules or importlib.util.find_spec("h5py") is not None:
+        pytest.skip("h5py is installed (or stubbed by oracle/ref_import.py earlier in this process)")
+    fp = tmp_path / "train.h5"
+    fp.write_bytes(b"")
+    with pytest.raises(ImportError, match="h5py"):
+        D.MMIMDb(str(fp), "train")

@@ -125,6 +125,7 @@ def test_shim_registers_yaml_tags_and_swaps_reference_model():
         ref_cls = resolve_dataset_name("avmnist")
         got = shim.install(datasets=True)
         assert resolve_dataset_name("avmnist") is D.AVMNIST and resolve_dataset_name("MOSI") is D.MOSI and resolve_dataset_name("mosei") is D.MOSEI
+        assert resolve_dataset_name("mm_imdb") is D.MMIMDb and resolve_model_name("mmimdb") is not D.MMIMDb  # the MODEL of that name is resolved separately
         assert got["reference.config.resolvers.AVMNIST"] is ref_cls and ref_cls is not D.AVMNIST
         ns = ref_import.import_reference()
         M = ns.Modality
@@ -141,7 +142,7 @@ def test_shim_registers_yaml_tags_and_swaps_reference_model():
         import config.resolvers as R
         import data as RDATA
 
-        for n in ("AVMNIST", "MOSI", "MOSEI"):  # leave the reference modules as they were for the other tests
+        for n in ("AVMNIST", "MOSI", "MOSEI", "MMIMDb"):  # leave the reference modules as they were for the other tests
             setattr(R, n, got[f"reference.config.resolvers.{n}"])
             setattr(RDATA, n, got[f"reference.data.{n}"])
 
