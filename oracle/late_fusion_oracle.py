@@ -33,7 +33,7 @@ from __future__ import annotations
 import math
 from collections import OrderedDict
 from itertools import chain, combinations
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn.functional as F

@@ -27,7 +27,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .engine import BF16, BN_EPS, BN_MOMENTUM, EncoderPlan, FlatState, _StepPlan
+from .engine import BN_EPS, BN_MOMENTUM, EncoderPlan, FlatState, _StepPlan
 
 CP = 64  # padded channel count of every activation inside a ConvBlock encoder
 

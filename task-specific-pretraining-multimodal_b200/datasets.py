@@ -32,7 +32,7 @@ from __future__ import annotations
 import random
 from itertools import combinations
 from pathlib import Path
-from typing import Any, Callable, Dict, Iterator, List, Mapping, Optional, Sequence, Union
+from typing import Any, Dict, Iterator, List, Mapping, Optional, Sequence, Union
 
 import numpy as np
 import torch

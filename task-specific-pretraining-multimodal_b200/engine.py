@@ -16,14 +16,12 @@ Layout in HBM
 """
 from __future__ import annotations
 
-import math
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import MMLError
 
 BF16 = torch.bfloat16
 BN_EPS = 1e-5

@@ -17,7 +17,7 @@ bn1d(MAXOUT) -> GEMM -> bn1d(MAXOUT) -> bce_head_fwd | bce_head_bwd -> bn1d_bwd/
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Tuple
+from typing import Callable, Dict, Optional
 
 import torch
 import torch.nn as nn
