@@ -180,15 +180,23 @@ class _PatternDataset(Dataset):
         return self.missing_patterns
 
     # ---- batch-granular machinery ------------------------------------------------------------------------------------------
-    def _epoch(self, batch_size: int, shuffle: Optional[bool], drop_last: bool, pattern: Optional[str], generator, rotate: int):
+    def _epoch(self, batch_size: int, shuffle: Optional[bool], drop_last: bool, pattern: Optional[str], generator, rotate: int,
+               rank: int = 0, world: int = 1):
         """(staging set, rows int64 [B], pattern names, masks fp32 [B, n_modalities]) per batch.
 
         Order: the training split visits every sample once (shuffled unless ``shuffle=False``) with an independent uniformly drawn
         pattern per sample (the vectorised form of ``random.choice``, base_dataset.py:87-89; drawn from ``generator``, not from
         Python's ``random``); the other splits walk ``selected_patterns`` in order, all samples of one pattern after the other --
-        dataset index order, base_dataset.py:90-93 -- or only ``pattern``."""
+        dataset index order, base_dataset.py:90-93 -- or only ``pattern``.
+
+        Data parallel (``world`` > 1): the epoch's order is laid out in GLOBAL batches of ``world * batch_size`` samples and rank
+        ``r`` takes rows ``[r * batch_size, (r + 1) * batch_size)`` of each -- every rank must pass a generator in the same state (same
+        seed), as with torch's ``DistributedSampler``.  Training needs ``drop_last=True`` then (a ragged last step would leave ranks with
+        different step counts and hang the gradient all-reduce); evaluation splits the ragged tail into near-equal contiguous shards."""
         if batch_size < 1 or rotate < 1:
             raise ValueError("batch_size and rotate must be positive")
+        if world < 1 or not 0 <= rank < world:
+            raise ValueError(f"rank {rank} is not in [0, world = {world})")
         gen = generator if generator is not None else self.generator
         train = self.split == "train"
         if shuffle is None:
@@ -211,10 +219,24 @@ class _PatternDataset(Dataset):
         table_row = torch.tensor([self._pat_index[p] for p in self.selected_patterns], dtype=torch.long)
         bufs: List[Dict[str, torch.Tensor]] = [dict() for _ in range(rotate)]
         total = rows.numel()
-        stop = total - (total % batch_size) if drop_last else total
-        for n, lo in enumerate(range(0, stop, batch_size)):
-            r, p = rows[lo:lo + batch_size], pats[lo:lo + batch_size]
+        gb = batch_size * world  # one global batch
+        if world > 1 and train and not drop_last and total % gb != 0:
+            raise ValueError(f"data-parallel training over {total} samples in global batches of {gb} leaves a ragged last step: pass drop_last=True")
+        stop = total - (total % gb) if drop_last else total
+        n = 0
+        for g0 in range(0, stop, gb):
+            size = min(gb, stop - g0)
+            if size == gb:
+                lo, hi = g0 + rank * batch_size, g0 + (rank + 1) * batch_size
+            else:  # ragged tail (evaluation, or one process): near-equal contiguous shards, the first ``size % world`` ranks take one more
+                q, rem = divmod(size, world)
+                lo = g0 + rank * q + min(rank, rem)
+                hi = lo + q + (1 if rank < rem else 0)
+                if hi == lo:
+                    continue
+            r, p = rows[lo:hi], pats[lo:hi]
             yield bufs[n % rotate], r, [self.selected_patterns[k] for k in p.tolist()], self._mask_table[table_row[p], :, r]
+            n += 1
 
     def _staging(self, buf: Dict[str, torch.Tensor], key: str, shape, dtype) -> torch.Tensor:
         """View of ``shape`` on the pinned buffer ``buf[key]`` (allocated once at the largest leading dimension seen: the ragged last
@@ -435,15 +457,17 @@ class AVMNIST(_PatternDataset):
 
     # ---- batch-granular path ------------------------------------------------------------------------------------------------
     def batches(self, batch_size: int, shuffle: Optional[bool] = None, drop_last: bool = False, pattern: Optional[str] = None,
-                image_form: str = "u8", rotate: int = 4, generator: Optional[torch.Generator] = None) -> Iterator[Dict[Any, Any]]:
+                image_form: str = "u8", rotate: int = 4, generator: Optional[torch.Generator] = None, rank: int = 0,
+                world: int = 1) -> Iterator[Dict[Any, Any]]:
         """Whole batches in the fused step's input form: ``labels`` int64 [B], ``pattern_name`` list, ``sample_idx`` int64 [B],
         ``audio_original`` fp32 [B, H, W], ``image_original`` uint8 [B, 1, h, w] (``image_form="u8"``: expand on the device with
         ``DevicePrefetcher(luts={"image_original": ds.lut})``) or fp32 (``"f32"``: table lookup on the host), ``<mod>_missing_index`` fp32 [B].
         Order: ``_PatternDataset._epoch``.  A yielded batch's tensors live in one of ``rotate`` pinned staging buffer sets and stay valid
-        until ``rotate - 1`` further batches have been drawn (enough for a copy stream one batch ahead of the step)."""
+        until ``rotate - 1`` further batches have been drawn (enough for a copy stream one batch ahead of the step).  ``rank`` / ``world``:
+        this process's shard of every global batch under data parallelism (``_epoch``)."""
         if image_form not in ("u8", "f32"):
             raise ValueError("image_form must be 'u8' or 'f32'")
-        for buf, r, names, m in self._epoch(batch_size, shuffle, drop_last, pattern, generator, rotate):
+        for buf, r, names, m in self._epoch(batch_size, shuffle, drop_last, pattern, generator, rotate, rank, world):
             out: Dict[Any, Any] = {"pattern_name": names}
             out["labels"] = self._gather(buf, "labels", self.labels, r)
             out["sample_idx"] = self._gather(buf, "sample_idx", None, r)
@@ -531,10 +555,10 @@ class MultimodalSentimentDataset(_PatternDataset):
         return sample
 
     def batches(self, batch_size: int, shuffle: Optional[bool] = None, drop_last: bool = False, pattern: Optional[str] = None,
-                rotate: int = 4, generator: Optional[torch.Generator] = None) -> Iterator[Dict[Any, Any]]:
+                rotate: int = 4, generator: Optional[torch.Generator] = None, rank: int = 0, world: int = 1) -> Iterator[Dict[Any, Any]]:
         """``label`` [B], ``pattern_name``, ``sample_idx``, ``<mod>_original`` fp32 [B, T, F] + ``<mod>_missing_index`` fp32 [B] for the
         loaded modalities and, for unaligned data, ``audio_length`` / ``video_length`` [B]; order and staging as in ``AVMNIST.batches``."""
-        for buf, r, names, msk in self._epoch(batch_size, shuffle, drop_last, pattern, generator, rotate):
+        for buf, r, names, msk in self._epoch(batch_size, shuffle, drop_last, pattern, generator, rotate, rank, world):
             out: Dict[Any, Any] = {"pattern_name": names}
             out["label"] = self._gather(buf, "label", self.data["label"], r)
             out["sample_idx"] = self._gather(buf, "sample_idx", None, r)
@@ -645,10 +669,10 @@ class MMIMDb(_PatternDataset):
         return sample
 
     def batches(self, batch_size: int, shuffle: Optional[bool] = None, drop_last: bool = False, pattern: Optional[str] = None,
-                rotate: int = 4, generator: Optional[torch.Generator] = None) -> Iterator[Dict[Any, Any]]:
+                rotate: int = 4, generator: Optional[torch.Generator] = None, rank: int = 0, world: int = 1) -> Iterator[Dict[Any, Any]]:
         """``label`` fp32 [B, 23], ``pattern_name``, ``sample_idx``, ``<mod>_original`` fp32 [B, D] + ``<mod>_missing_index`` fp32 [B] for the
         loaded modalities; order and staging as in ``AVMNIST.batches``."""
-        for buf, r, names, msk in self._epoch(batch_size, shuffle, drop_last, pattern, generator, rotate):
+        for buf, r, names, msk in self._epoch(batch_size, shuffle, drop_last, pattern, generator, rotate, rank, world):
             out: Dict[Any, Any] = {"pattern_name": names}
             out["label"] = self._gather(buf, "label", self.label, r)
             out["sample_idx"] = self._gather(buf, "sample_idx", None, r)

@@ -386,3 +386,39 @@ def test_mmimdb_without_h5py_says_so(tmp_path):
     fp.write_bytes(b"")
     with pytest.raises(ImportError, match="h5py"):
         D.MMIMDb(str(fp), "train")
+
+
+def test_data_parallel_shards_partition_every_global_batch(gold, csv):
+    """rank r takes rows [r*B, (r+1)*B) of each global batch; same generator state on every rank => same epoch order."""
+    n = 23
+    g = torch.Generator().manual_seed(0)
+    ds = AVMNIST.from_arrays(torch.arange(n) % 10, torch.rand(n, 3, 4, generator=g), torch.randint(0, 256, (n, 2, 2), dtype=torch.uint8, generator=g),
+                             "train", selected_patterns=["ai", "a"], cmap=gold["table"], generator=g, pin=False)
+    B, world = 3, 2
+    one = [b["sample_idx"].tolist() for b in ds.batches(B * world, drop_last=True, generator=torch.Generator().manual_seed(7))]
+    one_p = [b["pattern_name"] for b in ds.batches(B * world, drop_last=True, generator=torch.Generator().manual_seed(7))]
+    per_rank = [[(b["sample_idx"].tolist(), b["pattern_name"], b["audio_missing_index"].tolist())
+                 for b in ds.batches(B, drop_last=True, generator=torch.Generator().manual_seed(7), rank=r, world=world)] for r in range(world)]
+    assert len(one) == 3 and all(len(x) == 3 for x in per_rank)      # 23 samples -> three global batches of 6, five dropped
+    for k in range(3):                                                 # the ranks' batches concatenate to the single-process global batch
+        assert per_rank[0][k][0] + per_rank[1][k][0] == one[k] and per_rank[0][k][1] + per_rank[1][k][1] == one_p[k]
+        for r in range(world):
+            idx, pats, masks = per_rank[r][k]
+            assert masks == [float(ds.masks[p]["audio"][i]) for i, p in zip(idx, pats)]
+    with pytest.raises(ValueError, match="drop_last"):
+        next(ds.batches(B, rank=0, world=world))
+    with pytest.raises(ValueError, match="rank"):
+        next(ds.batches(B, rank=2, world=2, drop_last=True))
+    # evaluation: nothing is dropped, the ragged tail is split into near-equal contiguous shards, dataset order is kept
+    ev = AVMNIST.from_arrays(torch.arange(n) % 10, torch.rand(n, 3, 4), torch.zeros(n, 2, 2, dtype=torch.uint8), "valid", selected_patterns=["ai"],
+                             cmap=gold["table"], pin=False)
+    for world in (2, 3, 4):
+        shards = [[b["sample_idx"].tolist() for b in ev.batches(4, rank=r, world=world)] for r in range(world)]
+        flat = sorted(i for sh in shards for b in sh for i in b)
+        assert flat == list(range(n)), world
+        nb = -(-n // (4 * world))
+        assert all(len(sh) in (nb, nb - 1) for sh in shards) and all(len(b) <= 4 for sh in shards for b in sh)
+    # a tail smaller than the world: the last ranks get nothing for it (validation has no collective, so step counts may differ)
+    tiny = AVMNIST.from_arrays(torch.arange(9) % 10, torch.rand(9, 3, 4), torch.zeros(9, 2, 2, dtype=torch.uint8), "test", selected_patterns=["ai"],
+                               cmap=gold["table"], pin=False)
+    assert [[b["sample_idx"].tolist() for b in tiny.batches(2, rank=r, world=4)] for r in range(4)] == [[[0, 1], [8]], [[2, 3]], [[4, 5]], [[6, 7]]]
