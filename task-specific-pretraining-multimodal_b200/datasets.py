@@ -7,7 +7,7 @@ Reference: ``MML_Suite/data/avmnist.py:21-277`` (class ``AVMNIST``) on top of ``
 looks the sample's masks up and multiplies (``get_samples``, base_dataset.py:61-74).  One item per Python call on a DataLoader
 worker tops out four orders of magnitude below what the fused step eats (2.4 ms per 256 samples).
 
-Here every file is read ONCE at construction into three contiguous host arrays (pinned when CUDA is there) -- audio fp32
+Here every file is read ONCE at construction into three contiguous host arrays -- audio fp32
 ``[N, H, W]``, image uint8 ``[N, h, w]`` (one byte per pixel: the whole image chain is a 256-entry table, ``data.luma_lut``),
 labels int64 ``[N]`` -- plus the mask table ``[pattern][modality][len(self)]``.  Two views of that storage:
 
@@ -324,7 +324,8 @@ class _PatternDataset(Dataset):
 
 class AVMNIST(_PatternDataset):
     """Same constructor and item / batch contract as ``data.avmnist.AVMNIST`` (data/avmnist.py:45-59), plus ``cmap`` (colour table),
-    ``masks`` (explicit mask table), ``generator`` (mask draw / batch shuffling) and ``pin`` (default: pinned iff CUDA is available)."""
+    ``masks`` (explicit mask table), ``generator`` (mask draw / batch shuffling) and ``pin`` (staging buffers of the batch path in pinned
+    memory; default: iff CUDA is available -- the dataset arrays themselves stay in ordinary host memory)."""
 
     NUM_CLASSES: int = 10
     MODS = NAMES
@@ -381,12 +382,12 @@ class AVMNIST(_PatternDataset):
 
     def _store(self, labels, audio, image_u8, cmap, masks, generator, pin) -> None:
         self._finish(labels.numel(), masks, generator, pin)
-        self.labels = _maybe_pin(labels, self._pin)
-        self.audio = _maybe_pin(audio, self._pin) if audio is not None else None
+        self.labels = labels
+        self.audio = audio
         self.image_u8 = self.lut = None
         if image_u8 is not None:
             self.lut = luma_lut(_colour_table(cmap))  # fp32 [256]: the reference's image chain as a function of the pixel value
-            self.image_u8 = _maybe_pin(image_u8, self._pin)
+            self.image_u8 = image_u8
 
     # ---- file reading (once) ------------------------------------------------------------------------------------------
     @staticmethod
@@ -534,12 +535,12 @@ class MultimodalSentimentDataset(_PatternDataset):
         label = torch.tensor(split_data[labels_key], dtype=torch.float32 if "regression" in labels_key else torch.long)
         self.original_label_size = label.size(0)
         self._finish(len(label), masks, generator, pin)
-        self.data: Dict[Any, torch.Tensor] = {"label": _maybe_pin(label, self._pin)}
+        self.data: Dict[Any, torch.Tensor] = {"label": label}
         for m in self.MODS:  # the reference converts all three whatever the target modality (data/mosi.py:137-145)
-            self.data[self.keys[m]] = _maybe_pin(torch.tensor(split_data[self.RAW_KEYS[m]]).float().contiguous(), self._pin)
+            self.data[self.keys[m]] = torch.tensor(split_data[self.RAW_KEYS[m]]).float().contiguous()
         if not aligned:
-            self.data["audio_lengths"] = _maybe_pin(torch.tensor(split_data["audio_lengths"]).float(), self._pin)
-            self.data["video_lengths"] = _maybe_pin(torch.tensor(split_data["vision_lengths"]).float(), self._pin)
+            self.data["audio_lengths"] = torch.tensor(split_data["audio_lengths"]).float()
+            self.data["video_lengths"] = torch.tensor(split_data["vision_lengths"]).float()
 
     def __getitem__(self, idx: int) -> Dict[Any, Any]:
         pattern, i = self._item_head(idx)
@@ -603,7 +604,7 @@ def _open_h5(path):
 class MMIMDb(_PatternDataset):
     """MM-IMDb features: same constructor and item contract as ``data.mmimdb.MMIMDb`` (data/mmimdb.py:14-207) -- one HDF5 file per split
     with ``vgg_features`` [N, 4096], ``features`` [N, 300], multi-hot ``genres`` [N, 23] and ``imdb_ids``.  The reference indexes the open
-    file per item; here the four datasets are read once into (pinned) arrays.  Batches feed ``mml_b200.mmimdb.MMIMDb.train_step``."""
+    file per item; here the four datasets are read once into host arrays.  Batches feed ``mml_b200.mmimdb.MMIMDb.train_step``."""
 
     VALID_SPLITS: List[str] = ["train", "val", "test"]
     NUM_CLASSES: int = 23
@@ -651,8 +652,8 @@ class MMIMDb(_PatternDataset):
         img, txt = torch.as_tensor(np.asarray(image)).float().contiguous(), torch.as_tensor(np.asarray(text)).float().contiguous()
         if img.shape[0] != self.num_samples or txt.shape[0] != self.num_samples:
             raise ValueError(f"labels / image / text disagree on the number of samples: {lab.shape[0]} / {img.shape[0]} / {txt.shape[0]}")
-        self.label = _maybe_pin(lab, self._pin)
-        self.data = {"image": _maybe_pin(img, self._pin), "text": _maybe_pin(txt, self._pin)}
+        self.label = lab
+        self.data = {"image": img, "text": txt}
         self.imdb_ids = list(ids) if ids is not None else [str(i) for i in range(self.num_samples)]
 
     def _load_id(self, idx: int) -> str:
