@@ -27,7 +27,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 from ref_import import import_reference  # noqa: E402
 
-GOLDEN_DIR = os.path.join(os.path.dirname(HERE), "tests", "golden")
+GOLDEN_DIR = os.environ.get("MML_GOLDEN_DIR") or os.path.join(os.path.dirname(HERE), "tests", "golden")  # the override is for the regeneration test
 N, AUDIO_HW, IMAGE_HW = 5, (6, 9), (12, 10)
 
 

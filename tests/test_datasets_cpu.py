@@ -422,3 +422,25 @@ def test_data_parallel_shards_partition_every_global_batch(gold, csv):
     tiny = AVMNIST.from_arrays(torch.arange(9) % 10, torch.rand(9, 3, 4), torch.zeros(9, 2, 2, dtype=torch.uint8), "test", selected_patterns=["ai"],
                                cmap=gold["table"], pin=False)
     assert [[b["sample_idx"].tolist() for b in tiny.batches(2, rank=r, world=4)] for r in range(4)] == [[[0, 1], [8]], [[2, 3]], [[4, 5]], [[6, 7]]]
+
+
+def test_loader_fixtures_regenerate_from_the_reference(tmp_path):
+    """Build container only (the reference is not on the GPU box): ``oracle/make_golden_loader.py`` run afresh over the unmodified reference
+    classes writes exactly the three committed ``*_loader.npz`` fixtures."""
+    import subprocess
+    import sys
+
+    import ref_import
+
+    if not ref_import.reference_available():
+        pytest.skip("reference not mounted")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MML_GOLDEN_DIR=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(root, "oracle", "make_golden_loader.py")], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
+    for name in ("avmnist_loader.npz", "mosi_loader.npz", "mmimdb_loader.npz"):
+        new, old = np.load(str(tmp_path / name)), np.load(os.path.join(root, "tests", "golden", name))
+        assert sorted(new.files) == sorted(old.files), name
+        for k in old.files:
+            assert new[k].dtype == old[k].dtype and np.array_equal(new[k], old[k]), (name, k)
