@@ -4,7 +4,7 @@ Semantics: every rank holds the full fp32 weights + Adam 
 batch, keeps PER-REPLICA BatchNorm statistics (the reference is single-device; there is no SyncBN to match), and the
 gradients are summed over ranks and divided by the world size inside the Adam kernel (``hyper[5] = 1/world``).
 
-The flat gradient buffer ``G`` is reduced in two contiguous buckets, ordered so that communication hides under compute:
+The flat gradient buffer ``G`` is reduced in contiguous ranges (two buckets, each split once more by the step plan), ordered so that communication hides under compute:
 the image encoder has 2/3 of the parameters but few FLOPs, so its backward runs FIRST and bucket 0 (image encoder +
 head, ~85 MB) is all-reduced on a side stream while the audio encoder's backward (87 % of the FLOPs) is still running;
 the audio encoder follows in two ranges: layer3..fc (94 % of its parameters, ~42 MB) as soon as layer3's backward is
