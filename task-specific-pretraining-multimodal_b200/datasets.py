@@ -1,6 +1,6 @@
-"""The AVMNIST dataset of the reference, laid out for a step that consumes 100 k samples/s.
+"""The reference's dataset classes (AVMNIST, MMIMDb, MOSI / MOSEI), laid out for fused steps that consume 100 k samples/s.
 
-Reference: ``MML_Suite/data/avmnist.py:21-277`` (class ``AVMNIST``) on top of ``MultimodalBaseDataset``
+AVMNIST first.  Reference: ``MML_Suite/data/avmnist.py:21-277`` (class ``AVMNIST``) on top of ``MultimodalBaseDataset``
 (``data/base_dataset.py:16-154``) and ``PatternSpecificDataset`` (``data/pattern.py:6-19``): a CSV of
 ``audio`` / ``image`` / ``label`` columns whose cells are paths of ``torch.save``-d items; ``__getitem__`` loads both files
 (lru-cached), runs the image through ``uint8 -> cm.gist_earth -> PIL "L" -> PILToTensor -> ToDtype(float32, scale=True)``,
