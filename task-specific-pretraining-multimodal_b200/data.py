@@ -70,6 +70,38 @@ def draw_missing_masks(patterns: "Mapping[str, Mapping[str, float]]", num_sample
     return masks
 
 
+def _philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
+    """Philox4x32-10 (Salmon et al., SC'11) on uint64 numpy arrays holding 32-bit words; returns the four output words."""
+    m0, m1, lo = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    sh = np.uint64(32)
+    for r in range(10):
+        ka, kb = np.uint64((k0 + r * 0x9E3779B9) & 0xFFFFFFFF), np.uint64((k1 + r * 0xBB67AE85) & 0xFFFFFFFF)
+        a, b = m0 * c0, m1 * c2  # 32 x 32 -> 64 bit products
+        c0, c1, c2, c3 = (b >> sh) ^ c1 ^ ka, b & lo, (a >> sh) ^ c3 ^ kb, a & lo
+    return c0, c1, c2, c3
+
+
+def philox_missing_masks(patterns: "Mapping[str, Mapping[str, float]]", num_samples: int, seed: int,
+                         first_sample: int = 0) -> Dict[str, Dict[str, torch.Tensor]]:
+    """The table ``DeviceMaskTable(patterns, num_samples, seed, device)`` draws on the GPU (``mml_missing_mask_draw``), computed on the host:
+    pattern k, modality m, sample i is present iff the 24-bit uniform from word ``i % 4`` of the Philox block with counter
+    ``(lo32(i // 4), hi32(i // 4), m, k)`` and key ``(lo32(seed), hi32(seed))`` is below P(present).  A pure function of its arguments, so
+    the host datasets, every data-parallel rank and the device table agree bit for bit (``first_sample``: a shard of the sample range)."""
+    i = np.arange(first_sample, first_sample + int(num_samples), dtype=np.uint64)
+    q, word = i >> np.uint64(2), (i & np.uint64(3)).astype(np.int64)
+    c0, c1 = q & np.uint64(0xFFFFFFFF), q >> np.uint64(32)
+    k0, k1 = int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF
+    out: Dict[str, Dict[str, torch.Tensor]] = {}
+    for k, (pat, probs) in enumerate(patterns.items()):
+        out[pat] = {}
+        for m, (mod, p) in enumerate(probs.items()):
+            words = np.stack(_philox4x32_10(c0, c1, np.full_like(q, m), np.full_like(q, k), k0, k1))  # [4, n]
+            bits = words[word, np.arange(i.size)]
+            u = (bits >> np.uint64(8)).astype(np.float32) * np.float32(2.0 ** -24)
+            out[pat][mod] = torch.from_numpy((u < np.float32(p)).astype(np.float32))
+    return out
+
+
 def attach_masks(batch: Dict[Any, Any], masks: Mapping[str, torch.Tensor], modalities: Sequence[str]) -> Dict[Any, Any]:
     """Turn a batch of ORIGINAL tensors into the ``<mod>_original`` + ``<mod>_missing_index`` form the fused step consumes."""
     out = dict(batch)

@@ -38,7 +38,7 @@ import numpy as np
 import torch
 from torch.utils.data import Dataset
 
-from .data import draw_missing_masks, luma_lut
+from .data import draw_missing_masks, luma_lut, philox_missing_masks
 
 NAMES = ("audio", "image")
 
@@ -128,8 +128,10 @@ class _PatternDataset(Dataset):
     def _loads(self, m: str) -> bool:
         return self._target in ("multimodal", m)
 
-    def _finish(self, num_samples: int, masks, generator, pin) -> None:
-        """Mask table (given or drawn) once ``num_samples`` is known."""
+    def _finish(self, num_samples: int, masks, generator, pin, mask_seed: Optional[int] = None) -> None:
+        """Mask table (given, or drawn -- from ``generator`` with torch.bernoulli, or from ``mask_seed`` with the counter-based Philox draw
+        that ``data.DeviceMaskTable`` performs on the GPU: same table on the host, on the device and on every rank) once ``num_samples``
+        is known."""
         self.num_samples = int(num_samples)
         self.pattern_indices = {pattern: list(range(self.num_samples)) for pattern in self.selected_patterns}
         self._pin = torch.cuda.is_available() if pin is None else bool(pin)
@@ -139,6 +141,8 @@ class _PatternDataset(Dataset):
                 for m in self.MODS:
                     if pat not in self.masks or m not in self.masks[pat] or self.masks[pat][m].numel() < self.num_samples:
                         raise ValueError(f"masks[{pat!r}][{m!r}] must hold at least {self.num_samples} entries")
+        elif mask_seed is not None:
+            self.masks = philox_missing_masks(self.missing_patterns, len(self), int(mask_seed))
         else:
             # one draw per (pattern, modality, dataset index) at construction, length len(self) like base_dataset.py:46-59
             self.masks = draw_missing_masks(self.missing_patterns, len(self), generator)
@@ -338,7 +342,7 @@ class AVMNIST(_PatternDataset):
                  audio_column: str = "audio", image_column: str = "image", labels_column: str = "label",
                  split_indices: Optional[Sequence[int]] = None, _id: int = 1, cmap: Any = None,
                  masks: Optional[Mapping[str, Mapping[Any, torch.Tensor]]] = None, generator: Optional[torch.Generator] = None,
-                 pin: Optional[bool] = None) -> None:
+                 pin: Optional[bool] = None, mask_seed: Optional[int] = None) -> None:
         import pandas as pd
 
         self._configure(split, target_modality, missing_patterns, selected_patterns, _id)
@@ -355,12 +359,12 @@ class AVMNIST(_PatternDataset):
         labels = torch.from_numpy(np.array(self.data[labels_column].to_numpy(), dtype=np.int64))
         audio = self._read_audio(self.data[audio_column]) if self._loads("audio") else None
         image = self._read_images(self.data[image_column]) if self._loads("image") else None
-        self._store(labels, audio, image, cmap, masks, generator, pin)
+        self._store(labels, audio, image, cmap, masks, generator, pin, mask_seed)
 
     @classmethod
     def from_arrays(cls, labels, audio=None, image_u8=None, split: str = "train", target_modality: Any = "multimodal", *,
                     missing_patterns=None, selected_patterns=None, _id: int = 1, cmap: Any = None, masks=None,
-                    generator: Optional[torch.Generator] = None, pin: Optional[bool] = None) -> "AVMNIST":
+                    generator: Optional[torch.Generator] = None, pin: Optional[bool] = None, mask_seed: Optional[int] = None) -> "AVMNIST":
         """The same dataset over arrays that are already in memory (``audio`` fp32 [N, H, W], ``image_u8`` uint8 [N, h, w], ``labels``
         [N]) instead of a CSV of per-item files; ``None`` for a modality that the target does not load."""
         self = cls.__new__(cls)
@@ -377,11 +381,11 @@ class AVMNIST(_PatternDataset):
             if i.dtype != torch.uint8 or i.dim() != 3 or i.shape[0] != labels.numel():
                 raise TypeError(f"image_u8 must be uint8 [N, h, w] with N = {labels.numel()}, got {i.dtype} {tuple(i.shape)}")
             i = i.contiguous()
-        self._store(labels, a, i, cmap, masks, generator, pin)
+        self._store(labels, a, i, cmap, masks, generator, pin, mask_seed)
         return self
 
-    def _store(self, labels, audio, image_u8, cmap, masks, generator, pin) -> None:
-        self._finish(labels.numel(), masks, generator, pin)
+    def _store(self, labels, audio, image_u8, cmap, masks, generator, pin, mask_seed=None) -> None:
+        self._finish(labels.numel(), masks, generator, pin, mask_seed)
         self.labels = labels
         self.audio = audio
         self.image_u8 = self.lut = None
@@ -512,7 +516,7 @@ class MultimodalSentimentDataset(_PatternDataset):
                  missing_patterns: Optional[Mapping[str, Mapping[Any, float]]] = None, selected_patterns: Optional[Sequence[str]] = None,
                  labels_key: str = "classification_labels", aligned: bool = False, length: Optional[int] = None,
                  num_classes: Optional[int] = None, batch_size: int = 1, masks=None, generator: Optional[torch.Generator] = None,
-                 pin: Optional[bool] = None) -> None:
+                 pin: Optional[bool] = None, mask_seed: Optional[int] = None) -> None:
         import pickle
 
         if num_classes is not None:
@@ -534,7 +538,7 @@ class MultimodalSentimentDataset(_PatternDataset):
             raise KeyError(f"Labels key '{labels_key}' not found in data")
         label = torch.tensor(split_data[labels_key], dtype=torch.float32 if "regression" in labels_key else torch.long)
         self.original_label_size = label.size(0)
-        self._finish(len(label), masks, generator, pin)
+        self._finish(len(label), masks, generator, pin, mask_seed)
         self.data: Dict[Any, torch.Tensor] = {"label": label}
         for m in self.MODS:  # the reference converts all three whatever the target modality (data/mosi.py:137-145)
             self.data[self.keys[m]] = torch.tensor(split_data[self.RAW_KEYS[m]]).float().contiguous()
@@ -617,7 +621,7 @@ class MMIMDb(_PatternDataset):
                  missing_patterns: Optional[Mapping[str, Mapping[Any, float]]] = None, selected_patterns: Optional[Sequence[str]] = None,
                  image_key: str = "vgg_features", text_key: str = "features", labels_key: str = "genres", imdb_ids_key: str = "imdb_ids",
                  split_indices: Optional[Sequence[int]] = None, _id: int = 1, masks=None, generator: Optional[torch.Generator] = None,
-                 pin: Optional[bool] = None) -> None:
+                 pin: Optional[bool] = None, mask_seed: Optional[int] = None) -> None:
         self._configure(split, target_modality, missing_patterns, selected_patterns, _id)
         data_fp = Path(data_fp)
         if not data_fp.exists():
@@ -630,7 +634,7 @@ class MMIMDb(_PatternDataset):
             assert text_key in keys, f"Text key {text_key} not found in the dataset"
             assert labels_key in keys, f"Labels key {labels_key} not found in the dataset"
             ids = [x.decode("utf-8") if isinstance(x, bytes) else str(x) for x in np.asarray(f[imdb_ids_key][...]).tolist()]
-            self._store(np.asarray(f[labels_key][...]), np.asarray(f[image_key][...]), np.asarray(f[text_key][...]), ids, masks, generator, pin)
+            self._store(np.asarray(f[labels_key][...]), np.asarray(f[image_key][...]), np.asarray(f[text_key][...]), ids, masks, generator, pin, mask_seed)
         finally:
             close = getattr(f, "close", None)
             if close is not None:
@@ -639,16 +643,16 @@ class MMIMDb(_PatternDataset):
     @classmethod
     def from_arrays(cls, labels, image, text, imdb_ids: Optional[Sequence[str]] = None, split: str = "train", target_modality: Any = "multimodal", *,
                     missing_patterns=None, selected_patterns=None, _id: int = 1, masks=None, generator: Optional[torch.Generator] = None,
-                    pin: Optional[bool] = None) -> "MMIMDb":
+                    pin: Optional[bool] = None, mask_seed: Optional[int] = None) -> "MMIMDb":
         """The same dataset over arrays in memory: ``labels`` [N, 23], ``image`` [N, 4096], ``text`` [N, 300] (any float / integer dtype)."""
         self = cls.__new__(cls)
         self._configure(split, target_modality, missing_patterns, selected_patterns, _id)
-        self._store(labels, image, text, imdb_ids, masks, generator, pin)
+        self._store(labels, image, text, imdb_ids, masks, generator, pin, mask_seed)
         return self
 
-    def _store(self, labels, image, text, ids, masks, generator, pin) -> None:
+    def _store(self, labels, image, text, ids, masks, generator, pin, mask_seed=None) -> None:
         lab = torch.as_tensor(np.asarray(labels)).float().contiguous()  # ``torch.as_tensor(...).float()`` per item in the reference (:125-155)
-        self._finish(lab.shape[0], masks, generator, pin)
+        self._finish(lab.shape[0], masks, generator, pin, mask_seed)
         img, txt = torch.as_tensor(np.asarray(image)).float().contiguous(), torch.as_tensor(np.asarray(text)).float().contiguous()
         if img.shape[0] != self.num_samples or txt.shape[0] != self.num_samples:
             raise ValueError(f"labels / image / text disagree on the number of samples: {lab.shape[0]} / {img.shape[0]} / {txt.shape[0]}")

@@ -79,3 +79,35 @@ def test_luma_lut_rejects_bad_tables():
         luma_lut(np.zeros((255, 3)))
     with pytest.raises(ValueError):
         luma_lut(np.zeros((256, 3)), scale="x")
+
+
+def test_host_philox_table_equals_the_oracle_draw_and_feeds_the_datasets():
+    """``data.philox_missing_masks`` (product, host) against ``staging_oracle.draw_masks`` (which tests/test_staging_gpu.py holds the GPU
+    kernel to, bit for bit): host datasets, data-parallel ranks and ``DeviceMaskTable`` share one mask table per seed."""
+    from mml_b200.data import generate_patterns, philox_missing_masks
+    from mml_b200.datasets import AVMNIST
+
+    pats = generate_patterns({"audio": (0.2, None), "image": (0.4, ["i"])})
+    seed = 0xFEDC_BA98_7654_3210
+    tab = philox_missing_masks(pats, 5003, seed)
+    assert list(tab) == list(pats)
+    for k, (pat, probs) in enumerate(pats.items()):
+        want = S.draw_masks(list(probs.values()), 5003, seed, k)
+        for j, m in enumerate(probs):
+            assert tab[pat][m].dtype == torch.float32 and np.array_equal(tab[pat][m].numpy().view(np.uint32), want[j].view(np.uint32)), (pat, m)
+    # a shard of the sample range reproduces the slice (unaligned offsets, offsets beyond 2^32 blocks)
+    for first, n in ((3, 1), (1001, 2002), (2 ** 34 + 1, 7)):
+        part = philox_missing_masks(pats, n, seed, first_sample=first)
+        want = S.draw_masks(list(pats["ai"].values()), n, seed, list(pats).index("ai"), first_sample=first)
+        assert np.array_equal(part["ai"]["audio"].numpy(), want[0]) and np.array_equal(part["ai"]["image"].numpy(), want[1])
+    assert philox_missing_masks(pats, 0, seed)["ai"]["audio"].shape == (0,)
+    # datasets: mask_seed => the same table in every process, whatever the torch / Python RNG state
+    n = 37
+    mk = lambda: AVMNIST.from_arrays(torch.arange(n) % 10, torch.rand(n, 2, 3), torch.zeros(n, 2, 2, dtype=torch.uint8), "train", missing_patterns=pats,
+                                     selected_patterns=["ai", "i"], cmap=np.zeros((256, 3)), pin=False, mask_seed=99)
+    a, b = mk(), mk()
+    full = philox_missing_masks(pats, n, 99)
+    for pat in pats:
+        for m in ("audio", "image"):
+            assert torch.equal(a.masks[pat][m], b.masks[pat][m]) and torch.equal(a.masks[pat][m], full[pat][m])
+    assert 0.6 < float(a.masks["ai"]["audio"].mean()) <= 1.0 and not a.masks["i"]["audio"].any()
