@@ -83,3 +83,17 @@ def test_prefetcher_expands_uint8_images_on_the_device():
         n += 1
     assert n == 5
     assert pf.h2d_bytes == 5 * (32 * 28 * 28 + 32 * 8)  # one byte per pixel crosses PCIe
+
+
+def test_device_mask_table_equals_the_host_philox_table():
+    """One mask table per seed: what ``DeviceMaskTable`` draws on the GPU == what ``data.philox_missing_masks`` computes on the host (the
+    table ``datasets.*(mask_seed=...)`` uses), both == oracle/staging_oracle.py."""
+    from mml_b200.data import DeviceMaskTable, generate_patterns, philox_missing_masks
+
+    pats = generate_patterns({"audio": (0.2, None), "image": (0.4, ["i"])})
+    tab = DeviceMaskTable(pats, 5000, seed=11, device="cuda")
+    host = philox_missing_masks(pats, 5000, 11)
+    for pat, probs in pats.items():
+        dev = tab.masks[pat].cpu()
+        for j, m in enumerate(probs):
+            assert torch.equal(dev[j], host[pat][m]), (pat, m)
